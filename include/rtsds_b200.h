@@ -1,0 +1,239 @@
+/*
+ * rtsds_b200.h — C ABI of librtsds_b200.so (hand-written sm_100a kernels).
+ *
+ * The reference (sina-behnam/RTSDS) has no FFI of its own: its hot path is
+ * the Python nn.Module API.  This header is the boundary the
+ * drop-in modules under models/ and utils.fast_hist bind through ctypes
+ * (rtsds_b200/_lib.py).  Every entry point
+ *   - takes plain device pointers, sizes and a cudaStream_t (as void*),
+ *   - is asynchronous on that stream, never allocates, never synchronises,
+ *     and is CUDA-graph capturable,
+ *   - returns 0 on success or a negative RTSDS_E* code; the message is
+ *     available from rtsds_last_error_string() (thread-local),
+ *   - has NO CPU fallback: a non-sm_100 device is RTSDS_EARCH.
+ *
+ * Activation layout inside the path is NHWC (channels innermost), bf16 in
+ * the production mode and fp32 in the "fp32 check" mode (BASELINE.json
+ * tolerance 1e-4).  API-boundary tensors (input image, returned logits,
+ * labels) keep the reference's NCHW fp32 / int64 layout.
+ *
+ * Reference file:line citations are relative to /root/reference.
+ */
+#ifndef RTSDS_B200_H
+#define RTSDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTSDS_ABI_VERSION 1
+
+/* error codes */
+#define RTSDS_OK        0
+#define RTSDS_EINVAL   -1   /* bad shape / argument */
+#define RTSDS_EARCH    -2   /* device is not sm_100 */
+#define RTSDS_ECUDA    -3   /* CUDA runtime / launch error */
+#define RTSDS_EUNSUP   -4   /* configuration not supported by this kernel */
+#define RTSDS_EWS      -5   /* workspace too small */
+
+/* element types of activation buffers */
+#define RTSDS_F32   0
+#define RTSDS_BF16  1
+
+/* activations fused into conv epilogues */
+#define RTSDS_ACT_NONE   0
+#define RTSDS_ACT_RELU   1
+#define RTSDS_ACT_LRELU  2   /* LeakyReLU(slope) — models/domain_shift/adversarial/model.py:50 */
+
+typedef void* rtsds_stream_t;   /* cudaStream_t */
+
+int         rtsds_abi_version(void);
+const char* rtsds_last_error_string(void);
+/* RTSDS_OK if the current device is compute capability 10.x, else RTSDS_EARCH. */
+int         rtsds_check_device(void);
+/* number of kernel launches issued by this library since load (all threads). */
+int64_t     rtsds_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Metric: utils.fast_hist (utils.py:52-58)
+ *   k = (a >= 0) & (a < n); bincount(n*a[k] + b[k], minlength=n*n)
+ * hist (int64 [n_cls*n_cls], row = label, col = prediction) is ACCUMULATED
+ * into (caller zeroes it), which is what validation.py:55 does with
+ * total_hist.  Predictions must lie in [0, n_cls) for kept pixels, as they do
+ * for an argmax over n_cls channels; out-of-range predictions are counted in
+ * *n_bad (int64, may be NULL) instead of corrupting a neighbouring bin.
+ * Bit-exact integer arithmetic.
+ * ---------------------------------------------------------------------- */
+int rtsds_confusion_hist(const int64_t* label, const int64_t* pred, int64_t n_pix,
+                         int n_cls, int64_t* hist, int64_t* n_bad, rtsds_stream_t s);
+
+/* Fused torch.argmax(logits, 1) (validation.py:51) + fast_hist.
+ * logits: fp32 NCHW [n, n_cls, hw]; label int64 [n, hw];
+ * pred_out: optional int64 [n, hw] (argmax, first max on ties);
+ * hist accumulated as above. */
+int rtsds_argmax_hist(const float* logits, const int64_t* label, int n, int n_cls,
+                      int64_t hw, int64_t* pred_out, int64_t* hist, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * Convolution (nn.Conv2d as used by models/bisenet/build_bisenet.py:11-12,
+ * torchvision BasicBlock, models/deeplabv2/deeplabv2.py:13-24,59-61,
+ * models/domain_shift/adversarial/model.py:45-49).
+ *
+ * y[n,oh,ow,co] = act( scale[co] * (sum_{r,s,ci} x[n, oh*stride-pad+r*dil,
+ *                 ow*stride-pad+s*dil, ci] * w[co,r,s,ci]) + shift[co]
+ *                 + residual[n,oh,ow,co] )
+ * x: NHWC, pixel pitch in_ld elements (>= cin: views into concat buffers);
+ * y / residual: NHWC, pixel pitch out_ld / res_ld.
+ * w: packed [cout_pad][kh*kw][cin] (rtsds_pack_conv_weight), dtype = x dtype.
+ * scale/shift: fp32 [cout] or NULL (1 / 0) — folded eval BatchNorm or bias.
+ * stats: fp32 [2*cout] or NULL; when given, per-channel sum and sum of
+ *        squares of the RAW convolution result (before scale/shift) are
+ *        atomically accumulated: train-mode BatchNorm statistics.
+ * ---------------------------------------------------------------------- */
+typedef struct RtsdsConvDesc {
+    int n, h, w, cin, in_ld;
+    int cout, out_ld, res_ld;
+    int kh, kw, stride, pad, dil;
+    int oh, ow;
+    int act;
+    float slope;
+    int in_dtype;      /* RTSDS_BF16 (tensor-core path) or RTSDS_F32 (check path) */
+    int out_dtype;     /* RTSDS_BF16 or RTSDS_F32 */
+    int split_k;       /* >1: split the reduction over this many CTAs (tensor-core path) */
+} RtsdsConvDesc;
+
+/* tcgen05/TMEM implicit GEMM fed by TMA; x, w bf16; cin % 64 == 0.
+ * workspace: fp32 [n*oh*ow*cout_pad32] zero-filled by the call when split_k>1. */
+int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w,
+                        const float* scale, const float* shift, const void* residual,
+                        float* stats, void* y, void* workspace, size_t ws_bytes,
+                        rtsds_stream_t s);
+size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d);
+/* output-channel padding of the packed weight layout (32, 64 or a multiple of 128). */
+int rtsds_conv_cout_pad(int cout);
+/* process-wide tuning override for experiments: block_n in {0=auto,32,64,128}, stages (0=auto). */
+void rtsds_conv2d_tc_tune(int block_n, int stages);
+
+/* CUDA-core implicit GEMM with fp32 accumulation; any cin; x/w dtype per
+ * d->in_dtype.  This is the fp32 check mode (and a bf16 cross-check). */
+int rtsds_conv2d_simt_fwd(const RtsdsConvDesc* d, const void* x, const void* w,
+                          const float* scale, const float* shift, const void* residual,
+                          float* stats, void* y, rtsds_stream_t s);
+
+/* OIHW fp32 (nn.Conv2d.weight) -> [cout_pad][kh*kw][cin] of dtype; rows
+ * cout..cout_pad-1 are zero. */
+int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw,
+                           int cout_pad, int dtype, void* w_packed, rtsds_stream_t s);
+
+/* Stem convolutions read the API-boundary image directly:
+ * x fp32 NCHW [n,cin,h,w] (cin <= 32), w fp32 OIHW, y NHWC of out_dtype,
+ * with scale/shift/act/stats as above.  softmax_in != 0 applies a softmax
+ * over the cin channels of x while loading (train.py:225 F.softmax feeding
+ * the discriminator's conv1). */
+int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, int cin, int h, int w,
+                        int cout, int k, int stride, int pad,
+                        const float* scale, const float* shift, int act, float slope,
+                        int softmax_in, float* stats, int out_dtype, void* y,
+                        rtsds_stream_t s);
+
+/* nn.MaxPool2d(3, 2, 1[, ceil_mode]) on NHWC. */
+int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype,
+                           int ceil_mode, void* y, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * BatchNorm helpers (nn.BatchNorm2d, eps/momentum per build_bisenet.py:135-137)
+ * ---------------------------------------------------------------------- */
+/* eval: scale = gamma / sqrt(var+eps); shift = beta - mean*scale (+ scale*conv_bias). */
+int rtsds_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                  const float* conv_bias, float eps, int c, float* scale, float* shift,
+                  rtsds_stream_t s);
+/* train: from stats = [sum(c), sumsq(c)] over count samples produce
+ * scale/shift (biased variance) and update running_mean/var (unbiased,
+ * momentum) in place; save_mean/save_invstd (fp32 [c]) kept for backward. */
+int rtsds_bn_finalize(const float* stats, double count, const float* gamma, const float* beta,
+                      float eps, float momentum, int c, float* running_mean, float* running_var,
+                      float* scale, float* shift, float* save_mean, float* save_invstd,
+                      rtsds_stream_t s);
+/* y = act(scale[c]*x + shift[c] + residual) elementwise over NHWC. */
+int rtsds_scale_shift_act(const void* x, const float* scale, const float* shift,
+                          const void* residual, int64_t n_pix, int c, int x_ld, int res_ld,
+                          int y_ld, int act, float slope, int x_dtype, int y_dtype, void* y,
+                          rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * BiSeNet glue (models/bisenet/build_bisenet.py)
+ * ---------------------------------------------------------------------- */
+/* Global average pool over H*W per (n, c): AdaptiveAvgPool2d(1) (:42,:46,:75)
+ * and the context-path tail (build_contextpath.py:27-28).  out fp32 [n, c]. */
+int rtsds_global_avgpool(const void* x, int n, int64_t hw, int c, int ld, int dtype,
+                         float* out, rtsds_stream_t s);
+
+/* AttentionRefinementModule gate (:45-49): g = sigmoid(BN(W p + b)), p = pooled [n,c].
+ * w fp32 [c,c] (conv 1x1 weight), b fp32 [c].  train==0: BN folded from
+ * running stats (gamma,beta,mean,var); train!=0: batch statistics over n
+ * (biased var) and running stats updated in place (n must be >= 2, as in
+ * torch).  mul (fp32 [n,c], may be NULL) is multiplied into the gate: the
+ * `cx2 * tail` of :149. gate out fp32 [n,c].  Optional fp32 [n,c] outputs
+ * lin_out (W p + b) and xhat_out (normalised) are kept for backward. */
+int rtsds_arm_gate(const float* pooled, const float* w, const float* b, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, float eps,
+                   float momentum, int train, int n, int c, const float* mul, float* gate,
+                   float* lin_out, float* xhat_out, rtsds_stream_t s);
+
+/* Bilinear resize (F.interpolate(mode='bilinear', align_corners=False), :151-152)
+ * of src NHWC [n,h,w,c] scaled by gate[n,c] (NULL = 1) into dst NHWC
+ * [n,oh,ow,dst_ld] at channel offset dst_coff: writes straight into the
+ * torch.cat buffer of :153/:72. */
+int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int c, int src_ld,
+                           const float* gate, int oh, int ow, void* dst, int dst_ld,
+                           int dst_coff, int dtype, rtsds_stream_t s);
+
+/* FeatureFusionModule attention (:75-80) + final 1x1 conv (:167), evaluated at
+ * feature resolution (the 1x1 conv commutes with the bilinear resize):
+ *   a = sigmoid(W2 relu(W1 mean(f) + b1) + b2);   g = f*a + f;
+ *   z = Wc g + bc   (Wc NULL: z = g, the with_interpolation=False result)
+ * f: NHWC [n,hw,f_ld] (first c channels valid), pooled = mean(f) fp32 [n,c].
+ * z: fp32 NHWC [n,hw,z_ld].  c <= 32. */
+int rtsds_ffm_head(const void* f, int f_dtype, int f_ld, const float* pooled, int n, int64_t hw,
+                   int c, const float* w1, const float* b1, const float* w2, const float* b2,
+                   const float* wc, const float* bc, float* attn_out, float* z, int z_ld,
+                   rtsds_stream_t s);
+
+/* Bilinear resize of z fp32 NHWC [n,h,w,z_ld] (c valid channels) to the
+ * API-boundary logits fp32 NCHW [n,c,oh,ow] (:158-159,:166; deeplabv2.py:126). */
+int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow,
+                         float* out, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * Loss: bilinear resize + nn.CrossEntropyLoss(ignore_index) (main.py:124-130,
+ * train.py:86-92) + argmax / pixel accuracy (train.py:102-106) in one pass
+ * over the low-resolution logits z; the full-resolution logits are never
+ * materialised.
+ *   acc (double [4]): += { sum of -log softmax[target] over valid pixels,
+ *                          number of valid pixels,
+ *                          number of pixels with argmax == target,
+ *                          0 }
+ *   pred_out: optional int64 [n,oh,ow] argmax.
+ * Backward: dz[n,h,w,c] = sum over output pixels of bilinear weight *
+ *   (softmax - onehot) * grad_scale  (grad_scale = upstream/valid_count,
+ *   read from device memory: fp32 scalar). dz must be zero-filled by caller.
+ * ---------------------------------------------------------------------- */
+int rtsds_resize_ce_argmax_fwd(const float* z, int n, int h, int w, int c, int z_ld, int oh,
+                               int ow, const int64_t* target, int64_t ignore_index,
+                               double* acc, int64_t* pred_out, rtsds_stream_t s);
+int rtsds_resize_ce_bwd(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow,
+                        const int64_t* target, int64_t ignore_index, const float* grad_scale,
+                        float* dz, rtsds_stream_t s);
+
+/* CrossEntropyLoss + argmax on materialised NCHW logits (stock call sites). */
+int rtsds_ce_argmax_nchw_fwd(const float* logits, int n, int c, int64_t hw,
+                             const int64_t* target, int64_t ignore_index, double* acc,
+                             int64_t* pred_out, rtsds_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTSDS_B200_H */

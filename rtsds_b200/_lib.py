@@ -1,0 +1,107 @@
+"""ctypes binding of librtsds_b200.so (include/rtsds_b200.h).
+
+The library is the ONLY compute path: if it is missing or fails to load the
+import raises — there is no CPU / eager-PyTorch fallback (BASELINE.json
+north_star).  `build()` compiles it in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "librtsds_b200.so"
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    """RtsdsConvDesc (include/rtsds_b200.h)."""
+
+    _fields_ = [
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("in_ld", C.c_int),
+        ("cout", C.c_int), ("out_ld", C.c_int), ("res_ld", C.c_int),
+        ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("oh", C.c_int), ("ow", C.c_int),
+        ("act", C.c_int), ("slope", C.c_float),
+        ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("split_k", C.c_int),
+    ]
+
+
+_P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+_CD = C.POINTER(ConvDesc)
+
+# name -> (restype, argtypes); must list every function include/rtsds_b200.h declares
+SIGNATURES = {
+    "rtsds_abi_version": (_I, []),
+    "rtsds_last_error_string": (C.c_char_p, []),
+    "rtsds_check_device": (_I, []),
+    "rtsds_launch_count": (_L, []),
+    "rtsds_confusion_hist": (_I, [_P, _P, _L, _I, _P, _P, _P]),
+    "rtsds_argmax_hist": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
+    "rtsds_conv_cout_pad": (_I, [_I]),
+    "rtsds_conv2d_tc_tune": (None, [_I, _I]),
+    "rtsds_conv2d_tc_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "rtsds_conv2d_tc_workspace_bytes": (_Z, [_CD]),
+    "rtsds_conv2d_simt_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rtsds_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_stem_conv_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P, _I, _P, _P]),
+    "rtsds_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _I, _P, _P, _P]),
+    "rtsds_bn_finalize": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "rtsds_scale_shift_act": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
+    "rtsds_global_avgpool": (_I, [_P, _I, _L, _I, _I, _I, _P, _P]),
+    "rtsds_arm_gate": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "rtsds_gate_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),
+    "rtsds_ffm_head": (_I, [_P, _I, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "rtsds_resize_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_resize_ce_argmax_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
+    "rtsds_resize_ce_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
+    "rtsds_ce_argmax_nchw_fwd": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class RtsdsError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False, force: bool = False):
+    from .build import build as _build
+
+    return _build(verbose=verbose, force=force)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if os.environ.get("RTSDS_NO_AUTOBUILD"):
+            raise RtsdsError(f"{LIB_PATH} is missing; run `python -m rtsds_b200.build` (no CPU fallback exists)")
+        build()
+    try:
+        handle = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover
+        raise RtsdsError(f"cannot load {LIB_PATH}: {e} (no CPU fallback exists)") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as e:
+            raise RtsdsError(f"{LIB_PATH} does not export {name}; rebuild with `python -m rtsds_b200.build --force`") from e
+        fn.restype = res
+        fn.argtypes = args
+    if handle.rtsds_abi_version() != 1:
+        raise RtsdsError("librtsds_b200.so ABI version mismatch")
+    _lib = handle
+    return handle
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().rtsds_last_error_string().decode(errors="replace")
+        raise RtsdsError(f"{what or 'rtsds'} failed (code {rc}): {msg}")

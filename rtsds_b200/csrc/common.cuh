@@ -1,0 +1,80 @@
+// Shared helpers for librtsds_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/rtsds_b200.h"
+
+namespace rtsds {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int  check_launch(const char* what);          // cudaGetLastError -> RTSDS_ECUDA
+
+#define RTSDS_REQUIRE(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::rtsds::set_error(__VA_ARGS__);                      \
+            return RTSDS_EINVAL;                                  \
+        }                                                         \
+    } while (0)
+
+static inline cudaStream_t as_stream(rtsds_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+int num_sms();
+
+// ---- dtype helpers ---------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == RTSDS_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == RTSDS_ACT_LRELU) return v > 0.0f ? v : v * slope;
+    return v;
+}
+
+// ---- warp / block reductions ----------------------------------------------
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Bilinear source index, align_corners=False, as ATen's
+// area_pixel_compute_source_index (negative source clamped to 0).
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_src(int dst, float rscale, int in_size) {
+    float r = rscale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+    r = r < 0.0f ? 0.0f : r;
+    int i0 = static_cast<int>(r);
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    int p = (i0 < in_size - 1) ? 1 : 0;
+    Lerp o;
+    o.i0 = i0; o.i1 = i0 + p;
+    o.l1 = r - static_cast<float>(i0);
+    o.l0 = 1.0f - o.l1;
+    return o;
+}
+// scale used by F.interpolate(size=...) in fp32: (float)in / out
+static inline float resize_scale(int in_size, int out_size) {
+    return static_cast<float>(in_size) / static_cast<float>(out_size);
+}
+
+}  // namespace rtsds

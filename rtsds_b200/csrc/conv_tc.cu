@@ -1,0 +1,629 @@
+// tcgen05 / TMEM implicit-GEMM convolution fed by TMA (sm_100a).
+//
+// Replaces nn.Conv2d (+ folded BatchNorm / bias + residual + ReLU/LeakyReLU)
+// for every conv with cin % 64 == 0 on the hot path:
+//   models/bisenet/build_bisenet.py:11-18 (ConvBlock), :64 (FFM conv),
+//   torchvision BasicBlock convs via models/bisenet/build_contextpath.py:22-25,
+//   models/deeplabv2/deeplabv2.py:13-24 (Bottleneck), :59-61 (ASPP),
+//   models/domain_shift/adversarial/model.py:46-48 (discriminator conv2-4).
+//
+// GEMM view:  D[M = 128 output pixels, N = BLOCK_N output channels]
+//             += A[M, K = 64 input channels of one filter tap] * B[N, K]^T
+// looped over (filter tap, 64-channel chunk).
+//   * A tile: ONE 4-D TMA box [64 ch, tile_w, tile_h, 1 image] of the NHWC bf16
+//     activation tensor, shifted by the tap offset; out-of-bounds pixels are
+//     zero-filled by TMA (= the conv padding).  The box lands in shared memory
+//     as 128 rows x 128 B with the 128-byte swizzle: exactly the canonical
+//     K-major SWIZZLE_128B UMMA operand, no register staging.
+//     Stride-2 convs use one TMA map per input parity (h%2, w%2), so every tap
+//     is again a dense box.
+//   * B tile: 2-D TMA box [64 k, BLOCK_N rows] of the packed weights
+//     [cout_pad][tap][cin] (K-major, SWIZZLE_128B).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread issues
+//     tcgen05.mma, accumulators in TMEM), warps 2-5 = epilogue
+//     (tcgen05.ld -> scale/shift/residual/activation -> bf16/fp32 NHWC store,
+//     optional per-channel sum / sum-of-squares for train-mode BatchNorm).
+//   * multi-stage smem ring with full/empty mbarriers; tcgen05.commit releases
+//     a stage back to the producer and finally signals the epilogue.
+//   * split_k > 1: each z-slice of the grid reduces a share of the k-blocks
+//     and writes raw fp32 partials; a finishing kernel sums the slices in a
+//     fixed order (deterministic) and applies the epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <mutex>
+#include <cstring>
+
+namespace rtsds {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;              // bf16 elements = 128 B = one swizzle atom
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KiB
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_TAPS = 16;
+
+struct TcMaps {
+    CUtensorMap a[4];   // activation views (one per input parity for stride 2)
+    CUtensorMap b;      // packed weights
+};
+
+struct TcParams {
+    int n_img, oh, ow;            // output grid the M tiles cover
+    int tile_w, tile_h, tiles_w, tiles_h;
+    int cout, cout_pad;
+    int n_taps, kchunks;          // k-blocks = n_taps * kchunks
+    int stages;
+    int split_k;
+    signed char tap_dh[TC_MAX_TAPS], tap_dw[TC_MAX_TAPS], tap_map[TC_MAX_TAPS];
+    long long out_sn, out_sh, out_sw;     // element strides of y
+    long long res_sn, res_sh, res_sw;     // element strides of residual
+    const float* scale;
+    const float* shift;
+    const void* residual;                 // same dtype as y
+    float* stats;
+    void* y;
+    float* partial;                       // split-K slices [split][M_total][cout_pad]
+    int out_dtype, act;
+    float slope;
+};
+
+// Reduce 32 per-thread values across the 32 lanes of a warp so that lane j
+// ends up with the sum of element j (31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * TC_A_BYTES;
+    float* s_scale = reinterpret_cast<float*>(smem_b + static_cast<size_t>(stages) * B_BYTES);
+    float* s_shift = s_scale + BLOCK_N;
+    float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 2 * BLOCK_N);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tmem_full_bar = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ----
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int th = trem / p.tiles_w;
+    const int h0 = th * p.tile_h;
+    const int w0 = (trem - th * p.tiles_w) * p.tile_w;
+    const int n0 = blockIdx.y * BLOCK_N;
+    const int kb_total = p.n_taps * p.kchunks;
+    const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * blockIdx.z) / p.split_k);
+    const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (blockIdx.z + 1)) / p.split_k);
+
+    // ---- one-time setup ----
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&maps.b);
+        ptx::prefetch_tmap(&maps.a[0]);
+        for (int i = 0; i < stages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += TC_THREADS - 64) {
+            const int co = n0 + i;
+            s_scale[i] = (p.scale && co < p.cout) ? p.scale[co] : 1.0f;
+            s_shift[i] = (p.shift && co < p.cout) ? p.shift[co] : 0.0f;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =================== TMA producer ===================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int tap = kb / p.kchunks;
+                const int cc = kb - tap * p.kchunks;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + B_BYTES);
+                ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES,
+                                 &maps.a[p.tap_map[tap]], &full_bar[stage], cc * TC_BLOCK_K,
+                                 w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
+                ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
+                                 kb * TC_BLOCK_K, n0);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =================== MMA issuer ===================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + static_cast<size_t>(stage) * TC_A_BYTES));
+                const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(stage) * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                    // +32 B per 16-element K step inside the 128-B swizzle atom
+                    ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC,
+                                   (kb > kb_begin || k > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            ptx::umma_commit(tmem_full_bar);              // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // =================== epilogue (4 warps, 128 TMEM lanes) ===================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // GEMM row = pixel inside the tile
+        const int hl = row / p.tile_w;
+        const int oh = h0 + hl;
+        const int ow = w0 + (row - hl * p.tile_w);
+        const bool valid = (oh < p.oh) && (ow < p.ow);
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after();
+
+        const long long m_total = static_cast<long long>(p.n_img) * p.oh * p.ow;
+        const long long pix_lin = (static_cast<long long>(img) * p.oh + oh) * p.ow + ow;
+        const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
+        const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
+
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int co0 = n0 + c0;
+
+            if (p.split_k > 1) {
+                if (valid) {
+                    float* dst = p.partial + (static_cast<long long>(blockIdx.z) * m_total + pix_lin) * p.cout_pad + co0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                continue;
+            }
+
+            if (p.stats) {
+                float t[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
+                float s1 = warp_transpose_sum(t, lane);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] * v[j] : 0.0f;
+                float s2 = warp_transpose_sum(t, lane);
+                atomicAdd(&s_stats[c0 + lane], s1);
+                atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
+            }
+
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                const bool full = (co0 + 32 <= p.cout);
+                if (p.out_dtype == RTSDS_BF16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + out_off + co0;
+                    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+                    if (full) {
+                        if (res) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(res + res_off + co0);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 rv = __ldg(rp + g);
+                                float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y);
+                                float2 c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+                                v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
+                                v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 o;
+                            o.x = pack_bf16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope));
+                            o.y = pack_bf16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope));
+                            o.z = pack_bf16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope));
+                            o.w = pack_bf16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope));
+                            *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (co0 + j < p.cout) {
+                                float x = v[j];
+                                if (res) x += __bfloat162float(res[res_off + co0 + j]);
+                                dst[j] = __float2bfloat16_rn(apply_act(x, p.act, p.slope));
+                            }
+                        }
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.y) + out_off + co0;
+                    const float* res = reinterpret_cast<const float*>(p.residual);
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (res) {
+                                float4 rv = __ldg(reinterpret_cast<const float4*>(res + res_off + co0 + j));
+                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                            }
+                            o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
+                            o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
+                            *reinterpret_cast<float4*>(dst + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (co0 + j < p.cout) {
+                                float x = v[j];
+                                if (res) x += res[res_off + co0 + j];
+                                dst[j] = apply_act(x, p.act, p.slope);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (p.stats && p.split_k == 1) {
+            // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                const int co = n0 + i;
+                if (co < p.cout) {
+                    atomicAdd(&p.stats[co], s_stats[i]);
+                    atomicAdd(&p.stats[p.cout + co], s_stats[BLOCK_N + i]);
+                }
+            }
+        }
+    }
+
+    // ---- teardown ----
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Sum split-K slices in slice order and apply the epilogue.
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_total, int cout,
+                     int cout_pad, int oh, int ow, TcParams p) {
+    extern __shared__ float s_acc[];    // [2*cout] when stats
+    if (p.stats) {
+        for (int i = threadIdx.x; i < 2 * cout; i += blockDim.x) s_acc[i] = 0.0f;
+        __syncthreads();
+    }
+    const int groups = cout_pad / 4;
+    const long long total = m_total * groups;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / groups;
+        const int co = static_cast<int>(i - pix * groups) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < split; ++s) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * m_total + pix) * cout_pad + co));
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        float v[4] = {a.x, a.y, a.z, a.w};
+        const int img = static_cast<int>(pix / (static_cast<long long>(oh) * ow));
+        const long long rem = pix - static_cast<long long>(img) * oh * ow;
+        const int y = static_cast<int>(rem / ow);
+        const int x = static_cast<int>(rem - static_cast<long long>(y) * ow);
+        const long long out_off = img * p.out_sn + y * p.out_sh + x * p.out_sw;
+        const long long res_off = img * p.res_sn + y * p.res_sh + x * p.res_sw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = co + j;
+            if (c >= cout) break;
+            float raw = v[j];
+            if (p.stats) {
+                atomicAdd(&s_acc[c], raw);
+                atomicAdd(&s_acc[cout + c], raw * raw);
+            }
+            float o = raw * (p.scale ? p.scale[c] : 1.0f) + (p.shift ? p.shift[c] : 0.0f);
+            if (p.out_dtype == RTSDS_BF16) {
+                if (p.residual) o += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + c]);
+                reinterpret_cast<__nv_bfloat16*>(p.y)[out_off + c] = __float2bfloat16_rn(apply_act(o, p.act, p.slope));
+            } else {
+                if (p.residual) o += reinterpret_cast<const float*>(p.residual)[res_off + c];
+                reinterpret_cast<float*>(p.y)[out_off + c] = apply_act(o, p.act, p.slope);
+            }
+        }
+    }
+    if (p.stats) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * cout; i += blockDim.x)
+            if (s_acc[i] != 0.0f) atomicAdd(&p.stats[i], s_acc[i]);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 4-D bf16 activation view [C, W, H, N] with element strides (1, sw, sh, sn); box [64, bw, bh, 1].
+static int make_act_map(CUtensorMap* m, const void* base, int c, int wd, int hd, int n, long long sw,
+                        long long sh, long long sn, int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return RTSDS_ECUDA; }
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(wd), static_cast<cuuint64_t>(hd),
+                          static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(sw * 2), static_cast<cuuint64_t>(sh * 2),
+                             static_cast<cuuint64_t>(sn * 2)};
+    cuuint32_t box[4] = {TC_BLOCK_K, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_tc: cuTensorMapEncodeTiled(activation) failed: %d (dims %d,%d,%d,%d strides %lld,%lld,%lld box %d,%d)",
+                  static_cast<int>(r), c, wd, hd, n, sw, sh, sn, bw, bh);
+        return RTSDS_ECUDA;
+    }
+    return RTSDS_OK;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* base, long long ktot, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return RTSDS_ECUDA; }
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot * 2)};
+    cuuint32_t box[2] = {TC_BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed: %d (k %lld rows %d box %d)", static_cast<int>(r),
+                  ktot, rows, box_rows);
+        return RTSDS_ECUDA;
+    }
+    return RTSDS_OK;
+}
+
+int conv_cout_pad(int cout) {
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    return static_cast<int>(cdiv(cout, 128) * 128);
+}
+
+static void pick_tile(int oh, int ow, int* tw, int* th) {
+    // tile_w * tile_h == 128; minimise padded area, prefer wide tiles (longer contiguous rows).
+    const int cand_w[5] = {128, 64, 32, 16, 8};
+    long long best = -1;
+    for (int i = 0; i < 5; ++i) {
+        int w_ = cand_w[i], h_ = 128 / w_;
+        long long area = cdiv(ow, w_) * w_ * cdiv(oh, h_) * h_;
+        if (best < 0 || area < best) { best = area; *tw = w_; *th = h_; }
+    }
+}
+
+static size_t tc_smem_bytes(int block_n, int stages) {
+    return 1024 + static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) + 4 * block_n * 4 +
+           (2 * stages + 1) * 8 + 16;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st) {
+    size_t smem = tc_smem_bytes(BLOCK_N, p.stages);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        attr_done = true;
+    }
+    conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    count_launch();
+    return check_launch("conv_tc_kernel");
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+extern "C" int rtsds_conv_cout_pad(int cout) { return conv_cout_pad(cout); }
+
+// Tuning knobs (process-wide, set from Python for experiments): block_n in {0=auto,32,64,128},
+// stages 0=auto.
+static int g_force_block_n = 0, g_force_stages = 0;
+extern "C" void rtsds_conv2d_tc_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
+
+static int tc_pick_block_n(int cout_pad, long long m_tiles) {
+    if (g_force_block_n && cout_pad % g_force_block_n == 0) return g_force_block_n;
+    if (cout_pad <= 64) return cout_pad;
+    // few M tiles: narrower N tiles give more CTAs
+    if (m_tiles * (cout_pad / 128) < num_sms()) return 64;
+    return 128;
+}
+
+static int tc_auto_split(long long ctas, int kb_total) {
+    int split = 1;
+    const int sms = num_sms();
+    while (ctas * split * 2 <= sms && kb_total / (split * 2) >= 4 && split < 16) split *= 2;
+    return split;
+}
+
+extern "C" size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d) {
+    if (!d) return 0;
+    // upper bound: 16 slices
+    const int cout_pad = conv_cout_pad(d->cout);
+    return static_cast<size_t>(16) * d->n * d->oh * d->ow * cout_pad * sizeof(float);
+}
+
+extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w, const float* scale,
+                                   const float* shift, const void* residual, float* stats, void* y,
+                                   void* workspace, size_t ws_bytes, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && x && w && y, "conv2d_tc_fwd: NULL argument");
+    RTSDS_REQUIRE(d->in_dtype == RTSDS_BF16, "conv2d_tc_fwd: input must be bf16");
+    RTSDS_REQUIRE(d->out_dtype == RTSDS_BF16 || d->out_dtype == RTSDS_F32, "conv2d_tc_fwd: bad out_dtype");
+    RTSDS_REQUIRE(d->cin > 0 && d->cin % TC_BLOCK_K == 0, "conv2d_tc_fwd: cin=%d must be a multiple of 64", d->cin);
+    RTSDS_REQUIRE(d->stride == 1 || d->stride == 2, "conv2d_tc_fwd: stride %d unsupported", d->stride);
+    RTSDS_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= TC_MAX_TAPS, "conv2d_tc_fwd: %dx%d filter unsupported", d->kh, d->kw);
+    RTSDS_REQUIRE(d->dil >= 1 && d->pad >= 0, "conv2d_tc_fwd: bad dil/pad");
+    RTSDS_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->cout > 0, "conv2d_tc_fwd: empty tensor");
+    const int exp_oh = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+    const int exp_ow = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+    RTSDS_REQUIRE(d->oh == exp_oh && d->ow == exp_ow, "conv2d_tc_fwd: oh/ow (%d,%d) != expected (%d,%d)", d->oh, d->ow, exp_oh, exp_ow);
+    RTSDS_REQUIRE(d->in_ld >= d->cin && d->in_ld % 8 == 0, "conv2d_tc_fwd: in_ld=%d must be >= cin and a multiple of 8", d->in_ld);
+    RTSDS_REQUIRE(d->out_ld >= d->cout, "conv2d_tc_fwd: out_ld < cout");
+    RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv2d_tc_fwd: pointers must be 16-byte aligned");
+    const int vec = d->out_dtype == RTSDS_BF16 ? 8 : 4;
+    RTSDS_REQUIRE(d->out_ld % vec == 0, "conv2d_tc_fwd: out_ld=%d must be a multiple of %d", d->out_ld, vec);
+    if (residual) {
+        RTSDS_REQUIRE(d->res_ld >= d->cout && d->res_ld % vec == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                      "conv2d_tc_fwd: residual pitch/alignment");
+    }
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+
+    TcMaps maps;
+    TcParams p;
+    memset(&maps, 0, sizeof(maps));
+    memset(&p, 0, sizeof(p));
+    p.n_img = d->n; p.oh = d->oh; p.ow = d->ow;
+    pick_tile(d->oh, d->ow, &p.tile_w, &p.tile_h);
+    p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
+    p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
+    p.cout = d->cout;
+    p.cout_pad = conv_cout_pad(d->cout);
+    p.n_taps = d->kh * d->kw;
+    p.kchunks = d->cin / TC_BLOCK_K;
+    p.out_sw = d->out_ld; p.out_sh = static_cast<long long>(d->ow) * d->out_ld; p.out_sn = p.out_sh * d->oh;
+    p.res_sw = d->res_ld; p.res_sh = static_cast<long long>(d->ow) * d->res_ld; p.res_sn = p.res_sh * d->oh;
+    p.scale = scale; p.shift = shift; p.residual = residual; p.stats = stats; p.y = y;
+    p.out_dtype = d->out_dtype; p.act = d->act; p.slope = d->slope;
+
+    // activation maps + tap table
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    const long long ld = d->in_ld;
+    const int st = d->stride;
+    bool have_map[4] = {false, false, false, false};
+    for (int r = 0; r < d->kh; ++r) {
+        for (int q = 0; q < d->kw; ++q) {
+            const int t = r * d->kw + q;
+            const int a = r * d->dil - d->pad, b = q * d->dil - d->pad;
+            const int hp = ((a % st) + st) % st, wp = ((b % st) + st) % st;
+            const int dh = (a - hp) / st, dw = (b - wp) / st;
+            RTSDS_REQUIRE(dh >= -128 && dh <= 127 && dw >= -128 && dw <= 127, "conv2d_tc_fwd: tap offset out of range");
+            const int mi = hp * 2 + wp;
+            p.tap_dh[t] = static_cast<signed char>(dh);
+            p.tap_dw[t] = static_cast<signed char>(dw);
+            p.tap_map[t] = static_cast<signed char>(mi);
+            if (!have_map[mi]) {
+                const int hd = (d->h - hp + st - 1) / st, wd = (d->w - wp + st - 1) / st;
+                RTSDS_REQUIRE(hd > 0 && wd > 0, "conv2d_tc_fwd: degenerate parity view");
+                rc = make_act_map(&maps.a[mi], xb + (static_cast<long long>(hp) * d->w + wp) * ld, d->cin, wd, hd, d->n,
+                                  st * ld, static_cast<long long>(st) * d->w * ld, static_cast<long long>(d->h) * d->w * ld,
+                                  p.tile_w, p.tile_h);
+                if (rc != RTSDS_OK) return rc;
+                have_map[mi] = true;
+            }
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+        if (!have_map[i]) maps.a[i] = maps.a[p.tap_map[0]];
+
+    const long long m_tiles = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
+    const int block_n = tc_pick_block_n(p.cout_pad, m_tiles);
+    const int n_tiles = p.cout_pad / block_n;
+    const long long ktot = static_cast<long long>(p.n_taps) * d->cin;
+    rc = make_weight_map(&maps.b, w, ktot, p.cout_pad, block_n);
+    if (rc != RTSDS_OK) return rc;
+
+    const int kb_total = p.n_taps * p.kchunks;
+    int split = d->split_k;
+    if (split <= 0) split = tc_auto_split(m_tiles * n_tiles, kb_total);
+    if (split > kb_total) split = kb_total;
+    if (split > 16) split = 16;
+    p.split_k = split;
+    const long long m_total = static_cast<long long>(d->n) * d->oh * d->ow;
+    if (split > 1) {
+        const size_t need = static_cast<size_t>(split) * m_total * p.cout_pad * sizeof(float);
+        if (!workspace || ws_bytes < need) {
+            set_error("conv2d_tc_fwd: split_k=%d needs %zu workspace bytes, got %zu", split, need, ws_bytes);
+            return RTSDS_EWS;
+        }
+        RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_tc_fwd: workspace alignment");
+        p.partial = reinterpret_cast<float*>(workspace);
+    }
+    // stages: keep two CTAs resident per SM (epilogue of one overlaps the main loop of the other)
+    int stages = g_force_stages ? g_force_stages : (block_n == 128 ? 3 : (block_n == 64 ? 4 : 5));
+    const int kb_per = kb_total / split;
+    if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
+    while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
+    p.stages = stages;
+    RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv2d_tc_fwd: too many tiles");
+
+    dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
+    cudaStream_t stream = as_stream(s);
+    if (block_n == 128) rc = launch_tc<128>(maps, p, grid, stream);
+    else if (block_n == 64) rc = launch_tc<64>(maps, p, grid, stream);
+    else if (block_n == 32) rc = launch_tc<32>(maps, p, grid, stream);
+    else { set_error("conv2d_tc_fwd: block_n %d", block_n); return RTSDS_EUNSUP; }
+    if (rc != RTSDS_OK) return rc;
+
+    if (split > 1) {
+        const long long total = m_total * (p.cout_pad / 4);
+        long long want = cdiv(total, 256);
+        int g = static_cast<int>(want > 4LL * num_sms() ? 4LL * num_sms() : want);
+        size_t sm = stats ? 2 * static_cast<size_t>(d->cout) * sizeof(float) : 0;
+        splitk_finish_kernel<<<g, 256, sm, stream>>>(p.partial, split, m_total, d->cout, p.cout_pad, d->oh, d->ow, p);
+        count_launch();
+        rc = check_launch("splitk_finish_kernel");
+    }
+    return rc;
+}

@@ -1,0 +1,453 @@
+// Bandwidth-bound glue kernels of the BiSeNet forward (models/bisenet/build_bisenet.py):
+// BatchNorm folding / finalisation, scale-shift-activation, global average
+// pooling, the ARM channel gate, gated bilinear resize into the concat buffer,
+// the FFM attention + final 1x1 conv, and the bilinear resize to NCHW logits.
+// All are vectorised, coalesced, warp-shuffle / shared-memory reductions; none
+// is GEMM-shaped.
+#include "common.cuh"
+
+namespace rtsds {
+
+// ---------------------------------------------------------------- BatchNorm
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var,
+                               const float* conv_bias, float eps, int c, float* scale, float* shift) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float sc = (gamma ? gamma[i] : 1.f) / sqrtf(var[i] + eps);
+    float sh = (beta ? beta[i] : 0.f) - mean[i] * sc;
+    if (conv_bias) sh += conv_bias[i] * sc;
+    scale[i] = sc; shift[i] = sh;
+}
+
+__global__ void bn_finalize_kernel(const float* stats, double count, const float* gamma, const float* beta,
+                                   float eps, float momentum, int c, float* running_mean, float* running_var,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const double mean = static_cast<double>(stats[i]) / count;
+    double var = static_cast<double>(stats[c + i]) / count - mean * mean;     // biased
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+    const float sc = g * invstd;
+    scale[i] = sc;
+    shift[i] = b - static_cast<float>(mean) * sc;
+    if (save_mean) save_mean[i] = static_cast<float>(mean);
+    if (save_invstd) save_invstd[i] = invstd;
+    if (running_mean) running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * static_cast<float>(mean);
+    if (running_var) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[i] = (1.f - momentum) * running_var[i] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+// y = act(scale*x + shift + residual); 8 channels per thread.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+scale_shift_act_kernel(const TX* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                       const TY* __restrict__ residual, long long n_pix, int c, int x_ld, int res_ld, int y_ld,
+                       int act, float slope, TY* __restrict__ y) {
+    const int cg = (c + 7) / 8;
+    const long long total = n_pix * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / cg;
+        const int c0 = static_cast<int>(i - pix * cg) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = c0 + j;
+            if (ch < c) {
+                float v = to_f32(x[pix * x_ld + ch]) * (scale ? scale[ch] : 1.f) + (shift ? shift[ch] : 0.f);
+                if (residual) v += to_f32(residual[pix * res_ld + ch]);
+                y[pix * y_ld + ch] = from_f32<TY>(apply_act(v, act, slope));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- global average pool
+// grid (c/32, psplit, n), block 256 = 32 channels x 8 pixel lanes; out pre-zeroed.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gap_kernel(const T* __restrict__ x, long long hw, int c, int ld, float inv_hw, float* __restrict__ out) {
+    __shared__ float s[8][33];
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int pl = threadIdx.x >> 5;
+    const int img = blockIdx.z;
+    const long long per = (hw + gridDim.y - 1) / gridDim.y;
+    const long long p0 = per * blockIdx.y;
+    const long long p1 = (p0 + per < hw) ? p0 + per : hw;
+    float acc = 0.f;
+    if (ch < c) {
+        const T* base = x + static_cast<long long>(img) * hw * ld + ch;
+        long long p = p0 + pl;
+        for (; p + 24 < p1; p += 32) {
+            float a0 = to_f32(base[p * ld]), a1 = to_f32(base[(p + 8) * ld]);
+            float a2 = to_f32(base[(p + 16) * ld]), a3 = to_f32(base[(p + 24) * ld]);
+            acc += (a0 + a1) + (a2 + a3);
+        }
+        for (; p < p1; p += 8) acc += to_f32(base[p * ld]);
+    }
+    s[pl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (pl == 0 && ch < c) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x];
+        atomicAdd(&out[static_cast<long long>(img) * c + ch], t * inv_hw);
+    }
+}
+
+// ---------------------------------------------------------------- ARM gate
+// One warp per output channel; loops over the batch.  n <= ARM_MAX_N in train mode.
+constexpr int ARM_MAX_N = 128;
+__global__ void __launch_bounds__(256)
+arm_gate_kernel(const float* __restrict__ pooled, const float* __restrict__ w, const float* __restrict__ b,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                float* running_var, float eps, float momentum, int train, int n, int c,
+                const float* __restrict__ mul, float* __restrict__ gate, float* lin_out, float* xhat_out) {
+    __shared__ float s_lin[8][ARM_MAX_N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co = blockIdx.x * 8 + warp;
+    if (co >= c) return;
+    const float* wr = w + static_cast<long long>(co) * c;
+    const float bias = b ? b[co] : 0.f;
+    const float g = gamma[co], be = beta[co];
+    if (!train) {
+        const float sc = g / sqrtf(running_var[co] + eps);
+        const float sh = be - running_mean[co] * sc;
+        for (int i = 0; i < n; ++i) {
+            float acc = 0.f;
+            for (int k = lane; k < c; k += 32) acc = fmaf(wr[k], pooled[static_cast<long long>(i) * c + k], acc);
+            acc = warp_sum(acc) + bias;
+            if (lane == 0) {
+                float v = 1.f / (1.f + expf(-(acc * sc + sh)));
+                if (mul) v *= mul[static_cast<long long>(i) * c + co];
+                gate[static_cast<long long>(i) * c + co] = v;
+                if (lin_out) lin_out[static_cast<long long>(i) * c + co] = acc;
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        float acc = 0.f;
+        for (int k = lane; k < c; k += 32) acc = fmaf(wr[k], pooled[static_cast<long long>(i) * c + k], acc);
+        acc = warp_sum(acc) + bias;
+        if (lane == 0) s_lin[warp][i] = acc;
+    }
+    __syncwarp();
+    float m = 0.f;
+    for (int i = lane; i < n; i += 32) m += s_lin[warp][i];
+    m = warp_sum(m) / n;
+    float v = 0.f;
+    for (int i = lane; i < n; i += 32) { float d = s_lin[warp][i] - m; v += d * d; }
+    v = warp_sum(v) / n;                                 // biased variance
+    const float invstd = rsqrtf(v + eps);
+    for (int i = lane; i < n; i += 32) {
+        const float lin = s_lin[warp][i];
+        const float xh = (lin - m) * invstd;
+        float o = 1.f / (1.f + expf(-(xh * g + be)));
+        if (mul) o *= mul[static_cast<long long>(i) * c + co];
+        gate[static_cast<long long>(i) * c + co] = o;
+        if (lin_out) lin_out[static_cast<long long>(i) * c + co] = lin;
+        if (xhat_out) xhat_out[static_cast<long long>(i) * c + co] = xh;
+    }
+    if (lane == 0) {
+        if (running_mean) running_mean[co] = (1.f - momentum) * running_mean[co] + momentum * m;
+        if (running_var) running_var[co] = (1.f - momentum) * running_var[co] + momentum * (v * n / (n - 1));
+    }
+}
+
+// ---------------------------------------------------------------- gated bilinear resize NHWC -> NHWC slot
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int src_ld, const float* __restrict__ gate,
+                   int oh, int ow, float rh, float rw, T* __restrict__ dst, int dst_ld, int dst_coff) {
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * oh * ow * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g8 = static_cast<int>(i % cg);
+        long long r = i / cg;
+        const int ox = static_cast<int>(r % ow); r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int img = static_cast<int>(r / oh);
+        const Lerp ly = lerp_src(oy, rh, h), lx = lerp_src(ox, rw, w);
+        const T* b = src + static_cast<long long>(img) * h * w * src_ld + g8 * 8;
+        const T* p00 = b + (static_cast<long long>(ly.i0) * w + lx.i0) * src_ld;
+        const T* p01 = b + (static_cast<long long>(ly.i0) * w + lx.i1) * src_ld;
+        const T* p10 = b + (static_cast<long long>(ly.i1) * w + lx.i0) * src_ld;
+        const T* p11 = b + (static_cast<long long>(ly.i1) * w + lx.i1) * src_ld;
+        T* d = dst + ((static_cast<long long>(img) * oh + oy) * ow + ox) * dst_ld + dst_coff + g8 * 8;
+        const float* gp = gate ? gate + static_cast<long long>(img) * c + g8 * 8 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = ly.l0 * (lx.l0 * to_f32(p00[j]) + lx.l1 * to_f32(p01[j])) +
+                      ly.l1 * (lx.l0 * to_f32(p10[j]) + lx.l1 * to_f32(p11[j]));
+            if (gp) v *= gp[j];
+            d[j] = from_f32<T>(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- FFM attention + final 1x1 conv
+constexpr int FFM_MAX_C = 32;
+template <typename T>
+__global__ void __launch_bounds__(256)
+ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ pooled, long long hw, int c,
+                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
+                float* attn_out, float* __restrict__ z, int z_ld) {
+    __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C];
+    __shared__ float s_w[FFM_MAX_C * FFM_MAX_C], s_b[FFM_MAX_C];
+    const int img = blockIdx.y;
+    const int t = threadIdx.x;
+    const float* pp = pooled + static_cast<long long>(img) * c;
+    if (t < c) {
+        float acc = b1[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(w1[t * c + k], pp[k], acc);
+        s_h[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (t < c) {
+        float acc = b2[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(w2[t * c + k], s_h[k], acc);
+        const float a = 1.f / (1.f + expf(-acc));
+        s_a[t] = a;
+        if (attn_out && blockIdx.x == 0) attn_out[static_cast<long long>(img) * c + t] = a;
+    }
+    __syncthreads();
+    // fold g = f*a + f into the 1x1 conv: W'[o][k] = Wc[o][k]; applied to g computed per pixel
+    for (int i = t; i < c * c; i += blockDim.x) s_w[i] = wc ? wc[i] : 0.f;
+    if (t < c) s_b[t] = (wc && bc) ? bc[t] : 0.f;
+    __syncthreads();
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + t; p < hw;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const T* fp = f + (static_cast<long long>(img) * hw + p) * f_ld;
+        float g[FFM_MAX_C];
+#pragma unroll
+        for (int k = 0; k < FFM_MAX_C; ++k) {
+            if (k < c) { const float v = to_f32(fp[k]); g[k] = v * s_a[k] + v; } else g[k] = 0.f;
+        }
+        float* zp = z + (static_cast<long long>(img) * hw + p) * z_ld;
+        if (wc) {
+            for (int o = 0; o < c; ++o) {
+                float acc = s_b[o];
+#pragma unroll
+                for (int k = 0; k < FFM_MAX_C; ++k)
+                    if (k < c) acc = fmaf(s_w[o * c + k], g[k], acc);
+                zp[o] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FFM_MAX_C; ++k)
+                if (k < c) zp[k] = g[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- bilinear resize NHWC fp32 -> NCHW fp32
+constexpr int RS_THREADS = 256, RS_PX = 4, RS_TILE = RS_THREADS * RS_PX;
+__global__ void __launch_bounds__(RS_THREADS)
+resize_nchw_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
+                   float* __restrict__ out) {
+    extern __shared__ float sm[];     // [2][ncols][c]
+    const int img = blockIdx.z, oy = blockIdx.y;
+    const int ox0 = blockIdx.x * RS_TILE;
+    const int ox_last = min(ox0 + RS_TILE, ow) - 1;
+    const Lerp ly = lerp_src(oy, rh, h);
+    const int xs = lerp_src(ox0, rw, w).i0;
+    const int xe = lerp_src(ox_last, rw, w).i1;
+    const int ncols = xe - xs + 1;
+    float* s0 = sm;
+    float* s1 = sm + ncols * c;
+    const float* r0 = z + (static_cast<long long>(img) * h + ly.i0) * w * z_ld;
+    const float* r1 = z + (static_cast<long long>(img) * h + ly.i1) * w * z_ld;
+    for (int i = threadIdx.x; i < ncols * c; i += RS_THREADS) {
+        const int col = i / c, ch = i - col * c;
+        s0[i] = __ldg(r0 + static_cast<long long>(xs + col) * z_ld + ch);
+        s1[i] = __ldg(r1 + static_cast<long long>(xs + col) * z_ld + ch);
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x * RS_PX;
+    if (ox >= ow) return;
+    Lerp lx[RS_PX];
+#pragma unroll
+    for (int j = 0; j < RS_PX; ++j) {
+        lx[j] = lerp_src(min(ox + j, ow - 1), rw, w);
+        lx[j].i0 -= xs; lx[j].i1 -= xs;
+    }
+    const long long plane = static_cast<long long>(oh) * ow;
+    float* op = out + static_cast<long long>(img) * c * plane + static_cast<long long>(oy) * ow + ox;
+    const bool vec = (ox + RS_PX <= ow) && ((ow & 3) == 0);
+    for (int ch = 0; ch < c; ++ch) {
+        float v[RS_PX];
+#pragma unroll
+        for (int j = 0; j < RS_PX; ++j) {
+            v[j] = ly.l0 * (lx[j].l0 * s0[lx[j].i0 * c + ch] + lx[j].l1 * s0[lx[j].i1 * c + ch]) +
+                   ly.l1 * (lx[j].l0 * s1[lx[j].i0 * c + ch] + lx[j].l1 * s1[lx[j].i1 * c + ch]);
+        }
+        if (vec) {
+            __stcs(reinterpret_cast<float4*>(op + ch * plane), make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < RS_PX; ++j)
+                if (ox + j < ow) op[ch * plane + j] = v[j];
+        }
+    }
+}
+
+static int grid_for(long long total, int threads, int waves = 8) {
+    long long want = cdiv(total, threads);
+    long long cap = static_cast<long long>(waves) * num_sms();
+    return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+extern "C" int rtsds_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                             const float* conv_bias, float eps, int c, float* scale, float* shift,
+                             rtsds_stream_t s) {
+    RTSDS_REQUIRE(mean && var && scale && shift && c > 0, "bn_fold: bad argument");
+    bn_fold_kernel<<<static_cast<int>(cdiv(c, 128)), 128, 0, as_stream(s)>>>(gamma, beta, mean, var, conv_bias, eps, c, scale, shift);
+    count_launch();
+    return check_launch("bn_fold_kernel");
+}
+
+extern "C" int rtsds_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float eps,
+                                 float momentum, int c, float* running_mean, float* running_var, float* scale,
+                                 float* shift, float* save_mean, float* save_invstd, rtsds_stream_t s) {
+    RTSDS_REQUIRE(stats && scale && shift && c > 0 && count > 0, "bn_finalize: bad argument");
+    bn_finalize_kernel<<<static_cast<int>(cdiv(c, 128)), 128, 0, as_stream(s)>>>(stats, count, gamma, beta, eps, momentum, c,
+                                                                             running_mean, running_var, scale, shift,
+                                                                             save_mean, save_invstd);
+    count_launch();
+    return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int rtsds_scale_shift_act(const void* x, const float* scale, const float* shift, const void* residual,
+                                     int64_t n_pix, int c, int x_ld, int res_ld, int y_ld, int act, float slope,
+                                     int x_dtype, int y_dtype, void* y, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && y && n_pix >= 0 && c > 0, "scale_shift_act: bad argument");
+    if (n_pix == 0) return RTSDS_OK;
+    const int grid = grid_for(n_pix * ((c + 7) / 8), 256);
+    cudaStream_t st = as_stream(s);
+    if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_BF16)
+        scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(residual), n_pix, c,
+            x_ld, res_ld, y_ld, act, slope, reinterpret_cast<__nv_bfloat16*>(y));
+    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_F32)
+        scale_shift_act_kernel<float, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), scale, shift,
+                                                                   reinterpret_cast<const float*>(residual), n_pix, c, x_ld,
+                                                                   res_ld, y_ld, act, slope, reinterpret_cast<float*>(y));
+    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_BF16)
+        scale_shift_act_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(
+            reinterpret_cast<const float*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(residual), n_pix, c, x_ld,
+            res_ld, y_ld, act, slope, reinterpret_cast<__nv_bfloat16*>(y));
+    else if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_F32)
+        scale_shift_act_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const float*>(residual), n_pix, c, x_ld,
+            res_ld, y_ld, act, slope, reinterpret_cast<float*>(y));
+    else { set_error("scale_shift_act: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("scale_shift_act_kernel");
+}
+
+extern "C" int rtsds_global_avgpool(const void* x, int n, int64_t hw, int c, int ld, int dtype, float* out,
+                                    rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && out && n > 0 && hw > 0 && c > 0 && ld >= c, "global_avgpool: bad argument");
+    cudaStream_t st = as_stream(s);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n * c, st);
+    if (e != cudaSuccess) { set_error("global_avgpool: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+    const int cb = static_cast<int>(cdiv(c, 32));
+    long long psplit = cdiv(hw, 8 * 16);          // ~16 pixels per thread
+    const long long cap = cdiv(4LL * num_sms(), static_cast<long long>(cb) * n);
+    if (psplit > cap) psplit = cap;
+    if (psplit < 1) psplit = 1;
+    dim3 grid(cb, static_cast<unsigned>(psplit), n);
+    const float inv = 1.0f / static_cast<float>(hw);
+    if (dtype == RTSDS_BF16)
+        gap_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, ld, inv, out);
+    else if (dtype == RTSDS_F32)
+        gap_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), hw, c, ld, inv, out);
+    else { set_error("global_avgpool: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("gap_kernel");
+}
+
+extern "C" int rtsds_arm_gate(const float* pooled, const float* w, const float* b, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                              int train, int n, int c, const float* mul, float* gate, float* lin_out,
+                              float* xhat_out, rtsds_stream_t s) {
+    RTSDS_REQUIRE(pooled && w && gamma && beta && gate && n > 0 && c > 0, "arm_gate: bad argument");
+    RTSDS_REQUIRE(running_mean && running_var, "arm_gate: running stats required");
+    if (train) {
+        // nn.BatchNorm2d raises "Expected more than 1 value per channel when training" 
+        RTSDS_REQUIRE(n >= 2, "arm_gate: train-mode BatchNorm over [N,C,1,1] needs N >= 2 (got %d)", n);
+        RTSDS_REQUIRE(n <= ARM_MAX_N, "arm_gate: train-mode batch %d > %d", n, ARM_MAX_N);
+    }
+    arm_gate_kernel<<<static_cast<int>(cdiv(c, 8)), 256, 0, as_stream(s)>>>(pooled, w, b, gamma, beta, running_mean, running_var,
+                                                                        eps, momentum, train, n, c, mul, gate, lin_out, xhat_out);
+    count_launch();
+    return check_launch("arm_gate_kernel");
+}
+
+extern "C" int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int c, int src_ld, const float* gate,
+                                      int oh, int ow, void* dst, int dst_ld, int dst_coff, int dtype,
+                                      rtsds_stream_t s) {
+    RTSDS_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "gate_resize_nhwc: bad argument");
+    RTSDS_REQUIRE(c > 0 && c % 8 == 0 && src_ld >= c && dst_ld >= dst_coff + c, "gate_resize_nhwc: bad channel layout");
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    const int grid = grid_for(static_cast<long long>(n) * oh * ow * (c / 8), 256);
+    if (dtype == RTSDS_BF16)
+        gate_resize_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(src), n, h, w, c,
+                                                                          src_ld, gate, oh, ow, rh, rw,
+                                                                          reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff);
+    else if (dtype == RTSDS_F32)
+        gate_resize_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(src), n, h, w, c, src_ld, gate,
+                                                                  oh, ow, rh, rw, reinterpret_cast<float*>(dst), dst_ld, dst_coff);
+    else { set_error("gate_resize_nhwc: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("gate_resize_kernel");
+}
+
+extern "C" int rtsds_ffm_head(const void* f, int f_dtype, int f_ld, const float* pooled, int n, int64_t hw, int c,
+                              const float* w1, const float* b1, const float* w2, const float* b2, const float* wc,
+                              const float* bc, float* attn_out, float* z, int z_ld, rtsds_stream_t s) {
+    RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && z, "ffm_head: NULL argument");
+    RTSDS_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= FFM_MAX_C && f_ld >= c && z_ld >= c, "ffm_head: bad shape");
+    long long bx = cdiv(hw, 256);
+    const long long cap = cdiv(8LL * num_sms(), n);
+    if (bx > cap) bx = cap;
+    dim3 grid(static_cast<unsigned>(bx), n);
+    if (f_dtype == RTSDS_BF16)
+        ffm_head_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(f), f_ld, pooled, hw,
+                                                                       c, w1, b1, w2, b2, wc, bc, attn_out, z, z_ld);
+    else if (f_dtype == RTSDS_F32)
+        ffm_head_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(f), f_ld, pooled, hw, c, w1, b1, w2,
+                                                               b2, wc, bc, attn_out, z, z_ld);
+    else { set_error("ffm_head: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("ffm_head_kernel");
+}
+
+extern "C" int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow, float* out,
+                                    rtsds_stream_t s) {
+    RTSDS_REQUIRE(z && out && n > 0 && h > 0 && w > 0 && c > 0 && z_ld >= c && oh > 0 && ow > 0, "resize_to_nchw: bad argument");
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    // source columns touched by one 1024-pixel tile
+    const int max_cols = static_cast<int>(static_cast<double>(RS_TILE) * w / ow) + 4;
+    size_t smem = sizeof(float) * 2 * static_cast<size_t>(max_cols < w ? max_cols : w) * c;
+    RTSDS_REQUIRE(smem <= 200 * 1024, "resize_to_nchw: tile needs %zu bytes of shared memory", smem);
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(resize_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        done = true;
+    }
+    dim3 grid(static_cast<unsigned>(cdiv(ow, RS_TILE)), oh, n);
+    resize_nchw_kernel<<<grid, RS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw, out);
+    count_launch();
+    return check_launch("resize_nchw_kernel");
+}

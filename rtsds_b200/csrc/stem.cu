@@ -1,0 +1,280 @@
+// Direct (CUDA-core) convolutions for the layers whose input channel count is
+// too small for a tensor-core K tile: they read the API-boundary NCHW fp32
+// tensor and write NHWC.
+//   * Spatial path ConvBlock1: conv3x3 s2 p1 3->64  (models/bisenet/build_bisenet.py:24)
+//   * Context path / DeepLab stem: conv7x7 s2 p3 3->64 (torchvision resnet conv1 via
+//     models/bisenet/build_contextpath.py:19; models/deeplabv2/deeplabv2.py:73)
+//   * Discriminator conv1: conv4x4 s2 p1 19->64 + bias + LeakyReLU, with the
+//     F.softmax(dim=1) of train.py:225,245,256 fused into the loader
+//     (models/domain_shift/adversarial/model.py:45,72).
+// These are bandwidth/FFMA-bound (K = 27 / 147 / 304): one output pixel per
+// thread, all 64 output channels in registers, the input patch and the
+// [ci][tap][co] weight slice in shared memory (weights read as 16-byte
+// broadcasts), coalesced row loads from NCHW, 128/256-byte contiguous NHWC
+// stores per thread.  Also: MaxPool2d(3,2,1) on NHWC.
+#include "common.cuh"
+
+namespace rtsds {
+
+constexpr int ST_TW = 32, ST_TH = 8, ST_THREADS = ST_TW * ST_TH, ST_COUT = 64, ST_CCH = 4;
+
+struct StemParams {
+    int n, cin, h, w, oh, ow, pad;
+    int act;
+    float slope;
+    int softmax_in;
+    int out_dtype;
+};
+
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ scale,
+                 const float* __restrict__ shift, float* stats, void* y, StemParams p) {
+    constexpr int PH = (ST_TH - 1) * S + K, PW = (ST_TW - 1) * S + K;
+    constexpr int PWP = PW | 1;     // odd pitch: stride-S column reads spread over banks
+    extern __shared__ float smem[];
+    float* s_patch = smem;                                  // [ST_CCH][PH][PWP]
+    float* s_w = s_patch + ST_CCH * PH * PWP;               // [ST_CCH][K*K][64]
+    float* s_max = s_w + ST_CCH * K * K * ST_COUT;          // [PH*PW] (softmax_in)
+    float* s_inv = s_max + PH * PW;
+    __shared__ float s_stat[2 * ST_COUT];
+
+    const int tid = threadIdx.x;
+    const int lx = tid % ST_TW, ly = tid / ST_TW;
+    const int img = blockIdx.z;
+    const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+    const int iy0 = oy0 * S - p.pad, ix0 = ox0 * S - p.pad;
+    const long long plane = static_cast<long long>(p.h) * p.w;
+    const float* ximg = x + static_cast<long long>(img) * p.cin * plane;
+
+    if (tid < 2 * ST_COUT) s_stat[tid] = 0.f;
+
+    if (p.softmax_in) {
+        for (int i = tid; i < PH * PW; i += ST_THREADS) {
+            const int py = i / PW, px = i - py * PW;
+            const int iy = iy0 + py, ix = ix0 + px;
+            float m = -INFINITY, sum = 0.f;
+            if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+                const float* xp = ximg + static_cast<long long>(iy) * p.w + ix;
+                for (int c = 0; c < p.cin; ++c) m = fmaxf(m, __ldg(xp + c * plane));
+                for (int c = 0; c < p.cin; ++c) sum += expf(__ldg(xp + c * plane) - m);
+            }
+            s_max[i] = m;
+            s_inv[i] = sum > 0.f ? 1.0f / sum : 0.f;
+        }
+    }
+
+    float acc[ST_COUT];
+#pragma unroll
+    for (int i = 0; i < ST_COUT; ++i) acc[i] = 0.f;
+
+    for (int c0 = 0; c0 < p.cin; c0 += ST_CCH) {
+        const int nc = min(ST_CCH, p.cin - c0);
+        __syncthreads();
+        // patch: coalesced along W
+        for (int i = tid; i < nc * PH * PW; i += ST_THREADS) {
+            const int c = i / (PH * PW);
+            const int r = i - c * PH * PW;
+            const int py = r / PW, px = r - py * PW;
+            const int iy = iy0 + py, ix = ix0 + px;
+            float v = 0.f;
+            if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+                v = __ldg(ximg + (c0 + c) * plane + static_cast<long long>(iy) * p.w + ix);
+                if (p.softmax_in) v = expf(v - s_max[r]) * s_inv[r];
+            }
+            s_patch[(c * PH + py) * PWP + px] = v;
+        }
+        // weights OIHW -> [c][tap][co]
+        for (int i = tid; i < nc * K * K * ST_COUT; i += ST_THREADS) {
+            const int co = i % ST_COUT;
+            const int r = i / ST_COUT;
+            const int t = r % (K * K), c = r / (K * K);
+            s_w[i] = __ldg(wgt + (static_cast<long long>(co) * p.cin + c0 + c) * (K * K) + t);
+        }
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+#pragma unroll 1
+            for (int r = 0; r < K; ++r) {
+                const float* prow = s_patch + (c * PH + ly * S + r) * PWP + lx * S;
+                const float4* wrow = reinterpret_cast<const float4*>(s_w + (c * K * K + r * K) * ST_COUT);
+#pragma unroll
+                for (int q = 0; q < K; ++q) {
+                    const float a = prow[q];
+#pragma unroll
+                    for (int g = 0; g < ST_COUT / 4; ++g) {
+                        const float4 w4 = wrow[q * (ST_COUT / 4) + g];
+                        acc[g * 4 + 0] = fmaf(a, w4.x, acc[g * 4 + 0]);
+                        acc[g * 4 + 1] = fmaf(a, w4.y, acc[g * 4 + 1]);
+                        acc[g * 4 + 2] = fmaf(a, w4.z, acc[g * 4 + 2]);
+                        acc[g * 4 + 3] = fmaf(a, w4.w, acc[g * 4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    const bool valid = oy < p.oh && ox < p.ow;
+    if (stats) {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = valid ? acc[half * 32 + j] : 0.f;
+            float s1 = warp_transpose_sum32(t, lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = valid ? acc[half * 32 + j] * acc[half * 32 + j] : 0.f;
+            float s2 = warp_transpose_sum32(t, lane);
+            atomicAdd(&s_stat[half * 32 + lane], s1);
+            atomicAdd(&s_stat[ST_COUT + half * 32 + lane], s2);
+        }
+    }
+    if (valid) {
+        const long long pix = (static_cast<long long>(img) * p.oh + oy) * p.ow + ox;
+#pragma unroll
+        for (int j = 0; j < ST_COUT; ++j) {
+            float v = acc[j] * (scale ? __ldg(scale + j) : 1.f) + (shift ? __ldg(shift + j) : 0.f);
+            acc[j] = apply_act(v, p.act, p.slope);
+        }
+        if (p.out_dtype == RTSDS_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + pix * ST_COUT);
+#pragma unroll
+            for (int g = 0; g < ST_COUT / 8; ++g) {
+                uint4 o;
+                o.x = pack_bf16x2(acc[g * 8 + 0], acc[g * 8 + 1]);
+                o.y = pack_bf16x2(acc[g * 8 + 2], acc[g * 8 + 3]);
+                o.z = pack_bf16x2(acc[g * 8 + 4], acc[g * 8 + 5]);
+                o.w = pack_bf16x2(acc[g * 8 + 6], acc[g * 8 + 7]);
+                dst[g] = o;
+            }
+        } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + pix * ST_COUT);
+#pragma unroll
+            for (int g = 0; g < ST_COUT / 4; ++g)
+                dst[g] = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        if (tid < 2 * ST_COUT) atomicAdd(&stats[tid], s_stat[tid]);
+    }
+}
+
+template <int K, int S>
+static int launch_stem(const float* x, const float* w, const float* scale, const float* shift, float* stats,
+                       void* y, const StemParams& p, cudaStream_t st) {
+    constexpr int PH = (ST_TH - 1) * S + K, PW = (ST_TW - 1) * S + K, PWP = PW | 1;
+    size_t smem = sizeof(float) * (ST_CCH * PH * PWP + ST_CCH * K * K * ST_COUT + 2 * PH * PW);
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) { set_error("stem_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        done = true;
+    }
+    dim3 grid(static_cast<unsigned>(cdiv(p.ow, ST_TW)), static_cast<unsigned>(cdiv(p.oh, ST_TH)), static_cast<unsigned>(p.n));
+    stem_conv_kernel<K, S><<<grid, ST_THREADS, smem, st>>>(x, w, scale, shift, stats, y, p);
+    count_launch();
+    return check_launch("stem_conv_kernel");
+}
+
+// ---- MaxPool2d(kernel 3, stride 2, pad 1[, ceil_mode]) on NHWC --------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y) {
+    // one thread = one output pixel x 8 channels (16 B of bf16 / 32 B of fp32)
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * oh * ow * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % cg);
+        long long r = i / cg;
+        const int ox = static_cast<int>(r % ow); r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int img = static_cast<int>(r / oh);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= h) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= w) continue;
+                const T* px = x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], to_f32(px[j]));
+            }
+        }
+        T* py = y + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) py[j] = from_f32<T>(m[j]);
+    }
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+extern "C" int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, int cin, int h, int w, int cout,
+                                   int k, int stride, int pad, const float* scale, const float* shift, int act,
+                                   float slope, int softmax_in, float* stats, int out_dtype, void* y,
+                                   rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && w_oihw && y, "stem_conv_fwd: NULL argument");
+    RTSDS_REQUIRE(cout == ST_COUT, "stem_conv_fwd: cout=%d (only 64 supported)", cout);
+    RTSDS_REQUIRE(cin >= 1 && cin <= 32, "stem_conv_fwd: cin=%d out of range 1..32", cin);
+    RTSDS_REQUIRE(n > 0 && h > 0 && w > 0, "stem_conv_fwd: empty tensor");
+    RTSDS_REQUIRE(out_dtype == RTSDS_BF16 || out_dtype == RTSDS_F32, "stem_conv_fwd: bad out_dtype");
+    RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "stem_conv_fwd: y must be 16-byte aligned");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    StemParams p;
+    p.n = n; p.cin = cin; p.h = h; p.w = w; p.pad = pad;
+    p.oh = (h + 2 * pad - k) / stride + 1;
+    p.ow = (w + 2 * pad - k) / stride + 1;
+    RTSDS_REQUIRE(p.oh > 0 && p.ow > 0, "stem_conv_fwd: empty output");
+    p.act = act; p.slope = slope; p.softmax_in = softmax_in; p.out_dtype = out_dtype;
+    cudaStream_t st = as_stream(s);
+    if (k == 3 && stride == 2) return launch_stem<3, 2>(x, w_oihw, scale, shift, stats, y, p, st);
+    if (k == 4 && stride == 2) return launch_stem<4, 2>(x, w_oihw, scale, shift, stats, y, p, st);
+    if (k == 7 && stride == 2) return launch_stem<7, 2>(x, w_oihw, scale, shift, stats, y, p, st);
+    set_error("stem_conv_fwd: k=%d stride=%d unsupported (3/4/7 with stride 2)", k, stride);
+    return RTSDS_EUNSUP;
+}
+
+extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
+                                      void* y, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && y, "maxpool: NULL argument");
+    RTSDS_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape (c must be a multiple of 8)");
+    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "maxpool: bad dtype");
+    auto osz = [&](int in) {
+        int o = ceil_mode ? (in + 2 - 3 + 1) / 2 + 1 : (in + 2 - 3) / 2 + 1;
+        if (ceil_mode && (o - 1) * 2 >= in + 1) --o;   // last window must start inside input+left pad (torch rule)
+        return o;
+    };
+    const int oh = osz(h), ow = osz(w);
+    const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
+    int grid = static_cast<int>(cdiv(total, 256) > 16LL * num_sms() ? 16LL * num_sms() : cdiv(total, 256));
+    if (dtype == RTSDS_BF16)
+        maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh, ow,
+                                                                      reinterpret_cast<__nv_bfloat16*>(y));
+    else
+        maxpool_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, oh, ow,
+                                                              reinterpret_cast<float*>(y));
+    count_launch();
+    return check_launch("maxpool_kernel");
+}
