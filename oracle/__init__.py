@@ -1,0 +1,3 @@
+"""ORACLE — CPU restatements of the reference algorithms, used ONLY as the
+checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under rtsds_b200/ or models/ imports it."""

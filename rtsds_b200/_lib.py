@@ -75,9 +75,47 @@ def build(verbose: bool = False, force: bool = False):
     return _build(verbose=verbose, force=force)
 
 
-def lib() -> C.CDLL:
+class _DryLib:
+    """RTSDS_DRYRUN=1: record the launch sequence without touching a GPU.  It computes
+    NOTHING (outputs stay uninitialised) — it exists so the host-side planning logic can
+    be unit-tested on a CPU-only box, and is never selected implicitly."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in SIGNATURES:
+            raise AttributeError(name)
+
+        def fn(*args):
+            self.calls.append(name)
+            if name == "rtsds_conv_cout_pad":
+                c = args[0]
+                return 32 if c <= 32 else 64 if c <= 64 else (c + 127) // 128 * 128
+            if name == "rtsds_conv2d_tc_workspace_bytes":
+                return 1024
+            if name == "rtsds_last_error_string":
+                return b"dry run"
+            if name == "rtsds_launch_count":
+                return len(self.calls)
+            return 1 if name == "rtsds_abi_version" else 0
+
+        return fn
+
+
+def dry_run() -> bool:
+    return os.environ.get("RTSDS_DRYRUN") == "1"
+
+
+def lib():
     """Load (once) and return the shared library; raise loudly if unavailable."""
     global _lib
+    if dry_run():
+        if not isinstance(_lib, _DryLib):
+            _lib = _DryLib()
+        return _lib
+    if isinstance(_lib, _DryLib):
+        _lib = None
     if _lib is not None:
         return _lib
     if not LIB_PATH.exists():

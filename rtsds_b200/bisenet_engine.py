@@ -1,0 +1,350 @@
+"""Execution plan for BiSeNet (reference models/bisenet/build_bisenet.py:141-172).
+
+A plan is built once per (batch, height, width, mode, precision): it owns the
+NHWC activation buffers, the packed bf16 weights, the folded BatchNorm vectors
+and an ordered list of kernel launches into librtsds_b200.so.  PyTorch supplies
+memory, streams and CUDA-graph capture; no torch operator computes anything on
+the path.
+
+Data layout in HBM (bf16 production mode; fp32 in check mode):
+  image        NCHW fp32   [N,3,H,W]          (API boundary, read by both stems)
+  sp1/cp0      NHWC        [N,H/2,W/2,64]
+  sp2          NHWC        [N,H/4,W/4,128]
+  cat          NHWC        [N,H/8,W/8,1024]   sx | gated+resized cx1 | cx2 slots
+                                              (torch.cat of :153/:72 never happens)
+  layer1..4    NHWC        ResNet-18 stage buffers (tmp / ping / pong / downsample)
+  feat         NHWC fp32   [N,H/8,W/8,32]     FFM ConvBlock output (19 valid channels)
+  z, z1, z2    NHWC fp32   [N,H/8,W/8,32]     logits at 1/8 resolution
+  logits       NCHW fp32   [N,19,H,W]         (API boundary)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, BF16, F32
+
+
+class _BN:
+    """Folded (eval) or batch-statistics (train) BatchNorm attached to a conv."""
+
+    def __init__(self, plan, bn, c):
+        self.bn = bn
+        self.c = c
+        dev = plan.device
+        self.scale = torch.empty(c, dtype=torch.float32, device=dev)
+        self.shift = torch.empty(c, dtype=torch.float32, device=dev)
+        if plan.train:
+            self.stats = plan.alloc_stats(c)
+            self.save_mean = torch.empty(c, dtype=torch.float32, device=dev)
+            self.save_invstd = torch.empty(c, dtype=torch.float32, device=dev)
+
+
+class BiSeNetPlan:
+    def __init__(self, model, n: int, h: int, w: int, train: bool, precision: str = "bf16"):
+        p0 = model.conv.weight
+        if not p0.is_cuda and not ops._lib.dry_run():
+            raise ops._lib.RtsdsError("BiSeNet parameters must live on a CUDA device (no CPU fallback)")
+        ops.check(ops.lib().rtsds_check_device(), "device check")
+        self.model = model
+        self.device = p0.device
+        self.n, self.h, self.w = n, h, w
+        self.train = train
+        self.precision = precision
+        self.dt = BF16 if precision == "bf16" else F32
+        self.tdt = ops.torch_dtype(self.dt)
+        self.nc = model.conv.weight.shape[0]
+        if model._context_name != "resnet18":
+            raise ops._lib.RtsdsError("only the resnet18 context path is implemented (SURVEY C2: resnet101 out of scope)")
+        if self.nc > 32:
+            raise ops._lib.RtsdsError("num_classes > 32 is not supported by the fused head kernels")
+        self._stats_chunks = []
+        self._stats_total = 0
+        self.pre_steps = []      # read the caller's input tensor (outside the CUDA graph)
+        self.steps = []          # everything between the stems and the low-res logits
+        self.pack_steps = []     # weight repack / BN fold (run when parameters change)
+        self.ws = None
+        self._ws_bytes = 0
+        self._param_version = None
+        self.generation = 0
+        self.graph = None
+        self._build()
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=self.tdt if dtype is None else dtype, device=self.device)
+
+    def alloc_stats(self, c):
+        off = self._stats_total
+        self._stats_total += 2 * c
+        self._stats_chunks.append((off, c))
+        return off
+
+    def _stats_view(self, off, c):
+        return self.stats_all[off:off + 2 * c]
+
+    def _need_ws(self, d):
+        if self.dt == BF16:
+            need = int(ops.lib().rtsds_conv2d_tc_workspace_bytes(d))
+            self._ws_bytes = max(self._ws_bytes, need)
+
+    def _conv(self, conv, bnmod, x, xshape, y, out_ld, act, *, in_ld=None, residual=None, res_ld=0, out_dtype=None,
+              x_off=0, y_off=0, bias=None, steps=None):
+        """Append conv (+BN/bias, +residual, +act) reading NHWC x -> NHWC y.  Returns (oh, ow)."""
+        steps = self.steps if steps is None else steps
+        n, h, w, cin = xshape
+        in_ld = cin if in_ld is None else in_ld
+        cout = conv.weight.shape[0]
+        k = conv.kernel_size[0]
+        out_dtype = self.dt if out_dtype is None else out_dtype
+        d = ops.make_conv_desc(n, h, w, cin, in_ld, cout, out_ld, k, conv.stride[0], conv.padding[0], conv.dilation[0],
+                               act=ACT_NONE, in_dtype=self.dt, out_dtype=out_dtype, res_ld=res_ld)
+        wpk = torch.empty((ops.cout_pad(cout), k * k, cin), dtype=self.tdt, device=self.device)
+        self.pack_steps.append(lambda: ops.pack_conv_weight(conv.weight, self.dt, wpk))
+        xp = x.data_ptr() + x_off * x.element_size()
+        yp = y.data_ptr() + y_off * y.element_size()
+        rp = residual.data_ptr() if residual is not None else None
+        self._need_ws(d)
+        use_tc = self.dt == BF16
+        n_pix = n * d.oh * d.ow
+
+        def launch(desc, scale, shift, res, stats):
+            if use_tc:
+                ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats, self.ws)
+            else:
+                ops.conv2d_simt(desc, xp, wpk, yp, scale, shift, res, stats)
+
+        if bnmod is None:
+            d.act = act
+            b = conv.bias if bias is None else bias
+            steps.append(lambda: launch(d, None, b.detach() if b is not None else None, rp, None))
+        elif not self.train:
+            bn = _BN(self, bnmod, cout)
+            d.act = act
+            self.pack_steps.append(lambda: ops.bn_fold(bnmod, bn.scale, bn.shift, conv.bias))
+            steps.append(lambda: launch(d, bn.scale, bn.shift, rp, None))
+        else:
+            bn = _BN(self, bnmod, cout)
+
+            def run_train():
+                st = self._stats_view(bn.stats, cout)
+                launch(d, None, None, None, st)              # raw conv output + per-channel sums
+                ops.bn_finalize(st, n_pix, bnmod, bn.scale, bn.shift, bn.save_mean, bn.save_invstd)
+                ops.scale_shift_act_ptr(yp, yp, n_pix, cout, bn.scale, bn.shift, rp, act, 0.0, out_ld, out_ld,
+                                        res_ld if res_ld else cout, out_dtype, out_dtype)
+
+            steps.append(run_train)
+        return d.oh, d.ow
+
+    # ------------------------------------------------------------------ plan construction
+    def _build(self):
+        m = self.model
+        n, H, W = self.n, self.h, self.w
+        cs = ops.conv_out_size
+        nc = self.nc
+        f32 = torch.float32
+
+        # ---- spatial path (reference :21-32) ----
+        sp = m.saptial_path
+        h2, w2 = cs(H, 3, 2, 1), cs(W, 3, 2, 1)
+        h4, w4 = cs(h2, 3, 2, 1), cs(w2, 3, 2, 1)
+        h8, w8 = cs(h4, 3, 2, 1), cs(w4, 3, 2, 1)
+        self.h8, self.w8 = h8, w8
+        sp1 = self.buf(n, h2, w2, 64)
+        sp2 = self.buf(n, h4, w4, 128)
+        cat = self.buf(n, h8, w8, 1024)
+        self.cat = cat
+        self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
+        self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
+        self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, 1024, ACT_RELU)
+
+        # ---- context path: ResNet-18 (build_contextpath.py:18-29) ----
+        cp = m.context_path
+        ch2, cw2 = cs(H, 7, 2, 3), cs(W, 7, 2, 3)
+        cp0 = self.buf(n, ch2, cw2, 64)
+        self._stem(cp.conv1, cp.bn1, cp0, 7, 2, 3)
+        ph, pw = ops.maxpool_out_size(ch2), ops.maxpool_out_size(cw2)
+        x = self.buf(n, ph, pw, 64)
+        self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
+        shape = (n, ph, pw, 64)
+        feats = []
+        for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
+            for blk in layer:
+                x, shape = self._basic_block(blk, x, shape)
+            feats.append((x, shape))
+        (f3, s3), (f4, s4) = feats[2], feats[3]
+        if min(h8, w8, s4[1], s4[2]) <= 0:
+            raise ops._lib.RtsdsError("input too small for BiSeNet")
+
+        # ---- ARMs, tail, gated resize into the concat buffer (reference :147-153) ----
+        arm1, arm2 = m.attention_refinement_module1, m.attention_refinement_module2
+        c3, c4 = s3[3], s4[3]
+        pooled3 = self.buf(n, c3, dtype=f32)
+        pooled4 = self.buf(n, c4, dtype=f32)
+        gate3 = self.buf(n, c3, dtype=f32)
+        gate4 = self.buf(n, c4, dtype=f32)
+        self.arm_saved = dict(pooled3=pooled3, pooled4=pooled4, gate3=gate3, gate4=gate4)
+        if self.train:
+            for k_, c_ in (("lin3", c3), ("xhat3", c3), ("lin4", c4), ("xhat4", c4)):
+                self.arm_saved[k_] = self.buf(n, c_, dtype=f32)
+        sv = self.arm_saved
+        tr = self.train
+        dt = self.dt
+        self.steps.append(lambda: ops.global_avgpool(f3, n, s3[1] * s3[2], c3, c3, pooled3))
+        self.steps.append(lambda: ops.global_avgpool(f4, n, s4[1] * s4[2], c4, c4, pooled4))
+        self.steps.append(lambda: ops.arm_gate(pooled3, arm1.conv, arm1.bn, tr, n, c3, gate3, None, sv.get("lin3"), sv.get("xhat3")))
+        # cx2 = ARM2(cx2) * tail, tail = GAP(feature4) = pooled4 (build_contextpath.py:27-28)
+        self.steps.append(lambda: ops.arm_gate(pooled4, arm2.conv, arm2.bn, tr, n, c4, gate4, pooled4, sv.get("lin4"), sv.get("xhat4")))
+        self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, 1024, 256, dt))
+        self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, 1024, 256 + c3, dt))
+        self.f3, self.s3, self.f4, self.s4 = f3, s3, f4, s4
+
+        # ---- auxiliary heads, train only (reference :155-159) ----
+        if self.train:
+            self.z1 = self.buf(n, h8, w8, 32, dtype=f32)
+            self.z2 = self.buf(n, h8, w8, 32, dtype=f32)
+            self._conv(m.supervision1, None, cat, (n, h8, w8, c3), self.z1, 32, ACT_NONE, in_ld=1024, x_off=256, out_dtype=F32)
+            self._conv(m.supervision2, None, cat, (n, h8, w8, c4), self.z2, 32, ACT_NONE, in_ld=1024, x_off=256 + c3, out_dtype=F32)
+
+        # ---- feature fusion module + final 1x1 conv at 1/8 resolution (reference :162-167) ----
+        ffm = m.feature_fusion_module
+        self.feat = self.buf(n, h8, w8, 32, dtype=f32)
+        self.pooled_f = self.buf(n, nc, dtype=f32)
+        self.attn = self.buf(n, nc, dtype=f32)
+        self.z = self.buf(n, h8, w8, 32, dtype=f32)
+        self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, out_dtype=F32)
+        feat, pooled_f, z, attn = self.feat, self.pooled_f, self.z, self.attn
+        final = m.conv if m.with_interpolation else None
+        self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))
+        self.steps.append(lambda: ops.ffm_head(feat, F32, 32, pooled_f, n, h8 * w8, nc, ffm.conv1, ffm.conv2, final, z, 32, attn))
+
+        self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
+        if self._ws_bytes:
+            self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def _stem(self, conv, bnmod, y, k, stride, pad):
+        cout = conv.weight.shape[0]
+        if not self.train:
+            bn = _BN(self, bnmod, cout)
+            self.pack_steps.append(lambda: ops.bn_fold(bnmod, bn.scale, bn.shift))
+            self.pre_steps.append(lambda x: ops.stem_conv(x, conv.weight, y, k, stride, pad, bn.scale, bn.shift, ACT_RELU))
+        else:
+            bn = _BN(self, bnmod, cout)
+            n_pix = y.shape[0] * y.shape[1] * y.shape[2]
+
+            def run(x):
+                st = self._stats_view(bn.stats, cout)
+                ops.stem_conv(x, conv.weight, y, k, stride, pad, stats=st)
+                ops.bn_finalize(st, n_pix, bnmod, bn.scale, bn.shift, bn.save_mean, bn.save_invstd)
+                ops.scale_shift_act(y, y, n_pix, cout, bn.scale, bn.shift, None, ACT_RELU)
+
+            self.pre_steps.append(run)
+
+    def _basic_block(self, blk, x, shape):
+        """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + shortcut(x))."""
+        n, h, w, cin = shape
+        cout = blk.conv1.weight.shape[0]
+        st = blk.conv1.stride[0]
+        oh, ow = ops.conv_out_size(h, 3, st, 1), ops.conv_out_size(w, 3, st, 1)
+        t = self.buf(n, oh, ow, cout)
+        y = self.buf(n, oh, ow, cout)
+        self._conv(blk.conv1, blk.bn1, x, shape, t, cout, ACT_RELU)
+        if blk.downsample is not None:
+            ds = self.buf(n, oh, ow, cout)
+            self._conv(blk.downsample[0], blk.downsample[1], x, shape, ds, cout, ACT_NONE)
+            res = ds
+        else:
+            res = x
+        self._conv(blk.conv2, blk.bn2, t, (n, oh, ow, cout), y, cout, ACT_RELU, residual=res, res_ld=cout)
+        return y, (n, oh, ow, cout)
+
+    # ------------------------------------------------------------------ execution
+    def _params_version(self):
+        v = 0
+        for p in self.model.parameters():
+            v += p._version
+        for b in self.model.buffers():
+            v += b._version
+        return (v, self.model.conv.weight.data_ptr())
+
+    def refresh_weights(self, force=False):
+        ver = self._params_version()
+        if force or ver != self._param_version:
+            for s in self.pack_steps:
+                s()
+            self._param_version = self._params_version()
+            return True
+        return False
+
+    def run_pre(self, x):
+        for s in self.pre_steps:
+            s(x)
+
+    def run_mid(self):
+        for s in self.steps:
+            s()
+
+    def forward_lowres(self, x, use_graph: bool):
+        """Run everything up to the 1/8-resolution logits (self.z [, z1, z2])."""
+        self.refresh_weights()
+        if self.train and self._stats_total:
+            self.stats_all.zero_()
+        self.generation += 1
+        self.run_pre(x)
+        if use_graph and not self.train:
+            if self.graph is None:
+                self.run_mid()                       # warm-up: sets kernel attributes, primes caches
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.run_mid()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self.run_mid()
+
+    def logits(self, z):
+        n, H, W = self.n, self.h, self.w
+        if self.model.with_interpolation:
+            # F.interpolate(scale_factor=8) (reference :166): output is 8x the 1/8-resolution map
+            out = torch.empty((n, self.nc, self.h8 * 8, self.w8 * 8), dtype=torch.float32, device=self.device)
+        else:
+            out = torch.empty((n, self.nc, self.h8, self.w8), dtype=torch.float32, device=self.device)
+        ops.resize_to_nchw(z, n, self.h8, self.w8, self.nc, 32, out)
+        return out
+
+    def logits_aux(self, z):
+        """Auxiliary heads are resized to the INPUT size (reference :158-159), not x8."""
+        out = torch.empty((self.n, self.nc, self.h, self.w), dtype=torch.float32, device=self.device)
+        ops.resize_to_nchw(z, self.n, self.h8, self.w8, self.nc, 32, out)
+        return out
+
+
+def _get_plan(model, x, train):
+    plans = model.__dict__.setdefault("_rtsds_plans", {})
+    n, _, h, w = x.shape
+    key = (n, h, w, bool(train), model.rtsds_precision, x.device.index)
+    plan = plans.get(key)
+    if plan is None:
+        plan = BiSeNetPlan(model, n, h, w, bool(train), model.rtsds_precision)
+        plans[key] = plan
+    return plan
+
+
+def bisenet_forward(model, x):
+    """BiSeNet.forward (reference :141-172): train -> (result, cx1_sup, cx2_sup); eval -> result."""
+    if not x.is_cuda and not ops._lib.dry_run():
+        raise ops._lib.RtsdsError("BiSeNet.forward needs a CUDA tensor: rtsds_b200 has no CPU fallback")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected input [N,3,H,W], got {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    if model.training:
+        from .bisenet_autograd import bisenet_train_forward
+
+        return bisenet_train_forward(model, x)
+    plan = _get_plan(model, x, False)
+    with torch.no_grad():
+        plan.forward_lowres(x, use_graph=model.rtsds_cuda_graph)
+        return plan.logits(plan.z)

@@ -1,0 +1,229 @@
+"""Thin tensor-level wrappers over the C ABI (include/rtsds_b200.h).
+
+PyTorch is used for device memory and streams only: every function passes
+`tensor.data_ptr()`, sizes and the current CUDA stream to librtsds_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc, check, lib
+
+__all__ = [
+    "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ConvDesc", "dtype_code", "torch_dtype",
+    "confusion_hist", "argmax_hist", "conv_out_size", "cout_pad", "pack_conv_weight", "conv2d_tc",
+    "conv2d_simt", "stem_conv", "maxpool3x3s2", "bn_fold", "bn_finalize", "scale_shift_act",
+    "global_avgpool", "arm_gate", "gate_resize_nhwc", "ffm_head", "resize_to_nchw",
+    "resize_ce_argmax_fwd", "resize_ce_bwd", "ce_argmax_nchw_fwd", "launch_count",
+]
+
+
+def _p(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _s():
+    if _lib.dry_run():
+        return None
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not isinstance(t, int) and not t.is_cuda and not _lib.dry_run():
+            raise _lib.RtsdsError("rtsds_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {dt}")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+def launch_count() -> int:
+    return int(lib().rtsds_launch_count())
+
+
+# ----------------------------------------------------------------------------- metric
+def confusion_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.Tensor,
+                   n_bad: torch.Tensor | None = None) -> None:
+    """hist[int64 n_cls*n_cls] += fast_hist(label, pred, n_cls) (utils.py:52-58)."""
+    _cuda(label, pred, hist)
+    assert label.dtype == torch.int64 and pred.dtype == torch.int64 and hist.dtype == torch.int64
+    assert label.is_contiguous() and pred.is_contiguous() and label.numel() == pred.numel()
+    check(lib().rtsds_confusion_hist(_p(label), _p(pred), label.numel(), n_cls, _p(hist), _p(n_bad), _s()),
+          "confusion_hist")
+
+
+def argmax_hist(logits: torch.Tensor, label: torch.Tensor | None, hist: torch.Tensor | None,
+                pred_out: torch.Tensor | None = None) -> None:
+    _cuda(logits, label, hist, pred_out)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 4
+    n, c, h, w = logits.shape
+    check(lib().rtsds_argmax_hist(_p(logits), _p(label), n, c, h * w, _p(pred_out), _p(hist), _s()), "argmax_hist")
+
+
+# ----------------------------------------------------------------------------- conv
+def conv_out_size(i: int, k: int, stride: int, pad: int, dil: int = 1) -> int:
+    return (i + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def cout_pad(cout: int) -> int:
+    return int(lib().rtsds_conv_cout_pad(cout))
+
+
+def pack_conv_weight(w: torch.Tensor, dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """OIHW fp32 -> [cout_pad][kh*kw][cin] in `dtype`."""
+    _cuda(w)
+    w = w.detach()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    co, ci, kh, kw = w.shape
+    cp = cout_pad(co)
+    if out is None:
+        out = torch.empty((cp, kh * kw, ci), dtype=torch_dtype(dtype), device=w.device)
+    check(lib().rtsds_pack_conv_weight(_p(w), co, ci, kh, kw, cp, dtype, _p(out), _s()), "pack_conv_weight")
+    return out
+
+
+def make_conv_desc(n, h, w, cin, in_ld, cout, out_ld, k, stride, pad, dil=1, act=ACT_NONE, slope=0.0,
+                   in_dtype=BF16, out_dtype=BF16, res_ld=0, split_k=0, kw=None) -> ConvDesc:
+    kw = k if kw is None else kw
+    d = ConvDesc()
+    d.n, d.h, d.w, d.cin, d.in_ld = n, h, w, cin, in_ld
+    d.cout, d.out_ld, d.res_ld = cout, out_ld, res_ld
+    d.kh, d.kw, d.stride, d.pad, d.dil = k, kw, stride, pad, dil
+    d.oh, d.ow = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, kw, stride, pad, dil)
+    d.act, d.slope = act, slope
+    d.in_dtype, d.out_dtype, d.split_k = in_dtype, out_dtype, split_k
+    return d
+
+
+def conv2d_tc(d: ConvDesc, x, w, y, scale=None, shift=None, residual=None, stats=None, workspace=None) -> None:
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    check(lib().rtsds_conv2d_tc_fwd(C.byref(d), _p(x), _p(w), _p(scale), _p(shift), _p(residual), _p(stats), _p(y),
+                                    _p(workspace), ws_bytes, _s()), "conv2d_tc_fwd")
+
+
+def conv2d_simt(d: ConvDesc, x, w, y, scale=None, shift=None, residual=None, stats=None) -> None:
+    check(lib().rtsds_conv2d_simt_fwd(C.byref(d), _p(x), _p(w), _p(scale), _p(shift), _p(residual), _p(stats), _p(y),
+                                      _s()), "conv2d_simt_fwd")
+
+
+def stem_conv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, k: int, stride: int, pad: int, scale=None,
+              shift=None, act=ACT_NONE, slope=0.0, softmax_in=False, stats=None) -> None:
+    _cuda(x, w, y)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    w = w.detach()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    n, cin, h, ww = x.shape
+    check(lib().rtsds_stem_conv_fwd(_p(x), _p(w), n, cin, h, ww, w.shape[0], k, stride, pad, _p(scale), _p(shift), act,
+                                    slope, int(softmax_in), _p(stats), dtype_code(y.dtype), _p(y), _s()), "stem_conv_fwd")
+
+
+def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, ceil_mode: bool = False) -> None:
+    n, h, w, c = x.shape
+    check(lib().rtsds_maxpool3x3s2_fwd(_p(x), n, h, w, c, dtype_code(x.dtype), int(ceil_mode), _p(y), _s()), "maxpool")
+
+
+def maxpool_out_size(i: int, ceil_mode: bool = False) -> int:
+    if not ceil_mode:
+        return (i - 1) // 2 + 1
+    o = i // 2 + 1
+    if (o - 1) * 2 >= i + 1:
+        o -= 1
+    return o
+
+
+# ----------------------------------------------------------------------------- batch norm
+def bn_fold(bn, scale: torch.Tensor, shift: torch.Tensor, conv_bias=None) -> None:
+    c = scale.numel()
+    check(lib().rtsds_bn_fold(_p(bn.weight.detach() if bn.weight is not None else None),
+                              _p(bn.bias.detach() if bn.bias is not None else None), _p(bn.running_mean),
+                              _p(bn.running_var), _p(conv_bias.detach() if conv_bias is not None else None),
+                              float(bn.eps), c, _p(scale), _p(shift), _s()), "bn_fold")
+
+
+def bn_finalize(stats, count, bn, scale, shift, save_mean=None, save_invstd=None, update_running=True) -> None:
+    c = scale.numel()
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    check(lib().rtsds_bn_finalize(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
+                                  float(mom), c, _p(bn.running_mean if update_running else None),
+                                  _p(bn.running_var if update_running else None), _p(scale), _p(shift), _p(save_mean),
+                                  _p(save_invstd), _s()), "bn_finalize")
+
+
+def scale_shift_act(x, y, n_pix, c, scale=None, shift=None, residual=None, act=ACT_NONE, slope=0.0, x_ld=None,
+                    y_ld=None, res_ld=None) -> None:
+    x_ld = c if x_ld is None else x_ld
+    y_ld = c if y_ld is None else y_ld
+    res_ld = c if res_ld is None else res_ld
+    check(lib().rtsds_scale_shift_act(_p(x), _p(scale), _p(shift), _p(residual), n_pix, c, x_ld, res_ld, y_ld, act,
+                                      slope, dtype_code(x.dtype), dtype_code(y.dtype), _p(y), _s()), "scale_shift_act")
+
+
+def scale_shift_act_ptr(xp, yp, n_pix, c, scale, shift, resp, act, slope, x_ld, y_ld, res_ld, x_dtype, y_dtype) -> None:
+    """Pointer-level variant (views into larger buffers)."""
+    check(lib().rtsds_scale_shift_act(_p(xp), _p(scale), _p(shift), _p(resp), n_pix, c, x_ld, res_ld, y_ld, act, slope,
+                                      x_dtype, y_dtype, _p(yp), _s()), "scale_shift_act")
+
+
+# ----------------------------------------------------------------------------- BiSeNet glue
+def global_avgpool(x, n, hw, c, ld, out, dtype=None) -> None:
+    dt = dtype_code(x.dtype) if dtype is None else dtype
+    check(lib().rtsds_global_avgpool(_p(x), n, hw, c, ld, dt, _p(out), _s()), "global_avgpool")
+
+
+def arm_gate(pooled, conv, bn, train, n, c, gate, mul=None, lin_out=None, xhat_out=None) -> None:
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    check(lib().rtsds_arm_gate(_p(pooled), _p(conv.weight.detach()), _p(conv.bias.detach() if conv.bias is not None else None),
+                               _p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean), _p(bn.running_var),
+                               float(bn.eps), float(mom), int(train), n, c, _p(mul), _p(gate), _p(lin_out),
+                               _p(xhat_out), _s()), "arm_gate")
+
+
+def gate_resize_nhwc(src, n, h, w, c, src_ld, gate, oh, ow, dst, dst_ld, dst_coff, dtype) -> None:
+    check(lib().rtsds_gate_resize_nhwc(_p(src), n, h, w, c, src_ld, _p(gate), oh, ow, _p(dst), dst_ld, dst_coff, dtype,
+                                       _s()), "gate_resize_nhwc")
+
+
+def ffm_head(f, f_dtype, f_ld, pooled, n, hw, c, conv1, conv2, final_conv, z, z_ld, attn_out=None) -> None:
+    wc = final_conv.weight.detach() if final_conv is not None else None
+    bc = final_conv.bias.detach() if final_conv is not None and final_conv.bias is not None else None
+    check(lib().rtsds_ffm_head(_p(f), f_dtype, f_ld, _p(pooled), n, hw, c, _p(conv1.weight.detach()),
+                               _p(conv1.bias.detach()), _p(conv2.weight.detach()), _p(conv2.bias.detach()), _p(wc), _p(bc),
+                               _p(attn_out), _p(z), z_ld, _s()), "ffm_head")
+
+
+def resize_to_nchw(z, n, h, w, c, z_ld, out) -> None:
+    oh, ow = out.shape[-2:]
+    check(lib().rtsds_resize_to_nchw(_p(z), n, h, w, c, z_ld, oh, ow, _p(out), _s()), "resize_to_nchw")
+
+
+# ----------------------------------------------------------------------------- loss
+def resize_ce_argmax_fwd(z, n, h, w, c, z_ld, oh, ow, target, ignore_index, acc, pred_out=None) -> None:
+    check(lib().rtsds_resize_ce_argmax_fwd(_p(z), n, h, w, c, z_ld, oh, ow, _p(target), int(ignore_index), _p(acc),
+                                           _p(pred_out), _s()), "resize_ce_argmax_fwd")
+
+
+def resize_ce_bwd(z, n, h, w, c, z_ld, oh, ow, target, ignore_index, grad_scale, dz) -> None:
+    check(lib().rtsds_resize_ce_bwd(_p(z), n, h, w, c, z_ld, oh, ow, _p(target), int(ignore_index), _p(grad_scale),
+                                    _p(dz), _s()), "resize_ce_bwd")
+
+
+def ce_argmax_nchw_fwd(logits, target, ignore_index, acc, pred_out=None) -> None:
+    n, c, h, w = logits.shape
+    check(lib().rtsds_ce_argmax_nchw_fwd(_p(logits), n, c, h * w, _p(target), int(ignore_index), _p(acc), _p(pred_out),
+                                         _s()), "ce_argmax_nchw_fwd")

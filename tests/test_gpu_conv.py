@@ -1,0 +1,167 @@
+"""Parity of the convolution kernels against the CPU oracle (torch fp32 on CPU).
+
+tcgen05 path: operands are bf16, accumulation fp32 -> compare with the oracle on
+bf16-rounded operands; tolerance 2e-2 rel for bf16 outputs (BASELINE.json), much
+tighter when the output is kept in fp32.  SIMT fp32 path: 1e-4.
+"""
+import pytest
+import torch
+
+from rtsds_b200 import ops
+from rtsds_b200.ops import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32
+
+from gpu_util import conv_ref, rel_err, run_conv
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, cin, h, w, cout, k, seed=0, kw=None):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k if kw is None else kw, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    return x, wt, g
+
+
+# (name, n, cin, h, w, cout, k, stride, pad, dil)
+TC_CASES = [
+    ("gemm_1tile", 1, 64, 8, 16, 32, 1, 1, 0, 1),
+    ("gemm_2kblk", 1, 128, 8, 16, 64, 1, 1, 0, 1),
+    ("3x3_s1", 1, 64, 16, 32, 64, 3, 1, 1, 1),
+    ("3x3_s1_multi", 2, 64, 64, 128, 64, 3, 1, 1, 1),
+    ("3x3_s2_even", 1, 64, 32, 64, 128, 3, 2, 1, 1),
+    ("3x3_s2_odd", 2, 64, 45, 80, 128, 3, 2, 1, 1),
+    ("3x3_s2_odd2", 1, 128, 23, 41, 256, 3, 2, 1, 1),
+    ("1x1_s2", 2, 128, 24, 40, 256, 1, 2, 0, 1),
+    ("1x1_s2_odd", 1, 64, 45, 81, 128, 1, 2, 0, 1),
+    ("layer4", 2, 512, 4, 6, 512, 3, 1, 1, 1),
+    ("dil2", 1, 64, 17, 33, 64, 3, 1, 2, 2),
+    ("dil4", 1, 128, 20, 20, 128, 3, 1, 4, 4),
+    ("disc_4x4_s2", 2, 64, 32, 48, 128, 4, 2, 1, 1),
+    ("ragged_w", 1, 64, 9, 13, 64, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tc_raw_fp32_out(cuda, case):
+    _, n, cin, h, w, cout, k, stride, pad, dil = case
+    x, wt, _ = _mk(n, cin, h, w, cout, k)
+    y, _, _ = run_conv("tc", x, wt, stride=stride, pad=pad, dil=dil, out_dtype=F32, out_ld=ops.cout_pad(cout))
+    ref, _ = conv_ref(x, wt, stride=stride, pad=pad, dil=dil)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 2e-4, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("block_n", [32, 64, 128])
+def test_conv_tc_block_n_variants(cuda, block_n):
+    x, wt, _ = _mk(2, 128, 20, 36, 256, 3, seed=3)
+    ops.lib().rtsds_conv2d_tc_tune(block_n, 0)
+    try:
+        y, _, _ = run_conv("tc", x, wt, out_dtype=F32, out_ld=256)
+    finally:
+        ops.lib().rtsds_conv2d_tc_tune(0, 0)
+    ref, _ = conv_ref(x, wt)
+    assert rel_err(y, ref) < 2e-4
+
+
+@pytest.mark.parametrize("stages", [2, 3, 6])
+def test_conv_tc_stage_counts(cuda, stages):
+    x, wt, _ = _mk(1, 256, 16, 32, 128, 3, seed=4)
+    ops.lib().rtsds_conv2d_tc_tune(0, stages)
+    try:
+        y, _, _ = run_conv("tc", x, wt, out_dtype=F32, out_ld=128)
+    finally:
+        ops.lib().rtsds_conv2d_tc_tune(0, 0)
+    ref, _ = conv_ref(x, wt)
+    assert rel_err(y, ref) < 2e-4
+
+
+@pytest.mark.parametrize("split", [2, 4, 8])
+def test_conv_tc_split_k(cuda, split):
+    x, wt, g = _mk(1, 256, 16, 32, 256, 3, seed=5)
+    scale = torch.rand(256, generator=g) + 0.5
+    shift = torch.randn(256, generator=g)
+    res = torch.randn(1, 256, 16, 32, generator=g)
+    y, st, _ = run_conv("tc", x, wt, scale=scale, shift=shift, residual=res, act=ACT_RELU, split_k=split, want_stats=True)
+    ref, raw = conv_ref(x, wt, scale=scale, shift=shift, residual=res, act=ACT_RELU)
+    assert rel_err(y, ref) < 1e-2
+    s1 = raw.sum((0, 2, 3))
+    s2 = (raw * raw).sum((0, 2, 3))
+    assert rel_err(st[:256], s1) < 1e-3 and rel_err(st[256:], s2) < 1e-3
+
+
+def test_conv_tc_epilogue_bn_residual_relu_bf16(cuda):
+    x, wt, g = _mk(2, 64, 32, 64, 64, 3, seed=6)
+    scale = torch.rand(64, generator=g) + 0.5
+    shift = torch.randn(64, generator=g)
+    res = torch.randn(2, 64, 32, 64, generator=g)
+    y, _, _ = run_conv("tc", x, wt, scale=scale, shift=shift, residual=res, act=ACT_RELU)
+    ref, _ = conv_ref(x, wt, scale=scale, shift=shift, residual=res, act=ACT_RELU)
+    assert rel_err(y, ref) < 1e-2          # bf16 output rounding (2^-9 relative)
+
+
+def test_conv_tc_bias_leaky_relu(cuda):
+    x, wt, g = _mk(2, 64, 32, 48, 128, 4, seed=7)
+    bias = torch.randn(128, generator=g)
+    y, _, _ = run_conv("tc", x, wt, stride=2, pad=1, shift=bias, act=ACT_LRELU, slope=0.2, out_dtype=F32, out_ld=128)
+    ref, _ = conv_ref(x, wt, stride=2, pad=1, shift=bias, act=ACT_LRELU, slope=0.2)
+    assert rel_err(y, ref) < 2e-4
+
+
+def test_conv_tc_stats_for_train_bn(cuda):
+    x, wt, _ = _mk(2, 64, 45, 80, 128, 3, seed=8)
+    y, st, _ = run_conv("tc", x, wt, stride=2, want_stats=True)
+    ref, raw = conv_ref(x, wt, stride=2)
+    assert rel_err(y, ref) < 1e-2
+    assert rel_err(st[:128], raw.sum((0, 2, 3))) < 1e-3
+    assert rel_err(st[128:], (raw * raw).sum((0, 2, 3))) < 1e-3
+
+
+def test_conv_tc_skinny_cout19_from_concat_view(cuda):
+    """FFM conv (1024->19, fp32 out with pitch 32) and a supervision head reading a channel slice."""
+    x, wt, g = _mk(2, 1024, 12, 20, 19, 3, seed=9)
+    y, _, ybuf = run_conv("tc", x, wt, out_dtype=F32, out_ld=32, act=ACT_RELU)
+    ref, _ = conv_ref(x, wt, act=ACT_RELU)
+    assert rel_err(y, ref) < 2e-4
+    assert torch.isnan(ybuf[..., 19:]).all(), "padding channels beyond cout must not be written"
+    x2, w2, g = _mk(2, 256, 12, 20, 19, 1, seed=10)
+    bias = torch.randn(19, generator=g)
+    y2, _, _ = run_conv("tc", x2, w2, pad=0, shift=bias, out_dtype=F32, out_ld=32, in_ld=1024, x_off=256)
+    ref2, _ = conv_ref(x2, w2, pad=0, shift=bias)
+    assert rel_err(y2, ref2) < 2e-4
+
+
+def test_conv_tc_rejects_bad_arguments(cuda):
+    x, wt, _ = _mk(1, 48, 8, 8, 32, 3)
+    with pytest.raises(ops._lib.RtsdsError, match="multiple of 64"):
+        run_conv("tc", x, wt)
+
+
+SIMT_CASES = [
+    ("3x3_s1", 2, 64, 16, 32, 64, 3, 1, 1, 1),
+    ("3x3_s2_odd", 1, 64, 45, 80, 128, 3, 2, 1, 1),
+    ("cin19", 1, 19, 12, 20, 19, 1, 1, 0, 1),
+    ("1x1_s2", 1, 128, 24, 40, 256, 1, 2, 0, 1),
+    ("dil2", 1, 64, 17, 33, 64, 3, 1, 2, 2),
+    ("4x4_s2", 1, 64, 32, 48, 128, 4, 2, 1, 1),
+    ("ffm", 1, 1024, 12, 20, 19, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES, ids=[c[0] for c in SIMT_CASES])
+def test_conv_simt_fp32_check_mode(cuda, case):
+    _, n, cin, h, w, cout, k, stride, pad, dil = case
+    x, wt, g = _mk(n, cin, h, w, cout, k, seed=11)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g)
+    y, st, _ = run_conv("simt", x, wt, stride=stride, pad=pad, dil=dil, scale=scale, shift=shift, act=ACT_RELU, dtype=F32,
+                        want_stats=True)
+    ref, raw = conv_ref(x, wt, stride=stride, pad=pad, dil=dil, scale=scale, shift=shift, act=ACT_RELU, round_inputs=False)
+    assert rel_err(y, ref) < 1e-5
+    assert rel_err(st[:cout], raw.sum((0, 2, 3))) < 1e-4
+
+
+def test_conv_simt_bf16_cross_checks_tc(cuda):
+    x, wt, _ = _mk(2, 128, 23, 40, 128, 3, seed=12)
+    a, _, _ = run_conv("tc", x, wt, out_dtype=F32, out_ld=128)
+    b, _, _ = run_conv("simt", x, wt, out_dtype=F32, out_ld=128)
+    assert rel_err(a, b) < 1e-4
