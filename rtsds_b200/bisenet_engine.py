@@ -59,6 +59,7 @@ class BiSeNetPlan:
         if self.nc > 32:
             raise ops._lib.RtsdsError("num_classes > 32 is not supported by the fused head kernels")
         self._stats_chunks = []
+        self._keep = []
         self._stats_total = 0
         self.pre_steps = []      # read the caller's input tensor (outside the CUDA graph)
         self.steps = []          # everything between the stems and the low-res logits
@@ -72,7 +73,10 @@ class BiSeNetPlan:
 
     # ------------------------------------------------------------------ helpers
     def buf(self, *shape, dtype=None):
-        return torch.empty(shape, dtype=self.tdt if dtype is None else dtype, device=self.device)
+        # kernels are handed raw pointers, so the plan must keep every buffer alive itself
+        t = torch.empty(shape, dtype=self.tdt if dtype is None else dtype, device=self.device)
+        self._keep.append(t)
+        return t
 
     def alloc_stats(self, c):
         off = self._stats_total
@@ -99,7 +103,7 @@ class BiSeNetPlan:
         out_dtype = self.dt if out_dtype is None else out_dtype
         d = ops.make_conv_desc(n, h, w, cin, in_ld, cout, out_ld, k, conv.stride[0], conv.padding[0], conv.dilation[0],
                                act=ACT_NONE, in_dtype=self.dt, out_dtype=out_dtype, res_ld=res_ld)
-        wpk = torch.empty((ops.cout_pad(cout), k * k, cin), dtype=self.tdt, device=self.device)
+        wpk = self.buf(ops.cout_pad(cout), k * k, cin)
         self.pack_steps.append(lambda: ops.pack_conv_weight(conv.weight, self.dt, wpk))
         xp = x.data_ptr() + x_off * x.element_size()
         yp = y.data_ptr() + y_off * y.element_size()

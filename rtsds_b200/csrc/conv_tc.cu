@@ -496,11 +496,27 @@ static int tc_auto_split(long long ctas, int kb_total) {
     return split;
 }
 
+// block_n / split-K selection shared by the launcher and the workspace query
+static void tc_plan(const RtsdsConvDesc* d, int* block_n, int* split, int* tile_w, int* tile_h) {
+    pick_tile(d->oh, d->ow, tile_w, tile_h);
+    const long long m_tiles = static_cast<long long>(d->n) * cdiv(d->ow, *tile_w) * cdiv(d->oh, *tile_h);
+    const int cp = conv_cout_pad(d->cout);
+    *block_n = tc_pick_block_n(cp, m_tiles);
+    const int kb_total = d->kh * d->kw * (d->cin / TC_BLOCK_K);
+    int sp = d->split_k;
+    if (sp <= 0) sp = tc_auto_split(m_tiles * (cp / *block_n), kb_total);
+    if (sp > kb_total) sp = kb_total;
+    if (sp > 16) sp = 16;
+    if (sp < 1) sp = 1;
+    *split = sp;
+}
+
 extern "C" size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d) {
-    if (!d) return 0;
-    // upper bound: 16 slices
-    const int cout_pad = conv_cout_pad(d->cout);
-    return static_cast<size_t>(16) * d->n * d->oh * d->ow * cout_pad * sizeof(float);
+    if (!d || d->cin <= 0 || d->cin % TC_BLOCK_K) return 0;
+    int bn, sp, tw, th;
+    tc_plan(d, &bn, &sp, &tw, &th);
+    if (sp <= 1) return 0;
+    return static_cast<size_t>(sp) * d->n * d->oh * d->ow * conv_cout_pad(d->cout) * sizeof(float);
 }
 
 extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w, const float* scale,
@@ -535,7 +551,8 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
     memset(&maps, 0, sizeof(maps));
     memset(&p, 0, sizeof(p));
     p.n_img = d->n; p.oh = d->oh; p.ow = d->ow;
-    pick_tile(d->oh, d->ow, &p.tile_w, &p.tile_h);
+    int plan_bn, plan_split;
+    tc_plan(d, &plan_bn, &plan_split, &p.tile_w, &p.tile_h);
     p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
     p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
     p.cout = d->cout;
@@ -578,17 +595,14 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
         if (!have_map[i]) maps.a[i] = maps.a[p.tap_map[0]];
 
     const long long m_tiles = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
-    const int block_n = tc_pick_block_n(p.cout_pad, m_tiles);
+    const int block_n = plan_bn;
     const int n_tiles = p.cout_pad / block_n;
     const long long ktot = static_cast<long long>(p.n_taps) * d->cin;
     rc = make_weight_map(&maps.b, w, ktot, p.cout_pad, block_n);
     if (rc != RTSDS_OK) return rc;
 
     const int kb_total = p.n_taps * p.kchunks;
-    int split = d->split_k;
-    if (split <= 0) split = tc_auto_split(m_tiles * n_tiles, kb_total);
-    if (split > kb_total) split = kb_total;
-    if (split > 16) split = 16;
+    const int split = plan_split;
     p.split_k = split;
     const long long m_total = static_cast<long long>(d->n) * d->oh * d->ow;
     if (split > 1) {
