@@ -128,6 +128,39 @@ int rtsds_conv2d_simt_fwd(const RtsdsConvDesc* d, const void* x, const void* w,
 int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw,
                            int cout_pad, int dtype, void* w_packed, rtsds_stream_t s);
 
+/* ------------------------------------------------------------------------
+ * Convolution backward (autograd of nn.Conv2d, driven by loss.backward() at
+ * train.py:95,213,233,251,262).  `d` is always the FORWARD geometry.
+ *
+ * dgrad: dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r*dil)/stride,(w+pad-s*dil)/stride,co]
+ *                       * W[co,ci,r,s]  (+ residual[n,h,w,ci], which may alias dx)
+ *   dy: NHWC, dtype d->in_dtype, pitch d->out_ld.  Tensor-core path: pitch >=
+ *       roundup(cout,64) with the channels cout.. zero.
+ *   w_dgrad: [cin_pad][kh*kw][ck] from rtsds_pack_conv_weight_dgrad with
+ *       cin_pad = rtsds_conv_cout_pad(cin); ck = roundup(cout,64) (tensor-core)
+ *       or cout (CUDA-core).
+ *   dx: NHWC of dx_dtype, pitch d->in_ld; residual pitch d->res_ld (0: in_ld).
+ * wgrad: dw_packed[co][r*kw+s][ci] (fp32) += sum_{n,oh,ow} dy[n,oh,ow,co] *
+ *        x[n,oh*stride-pad+r*dil,ow*stride-pad+s*dil,ci]; the caller zeroes
+ *        dw_packed; rtsds_unpack_conv_wgrad converts it to the OIHW layout of
+ *        nn.Conv2d.weight.grad (assign or accumulate).
+ * ---------------------------------------------------------------------- */
+size_t rtsds_conv2d_tc_dgrad_workspace_bytes(const RtsdsConvDesc* d);
+int rtsds_conv2d_tc_dgrad(const RtsdsConvDesc* d, const void* dy, const void* w_dgrad,
+                          const void* residual, void* dx, int dx_dtype, void* workspace,
+                          size_t ws_bytes, rtsds_stream_t s);
+int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy,
+                          float* dw_packed, rtsds_stream_t s);
+int rtsds_conv2d_simt_dgrad(const RtsdsConvDesc* d, const void* dy, const void* w_dgrad,
+                            const void* residual, void* dx, int dx_dtype, rtsds_stream_t s);
+int rtsds_conv2d_simt_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy,
+                            float* dw_packed, rtsds_stream_t s);
+int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw,
+                                 int cin_pad, int ck, int dtype, void* w_packed,
+                                 rtsds_stream_t s);
+int rtsds_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int kh, int kw,
+                            int accumulate, float* grad_oihw, rtsds_stream_t s);
+
 /* Stem convolutions read the API-boundary image directly:
  * x fp32 NCHW [n,cin,h,w] (cin <= 32), w fp32 OIHW, y NHWC of out_dtype,
  * with scale/shift/act/stats as above.  softmax_in != 0 applies a softmax
@@ -161,6 +194,31 @@ int rtsds_bn_finalize(const float* stats, double count, const float* gamma, cons
 int rtsds_scale_shift_act(const void* x, const float* scale, const float* shift,
                           const void* residual, int64_t n_pix, int c, int x_ld, int res_ld,
                           int y_ld, int act, float slope, int x_dtype, int y_dtype, void* y,
+                          rtsds_stream_t s);
+
+/* BatchNorm(+ReLU) backward (autograd of nn.BatchNorm2d in train mode).
+ *   g = dy * (relu ? y > 0 : 1);  xhat = (raw - mean) * invstd
+ * reduce: sums[c] = sum g, sums[C+c] = sum g*xhat  (zeroed by the call)
+ * apply : d_raw = gamma*invstd*(g - sums[c]/M - xhat*sums[C+c]/M); g_out = g
+ *         (optional: gradient of a residual branch); dgamma += sums[C+c],
+ *         dbeta += sums[c] (optional, accumulated). */
+int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw,
+                        int raw_ld, const float* mean, const float* invstd, int64_t n_pix, int c,
+                        int relu, int dtype, float* sums, rtsds_stream_t s);
+int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw,
+                       int raw_ld, const float* mean, const float* invstd, const float* gamma,
+                       const float* sums, int64_t n_pix, int c, int relu, int dtype, void* d_raw,
+                       int d_raw_ld, int d_raw_dtype, void* g_out, int g_ld, float* dgamma,
+                       float* dbeta, rtsds_stream_t s);
+/* out[c] += sum over pixels of x[p][c] (conv bias gradients); caller zeroes or accumulates. */
+int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, int dtype, float* out,
+                      rtsds_stream_t s);
+/* nn.MaxPool2d(3,2,1) backward: gradient goes to the first maximum of each window. */
+int rtsds_maxpool3x3s2_bwd(const void* x, const void* dy, int n, int h, int w, int c, int dtype,
+                           int ceil_mode, void* dx, rtsds_stream_t s);
+/* weight gradient of a stem conv (x NCHW fp32, d_raw NHWC [n,oh,ow,64]); dw OIHW fp32 accumulated. */
+int rtsds_stem_conv_wgrad(const float* x, const void* d_raw, int d_dtype, int n, int cin, int h,
+                          int w, int cout, int k, int stride, int pad, float* dw_oihw,
                           rtsds_stream_t s);
 
 /* ------------------------------------------------------------------------
@@ -206,6 +264,35 @@ int rtsds_ffm_head(const void* f, int f_dtype, int f_ld, const float* pooled, in
  * API-boundary logits fp32 NCHW [n,c,oh,ow] (:158-159,:166; deeplabv2.py:126). */
 int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow,
                          float* out, rtsds_stream_t s);
+
+/* Backward of the glue above.
+ * resize_bwd_nhwc: adjoint of the bilinear resize of rtsds_gate_resize_nhwc:
+ *   d_src[n,y,x,c] (fp32 dense) = sum_dst weight * d_dst[n,oy,ox,dst_coff+c];
+ *   dgate[n,c] = sum_pix d_src * src (optional; zeroed by the call).
+ * gate_bwd_finish: dx = d_gated * gate[n,c] + add[n,c]*add_scale (GAP branch).
+ * arm_gate_bwd: backward of rtsds_arm_gate in train mode; dpooled [n,c] out,
+ *   parameter gradients accumulated; dlin_ws/dmul_ws: fp32 [n,c] scratch.
+ * ffm_head_bwd: backward of rtsds_ffm_head; df [n,hw,df_ld] out, parameter
+ *   gradients accumulated; da_ws/dpooled_ws fp32 [n,c] scratch.
+ * resize_to_nchw_bwd: adjoint of rtsds_resize_to_nchw. */
+int rtsds_resize_bwd_nhwc(const void* d_dst, int dst_ld, int dst_coff, int n, int h, int w, int c,
+                          int oh, int ow, const void* src, int dtype, float* d_src, float* dgate,
+                          rtsds_stream_t s);
+int rtsds_gate_bwd_finish(const float* d_gated, const float* gate, const float* add,
+                          float add_scale, int n, int64_t hw, int c, int out_dtype, void* dx,
+                          rtsds_stream_t s);
+int rtsds_arm_gate_bwd(const float* dgate, const float* pooled, const float* lin,
+                       const float* xhat, const float* w, const float* gamma, const float* beta,
+                       const float* mul, float eps, int n, int c, float* dlin_ws, float* dmul_ws,
+                       float* dpooled, float* dw, float* dbias, float* dgamma, float* dbeta,
+                       rtsds_stream_t s);
+int rtsds_ffm_head_bwd(const float* dz, int dz_ld, const float* f, int f_ld, const float* pooled,
+                       const float* attn, int n, int64_t hw, int c, const float* w1,
+                       const float* b1, const float* w2, const float* wc, float* da_ws,
+                       float* dpooled_ws, float* df, int df_ld, float* dw1, float* db1,
+                       float* dw2, float* db2, float* dwc, float* dbc, rtsds_stream_t s);
+int rtsds_resize_to_nchw_bwd(const float* dout, int n, int c, int oh, int ow, int h, int w,
+                             float* dz, int z_ld, rtsds_stream_t s);
 
 /* ------------------------------------------------------------------------
  * Loss: bilinear resize + nn.CrossEntropyLoss(ignore_index) (main.py:124-130,

@@ -47,11 +47,28 @@ SIGNATURES = {
     "rtsds_conv2d_tc_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_simt_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rtsds_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_conv2d_tc_dgrad_workspace_bytes": (_Z, [_CD]),
+    "rtsds_conv2d_tc_dgrad": (_I, [_CD, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "rtsds_conv2d_tc_wgrad": (_I, [_CD, _P, _P, _P, _P]),
+    "rtsds_conv2d_simt_dgrad": (_I, [_CD, _P, _P, _P, _P, _I, _P]),
+    "rtsds_conv2d_simt_wgrad": (_I, [_CD, _P, _P, _P, _P]),
+    "rtsds_pack_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_unpack_conv_wgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_stem_conv_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P, _I, _P, _P]),
     "rtsds_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _I, _P, _P, _P]),
     "rtsds_bn_finalize": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rtsds_scale_shift_act": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
+    "rtsds_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _L, _I, _I, _I, _P, _P]),
+    "rtsds_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),
+    "rtsds_channel_sum": (_I, [_P, _I, _L, _I, _I, _P, _P]),
+    "rtsds_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_resize_bwd_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "rtsds_gate_bwd_finish": (_I, [_P, _P, _P, _F, _I, _L, _I, _I, _P, _P]),
+    "rtsds_arm_gate_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rtsds_ffm_head_bwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "rtsds_resize_to_nchw_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rtsds_global_avgpool": (_I, [_P, _I, _L, _I, _I, _I, _P, _P]),
     "rtsds_arm_gate": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
     "rtsds_gate_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),

@@ -1,23 +1,151 @@
-"""Train-mode BiSeNet forward/backward as one autograd node
-(reference models/bisenet/build_bisenet.py:141-172, train.py:77-95).
+"""Autograd boundary of the train-mode BiSeNet path.
 
-forward: batch-statistics BatchNorm (running buffers updated), auxiliary heads,
-returns `(result, cx1_sup, cx2_sup)` as fp32 NCHW tensors.
+`bisenet_train_forward` is what `BiSeNet.forward` calls in train mode: it returns the
+reference's `(result, cx1_sup, cx2_sup)` tuple (build_bisenet.py:169-170) as ordinary fp32 NCHW
+autograd tensors, so the stock call sites work unchanged (`criterion(out, target)`,
+`loss.backward()`, `F.softmax(out)` -> discriminator, `.detach()`, `.max(1)`; train.py:86-106,
+:199-233).  Their backward is one hand-written pass (rtsds_b200/bisenet_train.py).
+
+`bisenet_fused_ce` is the fast path for the supervised step: bilinear resize + CrossEntropyLoss
+(ignore_index) + argmax + pixel-accuracy of all three heads are evaluated from the 1/8-resolution
+logits in one kernel each, and the backward starts from there — the three [N,19,H,W] fp32 tensors
+(119 MB/image at 512x1024) and their gradients are never materialised.
 """
 from __future__ import annotations
 
 import torch
 
 from . import ops
-from .bisenet_engine import _get_plan
+from .ops import _p, check, lib
+
+
+def _get_train_plan(model, x):
+    from .bisenet_train import BiSeNetTrainPlan
+
+    plans = model.__dict__.setdefault("_rtsds_train_plans", {})
+    n, _, h, w = x.shape
+    key = (n, h, w, model.rtsds_precision, x.device.index)
+    plan = plans.get(key)
+    if plan is None:
+        plan = BiSeNetTrainPlan(model, n, h, w, model.rtsds_precision)
+        plans[key] = plan
+    return plan
+
+
+def _bump_bn_counters(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
+            m.num_batches_tracked += 1
+
+
+def _grad_tuple(plan, params, gw):
+    return tuple(None if (p in plan.unused or p not in gw) else gw[p] for p in params)
+
+
+def _allreduce(flat):
+    """Data-parallel gradient all-reduce (NCCL over NVLink) when a process group is active."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / dist.get_world_size())
+
+
+class _BiSeNetTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        plan.forward(x)
+        outs = plan.logits()
+        ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        plan = ctx.plan
+        if plan.generation != ctx.gen:
+            raise ops._lib.RtsdsError("BiSeNet backward called after another forward of the same shape reused the plan's "
+                                      "saved activations; call backward() before the next forward()")
+        s = ops._s()
+        main, aux = plan.out_sizes()
+        for i, d in enumerate(douts):
+            oh, ow = main if i == 0 else aux
+            if d is None:
+                plan.dz[i].zero_()
+            else:
+                d = d.contiguous()
+                check(lib().rtsds_resize_to_nchw_bwd(_p(d), plan.n, plan.nc, oh, ow, plan.h8, plan.w8, _p(plan.dz[i]), 32, s),
+                      "resize_to_nchw_bwd")
+        flat, gw = plan.new_grads()
+        plan.backward_from_dz(gw)
+        if getattr(plan.model, "rtsds_ddp", False):
+            _allreduce(flat)
+        return (None, None) + _grad_tuple(plan, ctx.params, gw)
 
 
 def bisenet_train_forward(model, x):
-    plan = _get_plan(model, x, True)
-    with torch.no_grad():
-        plan.forward_lowres(x, use_graph=False)
-        outs = (plan.logits(plan.z), plan.logits_aux(plan.z1), plan.logits_aux(plan.z2))
-        for m in model.modules():
-            if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                m.num_batches_tracked += 1
+    plan = _get_train_plan(model, x)
+    params = tuple(plan.params)
+    if not torch.is_grad_enabled():
+        with torch.no_grad():
+            plan.forward(x)
+            outs = tuple(plan.logits())
+    else:
+        outs = _BiSeNetTrainFn.apply(plan, x, *params)
+    _bump_bn_counters(model)
     return outs
+
+
+class _BiSeNetFusedCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, target, ignore_index, *params):
+        plan.forward(x)
+        main, aux = plan.out_sizes()
+        plan.acc.zero_()
+        pred = torch.empty((plan.n,) + main, dtype=torch.int64, device=plan.device)
+        for i, z in enumerate((plan.z, plan.z1, plan.z2)):
+            oh, ow = main if i == 0 else aux
+            ops.resize_ce_argmax_fwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, target, ignore_index, plan.acc[i],
+                                     pred if i == 0 else None)
+        per_head = (plan.acc[:, 0] / plan.acc[:, 1]).float()          # mean over valid pixels, per head
+        loss = per_head.sum()
+        ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
+        ctx.target, ctx.ignore_index = target, ignore_index
+        stats = plan.acc.clone()
+        ctx.stats = stats
+        ctx.mark_non_differentiable(pred, stats)
+        return loss, pred, stats
+
+    @staticmethod
+    def backward(ctx, dloss, _dpred, _dstats):
+        plan = ctx.plan
+        if plan.generation != ctx.gen:
+            raise ops._lib.RtsdsError("BiSeNet backward called after another forward reused the plan's saved activations")
+        main, aux = plan.out_sizes()
+        plan.gscale.copy_((dloss.double() / ctx.stats[:, 1]).float())
+        for i, z in enumerate((plan.z, plan.z1, plan.z2)):
+            oh, ow = main if i == 0 else aux
+            plan.dz[i].zero_()
+            ops.resize_ce_bwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, ctx.target, ctx.ignore_index,
+                              plan.gscale[i:i + 1], plan.dz[i])
+        flat, gw = plan.new_grads()
+        plan.backward_from_dz(gw)
+        if getattr(plan.model, "rtsds_ddp", False):
+            _allreduce(flat)
+        return (None, None, None, None) + _grad_tuple(plan, ctx.params, gw)
+
+
+def bisenet_fused_ce(model, x, target, ignore_index=255):
+    """Sum of the three heads' CrossEntropyLoss(ignore_index) (train.py:86-92) without materialising
+    the full-resolution logits.  Returns (loss, argmax of the main head [N,H,W] int64,
+    stats [3,4] float64 = per head {sum of -log p, valid pixels, pixels with argmax == target, 0})."""
+    if not model.training:
+        raise ops._lib.RtsdsError("bisenet_fused_ce is the train-mode fast path; call model.train() first")
+    if not x.is_cuda and not ops._lib.dry_run():
+        raise ops._lib.RtsdsError("bisenet_fused_ce needs CUDA tensors: rtsds_b200 has no CPU fallback")
+    x = x.float().contiguous()
+    target = target.contiguous()
+    assert target.dtype == torch.int64
+    plan = _get_train_plan(model, x)
+    out = _BiSeNetFusedCEFn.apply(plan, x, target, int(ignore_index), *plan.params)
+    _bump_bn_counters(model)
+    return out

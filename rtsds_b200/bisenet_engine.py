@@ -51,7 +51,8 @@ class BiSeNetPlan:
         self.n, self.h, self.w = n, h, w
         self.train = train
         self.precision = precision
-        self.dt = BF16 if precision == "bf16" else F32
+        self.dt = F32 if precision == "fp32" else BF16
+        self.use_tc = precision == "bf16"          # "bf16_simt": bf16 storage, CUDA-core convs (cross-check)
         self.tdt = ops.torch_dtype(self.dt)
         self.nc = model.conv.weight.shape[0]
         if model._context_name != "resnet18":
@@ -88,7 +89,7 @@ class BiSeNetPlan:
         return self.stats_all[off:off + 2 * c]
 
     def _need_ws(self, d):
-        if self.dt == BF16:
+        if self.use_tc:
             need = int(ops.lib().rtsds_conv2d_tc_workspace_bytes(d))
             self._ws_bytes = max(self._ws_bytes, need)
 
@@ -109,7 +110,7 @@ class BiSeNetPlan:
         yp = y.data_ptr() + y_off * y.element_size()
         rp = residual.data_ptr() if residual is not None else None
         self._need_ws(d)
-        use_tc = self.dt == BF16
+        use_tc = self.use_tc
         n_pix = n * d.oh * d.ow
 
         def launch(desc, scale, shift, res, stats):

@@ -1,0 +1,759 @@
+// Backward kernels of the bandwidth-bound parts of the training step (autograd of
+// models/bisenet/build_bisenet.py driven by loss.backward(), train.py:95):
+// BatchNorm(+ReLU) backward, max-pool backward, adjoint bilinear resizes, ARM and
+// FFM attention backward, per-channel sums (bias grads), stem weight gradient.
+// All HBM-bound: vectorised 16-byte accesses, register/shuffle/shared-memory
+// reductions, one global atomic per channel per block.
+#include "common.cuh"
+
+namespace rtsds {
+
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    F8 r;
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ F8 ld8(const float* p) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    F8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]); u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]); u.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void st8(float* p, const F8& r) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+static int grid_for(long long total, int threads, int waves = 8) {
+    long long want = cdiv(total, threads);
+    long long cap = static_cast<long long>(waves) * num_sms();
+    return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+// ---------------------------------------------------------------- BatchNorm(+ReLU) backward
+// g = dy * (relu ? y > 0 : 1);  sums[c] += sum g;  sums[C+c] += sum g * xhat,  xhat = (raw-mean)*invstd
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ raw,
+                     int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd, long long n_pix, int c,
+                     int relu, float* sums) {
+    extern __shared__ float sh[];             // [2*cp]
+    const int cg = (c + 7) / 8, cp = cg * 8;
+    for (int i = threadIdx.x; i < 2 * cp; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int g8 = threadIdx.x % cg;
+    const int prow = threadIdx.x / cg, prows = blockDim.x / cg;
+    float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s1[j] = 0.f; s2[j] = 0.f;
+        const int ch = g8 * 8 + j;
+        mu[j] = ch < c ? mean[ch] : 0.f; is[j] = ch < c ? invstd[ch] : 0.f;
+    }
+    if (prow < prows) {
+        for (long long p = static_cast<long long>(blockIdx.x) * prows + prow; p < n_pix; p += static_cast<long long>(gridDim.x) * prows) {
+            const F8 d = ld8(dy + p * dy_ld + g8 * 8);
+            const F8 r = ld8(raw + p * raw_ld + g8 * 8);
+            F8 yy;
+            if (relu) yy = ld8(y + p * y_ld + g8 * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = (relu && !(yy.v[j] > 0.f)) ? 0.f : d.v[j];
+                s1[j] += g;
+                s2[j] += g * (r.v[j] - mu[j]) * is[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sh[g8 * 8 + j], s1[j]);
+            atomicAdd(&sh[cp + g8 * 8 + j], s2[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        atomicAdd(&sums[i], sh[i]);
+        atomicAdd(&sums[c + i], sh[cp + i]);
+    }
+}
+
+// d_raw = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M); optional g_out = g (gradient of the residual branch).
+// Parameter gradients: dgamma += sum_gx, dbeta += sum_g (block 0).
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ raw,
+                    int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, const float* __restrict__ sums, long long n_pix, int c, int relu,
+                    TO* __restrict__ d_raw, int d_raw_ld, T* __restrict__ g_out, int g_ld, float* dgamma, float* dbeta) {
+    const int cg = (c + 7) / 8;
+    const float inv_m = 1.0f / static_cast<float>(n_pix);
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            if (dgamma) dgamma[i] += sums[c + i];
+            if (dbeta) dbeta[i] += sums[i];
+        }
+    }
+    const long long total = n_pix * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i / cg;
+        const int g8 = static_cast<int>(i - p * cg);
+        const F8 d = ld8(dy + p * dy_ld + g8 * 8);
+        const F8 r = ld8(raw + p * raw_ld + g8 * 8);
+        F8 yy;
+        if (relu) yy = ld8(y + p * y_ld + g8 * 8);
+        F8 o, gg;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = g8 * 8 + j;
+            if (ch < c) {
+                const float g = (relu && !(yy.v[j] > 0.f)) ? 0.f : d.v[j];
+                const float is = invstd[ch];
+                const float xh = (r.v[j] - mean[ch]) * is;
+                o.v[j] = (gamma ? gamma[ch] : 1.f) * is * (g - sums[ch] * inv_m - xh * sums[c + ch] * inv_m);
+                gg.v[j] = g;
+            } else { o.v[j] = 0.f; gg.v[j] = 0.f; }
+        }
+        st8(d_raw + p * d_raw_ld + g8 * 8, o);
+        if (g_out) st8(g_out + p * g_ld + g8 * 8, gg);
+    }
+}
+
+// out[c] (+)= sum over pixels of x[p][c]   (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const T* __restrict__ x, int ld, long long n_pix, int c, float* out) {
+    __shared__ float sh[8][33];
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int pl = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (ch < c)
+        for (long long p = static_cast<long long>(blockIdx.y) * 8 + pl; p < n_pix; p += static_cast<long long>(gridDim.y) * 8)
+            acc += to_f32(x[p * ld + ch]);
+    sh[pl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (pl == 0 && ch < c) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        atomicAdd(&out[ch], t);
+    }
+}
+
+// ---------------------------------------------------------------- max-pool backward (3x3, s2, p1)
+// Gather form: each input pixel collects the gradient of every window whose FIRST maximum (row-major
+// scan, as ATen's max_pool2d records it) it is.  8 channels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int n, int h, int w, int c, int oh, int ow,
+                   T* __restrict__ dx) {
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * h * w * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g8 = static_cast<int>(i % cg);
+        long long r = i / cg;
+        const int ix = static_cast<int>(r % w); r /= w;
+        const int iy = static_cast<int>(r % h);
+        const int img = static_cast<int>(r / h);
+        const T* xin = x + static_cast<long long>(img) * h * w * c + g8 * 8;
+        const F8 me = ld8(xin + (static_cast<long long>(iy) * w + ix) * c);
+        F8 acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+        // windows (oy, ox) containing (iy, ix): oy*2-1 <= iy <= oy*2+1
+        const int oy_lo = max(0, (iy) / 2), oy_hi = min(oh - 1, (iy + 1) / 2);
+        const int ox_lo = max(0, (ix) / 2), ox_hi = min(ow - 1, (ix + 1) / 2);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                // is (iy, ix) the first maximum of this window?
+                bool first[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) first[j] = true;
+                for (int dy_ = 0; dy_ < 3; ++dy_) {
+                    const int yy = oy * 2 - 1 + dy_;
+                    if (yy < 0 || yy >= h) continue;
+                    for (int dx_ = 0; dx_ < 3; ++dx_) {
+                        const int xx = ox * 2 - 1 + dx_;
+                        if (xx < 0 || xx >= w || (yy == iy && xx == ix)) continue;
+                        const F8 o = ld8(xin + (static_cast<long long>(yy) * w + xx) * c);
+                        const bool before = (yy < iy) || (yy == iy && xx < ix);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            // an earlier element wins ties (>=), a later one must be strictly greater
+                            if (before ? (o.v[j] >= me.v[j]) : (o.v[j] > me.v[j])) first[j] = false;
+                        }
+                    }
+                }
+                const F8 g = ld8(dy + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + g8 * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (first[j]) acc.v[j] += g.v[j];
+            }
+        }
+        st8(dx + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g8 * 8, acc);
+    }
+}
+
+// ---------------------------------------------------------------- adjoint bilinear resize helpers
+// candidate destination range [lo, hi] that can reference source index s (checked exactly by the caller)
+__device__ __forceinline__ void dst_range(int s, float rscale, int out_size, int* lo, int* hi) {
+    const float inv = 1.0f / rscale;
+    int a = static_cast<int>(floorf((static_cast<float>(s) - 1.0f + 0.5f) * inv - 0.5f)) - 1;
+    int b = static_cast<int>(ceilf((static_cast<float>(s) + 1.0f + 0.5f) * inv - 0.5f)) + 1;
+    *lo = a < 0 ? 0 : a;
+    *hi = b > out_size - 1 ? out_size - 1 : b;
+}
+
+// d_src[n,y,x,c] = sum over dst pixels of bilinear weight * d_dst[n,oy,ox,coff+c]   (adjoint of gate_resize
+// before the gate multiply); dgate[n,c] += sum_pix d_src * src.  8 channels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_bwd_nhwc_kernel(const T* __restrict__ d_dst, int dst_ld, int dst_coff, int n, int h, int w, int c, int oh, int ow,
+                       float rh, float rw, const T* __restrict__ src, float* __restrict__ d_src, float* dgate) {
+    extern __shared__ float sh[];     // [c] per-image partial dgate (block works on one image)
+    const int cg = c / 8;
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const long long total = static_cast<long long>(h) * w * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g8 = static_cast<int>(i % cg);
+        const long long r = i / cg;
+        const int x = static_cast<int>(r % w), y = static_cast<int>(r / w);
+        int ylo, yhi, xlo, xhi;
+        dst_range(y, rh, oh, &ylo, &yhi);
+        dst_range(x, rw, ow, &xlo, &xhi);
+        F8 acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const Lerp ly = lerp_src(oy, rh, h);
+            const float wy = (ly.i0 == y ? ly.l0 : 0.f) + (ly.i1 == y ? ly.l1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const Lerp lx = lerp_src(ox, rw, w);
+                const float wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
+                if (wx == 0.f) continue;
+                const F8 g = ld8(d_dst + ((static_cast<long long>(img) * oh + oy) * ow + ox) * dst_ld + dst_coff + g8 * 8);
+                const float wgt = wy * wx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(wgt, g.v[j], acc.v[j]);
+            }
+        }
+        const long long sp = ((static_cast<long long>(img) * h + y) * w + x) * c + g8 * 8;
+        st8(d_src + sp, acc);
+        if (dgate) {
+            const F8 s = ld8(src + sp);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sh[g8 * 8 + j], acc.v[j] * s.v[j]);
+        }
+    }
+    if (dgate) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += blockDim.x)
+            if (sh[i] != 0.f) atomicAdd(&dgate[static_cast<long long>(img) * c + i], sh[i]);
+    }
+}
+
+// dx[n,p,c] = d_gated[n,p,c] * gate[n,c] + add[n,c] * add_scale     (ARM: x*gate and the GAP branch)
+template <typename TO>
+__global__ void __launch_bounds__(256)
+gate_bwd_finish_kernel(const float* __restrict__ d_gated, const float* __restrict__ gate, const float* __restrict__ add,
+                       float add_scale, int n, long long hw, int c, TO* __restrict__ dx) {
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * hw * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g8 = static_cast<int>(i % cg);
+        const long long p = i / cg;
+        const int img = static_cast<int>(p / hw);
+        const F8 d = ld8(d_gated + p * c + g8 * 8);
+        const F8 g = ld8(gate + static_cast<long long>(img) * c + g8 * 8);
+        F8 a;
+        if (add) a = ld8(add + static_cast<long long>(img) * c + g8 * 8);
+        F8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = d.v[j] * g.v[j] + (add ? a.v[j] * add_scale : 0.f);
+        st8(dx + p * c + g8 * 8, o);
+    }
+}
+
+// ---------------------------------------------------------------- ARM backward (tiny, [N,C])
+// gate = sigmoid(gamma*xhat+beta) * mul,  xhat = BN_over_batch(lin),  lin = W pooled + b
+// phase 1 (one warp per output channel co): dgamma, dbeta, db, dlin[n,co]; d(mul) -> dpooled_direct
+// phase 2 (one thread per (n, ci)): dpooled[n,ci] = sum_co dlin[n,co] W[co,ci] (+ direct); dW[co,ci] += sum_n dlin*pooled
+constexpr int ARMB_MAX_N = 128;
+__global__ void __launch_bounds__(256)
+arm_bwd_phase1_kernel(const float* __restrict__ dgate, const float* __restrict__ lin, const float* __restrict__ xhat,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mul,
+                      float eps, int n, int c, float* dlin, float* dmul, float* dgamma, float* dbeta, float* dbias) {
+    const int co = blockIdx.x * blockDim.x + threadIdx.x;
+    if (co >= c) return;
+    const float g = gamma[co], be = beta[co];
+    float mean = 0.f;
+    for (int i = 0; i < n; ++i) mean += lin[static_cast<long long>(i) * c + co];
+    mean /= n;
+    float var = 0.f;
+    for (int i = 0; i < n; ++i) { const float d = lin[static_cast<long long>(i) * c + co] - mean; var += d * d; }
+    var /= n;
+    const float invstd = rsqrtf(var + eps);
+    float sdx = 0.f, sdxx = 0.f, sg = 0.f, sb = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const long long k = static_cast<long long>(i) * c + co;
+        const float xh = xhat[k];
+        const float s = 1.f / (1.f + expf(-(xh * g + be)));
+        const float m = mul ? mul[k] : 1.f;
+        const float dg = dgate[k];
+        if (dmul) dmul[k] = dg * s;
+        const float du = dg * m * s * (1.f - s);
+        sg += du * xh; sb += du;
+        const float dxh = du * g;
+        sdx += dxh; sdxx += dxh * xh;
+    }
+    float sl = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const long long k = static_cast<long long>(i) * c + co;
+        const float xh = xhat[k];
+        const float s = 1.f / (1.f + expf(-(xh * g + be)));
+        const float m = mul ? mul[k] : 1.f;
+        const float dxh = dgate[k] * m * s * (1.f - s) * g;
+        const float dl = invstd * (dxh - sdx / n - xh * sdxx / n);
+        dlin[k] = dl;
+        sl += dl;
+    }
+    if (dgamma) dgamma[co] += sg;
+    if (dbeta) dbeta[co] += sb;
+    if (dbias) dbias[co] += sl;
+}
+
+__global__ void __launch_bounds__(256)
+arm_bwd_phase2_kernel(const float* __restrict__ dlin, const float* __restrict__ w, const float* __restrict__ pooled,
+                      const float* __restrict__ dmul, int n, int c, float* dpooled, float* dw) {
+    // blockIdx.y = 0..n-1: dpooled rows;  blockIdx.y = n: dW (one thread per (co, ci) strip)
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= c) return;
+    if (static_cast<int>(blockIdx.y) < n) {
+        const int i = blockIdx.y;
+        float acc = dmul ? dmul[static_cast<long long>(i) * c + ci] : 0.f;
+        for (int co = 0; co < c; ++co) acc = fmaf(dlin[static_cast<long long>(i) * c + co], w[static_cast<long long>(co) * c + ci], acc);
+        dpooled[static_cast<long long>(i) * c + ci] = acc;
+    } else if (dw) {
+        for (int co = 0; co < c; ++co) {
+            float acc = 0.f;
+            for (int i = 0; i < n; ++i) acc = fmaf(dlin[static_cast<long long>(i) * c + co], pooled[static_cast<long long>(i) * c + ci], acc);
+            dw[static_cast<long long>(co) * c + ci] += acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- FFM head backward
+// forward: a = sigmoid(W2 relu(W1 p + b1) + b2), g = f*(1+a), z = Wc g + bc (Wc NULL: z = g)
+// pass 1 (per pixel): dg = Wc^T dz;  da_raw[n,c] += dg*f;  dWc += dz (x) g;  dbc += dz
+constexpr int FB_MAXC = 32;
+__global__ void __launch_bounds__(128)
+ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ f, int f_ld,
+                          const float* __restrict__ attn, const float* __restrict__ wc, long long hw, int c,
+                          float* da_raw, float* dwc, float* dbc) {
+    __shared__ float s_w[FB_MAXC * FB_MAXC];
+    __shared__ float s_da[FB_MAXC], s_db[FB_MAXC], s_dw[FB_MAXC * FB_MAXC];
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) { s_w[i] = wc ? wc[i] : 0.f; s_dw[i] = 0.f; }
+    if (threadIdx.x < FB_MAXC) { s_da[threadIdx.x] = 0.f; s_db[threadIdx.x] = 0.f; }
+    __syncthreads();
+    float da[FB_MAXC];
+#pragma unroll
+    for (int k = 0; k < FB_MAXC; ++k) da[k] = 0.f;
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < hw;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float* dzp = dz + (static_cast<long long>(img) * hw + p) * dz_ld;
+        const float* fp = f + (static_cast<long long>(img) * hw + p) * f_ld;
+        float dzv[FB_MAXC], fv[FB_MAXC];
+#pragma unroll
+        for (int k = 0; k < FB_MAXC; ++k) { dzv[k] = k < c ? dzp[k] : 0.f; fv[k] = k < c ? fp[k] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < FB_MAXC; ++k) {
+            if (k < c) {
+                float dg = 0.f;
+                if (wc) { for (int o = 0; o < c; ++o) dg = fmaf(s_w[o * c + k], dzv[o], dg); } else dg = dzv[k];
+                da[k] += dg * fv[k];
+            }
+        }
+        if (wc) {
+            for (int o = 0; o < c; ++o) {
+                atomicAdd(&s_db[o], dzv[o]);
+#pragma unroll
+                for (int k = 0; k < FB_MAXC; ++k)
+                    if (k < c) atomicAdd(&s_dw[o * c + k], dzv[o] * fv[k] * (1.f + attn[static_cast<long long>(img) * c + k]));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < FB_MAXC; ++k)
+        if (k < c) atomicAdd(&s_da[k], da[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        atomicAdd(&da_raw[static_cast<long long>(img) * c + i], s_da[i]);
+        if (wc && dbc) atomicAdd(&dbc[i], s_db[i]);
+    }
+    if (wc && dwc)
+        for (int i = threadIdx.x; i < c * c; i += blockDim.x) atomicAdd(&dwc[i], s_dw[i]);
+}
+
+// pass 2 (one block per image, tiny): attention MLP backward -> dpooled[n,c] and parameter grads
+__global__ void __launch_bounds__(64)
+ffm_head_bwd_pass2_kernel(const float* __restrict__ da_raw, const float* __restrict__ pooled, const float* __restrict__ attn,
+                          const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2, int c,
+                          float* dpooled, float* dw1, float* db1, float* dw2, float* db2) {
+    __shared__ float s_h[FB_MAXC], s_dv[FB_MAXC], s_dh[FB_MAXC];
+    const int img = blockIdx.x, t = threadIdx.x;
+    const float* pp = pooled + static_cast<long long>(img) * c;
+    if (t < c) {
+        float acc = b1[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(w1[t * c + k], pp[k], acc);
+        s_h[t] = acc;                                        // pre-ReLU
+        const float a = attn[static_cast<long long>(img) * c + t];
+        s_dv[t] = da_raw[static_cast<long long>(img) * c + t] * a * (1.f - a);    // grad at conv2 output
+    }
+    __syncthreads();
+    if (t < c) {
+        float acc = 0.f;
+        for (int o = 0; o < c; ++o) acc = fmaf(w2[o * c + t], s_dv[o], acc);
+        s_dh[t] = s_h[t] > 0.f ? acc : 0.f;                  // grad at conv1 output (through ReLU)
+        atomicAdd(&db2[t], s_dv[t]);
+        for (int k = 0; k < c; ++k) atomicAdd(&dw2[t * c + k], s_dv[t] * fmaxf(s_h[k], 0.f));
+    }
+    __syncthreads();
+    if (t < c) {
+        float acc = 0.f;
+        for (int o = 0; o < c; ++o) acc = fmaf(w1[o * c + t], s_dh[o], acc);
+        dpooled[static_cast<long long>(img) * c + t] = acc;
+        atomicAdd(&db1[t], s_dh[t]);
+        for (int k = 0; k < c; ++k) atomicAdd(&dw1[t * c + k], s_dh[t] * pp[k]);
+    }
+}
+
+// pass 3 (per pixel): df = (Wc^T dz)*(1+a) + dpooled/hw
+__global__ void __launch_bounds__(128)
+ffm_head_bwd_pass3_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ attn,
+                          const float* __restrict__ wc, const float* __restrict__ dpooled, long long hw, int c,
+                          float* __restrict__ df, int df_ld) {
+    __shared__ float s_w[FB_MAXC * FB_MAXC], s_a[FB_MAXC], s_dp[FB_MAXC];
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) s_w[i] = wc ? wc[i] : 0.f;
+    if (threadIdx.x < c) {
+        s_a[threadIdx.x] = 1.f + attn[static_cast<long long>(img) * c + threadIdx.x];
+        s_dp[threadIdx.x] = dpooled[static_cast<long long>(img) * c + threadIdx.x] / static_cast<float>(hw);
+    }
+    __syncthreads();
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < hw;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float* dzp = dz + (static_cast<long long>(img) * hw + p) * dz_ld;
+        float dzv[FB_MAXC];
+#pragma unroll
+        for (int k = 0; k < FB_MAXC; ++k) dzv[k] = k < c ? dzp[k] : 0.f;
+        float* o = df + (static_cast<long long>(img) * hw + p) * df_ld;
+#pragma unroll
+        for (int k = 0; k < FB_MAXC; ++k) {
+            if (k < c) {
+                float dg = 0.f;
+                if (wc) { for (int q = 0; q < c; ++q) dg = fmaf(s_w[q * c + k], dzv[q], dg); } else dg = dzv[k];
+                o[k] = dg * s_a[k] + s_dp[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- adjoint of resize_to_nchw
+// dz[n,y,x,c] = sum over output pixels of bilinear weight * dout[n,c,oy,ox]; one thread per (n,y,x,c)
+__global__ void __launch_bounds__(256)
+resize_nchw_bwd_kernel(const float* __restrict__ dout, int n, int c, int oh, int ow, int h, int w, float rh, float rw,
+                       float* __restrict__ dz, int z_ld) {
+    const long long total = static_cast<long long>(n) * h * w * c;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // x fastest so that neighbouring threads read neighbouring dout columns
+        const int x = static_cast<int>(i % w);
+        long long r = i / w;
+        const int y = static_cast<int>(r % h); r /= h;
+        const int ch = static_cast<int>(r % c);
+        const int img = static_cast<int>(r / c);
+        int ylo, yhi, xlo, xhi;
+        dst_range(y, rh, oh, &ylo, &yhi);
+        dst_range(x, rw, ow, &xlo, &xhi);
+        const float* plane = dout + (static_cast<long long>(img) * c + ch) * oh * ow;
+        float acc = 0.f;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const Lerp ly = lerp_src(oy, rh, h);
+            const float wy = (ly.i0 == y ? ly.l0 : 0.f) + (ly.i1 == y ? ly.l1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const Lerp lx = lerp_src(ox, rw, w);
+                const float wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
+                if (wx != 0.f) acc = fmaf(wy * wx, __ldg(plane + static_cast<long long>(oy) * ow + ox), acc);
+            }
+        }
+        dz[((static_cast<long long>(img) * h + y) * w + x) * z_ld + ch] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- stem weight gradient
+// dw[co][ci][r][s] += sum_{n,oy,ox} d_raw[n,oy,ox,co] * x[n,ci,oy*2-pad+r,ox*2-pad+s]   (x NCHW fp32, d_raw NHWC)
+// block = one (ci, r) pair and a slab of output rows; thread = (co 0..63, s-group); shared-memory staged rows.
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ d_raw, int n, int cin, int h, int w, int oh, int ow,
+                  int pad, int rows_per_block, float* __restrict__ dw) {
+    constexpr int TW = 64;                       // output columns per smem tile
+    __shared__ float s_x[TW * 2 + K];            // input row segment
+    __shared__ float s_d[TW][65];                // d_raw tile [ox][co]
+    const int ci = blockIdx.y / K, r = blockIdx.y % K;
+    const int img = blockIdx.z;
+    const int oy0 = blockIdx.x * rows_per_block;
+    const int co = threadIdx.x & 63, sg = threadIdx.x >> 6;      // 4 s-groups
+    float acc[(K + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (K + 3) / 4; ++i) acc[i] = 0.f;
+    for (int oy = oy0; oy < min(oy0 + rows_per_block, oh); ++oy) {
+        const int iy = oy * 2 - pad + r;
+        if (iy < 0 || iy >= h) continue;         // uniform across the block
+        const float* xrow = x + ((static_cast<long long>(img) * cin + ci) * h + iy) * w;
+        for (int ox0 = 0; ox0 < ow; ox0 += TW) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < TW * 2 + K; i += 256) {
+                const int ix = ox0 * 2 - pad + i;
+                s_x[i] = (ix >= 0 && ix < w) ? xrow[ix] : 0.f;
+            }
+            for (int i = threadIdx.x; i < TW * 64; i += 256) {
+                const int o = i >> 6, c = i & 63;
+                s_d[o][c] = (ox0 + o < ow) ? to_f32(d_raw[((static_cast<long long>(img) * oh + oy) * ow + ox0 + o) * 64 + c]) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < (K + 3) / 4; ++i) {
+                const int s = sg + i * 4;
+                if (s < K) {
+                    float a = 0.f;
+#pragma unroll 8
+                    for (int o = 0; o < TW; ++o) a = fmaf(s_d[o][co], s_x[o * 2 + s], a);
+                    acc[i] += a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < (K + 3) / 4; ++i) {
+        const int s = sg + i * 4;
+        if (s < K && acc[i] != 0.f) atomicAdd(&dw[((static_cast<long long>(co) * cin + ci) * K + r) * K + s], acc[i]);
+    }
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+#define DISPATCH_T(dtype, CALL_BF16, CALL_F32, name)                       \
+    do {                                                                   \
+        if ((dtype) == RTSDS_BF16) { CALL_BF16; }                          \
+        else if ((dtype) == RTSDS_F32) { CALL_F32; }                       \
+        else { set_error(name ": bad dtype"); return RTSDS_EINVAL; }       \
+    } while (0)
+
+extern "C" int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                                   const float* mean, const float* invstd, int64_t n_pix, int c, int relu, int dtype,
+                                   float* sums, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dy && raw && mean && invstd && sums && n_pix > 0 && c > 0, "bn_bwd_reduce: bad argument");
+    RTSDS_REQUIRE(!relu || y, "bn_bwd_reduce: y required for the ReLU mask");
+    RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && (!relu || y_ld % 8 == 0), "bn_bwd_reduce: pitches must be multiples of 8");
+    const int cg = (c + 7) / 8;
+    RTSDS_REQUIRE(cg <= 256 && dy_ld >= cg * 8 && raw_ld >= cg * 8, "bn_bwd_reduce: channel count / pitch");
+    cudaStream_t st = as_stream(s);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st);
+    if (e != cudaSuccess) { set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+    const int prows = 256 / cg;
+    const int grid = grid_for(n_pix, prows, 4);
+    const size_t sm = sizeof(float) * 2 * cg * 8;
+    DISPATCH_T(dtype,
+               (bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(
+                   reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
+                   reinterpret_cast<const __nv_bfloat16*>(raw), raw_ld, mean, invstd, n_pix, c, relu, sums)),
+               (bn_bwd_reduce_kernel<float><<<grid, 256, sm, st>>>(
+                   reinterpret_cast<const float*>(dy), dy_ld, reinterpret_cast<const float*>(y), y_ld,
+                   reinterpret_cast<const float*>(raw), raw_ld, mean, invstd, n_pix, c, relu, sums)),
+               "bn_bwd_reduce");
+    count_launch();
+    return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
+                                  int64_t n_pix, int c, int relu, int dtype, void* d_raw, int d_raw_ld, int d_raw_dtype,
+                                  void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dy && raw && mean && invstd && sums && d_raw && n_pix > 0 && c > 0, "bn_bwd_apply: bad argument");
+    RTSDS_REQUIRE(!relu || y, "bn_bwd_apply: y required for the ReLU mask");
+    const int cg = (c + 7) / 8;
+    RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && d_raw_ld % 8 == 0 && d_raw_ld >= cg * 8, "bn_bwd_apply: pitches must be multiples of 8");
+    RTSDS_REQUIRE(!g_out || (g_ld % 8 == 0 && g_ld >= cg * 8), "bn_bwd_apply: g_out pitch");
+    cudaStream_t st = as_stream(s);
+    const int grid = grid_for(n_pix * cg, 256);
+#define BN_APPLY(T, TO)                                                                                                  \
+    bn_bwd_apply_kernel<T, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(dy), dy_ld, reinterpret_cast<const T*>(y), \
+                                                     y_ld, reinterpret_cast<const T*>(raw), raw_ld, mean, invstd, gamma,   \
+                                                     sums, n_pix, c, relu, reinterpret_cast<TO*>(d_raw), d_raw_ld,         \
+                                                     reinterpret_cast<T*>(g_out), g_ld, dgamma, dbeta)
+    if (dtype == RTSDS_BF16 && d_raw_dtype == RTSDS_BF16) BN_APPLY(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == RTSDS_F32 && d_raw_dtype == RTSDS_F32) BN_APPLY(float, float);
+    else if (dtype == RTSDS_F32 && d_raw_dtype == RTSDS_BF16) BN_APPLY(float, __nv_bfloat16);
+    else { set_error("bn_bwd_apply: unsupported dtype combination"); return RTSDS_EINVAL; }
+#undef BN_APPLY
+    count_launch();
+    return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, int dtype, float* out, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && out && n_pix > 0 && c > 0 && ld >= c, "channel_sum: bad argument");
+    long long py = cdiv(n_pix, 8 * 32);
+    const long long cap = cdiv(4LL * num_sms(), cdiv(c, 32));
+    if (py > cap) py = cap;
+    if (py < 1) py = 1;
+    dim3 grid(static_cast<unsigned>(cdiv(c, 32)), static_cast<unsigned>(py));
+    DISPATCH_T(dtype, (channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, n_pix, c, out)),
+               (channel_sum_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, n_pix, c, out)), "channel_sum");
+    count_launch();
+    return check_launch("channel_sum_kernel");
+}
+
+extern "C" int rtsds_maxpool3x3s2_bwd(const void* x, const void* dy, int n, int h, int w, int c, int dtype, int ceil_mode,
+                                      void* dx, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool_bwd: bad argument");
+    auto osz = [&](int in) {
+        int o = ceil_mode ? in / 2 + 1 : (in - 1) / 2 + 1;
+        if (ceil_mode && (o - 1) * 2 >= in + 1) --o;
+        return o;
+    };
+    const int oh = osz(h), ow = osz(w);
+    const int grid = grid_for(static_cast<long long>(n) * h * w * (c / 8), 256);
+    DISPATCH_T(dtype,
+               (maxpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), n, h, w, c, oh, ow, reinterpret_cast<__nv_bfloat16*>(dx))),
+               (maxpool_bwd_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy), n, h, w, c, oh, ow, reinterpret_cast<float*>(dx))),
+               "maxpool_bwd");
+    count_launch();
+    return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int rtsds_resize_bwd_nhwc(const void* d_dst, int dst_ld, int dst_coff, int n, int h, int w, int c, int oh, int ow,
+                                     const void* src, int dtype, float* d_src, float* dgate, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d_dst && d_src && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && oh > 0 && ow > 0, "resize_bwd_nhwc: bad argument");
+    RTSDS_REQUIRE(dst_ld % 8 == 0 && dst_coff % 8 == 0 && (!dgate || src), "resize_bwd_nhwc: layout");
+    cudaStream_t st = as_stream(s);
+    if (dgate) {
+        cudaError_t e = cudaMemsetAsync(dgate, 0, sizeof(float) * n * c, st);
+        if (e != cudaSuccess) { set_error("resize_bwd_nhwc: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+    }
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    long long bx = cdiv(static_cast<long long>(h) * w * (c / 8), 256);
+    const long long cap = cdiv(8LL * num_sms(), n);
+    if (bx > cap) bx = cap;
+    dim3 grid(static_cast<unsigned>(bx), n);
+    const size_t sm = sizeof(float) * c;
+    DISPATCH_T(dtype,
+               (resize_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const __nv_bfloat16*>(src), d_src, dgate)),
+               (resize_bwd_nhwc_kernel<float><<<grid, 256, sm, st>>>(reinterpret_cast<const float*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const float*>(src), d_src, dgate)),
+               "resize_bwd_nhwc");
+    count_launch();
+    return check_launch("resize_bwd_nhwc_kernel");
+}
+
+extern "C" int rtsds_gate_bwd_finish(const float* d_gated, const float* gate, const float* add, float add_scale, int n,
+                                     int64_t hw, int c, int out_dtype, void* dx, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d_gated && gate && dx && n > 0 && hw > 0 && c > 0 && c % 8 == 0, "gate_bwd_finish: bad argument");
+    const int grid = grid_for(static_cast<long long>(n) * hw * (c / 8), 256);
+    DISPATCH_T(out_dtype,
+               (gate_bwd_finish_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(d_gated, gate, add, add_scale, n, hw, c, reinterpret_cast<__nv_bfloat16*>(dx))),
+               (gate_bwd_finish_kernel<float><<<grid, 256, 0, as_stream(s)>>>(d_gated, gate, add, add_scale, n, hw, c, reinterpret_cast<float*>(dx))),
+               "gate_bwd_finish");
+    count_launch();
+    return check_launch("gate_bwd_finish_kernel");
+}
+
+extern "C" int rtsds_arm_gate_bwd(const float* dgate, const float* pooled, const float* lin, const float* xhat,
+                                  const float* w, const float* gamma, const float* beta, const float* mul, float eps, int n,
+                                  int c, float* dlin_ws, float* dmul_ws, float* dpooled, float* dw, float* dbias,
+                                  float* dgamma, float* dbeta, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dgate && pooled && lin && xhat && w && gamma && beta && dlin_ws && dpooled, "arm_gate_bwd: NULL argument");
+    RTSDS_REQUIRE(n >= 2 && c > 0, "arm_gate_bwd: needs N >= 2");
+    RTSDS_REQUIRE(!mul || dmul_ws, "arm_gate_bwd: dmul workspace required when mul is given");
+    cudaStream_t st = as_stream(s);
+    arm_bwd_phase1_kernel<<<static_cast<int>(cdiv(c, 128)), 128, 0, st>>>(dgate, lin, xhat, gamma, beta, mul, eps, n, c, dlin_ws,
+                                                                      mul ? dmul_ws : nullptr, dgamma, dbeta, dbias);
+    dim3 grid(static_cast<unsigned>(cdiv(c, 128)), n + 1);
+    arm_bwd_phase2_kernel<<<grid, 128, 0, st>>>(dlin_ws, w, pooled, mul ? dmul_ws : nullptr, n, c, dpooled, dw);
+    count_launch(2);
+    return check_launch("arm_bwd kernels");
+}
+
+extern "C" int rtsds_ffm_head_bwd(const float* dz, int dz_ld, const float* f, int f_ld, const float* pooled,
+                                  const float* attn, int n, int64_t hw, int c, const float* w1, const float* b1,
+                                  const float* w2, const float* wc, float* da_ws, float* dpooled_ws, float* df, int df_ld,
+                                  float* dw1, float* db1, float* dw2, float* db2, float* dwc, float* dbc, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dz && f && pooled && attn && w1 && b1 && w2 && da_ws && dpooled_ws && df, "ffm_head_bwd: NULL argument");
+    RTSDS_REQUIRE(dw1 && db1 && dw2 && db2, "ffm_head_bwd: gradient buffers required");
+    RTSDS_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= FB_MAXC && dz_ld >= c && f_ld >= c && df_ld >= c, "ffm_head_bwd: bad shape");
+    cudaStream_t st = as_stream(s);
+    cudaError_t e = cudaMemsetAsync(da_ws, 0, sizeof(float) * n * c, st);
+    if (e != cudaSuccess) { set_error("ffm_head_bwd: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+    long long bx = cdiv(hw, 128);
+    const long long cap = cdiv(2LL * num_sms(), n);
+    if (bx > cap) bx = cap;
+    dim3 grid(static_cast<unsigned>(bx), n);
+    ffm_head_bwd_pass1_kernel<<<grid, 128, 0, st>>>(dz, dz_ld, f, f_ld, attn, wc, hw, c, da_ws, dwc, dbc);
+    ffm_head_bwd_pass2_kernel<<<n, 64, 0, st>>>(da_ws, pooled, attn, w1, b1, w2, c, dpooled_ws, dw1, db1, dw2, db2);
+    long long bx3 = cdiv(hw, 128);
+    const long long cap3 = cdiv(8LL * num_sms(), n);
+    if (bx3 > cap3) bx3 = cap3;
+    dim3 grid3(static_cast<unsigned>(bx3), n);
+    ffm_head_bwd_pass3_kernel<<<grid3, 128, 0, st>>>(dz, dz_ld, attn, wc, dpooled_ws, hw, c, df, df_ld);
+    count_launch(3);
+    return check_launch("ffm_head_bwd kernels");
+}
+
+extern "C" int rtsds_resize_to_nchw_bwd(const float* dout, int n, int c, int oh, int ow, int h, int w, float* dz, int z_ld,
+                                        rtsds_stream_t s) {
+    RTSDS_REQUIRE(dout && dz && n > 0 && c > 0 && oh > 0 && ow > 0 && h > 0 && w > 0 && z_ld >= c, "resize_to_nchw_bwd: bad argument");
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    const int grid = grid_for(static_cast<long long>(n) * h * w * c, 256);
+    resize_nchw_bwd_kernel<<<grid, 256, 0, as_stream(s)>>>(dout, n, c, oh, ow, h, w, rh, rw, dz, z_ld);
+    count_launch();
+    return check_launch("resize_nchw_bwd_kernel");
+}
+
+extern "C" int rtsds_stem_conv_wgrad(const float* x, const void* d_raw, int d_dtype, int n, int cin, int h, int w, int cout,
+                                     int k, int stride, int pad, float* dw_oihw, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && d_raw && dw_oihw, "stem_conv_wgrad: NULL argument");
+    RTSDS_REQUIRE(cout == 64 && stride == 2 && cin >= 1 && cin <= 32, "stem_conv_wgrad: unsupported geometry");
+    const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+    int rpb = static_cast<int>(cdiv(static_cast<long long>(oh) * n * cin * k, 4LL * num_sms()));
+    if (rpb < 1) rpb = 1;
+    dim3 grid(static_cast<unsigned>(cdiv(oh, rpb)), cin * k, n);
+    cudaStream_t st = as_stream(s);
+#define STEM_WG(T, KK) stem_wgrad_kernel<T, KK><<<grid, 256, 0, st>>>(x, reinterpret_cast<const T*>(d_raw), n, cin, h, w, oh, ow, pad, rpb, dw_oihw)
+    if (d_dtype == RTSDS_BF16) {
+        if (k == 3) STEM_WG(__nv_bfloat16, 3); else if (k == 4) STEM_WG(__nv_bfloat16, 4); else if (k == 7) STEM_WG(__nv_bfloat16, 7);
+        else { set_error("stem_conv_wgrad: k=%d unsupported", k); return RTSDS_EUNSUP; }
+    } else if (d_dtype == RTSDS_F32) {
+        if (k == 3) STEM_WG(float, 3); else if (k == 4) STEM_WG(float, 4); else if (k == 7) STEM_WG(float, 7);
+        else { set_error("stem_conv_wgrad: k=%d unsupported", k); return RTSDS_EUNSUP; }
+    } else { set_error("stem_conv_wgrad: bad dtype"); return RTSDS_EINVAL; }
+#undef STEM_WG
+    count_launch();
+    return check_launch("stem_wgrad_kernel");
+}

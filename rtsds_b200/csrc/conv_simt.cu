@@ -1,37 +1,27 @@
-// CUDA-core implicit-GEMM convolution with fp32 accumulation.
+// CUDA-core implicit-GEMM convolution (forward, dgrad, wgrad) with fp32 accumulation.
 //
 // This is the "fp32 check mode" of BASELINE.json (logits within 1e-4 of the
 // reference) and, instantiated for bf16 tensors, an independent cross-check of
-// the tcgen05 kernel (same operands, different machinery).  It accepts any
+// the tcgen05 kernels (same operands, different machinery).  It accepts any
 // cin / filter / stride / dilation.  Not the production path for bf16.
 //
-// Tiling: 64 output pixels x 64 output channels per 256-thread block, 4x4
+// Forward and dgrad run the same kernel on a TapProblem (tap_problem.cuh);
+// tiling: 64 output pixels x 64 output channels per 256-thread block, 4x4
 // register tile per thread, K walked as (tap, 16-channel chunk) through shared
-// memory.
+// memory.  Also here: the weight repacking kernels shared with the tensor-core path.
 #include "common.cuh"
+#include "tap_problem.cuh"
 
 namespace rtsds {
 
 constexpr int SC_TM = 64, SC_TN = 64, SC_TK = 16, SC_THREADS = 256;
 
-struct SimtParams {
-    int n, h, w, cin, in_ld;
-    int cout, cout_pad, out_ld, res_ld;
-    int kh, kw, stride, pad, dil, oh, ow;
-    int act;
-    float slope;
-    int out_dtype;
-    long long m_total;
-};
-
 template <typename T>
 __global__ void __launch_bounds__(SC_THREADS)
-conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wgt, const float* __restrict__ scale,
-                 const float* __restrict__ shift, const void* __restrict__ residual, float* stats, void* y,
-                 SimtParams p) {
+tap_simt_kernel(const TapProblem p, long long m_total) {
     __shared__ float sA[SC_TK][SC_TM + 4];
     __shared__ float sB[SC_TK][SC_TN + 4];
-    __shared__ int s_img[SC_TM], s_ih0[SC_TM], s_iw0[SC_TM];
+    __shared__ int s_img[SC_TM], s_oy[SC_TM], s_ox[SC_TM];
     __shared__ float s_sum[SC_TN], s_sq[SC_TN];
 
     const int tid = threadIdx.x;
@@ -41,13 +31,13 @@ conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wgt, const float
 
     if (tid < SC_TM) {
         long long m = m0 + tid;
-        if (m < p.m_total) {
+        if (m < m_total) {
             int img = static_cast<int>(m / (static_cast<long long>(p.oh) * p.ow));
             long long r = m - static_cast<long long>(img) * p.oh * p.ow;
-            int oy = static_cast<int>(r / p.ow), ox = static_cast<int>(r - static_cast<long long>(oy) * p.ow);
-            s_img[tid] = img; s_ih0[tid] = oy * p.stride - p.pad; s_iw0[tid] = ox * p.stride - p.pad;
+            int oy = static_cast<int>(r / p.ow);
+            s_img[tid] = img; s_oy[tid] = oy; s_ox[tid] = static_cast<int>(r - static_cast<long long>(oy) * p.ow);
         } else {
-            s_img[tid] = -1; s_ih0[tid] = 0; s_iw0[tid] = 0;
+            s_img[tid] = -1; s_oy[tid] = 0; s_ox[tid] = 0;
         }
         s_sum[tid] = 0.f; s_sq[tid] = 0.f;
     }
@@ -59,26 +49,26 @@ conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wgt, const float
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    const int taps = p.kh * p.kw;
-    const long long wrow = static_cast<long long>(taps) * p.cin;   // elements per output channel
-    const int a_pix = tid >> 2, a_k = (tid & 3) * 4;                // A loader: pixel, 4 channels
-    const int b_co = tid >> 2, b_k = (tid & 3) * 4;                 // B loader: out channel, 4 k
+    const T* wgt = reinterpret_cast<const T*>(p.w);
+    const int a_pix = tid >> 2, a_k = (tid & 3) * 4;
+    const int b_co = tid >> 2, b_k = (tid & 3) * 4;
+    const int cout_pad = (p.cout <= 32) ? 32 : (p.cout <= 64 ? 64 : (p.cout + 127) / 128 * 128);
 
-    for (int t = 0; t < taps; ++t) {
-        const int r = t / p.kw, q = t - r * p.kw;
+    for (int t = 0; t < p.n_taps; ++t) {
+        const TapView& v = p.view[p.map[t]];
         const int img = s_img[a_pix];
-        const int ih = s_ih0[a_pix] + r * p.dil, iw = s_iw0[a_pix] + q * p.dil;
-        const bool inb = img >= 0 && ih >= 0 && ih < p.h && iw >= 0 && iw < p.w;
-        const T* xp = inb ? x + ((static_cast<long long>(img) * p.h + ih) * p.w + iw) * p.in_ld : nullptr;
+        const int iy = s_oy[a_pix] + p.dh[t], ix = s_ox[a_pix] + p.dw[t];
+        const bool inb = img >= 0 && iy >= 0 && iy < v.hd && ix >= 0 && ix < v.wd;
+        const T* xp = inb ? reinterpret_cast<const T*>(v.base) + img * v.sn + iy * v.sh + ix * v.sw : nullptr;
         const int co = n0 + b_co;
-        const T* wp = (co < p.cout_pad) ? wgt + co * wrow + static_cast<long long>(t) * p.cin : nullptr;
-        for (int c0 = 0; c0 < p.cin; c0 += SC_TK) {
+        const T* wp = (co < cout_pad) ? wgt + co * p.w_ktot + static_cast<long long>(p.kb[t]) : nullptr;
+        for (int c0 = 0; c0 < p.ck; c0 += SC_TK) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = c0 + a_k + j;
-                sA[a_k + j][a_pix] = (xp && c < p.cin) ? to_f32(xp[c]) : 0.f;
+                sA[a_k + j][a_pix] = (xp && c < p.c_extent) ? to_f32(xp[c]) : 0.f;
                 const int cb = c0 + b_k + j;
-                sB[b_k + j][b_co] = (wp && cb < p.cin) ? to_f32(wp[cb]) : 0.f;
+                sB[b_k + j][b_co] = (wp && cb < p.ck) ? to_f32(wp[cb]) : 0.f;
             }
             __syncthreads();
 #pragma unroll
@@ -95,29 +85,30 @@ conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wgt, const float
         }
     }
 
-    // epilogue
     float cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const long long m = m0 + ty * 4 + i;
-        if (m >= p.m_total) continue;
+        const int mi = ty * 4 + i;
+        if (m0 + mi >= m_total) continue;
+        const long long ooff = s_img[mi] * p.out_sn + s_oy[mi] * p.out_sh + s_ox[mi] * p.out_sw;
+        const long long roff = s_img[mi] * p.res_sn + s_oy[mi] * p.res_sh + s_ox[mi] * p.res_sw;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int co = n0 + tx * 4 + j;
             if (co >= p.cout) continue;
             float raw = acc[i][j];
             cs[j] += raw; cq[j] += raw * raw;
-            float v = raw * (scale ? scale[co] : 1.f) + (shift ? shift[co] : 0.f);
+            float v = raw * (p.scale ? p.scale[co] : 1.f) + (p.shift ? p.shift[co] : 0.f);
             if (p.out_dtype == RTSDS_BF16) {
-                if (residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[m * p.res_ld + co]);
-                reinterpret_cast<__nv_bfloat16*>(y)[m * p.out_ld + co] = __float2bfloat16_rn(apply_act(v, p.act, p.slope));
+                if (p.residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[roff + co]);
+                reinterpret_cast<__nv_bfloat16*>(p.y)[ooff + co] = __float2bfloat16_rn(apply_act(v, p.act, p.slope));
             } else {
-                if (residual) v += reinterpret_cast<const float*>(residual)[m * p.res_ld + co];
-                reinterpret_cast<float*>(y)[m * p.out_ld + co] = apply_act(v, p.act, p.slope);
+                if (p.residual) v += reinterpret_cast<const float*>(p.residual)[roff + co];
+                reinterpret_cast<float*>(p.y)[ooff + co] = apply_act(v, p.act, p.slope);
             }
         }
     }
-    if (stats) {
+    if (p.stats) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             atomicAdd(&s_sum[tx * 4 + j], cs[j]);
@@ -125,8 +116,87 @@ conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wgt, const float
         }
         __syncthreads();
         if (tid < SC_TN && n0 + tid < p.cout) {
-            atomicAdd(&stats[n0 + tid], s_sum[tid]);
-            atomicAdd(&stats[p.cout + n0 + tid], s_sq[tid]);
+            atomicAdd(&p.stats[n0 + tid], s_sum[tid]);
+            atomicAdd(&p.stats[p.cout + n0 + tid], s_sq[tid]);
+        }
+    }
+}
+
+// wgrad: dw[co][t][ci] += sum_pixels dy[pix][co] * x[pix shifted by tap t][ci]
+// grid (ceil(cout/64), ceil(cin/64) * n_taps, pixel splits); fp32 atomics into dw.
+struct WgradSimt {
+    TapView xview[4];
+    const void* dy; long long dy_ld;
+    int n_img, oh, ow, cin, cout, n_taps;
+    signed char dh[TAP_MAX], dw[TAP_MAX], map[TAP_MAX];
+    float* out;
+    long long pix_per_split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SC_THREADS)
+wgrad_simt_kernel(const WgradSimt p) {
+    __shared__ float sA[SC_TK][SC_TM + 4];      // [pixel][co]
+    __shared__ float sB[SC_TK][SC_TN + 4];      // [pixel][ci]
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int co0 = blockIdx.x * SC_TM;
+    const int ci_tiles = (p.cin + SC_TN - 1) / SC_TN;
+    const int t = blockIdx.y / ci_tiles;
+    const int ci0 = (blockIdx.y - t * ci_tiles) * SC_TN;
+    const long long m_total = static_cast<long long>(p.n_img) * p.oh * p.ow;
+    const long long m_begin = p.pix_per_split * blockIdx.z;
+    const long long m_end = (m_begin + p.pix_per_split < m_total) ? m_begin + p.pix_per_split : m_total;
+    const TapView& v = p.xview[p.map[t]];
+    const T* dy = reinterpret_cast<const T*>(p.dy);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int l_pix = tid >> 4, l_c = (tid & 15) * 4;     // 16 pixels x 64 channels per load step
+    for (long long m0 = m_begin; m0 < m_end; m0 += SC_TK) {
+        const long long m = m0 + l_pix;
+        const T* ap = nullptr;
+        const T* bp = nullptr;
+        if (m < m_end) {
+            const int img = static_cast<int>(m / (static_cast<long long>(p.oh) * p.ow));
+            const long long r = m - static_cast<long long>(img) * p.oh * p.ow;
+            const int oy = static_cast<int>(r / p.ow), ox = static_cast<int>(r - static_cast<long long>(oy) * p.ow);
+            ap = dy + m * p.dy_ld;
+            const int iy = oy + p.dh[t], ix = ox + p.dw[t];
+            if (iy >= 0 && iy < v.hd && ix >= 0 && ix < v.wd)
+                bp = reinterpret_cast<const T*>(v.base) + img * v.sn + iy * v.sh + ix * v.sw;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + l_c + j, ci = ci0 + l_c + j;
+            sA[l_pix][l_c + j] = (ap && co < p.cout) ? to_f32(ap[co]) : 0.f;
+            sB[l_pix][l_c + j] = (bp && ci < p.cin) ? to_f32(bp[ci]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SC_TK; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= p.cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + tx * 4 + j;
+            if (ci < p.cin) atomicAdd(&p.out[(static_cast<long long>(co) * p.n_taps + t) * p.cin + ci], acc[i][j]);
         }
     }
 }
@@ -147,7 +217,48 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     }
 }
 
+// OIHW fp32 -> dgrad operand [cin_pad][kh*kw][ck] (ck >= cout, zero padded): out[ci][t][co] = w[co][ci][t]
+template <typename T>
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cin_pad, int ck,
+                                         T* __restrict__ out) {
+    const long long total = static_cast<long long>(cin_pad) * taps * ck;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % ck);
+        const long long r = i / ck;
+        const int t = static_cast<int>(r % taps);
+        const int ci = static_cast<int>(r / taps);
+        float v = (co < cout && ci < cin) ? w[(static_cast<long long>(co) * cin + ci) * taps + t] : 0.f;
+        out[i] = from_f32<T>(v);
+    }
+}
+
+// wgrad result [cout][taps][cin] fp32 -> OIHW fp32 gradient (assign or accumulate)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int cout, int cin, int taps, int accumulate,
+                                    float* __restrict__ grad) {
+    const long long total = static_cast<long long>(cout) * cin * taps;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % taps);
+        const long long r = i / taps;
+        const int ci = static_cast<int>(r % cin);
+        const int co = static_cast<int>(r / cin);
+        const float v = dw[(static_cast<long long>(co) * taps + t) * cin + ci];
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+
 int conv_cout_pad(int cout);
+
+static int simt_run(const TapProblem& t, int in_dtype, cudaStream_t st) {
+    const long long m_total = static_cast<long long>(t.n_img) * t.oh * t.ow;
+    if (m_total == 0) return RTSDS_OK;
+    dim3 grid(static_cast<unsigned>(cdiv(m_total, SC_TM)), static_cast<unsigned>(cdiv(t.cout, SC_TN)));
+    if (in_dtype == RTSDS_BF16) tap_simt_kernel<__nv_bfloat16><<<grid, SC_THREADS, 0, st>>>(t, m_total);
+    else tap_simt_kernel<float><<<grid, SC_THREADS, 0, st>>>(t, m_total);
+    count_launch();
+    return check_launch("tap_simt_kernel");
+}
 
 }  // namespace rtsds
 
@@ -159,31 +270,66 @@ extern "C" int rtsds_conv2d_simt_fwd(const RtsdsConvDesc* d, const void* x, cons
     RTSDS_REQUIRE(d && x && w && y, "conv2d_simt_fwd: NULL argument");
     RTSDS_REQUIRE(d->in_dtype == RTSDS_BF16 || d->in_dtype == RTSDS_F32, "conv2d_simt_fwd: bad in_dtype");
     RTSDS_REQUIRE(d->out_dtype == RTSDS_BF16 || d->out_dtype == RTSDS_F32, "conv2d_simt_fwd: bad out_dtype");
-    RTSDS_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv2d_simt_fwd: empty tensor");
-    RTSDS_REQUIRE(d->stride >= 1 && d->dil >= 1 && d->pad >= 0 && d->kh >= 1 && d->kw >= 1, "conv2d_simt_fwd: bad geometry");
-    const int exp_oh = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
-    const int exp_ow = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
-    RTSDS_REQUIRE(d->oh == exp_oh && d->ow == exp_ow, "conv2d_simt_fwd: oh/ow (%d,%d) != expected (%d,%d)", d->oh, d->ow, exp_oh, exp_ow);
-    RTSDS_REQUIRE(d->in_ld >= d->cin && d->out_ld >= d->cout, "conv2d_simt_fwd: pitch smaller than channel count");
+    RTSDS_REQUIRE(d->out_ld >= d->cout, "conv2d_simt_fwd: pitch smaller than channel count");
     if (residual) RTSDS_REQUIRE(d->res_ld >= d->cout, "conv2d_simt_fwd: res_ld < cout");
     int rc = rtsds_check_device();
     if (rc != RTSDS_OK) return rc;
-    SimtParams p;
-    p.n = d->n; p.h = d->h; p.w = d->w; p.cin = d->cin; p.in_ld = d->in_ld;
-    p.cout = d->cout; p.cout_pad = conv_cout_pad(d->cout); p.out_ld = d->out_ld; p.res_ld = d->res_ld;
-    p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.oh = d->oh; p.ow = d->ow;
-    p.act = d->act; p.slope = d->slope; p.out_dtype = d->out_dtype;
-    p.m_total = static_cast<long long>(d->n) * d->oh * d->ow;
-    dim3 grid(static_cast<unsigned>(cdiv(p.m_total, SC_TM)), static_cast<unsigned>(cdiv(d->cout, SC_TN)));
-    if (d->in_dtype == RTSDS_BF16)
-        conv_simt_kernel<__nv_bfloat16><<<grid, SC_THREADS, 0, as_stream(s)>>>(
-            reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w), scale, shift,
-            residual, stats, y, p);
-    else
-        conv_simt_kernel<float><<<grid, SC_THREADS, 0, as_stream(s)>>>(
-            reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w), scale, shift, residual, stats, y, p);
+    TapProblem t;
+    rc = fwd_problem(d, x, w, 1, d->in_dtype == RTSDS_BF16 ? 2 : 4, &t);
+    if (rc != RTSDS_OK) return rc;
+    t.scale = scale; t.shift = shift; t.residual = residual; t.stats = stats; t.y = y;
+    return simt_run(t, d->in_dtype, as_stream(s));
+}
+
+// dgrad on CUDA cores; dy dtype = d->in_dtype (pitch d->out_ld), w_dgrad [cin_pad][taps][cout] of the same dtype.
+extern "C" int rtsds_conv2d_simt_dgrad(const RtsdsConvDesc* d, const void* dy, const void* w_dgrad, const void* residual,
+                                       void* dx, int dx_dtype, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && dy && w_dgrad && dx, "conv2d_simt_dgrad: NULL argument");
+    RTSDS_REQUIRE(d->stride == 1 || d->stride == 2, "conv2d_simt_dgrad: stride %d unsupported", d->stride);
+    RTSDS_REQUIRE(d->out_ld >= d->cout && d->in_ld >= d->cin, "conv2d_simt_dgrad: pitch");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    for (int ph = 0; ph < d->stride; ++ph)
+        for (int pw = 0; pw < d->stride; ++pw) {
+            TapProblem t;
+            rc = dgrad_problem(d, dy, w_dgrad, residual, dx, dx_dtype, ph, pw, 1, d->in_dtype == RTSDS_BF16 ? 2 : 4, &t);
+            if (rc != RTSDS_OK) return rc;
+            if (t.oh <= 0 || t.ow <= 0) continue;
+            rc = simt_run(t, d->in_dtype, as_stream(s));
+            if (rc != RTSDS_OK) return rc;
+        }
+    return RTSDS_OK;
+}
+
+// wgrad on CUDA cores: dw_packed fp32 [cout][taps][cin] is ACCUMULATED into (caller zeroes).
+extern "C" int rtsds_conv2d_simt_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy, float* dw_packed,
+                                       rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && x && dy && dw_packed, "conv2d_simt_wgrad: NULL argument");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    TapProblem t;
+    rc = fwd_problem(d, x, nullptr, 1, d->in_dtype == RTSDS_BF16 ? 2 : 4, &t);
+    if (rc != RTSDS_OK) return rc;
+    WgradSimt p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 4; ++i) p.xview[i] = t.view[i];
+    p.dy = dy; p.dy_ld = d->out_ld;
+    p.n_img = d->n; p.oh = d->oh; p.ow = d->ow; p.cin = d->cin; p.cout = d->cout; p.n_taps = t.n_taps;
+    for (int i = 0; i < t.n_taps; ++i) { p.dh[i] = t.dh[i]; p.dw[i] = t.dw[i]; p.map[i] = t.map[i]; }
+    p.out = dw_packed;
+    const long long m_total = static_cast<long long>(d->n) * d->oh * d->ow;
+    const int base = static_cast<int>(cdiv(d->cout, SC_TM) * cdiv(d->cin, SC_TN) * t.n_taps);
+    long long splits = cdiv(4LL * num_sms(), base);
+    if (splits > cdiv(m_total, 256)) splits = cdiv(m_total, 256);
+    if (splits < 1) splits = 1;
+    p.pix_per_split = cdiv(cdiv(m_total, splits), SC_TK) * SC_TK;
+    splits = cdiv(m_total, p.pix_per_split);
+    dim3 grid(static_cast<unsigned>(cdiv(d->cout, SC_TM)), static_cast<unsigned>(cdiv(d->cin, SC_TN) * t.n_taps),
+              static_cast<unsigned>(splits));
+    if (d->in_dtype == RTSDS_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, SC_THREADS, 0, as_stream(s)>>>(p);
+    else wgrad_simt_kernel<float><<<grid, SC_THREADS, 0, as_stream(s)>>>(p);
     count_launch();
-    return check_launch("conv_simt_kernel");
+    return check_launch("wgrad_simt_kernel");
 }
 
 extern "C" int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cout_pad,
@@ -201,4 +347,31 @@ extern "C" int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, in
                                                                  reinterpret_cast<float*>(w_packed));
     count_launch();
     return check_launch("pack_weight_kernel");
+}
+
+extern "C" int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, int cin_pad, int ck,
+                                            int dtype, void* w_packed, rtsds_stream_t s) {
+    RTSDS_REQUIRE(w_oihw && w_packed, "pack_conv_weight_dgrad: NULL argument");
+    RTSDS_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cin_pad >= cin && ck >= cout, "pack_conv_weight_dgrad: bad shape");
+    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "pack_conv_weight_dgrad: bad dtype");
+    const long long total = static_cast<long long>(cin_pad) * kh * kw * ck;
+    int grid = static_cast<int>(cdiv(total, 256) > 2048 ? 2048 : cdiv(total, 256));
+    if (dtype == RTSDS_BF16)
+        pack_weight_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, kh * kw, cin_pad, ck,
+                                                                               reinterpret_cast<__nv_bfloat16*>(w_packed));
+    else
+        pack_weight_dgrad_kernel<float><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, kh * kw, cin_pad, ck,
+                                                                       reinterpret_cast<float*>(w_packed));
+    count_launch();
+    return check_launch("pack_weight_dgrad_kernel");
+}
+
+extern "C" int rtsds_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int kh, int kw, int accumulate,
+                                       float* grad_oihw, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dw_packed && grad_oihw && cout > 0 && cin > 0 && kh > 0 && kw > 0, "unpack_conv_wgrad: bad argument");
+    const long long total = static_cast<long long>(cout) * cin * kh * kw;
+    int grid = static_cast<int>(cdiv(total, 256) > 2048 ? 2048 : cdiv(total, 256));
+    unpack_wgrad_kernel<<<grid, 256, 0, as_stream(s)>>>(dw_packed, cout, cin, kh * kw, accumulate, grad_oihw);
+    count_launch();
+    return check_launch("unpack_wgrad_kernel");
 }

@@ -30,6 +30,7 @@
 //     fixed order (deterministic) and applies the epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tap_problem.cuh"
 #include <mutex>
 #include <cstring>
 
@@ -39,7 +40,6 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;              // bf16 elements = 128 B = one swizzle atom
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KiB
 constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_TAPS = 16;
 
 struct TcMaps {
     CUtensorMap a[4];   // activation views (one per input parity for stride 2)
@@ -53,7 +53,8 @@ struct TcParams {
     int n_taps, kchunks;          // k-blocks = n_taps * kchunks
     int stages;
     int split_k;
-    signed char tap_dh[TC_MAX_TAPS], tap_dw[TC_MAX_TAPS], tap_map[TC_MAX_TAPS];
+    signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
+    short tap_kb[TAP_MAX];            // first weight k-block of each tap
     long long out_sn, out_sh, out_sw;     // element strides of y
     long long res_sn, res_sh, res_sw;     // element strides of residual
     const float* scale;
@@ -119,8 +120,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
     // ---- one-time setup ----
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&maps.b);
-        ptx::prefetch_tmap(&maps.a[0]);
+        if (p.n_taps > 0) {
+            ptx::prefetch_tmap(&maps.b);
+            ptx::prefetch_tmap(&maps.a[0]);
+        }
         for (int i = 0; i < stages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -159,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                                  &maps.a[p.tap_map[tap]], &full_bar[stage], cc * TC_BLOCK_K,
                                  w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
                 ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
-                                 kb * TC_BLOCK_K, n0);
+                                 (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -183,7 +186,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 ptx::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(tmem_full_bar);              // accumulator complete
+            if (kb_end > kb_begin) ptx::umma_commit(tmem_full_bar);   // accumulator complete
         }
         __syncwarp();
     } else {
@@ -194,8 +197,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int oh = h0 + hl;
         const int ow = w0 + (row - hl * p.tile_w);
         const bool valid = (oh < p.oh) && (ow < p.ow);
-        ptx::mbar_wait(tmem_full_bar, 0);
-        ptx::tc_fence_after();
+        const bool have_acc = kb_end > kb_begin;     // a tap-less problem (e.g. odd pixels of a 1x1 s2 dgrad) is all zeros
+        if (have_acc) {
+            ptx::mbar_wait(tmem_full_bar, 0);
+            ptx::tc_fence_after();
+        }
 
         const long long m_total = static_cast<long long>(p.n_img) * p.oh * p.ow;
         const long long pix_lin = (static_cast<long long>(img) * p.oh + oh) * p.ow + ow;
@@ -205,8 +211,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
             uint32_t r[32];
-            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-            ptx::tmem_ld_wait();
+            if (have_acc) {
+                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+                ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -496,14 +507,13 @@ static int tc_auto_split(long long ctas, int kb_total) {
     return split;
 }
 
-// block_n / split-K selection shared by the launcher and the workspace query
-static void tc_plan(const RtsdsConvDesc* d, int* block_n, int* split, int* tile_w, int* tile_h) {
-    pick_tile(d->oh, d->ow, tile_w, tile_h);
-    const long long m_tiles = static_cast<long long>(d->n) * cdiv(d->ow, *tile_w) * cdiv(d->oh, *tile_h);
-    const int cp = conv_cout_pad(d->cout);
+static void tp_plan(const TapProblem& t, int* block_n, int* split, int* tile_w, int* tile_h) {
+    pick_tile(t.oh, t.ow, tile_w, tile_h);
+    const long long m_tiles = static_cast<long long>(t.n_img) * cdiv(t.ow, *tile_w) * cdiv(t.oh, *tile_h);
+    const int cp = conv_cout_pad(t.cout);
     *block_n = tc_pick_block_n(cp, m_tiles);
-    const int kb_total = d->kh * d->kw * (d->cin / TC_BLOCK_K);
-    int sp = d->split_k;
+    const int kb_total = t.n_taps * (t.ck / TC_BLOCK_K);
+    int sp = t.split_req;
     if (sp <= 0) sp = tc_auto_split(m_tiles * (cp / *block_n), kb_total);
     if (sp > kb_total) sp = kb_total;
     if (sp > 16) sp = 16;
@@ -511,12 +521,91 @@ static void tc_plan(const RtsdsConvDesc* d, int* block_n, int* split, int* tile_
     *split = sp;
 }
 
-extern "C" size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d) {
-    if (!d || d->cin <= 0 || d->cin % TC_BLOCK_K) return 0;
+static size_t tp_workspace(const TapProblem& t) {
     int bn, sp, tw, th;
-    tc_plan(d, &bn, &sp, &tw, &th);
+    tp_plan(t, &bn, &sp, &tw, &th);
     if (sp <= 1) return 0;
-    return static_cast<size_t>(sp) * d->n * d->oh * d->ow * conv_cout_pad(d->cout) * sizeof(float);
+    return static_cast<size_t>(sp) * t.n_img * t.oh * t.ow * conv_cout_pad(t.cout) * sizeof(float);
+}
+
+static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    TcMaps maps;
+    TcParams p;
+    memset(&maps, 0, sizeof(maps));
+    memset(&p, 0, sizeof(p));
+    int block_n, split;
+    tp_plan(t, &block_n, &split, &p.tile_w, &p.tile_h);
+    p.n_img = t.n_img; p.oh = t.oh; p.ow = t.ow;
+    p.tiles_w = static_cast<int>(cdiv(t.ow, p.tile_w));
+    p.tiles_h = static_cast<int>(cdiv(t.oh, p.tile_h));
+    p.cout = t.cout; p.cout_pad = conv_cout_pad(t.cout);
+    p.n_taps = t.n_taps; p.kchunks = t.ck / TC_BLOCK_K;
+    p.out_sn = t.out_sn; p.out_sh = t.out_sh; p.out_sw = t.out_sw;
+    p.res_sn = t.res_sn; p.res_sh = t.res_sh; p.res_sw = t.res_sw;
+    p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.y = t.y;
+    p.out_dtype = t.out_dtype; p.act = t.act; p.slope = t.slope;
+    int first_used = -1;
+    for (int i = 0; i < 4; ++i) {
+        if (!t.view[i].used) continue;
+        int rc = make_act_map(&maps.a[i], t.view[i].base, t.c_extent, t.view[i].wd, t.view[i].hd, t.n_img, t.view[i].sw,
+                              t.view[i].sh, t.view[i].sn, p.tile_w, p.tile_h);
+        if (rc != RTSDS_OK) return rc;
+        if (first_used < 0) first_used = i;
+    }
+    if (first_used < 0 && t.n_taps > 0) { set_error("conv_tc: no activation view"); return RTSDS_EINVAL; }
+    for (int i = 0; i < 4; ++i)
+        if (!t.view[i].used && first_used >= 0) maps.a[i] = maps.a[first_used];
+    for (int i = 0; i < t.n_taps; ++i) { p.tap_dh[i] = t.dh[i]; p.tap_dw[i] = t.dw[i]; p.tap_map[i] = t.map[i]; p.tap_kb[i] = static_cast<short>(t.kb[i]); }
+    if (t.n_taps > 0) {
+        int rc = make_weight_map(&maps.b, t.w, t.w_ktot, p.cout_pad, block_n);
+        if (rc != RTSDS_OK) return rc;
+    }
+    const long long m_tiles = static_cast<long long>(t.n_img) * p.tiles_w * p.tiles_h;
+    const int n_tiles = p.cout_pad / block_n;
+    const int kb_total = p.n_taps * p.kchunks;
+    p.split_k = split;
+    const long long m_total = static_cast<long long>(t.n_img) * t.oh * t.ow;
+    if (split > 1) {
+        const size_t need = static_cast<size_t>(split) * m_total * p.cout_pad * sizeof(float);
+        if (!workspace || ws_bytes < need) {
+            set_error("conv_tc: split_k=%d needs %zu workspace bytes, got %zu", split, need, ws_bytes);
+            return RTSDS_EWS;
+        }
+        RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv_tc: workspace alignment");
+        p.partial = reinterpret_cast<float*>(workspace);
+    }
+    // stages: keep two CTAs resident per SM (epilogue of one overlaps the main loop of the other)
+    int stages = g_force_stages ? g_force_stages : (block_n == 128 ? 3 : (block_n == 64 ? 4 : 5));
+    const int kb_per = kb_total / split;
+    if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
+    while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
+    p.stages = stages;
+    RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv_tc: too many tiles");
+
+    dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
+    int rc;
+    if (block_n == 128) rc = launch_tc<128>(maps, p, grid, stream);
+    else if (block_n == 64) rc = launch_tc<64>(maps, p, grid, stream);
+    else if (block_n == 32) rc = launch_tc<32>(maps, p, grid, stream);
+    else { set_error("conv_tc: block_n %d", block_n); return RTSDS_EUNSUP; }
+    if (rc != RTSDS_OK) return rc;
+    if (split > 1) {
+        const long long total = m_total * (p.cout_pad / 4);
+        long long want = cdiv(total, 256);
+        int g = static_cast<int>(want > 4LL * num_sms() ? 4LL * num_sms() : want);
+        size_t sm = t.stats ? 2 * static_cast<size_t>(t.cout) * sizeof(float) : 0;
+        splitk_finish_kernel<<<g, 256, sm, stream>>>(p.partial, split, m_total, t.cout, p.cout_pad, t.oh, t.ow, p);
+        count_launch();
+        rc = check_launch("splitk_finish_kernel");
+    }
+    return rc;
+}
+
+extern "C" size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d) {
+    if (!d) return 0;
+    TapProblem t;
+    if (fwd_problem(d, nullptr, nullptr, TC_BLOCK_K, 2, &t) != RTSDS_OK) return 0;
+    return tp_workspace(t);
 }
 
 extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w, const float* scale,
@@ -525,15 +614,6 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
     RTSDS_REQUIRE(d && x && w && y, "conv2d_tc_fwd: NULL argument");
     RTSDS_REQUIRE(d->in_dtype == RTSDS_BF16, "conv2d_tc_fwd: input must be bf16");
     RTSDS_REQUIRE(d->out_dtype == RTSDS_BF16 || d->out_dtype == RTSDS_F32, "conv2d_tc_fwd: bad out_dtype");
-    RTSDS_REQUIRE(d->cin > 0 && d->cin % TC_BLOCK_K == 0, "conv2d_tc_fwd: cin=%d must be a multiple of 64", d->cin);
-    RTSDS_REQUIRE(d->stride == 1 || d->stride == 2, "conv2d_tc_fwd: stride %d unsupported", d->stride);
-    RTSDS_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= TC_MAX_TAPS, "conv2d_tc_fwd: %dx%d filter unsupported", d->kh, d->kw);
-    RTSDS_REQUIRE(d->dil >= 1 && d->pad >= 0, "conv2d_tc_fwd: bad dil/pad");
-    RTSDS_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->cout > 0, "conv2d_tc_fwd: empty tensor");
-    const int exp_oh = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
-    const int exp_ow = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
-    RTSDS_REQUIRE(d->oh == exp_oh && d->ow == exp_ow, "conv2d_tc_fwd: oh/ow (%d,%d) != expected (%d,%d)", d->oh, d->ow, exp_oh, exp_ow);
-    RTSDS_REQUIRE(d->in_ld >= d->cin && d->in_ld % 8 == 0, "conv2d_tc_fwd: in_ld=%d must be >= cin and a multiple of 8", d->in_ld);
     RTSDS_REQUIRE(d->out_ld >= d->cout, "conv2d_tc_fwd: out_ld < cout");
     RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv2d_tc_fwd: pointers must be 16-byte aligned");
@@ -545,99 +625,257 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
     }
     int rc = rtsds_check_device();
     if (rc != RTSDS_OK) return rc;
+    TapProblem t;
+    rc = fwd_problem(d, x, w, TC_BLOCK_K, 2, &t);
+    if (rc != RTSDS_OK) return rc;
+    t.scale = scale; t.shift = shift; t.residual = residual; t.stats = stats; t.y = y;
+    return tp_run(t, workspace, ws_bytes, as_stream(s));
+}
 
-    TcMaps maps;
-    TcParams p;
-    memset(&maps, 0, sizeof(maps));
-    memset(&p, 0, sizeof(p));
-    p.n_img = d->n; p.oh = d->oh; p.ow = d->ow;
-    int plan_bn, plan_split;
-    tc_plan(d, &plan_bn, &plan_split, &p.tile_w, &p.tile_h);
-    p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
-    p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
-    p.cout = d->cout;
-    p.cout_pad = conv_cout_pad(d->cout);
-    p.n_taps = d->kh * d->kw;
-    p.kchunks = d->cin / TC_BLOCK_K;
-    p.out_sw = d->out_ld; p.out_sh = static_cast<long long>(d->ow) * d->out_ld; p.out_sn = p.out_sh * d->oh;
-    p.res_sw = d->res_ld; p.res_sh = static_cast<long long>(d->ow) * d->res_ld; p.res_sn = p.res_sh * d->oh;
-    p.scale = scale; p.shift = shift; p.residual = residual; p.stats = stats; p.y = y;
-    p.out_dtype = d->out_dtype; p.act = d->act; p.slope = d->slope;
+extern "C" size_t rtsds_conv2d_tc_dgrad_workspace_bytes(const RtsdsConvDesc* d) {
+    if (!d || (d->stride != 1 && d->stride != 2)) return 0;
+    size_t m = 0;
+    for (int ph = 0; ph < d->stride; ++ph)
+        for (int pw = 0; pw < d->stride; ++pw) {
+            TapProblem t;
+            if (dgrad_problem(d, nullptr, nullptr, nullptr, nullptr, RTSDS_BF16, ph, pw, TC_BLOCK_K, 2, &t) != RTSDS_OK) return 0;
+            if (t.oh <= 0 || t.ow <= 0 || t.n_taps == 0) continue;
+            size_t b = tp_workspace(t);
+            if (b > m) m = b;
+        }
+    return m;
+}
 
-    // activation maps + tap table
-    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-    const long long ld = d->in_ld;
-    const int st = d->stride;
-    bool have_map[4] = {false, false, false, false};
-    for (int r = 0; r < d->kh; ++r) {
-        for (int q = 0; q < d->kw; ++q) {
-            const int t = r * d->kw + q;
-            const int a = r * d->dil - d->pad, b = q * d->dil - d->pad;
-            const int hp = ((a % st) + st) % st, wp = ((b % st) + st) % st;
-            const int dh = (a - hp) / st, dw = (b - wp) / st;
-            RTSDS_REQUIRE(dh >= -128 && dh <= 127 && dw >= -128 && dw <= 127, "conv2d_tc_fwd: tap offset out of range");
-            const int mi = hp * 2 + wp;
-            p.tap_dh[t] = static_cast<signed char>(dh);
-            p.tap_dw[t] = static_cast<signed char>(dw);
-            p.tap_map[t] = static_cast<signed char>(mi);
-            if (!have_map[mi]) {
-                const int hd = (d->h - hp + st - 1) / st, wd = (d->w - wp + st - 1) / st;
-                RTSDS_REQUIRE(hd > 0 && wd > 0, "conv2d_tc_fwd: degenerate parity view");
-                rc = make_act_map(&maps.a[mi], xb + (static_cast<long long>(hp) * d->w + wp) * ld, d->cin, wd, hd, d->n,
-                                  st * ld, static_cast<long long>(st) * d->w * ld, static_cast<long long>(d->h) * d->w * ld,
-                                  p.tile_w, p.tile_h);
-                if (rc != RTSDS_OK) return rc;
-                have_map[mi] = true;
+extern "C" int rtsds_conv2d_tc_dgrad(const RtsdsConvDesc* d, const void* dy, const void* w_dgrad, const void* residual,
+                                     void* dx, int dx_dtype, void* workspace, size_t ws_bytes, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && dy && w_dgrad && dx, "conv2d_tc_dgrad: NULL argument");
+    RTSDS_REQUIRE(d->stride == 1 || d->stride == 2, "conv2d_tc_dgrad: stride %d unsupported", d->stride);
+    RTSDS_REQUIRE(d->kh * d->kw <= TAP_MAX, "conv2d_tc_dgrad: filter too large");
+    const int ck = static_cast<int>(cdiv(d->cout, TC_BLOCK_K) * TC_BLOCK_K);
+    RTSDS_REQUIRE(d->out_ld >= ck && d->out_ld % 8 == 0, "conv2d_tc_dgrad: dy pitch %d must be >= %d (cout rounded up to 64, zero padded)", d->out_ld, ck);
+    RTSDS_REQUIRE(dx_dtype == RTSDS_BF16 || dx_dtype == RTSDS_F32, "conv2d_tc_dgrad: bad dx dtype");
+    const int vec = dx_dtype == RTSDS_BF16 ? 8 : 4;
+    RTSDS_REQUIRE(d->in_ld >= d->cin && d->in_ld % vec == 0, "conv2d_tc_dgrad: dx pitch");
+    RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(w_dgrad) & 15) == 0, "conv2d_tc_dgrad: pointers must be 16-byte aligned");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    for (int ph = 0; ph < d->stride; ++ph)
+        for (int pw = 0; pw < d->stride; ++pw) {
+            TapProblem t;
+            rc = dgrad_problem(d, dy, w_dgrad, residual, dx, dx_dtype, ph, pw, TC_BLOCK_K, 2, &t);
+            if (rc != RTSDS_OK) return rc;
+            if (t.oh <= 0 || t.ow <= 0) continue;
+            rc = tp_run(t, workspace, ws_bytes, as_stream(s));
+            if (rc != RTSDS_OK) return rc;
+        }
+    return RTSDS_OK;
+}
+
+// =====================================================================================
+// wgrad on tensor cores: dW[co][tap][ci] = sum_pixels dy[pix][co] * x[pix shifted by tap][ci]
+//
+// GEMM view per (tap, 128-wide co tile, ci tile): D[M = co, N = ci] += A[M, K = 16 pixels] * B[N, K]^T with
+// K running over the pixels of 128-pixel tiles.  Both operands are "MN-major": in NHWC the channel
+// (M or N) index is the contiguous one.  A TMA box [64 ch, tile_w, tile_h, 1] lands as 128 pixel rows
+// of 128 B with the 128-byte swizzle, which is exactly the canonical MN-major SWIZZLE_128B UMMA
+// operand (8-pixel groups 1024 B apart = SBO; further 64-channel chunks one box apart = LBO).
+// The pixel range is split over CTAs; partial results are accumulated into the fp32 dW with
+// red.global.add (dW is a few MB at most).
+// =====================================================================================
+namespace rtsds {
+
+constexpr int WG_BOX_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;    // [128 pixels][64 channels] bf16 = 16 KiB
+
+struct WgMaps {
+    CUtensorMap a;        // dy  [ck, ow, oh, n]
+    CUtensorMap b[4];     // x parity views [cin, wd, hd, n]
+};
+
+struct WgParams {
+    int n_img, oh, ow, tile_w, tile_h, tiles_w, tiles_h;
+    int cout, cin, n_taps, ci_tiles;
+    int tiles_total, tiles_per_split;
+    int stages;
+    signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
+    float* dw;
+};
+
+template <int BLOCK_N>     // ci per CTA: 64 or 128
+__global__ void __launch_bounds__(TC_THREADS)
+wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
+    constexpr int A_BYTES = 2 * WG_BOX_BYTES;                  // 128 co = two 64-channel boxes
+    constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N, 1, 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(stages) * B_BYTES);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tmem_full_bar = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.y / p.ci_tiles;
+    const int ci0 = (blockIdx.y - tap * p.ci_tiles) * BLOCK_N;
+    const int co0 = blockIdx.z * TC_BLOCK_M;
+    const int t_begin = blockIdx.x * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&maps.a);
+        ptx::prefetch_tmap(&maps.b[p.tap_map[tap]]);
+        for (int i = 0; i < stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, BLOCK_N); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const CUtensorMap* bm = &maps.b[p.tap_map[tap]];
+            for (int t = t_begin; t < t_end; ++t) {
+                const int img = t / tiles_per_img;
+                const int r = t - img * tiles_per_img;
+                const int th = r / p.tiles_w;
+                const int h0 = th * p.tile_h, w0 = (r - th * p.tiles_w) * p.tile_w;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_BYTES;
+                uint8_t* sb = smem_b + static_cast<size_t>(stage) * B_BYTES;
+                ptx::tma_load_4d(sa, &maps.a, &full_bar[stage], co0, w0, h0, img);
+                ptx::tma_load_4d(sa + WG_BOX_BYTES, &maps.a, &full_bar[stage], co0 + 64, w0, h0, img);
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                    ptx::tma_load_4d(sb + j * WG_BOX_BYTES, bm, &full_bar[stage], ci0 + j * 64, w0 + p.tap_dw[tap],
+                                     h0 + p.tap_dh[tap], img);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem_a + static_cast<size_t>(stage) * A_BYTES);
+                const uint32_t sb = ptx::smem_u32(smem_b + static_cast<size_t>(stage) * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_M / 16; ++k) {      // 16 pixels (rows) per MMA = 2048 B
+                    const uint64_t da = ptx::umma_desc_mn_sw128(sa + k * 2048, WG_BOX_BYTES);
+                    const uint64_t db = ptx::umma_desc_mn_sw128(sb + k * 2048, WG_BOX_BYTES);
+                    ptx::umma_bf16(tmem_base, da, db, IDESC, (t > t_begin || k > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            if (t_end > t_begin) ptx::umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else if (t_end > t_begin) {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_wait();
+            if (co < p.cout) {
+                float* dst = p.dw + (static_cast<long long>(co) * p.n_taps + tap) * p.cin + ci0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (ci0 + c0 + j < p.cin) atomicAdd(dst + j, __uint_as_float(r[j]));
             }
         }
     }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, BLOCK_N); }
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const WgMaps& maps, const WgParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (2 + BLOCK_N / 64) * WG_BOX_BYTES + (2 * p.stages + 1) * 8 + 16;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        done = true;
+    }
+    wgrad_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    count_launch();
+    return check_launch("wgrad_tc_kernel");
+}
+
+}  // namespace rtsds
+
+// x: NHWC bf16 (pitch d->in_ld), dy: NHWC bf16 (pitch d->out_ld, a multiple of 8; channels >= cout read as zero
+// via TMA bounds), dw_packed: fp32 [cout][kh*kw][cin], ACCUMULATED into (caller zeroes it).
+extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy, float* dw_packed,
+                                     rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && x && dy && dw_packed, "conv2d_tc_wgrad: NULL argument");
+    RTSDS_REQUIRE(d->in_dtype == RTSDS_BF16, "conv2d_tc_wgrad: operands must be bf16");
+    RTSDS_REQUIRE(d->out_ld % 8 == 0 && d->out_ld >= d->cout, "conv2d_tc_wgrad: dy pitch must be a multiple of 8");
+    RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv2d_tc_wgrad: alignment");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    TapProblem t;
+    rc = fwd_problem(d, x, nullptr, TC_BLOCK_K, 2, &t);
+    if (rc != RTSDS_OK) return rc;
+    WgMaps maps;
+    WgParams p;
+    memset(&maps, 0, sizeof(maps));
+    memset(&p, 0, sizeof(p));
+    pick_tile(d->oh, d->ow, &p.tile_w, &p.tile_h);
+    p.n_img = d->n; p.oh = d->oh; p.ow = d->ow;
+    p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
+    p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
+    p.cout = d->cout; p.cin = d->cin; p.n_taps = t.n_taps;
+    const int block_n = d->cin >= 128 ? 128 : 64;
+    p.ci_tiles = static_cast<int>(cdiv(d->cin, block_n));
+    const long long tiles_total = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
+    RTSDS_REQUIRE(tiles_total < (1LL << 30), "conv2d_tc_wgrad: too many tiles");
+    p.tiles_total = static_cast<int>(tiles_total);
+    const int co_tiles = static_cast<int>(cdiv(d->cout, TC_BLOCK_M));
+    const long long base = static_cast<long long>(t.n_taps) * p.ci_tiles * co_tiles;
+    long long splits = cdiv(2LL * num_sms(), base);
+    if (splits > tiles_total) splits = tiles_total;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = static_cast<int>(cdiv(tiles_total, splits));
+    splits = cdiv(tiles_total, p.tiles_per_split);
+    for (int i = 0; i < t.n_taps; ++i) { p.tap_dh[i] = t.dh[i]; p.tap_dw[i] = t.dw[i]; p.tap_map[i] = t.map[i]; }
+    p.dw = dw_packed;
+    const long long ldy = d->out_ld;
+    // dy view: channel extent = cout (TMA zero-fills channels >= cout), pitch out_ld
+    rc = make_act_map(&maps.a, dy, d->cout, d->ow, d->oh, d->n, ldy, static_cast<long long>(d->ow) * ldy,
+                      static_cast<long long>(d->oh) * d->ow * ldy, p.tile_w, p.tile_h);
+    if (rc != RTSDS_OK) return rc;
+    int first = -1;
+    for (int i = 0; i < 4; ++i) {
+        if (!t.view[i].used) continue;
+        rc = make_act_map(&maps.b[i], t.view[i].base, d->cin, t.view[i].wd, t.view[i].hd, d->n, t.view[i].sw, t.view[i].sh,
+                          t.view[i].sn, p.tile_w, p.tile_h);
+        if (rc != RTSDS_OK) return rc;
+        if (first < 0) first = i;
+    }
     for (int i = 0; i < 4; ++i)
-        if (!have_map[i]) maps.a[i] = maps.a[p.tap_map[0]];
-
-    const long long m_tiles = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
-    const int block_n = plan_bn;
-    const int n_tiles = p.cout_pad / block_n;
-    const long long ktot = static_cast<long long>(p.n_taps) * d->cin;
-    rc = make_weight_map(&maps.b, w, ktot, p.cout_pad, block_n);
-    if (rc != RTSDS_OK) return rc;
-
-    const int kb_total = p.n_taps * p.kchunks;
-    const int split = plan_split;
-    p.split_k = split;
-    const long long m_total = static_cast<long long>(d->n) * d->oh * d->ow;
-    if (split > 1) {
-        const size_t need = static_cast<size_t>(split) * m_total * p.cout_pad * sizeof(float);
-        if (!workspace || ws_bytes < need) {
-            set_error("conv2d_tc_fwd: split_k=%d needs %zu workspace bytes, got %zu", split, need, ws_bytes);
-            return RTSDS_EWS;
-        }
-        RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_tc_fwd: workspace alignment");
-        p.partial = reinterpret_cast<float*>(workspace);
-    }
-    // stages: keep two CTAs resident per SM (epilogue of one overlaps the main loop of the other)
-    int stages = g_force_stages ? g_force_stages : (block_n == 128 ? 3 : (block_n == 64 ? 4 : 5));
-    const int kb_per = kb_total / split;
-    if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
-    while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
+        if (!t.view[i].used) maps.b[i] = maps.b[first];
+    int stages = block_n == 128 ? 3 : 4;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
     p.stages = stages;
-    RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv2d_tc_fwd: too many tiles");
-
-    dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
-    cudaStream_t stream = as_stream(s);
-    if (block_n == 128) rc = launch_tc<128>(maps, p, grid, stream);
-    else if (block_n == 64) rc = launch_tc<64>(maps, p, grid, stream);
-    else if (block_n == 32) rc = launch_tc<32>(maps, p, grid, stream);
-    else { set_error("conv2d_tc_fwd: block_n %d", block_n); return RTSDS_EUNSUP; }
-    if (rc != RTSDS_OK) return rc;
-
-    if (split > 1) {
-        const long long total = m_total * (p.cout_pad / 4);
-        long long want = cdiv(total, 256);
-        int g = static_cast<int>(want > 4LL * num_sms() ? 4LL * num_sms() : want);
-        size_t sm = stats ? 2 * static_cast<size_t>(d->cout) * sizeof(float) : 0;
-        splitk_finish_kernel<<<g, 256, sm, stream>>>(p.partial, split, m_total, d->cout, p.cout_pad, d->oh, d->ow, p);
-        count_launch();
-        rc = check_launch("splitk_finish_kernel");
-    }
-    return rc;
+    dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps * p.ci_tiles), static_cast<unsigned>(co_tiles));
+    if (block_n == 128) return launch_wgrad<128>(maps, p, grid, as_stream(s));
+    return launch_wgrad<64>(maps, p, grid, as_stream(s));
 }

@@ -159,6 +159,32 @@ arm_gate_kernel(const float* __restrict__ pooled, const float* __restrict__ w, c
 }
 
 // ---------------------------------------------------------------- gated bilinear resize NHWC -> NHWC slot
+struct V8 { float v[8]; };
+__device__ __forceinline__ V8 ld8(const __nv_bfloat16* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    V8 r;
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ V8 ld8(const float* p) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    V8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]); u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]); u.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void st8(float* p, const V8& r) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// one thread = one destination pixel x 8 channels (16-byte loads/stores for bf16)
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int src_ld, const float* __restrict__ gate,
@@ -174,26 +200,27 @@ gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int sr
         const int img = static_cast<int>(r / oh);
         const Lerp ly = lerp_src(oy, rh, h), lx = lerp_src(ox, rw, w);
         const T* b = src + static_cast<long long>(img) * h * w * src_ld + g8 * 8;
-        const T* p00 = b + (static_cast<long long>(ly.i0) * w + lx.i0) * src_ld;
-        const T* p01 = b + (static_cast<long long>(ly.i0) * w + lx.i1) * src_ld;
-        const T* p10 = b + (static_cast<long long>(ly.i1) * w + lx.i0) * src_ld;
-        const T* p11 = b + (static_cast<long long>(ly.i1) * w + lx.i1) * src_ld;
-        T* d = dst + ((static_cast<long long>(img) * oh + oy) * ow + ox) * dst_ld + dst_coff + g8 * 8;
-        const float* gp = gate ? gate + static_cast<long long>(img) * c + g8 * 8 : nullptr;
+        const V8 p00 = ld8(b + (static_cast<long long>(ly.i0) * w + lx.i0) * src_ld);
+        const V8 p01 = ld8(b + (static_cast<long long>(ly.i0) * w + lx.i1) * src_ld);
+        const V8 p10 = ld8(b + (static_cast<long long>(ly.i1) * w + lx.i0) * src_ld);
+        const V8 p11 = ld8(b + (static_cast<long long>(ly.i1) * w + lx.i1) * src_ld);
+        V8 gv;
+        if (gate) gv = ld8(gate + static_cast<long long>(img) * c + g8 * 8);
+        V8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = ly.l0 * (lx.l0 * to_f32(p00[j]) + lx.l1 * to_f32(p01[j])) +
-                      ly.l1 * (lx.l0 * to_f32(p10[j]) + lx.l1 * to_f32(p11[j]));
-            if (gp) v *= gp[j];
-            d[j] = from_f32<T>(v);
+            float v = ly.l0 * (lx.l0 * p00.v[j] + lx.l1 * p01.v[j]) + ly.l1 * (lx.l0 * p10.v[j] + lx.l1 * p11.v[j]);
+            if (gate) v *= gv.v[j];
+            o.v[j] = v;
         }
+        st8(dst + ((static_cast<long long>(img) * oh + oy) * ow + ox) * dst_ld + dst_coff + g8 * 8, o);
     }
 }
 
 // ---------------------------------------------------------------- FFM attention + final 1x1 conv
 constexpr int FFM_MAX_C = 32;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ pooled, long long hw, int c,
                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
@@ -399,6 +426,7 @@ extern "C" int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int 
                                       rtsds_stream_t s) {
     RTSDS_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "gate_resize_nhwc: bad argument");
     RTSDS_REQUIRE(c > 0 && c % 8 == 0 && src_ld >= c && dst_ld >= dst_coff + c, "gate_resize_nhwc: bad channel layout");
+    RTSDS_REQUIRE(src_ld % 8 == 0 && dst_ld % 8 == 0 && dst_coff % 8 == 0, "gate_resize_nhwc: pitches/offset must be multiples of 8");
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
     const int grid = grid_for(static_cast<long long>(n) * oh * ow * (c / 8), 256);
     if (dtype == RTSDS_BF16)
@@ -418,15 +446,15 @@ extern "C" int rtsds_ffm_head(const void* f, int f_dtype, int f_ld, const float*
                               const float* bc, float* attn_out, float* z, int z_ld, rtsds_stream_t s) {
     RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && z, "ffm_head: NULL argument");
     RTSDS_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= FFM_MAX_C && f_ld >= c && z_ld >= c, "ffm_head: bad shape");
-    long long bx = cdiv(hw, 256);
-    const long long cap = cdiv(8LL * num_sms(), n);
+    long long bx = cdiv(hw, 64);
+    const long long cap = cdiv(16LL * num_sms(), n);
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), n);
     if (f_dtype == RTSDS_BF16)
-        ffm_head_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(f), f_ld, pooled, hw,
+        ffm_head_kernel<__nv_bfloat16><<<grid, 64, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(f), f_ld, pooled, hw,
                                                                        c, w1, b1, w2, b2, wc, bc, attn_out, z, z_ld);
     else if (f_dtype == RTSDS_F32)
-        ffm_head_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(f), f_ld, pooled, hw, c, w1, b1, w2,
+        ffm_head_kernel<float><<<grid, 64, 0, as_stream(s)>>>(reinterpret_cast<const float*>(f), f_ld, pooled, hw, c, w1, b1, w2,
                                                                b2, wc, bc, attn_out, z, z_ld);
     else { set_error("ffm_head: bad dtype"); return RTSDS_EINVAL; }
     count_launch();

@@ -193,10 +193,35 @@ static int launch_stem(const float* x, const float* w, const float* scale, const
 }
 
 // ---- MaxPool2d(kernel 3, stride 2, pad 1[, ceil_mode]) on NHWC --------------------
+// one thread = one output pixel x 8 channels; 16-byte (bf16) / 2x16-byte (fp32) vector loads.
+struct Vec8 { float v[8]; };
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    Vec8 r;
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ Vec8 load8(const float* p) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    Vec8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]); u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]); u.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(float* p, const Vec8& r) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y) {
-    // one thread = one output pixel x 8 channels (16 B of bf16 / 32 B of fp32)
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -206,23 +231,23 @@ maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int 
         const int ox = static_cast<int>(r % ow); r /= ow;
         const int oy = static_cast<int>(r % oh);
         const int img = static_cast<int>(r / oh);
-        float m[8];
+        Vec8 m;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int j = 0; j < 8; ++j) m.v[j] = -INFINITY;
+#pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int iy = oy * 2 - 1 + dy;
             if (iy < 0 || iy >= h) continue;
+#pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = ox * 2 - 1 + dx;
                 if (ix < 0 || ix >= w) continue;
-                const T* px = x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g * 8;
+                const Vec8 t = load8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g * 8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], to_f32(px[j]));
+                for (int j = 0; j < 8; ++j) m.v[j] = fmaxf(m.v[j], t.v[j]);
             }
         }
-        T* py = y + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) py[j] = from_f32<T>(m[j]);
+        store8(y + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + g * 8, m);
     }
 }
 

@@ -122,6 +122,43 @@ def conv2d_simt(d: ConvDesc, x, w, y, scale=None, shift=None, residual=None, sta
                                       _s()), "conv2d_simt_fwd")
 
 
+def dgrad_ck(cout: int, tc: bool) -> int:
+    """Channel extent of the dy operand / dgrad weight K dimension."""
+    return (cout + 63) // 64 * 64 if tc else cout
+
+
+def pack_conv_weight_dgrad(w: torch.Tensor, dtype: int, tc: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """OIHW fp32 -> dgrad operand [cout_pad(cin)][kh*kw][ck] in `dtype`."""
+    w = w.detach()
+    co, ci, kh, kw = w.shape
+    cp, ck = cout_pad(ci), dgrad_ck(co, tc)
+    if out is None:
+        out = torch.empty((cp, kh * kw, ck), dtype=torch_dtype(dtype), device=w.device)
+    check(lib().rtsds_pack_conv_weight_dgrad(_p(w), co, ci, kh, kw, cp, ck, dtype, _p(out), _s()), "pack_conv_weight_dgrad")
+    return out
+
+
+def conv2d_dgrad(d: ConvDesc, dy, w_dgrad, dx, dx_dtype, tc: bool, residual=None, workspace=None) -> None:
+    if tc:
+        ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+        check(lib().rtsds_conv2d_tc_dgrad(C.byref(d), _p(dy), _p(w_dgrad), _p(residual), _p(dx), dx_dtype, _p(workspace),
+                                          ws_bytes, _s()), "conv2d_tc_dgrad")
+    else:
+        check(lib().rtsds_conv2d_simt_dgrad(C.byref(d), _p(dy), _p(w_dgrad), _p(residual), _p(dx), dx_dtype, _s()),
+              "conv2d_simt_dgrad")
+
+
+def conv2d_wgrad(d: ConvDesc, x, dy, dw_packed, tc: bool) -> None:
+    fn = lib().rtsds_conv2d_tc_wgrad if tc else lib().rtsds_conv2d_simt_wgrad
+    check(fn(C.byref(d), _p(x), _p(dy), _p(dw_packed), _s()), "conv2d_wgrad")
+
+
+def unpack_conv_wgrad(dw_packed, grad_oihw: torch.Tensor, accumulate: bool) -> None:
+    co, ci, kh, kw = grad_oihw.shape
+    check(lib().rtsds_unpack_conv_wgrad(_p(dw_packed), co, ci, kh, kw, int(accumulate), _p(grad_oihw), _s()),
+          "unpack_conv_wgrad")
+
+
 def stem_conv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, k: int, stride: int, pad: int, scale=None,
               shift=None, act=ACT_NONE, slope=0.0, softmax_in=False, stats=None) -> None:
     _cuda(x, w, y)

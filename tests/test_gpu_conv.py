@@ -10,7 +10,7 @@ import torch
 from rtsds_b200 import ops
 from rtsds_b200.ops import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32
 
-from gpu_util import conv_ref, rel_err, run_conv
+from gpu_util import bf16_round, conv_ref, nchw, nhwc, rel_err, run_conv
 
 pytestmark = pytest.mark.gpu
 
@@ -165,3 +165,85 @@ def test_conv_simt_bf16_cross_checks_tc(cuda):
     a, _, _ = run_conv("tc", x, wt, out_dtype=F32, out_ld=128)
     b, _, _ = run_conv("simt", x, wt, out_dtype=F32, out_ld=128)
     assert rel_err(a, b) < 1e-4
+
+
+# ----------------------------------------------------------------------------- backward (dgrad / wgrad)
+BWD_CASES = [
+    ("3x3_s1", 2, 64, 16, 32, 64, 3, 1, 1, 1),
+    ("3x3_s1_c128", 1, 128, 20, 36, 256, 3, 1, 1, 1),
+    ("3x3_s2_even", 2, 64, 32, 64, 128, 3, 2, 1, 1),
+    ("3x3_s2_odd", 1, 64, 45, 81, 128, 3, 2, 1, 1),
+    ("1x1_s2", 2, 128, 24, 40, 256, 1, 2, 0, 1),
+    ("1x1_s2_odd", 1, 64, 23, 41, 128, 1, 2, 0, 1),
+    ("1x1_s1_cout19", 2, 256, 12, 20, 19, 1, 1, 0, 1),
+    ("ffm_cout19", 1, 1024, 12, 20, 19, 3, 1, 1, 1),
+    ("layer4", 2, 512, 4, 6, 512, 3, 1, 1, 1),
+    ("4x4_s2", 1, 64, 32, 48, 128, 4, 2, 1, 1),
+    ("dil2", 1, 64, 17, 33, 64, 3, 1, 2, 2),
+]
+
+
+def _bwd_ref(x, wt, dy, stride, pad, dil, rnd):
+    xr, wr, dyr = (bf16_round(x), bf16_round(wt), bf16_round(dy)) if rnd else (x, wt, dy)
+    xr = xr.clone().requires_grad_(True)
+    wr1 = wr.clone().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xr, wr1, None, stride, pad, dil)
+    y.backward(dyr)
+    return xr.grad, wr1.grad
+
+
+def _run_bwd(kind, x, wt, dy, stride, pad, dil, dtype, residual=None):
+    tc = kind == "tc"
+    tdt = ops.torch_dtype(dtype)
+    n, cin, h, w = x.shape
+    cout, _, kh, kw = wt.shape
+    ck = ops.dgrad_ck(cout, tc)
+    dy_ld = max(ck, (cout + 7) // 8 * 8)
+    d = ops.make_conv_desc(n, h, w, cin, cin, cout, dy_ld, kh, stride, pad, dil, in_dtype=dtype, out_dtype=dtype, kw=kw)
+    dyg = torch.zeros(n, d.oh, d.ow, dy_ld, dtype=tdt, device="cuda")
+    dyg[..., :cout] = nhwc(dy, tdt)
+    xg = nhwc(x, tdt)
+    wd = ops.pack_conv_weight_dgrad(wt.cuda().contiguous(), dtype, tc)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.float32, device="cuda")
+    res = nhwc(residual, torch.float32) if residual is not None else None
+    ws = torch.empty(max(1, int(ops.lib().rtsds_conv2d_tc_dgrad_workspace_bytes(d))), dtype=torch.uint8, device="cuda") if tc else None
+    ops.conv2d_dgrad(d, dyg, wd, dx, F32, tc, res, ws)
+    dwp = torch.zeros(cout, kh * kw, cin, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(d, xg, dyg, dwp, tc)
+    gw = torch.ones(cout, cin, kh, kw, device="cuda")
+    ops.unpack_conv_wgrad(dwp, gw, True)
+    torch.cuda.synchronize()
+    return nchw(dx), gw.cpu() - 1.0
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=[c[0] for c in BWD_CASES])
+def test_conv_tc_backward(cuda, case):
+    from gpu_util import bf16_round  # noqa: F401
+    _, n, cin, h, w, cout, k, stride, pad, dil = case
+    x, wt, g = _mk(n, cin, h, w, cout, k, seed=21)
+    oh, ow = ops.conv_out_size(h, k, stride, pad, dil), ops.conv_out_size(w, k, stride, pad, dil)
+    dy = torch.randn(n, cout, oh, ow, generator=g)
+    res = torch.randn(n, cin, h, w, generator=g)
+    dx, dw = _run_bwd("tc", x, wt, dy, stride, pad, dil, BF16, residual=res)
+    rdx, rdw = _bwd_ref(x, wt, dy, stride, pad, dil, True)
+    assert rel_err(dx, rdx + res) < 2e-4, rel_err(dx, rdx + res)
+    assert rel_err(dw, rdw) < 2e-4, rel_err(dw, rdw)
+
+
+@pytest.mark.parametrize("case", BWD_CASES[:6] + BWD_CASES[9:], ids=[c[0] for c in BWD_CASES[:6] + BWD_CASES[9:]])
+def test_conv_simt_backward_fp32(cuda, case):
+    _, n, cin, h, w, cout, k, stride, pad, dil = case
+    x, wt, g = _mk(n, cin, h, w, cout, k, seed=22)
+    oh, ow = ops.conv_out_size(h, k, stride, pad, dil), ops.conv_out_size(w, k, stride, pad, dil)
+    dy = torch.randn(n, cout, oh, ow, generator=g)
+    dx, dw = _run_bwd("simt", x, wt, dy, stride, pad, dil, F32)
+    rdx, rdw = _bwd_ref(x, wt, dy, stride, pad, dil, False)
+    assert rel_err(dx, rdx) < 1e-5 and rel_err(dw, rdw) < 1e-4
+
+
+def test_conv_simt_backward_odd_channels(cuda):
+    x, wt, g = _mk(1, 19, 12, 20, 19, 1, seed=23)
+    dy = torch.randn(1, 19, 12, 20, generator=g)
+    dx, dw = _run_bwd("simt", x, wt, dy, 1, 0, 1, F32)
+    rdx, rdw = _bwd_ref(x, wt, dy, 1, 0, 1, False)
+    assert rel_err(dx, rdx) < 1e-5 and rel_err(dw, rdw) < 1e-4
