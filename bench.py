@@ -364,6 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="rtsds_b200", choices=["rtsds_b200", "reference"])
     ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch of the train workload")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,0 +1,141 @@
+"""Training workload of bench.py (BASELINE.json configs[2]): BiSeNet-ResNet18 supervised training on
+synthetic GTA5-shaped 720x1280 batches, data-parallel (one process per GPU, NCCL gradient all-reduce),
+Adam lr 1e-4, 3 x CrossEntropyLoss(ignore_index=19), followed by an on-device fast_hist/mIoU validation
+pass at 512x1024.  A step is what the reference's train() loop body does (train.py:68-106): poly LR,
+zero_grad, forward, 3 x CE, backward, optimizer.step(), pixel accuracy."""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import time
+
+import torch
+
+TRAIN_GFLOP_PER_IMG_720 = 267.5      # fwd + dgrad + wgrad conv FLOPs at 720x1280
+TRAIN_CONV_MB_PER_IMG_720 = 3 * 408.0
+
+
+def poly_lr(optimizer, init_lr, it, max_iter, power=0.9):
+    """utils.poly_lr_scheduler (utils.py:33-48): only param_groups[0] is updated."""
+    lr = init_lr * (1 - it / max_iter) ** power
+    optimizer.param_groups[0]["lr"] = lr
+    return lr
+
+
+def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280):
+    import bench
+    from rtsds_b200 import ops
+    from rtsds_b200.bisenet_autograd import bisenet_fused_ce
+
+    dev = torch.device("cuda", local)
+    model = bench.make_model(dev).train()
+    model.rtsds_ddp = world > 1
+    if world > 1:
+        import torch.distributed as dist
+
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+        for b in model.buffers():
+            dist.broadcast(b.data, 0)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    n_sets = 4                                           # 4 x b x 11 MB images: far larger than the 126 MB L2 for b >= 4
+    g = torch.Generator().manual_seed(42 + rank)
+    host_x = torch.randn(n_sets, batch, 3, h, w, generator=g).pin_memory()
+    host_y = torch.randint(0, 20, (n_sets, batch, h, w), generator=g).pin_memory()
+    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+    max_iter = 10 * (steps + warmup)
+
+    def step(i, x, y):
+        poly_lr(opt, 1e-4, i, max_iter)
+        opt.zero_grad(set_to_none=True)
+        loss, pred, stats = bisenet_fused_ce(model, x, y, 19)
+        loss.backward()
+        opt.step()
+        return loss, stats
+
+    for i in range(warmup):
+        step(i, dev_x[i % n_sets], dev_y[i % n_sets])
+    torch.cuda.synchronize()
+    c0 = ops.launch_count()
+    step(warmup, dev_x[0], dev_y[0])
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - c0
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bench.barrier(world)
+    with bench.ClockSampler(local) as clk:
+        e0.record()
+        for i in range(steps):
+            loss, stats = step(warmup + i, dev_x[i % n_sets], dev_y[i % n_sets])
+        e1.record()
+        bench.barrier(world)
+    ms = bench.max_over_ranks(e0.elapsed_time(e1), world)
+    last_loss = loss.item()
+
+    # end to end: pinned host batch -> device, step, loss read back every step (train.py:71-72,99)
+    sx, sy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
+    bench.barrier(world)
+    e0.record()
+    for i in range(steps):
+        sx.copy_(host_x[i % n_sets], non_blocking=True)
+        sy.copy_(host_y[i % n_sets], non_blocking=True)
+        loss, stats = step(warmup + steps + i, sx, sy)
+        _ = loss.item()
+    e1.record()
+    bench.barrier(world)
+    ms_e2e = bench.max_over_ranks(e0.elapsed_time(e1), world)
+
+    # validation pass: eval forward at 512x1024 + fused argmax/fast_hist on device, matrix all-reduced once
+    model.eval()
+    hist = torch.zeros(19 * 19, dtype=torch.int64, device=dev)
+    vx = torch.randn(1, 3, 512, 1024, generator=g).to(dev)
+    vy = torch.randint(0, 20, (1, 512, 1024), generator=g).to(dev)
+    with torch.no_grad():
+        for _ in range(4):
+            out = model(vx)
+            ops.argmax_hist(out, vy, hist, None)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(hist)
+    hh = hist.cpu().numpy().reshape(19, 19).astype("float64")
+    import numpy as np
+
+    iou = np.diag(hh) / (hh.sum(1) + hh.sum(0) - np.diag(hh) + 1e-5)        # utils.per_class_iou
+    return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, loss=last_loss, clocks=clk.summary(), miou=float(np.nanmean(iou)),
+                h2d=batch * (3 * h * w * 4 + h * w * 8))
+
+
+def run_train(args, rank, world, local):
+    import bench
+
+    batch = args.batch
+    r = measure_train(args, rank, world, local, args.steps, args.warmup, batch)
+    if rank != 0:
+        return
+    pk = bench.peaks()
+    K = args.steps
+    img_s = world * batch * K / (r["ms"] / 1e3)
+    img_s_e2e = world * batch * K / (r["ms_e2e"] / 1e3)
+    per_gpu = img_s / world
+    line = {
+        "metric": "BiSeNet-R18 720x1280 data-parallel training throughput", "value": round(img_s, 2), "unit": "images/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": round(r["ms"] / K, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "bisenet_r18_train_3x720x1280 (BASELINE.json configs[2])", "per_gpu_batch": batch,
+                   "global_batch": batch * world, "optimizer": "Adam lr 1e-4 (torch.optim), poly LR", "loss": "3 x CE(ignore_index=19), fused resize+CE",
+                   "parallelism": f"dp{world}", "l2": "4 rotating input sets per rank, each larger than L2 for b>=4"},
+        "clocks": r["clocks"],
+        "e2e": {"value": round(img_s_e2e, 2), "unit": "images/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
+                "ms_per_step": round(r["ms_e2e"] / K, 3)},
+        "gpu_launches": int(r["launches"] * K), "launches_per_step": int(r["launches"]),
+        "roofline": {"bound": "tensor", "achieved": round(per_gpu * TRAIN_GFLOP_PER_IMG_720 / 1e3, 2), "peak": pk["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": round(per_gpu * TRAIN_GFLOP_PER_IMG_720 / 1e3 / pk["bf16_tflops_sustained"], 4),
+                     "traffic": None, "peak_source": pk["source"], "kernel": "whole training step (conv FLOPs only), per GPU"},
+        "whole_step_hbm": {"algorithmic_gbs": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3, 1),
+                           "frac_of_hbm_peak": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3 / pk["hbm_gbs"], 4)},
+        "final_loss": round(r["loss"], 4), "val_miou_random_weights": round(r["miou"], 5),
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))

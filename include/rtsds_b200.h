@@ -158,7 +158,7 @@ int rtsds_conv2d_simt_wgrad(const RtsdsConvDesc* d, const void* x, const void* d
 int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw,
                                  int cin_pad, int ck, int dtype, void* w_packed,
                                  rtsds_stream_t s);
-int rtsds_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int kh, int kw,
+int rtsds_unpack_conv_wgrad(float* dw_packed /* zeroed on return */, int cout, int cin, int kh, int kw,
                             int accumulate, float* grad_oihw, rtsds_stream_t s);
 
 /* Stem convolutions read the API-boundary image directly:
@@ -171,6 +171,21 @@ int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, int cin, int
                         const float* scale, const float* shift, int act, float slope,
                         int softmax_in, float* stats, int out_dtype, void* y,
                         rtsds_stream_t s);
+
+/* Tensor-core stems of BiSeNet: the context-path conv7x7 s2 p3 3->64 (build_contextpath.py:19) and the
+ * spatial-path conv3x3 s2 p1 3->64 (build_bisenet.py:24) read the same image on the same output grid and are
+ * fused into one tcgen05 implicit GEMM (N = 64 + 64) whose im2col tile is gathered into swizzled shared
+ * memory.  wpk: bf16 [128][192] from rtsds_stem_pack_weights; scale/shift: fp32 [128] (context-path BN in
+ * 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
+ * wgrad: d_raw_*: NHWC bf16 [n,oh,ow,64]; dw_ws: fp32 [128*192] scratch, zero on entry and on return;
+ * g7/g3: OIHW fp32 gradients, accumulated. */
+int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, void* wpk, rtsds_stream_t s);
+int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                           const float* shift, int relu, float* stats_cp, float* stats_sp, void* y_cp,
+                           void* y_sp, rtsds_stream_t s);
+int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_raw_cp,
+                             const void* d_raw_sp, float* dw_ws, float* g7_oihw, float* g3_oihw,
+                             rtsds_stream_t s);
 
 /* nn.MaxPool2d(3, 2, 1[, ceil_mode]) on NHWC. */
 int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype,

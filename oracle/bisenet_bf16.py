@@ -22,8 +22,9 @@ def _fold(sd, p, eps=1e-5):
 
 
 def bisenet_eval_bf16(x, sd, return_intermediates=False):
-    # spatial path: stem keeps fp32 weights (CUDA-core kernel), output buffer bf16
-    s = F.conv2d(x, sd["saptial_path.convblock1.conv1.weight"], None, 2, 1)
+    # both stems run on the tensor cores too: bf16 image and weights, fp32 accumulation, bf16 output buffer
+    x = _r(x)
+    s = F.conv2d(x, _r(sd["saptial_path.convblock1.conv1.weight"]), None, 2, 1)
     sc, sh = _fold(sd, "saptial_path.convblock1.bn")
     s = _r(F.relu(s * sc + sh))
     for i in (2, 3):
@@ -32,7 +33,7 @@ def bisenet_eval_bf16(x, sd, return_intermediates=False):
         sc, sh = _fold(sd, p + ".bn")
         s = _r(F.relu(s * sc + sh))
     P = "context_path.features"
-    c = F.conv2d(x, sd[P + ".conv1.weight"], None, 2, 3)
+    c = F.conv2d(x, _r(sd[P + ".conv1.weight"]), None, 2, 3)
     sc, sh = _fold(sd, P + ".bn1")
     c = F.max_pool2d(_r(F.relu(c * sc + sh)), 3, 2, 1)
     feats = []
@@ -98,9 +99,9 @@ class _Bf16Functional:
     def conv2d(self, x, w, b=None, *a, **k):
         if x.shape[-1] == 1 and x.shape[-2] == 1:          # ARM / FFM attention 1x1 on pooled vectors: fp32 kernels
             return F.conv2d(x, w, b, *a, **k)
-        if w.shape[1] > 3:                                  # tensor-core conv: bf16 weights
-            w = self._ste(w)
-        return self._ste(F.conv2d(x, w, b, *a, **k))
+        if w.shape[1] == 3:                                 # fused tensor-core stems: bf16 image
+            x = self._ste(x)
+        return self._ste(F.conv2d(x, self._ste(w), b, *a, **k))   # bf16 weights, bf16 raw output
 
     def relu(self, x):
         return self._ste(F.relu(x)) if x.shape[-1] > 1 else F.relu(x)

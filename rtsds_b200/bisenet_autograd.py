@@ -33,9 +33,13 @@ def _get_train_plan(model, x):
 
 
 def _bump_bn_counters(model):
-    for m in model.modules():
-        if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
-            m.num_batches_tracked += 1
+    counters = model.__dict__.get("_rtsds_bn_counters")
+    if counters is None or (counters and counters[0].device != model.conv.weight.device):
+        counters = [m.num_batches_tracked for m in model.modules()
+                    if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None]
+        model.__dict__["_rtsds_bn_counters"] = counters
+    if counters:
+        torch._foreach_add_(counters, 1)
 
 
 def _grad_tuple(plan, params, gw):

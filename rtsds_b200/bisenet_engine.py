@@ -159,7 +159,9 @@ class BiSeNetPlan:
         sp2 = self.buf(n, h4, w4, 128)
         cat = self.buf(n, h8, w8, 1024)
         self.cat = cat
-        self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
+        fused_stems = self.use_tc and not self.train
+        if not fused_stems:
+            self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
         self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
         self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, 1024, ACT_RELU)
 
@@ -167,7 +169,10 @@ class BiSeNetPlan:
         cp = m.context_path
         ch2, cw2 = cs(H, 7, 2, 3), cs(W, 7, 2, 3)
         cp0 = self.buf(n, ch2, cw2, 64)
-        self._stem(cp.conv1, cp.bn1, cp0, 7, 2, 3)
+        if fused_stems:
+            self._stem_pair(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, cp0, sp1)
+        else:
+            self._stem(cp.conv1, cp.bn1, cp0, 7, 2, 3)
         ph, pw = ops.maxpool_out_size(ch2), ops.maxpool_out_size(cw2)
         x = self.buf(n, ph, pw, 64)
         self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
@@ -226,6 +231,16 @@ class BiSeNetPlan:
         self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
         if self._ws_bytes:
             self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp):
+        """Both stems in one tensor-core kernel (csrc/stem_tc.cu); eval mode: BN folded + ReLU."""
+        wpk = self.buf(128, 192, dtype=torch.bfloat16)
+        scale = self.buf(128, dtype=torch.float32)
+        shift = self.buf(128, dtype=torch.float32)
+        self.pack_steps.append(lambda: ops.stem_pack_weights(conv7.weight, conv3.weight, wpk))
+        self.pack_steps.append(lambda: ops.bn_fold(bn7, scale[:64], shift[:64]))
+        self.pack_steps.append(lambda: ops.bn_fold(bn3, scale[64:], shift[64:]))
+        self.pre_steps.append(lambda x: ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True))
 
     def _stem(self, conv, bnmod, y, k, stride, pad):
         cout = conv.weight.shape[0]

@@ -137,8 +137,7 @@ class _ConvBN:
         dd.out_ld = d_raw.ld
         gwt = gw.get(self.conv.weight)
         if gwt is not None:
-            dwp = p.dw_view(self.cout * self.k * self.k * self.cin)
-            dwp.zero_()
+            dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
             ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)
             ops.unpack_conv_wgrad(dwp, gwt, True)
         if dx is not None:
@@ -161,25 +160,28 @@ class _Stem:
         self.stats = plan.alloc_stats(64)
         self.sums = plan.buf(128, dtype=torch.float32)
         plan.note_scratch(self.n_pix * 64, 0)
+        # the fused tensor-core weight gradient needs both stems' conv-output gradients at once
+        self.d_raw = _Buf(plan.buf(n, self.oh, self.ow, 64)) if plan.use_tc else None
 
-    def forward(self, x):
+    def forward(self, x, conv_done=False):
         p = self.plan
         st = p.stats_view(self.stats, 64)
-        ops.stem_conv(x, self.conv.weight, self.raw.t, self.k, 2, self.pad, stats=st)
+        if not conv_done:
+            ops.stem_conv(x, self.conv.weight, self.raw.t, self.k, 2, self.pad, stats=st)
         ops.bn_finalize(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd)
         ops.scale_shift_act(self.raw.t, self.y.t, self.n_pix, 64, self.scale, self.shift, None, ACT_RELU)
 
-    def backward(self, x, dy: _Buf, gw):
+    def backward(self, x, dy: _Buf, gw, wgrad=True):
         p = self.plan
         s = _s()
-        d_raw = p.d_raw_view(64)
+        d_raw = self.d_raw if self.d_raw is not None else p.d_raw_view(64)
         check(lib().rtsds_bn_bwd_reduce(dy.ptr, dy.ld, self.y.ptr, 64, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
                                         self.n_pix, 64, 1, dy.dtype, _p(self.sums), s), "bn_bwd_reduce")
         check(lib().rtsds_bn_bwd_apply(dy.ptr, dy.ld, self.y.ptr, 64, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
                                        _p(self.bn.weight.detach()), _p(self.sums), self.n_pix, 64, 1, dy.dtype, d_raw.ptr, 64,
                                        p.dt, None, 0, _p(gw.get(self.bn.weight)), _p(gw.get(self.bn.bias)), s), "bn_bwd_apply")
         gwt = gw.get(self.conv.weight)
-        if gwt is not None:
+        if wgrad and gwt is not None:
             n, cin, h, w = x.shape
             check(lib().rtsds_stem_conv_wgrad(_p(x), d_raw.ptr, p.dt, n, cin, h, w, 64, self.k, 2, self.pad, _p(gwt), s),
                   "stem_conv_wgrad")
@@ -301,9 +303,13 @@ class BiSeNetTrainPlan:
         self.gA, self.gB, self.gT, self.gG = (self.buf(max_act) for _ in range(4))
         self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
         self.d_raw_scratch = self.zeros(max(self._scratch_act, 1))
-        self.dw_scratch = self.buf(max(self._scratch_w, 1), dtype=f32)
+        self.dw_scratch = self.zeros(max(self._scratch_w, 1), dtype=f32)
         if self._ws_bytes:
             self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+        if self.use_tc:
+            self.stem_wpk = self.buf(128, 192, dtype=torch.bfloat16)
+            self.stem_dw_ws = self.zeros(128 * 192, dtype=f32)
+            self.pack_steps.append(lambda: ops.stem_pack_weights(cp.conv1.weight, sp.convblock1.conv1.weight, self.stem_wpk))
         self.acc = torch.zeros(3, 4, dtype=torch.float64, device=self.device)      # fused-loss accumulators
         self.gscale = torch.zeros(3, dtype=f32, device=self.device)
         # flat parameter-gradient buffer
@@ -352,10 +358,13 @@ class BiSeNetTrainPlan:
         self.stats_all.zero_()
         self.generation += 1
         self.x = x
-        self.sp1.forward(x)
+        if self.use_tc:      # both stems in one tensor-core kernel (raw outputs + BatchNorm statistics)
+            ops.stem_pair_tc_fwd(x, self.stem_wpk, self.cp0.raw.t, self.sp1.raw.t, None, None, False,
+                                 self.stats_view(self.cp0.stats, 64), self.stats_view(self.sp1.stats, 64))
+        self.sp1.forward(x, conv_done=self.use_tc)
         self.sp2.forward()
         self.sp3.forward()
-        self.cp0.forward(x)
+        self.cp0.forward(x, conv_done=self.use_tc)
         ops.maxpool3x3s2(self.cp0.y.t, self.pool.t)
         for b in self.blocks:
             b["c1"].forward()
@@ -472,13 +481,17 @@ class BiSeNetTrainPlan:
         n_, ph, pw, _ = self.pool_shape
         dcp0 = _Buf(self.gT, ld=64, dtype=dt)
         check(lib().rtsds_maxpool3x3s2_bwd(self.cp0.y.ptr, dy.ptr, n, self.cp0.oh, self.cp0.ow, 64, dt, 0, dcp0.ptr, s), "maxpool_bwd")
-        self.cp0.backward(self.x, dcp0, gw)
+        self.cp0.backward(self.x, dcp0, gw, wgrad=not self.use_tc)
         # ---- spatial path ----
         d2 = _Buf(self.gA, ld=128, dtype=dt)
         self.sp3.backward(_Buf(self.dcat, ld=1024), gw, dx=d2, dx_accumulate=False)
         d1 = _Buf(self.gB, ld=64, dtype=dt)
         self.sp2.backward(d2, gw, dx=d1, dx_accumulate=False)
-        self.sp1.backward(self.x, d1, gw)
+        self.sp1.backward(self.x, d1, gw, wgrad=not self.use_tc)
+        if self.use_tc:
+            g7, g3 = gw.get(self.cp0.conv.weight), gw.get(self.sp1.conv.weight)
+            if g7 is not None or g3 is not None:
+                ops.stem_pair_tc_wgrad(self.x, self.cp0.d_raw.t, self.sp1.d_raw.t, self.stem_dw_ws, g7, g3)
 
     def _g(self, gw, p):
         g = gw.get(p)

@@ -347,39 +347,57 @@ arm_bwd_phase2_kernel(const float* __restrict__ dlin, const float* __restrict__ 
         float acc = dmul ? dmul[static_cast<long long>(i) * c + ci] : 0.f;
         for (int co = 0; co < c; ++co) acc = fmaf(dlin[static_cast<long long>(i) * c + co], w[static_cast<long long>(co) * c + ci], acc);
         dpooled[static_cast<long long>(i) * c + ci] = acc;
-    } else if (dw) {
-        for (int co = 0; co < c; ++co) {
-            float acc = 0.f;
-            for (int i = 0; i < n; ++i) acc = fmaf(dlin[static_cast<long long>(i) * c + co], pooled[static_cast<long long>(i) * c + ci], acc);
-            dw[static_cast<long long>(co) * c + ci] += acc;
-        }
     }
+}
+
+// dW[co][ci] += sum_n dlin[n][co] * pooled[n][ci]; one thread per (co, ci)
+__global__ void __launch_bounds__(256)
+arm_bwd_dw_kernel(const float* __restrict__ dlin, const float* __restrict__ pooled, int n, int c, float* dw) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(c) * c) return;
+    const int co = static_cast<int>(i / c), ci = static_cast<int>(i - static_cast<long long>(co) * c);
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc = fmaf(dlin[static_cast<long long>(k) * c + co], pooled[static_cast<long long>(k) * c + ci], acc);
+    dw[i] += acc;
 }
 
 // ---------------------------------------------------------------- FFM head backward
 // forward: a = sigmoid(W2 relu(W1 p + b1) + b2), g = f*(1+a), z = Wc g + bc (Wc NULL: z = g)
-// pass 1 (per pixel): dg = Wc^T dz;  da_raw[n,c] += dg*f;  dWc += dz (x) g;  dbc += dz
+// pass 1: dg = Wc^T dz;  da_raw[n,c] += dg*f;  dWc += dz (x) g;  dbc += dz.
+// Pixels are staged through shared memory in chunks of 128.  Thread t owns pixel t of the chunk for
+// da_raw (registers); for the dWc outer product lane o (< c) of every warp owns row o: it walks the
+// warp's 32 pixels keeping dWc[o][0..c) and dbc[o] in registers (broadcast shared loads, no atomics).
 constexpr int FB_MAXC = 32;
-__global__ void __launch_bounds__(128)
+constexpr int FB_CHUNK = 128;
+__global__ void __launch_bounds__(FB_CHUNK)
 ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ f, int f_ld,
                           const float* __restrict__ attn, const float* __restrict__ wc, long long hw, int c,
                           float* da_raw, float* dwc, float* dbc) {
     __shared__ float s_w[FB_MAXC * FB_MAXC];
-    __shared__ float s_da[FB_MAXC], s_db[FB_MAXC], s_dw[FB_MAXC * FB_MAXC];
+    __shared__ float s_dz[FB_CHUNK][FB_MAXC + 1], s_g[FB_CHUNK][FB_MAXC + 1];
+    __shared__ float s_da[FB_MAXC], s_a1[FB_MAXC];
     const int img = blockIdx.y;
-    for (int i = threadIdx.x; i < c * c; i += blockDim.x) { s_w[i] = wc ? wc[i] : 0.f; s_dw[i] = 0.f; }
-    if (threadIdx.x < FB_MAXC) { s_da[threadIdx.x] = 0.f; s_db[threadIdx.x] = 0.f; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < c * c; i += blockDim.x) s_w[i] = wc ? wc[i] : 0.f;
+    if (tid < FB_MAXC) { s_da[tid] = 0.f; s_a1[tid] = tid < c ? 1.f + attn[static_cast<long long>(img) * c + tid] : 0.f; }
     __syncthreads();
-    float da[FB_MAXC];
+    float da[FB_MAXC], dw_row[FB_MAXC];
+    float db = 0.f;
 #pragma unroll
-    for (int k = 0; k < FB_MAXC; ++k) da[k] = 0.f;
-    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < hw;
-         p += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float* dzp = dz + (static_cast<long long>(img) * hw + p) * dz_ld;
-        const float* fp = f + (static_cast<long long>(img) * hw + p) * f_ld;
+    for (int k = 0; k < FB_MAXC; ++k) { da[k] = 0.f; dw_row[k] = 0.f; }
+    for (long long p0 = static_cast<long long>(blockIdx.x) * FB_CHUNK; p0 < hw; p0 += static_cast<long long>(gridDim.x) * FB_CHUNK) {
+        const long long p = p0 + tid;
+        const bool ok = p < hw;
+        const float* dzp = dz + (static_cast<long long>(img) * hw + (ok ? p : 0)) * dz_ld;
+        const float* fp = f + (static_cast<long long>(img) * hw + (ok ? p : 0)) * f_ld;
         float dzv[FB_MAXC], fv[FB_MAXC];
 #pragma unroll
-        for (int k = 0; k < FB_MAXC; ++k) { dzv[k] = k < c ? dzp[k] : 0.f; fv[k] = k < c ? fp[k] : 0.f; }
+        for (int k = 0; k < FB_MAXC; ++k) {
+            dzv[k] = (ok && k < c) ? dzp[k] : 0.f;
+            fv[k] = (ok && k < c) ? fp[k] : 0.f;
+            s_dz[tid][k] = dzv[k];
+            s_g[tid][k] = fv[k] * s_a1[k];
+        }
 #pragma unroll
         for (int k = 0; k < FB_MAXC; ++k) {
             if (k < c) {
@@ -388,25 +406,31 @@ ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* 
                 da[k] += dg * fv[k];
             }
         }
-        if (wc) {
-            for (int o = 0; o < c; ++o) {
-                atomicAdd(&s_db[o], dzv[o]);
+        __syncwarp();
+        if (wc && lane < c) {
+            for (int q = 0; q < 32; ++q) {
+                const float d = s_dz[warp * 32 + q][lane];
+                db += d;
 #pragma unroll
                 for (int k = 0; k < FB_MAXC; ++k)
-                    if (k < c) atomicAdd(&s_dw[o * c + k], dzv[o] * fv[k] * (1.f + attn[static_cast<long long>(img) * c + k]));
+                    if (k < c) dw_row[k] = fmaf(d, s_g[warp * 32 + q][k], dw_row[k]);
             }
         }
+        __syncwarp();
     }
 #pragma unroll
     for (int k = 0; k < FB_MAXC; ++k)
         if (k < c) atomicAdd(&s_da[k], da[k]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        atomicAdd(&da_raw[static_cast<long long>(img) * c + i], s_da[i]);
-        if (wc && dbc) atomicAdd(&dbc[i], s_db[i]);
+    if (wc && lane < c) {
+        if (dbc) atomicAdd(&dbc[lane], db);
+        if (dwc) {
+#pragma unroll
+            for (int k = 0; k < FB_MAXC; ++k)
+                if (k < c) atomicAdd(&dwc[lane * c + k], dw_row[k]);
+        }
     }
-    if (wc && dwc)
-        for (int i = threadIdx.x; i < c * c; i += blockDim.x) atomicAdd(&dwc[i], s_dw[i]);
+    __syncthreads();
+    for (int i = tid; i < c; i += blockDim.x) atomicAdd(&da_raw[static_cast<long long>(img) * c + i], s_da[i]);
 }
 
 // pass 2 (one block per image, tiny): attention MLP backward -> dpooled[n,c] and parameter grads
@@ -695,9 +719,10 @@ extern "C" int rtsds_arm_gate_bwd(const float* dgate, const float* pooled, const
     cudaStream_t st = as_stream(s);
     arm_bwd_phase1_kernel<<<static_cast<int>(cdiv(c, 128)), 128, 0, st>>>(dgate, lin, xhat, gamma, beta, mul, eps, n, c, dlin_ws,
                                                                       mul ? dmul_ws : nullptr, dgamma, dbeta, dbias);
-    dim3 grid(static_cast<unsigned>(cdiv(c, 128)), n + 1);
+    dim3 grid(static_cast<unsigned>(cdiv(c, 128)), n);
     arm_bwd_phase2_kernel<<<grid, 128, 0, st>>>(dlin_ws, w, pooled, mul ? dmul_ws : nullptr, n, c, dpooled, dw);
-    count_launch(2);
+    if (dw) arm_bwd_dw_kernel<<<static_cast<int>(cdiv(static_cast<long long>(c) * c, 256)), 256, 0, st>>>(dlin_ws, pooled, n, c, dw);
+    count_launch(dw ? 3 : 2);
     return check_launch("arm_bwd kernels");
 }
 
@@ -711,11 +736,11 @@ extern "C" int rtsds_ffm_head_bwd(const float* dz, int dz_ld, const float* f, in
     cudaStream_t st = as_stream(s);
     cudaError_t e = cudaMemsetAsync(da_ws, 0, sizeof(float) * n * c, st);
     if (e != cudaSuccess) { set_error("ffm_head_bwd: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
-    long long bx = cdiv(hw, 128);
+    long long bx = cdiv(hw, FB_CHUNK);
     const long long cap = cdiv(2LL * num_sms(), n);
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), n);
-    ffm_head_bwd_pass1_kernel<<<grid, 128, 0, st>>>(dz, dz_ld, f, f_ld, attn, wc, hw, c, da_ws, dwc, dbc);
+    ffm_head_bwd_pass1_kernel<<<grid, FB_CHUNK, 0, st>>>(dz, dz_ld, f, f_ld, attn, wc, hw, c, da_ws, dwc, dbc);
     ffm_head_bwd_pass2_kernel<<<n, 64, 0, st>>>(da_ws, pooled, attn, w1, b1, w2, c, dpooled_ws, dw1, db1, dw2, db2);
     long long bx3 = cdiv(hw, 128);
     const long long cap3 = cdiv(8LL * num_sms(), n);

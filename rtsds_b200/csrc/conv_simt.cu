@@ -233,18 +233,29 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, 
     }
 }
 
-// wgrad result [cout][taps][cin] fp32 -> OIHW fp32 gradient (assign or accumulate)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int cout, int cin, int taps, int accumulate,
-                                    float* __restrict__ grad) {
-    const long long total = static_cast<long long>(cout) * cin * taps;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int t = static_cast<int>(i % taps);
-        const long long r = i / taps;
-        const int ci = static_cast<int>(r % cin);
-        const int co = static_cast<int>(r / cin);
-        const float v = dw[(static_cast<long long>(co) * taps + t) * cin + ci];
-        grad[i] = accumulate ? grad[i] + v : v;
+// wgrad result [cout][taps][cin] fp32 -> OIHW fp32 gradient (assign or accumulate); the source is zeroed
+// (the scratch stays clean for the next wgrad, no separate memset).  One block = one output channel x
+// 256 input channels, transposed through shared memory so that both sides are coalesced.
+constexpr int UNP_CI = 256;
+__global__ void __launch_bounds__(256)
+unpack_wgrad_kernel(float* __restrict__ dw, int cout, int cin, int taps, int accumulate, float* __restrict__ grad) {
+    extern __shared__ float s_t[];                  // [taps][UNP_CI + 1]
+    const int co = blockIdx.y;
+    const int ci0 = blockIdx.x * UNP_CI;
+    const int nci = min(UNP_CI, cin - ci0);
+    float* src = dw + static_cast<long long>(co) * taps * cin;
+    for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
+        const int t = i / nci, c = i - t * nci;
+        float* p = src + static_cast<long long>(t) * cin + ci0 + c;
+        s_t[t * (UNP_CI + 1) + c] = *p;
+        *p = 0.f;
+    }
+    __syncthreads();
+    float* dst = grad + (static_cast<long long>(co) * cin + ci0) * taps;
+    for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
+        const int c = i / taps, t = i - c * taps;
+        const float v = s_t[t * (UNP_CI + 1) + c];
+        dst[i] = accumulate ? dst[i] + v : v;
     }
 }
 
@@ -366,12 +377,13 @@ extern "C" int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int c
     return check_launch("pack_weight_dgrad_kernel");
 }
 
-extern "C" int rtsds_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int kh, int kw, int accumulate,
+extern "C" int rtsds_unpack_conv_wgrad(float* dw_packed, int cout, int cin, int kh, int kw, int accumulate,
                                        float* grad_oihw, rtsds_stream_t s) {
     RTSDS_REQUIRE(dw_packed && grad_oihw && cout > 0 && cin > 0 && kh > 0 && kw > 0, "unpack_conv_wgrad: bad argument");
-    const long long total = static_cast<long long>(cout) * cin * kh * kw;
-    int grid = static_cast<int>(cdiv(total, 256) > 2048 ? 2048 : cdiv(total, 256));
-    unpack_wgrad_kernel<<<grid, 256, 0, as_stream(s)>>>(dw_packed, cout, cin, kh * kw, accumulate, grad_oihw);
+    RTSDS_REQUIRE(cout <= 65535 && kh * kw <= 49, "unpack_conv_wgrad: shape out of range");
+    dim3 grid(static_cast<unsigned>(cdiv(cin, UNP_CI)), cout);
+    const size_t smem = sizeof(float) * kh * kw * (UNP_CI + 1);
+    unpack_wgrad_kernel<<<grid, 256, smem, as_stream(s)>>>(dw_packed, cout, cin, kh * kw, accumulate, grad_oihw);
     count_launch();
     return check_launch("unpack_wgrad_kernel");
 }

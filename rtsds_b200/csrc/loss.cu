@@ -91,85 +91,115 @@ resize_ce_fwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld,
     if (acc) block_acc3(loss, nvalid, ncorrect, acc);
 }
 
-// Backward of mean-CE through the bilinear resize, scattered to z resolution.
-// grid (ceil(ow/1024), ceil(oh/rows_per_block), n)
+// Backward of mean-CE through the bilinear resize, accumulated at z resolution.
+// One block = a tile of BW_ROWS x BW_COLS output pixels of one image.
+//   phase 1: every thread evaluates (softmax - onehot) * grad_scale for its output pixels from the z
+//            footprint staged in shared memory and stores it to a shared-memory tile G[pixel][c];
+//   phase 2: every (footprint pixel, channel) GATHERS its bilinear-weighted sum over the tile from G
+//            (conflict-free shared loads, no shared atomics), then one global atomic per value
+//            (footprints of neighbouring tiles overlap by one row / column).
+constexpr int BW_ROWS = 8, BW_COLS = 128, BW_GP = 21;      // G pitch: odd, so per-pixel rows spread over all banks
 __global__ void __launch_bounds__(LS_THREADS)
 resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
-                     int rows_per_block, const long long* __restrict__ target, long long ignore_index,
-                     const float* __restrict__ grad_scale, float* __restrict__ dz) {
+                     const long long* __restrict__ target, long long ignore_index,
+                     const float* __restrict__ grad_scale, float* __restrict__ dz, int max_rows, int max_cols) {
     extern __shared__ float sm[];
     const int img = blockIdx.z;
-    const int oy0 = blockIdx.y * rows_per_block;
-    const int oy1 = min(oy0 + rows_per_block, oh) - 1;
-    const int ox0 = blockIdx.x * LS_TILE;
-    const int ox_last = min(ox0 + LS_TILE, ow) - 1;
+    const int oy0 = blockIdx.y * BW_ROWS, ox0 = blockIdx.x * BW_COLS;
+    const int oy1 = min(oy0 + BW_ROWS, oh) - 1, ox1 = min(ox0 + BW_COLS, ow) - 1;
     const int ys = lerp_src(oy0, rh, h).i0, ye = lerp_src(oy1, rh, h).i1;
-    const int xs = lerp_src(ox0, rw, w).i0, xe = lerp_src(ox_last, rw, w).i1;
+    const int xs = lerp_src(ox0, rw, w).i0, xe = lerp_src(ox1, rw, w).i1;
     const int nrows = ye - ys + 1, ncols = xe - xs + 1;
-    float* s_z = sm;                               // [nrows][ncols][c]
-    float* s_d = sm + nrows * ncols * c;
-    for (int i = threadIdx.x; i < nrows * ncols * c; i += LS_THREADS) {
+    const int gp = c <= BW_GP ? BW_GP : LS_MAXC + 1;
+    float* s_z = sm;                                            // [nrows][ncols][c]
+    float* s_g = sm + max_rows * max_cols * c;                  // [BW_ROWS*BW_COLS][gp]
+    int* s_yi = reinterpret_cast<int*>(s_g + BW_ROWS * BW_COLS * gp);   // [BW_ROWS][2] local i0,i1
+    float* s_yl = reinterpret_cast<float*>(s_yi + 2 * BW_ROWS);         // [BW_ROWS][2] l0,l1
+    int* s_xi = reinterpret_cast<int*>(s_yl + 2 * BW_ROWS);             // [BW_COLS][2]
+    float* s_xl = reinterpret_cast<float*>(s_xi + 2 * BW_COLS);         // [BW_COLS][2]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nrows * ncols * c; i += LS_THREADS) {
         const int ch = i % c;
         const int rc = i / c;
         const int col = rc % ncols, row = rc / ncols;
         s_z[i] = __ldg(z + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch);
-        s_d[i] = 0.f;
+    }
+    if (tid < BW_ROWS) {
+        const Lerp l = lerp_src(min(oy0 + tid, oh - 1), rh, h);
+        const bool ok = oy0 + tid < oh;
+        s_yi[2 * tid] = l.i0 - ys; s_yi[2 * tid + 1] = l.i1 - ys;
+        s_yl[2 * tid] = ok ? l.l0 : 0.f; s_yl[2 * tid + 1] = ok ? l.l1 : 0.f;
+    }
+    if (tid < BW_COLS) {
+        const Lerp l = lerp_src(min(ox0 + tid, ow - 1), rw, w);
+        const bool ok = ox0 + tid < ow;
+        s_xi[2 * tid] = l.i0 - xs; s_xi[2 * tid + 1] = l.i1 - xs;
+        s_xl[2 * tid] = ok ? l.l0 : 0.f; s_xl[2 * tid + 1] = ok ? l.l1 : 0.f;
     }
     __syncthreads();
     const float gs = __ldg(grad_scale);
-    const int ox = ox0 + threadIdx.x * LS_PX;
-    if (ox < ow) {
-        for (int oy = oy0; oy <= oy1; ++oy) {
-            Lerp ly = lerp_src(oy, rh, h);
-            ly.i0 -= ys; ly.i1 -= ys;
-            const long long pix0 = (static_cast<long long>(img) * oh + oy) * ow + ox;
+    // ---- phase 1: G = (softmax - onehot) * gs; 4 pixels per thread (one column, 4 rows apart by 2) ----
+    for (int pidx = tid; pidx < BW_ROWS * BW_COLS; pidx += LS_THREADS) {
+        const int ry = pidx / BW_COLS, rx = pidx - ry * BW_COLS;
+        const int oy = oy0 + ry, ox = ox0 + rx;
+        float* gout = s_g + pidx * gp;
+        long long t = ignore_index;
+        if (oy < oh && ox < ow) t = __ldg(target + (static_cast<long long>(img) * oh + oy) * ow + ox);
+        if (t == ignore_index || t < 0 || t >= c) {
+            for (int ch = 0; ch < c; ++ch) gout[ch] = 0.f;
+            continue;
+        }
+        const float w00 = s_yl[2 * ry] * s_xl[2 * rx], w01 = s_yl[2 * ry] * s_xl[2 * rx + 1];
+        const float w10 = s_yl[2 * ry + 1] * s_xl[2 * rx], w11 = s_yl[2 * ry + 1] * s_xl[2 * rx + 1];
+        const float ly0 = s_yl[2 * ry], ly1 = s_yl[2 * ry + 1], lx0 = s_xl[2 * rx], lx1 = s_xl[2 * rx + 1];
+        const int o00 = (s_yi[2 * ry] * ncols + s_xi[2 * rx]) * c, o01 = (s_yi[2 * ry] * ncols + s_xi[2 * rx + 1]) * c;
+        const int o10 = (s_yi[2 * ry + 1] * ncols + s_xi[2 * rx]) * c, o11 = (s_yi[2 * ry + 1] * ncols + s_xi[2 * rx + 1]) * c;
+        (void)w00; (void)w01; (void)w10; (void)w11;
+        float v[LS_MAXC];
+        float m = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < LS_PX; ++j) {
-                if (ox + j >= ow) break;
-                const long long t = __ldg(target + pix0 + j);
-                if (t == ignore_index || t < 0 || t >= c) continue;
-                Lerp lx = lerp_src(ox + j, rw, w);
-                lx.i0 -= xs; lx.i1 -= xs;
-                const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
-                const int o00 = (ly.i0 * ncols + lx.i0) * c, o01 = (ly.i0 * ncols + lx.i1) * c;
-                const int o10 = (ly.i1 * ncols + lx.i0) * c, o11 = (ly.i1 * ncols + lx.i1) * c;
-                float v[LS_MAXC];
-                float m = -INFINITY;
-#pragma unroll
-                for (int ch = 0; ch < LS_MAXC; ++ch) {
-                    if (ch < c) {
-                        v[ch] = ly.l0 * (lx.l0 * s_z[o00 + ch] + lx.l1 * s_z[o01 + ch]) +
-                                ly.l1 * (lx.l0 * s_z[o10 + ch] + lx.l1 * s_z[o11 + ch]);
-                        m = fmaxf(m, v[ch]);
-                    }
-                }
-                float s = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < LS_MAXC; ++ch)
-                    if (ch < c) { v[ch] = expf(v[ch] - m); s += v[ch]; }
-                const float inv = gs / s;
-#pragma unroll
-                for (int ch = 0; ch < LS_MAXC; ++ch) {
-                    if (ch < c) {
-                        const float g = v[ch] * inv - (ch == t ? gs : 0.f);
-                        atomicAdd(&s_d[o00 + ch], w00 * g);
-                        atomicAdd(&s_d[o01 + ch], w01 * g);
-                        atomicAdd(&s_d[o10 + ch], w10 * g);
-                        atomicAdd(&s_d[o11 + ch], w11 * g);
-                    }
-                }
+        for (int ch = 0; ch < LS_MAXC; ++ch) {
+            if (ch < c) {
+                v[ch] = ly0 * (lx0 * s_z[o00 + ch] + lx1 * s_z[o01 + ch]) + ly1 * (lx0 * s_z[o10 + ch] + lx1 * s_z[o11 + ch]);
+                m = fmaxf(m, v[ch]);
             }
         }
+        float ssum = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < LS_MAXC; ++ch)
+            if (ch < c) { v[ch] = expf(v[ch] - m); ssum += v[ch]; }
+        const float inv = gs / ssum;
+#pragma unroll
+        for (int ch = 0; ch < LS_MAXC; ++ch)
+            if (ch < c) gout[ch] = v[ch] * inv - (ch == t ? gs : 0.f);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nrows * ncols * c; i += LS_THREADS) {
-        const float g = s_d[i];
-        if (g != 0.f) {
-            const int ch = i % c;
-            const int rc = i / c;
-            const int col = rc % ncols, row = rc / ncols;
-            atomicAdd(dz + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch, g);
+    // ---- phase 2: gather per (footprint pixel, channel) ----
+    for (int i = tid; i < nrows * ncols * c; i += LS_THREADS) {
+        const int ch = i % c;
+        const int rc = i / c;
+        const int col = rc % ncols, row = rc / ncols;
+        // output columns that can reference source column xs+col
+        int xlo, xhi;
+        {
+            const float inv = 1.0f / rw;
+            int a = static_cast<int>(floorf((static_cast<float>(xs + col) - 0.5f) * inv - 0.5f)) - 1;
+            int b = static_cast<int>(ceilf((static_cast<float>(xs + col) + 1.5f) * inv - 0.5f)) + 1;
+            xlo = max(a - ox0, 0); xhi = min(b - ox0, BW_COLS - 1);
         }
+        float acc = 0.f;
+        for (int ry = 0; ry < BW_ROWS; ++ry) {
+            const float wy = (s_yi[2 * ry] == row ? s_yl[2 * ry] : 0.f) + (s_yi[2 * ry + 1] == row ? s_yl[2 * ry + 1] : 0.f);
+            if (wy == 0.f) continue;
+            float rowacc = 0.f;
+            for (int rx = xlo; rx <= xhi; ++rx) {
+                const float wx = (s_xi[2 * rx] == col ? s_xl[2 * rx] : 0.f) + (s_xi[2 * rx + 1] == col ? s_xl[2 * rx + 1] : 0.f);
+                rowacc = fmaf(wx, s_g[(ry * BW_COLS + rx) * gp + ch], rowacc);
+            }
+            acc = fmaf(wy, rowacc, acc);
+        }
+        if (acc != 0.f)
+            atomicAdd(dz + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch, acc);
     }
 }
 
@@ -255,23 +285,20 @@ extern "C" int rtsds_resize_ce_bwd(const float* z, int n, int h, int w, int c, i
     RTSDS_REQUIRE(z && target && grad_scale && dz, "resize_ce_bwd: NULL argument");
     RTSDS_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c <= LS_MAXC && z_ld >= c && oh > 0 && ow > 0, "resize_ce_bwd: bad shape");
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
-    size_t cols = ls_cols(w, ow);
-    if (cols > static_cast<size_t>(w)) cols = w;
-    int rpb = 8;
-    size_t smem = 0;
-    for (; rpb >= 1; rpb >>= 1) {
-        size_t rows = static_cast<size_t>(static_cast<double>(rpb) * h / oh) + 3;
-        if (rows > static_cast<size_t>(h)) rows = h;
-        smem = sizeof(float) * 2 * rows * cols * c;
-        if (smem <= 160 * 1024) break;
-    }
-    RTSDS_REQUIRE(rpb >= 1, "resize_ce_bwd: tile does not fit shared memory (%zu bytes)", smem);
+    int max_rows = static_cast<int>(static_cast<double>(BW_ROWS) * h / oh) + 3;
+    int max_cols = static_cast<int>(static_cast<double>(BW_COLS) * w / ow) + 3;
+    if (max_rows > h) max_rows = h;
+    if (max_cols > w) max_cols = w;
+    const int gp = c <= BW_GP ? BW_GP : LS_MAXC + 1;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(max_rows) * max_cols * c + BW_ROWS * BW_COLS * gp) +
+                        sizeof(float) * 4 * (BW_ROWS + BW_COLS);
+    RTSDS_REQUIRE(smem <= 220 * 1024, "resize_ce_bwd: tile needs %zu bytes of shared memory (upsampling factor too small)", smem);
     static bool done = false;
-    if (!done) { cudaFuncSetAttribute(resize_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; }
-    dim3 grid(static_cast<unsigned>(cdiv(ow, LS_TILE)), static_cast<unsigned>(cdiv(oh, rpb)), n);
-    resize_ce_bwd_kernel<<<grid, LS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw, rpb,
+    if (!done) { cudaFuncSetAttribute(resize_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); done = true; }
+    dim3 grid(static_cast<unsigned>(cdiv(ow, BW_COLS)), static_cast<unsigned>(cdiv(oh, BW_ROWS)), n);
+    resize_ce_bwd_kernel<<<grid, LS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
                                                                    reinterpret_cast<const long long*>(target), ignore_index,
-                                                                   grad_scale, dz);
+                                                                   grad_scale, dz, max_rows, max_cols);
     count_launch();
     return check_launch("resize_ce_bwd_kernel");
 }

@@ -41,25 +41,63 @@ __global__ void bn_finalize_kernel(const float* stats, double count, const float
     }
 }
 
-// y = act(scale*x + shift + residual); 8 channels per thread.
-template <typename TX, typename TY>
+// y = act(scale*x + shift + residual); 8 channels per thread.  VEC: 16-byte accesses (c and all pitches
+// multiples of 8); otherwise a scalar tail-safe path.
+template <typename T> struct V8io;
+template <> struct V8io<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+template <> struct V8io<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+template <typename TX, typename TY, bool VEC>
 __global__ void __launch_bounds__(256)
 scale_shift_act_kernel(const TX* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                       const TY* __restrict__ residual, long long n_pix, int c, int x_ld, int res_ld, int y_ld,
-                       int act, float slope, TY* __restrict__ y) {
+                       const TY* residual, long long n_pix, int c, int x_ld, int res_ld, int y_ld,
+                       int act, float slope, TY* y) {
     const int cg = (c + 7) / 8;
     const long long total = n_pix * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long pix = i / cg;
         const int c0 = static_cast<int>(i - pix * cg) * 8;
+        if (VEC) {
+            float v[8], r[8];
+            V8io<TX>::ld(x + pix * x_ld + c0, v);
+            if (residual) V8io<TY>::ld(residual + pix * res_ld + c0, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int ch = c0 + j;
-            if (ch < c) {
-                float v = to_f32(x[pix * x_ld + ch]) * (scale ? scale[ch] : 1.f) + (shift ? shift[ch] : 0.f);
-                if (residual) v += to_f32(residual[pix * res_ld + ch]);
-                y[pix * y_ld + ch] = from_f32<TY>(apply_act(v, act, slope));
+            for (int j = 0; j < 8; ++j) {
+                float t = v[j] * (scale ? __ldg(scale + c0 + j) : 1.f) + (shift ? __ldg(shift + c0 + j) : 0.f);
+                if (residual) t += r[j];
+                v[j] = apply_act(t, act, slope);
+            }
+            V8io<TY>::st(y + pix * y_ld + c0, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = c0 + j;
+                if (ch < c) {
+                    float v = to_f32(x[pix * x_ld + ch]) * (scale ? scale[ch] : 1.f) + (shift ? shift[ch] : 0.f);
+                    if (residual) v += to_f32(residual[pix * res_ld + ch]);
+                    y[pix * y_ld + ch] = from_f32<TY>(apply_act(v, act, slope));
+                }
             }
         }
     }
@@ -361,23 +399,23 @@ extern "C" int rtsds_scale_shift_act(const void* x, const float* scale, const fl
     if (n_pix == 0) return RTSDS_OK;
     const int grid = grid_for(n_pix * ((c + 7) / 8), 256);
     cudaStream_t st = as_stream(s);
-    if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_BF16)
-        scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
-            reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(residual), n_pix, c,
-            x_ld, res_ld, y_ld, act, slope, reinterpret_cast<__nv_bfloat16*>(y));
-    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_F32)
-        scale_shift_act_kernel<float, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), scale, shift,
-                                                                   reinterpret_cast<const float*>(residual), n_pix, c, x_ld,
-                                                                   res_ld, y_ld, act, slope, reinterpret_cast<float*>(y));
-    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_BF16)
-        scale_shift_act_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(
-            reinterpret_cast<const float*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(residual), n_pix, c, x_ld,
-            res_ld, y_ld, act, slope, reinterpret_cast<__nv_bfloat16*>(y));
-    else if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_F32)
-        scale_shift_act_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(
-            reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const float*>(residual), n_pix, c, x_ld,
-            res_ld, y_ld, act, slope, reinterpret_cast<float*>(y));
+    const size_t ex = x_dtype == RTSDS_BF16 ? 2 : 4, ey = y_dtype == RTSDS_BF16 ? 2 : 4;
+    const bool vec = c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && (!residual || res_ld % 8 == 0) &&
+                     (reinterpret_cast<uintptr_t>(x) % (8 * ex) == 0) && (reinterpret_cast<uintptr_t>(y) % (8 * ey) == 0) &&
+                     (!residual || reinterpret_cast<uintptr_t>(residual) % (8 * ey) == 0);
+#define SSA(TX, TY)                                                                                                        \
+    do {                                                                                                                   \
+        if (vec) scale_shift_act_kernel<TX, TY, true><<<grid, 256, 0, st>>>(reinterpret_cast<const TX*>(x), scale, shift,     \
+                     reinterpret_cast<const TY*>(residual), n_pix, c, x_ld, res_ld, y_ld, act, slope, reinterpret_cast<TY*>(y)); \
+        else scale_shift_act_kernel<TX, TY, false><<<grid, 256, 0, st>>>(reinterpret_cast<const TX*>(x), scale, shift,        \
+                     reinterpret_cast<const TY*>(residual), n_pix, c, x_ld, res_ld, y_ld, act, slope, reinterpret_cast<TY*>(y)); \
+    } while (0)
+    if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_BF16) SSA(__nv_bfloat16, __nv_bfloat16);
+    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_F32) SSA(float, float);
+    else if (x_dtype == RTSDS_F32 && y_dtype == RTSDS_BF16) SSA(float, __nv_bfloat16);
+    else if (x_dtype == RTSDS_BF16 && y_dtype == RTSDS_F32) SSA(__nv_bfloat16, float);
     else { set_error("scale_shift_act: bad dtype"); return RTSDS_EINVAL; }
+#undef SSA
     count_launch();
     return check_launch("scale_shift_act_kernel");
 }

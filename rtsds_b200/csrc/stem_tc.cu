@@ -1,0 +1,471 @@
+// Tensor-core stems: the two first convolutions of BiSeNet read the same image
+//   context path  conv7x7 s2 p3 3->64 (torchvision resnet conv1, build_contextpath.py:19)
+//   spatial path  conv3x3 s2 p1 3->64 (build_bisenet.py:24)
+// and have the same output grid, and the 3x3 window is the centre of the 7x7 window.  They are fused
+// into ONE implicit GEMM:  D[128 pixels, 128 = 64 cp + 64 sp channels] = A[128, K] * B[128, K]^T,
+// K = 3*7*7 = 147 (padded to 192), the 3x3 weights embedded (zero-padded) in the 7x7 K layout.
+//
+// There is no TMA path for an im2col of a 3-channel NCHW fp32 image, so the A tile is built by
+// 128 gather threads (one output pixel each): 147 L1-cached loads, converted to bf16 and written
+// with 16-byte stores straight into the 128-byte-swizzled K-major UMMA layout (conflict-free thanks
+// to the swizzle).  Persistent CTAs, warp-specialised:
+//   warps 0-3  gather (double-buffered A), warp 4 MMA issuer (tcgen05, 2 TMEM accumulators),
+//   warps 5-8  epilogue (tcgen05.ld -> folded BN + ReLU -> bf16 NHWC to both outputs; train mode:
+//              raw outputs + per-channel sum / sum of squares).
+// The same gathered tile is also exactly the MN-major B operand of the weight-gradient GEMM
+//   dW[128 co, K] = sum_pixels d_raw[pix, co] * im2col[pix, K]
+// (stem_wgrad_tc_kernel): d_raw tiles arrive by TMA, the im2col tile is re-gathered.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cstring>
+
+namespace rtsds {
+
+constexpr int SK = 192;                         // padded K (3 swizzle atoms of 64 bf16)
+constexpr int SK_REAL = 147;
+constexpr int S_ATOM_BYTES = 128 * 128;         // 128 rows x 128 B
+constexpr int S_A_BYTES = 3 * S_ATOM_BYTES;     // one gathered tile: 48 KiB
+constexpr int S_THREADS = 9 * 32;
+
+struct StemTcParams {
+    const float* x;            // NCHW fp32 [n,3,h,w]
+    int n, h, w, oh, ow;
+    int tile_w, tile_h, tiles_w, tiles_h, tiles_total;
+    // forward
+    const __nv_bfloat16* wpk;  // [128][192] bf16, K order (c, r, s) of the 7x7 window
+    const float* scale;        // [128] or NULL
+    const float* shift;        // [128] or NULL
+    int relu;
+    float* stats_cp;           // [2*64] or NULL (train)
+    float* stats_sp;
+    __nv_bfloat16* y_cp;       // NHWC [n,oh,ow,64]
+    __nv_bfloat16* y_sp;
+    // wgrad
+    float* dw;                 // [128][192] fp32, accumulated
+};
+
+// one thread gathers the 7x7x3 window of output pixel (img, oy, ox) into row `m` of the swizzled tile.
+// Fully unrolled: every k = (c*7 + r)*7 + s is a compile-time constant, so the 8-value staging
+// registers never touch local memory.
+__device__ __forceinline__ void gather_row(const StemTcParams& p, uint8_t* tile, int m, int img, int oy, int ox, bool valid) {
+    const int iy0 = oy * 2 - 3, ix0 = ox * 2 - 3;
+    const float* xi = p.x + static_cast<long long>(img) * 3 * p.h * p.w + static_cast<long long>(iy0) * p.w + ix0;
+    unsigned rmask = 0, cmask = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        if (valid && iy0 + i >= 0 && iy0 + i < p.h) rmask |= 1u << i;
+        if (ix0 + i >= 0 && ix0 + i < p.w) cmask |= 1u << i;
+    }
+    const long long plane = static_cast<long long>(p.h) * p.w;
+#pragma unroll
+    for (int chunk = 0; chunk < SK / 8; ++chunk) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = chunk * 8 + e;
+            if (k < SK_REAL) {
+                const int c = k / 49, r = (k % 49) / 7, sx = k % 7;
+                const bool ok = ((rmask >> r) & 1u) && ((cmask >> sx) & 1u);
+                v[e] = ok ? __ldg(xi + c * plane + static_cast<long long>(r) * p.w + sx) : 0.f;
+            } else {
+                v[e] = 0.f;
+            }
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        const int atom = chunk >> 3, j = chunk & 7;
+        *reinterpret_cast<uint4*>(tile + atom * S_ATOM_BYTES + m * 128 + ((j ^ (m & 7)) << 4)) = u;
+    }
+}
+
+__device__ __forceinline__ void tile_coords(const StemTcParams& p, int t, int m, int* img, int* oy, int* ox) {
+    const int per = p.tiles_w * p.tiles_h;
+    *img = t / per;
+    const int r = t - *img * per;
+    const int th = r / p.tiles_w;
+    const int ml = m / p.tile_w;
+    *oy = th * p.tile_h + ml;
+    *ox = (r - th * p.tiles_w) * p.tile_w + (m - ml * p.tile_w);
+}
+
+__device__ __forceinline__ float warp_tsum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+stem_fwd_tc_kernel(const StemTcParams p) {
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 128);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_a = smem;                                   // 2 x 48 KiB
+    uint8_t* s_b = smem + 2 * S_A_BYTES;                   // 48 KiB: weights [128 rows][192 k], K-major swizzled
+    float* s_scale = reinterpret_cast<float*>(s_b + S_A_BYTES);
+    float* s_shift = s_scale + 128;
+    float* s_stats = s_shift + 128;                        // [2*128]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(s_stats + 256);      // [2]
+    uint64_t* a_empty = a_full + 2;                                     // [2]
+    uint64_t* d_full = a_empty + 2;                                     // [2]
+    uint64_t* d_empty = d_full + 2;                                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // weights -> smem (swizzled), scale/shift, barriers
+    for (int i = threadIdx.x; i < 128 * (SK / 8); i += S_THREADS) {
+        const int row = i / (SK / 8), chunk = i - row * (SK / 8);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.wpk + row * SK + chunk * 8));
+        const int atom = chunk >> 3, j = chunk & 7;
+        *reinterpret_cast<uint4*>(s_b + atom * S_ATOM_BYTES + row * 128 + ((j ^ (row & 7)) << 4)) = u;
+    }
+    for (int i = threadIdx.x; i < 128; i += S_THREADS) {
+        s_scale[i] = p.scale ? p.scale[i] : 1.f;
+        s_shift[i] = p.shift ? p.shift[i] : 0.f;
+        s_stats[i] = 0.f; s_stats[128 + i] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
+            ptx::mbar_init(&d_full[i], 1); ptx::mbar_init(&d_empty[i], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    ptx::fence_proxy_async();                              // weight tile written by generic stores, read by UMMA
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================= gather =================
+        const int m = threadIdx.x;                         // row of the tile
+        int it = 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            ptx::mbar_wait(&a_empty[buf], ph ^ 1);
+            int img, oy, ox;
+            tile_coords(p, t, m, &img, &oy, &ox);
+            gather_row(p, s_a + buf * S_A_BYTES, m, img, oy, ox, oy < p.oh && ox < p.ow);
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&a_full[buf]);
+        }
+    } else if (warp == 4) {
+        // ================= MMA =================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                ptx::mbar_wait(&d_empty[buf], ph ^ 1);     // epilogue drained this accumulator
+                ptx::mbar_wait(&a_full[buf], ph);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(s_a + buf * S_A_BYTES), sb = ptx::smem_u32(s_b);
+#pragma unroll
+                for (int k = 0; k < SK / 16; ++k) {
+                    const uint32_t off = (k >> 2) * S_ATOM_BYTES + (k & 3) * 32;
+                    ptx::umma_bf16(tmem_base + buf * 128, ptx::umma_desc_k_sw128(sa + off), ptx::umma_desc_k_sw128(sb + off),
+                                   IDESC, k > 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&a_empty[buf]);
+                ptx::umma_commit(&d_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            int img, oy, ox;
+            tile_coords(p, t, m, &img, &oy, &ox);
+            const bool valid = oy < p.oh && ox < p.ow;
+            const long long pix = (static_cast<long long>(img) * p.oh + oy) * p.ow + ox;
+            ptx::mbar_wait(&d_full[buf], ph);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.stats_cp) {
+                    float tt[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tt[j] = valid ? v[j] : 0.f;
+                    const float s1 = warp_tsum(tt, lane);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tt[j] = valid ? v[j] * v[j] : 0.f;
+                    const float s2 = warp_tsum(tt, lane);
+                    atomicAdd(&s_stats[c0 + lane], s1);
+                    atomicAdd(&s_stats[128 + c0 + lane], s2);
+                }
+                if (valid) {
+                    __nv_bfloat16* dst = (c0 < 64 ? p.y_cp : p.y_sp) + pix * 64 + (c0 & 63);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float xv = v[g * 8 + j] * s_scale[c0 + g * 8 + j] + s_shift[c0 + g * 8 + j];
+                            o[j] = p.relu ? fmaxf(xv, 0.f) : xv;
+                        }
+                        uint4 u;
+                        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+                        u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+                        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&d_empty[buf]);
+        }
+        if (p.stats_cp) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int i = threadIdx.x - 160;              // 0..127
+            float* dst = i < 64 ? p.stats_cp : p.stats_sp;
+            atomicAdd(&dst[i & 63], s_stats[i]);
+            atomicAdd(&dst[64 + (i & 63)], s_stats[128 + i]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+}
+
+// ---- weight gradient: dW[128 co][192 k] += sum_pixels d_raw[pix][co] * im2col[pix][k] --------------------
+struct StemWgMaps { CUtensorMap d_cp, d_sp; };      // d_raw [64, ow, oh, n] bf16 each
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, SK, 1, 1);     // both operands MN-major, N = 192
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_b = smem;                                   // 2 x 48 KiB gathered im2col tiles
+    uint8_t* s_a = smem + 2 * S_A_BYTES;                   // 2 x 32 KiB d_raw tiles (two 64-channel boxes)
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(s_a + 2 * 2 * S_ATOM_BYTES);
+    uint64_t* a_full = b_full + 2;
+    uint64_t* empty = a_full + 2;
+    uint64_t* d_full = empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&maps.d_cp); ptx::prefetch_tmap(&maps.d_sp);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&b_full[i], 128); ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(d_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool have = static_cast<int>(blockIdx.x) < p.tiles_total;
+
+    if (warp < 4) {
+        const int m = threadIdx.x;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            ptx::mbar_wait(&empty[buf], ph ^ 1);
+            int img, oy, ox;
+            tile_coords(p, t, m, &img, &oy, &ox);
+            if (m == 0) {       // d_raw tiles by TMA (out-of-range pixels are zero-filled: they contribute nothing)
+                ptx::mbar_expect_tx(&a_full[buf], 2 * S_ATOM_BYTES);
+                ptx::tma_load_4d(s_a + buf * 2 * S_ATOM_BYTES, &maps.d_cp, &a_full[buf], 0, ox, oy, img);
+                ptx::tma_load_4d(s_a + buf * 2 * S_ATOM_BYTES + S_ATOM_BYTES, &maps.d_sp, &a_full[buf], 0, ox, oy, img);
+            }
+            gather_row(p, s_b + buf * S_A_BYTES, m, img, oy, ox, oy < p.oh && ox < p.ow);
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&b_full[buf]);
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                ptx::mbar_wait(&a_full[buf], ph);
+                ptx::mbar_wait(&b_full[buf], ph);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(s_a + buf * 2 * S_ATOM_BYTES), sb = ptx::smem_u32(s_b + buf * S_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < 128 / 16; ++k)       // 16 pixels per MMA
+                    ptx::umma_bf16(tmem_base, ptx::umma_desc_mn_sw128(sa + k * 2048, S_ATOM_BYTES),
+                                   ptx::umma_desc_mn_sw128(sb + k * 2048, S_ATOM_BYTES), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                ptx::umma_commit(&empty[buf]);
+            }
+            if (have) ptx::umma_commit(d_full);
+        }
+        __syncwarp();
+    } else if (have) {
+        const int q = warp & 3;
+        const int co = q * 32 + lane;
+        ptx::mbar_wait(d_full, 0);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < SK; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < SK_REAL) atomicAdd(&p.dw[co * SK + c0 + j], __uint_as_float(r[j]));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+}
+
+// pack both stems' OIHW fp32 weights into the fused [128][192] bf16 operand
+__global__ void stem_pack_kernel(const float* __restrict__ w7, const float* __restrict__ w3, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * SK) return;
+    const int row = i / SK, k = i - row * SK;
+    float v = 0.f;
+    if (k < SK_REAL) {
+        const int c = k / 49, r = (k % 49) / 7, s = k % 7;
+        if (row < 64) v = w7[(row * 3 + c) * 49 + r * 7 + s];
+        else if (r >= 2 && r <= 4 && s >= 2 && s <= 4) v = w3[((row - 64) * 3 + c) * 9 + (r - 2) * 3 + (s - 2)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+// scatter the fused fp32 gradient [128][192] back to the two OIHW gradients (accumulate), and clear it
+__global__ void stem_unpack_kernel(float* __restrict__ dw, float* __restrict__ g7, float* __restrict__ g3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * SK) return;
+    const int row = i / SK, k = i - row * SK;
+    const float v = dw[i];
+    dw[i] = 0.f;
+    if (k >= SK_REAL) return;
+    const int c = k / 49, r = (k % 49) / 7, s = k % 7;
+    if (row < 64) { if (g7) g7[(row * 3 + c) * 49 + r * 7 + s] += v; }
+    else if (g3 && r >= 2 && r <= 4 && s >= 2 && s <= 4) g3[((row - 64) * 3 + c) * 9 + (r - 2) * 3 + (s - 2)] += v;
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int stem_geometry(int n, int h, int w, StemTcParams* p) {
+    p->n = n; p->h = h; p->w = w;
+    p->oh = (h - 1) / 2 + 1; p->ow = (w - 1) / 2 + 1;
+    p->tile_w = p->ow >= 32 ? 32 : (p->ow >= 16 ? 16 : 8);
+    p->tile_h = 128 / p->tile_w;
+    p->tiles_w = static_cast<int>(cdiv(p->ow, p->tile_w));
+    p->tiles_h = static_cast<int>(cdiv(p->oh, p->tile_h));
+    const long long tt = static_cast<long long>(n) * p->tiles_w * p->tiles_h;
+    if (tt >= (1LL << 30)) { set_error("stem_tc: too many tiles"); return RTSDS_EINVAL; }
+    p->tiles_total = static_cast<int>(tt);
+    return RTSDS_OK;
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, void* wpk, rtsds_stream_t s) {
+    RTSDS_REQUIRE(w7_oihw && w3_oihw && wpk, "stem_pack_weights: NULL argument");
+    stem_pack_kernel<<<static_cast<int>(cdiv(128 * SK, 256)), 256, 0, as_stream(s)>>>(w7_oihw, w3_oihw,
+                                                                                   reinterpret_cast<__nv_bfloat16*>(wpk));
+    count_launch();
+    return check_launch("stem_pack_kernel");
+}
+
+// Fused tensor-core stems.  x: NCHW fp32 [n,3,h,w]; wpk from rtsds_stem_pack_weights; scale/shift: fp32 [128]
+// (context-path BN in 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
+extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                                      const float* shift, int relu, float* stats_cp, float* stats_sp, void* y_cp,
+                                      void* y_sp, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && wpk && y_cp && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
+    RTSDS_REQUIRE((stats_cp == nullptr) == (stats_sp == nullptr), "stem_pair_tc_fwd: stats go together");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    StemTcParams p;
+    memset(&p, 0, sizeof(p));
+    rc = stem_geometry(n, h, w, &p);
+    if (rc != RTSDS_OK) return rc;
+    p.x = x; p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.scale = scale; p.shift = shift; p.relu = relu;
+    p.stats_cp = stats_cp; p.stats_sp = stats_sp;
+    p.y_cp = reinterpret_cast<__nv_bfloat16*>(y_cp); p.y_sp = reinterpret_cast<__nv_bfloat16*>(y_sp);
+    const size_t smem = 1024 + 3 * S_A_BYTES + 512 * 4 + 8 * 8 + 16;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("stem_pair_tc_fwd: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        done = true;
+    }
+    const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
+    stem_fwd_tc_kernel<<<grid, S_THREADS, smem, as_stream(s)>>>(p);
+    count_launch();
+    return check_launch("stem_fwd_tc_kernel");
+}
+
+// Fused weight gradient of both stems.  d_raw_*: NHWC bf16 [n,oh,ow,64]; dw_ws: fp32 [128*192] scratch that is
+// zero on entry and zero again on return; g7/g3: OIHW fp32 gradients, accumulated (NULL = frozen).
+extern "C" int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_raw_cp, const void* d_raw_sp,
+                                        float* dw_ws, float* g7_oihw, float* g3_oihw, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && d_raw_cp && d_raw_sp && dw_ws && n > 0 && h > 0 && w > 0, "stem_pair_tc_wgrad: bad argument");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    StemTcParams p;
+    memset(&p, 0, sizeof(p));
+    rc = stem_geometry(n, h, w, &p);
+    if (rc != RTSDS_OK) return rc;
+    p.x = x; p.dw = dw_ws;
+    static EncodeTiledFn2 enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("stem_pair_tc_wgrad: cuTensorMapEncodeTiled unavailable");
+            return RTSDS_ECUDA;
+        }
+        enc = reinterpret_cast<EncodeTiledFn2>(fp);
+    }
+    StemWgMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const void* bases[2] = {d_raw_cp, d_raw_sp};
+    CUtensorMap* ms[2] = {&maps.d_cp, &maps.d_sp};
+    for (int i = 0; i < 2; ++i) {
+        cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(p.ow), static_cast<cuuint64_t>(p.oh), static_cast<cuuint64_t>(n)};
+        cuuint64_t strides[3] = {64 * 2, static_cast<cuuint64_t>(p.ow) * 64 * 2, static_cast<cuuint64_t>(p.oh) * p.ow * 64 * 2};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.tile_w), static_cast<cuuint32_t>(p.tile_h), 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[i]), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("stem_pair_tc_wgrad: cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return RTSDS_ECUDA; }
+    }
+    const size_t smem = 1024 + 2 * S_A_BYTES + 4 * S_ATOM_BYTES + 7 * 8 + 16;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("stem_pair_tc_wgrad: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        done = true;
+    }
+    const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
+    cudaStream_t st = as_stream(s);
+    stem_wgrad_tc_kernel<<<grid, S_THREADS, smem, st>>>(maps, p);
+    stem_unpack_kernel<<<static_cast<int>(cdiv(128 * SK, 256)), 256, 0, st>>>(dw_ws, g7_oihw, g3_oihw);
+    count_launch(2);
+    return check_launch("stem_wgrad_tc kernels");
+}

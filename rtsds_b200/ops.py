@@ -170,6 +170,25 @@ def stem_conv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, k: int, stride:
                                     slope, int(softmax_in), _p(stats), dtype_code(y.dtype), _p(y), _s()), "stem_conv_fwd")
 
 
+def stem_pack_weights(w7: torch.Tensor, w3: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((128, 192), dtype=torch.bfloat16, device=w7.device)
+    check(lib().rtsds_stem_pack_weights(_p(w7.detach()), _p(w3.detach()), _p(out), _s()), "stem_pack_weights")
+    return out
+
+
+def stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale=None, shift=None, relu=True, stats_cp=None, stats_sp=None) -> None:
+    n, _, h, w = x.shape
+    check(lib().rtsds_stem_pair_tc_fwd(_p(x), n, h, w, _p(wpk), _p(scale), _p(shift), int(relu), _p(stats_cp), _p(stats_sp),
+                                       _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
+
+
+def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
+    n, _, h, w = x.shape
+    check(lib().rtsds_stem_pair_tc_wgrad(_p(x), n, h, w, _p(d_raw_cp), _p(d_raw_sp), _p(dw_ws), _p(g7), _p(g3), _s()),
+          "stem_pair_tc_wgrad")
+
+
 def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, ceil_mode: bool = False) -> None:
     n, h, w, c = x.shape
     check(lib().rtsds_maxpool3x3s2_fwd(_p(x), n, h, w, c, dtype_code(x.dtype), int(ceil_mode), _p(y), _s()), "maxpool")

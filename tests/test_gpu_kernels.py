@@ -291,3 +291,51 @@ def test_ce_argmax_nchw(cuda):
     a = acc.cpu()
     assert abs(a[0].item() / a[1].item() - ref.item()) < 1e-5
     assert (pred.cpu() == logits.argmax(1)).all()
+
+
+# ----------------------------------------------------------------------------- fused tensor-core stems
+@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (1, 512, 1024)])
+@pytest.mark.parametrize("train", [False, True])
+def test_stem_pair_tc(cuda, n, h, w, train):
+    g = torch.Generator().manual_seed(h + w)
+    x = torch.randn(n, 3, h, w, generator=g)
+    w7 = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    w3 = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    scale = torch.rand(128, generator=g) + 0.5
+    shift = torch.randn(128, generator=g)
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    wpk = ops.stem_pack_weights(w7.cuda(), w3.cuda())
+    ycp = torch.full((n, oh, ow, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ysp = torch.full((n, oh, ow, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    xr, w7r, w3r = x.bfloat16().float(), w7.bfloat16().float(), w3.bfloat16().float()
+    raw7 = F.conv2d(xr, w7r, None, 2, 3)
+    raw3 = F.conv2d(xr, w3r, None, 2, 1)
+    if train:
+        st7 = torch.zeros(128, device="cuda"); st3 = torch.zeros(128, device="cuda")
+        ops.stem_pair_tc_fwd(x.cuda(), wpk, ycp, ysp, None, None, False, st7, st3)
+        assert rel_err(nchw(ycp), raw7) < 1e-2 and rel_err(nchw(ysp), raw3) < 1e-2
+        assert rel_err(st7[:64].cpu(), raw7.sum((0, 2, 3))) < 2e-3 and rel_err(st7[64:].cpu(), (raw7 * raw7).sum((0, 2, 3))) < 2e-3
+        assert rel_err(st3[:64].cpu(), raw3.sum((0, 2, 3))) < 2e-3 and rel_err(st3[64:].cpu(), (raw3 * raw3).sum((0, 2, 3))) < 2e-3
+    else:
+        ops.stem_pair_tc_fwd(x.cuda(), wpk, ycp, ysp, scale.cuda(), shift.cuda(), True)
+        r7 = F.relu(raw7 * scale[:64].view(1, -1, 1, 1) + shift[:64].view(1, -1, 1, 1))
+        r3 = F.relu(raw3 * scale[64:].view(1, -1, 1, 1) + shift[64:].view(1, -1, 1, 1))
+        assert rel_err(nchw(ycp), r7) < 1e-2 and rel_err(nchw(ysp), r3) < 1e-2
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (2, 256, 512)])
+def test_stem_pair_tc_wgrad(cuda, n, h, w):
+    g = torch.Generator().manual_seed(h * 3 + w)
+    x = torch.randn(n, 3, h, w, generator=g)
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    d7 = torch.randn(n, 64, oh, ow, generator=g)
+    d3 = torch.randn(n, 64, oh, ow, generator=g)
+    xr = x.bfloat16().float()
+    w7 = torch.zeros(64, 3, 7, 7, requires_grad=True); w3 = torch.zeros(64, 3, 3, 3, requires_grad=True)
+    (F.conv2d(xr, w7, None, 2, 3) * d7.bfloat16().float()).sum().backward()
+    (F.conv2d(xr, w3, None, 2, 1) * d3.bfloat16().float()).sum().backward()
+    ws = torch.zeros(128 * 192, device="cuda")
+    g7 = torch.ones(64, 3, 7, 7, device="cuda"); g3 = torch.ones(64, 3, 3, 3, device="cuda")
+    ops.stem_pair_tc_wgrad(x.cuda(), nhwc(d7, torch.bfloat16), nhwc(d3, torch.bfloat16), ws, g7, g3)
+    assert rel_err(g7.cpu() - 1, w7.grad) < 2e-3 and rel_err(g3.cpu() - 1, w3.grad) < 2e-3
+    assert (ws == 0).all()
