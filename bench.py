@@ -206,6 +206,7 @@ def run_infer(args, rank, world, local):
     dev_in = host.to(dev)
     K, Wm = args.steps, args.warmup
 
+    cuda_graph = bool(model.rtsds_cuda_graph)
     with torch.no_grad():
         for i in range(Wm):
             model(dev_in[i % n_inputs])
@@ -272,6 +273,17 @@ def run_infer(args, rank, world, local):
 
         rows = tc_conv_profile(model, dev_in[0]) if rank == 0 else []
 
+    # ---- the other half of BASELINE.json's metric: data-parallel training images/s (configs[2]) ----
+    train = None
+    if not args.no_train:
+        import bench_train
+
+        del dev_in, host, model
+        torch.cuda.empty_cache()
+        tk = max(5, min(K // 8, 30))
+        tr = bench_train.measure_train(args, rank, world, local, tk, 3, args.batch)
+        train = bench_train.train_summary(tr, world, args.batch, tk)
+
     if rank != 0:
         return
     pk = peaks()
@@ -289,7 +301,7 @@ def run_infer(args, rank, world, local):
                    "weights": "random-init, seeded", "parallelism": "replicas only" if world > 1 else "single GPU",
                    "l2": "inputs rotate over 32 distinct images (201 MB > 126 MB L2); weights stay L2-resident as in "
                          "steady-state serving; latency_cold_l2_ms flushes L2 before every iteration",
-                   "cuda_graph": bool(model.rtsds_cuda_graph)},
+                   "cuda_graph": cuda_graph},
         "clocks": clk.summary(),
         "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                 "d2h_bytes_per_step": H * W * 8, "ms_per_step": round(e2e_ms / K, 4)},
@@ -307,6 +319,7 @@ def run_infer(args, rank, world, local):
                        "algorithmic_gbs": round(hbm_achieved, 1), "frac_of_hbm_peak": round(hbm_achieved / pk["hbm_gbs"], 4)},
         "conv_layers": [{"layer": r[2], "ms": round(r[3], 4), "tflops": round(r[0] / (r[3] * 1e-3) / 1e12, 1),
                          "gbs": round(r[1] / (r[3] * 1e-3) / 1e9, 1)} for r in rows],
+        "train": train,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -365,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="rtsds_b200", choices=["rtsds_b200", "reference"])
     ap.add_argument("--workload", default="infer", choices=["infer", "train"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch of the train workload")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

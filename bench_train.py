@@ -31,13 +31,9 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
     dev = torch.device("cuda", local)
     model = bench.make_model(dev).train()
     model.rtsds_ddp = world > 1
-    if world > 1:
-        import torch.distributed as dist
+    from rtsds_b200 import ddp
 
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-        for b in model.buffers():
-            dist.broadcast(b.data, 0)
+    ddp.broadcast_module(model, 0)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     n_sets = 4                                           # 4 x b x 11 MB images: far larger than the 126 MB L2 for b >= 4
     g = torch.Generator().manual_seed(42 + rank)
@@ -95,16 +91,30 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
         for _ in range(4):
             out = model(vx)
             ops.argmax_hist(out, vy, hist, None)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(hist)
+    ddp.allreduce_confusion(hist)
     hh = hist.cpu().numpy().reshape(19, 19).astype("float64")
     import numpy as np
 
     iou = np.diag(hh) / (hh.sum(1) + hh.sum(0) - np.diag(hh) + 1e-5)        # utils.per_class_iou
     return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, loss=last_loss, clocks=clk.summary(), miou=float(np.nanmean(iou)),
                 h2d=batch * (3 * h * w * 4 + h * w * 8))
+
+
+def train_summary(r, world, batch, K):
+    """Compact object attached to the default (inference) bench line."""
+    import bench
+
+    pk = bench.peaks()
+    img_s = world * batch * K / (r["ms"] / 1e3)
+    per_gpu = img_s / world
+    return {"metric": "BiSeNet-R18 720x1280 data-parallel training throughput", "value": round(img_s, 2), "unit": "images/s",
+            "per_gpu_batch": batch, "steps": K, "ms_per_step": round(r["ms"] / K, 3),
+            "e2e_images_per_s": round(world * batch * K / (r["ms_e2e"] / 1e3), 2), "launches_per_step": int(r["launches"]),
+            "tflops_per_gpu": round(per_gpu * TRAIN_GFLOP_PER_IMG_720 / 1e3, 2),
+            "frac_of_bf16_sustained_peak": round(per_gpu * TRAIN_GFLOP_PER_IMG_720 / 1e3 / pk["bf16_tflops_sustained"], 4),
+            "algorithmic_gbs_per_gpu": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3, 1),
+            "frac_of_hbm_peak": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3 / pk["hbm_gbs"], 4),
+            "final_loss": round(r["loss"], 4), "parallelism": f"dp{world}, NCCL bucketed all-reduce overlapped with backward"}
 
 
 def run_train(args, rank, world, local):

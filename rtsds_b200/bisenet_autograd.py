@@ -46,13 +46,19 @@ def _grad_tuple(plan, params, gw):
     return tuple(None if (p in plan.unused or p not in gw) else gw[p] for p in params)
 
 
-def _allreduce(flat):
-    """Data-parallel gradient all-reduce (NCCL over NVLink) when a process group is active."""
-    import torch.distributed as dist
+def _run_backward(plan, gw, flat):
+    """Backward + (when model.rtsds_ddp and a process group is active) the bucketed gradient all-reduce
+    overlapped with it (rtsds_b200/ddp.py)."""
+    from . import ddp
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.mul_(1.0 / dist.get_world_size())
+    if getattr(plan.model, "rtsds_ddp", False) and ddp.is_distributed():
+        if getattr(plan, "_buckets", None) is None:
+            plan._buckets = ddp.param_buckets(list(plan.model.named_parameters()), ddp.BISENET_GROUPS)
+        red = ddp.BucketedAllReduce(flat, plan._buckets)
+        plan.backward_from_dz(gw, red.ready)
+        red.finish()
+    else:
+        plan.backward_from_dz(gw)
 
 
 class _BiSeNetTrainFn(torch.autograd.Function):
@@ -80,9 +86,7 @@ class _BiSeNetTrainFn(torch.autograd.Function):
                 check(lib().rtsds_resize_to_nchw_bwd(_p(d), plan.n, plan.nc, oh, ow, plan.h8, plan.w8, _p(plan.dz[i]), 32, s),
                       "resize_to_nchw_bwd")
         flat, gw = plan.new_grads()
-        plan.backward_from_dz(gw)
-        if getattr(plan.model, "rtsds_ddp", False):
-            _allreduce(flat)
+        _run_backward(plan, gw, flat)
         return (None, None) + _grad_tuple(plan, ctx.params, gw)
 
 
@@ -132,9 +136,7 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
             ops.resize_ce_bwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, ctx.target, ctx.ignore_index,
                               plan.gscale[i:i + 1], plan.dz[i])
         flat, gw = plan.new_grads()
-        plan.backward_from_dz(gw)
-        if getattr(plan.model, "rtsds_ddp", False):
-            _allreduce(flat)
+        _run_backward(plan, gw, flat)
         return (None, None, None, None) + _grad_tuple(plan, ctx.params, gw)
 
 

@@ -411,8 +411,9 @@ class BiSeNetTrainPlan:
             off += p.numel()
         return flat, gw
 
-    def backward_from_dz(self, gw):
-        """self.dz[0..2] hold the gradients w.r.t. z, z1, z2 (fp32 NHWC pitch 32)."""
+    def backward_from_dz(self, gw, ready=lambda group: None):
+        """self.dz[0..2] hold the gradients w.r.t. z, z1, z2 (fp32 NHWC pitch 32).  `ready(group)` is called
+        as soon as every parameter gradient of a bucket (rtsds_b200/ddp.py) is final."""
         m, n, dt = self.model, self.n, self.dt
         s = _s()
         a = self.arm
@@ -458,6 +459,7 @@ class BiSeNetTrainPlan:
             check(lib().rtsds_gate_bwd_finish(_p(dgt), _p(a["gate" + tag]), _p(a["dpooled" + tag]), 1.0 / hw, n, hw, c, dt,
                                               dfb.ptr, s), "gate_bwd_finish")
             dF[tag] = dfb
+        ready("head")
         # ---- ResNet-18 stages in reverse ----
         # gA holds the gradient of f4 (block 7 output); gB the ARM1 part of the gradient of f3 (block 5
         # output = block 6 input).  A block consumes dy completely (BN backward of conv2) before its input
@@ -477,6 +479,8 @@ class BiSeNetTrainPlan:
                 self._copy(g, dx, b["xshape"])            # identity shortcut (never the accumulating block)
             b["c1"].backward(dT, gw, dx=dx, dx_accumulate=True)
             dy = dx
+            if bi in (6, 4, 2):
+                ready({6: "layer4", 4: "layer3", 2: "layer2"}[bi])
         # ---- max-pool and the 7x7 stem ----
         n_, ph, pw, _ = self.pool_shape
         dcp0 = _Buf(self.gT, ld=64, dtype=dt)
