@@ -203,16 +203,16 @@ wgrad_simt_kernel(const WgradSimt p) {
 
 // OIHW fp32 -> [cout_pad][kh*kw][cin]
 template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad,
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int cin_pad, int taps, int cout_pad,
                                    T* __restrict__ out) {
-    const long long total = static_cast<long long>(cout_pad) * taps * cin;
+    const long long total = static_cast<long long>(cout_pad) * taps * cin_pad;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % cin);
-        const long long r = i / cin;
+        const int c = static_cast<int>(i % cin_pad);
+        const long long r = i / cin_pad;
         const int t = static_cast<int>(r % taps);
         const int co = static_cast<int>(r / taps);
-        float v = (co < cout) ? w[(static_cast<long long>(co) * cin + c) * taps + t] : 0.f;
+        float v = (co < cout && c < cin) ? w[(static_cast<long long>(co) * cin + c) * taps + t] : 0.f;
         out[i] = from_f32<T>(v);
     }
 }
@@ -238,21 +238,23 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, 
 // 256 input channels, transposed through shared memory so that both sides are coalesced.
 constexpr int UNP_CI = 256;
 __global__ void __launch_bounds__(256)
-unpack_wgrad_kernel(float* __restrict__ dw, int cout, int cin, int taps, int accumulate, float* __restrict__ grad) {
+unpack_wgrad_kernel(float* __restrict__ dw, int cout, int cin, int cin_src, int taps, int accumulate, float* __restrict__ grad) {
     extern __shared__ float s_t[];                  // [taps][UNP_CI + 1]
     const int co = blockIdx.y;
     const int ci0 = blockIdx.x * UNP_CI;
-    const int nci = min(UNP_CI, cin - ci0);
-    float* src = dw + static_cast<long long>(co) * taps * cin;
+    const int nci = min(UNP_CI, cin_src - ci0);     // source channels (>= cin: padded channels are only cleared)
+    float* src = dw + static_cast<long long>(co) * taps * cin_src;
     for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
         const int t = i / nci, c = i - t * nci;
-        float* p = src + static_cast<long long>(t) * cin + ci0 + c;
+        float* p = src + static_cast<long long>(t) * cin_src + ci0 + c;
         s_t[t * (UNP_CI + 1) + c] = *p;
         *p = 0.f;
     }
     __syncthreads();
+    const int nout = min(nci, cin - ci0);
+    if (nout <= 0) return;
     float* dst = grad + (static_cast<long long>(co) * cin + ci0) * taps;
-    for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
+    for (int i = threadIdx.x; i < taps * nout; i += blockDim.x) {
         const int c = i / taps, t = i - c * taps;
         const float v = s_t[t * (UNP_CI + 1) + c];
         dst[i] = accumulate ? dst[i] + v : v;
@@ -343,21 +345,33 @@ extern "C" int rtsds_conv2d_simt_wgrad(const RtsdsConvDesc* d, const void* x, co
     return check_launch("wgrad_simt_kernel");
 }
 
-extern "C" int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cout_pad,
-                                      int dtype, void* w_packed, rtsds_stream_t s) {
+static int pack_weight_impl(const float* w_oihw, int cout, int cin, int cin_pad, int kh, int kw, int cout_pad, int dtype,
+                            void* w_packed, rtsds_stream_t s) {
     RTSDS_REQUIRE(w_oihw && w_packed, "pack_conv_weight: NULL argument");
-    RTSDS_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout, "pack_conv_weight: bad shape");
+    RTSDS_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout && cin_pad >= cin, "pack_conv_weight: bad shape");
     RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "pack_conv_weight: bad dtype");
-    const long long total = static_cast<long long>(cout_pad) * kh * kw * cin;
+    const long long total = static_cast<long long>(cout_pad) * kh * kw * cin_pad;
     int grid = static_cast<int>(cdiv(total, 256) > 2048 ? 2048 : cdiv(total, 256));
     if (dtype == RTSDS_BF16)
-        pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, kh * kw, cout_pad,
+        pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, cin_pad, kh * kw, cout_pad,
                                                                          reinterpret_cast<__nv_bfloat16*>(w_packed));
     else
-        pack_weight_kernel<float><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, kh * kw, cout_pad,
+        pack_weight_kernel<float><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, cin_pad, kh * kw, cout_pad,
                                                                  reinterpret_cast<float*>(w_packed));
     count_launch();
     return check_launch("pack_weight_kernel");
+}
+
+extern "C" int rtsds_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cout_pad,
+                                      int dtype, void* w_packed, rtsds_stream_t s) {
+    return pack_weight_impl(w_oihw, cout, cin, cin, kh, kw, cout_pad, dtype, w_packed, s);
+}
+
+// as above with the input-channel dimension zero-padded to cin_pad (layers whose activation buffer carries
+// padding channels, e.g. the 19-class probability map padded to 64 for the tensor-core K tile)
+extern "C" int rtsds_pack_conv_weight_cpad(const float* w_oihw, int cout, int cin, int cin_pad, int kh, int kw, int cout_pad,
+                                           int dtype, void* w_packed, rtsds_stream_t s) {
+    return pack_weight_impl(w_oihw, cout, cin, cin_pad, kh, kw, cout_pad, dtype, w_packed, s);
 }
 
 extern "C" int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, int cin_pad, int ck,
@@ -377,13 +391,23 @@ extern "C" int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int c
     return check_launch("pack_weight_dgrad_kernel");
 }
 
-extern "C" int rtsds_unpack_conv_wgrad(float* dw_packed, int cout, int cin, int kh, int kw, int accumulate,
-                                       float* grad_oihw, rtsds_stream_t s) {
-    RTSDS_REQUIRE(dw_packed && grad_oihw && cout > 0 && cin > 0 && kh > 0 && kw > 0, "unpack_conv_wgrad: bad argument");
+static int unpack_impl(float* dw_packed, int cout, int cin, int cin_src, int kh, int kw, int accumulate, float* grad_oihw,
+                       rtsds_stream_t s) {
+    RTSDS_REQUIRE(dw_packed && grad_oihw && cout > 0 && cin > 0 && cin_src >= cin && kh > 0 && kw > 0, "unpack_conv_wgrad: bad argument");
     RTSDS_REQUIRE(cout <= 65535 && kh * kw <= 49, "unpack_conv_wgrad: shape out of range");
-    dim3 grid(static_cast<unsigned>(cdiv(cin, UNP_CI)), cout);
+    dim3 grid(static_cast<unsigned>(cdiv(cin_src, UNP_CI)), cout);
     const size_t smem = sizeof(float) * kh * kw * (UNP_CI + 1);
-    unpack_wgrad_kernel<<<grid, 256, smem, as_stream(s)>>>(dw_packed, cout, cin, kh * kw, accumulate, grad_oihw);
+    unpack_wgrad_kernel<<<grid, 256, smem, as_stream(s)>>>(dw_packed, cout, cin, cin_src, kh * kw, accumulate, grad_oihw);
     count_launch();
     return check_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int rtsds_unpack_conv_wgrad(float* dw_packed, int cout, int cin, int kh, int kw, int accumulate,
+                                       float* grad_oihw, rtsds_stream_t s) {
+    return unpack_impl(dw_packed, cout, cin, cin, kh, kw, accumulate, grad_oihw, s);
+}
+
+extern "C" int rtsds_unpack_conv_wgrad_cpad(float* dw_packed, int cout, int cin, int cin_src, int kh, int kw, int accumulate,
+                                            float* grad_oihw, rtsds_stream_t s) {
+    return unpack_impl(dw_packed, cout, cin, cin_src, kh, kw, accumulate, grad_oihw, s);
 }

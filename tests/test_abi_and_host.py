@@ -88,7 +88,7 @@ def test_bisenet_parameter_tree_matches_reference_contract():
 
 
 def test_plan_launch_sequence_dry_run(monkeypatch):
-    """RTSDS_DRYRUN records launches without a GPU: 22 tensor-core convs, 2 stems, ... per eval forward."""
+    """RTSDS_DRYRUN records launches without a GPU: 22 tensor-core convs, 1 fused stem pair, ... per eval forward."""
     monkeypatch.setenv("RTSDS_DRYRUN", "1")
     from models.bisenet.build_bisenet import BiSeNet
     from rtsds_b200 import _lib
@@ -98,7 +98,8 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     out = m(torch.zeros(1, 3, 512, 1024))
     assert out.shape == (1, 19, 512, 1024)
     c = collections.Counter(_lib.lib().calls)
-    assert c["rtsds_conv2d_tc_fwd"] == 22 and c["rtsds_stem_conv_fwd"] == 2 and c["rtsds_maxpool3x3s2_fwd"] == 1
+    assert c["rtsds_conv2d_tc_fwd"] == 22 and c["rtsds_stem_pair_tc_fwd"] == 1 and c["rtsds_maxpool3x3s2_fwd"] == 1
+    assert c["rtsds_stem_conv_fwd"] == 0          # both stems run as one tensor-core kernel
     assert c["rtsds_arm_gate"] == 2 and c["rtsds_gate_resize_nhwc"] == 2 and c["rtsds_ffm_head"] == 1
     assert c["rtsds_resize_to_nchw"] == 1 and c["rtsds_bn_fold"] == 24
     _lib.lib().calls.clear()
