@@ -309,6 +309,63 @@ int rtsds_ffm_head_bwd(const float* dz, int dz_ld, const float* f, int f_ld, con
 int rtsds_resize_to_nchw_bwd(const float* dout, int n, int c, int oh, int ow, int h, int w,
                              float* dz, int z_ld, rtsds_stream_t s);
 
+/* Variants of pack/unpack with the input-channel dimension zero-padded to cin_pad (activation buffers that
+ * carry padding channels). */
+int rtsds_pack_conv_weight_cpad(const float* w_oihw, int cout, int cin, int cin_pad, int kh, int kw,
+                                int cout_pad, int dtype, void* w_packed, rtsds_stream_t s);
+int rtsds_unpack_conv_wgrad_cpad(float* dw_packed, int cout, int cin, int cin_src, int kh, int kw,
+                                 int accumulate, float* grad_oihw, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * Discriminators (models/domain_shift/adversarial/model.py:30-83) and the
+ * adversarial step around them (train.py:218-263).
+ *
+ * conv1 (num_classes -> 64, 4x4 s2 p1, bias, LeakyReLU 0.2; model.py:45,54 /
+ * :72,78) runs as a 2x2 stride-1 conv over the space-to-depth form of the
+ * padded input:
+ *   xs[n,i,j,(ph*2+pw)*32+c] = x[n,c,2i+ph-1,2j+pw-1]   (zero outside; c < 32)
+ * xs: NHWC [n, h/2+1, w/2+1, 128] of dtype.  s2d_fwd reads the fp32 NCHW
+ * probabilities — or, with softmax != 0, the LOGITS, applying F.softmax(dim=1)
+ * (train.py:225,245,256) on the fly.  s2d_bwd is its adjoint: g fp32 NHWC gradient
+ * w.r.t. xs -> dx fp32 NCHW; p (the forward xs) non-NULL applies the softmax
+ * backward p*(g - sum_k g_k p_k); g is always fp32 (that difference cancels), dtype
+ * describes p.
+ * s2d_weight: OIHW [cout,c,4,4] -> OIHW [cout,128,2,2] (the weight of the 2x2
+ * conv, packed further with rtsds_pack_conv_weight*); s2d_weight_grad is its
+ * adjoint, ACCUMULATING into the [cout,c,4,4] gradient.
+ * ---------------------------------------------------------------------- */
+int rtsds_s2d_out_size(int in_size);
+int rtsds_s2d_fwd(const float* x, int n, int c, int h, int w, int softmax, int dtype, void* xs,
+                  rtsds_stream_t s);
+int rtsds_s2d_bwd(const float* g, const void* p, int n, int c, int h, int w, int dtype, float* dx,
+                  rtsds_stream_t s);
+int rtsds_s2d_weight(const float* w_oihw, int cout, int c, float* w2_oihw, rtsds_stream_t s);
+int rtsds_s2d_weight_grad(const float* gw2_oihw, int cout, int c, float* gw_oihw, rtsds_stream_t s);
+
+/* (Leaky)ReLU backward: d_raw = dy * (y > 0 ? 1 : slope) over NHWC (c % 8 == 0);
+ * dbias[c] += sum d_raw (NULL: skip) — the conv bias gradient (model.py:45-48). */
+int rtsds_act_bwd(const void* dy, int dy_ld, const void* y, int y_ld, int64_t n_pix, int c, int act,
+                  float slope, int dtype, void* d_raw, int d_raw_ld, float* dbias, rtsds_stream_t s);
+
+/* classifier conv (Cout=1, 4x4 s2 p1, bias; model.py:49,58 / :73,80) + AdaptiveAvgPool2d(1) (:52,60 / :76,81):
+ *   out[n] = b + 1/P * sum_{t,c} w[c,t] * tapsum[n,t,c],  tapsum = per-tap sums of x (fp32 [n,16,c],
+ *   written by fwd, consumed by bwd), P = (h/2)*(w/2).  x NHWC [n,h,w,ld], c % 8 == 0.
+ * bwd: g fp32 [n] = dL/dout (times g_scale, e.g. -lambda for the gradient reversal layer, model.py:9-17);
+ *   dw [1,c,4,4] / dbias [1] accumulated (NULL: skip); d_raw (NULL: skip) = dL/dx, multiplied by the
+ *   LeakyReLU mask of x when masked != 0 (x is then the preceding layer's activation output) and
+ *   channel-summed into dbias_prev (NULL: skip). */
+int rtsds_disc_cls_fwd(const void* x, int ld, int dtype, int n, int h, int w, int c, const float* w_oihw,
+                       const float* bias, float* tapsum, float* out, rtsds_stream_t s);
+int rtsds_disc_cls_bwd(const float* g, float g_scale, const float* tapsum, const float* w_oihw, const void* x,
+                       int ld, int dtype, int n, int h, int w, int c, int masked, float slope, void* d_raw,
+                       int d_ld, float* dbias_prev, float* dw, float* dbias, rtsds_stream_t s);
+
+/* nn.BCEWithLogitsLoss (main.py:132-134) of n logits against a constant target (train.py:228-229,
+ * 246-247, 257-258): loss[0] = scale * mean(...), dlogit[i] = scale * (sigmoid(x_i) - target) / n.
+ * Either output may be NULL. */
+int rtsds_bce_logits(const float* logit, int n, float target, float scale, float* loss, float* dlogit,
+                     rtsds_stream_t s);
+
 /* ------------------------------------------------------------------------
  * Loss: bilinear resize + nn.CrossEntropyLoss(ignore_index) (main.py:124-130,
  * train.py:86-92) + argmax / pixel accuracy (train.py:102-106) in one pass

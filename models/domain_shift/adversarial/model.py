@@ -1,0 +1,102 @@
+"""Domain discriminators — drop-in for the reference's models/domain_shift/adversarial/model.py.
+
+Class names, constructor signatures, parameter names/shapes and the forward contract are the
+reference's: `DomainDiscriminator(num_classes=19, with_grl=False, lambda_=0.1)` (:39) is the
+AdaptSegNet FCDiscriminator topology (5x conv4x4 s2 p1, 64/128/256/512/1, LeakyReLU 0.2) followed by
+a global average pool, `TinyDomainDiscriminator(num_classes=19)` (:69) its two-conv version;
+`forward(x)` takes the [N,C,H,W] fp32 class-probability map and returns [N,1,1,1] fp32 logits,
+autograd-tracked, so the stock call sites (train.py:225-229, :245-262: `discriminator(F.softmax(.))`,
+`BCEWithLogitsLoss`, `requires_grad` freezing, `.backward()`) work unchanged.  The modules own
+parameters only; every FLOP runs in hand-written sm_100a kernels (rtsds_b200/disc_engine.py).
+`forward_logits(x)` is the fused fast path: it takes the generator's LOGITS and applies the
+softmax inside the first kernel.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+warnings.filterwarnings(action="ignore")
+
+
+class GradientReversalFunction(Function):
+    """Identity forward, -alpha * grad backward (reference :9-17)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = alpha
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.neg() * ctx.alpha, None
+
+
+class UpSampler(nn.Module):
+    """x8 bilinear + 1x1 conv (reference :19-28; never instantiated by main.py).  Evaluated with the
+    BiSeNet head kernels: the 1x1 conv commutes with the bilinear resize."""
+
+    def __init__(self, num_classes) -> None:
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels=num_classes, out_channels=num_classes, kernel_size=1)
+
+    def forward(self, x):
+        from rtsds_b200.module_ops import upsampler_forward
+
+        return upsampler_forward(self, x)
+
+
+class _DiscBase(nn.Module):
+    def _init_exec(self):
+        # rtsds_b200 execution option (not part of the reference API): "bf16" (tcgen05 path) or
+        # "fp32" (check mode, BASELINE.json 1e-4 tolerance)
+        self.rtsds_precision = "bf16"
+
+    def forward_logits(self, x):
+        """discriminator(F.softmax(x, dim=1)) with the softmax fused into the first kernel."""
+        from rtsds_b200.disc_engine import disc_forward
+
+        return self._grl(disc_forward(self, x, softmax_in=True))
+
+    def _grl(self, out):
+        if getattr(self, "with_grl", False):
+            out = GradientReversalFunction.apply(out, self.lambda_)
+        return out
+
+    def forward(self, x):
+        from rtsds_b200.disc_engine import disc_forward
+
+        return self._grl(disc_forward(self, x, softmax_in=False))
+
+
+class DomainDiscriminator(_DiscBase):
+    def __init__(self, num_classes=19, with_grl=False, lambda_: float = 0.1) -> None:
+        super().__init__()
+        self.with_grl = with_grl
+        self.lambda_ = lambda_
+        # the reference hard-codes 19 input channels here (:45) whatever num_classes says
+        self.conv1 = nn.Conv2d(19, 64, kernel_size=4, stride=2, padding=1)
+        self.conv2 = nn.Conv2d(64, 128, kernel_size=4, stride=2, padding=1)
+        self.conv3 = nn.Conv2d(128, 256, kernel_size=4, stride=2, padding=1)
+        self.conv4 = nn.Conv2d(256, 512, kernel_size=4, stride=2, padding=1)
+        self.classifier = nn.Conv2d(512, 1, kernel_size=4, stride=2, padding=1)
+        self.leaky_relu = nn.LeakyReLU(0.2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self._init_exec()
+
+
+class TinyDomainDiscriminator(_DiscBase):
+    def __init__(self, num_classes=19) -> None:
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_classes, 64, kernel_size=4, stride=2, padding=1)
+        self.classifier = nn.Conv2d(64, 1, kernel_size=4, stride=2, padding=1)
+        self.leaky_relu = nn.LeakyReLU(0.2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self._init_exec()
+
+
+# BASELINE.json's north_star calls the AdaptSegNet topology by its original name
+FCDiscriminator = DomainDiscriminator

@@ -80,6 +80,17 @@ SIGNATURES = {
     "rtsds_resize_ce_argmax_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
     "rtsds_resize_ce_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
     "rtsds_ce_argmax_nchw_fwd": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P]),
+    "rtsds_pack_conv_weight_cpad": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_unpack_conv_wgrad_cpad": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_s2d_out_size": (_I, [_I]),
+    "rtsds_s2d_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_s2d_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_s2d_weight": (_I, [_P, _I, _I, _P, _P]),
+    "rtsds_s2d_weight_grad": (_I, [_P, _I, _I, _P, _P]),
+    "rtsds_act_bwd": (_I, [_P, _I, _P, _I, _L, _I, _I, _F, _I, _P, _I, _P, _P]),
+    "rtsds_disc_cls_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "rtsds_disc_cls_bwd": (_I, [_P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P]),
+    "rtsds_bce_logits": (_I, [_P, _I, _F, _F, _P, _P, _P]),
 }
 
 _lib = None

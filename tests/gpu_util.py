@@ -79,3 +79,10 @@ def conv_ref(x, w, *, stride=1, pad=1, dil=1, scale=None, shift=None, residual=N
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b| (the BASELINE.json 'rel' tolerance)."""
     return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-12)
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a-b||_2 / ||b||_2 — the metric for bf16 GRADIENTS: a bf16 forward flips the (Leaky)ReLU mask of
+    activations within round-off of zero, which changes individual gradient elements by a whole term
+    (max-abs error ~ 1/sqrt(fan)) while the gradient as a vector stays within round-off."""
+    return (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)

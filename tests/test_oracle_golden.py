@@ -79,6 +79,23 @@ def test_fast_hist_properties():
     assert (iou == 0).all()  # empty class -> 0, not NaN (epsilon in the denominator)
 
 
-def test_discriminator_golden_is_loadable(golden_dir):
+@pytest.mark.parametrize("tiny", [True, False])
+def test_discriminator_oracle_matches_reference_outputs(golden_dir, tiny):
+    """oracle/disc_ref.py against the REAL reference's outputs, losses and gradients (gen_golden.gen_discriminators)."""
+    from oracle import disc_ref
+
     gold = np.load(os.path.join(golden_dir, "discriminators.npz"))
-    assert gold["full_out"].shape == (2, 1, 1, 1) and gold["tiny_out"].shape == (2, 1, 1, 1)
+    tag = "tiny" if tiny else "full"
+    g = torch.Generator().manual_seed(int(gold["seed"][0]))
+    logits = torch.randn(2, 19, 64, 96, generator=g) * 3
+    sd = weights.discriminator_state(3, tiny=tiny)
+    for target in (0.0, 1.0):
+        x = logits.clone().requires_grad_(True)
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        loss, p = disc_ref.adversarial_bce(x, sdg, target)
+        loss.backward()
+        np.testing.assert_allclose(p.detach().numpy(), gold[tag + "_out"], rtol=1e-5, atol=1e-6)
+        assert abs(loss.item() - float(gold[f"{tag}_bce{int(target)}"][0])) < 1e-6
+        np.testing.assert_allclose(x.grad[..., ::SUB, ::SUB].numpy(), gold[f"{tag}_bce{int(target)}_dx"], rtol=1e-4, atol=1e-9)
+        gn = np.array([sdg[k].grad.double().norm().item() for k in sd])     # state_dict order == parameters() order
+        np.testing.assert_allclose(gn, gold[f"{tag}_bce{int(target)}_gnorm"], rtol=1e-5)
