@@ -140,10 +140,12 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
         return (None, None, None, None) + _grad_tuple(plan, ctx.params, gw)
 
 
-def bisenet_fused_ce(model, x, target, ignore_index=255):
+def bisenet_fused_ce(model, x, target, ignore_index=255, return_logits=False):
     """Sum of the three heads' CrossEntropyLoss(ignore_index) (train.py:86-92) without materialising
     the full-resolution logits.  Returns (loss, argmax of the main head [N,H,W] int64,
-    stats [3,4] float64 = per head {sum of -log p, valid pixels, pixels with argmax == target, 0})."""
+    stats [3,4] float64 = per head {sum of -log p, valid pixels, pixels with argmax == target, 0}).
+    return_logits=True appends the main head's full-resolution logits, DETACHED (what the adversarial
+    loop feeds to the discriminator after `.detach()`, train.py:242,245)."""
     if not model.training:
         raise ops._lib.RtsdsError("bisenet_fused_ce is the train-mode fast path; call model.train() first")
     if not x.is_cuda and not ops._lib.dry_run():
@@ -154,4 +156,9 @@ def bisenet_fused_ce(model, x, target, ignore_index=255):
     plan = _get_train_plan(model, x)
     out = _BiSeNetFusedCEFn.apply(plan, x, target, int(ignore_index), *plan.params)
     _bump_bn_counters(model)
+    if return_logits:
+        (oh, ow), _ = plan.out_sizes()
+        logits = torch.empty((plan.n, plan.nc, oh, ow), dtype=torch.float32, device=plan.device)
+        ops.resize_to_nchw(plan.z, plan.n, plan.h8, plan.w8, plan.nc, 32, logits)
+        return out + (logits,)
     return out
