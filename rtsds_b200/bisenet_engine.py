@@ -311,7 +311,7 @@ class BiSeNetPlan:
             self.stats_all.zero_()
         self.generation += 1
         self.run_pre(x)
-        if use_graph and not self.train:
+        if use_graph and not self.train and not ops._lib.dry_run():
             if self.graph is None:
                 self.run_mid()                       # warm-up: sets kernel attributes, primes caches
                 torch.cuda.current_stream().synchronize()

@@ -52,6 +52,24 @@ def per_class_iou(hist):
     return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist) + epsilon)
 
 
+class IntRangeTransformer:
+    """Label transform of main.py:74-77 (utils.py:67-75): clamp into [min_val, max_val], cast to int64.
+    Host-side dataset tooling, kept so `from utils import IntRangeTransformer, forModel` (main.py:20) resolves."""
+
+    def __init__(self, min_val=0, max_val=255):
+        self.min_val, self.max_val = min_val, max_val
+
+    def __call__(self, sample):
+        return torch.clamp(sample, self.min_val, self.max_val).long()
+
+
+def tabular_print(log_dict):
+    """Epoch summary printer used by train.py:288,467 (utils.py:77-94): one `key: value` row per entry."""
+    width = max((len(str(k)) for k in log_dict), default=0)
+    for k, v in log_dict.items():
+        print(f"{str(k):<{width}} : {v}")
+
+
 def forModel(model, device):
     """Device placement (utils.py:97-107).  The reference wraps the model in nn.DataParallel when several
     GPUs are visible; here multi-GPU is one process per GPU with NCCL gradient all-reduce
