@@ -387,6 +387,16 @@ int rtsds_resize_ce_bwd(const float* z, int n, int h, int w, int c, int z_ld, in
                         const int64_t* target, int64_t ignore_index, const float* grad_scale,
                         float* dz, rtsds_stream_t s);
 
+/* Fused forward+backward of the same loss for the ~x8 heads (both scales > 7.1, c <= 20; query with
+ * rtsds_resize_ce_fused_supported): one pass produces acc / pred_out as above AND the UNNORMALISED gradient
+ * dz_unnorm[n,h,w,c] += sum over valid output pixels of bilinear weight * (softmax - onehot) (caller zeroes it;
+ * NULL: skip).  The backward pass is then rtsds_scale_by_device_scalar(dz, numel, upstream / valid_count). */
+int rtsds_resize_ce_fused_supported(int h, int w, int c, int oh, int ow);
+int rtsds_resize_ce_fused(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow,
+                          const int64_t* target, int64_t ignore_index, double* acc, int64_t* pred_out,
+                          float* dz_unnorm, rtsds_stream_t s);
+int rtsds_scale_by_device_scalar(float* x, int64_t n, const float* scale, rtsds_stream_t s);
+
 /* CrossEntropyLoss + argmax on materialised NCHW logits (stock call sites). */
 int rtsds_ce_argmax_nchw_fwd(const float* logits, int n, int c, int64_t hw,
                              const int64_t* target, int64_t ignore_index, double* acc,

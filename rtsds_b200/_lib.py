@@ -80,6 +80,9 @@ SIGNATURES = {
     "rtsds_resize_ce_argmax_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
     "rtsds_resize_ce_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
     "rtsds_ce_argmax_nchw_fwd": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P]),
+    "rtsds_resize_ce_fused_supported": (_I, [_I, _I, _I, _I, _I]),
+    "rtsds_resize_ce_fused": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P, _P]),
+    "rtsds_scale_by_device_scalar": (_I, [_P, _L, _P, _P]),
     "rtsds_pack_conv_weight_cpad": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_unpack_conv_wgrad_cpad": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_s2d_out_size": (_I, [_I]),

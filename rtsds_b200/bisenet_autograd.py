@@ -110,10 +110,20 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
         main, aux = plan.out_sizes()
         plan.acc.zero_()
         pred = torch.empty((plan.n,) + main, dtype=torch.int64, device=plan.device)
+        # ~x8 heads: loss, argmax and the unnormalised gradient in ONE pass over the labels (csrc/loss.cu)
+        one_pass = torch.is_grad_enabled() or any(ctx.needs_input_grad)
+        ctx.one_pass = []
         for i, z in enumerate((plan.z, plan.z1, plan.z2)):
             oh, ow = main if i == 0 else aux
-            ops.resize_ce_argmax_fwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, target, ignore_index, plan.acc[i],
-                                     pred if i == 0 else None)
+            fused = one_pass and ops.resize_ce_fused_supported(plan.h8, plan.w8, plan.nc, oh, ow)
+            ctx.one_pass.append(fused)
+            if fused:
+                plan.dz[i].zero_()
+                ops.resize_ce_fused(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, target, ignore_index, plan.acc[i],
+                                    pred if i == 0 else None, plan.dz[i])
+            else:
+                ops.resize_ce_argmax_fwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, target, ignore_index, plan.acc[i],
+                                         pred if i == 0 else None)
         per_head = (plan.acc[:, 0] / plan.acc[:, 1]).float()          # mean over valid pixels, per head
         loss = per_head.sum()
         ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
@@ -132,9 +142,12 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
         plan.gscale.copy_((dloss.double() / ctx.stats[:, 1]).float())
         for i, z in enumerate((plan.z, plan.z1, plan.z2)):
             oh, ow = main if i == 0 else aux
-            plan.dz[i].zero_()
-            ops.resize_ce_bwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, ctx.target, ctx.ignore_index,
-                              plan.gscale[i:i + 1], plan.dz[i])
+            if ctx.one_pass[i]:
+                ops.scale_by_device_scalar(plan.dz[i], plan.gscale[i:i + 1])
+            else:
+                plan.dz[i].zero_()
+                ops.resize_ce_bwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, ctx.target, ctx.ignore_index,
+                                  plan.gscale[i:i + 1], plan.dz[i])
         flat, gw = plan.new_grads()
         _run_backward(plan, gw, flat)
         return (None, None, None, None) + _grad_tuple(plan, ctx.params, gw)

@@ -203,6 +203,154 @@ resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused forward + backward of  bilinear resize -> CrossEntropyLoss(ignore_index) -> argmax  for the ~x8 heads
+// (scale > 7.1 in both directions, c <= 20): ONE pass over the labels evaluates the softmax of every
+// output pixel once and produces the loss / valid / correct sums, the argmax map and the UNNORMALISED
+// gradient  dz[n,y,x,c] = sum_pixels bilinear_weight * (softmax - onehot)  at z resolution; the
+// backward pass proper is then a scale by upstream / valid_count (rtsds_scale_by_device_scalar).
+// One thread owns one output column of an 8-row strip: the x-interpolated z values of its <= 3
+// source rows live in registers, the row-direction adjoint is accumulated in registers, the
+// column-direction adjoint goes through shared memory, one global atomic per (source pixel, class)
+// and block.
+constexpr int FU_COLS = 128, FU_ROWS = 8, FU_CMAX = 20, FU_KR = 3, FU_FC = 20, FU_AP = FU_KR * FU_CMAX + 1;
+
+__device__ __forceinline__ float sel3(const float (&a)[FU_KR][FU_CMAX], int k, int ch) {
+    return k == 0 ? a[0][ch] : (k == 1 ? a[1][ch] : a[2][ch]);
+}
+
+__global__ void __launch_bounds__(FU_COLS)
+resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
+                       const long long* __restrict__ target, long long ignore_index, double* acc,
+                       long long* __restrict__ pred_out, float* __restrict__ dz) {
+    __shared__ float s_z[FU_KR * FU_FC * FU_CMAX];
+    __shared__ float s_a[FU_COLS * FU_AP];
+    __shared__ int s_xi[2 * FU_COLS];
+    __shared__ float s_xl[2 * FU_COLS];
+    __shared__ double s_red[3][FU_COLS / 32];
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z, oy0 = blockIdx.y * FU_ROWS, ox0 = blockIdx.x * FU_COLS;
+    const int oy1 = min(oy0 + FU_ROWS, oh) - 1, ox1 = min(ox0 + FU_COLS, ow) - 1;
+    const int ys = lerp_src(oy0, rh, h).i0, ye = lerp_src(oy1, rh, h).i1;
+    const int xs = lerp_src(ox0, rw, w).i0, xe = lerp_src(ox1, rw, w).i1;
+    const int nrows = min(ye - ys + 1, FU_KR), ncols = min(xe - xs + 1, FU_FC);
+    for (int i = tid; i < nrows * ncols * c; i += FU_COLS) {
+        const int ch = i % c;
+        const int rc = i / c;
+        const int col = rc % ncols, row = rc / ncols;
+        s_z[i] = __ldg(z + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch);
+    }
+    const int ox = ox0 + tid;
+    const bool col_ok = ox < ow;
+    const Lerp lx = lerp_src(min(ox, ow - 1), rw, w);
+    const int xi0 = lx.i0 - xs, xi1 = lx.i1 - xs;
+    s_xi[2 * tid] = xi0; s_xi[2 * tid + 1] = xi1;
+    s_xl[2 * tid] = col_ok ? lx.l0 : 0.f; s_xl[2 * tid + 1] = col_ok ? lx.l1 : 0.f;
+    __syncthreads();
+    float zx[FU_KR][FU_CMAX], a[FU_KR][FU_CMAX];
+#pragma unroll
+    for (int k = 0; k < FU_KR; ++k)
+#pragma unroll
+        for (int ch = 0; ch < FU_CMAX; ++ch) {
+            a[k][ch] = 0.f;
+            zx[k][ch] = (k < nrows && ch < c) ? lx.l0 * s_z[(k * ncols + xi0) * c + ch] + lx.l1 * s_z[(k * ncols + xi1) * c + ch] : 0.f;
+        }
+    float loss = 0.f, nvalid = 0.f, ncorrect = 0.f;
+    if (col_ok) {
+#pragma unroll 1
+        for (int ry = 0; ry < FU_ROWS; ++ry) {
+            const int oy = oy0 + ry;
+            if (oy >= oh) break;
+            const Lerp ly = lerp_src(oy, rh, h);
+            const int k0 = ly.i0 - ys, k1 = ly.i1 - ys;
+            const long long pix = (static_cast<long long>(img) * oh + oy) * ow + ox;
+            const long long t = target ? __ldg(target + pix) : ignore_index;
+            float v[FU_CMAX];
+            float m = -INFINITY;
+            int arg = 0;
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) {
+                if (ch < c) {
+                    v[ch] = ly.l0 * sel3(zx, k0, ch) + ly.l1 * sel3(zx, k1, ch);
+                    if (v[ch] > m || (v[ch] != v[ch] && m == m)) { m = v[ch]; arg = ch; }
+                }
+            }
+            if (pred_out) pred_out[pix] = arg;
+            if (arg == t) ncorrect += 1.f;
+            if (t == ignore_index || t < 0 || t >= c) continue;
+            float ssum = 0.f, vt = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) {
+                if (ch < c) {
+                    if (ch == t) vt = v[ch];
+                    v[ch] = __expf(v[ch] - m);
+                    ssum += v[ch];
+                }
+            }
+            loss += m + __logf(ssum) - vt;
+            nvalid += 1.f;
+            const float inv = 1.0f / ssum;
+            const float w0 = (k0 == 0 ? ly.l0 : 0.f) + (k1 == 0 ? ly.l1 : 0.f);
+            const float w1 = (k0 == 1 ? ly.l0 : 0.f) + (k1 == 1 ? ly.l1 : 0.f);
+            const float w2 = (k0 == 2 ? ly.l0 : 0.f) + (k1 == 2 ? ly.l1 : 0.f);
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) {
+                if (ch < c) {
+                    const float g = v[ch] * inv - (ch == t ? 1.f : 0.f);
+                    a[0][ch] = fmaf(w0, g, a[0][ch]);
+                    a[1][ch] = fmaf(w1, g, a[1][ch]);
+                    a[2][ch] = fmaf(w2, g, a[2][ch]);
+                }
+            }
+        }
+    }
+    if (dz) {
+#pragma unroll
+        for (int k = 0; k < FU_KR; ++k)
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) s_a[tid * FU_AP + k * FU_CMAX + ch] = a[k][ch];
+        __syncthreads();
+        const float inv_rw = 1.0f / rw;
+        for (int i = tid; i < nrows * ncols * c; i += FU_COLS) {
+            const int ch = i % c;
+            const int rc = i / c;
+            const int col = rc % ncols, k = rc / ncols;
+            int lo = static_cast<int>(floorf((static_cast<float>(xs + col) - 0.5f) * inv_rw - 0.5f)) - 1 - ox0;
+            int hi = static_cast<int>(ceilf((static_cast<float>(xs + col) + 1.5f) * inv_rw - 0.5f)) + 1 - ox0;
+            lo = max(lo, 0); hi = min(hi, FU_COLS - 1);
+            float sum = 0.f;
+            for (int tx = lo; tx <= hi; ++tx) {
+                const float wx = (s_xi[2 * tx] == col ? s_xl[2 * tx] : 0.f) + (s_xi[2 * tx + 1] == col ? s_xl[2 * tx + 1] : 0.f);
+                sum = fmaf(wx, s_a[tx * FU_AP + k * FU_CMAX + ch], sum);
+            }
+            if (sum != 0.f)
+                atomicAdd(dz + ((static_cast<long long>(img) * h + ys + k) * w + xs + col) * z_ld + ch, sum);
+        }
+    }
+    if (acc) {
+        double d0 = warp_sum(static_cast<double>(loss)), d1 = warp_sum(static_cast<double>(nvalid)), d2 = warp_sum(static_cast<double>(ncorrect));
+        if ((tid & 31) == 0) { s_red[0][tid >> 5] = d0; s_red[1][tid >> 5] = d1; s_red[2][tid >> 5] = d2; }
+        __syncthreads();
+        if (tid == 0) {
+            double ta = 0, tb = 0, tc = 0;
+            for (int i = 0; i < FU_COLS / 32; ++i) { ta += s_red[0][i]; tb += s_red[1][i]; tc += s_red[2][i]; }
+            if (ta != 0.0) atomicAdd(&acc[0], ta);
+            if (tb != 0.0) atomicAdd(&acc[1], tb);
+            if (tc != 0.0) atomicAdd(&acc[2], tc);
+        }
+    }
+}
+
+__global__ void scale_by_device_scalar_kernel(float* __restrict__ x, long long n4, const float* __restrict__ s) {
+    const float f = __ldg(s);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
 // CE + argmax over materialised fp32 NCHW logits; 4 pixels per thread.
 __global__ void __launch_bounds__(LS_THREADS)
 ce_nchw_fwd_kernel(const float* __restrict__ logits, int n, int c, long long hw, const long long* __restrict__ target,
@@ -315,4 +463,36 @@ extern "C" int rtsds_ce_argmax_nchw_fwd(const float* logits, int n, int c, int64
                                                               ignore_index, acc, reinterpret_cast<long long*>(pred_out), vec);
     count_launch();
     return check_launch("ce_nchw_fwd_kernel");
+}
+
+// 1 when rtsds_resize_ce_fused supports the geometry (both scales > 7.1, c <= 20), else 0.
+extern "C" int rtsds_resize_ce_fused_supported(int h, int w, int c, int oh, int ow) {
+    if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0 || c <= 0 || c > FU_CMAX) return 0;
+    return (static_cast<double>(oh) / h > 7.1 && static_cast<double>(ow) / w > 7.1) ? 1 : 0;
+}
+
+extern "C" int rtsds_resize_ce_fused(const float* z, int n, int h, int w, int c, int z_ld, int oh, int ow,
+                                     const int64_t* target, int64_t ignore_index, double* acc, int64_t* pred_out,
+                                     float* dz_unnorm, rtsds_stream_t s) {
+    RTSDS_REQUIRE(z && target && n > 0 && z_ld >= c, "resize_ce_fused: bad argument");
+    if (!rtsds_resize_ce_fused_supported(h, w, c, oh, ow)) {
+        set_error("resize_ce_fused: needs an upsampling factor > 7.1 and c <= %d (got %dx%d -> %dx%d, c=%d)", FU_CMAX, h, w, oh, ow, c);
+        return RTSDS_EUNSUP;
+    }
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    dim3 grid(static_cast<unsigned>(cdiv(ow, FU_COLS)), static_cast<unsigned>(cdiv(oh, FU_ROWS)), n);
+    resize_ce_fused_kernel<<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
+                                                              reinterpret_cast<const long long*>(target), ignore_index, acc,
+                                                              reinterpret_cast<long long*>(pred_out), dz_unnorm);
+    count_launch();
+    return check_launch("resize_ce_fused_kernel");
+}
+
+extern "C" int rtsds_scale_by_device_scalar(float* x, int64_t n, const float* scale, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && scale && n > 0 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "scale_by_device_scalar: bad argument (n % 4 == 0, 16-byte aligned)");
+    long long want = cdiv(n / 4, 256);
+    int grid = static_cast<int>(want > 8LL * num_sms() ? 8LL * num_sms() : want);
+    scale_by_device_scalar_kernel<<<grid, 256, 0, as_stream(s)>>>(x, n / 4, scale);
+    count_launch();
+    return check_launch("scale_by_device_scalar_kernel");
 }

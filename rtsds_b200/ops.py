@@ -279,6 +279,19 @@ def resize_ce_bwd(z, n, h, w, c, z_ld, oh, ow, target, ignore_index, grad_scale,
                                     _p(dz), _s()), "resize_ce_bwd")
 
 
+def resize_ce_fused_supported(h, w, c, oh, ow) -> bool:
+    return bool(lib().rtsds_resize_ce_fused_supported(h, w, c, oh, ow))
+
+
+def resize_ce_fused(z, n, h, w, c, z_ld, oh, ow, target, ignore_index, acc, pred_out, dz_unnorm) -> None:
+    check(lib().rtsds_resize_ce_fused(_p(z), n, h, w, c, z_ld, oh, ow, _p(target), int(ignore_index), _p(acc), _p(pred_out),
+                                      _p(dz_unnorm), _s()), "resize_ce_fused")
+
+
+def scale_by_device_scalar(x, scale) -> None:
+    check(lib().rtsds_scale_by_device_scalar(_p(x), x.numel(), _p(scale), _s()), "scale_by_device_scalar")
+
+
 def ce_argmax_nchw_fwd(logits, target, ignore_index, acc, pred_out=None) -> None:
     n, c, h, w = logits.shape
     check(lib().rtsds_ce_argmax_nchw_fwd(_p(logits), n, c, h * w, _p(target), int(ignore_index), _p(acc), _p(pred_out),

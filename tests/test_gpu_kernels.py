@@ -280,6 +280,41 @@ def test_fused_resize_ce_argmax(cuda, ignore, h, w, s):
     assert (dz[..., c:] == 0).all()
 
 
+@pytest.mark.parametrize("ignore", [19, 255])
+@pytest.mark.parametrize("h,w,oh,ow,c", [(16, 24, 128, 192, 19), (9, 13, 72, 104, 19), (23, 40, 180, 320, 19), (65, 129, 512, 1024, 19),
+                                         (12, 20, 96, 160, 7), (90, 160, 720, 1280, 19)])
+def test_one_pass_resize_ce_forward_and_gradient(cuda, ignore, h, w, oh, ow, c):
+    """rtsds_resize_ce_fused: loss sums, argmax and the unnormalised gradient in one pass (~x8 heads, incl. the
+    non-integer 7.8x of the aux heads at 720x1280 and DeepLab's 65x129 -> 512x1024)."""
+    g = torch.Generator().manual_seed(h + ignore)
+    n = 2 if oh < 700 else 1
+    z = (torch.randn(n, c, h, w, generator=g) * 2).requires_grad_(True)
+    target = torch.randint(0, c + 1, (n, oh, ow), generator=g)
+    target[target == c] = ignore
+    assert ops.resize_ce_fused_supported(h, w, c, oh, ow) and not ops.resize_ce_fused_supported(h, w, c, 4 * h, 4 * w)
+    logits = F.interpolate(z, size=(oh, ow), mode="bilinear")
+    loss = F.cross_entropy(logits, target, ignore_index=ignore)
+    (3.0 * loss).backward()
+    zg = torch.zeros(n, h, w, 32, device="cuda"); zg[..., :c] = nhwc(z.detach(), torch.float32)
+    acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+    pred = torch.empty(n, oh, ow, dtype=torch.int64, device="cuda")
+    dz = torch.zeros(n, h, w, 32, device="cuda")
+    ops.resize_ce_fused(zg, n, h, w, c, 32, oh, ow, target.cuda(), ignore, acc, pred, dz)
+    a = acc.cpu()
+    valid = (target != ignore).sum().item()
+    assert a[1].item() == valid
+    assert abs(a[0].item() / valid - loss.item()) < 1e-5 * max(1.0, loss.item())
+    assert (pred.cpu() == logits.argmax(1)).float().mean().item() > 0.9999
+    assert a[2].item() == (pred.cpu() == target).sum().item()
+    ops.scale_by_device_scalar(dz, torch.tensor([3.0 / valid], device="cuda"))
+    assert rel_err(nchw(dz[..., :c]), z.grad) < 1e-4, rel_err(nchw(dz[..., :c]), z.grad)
+    assert (dz[..., c:] == 0).all()
+    # agrees with the two-kernel generic path
+    acc2 = torch.zeros(4, dtype=torch.float64, device="cuda")
+    ops.resize_ce_argmax_fwd(zg, n, h, w, c, 32, oh, ow, target.cuda(), ignore, acc2, None)
+    assert abs(acc2[0].item() - a[0].item()) < 1e-5 * abs(a[0].item()) and acc2[1].item() == a[1].item()
+
+
 def test_ce_argmax_nchw(cuda):
     g = torch.Generator().manual_seed(11)
     logits = torch.randn(2, 19, 33, 47, generator=g) * 3
