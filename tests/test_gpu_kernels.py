@@ -127,6 +127,25 @@ def test_maxpool(cuda, h, w, ceil, dtype):
     assert torch.equal(nchw(y), ref)
 
 
+@pytest.mark.parametrize("h,w,c,ceil", [(32, 48, 64, False), (45, 81, 64, False), (45, 81, 64, True), (65, 129, 64, True), (33, 35, 24, False),
+                                        (18, 70, 128, True)])
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_maxpool_backward(cuda, h, w, c, ceil, dtype):
+    """Gradient goes to the FIRST maximum of each window (ties: values drawn from 5 levels), ceil_mode windows that
+    hang over the border, channel counts that are not a multiple of 64."""
+    g = torch.Generator().manual_seed(h * 7 + w)
+    tdt = ops.torch_dtype(dtype)
+    x = torch.randint(0, 5, (2, c, h, w), generator=g).float().requires_grad_(True)
+    y = F.max_pool2d(x, 3, 2, 1, ceil_mode=ceil)
+    dy = torch.randint(-8, 9, y.shape, generator=g).float()
+    y.backward(dy)
+    dx = torch.full((2, h, w, c), float("nan"), dtype=tdt, device="cuda")
+    xg, dyg = nhwc(x.detach(), tdt), nhwc(dy, tdt)           # keep the device copies alive across the launch
+    ops.check(ops.lib().rtsds_maxpool3x3s2_bwd(xg.data_ptr(), dyg.data_ptr(), 2, h, w, c, dtype, int(ceil), dx.data_ptr(), ops._s()),
+              "maxpool_bwd")
+    assert torch.equal(nchw(dx), x.grad)
+
+
 # ----------------------------------------------------------------------------- batch norm helpers
 def test_bn_fold_and_finalize(cuda):
     g = torch.Generator().manual_seed(2)
