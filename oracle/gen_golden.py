@@ -144,6 +144,47 @@ def gen_discriminators(R):
     print("wrote discriminators")
 
 
+def gen_deeplab(R, name, seed, n, h, w):
+    """DeepLabV2-R101 (models/deeplabv2/deeplabv2.py) eval + train forward, CE loss, gradients."""
+    from oracle import deeplab_ref  # noqa: F401  (same input recipe as the tests)
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    x, y = make_input(2000 + seed, n, h, w)
+    out = {"shape": np.array([n, h, w]), "seed": np.array([seed])}
+    sd = weights.deeplab_state(seed)
+    m = R["get_deeplab_v2"](19, pretrain=False)
+    m.load_state_dict(weights.clone_state(sd))
+    m.eval()
+    with torch.no_grad():
+        r = m(x)
+    out["eval_result"] = sub(r)
+    out["eval_result_sum"] = summarize(r)
+    out["eval_argmax"] = r.argmax(1)[..., ::SUB, ::SUB].numpy().astype(np.int16)
+    m = R["get_deeplab_v2"](19, pretrain=False)
+    m.load_state_dict(weights.clone_state(sd))
+    m.train()
+    res, a1, a2 = m(x)
+    assert a1 is None and a2 is None
+    out["train_result"] = sub(res)
+    out["train_result_sum"] = summarize(res)
+    loss = F.cross_entropy(res, y, ignore_index=19)
+    out["train_loss_ign19"] = np.array([loss.item()], dtype=np.float64)
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    out["grad_names"] = np.array(sorted(grads.keys()))
+    out["grad_norms"] = np.array([grads[k].double().norm().item() for k in sorted(grads.keys())])
+    out["grad_none"] = np.array(sorted(k for k, p in m.named_parameters() if p.grad is None))
+    for k in ("conv1.weight", "layer1.0.conv1.weight", "layer2.0.downsample.0.weight", "layer3.11.conv2.weight",
+              "layer6.conv2d_list.3.bias", "layer6.conv2d_list.0.weight"):
+        g_ = grads[k]
+        out["grad:" + k] = (g_ if g_.numel() < 200000 else g_.flatten()[::37]).numpy().astype(np.float32)
+    bufs = dict(m.named_buffers())
+    for k in ("bn1.running_mean", "layer2.0.downsample.1.running_var", "layer3.22.bn3.running_var", "layer4.2.bn2.running_mean"):
+        out["buf:" + k] = bufs[k].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     assert refshim.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
@@ -154,6 +195,7 @@ def main():
     gen_bisenet(R, "bisenet_64x96", 0, 2, 64, 96)
     gen_bisenet(R, "bisenet_72x104", 1, 2, 72, 104)
     gen_discriminators(R)
+    gen_deeplab(R, "deeplab_72x104", 2, 2, 72, 104)
 
 
 if __name__ == "__main__":

@@ -107,6 +107,36 @@ def discriminator_state(seed: int = 0, tiny: bool = False, num_classes: int = 19
     return sd
 
 
+def deeplab_state(seed: int = 0, num_classes: int = 19) -> dict:
+    """State dict of the reference's get_deeplab_v2 (ResNetMulti(Bottleneck, [3,4,23,3]), deeplabv2.py:69-111): same
+    keys, shapes and order as model.state_dict().  Conv weights get a He-style scale (the reference's N(0, 0.01)
+    init makes the activations vanish through 101 layers, which would not exercise the arithmetic); BatchNorm
+    parameters and buffers are non-trivial so that eval-mode folding is tested."""
+    sd = {}
+    sd["conv1.weight"] = _conv_w("conv1.weight", seed, 64, 3, 7)
+    _bn(sd, "bn1", seed, 64)
+    inpl = 64
+    for name, planes, blocks in (("layer1", 64, 3), ("layer2", 128, 4), ("layer3", 256, 23), ("layer4", 512, 3)):
+        for b in range(blocks):
+            p = f"{name}.{b}"
+            cin = inpl if b == 0 else planes * 4
+            sd[p + ".conv1.weight"] = _conv_w(p + ".conv1.weight", seed, planes, cin, 1)
+            _bn(sd, p + ".bn1", seed, planes)
+            sd[p + ".conv2.weight"] = _conv_w(p + ".conv2.weight", seed, planes, planes, 3)
+            _bn(sd, p + ".bn2", seed, planes)
+            sd[p + ".conv3.weight"] = _conv_w(p + ".conv3.weight", seed, planes * 4, planes, 1, gain=1.0)
+            _bn(sd, p + ".bn3", seed, planes * 4)
+            sd[p + ".bn3.weight"] = sd[p + ".bn3.weight"] * 0.25      # keeps the 33 residual sums bounded in eval mode
+            if b == 0:
+                sd[p + ".downsample.0.weight"] = _conv_w(p + ".downsample.0.weight", seed, planes * 4, cin, 1, gain=1.0)
+                _bn(sd, p + ".downsample.1", seed, planes * 4)
+        inpl = planes * 4
+    for i in range(4):
+        sd[f"layer6.conv2d_list.{i}.weight"] = _conv_w(f"layer6.conv2d_list.{i}.weight", seed, num_classes, 2048, 3, gain=0.5)
+        sd[f"layer6.conv2d_list.{i}.bias"] = _vec(f"layer6.conv2d_list.{i}.bias", seed, num_classes)
+    return sd
+
+
 def clone_state(sd: dict) -> dict:
     """Deep copy preserving aliasing between duplicated keys."""
     memo = {}
