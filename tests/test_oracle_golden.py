@@ -99,3 +99,39 @@ def test_discriminator_oracle_matches_reference_outputs(golden_dir, tiny):
         np.testing.assert_allclose(x.grad[..., ::SUB, ::SUB].numpy(), gold[f"{tag}_bce{int(target)}_dx"], rtol=1e-4, atol=1e-9)
         gn = np.array([sdg[k].grad.double().norm().item() for k in sd])     # state_dict order == parameters() order
         np.testing.assert_allclose(gn, gold[f"{tag}_bce{int(target)}_gnorm"], rtol=1e-5)
+
+
+def test_deeplab_oracle_matches_reference_outputs(golden_dir):
+    """oracle/deeplab_ref.py against the REAL reference's DeepLabV2-R101 (gen_golden.gen_deeplab): eval and train
+    logits, loss, every gradient norm, selected gradient tensors, running buffers."""
+    from oracle import deeplab_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    gold = np.load(os.path.join(golden_dir, "deeplab_72x104.npz"))
+    n, h, w = (int(v) for v in gold["shape"])
+    seed = int(gold["seed"][0])
+    g = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    y = torch.randint(0, 20, (n, h, w), generator=g)
+    sd = weights.deeplab_state(seed)
+    assert len(sd) == 632
+    with torch.no_grad():
+        r = deeplab_ref.deeplab_forward(x, weights.clone_state(sd), False)
+    np.testing.assert_allclose(r[..., ::SUB, ::SUB].numpy(), gold["eval_result"], rtol=1e-4, atol=1e-5)
+    assert (r.argmax(1)[..., ::SUB, ::SUB].numpy() == gold["eval_argmax"]).mean() > 0.999
+    sdt = weights.clone_state(sd)
+    leaves = {k: v.requires_grad_(True) for k, v in sdt.items() if v.dtype.is_floating_point and "running" not in k}
+    out = deeplab_ref.deeplab_forward(x, sdt, True)
+    np.testing.assert_allclose(out.detach()[..., ::SUB, ::SUB].numpy(), gold["train_result"], rtol=1e-4, atol=2e-5)
+    loss = F.cross_entropy(out, y, ignore_index=19)
+    assert abs(loss.item() - float(gold["train_loss_ign19"][0])) < 1e-5
+    loss.backward()
+    for k, rn in zip((str(s) for s in gold["grad_names"]), gold["grad_norms"]):
+        assert abs(leaves[k].grad.double().norm().item() - rn) <= 1e-4 * max(rn, 1e-8), k
+    for k in gold.files:
+        if k.startswith("grad:"):
+            g_ = leaves[k[5:]].grad
+            g_ = g_ if g_.numel() < 200000 else g_.flatten()[::37]
+            np.testing.assert_allclose(g_.numpy(), gold[k], rtol=2e-3, atol=1e-7)
+        if k.startswith("buf:"):
+            np.testing.assert_allclose(sdt[k[4:]].detach().numpy(), gold[k], rtol=1e-4, atol=1e-6)
