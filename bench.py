@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the RTSDS hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train|adversarial|deeplab] [--impl reference]
 
 Default workload (BASELINE.json configs[1]): BiSeNet-ResNet18 eval inference, batch 1, 3x512x1024,
 metric = frames per second.  One JSON line is printed by rank 0.
@@ -376,12 +376,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="rtsds_b200", choices=["rtsds_b200", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch of the train workload")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "adversarial", "deeplab"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 train, 4 adversarial, 2 deeplab)")
+    ap.add_argument("--disc", default="tiny", choices=["tiny", "full"], help="discriminator of the adversarial workload")
+    ap.add_argument("--stock", action="store_true", help="adversarial workload: the reference's exact call sequence instead of the fused fast paths")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload in ("infer", "train") and not args.batch:
+        args.batch = 8
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
@@ -391,6 +395,14 @@ def main():
     try:
         if args.workload == "infer":
             run_infer(args, rank, world, local)
+        elif args.workload == "adversarial":
+            import bench_extra
+
+            bench_extra.run_adversarial(args, rank, world, local)
+        elif args.workload == "deeplab":
+            import bench_extra
+
+            bench_extra.run_deeplab(args, rank, world, local)
         else:
             from bench_train import run_train
 
