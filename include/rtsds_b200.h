@@ -225,6 +225,16 @@ int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int y_ld, const
                        const float* sums, int64_t n_pix, int c, int relu, int dtype, void* d_raw,
                        int d_raw_ld, int d_raw_dtype, void* g_out, int g_ld, float* dgamma,
                        float* dbeta, rtsds_stream_t s);
+/* Same for a BatchNorm+ReLU layer WITHOUT a residual input: the ReLU mask is recomputed from raw as
+ * fma(raw, fwd_scale, fwd_shift) > 0 with the scale/shift vectors rtsds_bn_finalize produced for the forward (the
+ * very fma the forward evaluated, so the mask is bit-identical) and the activation y is not re-read. */
+int rtsds_bn_bwd_reduce_rawmask(const void* dy, int dy_ld, const void* raw, int raw_ld, const float* mean,
+                                const float* invstd, const float* fwd_scale, const float* fwd_shift, int64_t n_pix,
+                                int c, int dtype, float* sums, rtsds_stream_t s);
+int rtsds_bn_bwd_apply_rawmask(const void* dy, int dy_ld, const void* raw, int raw_ld, const float* mean,
+                               const float* invstd, const float* gamma, const float* sums, const float* fwd_scale,
+                               const float* fwd_shift, int64_t n_pix, int c, int dtype, void* d_raw, int d_raw_ld,
+                               int d_raw_dtype, void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s);
 /* out[c] += sum over pixels of x[p][c] (conv bias gradients); caller zeroes or accumulates. */
 int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, int dtype, float* out,
                       rtsds_stream_t s);

@@ -64,6 +64,8 @@ SIGNATURES = {
     "rtsds_scale_shift_act": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
     "rtsds_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _L, _I, _I, _I, _P, _P]),
     "rtsds_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),
+    "rtsds_bn_bwd_reduce_rawmask": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
+    "rtsds_bn_bwd_apply_rawmask": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),
     "rtsds_channel_sum": (_I, [_P, _I, _L, _I, _I, _P, _P]),
     "rtsds_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

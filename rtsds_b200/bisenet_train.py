@@ -122,14 +122,26 @@ class _ConvBN:
             d_raw = p.d_raw_view(self.dyld)
             gamma = self.bn.weight
             dgam, dbet = gw.get(self.bn.weight), gw.get(self.bn.bias)
-            check(lib().rtsds_bn_bwd_reduce(dy.ptr, dy.ld, self.y.ptr, self.y.ld, self.raw.ptr, self.raw.ld,
-                                            _p(self.save_mean), _p(self.save_invstd), self.n_pix, self.cout, int(self.relu),
-                                            dy.dtype, _p(self.sums), s), "bn_bwd_reduce")
-            check(lib().rtsds_bn_bwd_apply(dy.ptr, dy.ld, self.y.ptr, self.y.ld, self.raw.ptr, self.raw.ld, _p(self.save_mean),
-                                           _p(self.save_invstd), _p(gamma.detach()), _p(self.sums), self.n_pix, self.cout,
-                                           int(self.relu), dy.dtype, d_raw.ptr, self.dyld, dt,
-                                           g_out.ptr if g_out is not None else None, g_out.ld if g_out is not None else 0,
-                                           _p(dgam), _p(dbet), s), "bn_bwd_apply")
+            if self.relu and self.res is None and self.raw.dtype == dy.dtype:
+                # no residual: the ReLU mask is a function of raw alone -> the activation is not re-read
+                check(lib().rtsds_bn_bwd_reduce_rawmask(dy.ptr, dy.ld, self.raw.ptr, self.raw.ld, _p(self.save_mean),
+                                                        _p(self.save_invstd), _p(self.scale), _p(self.shift), self.n_pix,
+                                                        self.cout, dy.dtype, _p(self.sums), s), "bn_bwd_reduce_rawmask")
+                check(lib().rtsds_bn_bwd_apply_rawmask(dy.ptr, dy.ld, self.raw.ptr, self.raw.ld, _p(self.save_mean),
+                                                       _p(self.save_invstd), _p(gamma.detach()), _p(self.sums), _p(self.scale),
+                                                       _p(self.shift), self.n_pix, self.cout, dy.dtype, d_raw.ptr, self.dyld, dt,
+                                                       g_out.ptr if g_out is not None else None,
+                                                       g_out.ld if g_out is not None else 0, _p(dgam), _p(dbet), s),
+                      "bn_bwd_apply_rawmask")
+            else:
+                check(lib().rtsds_bn_bwd_reduce(dy.ptr, dy.ld, self.y.ptr, self.y.ld, self.raw.ptr, self.raw.ld,
+                                                _p(self.save_mean), _p(self.save_invstd), self.n_pix, self.cout, int(self.relu),
+                                                dy.dtype, _p(self.sums), s), "bn_bwd_reduce")
+                check(lib().rtsds_bn_bwd_apply(dy.ptr, dy.ld, self.y.ptr, self.y.ld, self.raw.ptr, self.raw.ld, _p(self.save_mean),
+                                               _p(self.save_invstd), _p(gamma.detach()), _p(self.sums), self.n_pix, self.cout,
+                                               int(self.relu), dy.dtype, d_raw.ptr, self.dyld, dt,
+                                               g_out.ptr if g_out is not None else None, g_out.ld if g_out is not None else 0,
+                                               _p(dgam), _p(dbet), s), "bn_bwd_apply")
         else:
             d_raw = dy                                   # bias-only conv: dy already is the conv-output gradient
             assert dy.ld >= self.dyld and dy.dtype == dt
@@ -175,11 +187,13 @@ class _Stem:
         p = self.plan
         s = _s()
         d_raw = self.d_raw if self.d_raw is not None else p.d_raw_view(64)
-        check(lib().rtsds_bn_bwd_reduce(dy.ptr, dy.ld, self.y.ptr, 64, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
-                                        self.n_pix, 64, 1, dy.dtype, _p(self.sums), s), "bn_bwd_reduce")
-        check(lib().rtsds_bn_bwd_apply(dy.ptr, dy.ld, self.y.ptr, 64, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
-                                       _p(self.bn.weight.detach()), _p(self.sums), self.n_pix, 64, 1, dy.dtype, d_raw.ptr, 64,
-                                       p.dt, None, 0, _p(gw.get(self.bn.weight)), _p(gw.get(self.bn.bias)), s), "bn_bwd_apply")
+        check(lib().rtsds_bn_bwd_reduce_rawmask(dy.ptr, dy.ld, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
+                                                _p(self.scale), _p(self.shift), self.n_pix, 64, dy.dtype, _p(self.sums), s),
+              "bn_bwd_reduce_rawmask")
+        check(lib().rtsds_bn_bwd_apply_rawmask(dy.ptr, dy.ld, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
+                                               _p(self.bn.weight.detach()), _p(self.sums), _p(self.scale), _p(self.shift),
+                                               self.n_pix, 64, dy.dtype, d_raw.ptr, 64, p.dt, None, 0,
+                                               _p(gw.get(self.bn.weight)), _p(gw.get(self.bn.bias)), s), "bn_bwd_apply_rawmask")
         gwt = gw.get(self.conv.weight)
         if wgrad and gwt is not None:
             n, cin, h, w = x.shape

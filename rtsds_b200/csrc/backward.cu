@@ -44,7 +44,8 @@ static int grid_for(long long total, int threads, int waves = 8) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ raw,
-                     int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd, long long n_pix, int c,
+                     int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ fsc, const float* __restrict__ fsh, long long n_pix, int c,
                      int relu, float* sums) {
     extern __shared__ float sh[];             // [2*cp]
     const int cg = (c + 7) / 8, cp = cg * 8;
@@ -52,19 +53,28 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
     __syncthreads();
     const int g8 = threadIdx.x % cg;
     const int prow = threadIdx.x / cg, prows = blockDim.x / cg;
-    float s1[8], s2[8], mu[8], is[8];
+    // ReLU mask: from the stored activation y, or (y == NULL) recomputed from raw with the forward's own
+    // scale / shift — the same fp32 fma the forward evaluated, so the mask is bit-identical and y is not re-read
+    const bool rawmask = relu && y == nullptr;
+    float s1[8], s2[8], mu[8], is[8], fa[8], fb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         s1[j] = 0.f; s2[j] = 0.f;
         const int ch = g8 * 8 + j;
         mu[j] = ch < c ? mean[ch] : 0.f; is[j] = ch < c ? invstd[ch] : 0.f;
+        fa[j] = (rawmask && ch < c) ? fsc[ch] : 0.f; fb[j] = (rawmask && ch < c) ? fsh[ch] : 0.f;
     }
     if (prow < prows) {
         for (long long p = static_cast<long long>(blockIdx.x) * prows + prow; p < n_pix; p += static_cast<long long>(gridDim.x) * prows) {
             const F8 d = ld8(dy + p * dy_ld + g8 * 8);
             const F8 r = ld8(raw + p * raw_ld + g8 * 8);
             F8 yy;
-            if (relu) yy = ld8(y + p * y_ld + g8 * 8);
+            if (rawmask) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) yy.v[j] = fmaf(r.v[j], fa[j], fb[j]);
+            } else if (relu) {
+                yy = ld8(y + p * y_ld + g8 * 8);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float g = (relu && !(yy.v[j] > 0.f)) ? 0.f : d.v[j];
@@ -91,15 +101,56 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ raw,
                     int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const float* __restrict__ sums, long long n_pix, int c, int relu,
+                    const float* __restrict__ gamma, const float* __restrict__ sums, const float* __restrict__ fsc,
+                    const float* __restrict__ fsh, long long n_pix, int c, int relu,
                     TO* __restrict__ d_raw, int d_raw_ld, T* __restrict__ g_out, int g_ld, float* dgamma, float* dbeta) {
     const int cg = (c + 7) / 8;
+    const bool rawmask = relu && y == nullptr;
     const float inv_m = 1.0f / static_cast<float>(n_pix);
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
             if (dgamma) dgamma[i] += sums[c + i];
             if (dbeta) dbeta[i] += sums[i];
         }
+    }
+    if (blockDim.x % cg == 0) {
+        // one 8-channel group per thread: d_raw = ca*g + cb*raw + cc with per-channel coefficients in registers
+        //   ca = gamma*invstd,  cb = -gamma*invstd^2*sum_gx/M,  cc = -ca*sum_g/M - cb*mean
+        const int g8 = threadIdx.x % cg;
+        const long long prows = blockDim.x / cg, stride = prows * gridDim.x;
+        float ca[8], cb[8], cc[8], fa[8], fb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = g8 * 8 + j;
+            if (ch < c) {
+                const float is = invstd[ch], gm = gamma ? gamma[ch] : 1.f;
+                ca[j] = gm * is;
+                cb[j] = -gm * is * is * sums[c + ch] * inv_m;
+                cc[j] = -ca[j] * sums[ch] * inv_m - cb[j] * mean[ch];
+                fa[j] = rawmask ? fsc[ch] : 0.f; fb[j] = rawmask ? fsh[ch] : 0.f;
+            } else { ca[j] = cb[j] = cc[j] = fa[j] = fb[j] = 0.f; }
+        }
+        for (long long p = static_cast<long long>(blockIdx.x) * prows + threadIdx.x / cg; p < n_pix; p += stride) {
+            const F8 d = ld8(dy + p * dy_ld + g8 * 8);
+            const F8 r = ld8(raw + p * raw_ld + g8 * 8);
+            F8 yy;
+            if (rawmask) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) yy.v[j] = fmaf(r.v[j], fa[j], fb[j]);
+            } else if (relu) {
+                yy = ld8(y + p * y_ld + g8 * 8);
+            }
+            F8 o, gg;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = (relu && !(yy.v[j] > 0.f)) ? 0.f : d.v[j];
+                gg.v[j] = (g8 * 8 + j < c) ? g : 0.f;
+                o.v[j] = fmaf(ca[j], g, fmaf(cb[j], r.v[j], cc[j]));
+            }
+            st8(d_raw + p * d_raw_ld + g8 * 8, o);
+            if (g_out) st8(g_out + p * g_ld + g8 * 8, gg);
+        }
+        return;
     }
     const long long total = n_pix * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -109,7 +160,15 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y
         const F8 d = ld8(dy + p * dy_ld + g8 * 8);
         const F8 r = ld8(raw + p * raw_ld + g8 * 8);
         F8 yy;
-        if (relu) yy = ld8(y + p * y_ld + g8 * 8);
+        if (rawmask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = g8 * 8 + j;
+                yy.v[j] = ch < c ? fmaf(r.v[j], fsc[ch], fsh[ch]) : 0.f;
+            }
+        } else if (relu) {
+            yy = ld8(y + p * y_ld + g8 * 8);
+        }
         F8 o, gg;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -619,12 +678,12 @@ using namespace rtsds;
         else { set_error(name ": bad dtype"); return RTSDS_EINVAL; }       \
     } while (0)
 
-extern "C" int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
-                                   const float* mean, const float* invstd, int64_t n_pix, int c, int relu, int dtype,
-                                   float* sums, rtsds_stream_t s) {
+static int bn_bwd_reduce_impl(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                              const float* mean, const float* invstd, const float* fsc, const float* fsh, int64_t n_pix, int c,
+                              int relu, int dtype, float* sums, rtsds_stream_t s) {
     RTSDS_REQUIRE(dy && raw && mean && invstd && sums && n_pix > 0 && c > 0, "bn_bwd_reduce: bad argument");
-    RTSDS_REQUIRE(!relu || y, "bn_bwd_reduce: y required for the ReLU mask");
-    RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && (!relu || y_ld % 8 == 0), "bn_bwd_reduce: pitches must be multiples of 8");
+    RTSDS_REQUIRE(!relu || y || (fsc && fsh), "bn_bwd_reduce: the ReLU mask needs y or the forward scale/shift");
+    RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && (!relu || !y || y_ld % 8 == 0), "bn_bwd_reduce: pitches must be multiples of 8");
     const int cg = (c + 7) / 8;
     RTSDS_REQUIRE(cg <= 256 && dy_ld >= cg * 8 && raw_ld >= cg * 8, "bn_bwd_reduce: channel count / pitch");
     cudaStream_t st = as_stream(s);
@@ -636,21 +695,34 @@ extern "C" int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int
     DISPATCH_T(dtype,
                (bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(
                    reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
-                   reinterpret_cast<const __nv_bfloat16*>(raw), raw_ld, mean, invstd, n_pix, c, relu, sums)),
+                   reinterpret_cast<const __nv_bfloat16*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums)),
                (bn_bwd_reduce_kernel<float><<<grid, 256, sm, st>>>(
                    reinterpret_cast<const float*>(dy), dy_ld, reinterpret_cast<const float*>(y), y_ld,
-                   reinterpret_cast<const float*>(raw), raw_ld, mean, invstd, n_pix, c, relu, sums)),
+                   reinterpret_cast<const float*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums)),
                "bn_bwd_reduce");
     count_launch();
     return check_launch("bn_bwd_reduce_kernel");
 }
 
-extern "C" int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
-                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
-                                  int64_t n_pix, int c, int relu, int dtype, void* d_raw, int d_raw_ld, int d_raw_dtype,
-                                  void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s) {
+extern "C" int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                                   const float* mean, const float* invstd, int64_t n_pix, int c, int relu, int dtype,
+                                   float* sums, rtsds_stream_t s) {
+    RTSDS_REQUIRE(!relu || y, "bn_bwd_reduce: y required for the ReLU mask");
+    return bn_bwd_reduce_impl(dy, dy_ld, y, y_ld, raw, raw_ld, mean, invstd, nullptr, nullptr, n_pix, c, relu, dtype, sums, s);
+}
+
+extern "C" int rtsds_bn_bwd_reduce_rawmask(const void* dy, int dy_ld, const void* raw, int raw_ld, const float* mean,
+                                           const float* invstd, const float* fwd_scale, const float* fwd_shift, int64_t n_pix,
+                                           int c, int dtype, float* sums, rtsds_stream_t s) {
+    return bn_bwd_reduce_impl(dy, dy_ld, nullptr, 0, raw, raw_ld, mean, invstd, fwd_scale, fwd_shift, n_pix, c, 1, dtype, sums, s);
+}
+
+static int bn_bwd_apply_impl(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                             const float* mean, const float* invstd, const float* gamma, const float* sums, const float* fsc,
+                             const float* fsh, int64_t n_pix, int c, int relu, int dtype, void* d_raw, int d_raw_ld,
+                             int d_raw_dtype, void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s) {
     RTSDS_REQUIRE(dy && raw && mean && invstd && sums && d_raw && n_pix > 0 && c > 0, "bn_bwd_apply: bad argument");
-    RTSDS_REQUIRE(!relu || y, "bn_bwd_apply: y required for the ReLU mask");
+    RTSDS_REQUIRE(!relu || y || (fsc && fsh), "bn_bwd_apply: the ReLU mask needs y or the forward scale/shift");
     const int cg = (c + 7) / 8;
     RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && d_raw_ld % 8 == 0 && d_raw_ld >= cg * 8, "bn_bwd_apply: pitches must be multiples of 8");
     RTSDS_REQUIRE(!g_out || (g_ld % 8 == 0 && g_ld >= cg * 8), "bn_bwd_apply: g_out pitch");
@@ -659,7 +731,7 @@ extern "C" int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int 
 #define BN_APPLY(T, TO)                                                                                                  \
     bn_bwd_apply_kernel<T, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(dy), dy_ld, reinterpret_cast<const T*>(y), \
                                                      y_ld, reinterpret_cast<const T*>(raw), raw_ld, mean, invstd, gamma,   \
-                                                     sums, n_pix, c, relu, reinterpret_cast<TO*>(d_raw), d_raw_ld,         \
+                                                     sums, fsc, fsh, n_pix, c, relu, reinterpret_cast<TO*>(d_raw), d_raw_ld, \
                                                      reinterpret_cast<T*>(g_out), g_ld, dgamma, dbeta)
     if (dtype == RTSDS_BF16 && d_raw_dtype == RTSDS_BF16) BN_APPLY(__nv_bfloat16, __nv_bfloat16);
     else if (dtype == RTSDS_F32 && d_raw_dtype == RTSDS_F32) BN_APPLY(float, float);
@@ -668,6 +740,23 @@ extern "C" int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int 
 #undef BN_APPLY
     count_launch();
     return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int rtsds_bn_bwd_apply(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,
+                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
+                                  int64_t n_pix, int c, int relu, int dtype, void* d_raw, int d_raw_ld, int d_raw_dtype,
+                                  void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s) {
+    RTSDS_REQUIRE(!relu || y, "bn_bwd_apply: y required for the ReLU mask");
+    return bn_bwd_apply_impl(dy, dy_ld, y, y_ld, raw, raw_ld, mean, invstd, gamma, sums, nullptr, nullptr, n_pix, c, relu, dtype,
+                             d_raw, d_raw_ld, d_raw_dtype, g_out, g_ld, dgamma, dbeta, s);
+}
+
+extern "C" int rtsds_bn_bwd_apply_rawmask(const void* dy, int dy_ld, const void* raw, int raw_ld, const float* mean,
+                                          const float* invstd, const float* gamma, const float* sums, const float* fwd_scale,
+                                          const float* fwd_shift, int64_t n_pix, int c, int dtype, void* d_raw, int d_raw_ld,
+                                          int d_raw_dtype, void* g_out, int g_ld, float* dgamma, float* dbeta, rtsds_stream_t s) {
+    return bn_bwd_apply_impl(dy, dy_ld, nullptr, 0, raw, raw_ld, mean, invstd, gamma, sums, fwd_scale, fwd_shift, n_pix, c, 1, dtype,
+                             d_raw, d_raw_ld, d_raw_dtype, g_out, g_ld, dgamma, dbeta, s);
 }
 
 extern "C" int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, int dtype, float* out, rtsds_stream_t s) {

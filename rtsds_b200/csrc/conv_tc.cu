@@ -33,6 +33,7 @@
 #include "tap_problem.cuh"
 #include <mutex>
 #include <cstring>
+#include <cstdlib>
 
 namespace rtsds {
 
@@ -794,9 +795,18 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             ptx::tmem_ld_wait();
             if (co < p.cout) {
                 float* dst = p.dw + (static_cast<long long>(co) * p.n_taps + tap) * p.cin + ci0 + c0;
+                if (ci0 + c0 + 32 <= p.cin) {
+                    // 16-byte vector reductions: 8 per thread instead of 32 scalar atomics (cin % 64 == 0 keeps dst aligned)
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (ci0 + c0 + j < p.cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ci0 + c0 + j < p.cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+                }
             }
         }
     }
@@ -843,14 +853,15 @@ extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, cons
     p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
     p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
     p.cout = d->cout; p.cin = d->cin; p.n_taps = t.n_taps;
-    const int block_n = d->cin >= 128 ? 128 : 64;
+    const int block_n = d->cin >= 256 ? 256 : (d->cin >= 128 ? 128 : 64);
     p.ci_tiles = static_cast<int>(cdiv(d->cin, block_n));
     const long long tiles_total = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
     RTSDS_REQUIRE(tiles_total < (1LL << 30), "conv2d_tc_wgrad: too many tiles");
     p.tiles_total = static_cast<int>(tiles_total);
     const int co_tiles = static_cast<int>(cdiv(d->cout, TC_BLOCK_M));
     const long long base = static_cast<long long>(t.n_taps) * p.ci_tiles * co_tiles;
-    long long splits = cdiv(2LL * num_sms(), base);
+    // one CTA per SM is resident (shared memory): aim at whole waves, never a ragged extra one
+    long long splits = (base >= num_sms() / 2 ? 1LL : 2LL) * num_sms() / base;
     if (splits > tiles_total) splits = tiles_total;
     if (splits < 1) splits = 1;
     p.tiles_per_split = static_cast<int>(cdiv(tiles_total, splits));
@@ -872,10 +883,11 @@ extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, cons
     }
     for (int i = 0; i < 4; ++i)
         if (!t.view[i].used) maps.b[i] = maps.b[first];
-    int stages = block_n == 128 ? 3 : 4;
+    int stages = block_n == 256 ? 2 : (block_n == 128 ? 3 : 4);
     if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
     p.stages = stages;
     dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps * p.ci_tiles), static_cast<unsigned>(co_tiles));
+    if (block_n == 256) return launch_wgrad<256>(maps, p, grid, as_stream(s));
     if (block_n == 128) return launch_wgrad<128>(maps, p, grid, as_stream(s));
     return launch_wgrad<64>(maps, p, grid, as_stream(s));
 }

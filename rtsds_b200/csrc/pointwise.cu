@@ -73,6 +73,35 @@ scale_shift_act_kernel(const TX* __restrict__ x, const float* __restrict__ scale
                        const TY* residual, long long n_pix, int c, int x_ld, int res_ld, int y_ld,
                        int act, float slope, TY* y) {
     const int cg = (c + 7) / 8;
+    if (VEC && blockDim.x % cg == 0) {
+        // every thread keeps ONE 8-channel group: its scale / shift live in registers, two pixels in flight per iteration
+        const int c0 = (threadIdx.x % cg) * 8;
+        const long long prows = blockDim.x / cg, stride = prows * gridDim.x;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale ? __ldg(scale + c0 + j) : 1.f; sh[j] = shift ? __ldg(shift + c0 + j) : 0.f; }
+        for (long long p0 = static_cast<long long>(blockIdx.x) * prows + threadIdx.x / cg; p0 < n_pix; p0 += 2 * stride) {
+            const long long p1 = p0 + stride;
+            const bool two = p1 < n_pix;
+            float v0[8], v1[8], r0[8], r1[8];
+            V8io<TX>::ld(x + p0 * x_ld + c0, v0);
+            if (two) V8io<TX>::ld(x + p1 * x_ld + c0, v1);
+            if (residual) {
+                V8io<TY>::ld(residual + p0 * res_ld + c0, r0);
+                if (two) V8io<TY>::ld(residual + p1 * res_ld + c0, r1);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t0 = v0[j] * sc[j] + sh[j], t1 = v1[j] * sc[j] + sh[j];
+                if (residual) { t0 += r0[j]; t1 += r1[j]; }
+                v0[j] = apply_act(t0, act, slope);
+                v1[j] = apply_act(t1, act, slope);
+            }
+            V8io<TY>::st(y + p0 * y_ld + c0, v0);
+            if (two) V8io<TY>::st(y + p1 * y_ld + c0, v1);
+        }
+        return;
+    }
     const long long total = n_pix * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
