@@ -215,18 +215,14 @@ resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld,
 // and block.
 constexpr int FU_COLS = 128, FU_ROWS = 8, FU_CMAX = 20, FU_KR = 3, FU_FC = 20, FU_AP = FU_KR * FU_CMAX + 1;
 
-__device__ __forceinline__ float sel3(const float (&a)[FU_KR][FU_CMAX], int k, int ch) {
-    return k == 0 ? a[0][ch] : (k == 1 ? a[1][ch] : a[2][ch]);
-}
-
 __global__ void __launch_bounds__(FU_COLS)
 resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
                        const long long* __restrict__ target, long long ignore_index, double* acc,
                        long long* __restrict__ pred_out, float* __restrict__ dz) {
     __shared__ float s_z[FU_KR * FU_FC * FU_CMAX];
     __shared__ float s_a[FU_COLS * FU_AP];
-    __shared__ int s_xi[2 * FU_COLS];
     __shared__ float s_xl[2 * FU_COLS];
+    __shared__ int s_run[4 * FU_FC];          // per source column: [first, last] thread whose i0 / i1 it is
     __shared__ double s_red[3][FU_COLS / 32];
     const int tid = threadIdx.x;
     const int img = blockIdx.z, oy0 = blockIdx.y * FU_ROWS, ox0 = blockIdx.x * FU_COLS;
@@ -240,89 +236,111 @@ resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_l
         const int col = rc % ncols, row = rc / ncols;
         s_z[i] = __ldg(z + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch);
     }
+    for (int i = tid; i < 4 * FU_FC; i += FU_COLS) s_run[i] = (i & 1) ? -1 : FU_COLS;      // empty runs: first > last
     const int ox = ox0 + tid;
     const bool col_ok = ox < ow;
     const Lerp lx = lerp_src(min(ox, ow - 1), rw, w);
     const int xi0 = lx.i0 - xs, xi1 = lx.i1 - xs;
-    s_xi[2 * tid] = xi0; s_xi[2 * tid + 1] = xi1;
     s_xl[2 * tid] = col_ok ? lx.l0 : 0.f; s_xl[2 * tid + 1] = col_ok ? lx.l1 : 0.f;
     __syncthreads();
-    float zx[FU_KR][FU_CMAX], a[FU_KR][FU_CMAX];
+    // source columns are non-decreasing in tid: the threads that use column j as i0 (or i1) form one contiguous run
+    {
+        const Lerp lp = lerp_src(min(max(ox - 1, 0), ow - 1), rw, w), ln = lerp_src(min(ox + 1, ow - 1), rw, w);
+        const bool first = tid == 0, last = tid == FU_COLS - 1;
+        if (first || lp.i0 - xs != xi0) s_run[4 * xi0 + 0] = tid;
+        if (last || ln.i0 - xs != xi0) s_run[4 * xi0 + 1] = tid;
+        if (first || lp.i1 - xs != xi1) s_run[4 * xi1 + 2] = tid;
+        if (last || ln.i1 - xs != xi1) s_run[4 * xi1 + 3] = tid;
+    }
+    // Registers hold the x-interpolated z values of the CURRENT source-row pair (zA = row kcur, zB = row kcur+1) and
+    // the row-direction adjoint accumulators of the same two rows; when the strip moves on to the next source row
+    // the finished accumulator row is flushed to shared memory and the pair shifts (no dynamic register indexing).
+    float zA[FU_CMAX], zB[FU_CMAX], aA[FU_CMAX], aB[FU_CMAX];
+    auto load_row = [&](float (&dst)[FU_CMAX], int k) {
 #pragma unroll
-    for (int k = 0; k < FU_KR; ++k)
+        for (int ch = 0; ch < FU_CMAX; ++ch)
+            dst[ch] = (k < nrows && ch < c) ? lx.l0 * s_z[(k * ncols + xi0) * c + ch] + lx.l1 * s_z[(k * ncols + xi1) * c + ch] : 0.f;
+    };
+    auto flush_row = [&](const float (&src)[FU_CMAX], int k) {
+        if (k < FU_KR) {
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) s_a[tid * FU_AP + k * FU_CMAX + ch] = src[ch];
+        }
+    };
+    load_row(zA, 0);
+    load_row(zB, 1);
+#pragma unroll
+    for (int ch = 0; ch < FU_CMAX; ++ch) { aA[ch] = 0.f; aB[ch] = 0.f; }
+    int kcur = 0;
+    float loss = 0.f, nvalid = 0.f, ncorrect = 0.f;
+#pragma unroll 1
+    for (int ry = 0; ry < FU_ROWS; ++ry) {
+        const int oy = oy0 + ry;
+        if (oy >= oh) break;
+        const Lerp ly = lerp_src(oy, rh, h);
+        const int k0 = ly.i0 - ys, k1 = ly.i1 - ys;
+        while (kcur < k0) {                                    // uniform across the block (same output row)
+            flush_row(aA, kcur);
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch) { aA[ch] = aB[ch]; aB[ch] = 0.f; zA[ch] = zB[ch]; }
+            ++kcur;
+            load_row(zB, kcur + 1);
+        }
+        if (!col_ok) continue;
+        const float l0 = (k1 == k0) ? ly.l0 + ly.l1 : ly.l0;     // clamped border row: both weights hit the same source row
+        const float l1 = (k1 == k0) ? 0.f : ly.l1;
+        const long long pix = (static_cast<long long>(img) * oh + oy) * ow + ox;
+        const long long t = target ? __ldg(target + pix) : ignore_index;
+        float v[FU_CMAX];
+        float m = -INFINITY;
+        int arg = 0;
 #pragma unroll
         for (int ch = 0; ch < FU_CMAX; ++ch) {
-            a[k][ch] = 0.f;
-            zx[k][ch] = (k < nrows && ch < c) ? lx.l0 * s_z[(k * ncols + xi0) * c + ch] + lx.l1 * s_z[(k * ncols + xi1) * c + ch] : 0.f;
+            if (ch < c) {
+                v[ch] = l0 * zA[ch] + l1 * zB[ch];
+                if (v[ch] > m || (v[ch] != v[ch] && m == m)) { m = v[ch]; arg = ch; }
+            }
         }
-    float loss = 0.f, nvalid = 0.f, ncorrect = 0.f;
-    if (col_ok) {
-#pragma unroll 1
-        for (int ry = 0; ry < FU_ROWS; ++ry) {
-            const int oy = oy0 + ry;
-            if (oy >= oh) break;
-            const Lerp ly = lerp_src(oy, rh, h);
-            const int k0 = ly.i0 - ys, k1 = ly.i1 - ys;
-            const long long pix = (static_cast<long long>(img) * oh + oy) * ow + ox;
-            const long long t = target ? __ldg(target + pix) : ignore_index;
-            float v[FU_CMAX];
-            float m = -INFINITY;
-            int arg = 0;
+        if (pred_out) pred_out[pix] = arg;
+        if (arg == t) ncorrect += 1.f;
+        if (t == ignore_index || t < 0 || t >= c) continue;
+        float ssum = 0.f, vt = 0.f;
 #pragma unroll
-            for (int ch = 0; ch < FU_CMAX; ++ch) {
-                if (ch < c) {
-                    v[ch] = ly.l0 * sel3(zx, k0, ch) + ly.l1 * sel3(zx, k1, ch);
-                    if (v[ch] > m || (v[ch] != v[ch] && m == m)) { m = v[ch]; arg = ch; }
-                }
+        for (int ch = 0; ch < FU_CMAX; ++ch) {
+            if (ch < c) {
+                if (ch == t) vt = v[ch];
+                v[ch] = __expf(v[ch] - m);
+                ssum += v[ch];
             }
-            if (pred_out) pred_out[pix] = arg;
-            if (arg == t) ncorrect += 1.f;
-            if (t == ignore_index || t < 0 || t >= c) continue;
-            float ssum = 0.f, vt = 0.f;
+        }
+        loss += m + __logf(ssum) - vt;
+        nvalid += 1.f;
+        const float inv = 1.0f / ssum;
 #pragma unroll
-            for (int ch = 0; ch < FU_CMAX; ++ch) {
-                if (ch < c) {
-                    if (ch == t) vt = v[ch];
-                    v[ch] = __expf(v[ch] - m);
-                    ssum += v[ch];
-                }
-            }
-            loss += m + __logf(ssum) - vt;
-            nvalid += 1.f;
-            const float inv = 1.0f / ssum;
-            const float w0 = (k0 == 0 ? ly.l0 : 0.f) + (k1 == 0 ? ly.l1 : 0.f);
-            const float w1 = (k0 == 1 ? ly.l0 : 0.f) + (k1 == 1 ? ly.l1 : 0.f);
-            const float w2 = (k0 == 2 ? ly.l0 : 0.f) + (k1 == 2 ? ly.l1 : 0.f);
-#pragma unroll
-            for (int ch = 0; ch < FU_CMAX; ++ch) {
-                if (ch < c) {
-                    const float g = v[ch] * inv - (ch == t ? 1.f : 0.f);
-                    a[0][ch] = fmaf(w0, g, a[0][ch]);
-                    a[1][ch] = fmaf(w1, g, a[1][ch]);
-                    a[2][ch] = fmaf(w2, g, a[2][ch]);
-                }
+        for (int ch = 0; ch < FU_CMAX; ++ch) {
+            if (ch < c) {
+                const float g = v[ch] * inv - (ch == t ? 1.f : 0.f);
+                aA[ch] = fmaf(l0, g, aA[ch]);
+                aB[ch] = fmaf(l1, g, aB[ch]);
             }
         }
     }
     if (dz) {
+        flush_row(aA, kcur);
+        flush_row(aB, kcur + 1);
+        for (int k = kcur + 2; k < FU_KR; ++k) {
 #pragma unroll
-        for (int k = 0; k < FU_KR; ++k)
-#pragma unroll
-            for (int ch = 0; ch < FU_CMAX; ++ch) s_a[tid * FU_AP + k * FU_CMAX + ch] = a[k][ch];
+            for (int ch = 0; ch < FU_CMAX; ++ch) s_a[tid * FU_AP + k * FU_CMAX + ch] = 0.f;
+        }
         __syncthreads();
-        const float inv_rw = 1.0f / rw;
         for (int i = tid; i < nrows * ncols * c; i += FU_COLS) {
             const int ch = i % c;
             const int rc = i / c;
             const int col = rc % ncols, k = rc / ncols;
-            int lo = static_cast<int>(floorf((static_cast<float>(xs + col) - 0.5f) * inv_rw - 0.5f)) - 1 - ox0;
-            int hi = static_cast<int>(ceilf((static_cast<float>(xs + col) + 1.5f) * inv_rw - 0.5f)) + 1 - ox0;
-            lo = max(lo, 0); hi = min(hi, FU_COLS - 1);
+            const int off = k * FU_CMAX + ch;
             float sum = 0.f;
-            for (int tx = lo; tx <= hi; ++tx) {
-                const float wx = (s_xi[2 * tx] == col ? s_xl[2 * tx] : 0.f) + (s_xi[2 * tx + 1] == col ? s_xl[2 * tx + 1] : 0.f);
-                sum = fmaf(wx, s_a[tx * FU_AP + k * FU_CMAX + ch], sum);
-            }
+            for (int tx = s_run[4 * col + 0]; tx <= s_run[4 * col + 1]; ++tx) sum = fmaf(s_xl[2 * tx], s_a[tx * FU_AP + off], sum);
+            for (int tx = s_run[4 * col + 2]; tx <= s_run[4 * col + 3]; ++tx) sum = fmaf(s_xl[2 * tx + 1], s_a[tx * FU_AP + off], sum);
             if (sum != 0.f)
                 atomicAdd(dz + ((static_cast<long long>(img) * h + ys + k) * w + xs + col) * z_ld + ch, sum);
         }
