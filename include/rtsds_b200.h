@@ -161,6 +161,24 @@ int rtsds_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int kh,
 int rtsds_unpack_conv_wgrad(float* dw_packed /* zeroed on return */, int cout, int cin, int kh, int kw,
                             int accumulate, float* grad_oihw, rtsds_stream_t s);
 
+/* Batched forms of the weight (re)packing and gradient unpacking above: one launch for up to 40 / 48 layers
+ * (the per-layer kernels are launch-latency bound: a training step repacks every conv weight after
+ * optimizer.step(), train.py:96, and converts every wgrad result).  `jobs` is a HOST array.
+ *   pack job:   kind 0 -> out[cout_pad][taps][cin_pad];  kind 1 -> dgrad operand out[cin_pad][taps][ck]
+ *   unpack job: as rtsds_unpack_conv_wgrad_cpad (dw_packed is zeroed on return). */
+typedef struct RtsdsPackJob {
+    const float* w;     /* OIHW fp32 */
+    void* out;
+    int cout, cin, cin_pad, taps, cout_pad, kind, ck;
+} RtsdsPackJob;
+typedef struct RtsdsUnpackJob {
+    float* dw_packed;   /* fp32 [cout][taps][cin_src] */
+    float* grad;        /* OIHW fp32 */
+    int cout, cin, cin_src, taps, accumulate;
+} RtsdsUnpackJob;
+int rtsds_pack_conv_weights_batch(const RtsdsPackJob* jobs, int n_jobs, int dtype, rtsds_stream_t s);
+int rtsds_unpack_conv_wgrads_batch(const RtsdsUnpackJob* jobs, int n_jobs, rtsds_stream_t s);
+
 /* Stem convolutions read the API-boundary image directly:
  * x fp32 NCHW [n,cin,h,w] (cin <= 32), w fp32 OIHW, y NHWC of out_dtype,
  * with scale/shift/act/stats as above.  softmax_in != 0 applies a softmax

@@ -30,6 +30,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """RtsdsPackJob (include/rtsds_b200.h)."""
+
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("cout", C.c_int), ("cin", C.c_int), ("cin_pad", C.c_int),
+                ("taps", C.c_int), ("cout_pad", C.c_int), ("kind", C.c_int), ("ck", C.c_int)]
+
+
+class UnpackJob(C.Structure):
+    """RtsdsUnpackJob (include/rtsds_b200.h)."""
+
+    _fields_ = [("dw_packed", C.c_void_p), ("grad", C.c_void_p), ("cout", C.c_int), ("cin", C.c_int), ("cin_src", C.c_int),
+                ("taps", C.c_int), ("accumulate", C.c_int)]
+
+
 _P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _CD = C.POINTER(ConvDesc)
 
@@ -47,6 +61,8 @@ SIGNATURES = {
     "rtsds_conv2d_tc_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_simt_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rtsds_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_pack_conv_weights_batch": (_I, [_P, _I, _I, _P]),
+    "rtsds_unpack_conv_wgrads_batch": (_I, [_P, _I, _P]),
     "rtsds_conv2d_tc_dgrad_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_tc_dgrad": (_I, [_CD, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "rtsds_conv2d_tc_wgrad": (_I, [_CD, _P, _P, _P, _P]),

@@ -70,11 +70,20 @@ class _ConvBN:
             self.d.out_ld = y.ld
             self.d.out_dtype = y.dtype
         self.wpk = plan.buf(ops.cout_pad(self.cout), k * k, cin)
-        plan.pack_steps.append(lambda: ops.pack_conv_weight(conv.weight, dt, self.wpk))
+        batched = hasattr(plan, "pack_jobs")        # plans that batch weight packing / gradient unpacking into few launches
+        if batched:
+            plan.pack_jobs.append((conv, self.wpk, 0))
+            self.dw = plan.zeros(self.cout * k * k * cin, dtype=torch.float32)     # kept zero: unpack clears what it reads
+        else:
+            plan.pack_steps.append(lambda: ops.pack_conv_weight(conv.weight, dt, self.wpk))
+            self.dw = None
         self.ck = ops.dgrad_ck(self.cout, self.tc)
         if need_dx:
             self.wdg = plan.buf(ops.cout_pad(cin), k * k, self.ck)
-            plan.pack_steps.append(lambda: ops.pack_conv_weight_dgrad(conv.weight, dt, self.tc, self.wdg))
+            if batched:
+                plan.pack_jobs.append((conv, self.wdg, 1))
+            else:
+                plan.pack_steps.append(lambda: ops.pack_conv_weight_dgrad(conv.weight, dt, self.tc, self.wdg))
         # backward geometry: dy operand (d_raw) pitch = ck (tensor cores) / cout rounded to 8
         self.dyld = max(self.ck, cpad8)
         plan.note_scratch(n * self.oh * self.ow * self.dyld, self.cout * k * k * cin)
@@ -149,9 +158,13 @@ class _ConvBN:
         dd.out_ld = d_raw.ld
         gwt = gw.get(self.conv.weight)
         if gwt is not None:
-            dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
-            ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)
-            ops.unpack_conv_wgrad(dwp, gwt, True)
+            if self.dw is not None:
+                ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, self.dw, self.tc)
+                p.pending_unpack.append((self.dw, gwt, True))                # converted in one launch per bucket
+            else:
+                dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
+                ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)
+                ops.unpack_conv_wgrad(dwp, gwt, True)
         if dx is not None:
             dd.in_ld = dx.ld
             dd.res_ld = dx.ld
@@ -218,12 +231,18 @@ class BiSeNetTrainPlan:
         self.tdt = ops.torch_dtype(self.dt)
         self.nc = model.conv.weight.shape[0]
         self._keep, self.pack_steps = [], []
+        self.pack_jobs, self.pending_unpack = [], []
         self._stats_total = 0
         self._scratch_act, self._scratch_w, self._ws_bytes = 0, 0, 0
         self._param_version = None
         self.generation = 0
         self.ws = None
         self._build()
+
+    def flush_unpack(self):
+        if self.pending_unpack:
+            ops.unpack_conv_wgrads_batch(self.pending_unpack)
+            self.pending_unpack = []
 
     # ---------------- allocation helpers ----------------
     def buf(self, *shape, dtype=None):
@@ -363,6 +382,7 @@ class BiSeNetTrainPlan:
         if ver != self._param_version:
             for s in self.pack_steps:
                 s()
+            ops.pack_conv_weights_batch([(c.weight, out, kind) for c, out, kind in self.pack_jobs], self.dt, self.use_tc)
             self._param_version = self._params_version()
 
     # ---------------- forward ----------------
@@ -431,6 +451,13 @@ class BiSeNetTrainPlan:
         m, n, dt = self.model, self.n, self.dt
         s = _s()
         a = self.arm
+        user_ready = ready
+
+        def ready(group):                       # a bucket is final only once its wgrad results are in OIHW form
+            self.flush_unpack()
+            user_ready(group)
+
+        self.pending_unpack = []
         h8, w8, nc, c3, c4, s3, s4 = self.h8, self.w8, self.nc, self.c3, self.c4, self.s3, self.s4
         npix8 = n * h8 * w8
         ffm = m.feature_fusion_module
@@ -506,6 +533,7 @@ class BiSeNetTrainPlan:
         d1 = _Buf(self.gB, ld=64, dtype=dt)
         self.sp2.backward(d2, gw, dx=d1, dx_accumulate=False)
         self.sp1.backward(self.x, d1, gw, wgrad=not self.use_tc)
+        self.flush_unpack()
         if self.use_tc:
             g7, g3 = gw.get(self.cp0.conv.weight), gw.get(self.sp1.conv.weight)
             if g7 is not None or g3 is not None:

@@ -10,6 +10,7 @@
 // register tile per thread, K walked as (tap, 16-channel chunk) through shared
 // memory.  Also here: the weight repacking kernels shared with the tensor-core path.
 #include "common.cuh"
+#include <cstring>
 #include "tap_problem.cuh"
 
 namespace rtsds {
@@ -261,6 +262,70 @@ unpack_wgrad_kernel(float* __restrict__ dw, int cout, int cin, int cin_src, int 
     }
 }
 
+// ---- batched variants: one launch for many layers (the per-layer kernels above are launch-latency bound) ----
+constexpr int PACK_BATCH = 40;
+struct PackBatch { RtsdsPackJob jobs[PACK_BATCH]; };
+template <typename T>
+__global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__ PackBatch b) {
+    const RtsdsPackJob& j = b.jobs[blockIdx.y];
+    T* out = reinterpret_cast<T*>(j.out);
+    const float* __restrict__ w = j.w;
+    if (j.kind == 0) {              // [cout_pad][taps][cin_pad]
+        const long long total = static_cast<long long>(j.cout_pad) * j.taps * j.cin_pad;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int c = static_cast<int>(i % j.cin_pad);
+            const long long r = i / j.cin_pad;
+            const int t = static_cast<int>(r % j.taps);
+            const int co = static_cast<int>(r / j.taps);
+            const float v = (co < j.cout && c < j.cin) ? w[(static_cast<long long>(co) * j.cin + c) * j.taps + t] : 0.f;
+            out[i] = from_f32<T>(v);
+        }
+    } else {                        // dgrad operand [cin_pad][taps][ck]
+        const long long total = static_cast<long long>(j.cin_pad) * j.taps * j.ck;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int co = static_cast<int>(i % j.ck);
+            const long long r = i / j.ck;
+            const int t = static_cast<int>(r % j.taps);
+            const int ci = static_cast<int>(r / j.taps);
+            const float v = (co < j.cout && ci < j.cin) ? w[(static_cast<long long>(co) * j.cin + ci) * j.taps + t] : 0.f;
+            out[i] = from_f32<T>(v);
+        }
+    }
+}
+
+constexpr int UNPACK_BATCH = 48;
+struct UnpackBatch { RtsdsUnpackJob jobs[UNPACK_BATCH]; int first_block[UNPACK_BATCH + 1]; int n; };
+__global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant__ UnpackBatch b) {
+    extern __shared__ float s_t[];                  // [taps][UNP_CI + 1]
+    int ji = 0;
+    while (ji + 1 < b.n && static_cast<int>(blockIdx.x) >= b.first_block[ji + 1]) ++ji;
+    const RtsdsUnpackJob& j = b.jobs[ji];
+    const int local = blockIdx.x - b.first_block[ji];
+    const int chunks = (j.cin_src + UNP_CI - 1) / UNP_CI;
+    const int co = local / chunks;
+    const int ci0 = (local - co * chunks) * UNP_CI;
+    const int taps = j.taps;
+    const int nci = min(UNP_CI, j.cin_src - ci0);
+    float* src = j.dw_packed + static_cast<long long>(co) * taps * j.cin_src;
+    for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
+        const int t = i / nci, c = i - t * nci;
+        float* p = src + static_cast<long long>(t) * j.cin_src + ci0 + c;
+        s_t[t * (UNP_CI + 1) + c] = *p;
+        *p = 0.f;
+    }
+    __syncthreads();
+    const int nout = min(nci, j.cin - ci0);
+    if (nout <= 0) return;
+    float* dst = j.grad + (static_cast<long long>(co) * j.cin + ci0) * taps;
+    for (int i = threadIdx.x; i < taps * nout; i += blockDim.x) {
+        const int c = i / taps, t = i - c * taps;
+        const float v = s_t[t * (UNP_CI + 1) + c];
+        dst[i] = j.accumulate ? dst[i] + v : v;
+    }
+}
+
 int conv_cout_pad(int cout);
 
 static int simt_run(const TapProblem& t, int in_dtype, cudaStream_t st) {
@@ -410,4 +475,58 @@ extern "C" int rtsds_unpack_conv_wgrad(float* dw_packed, int cout, int cin, int 
 extern "C" int rtsds_unpack_conv_wgrad_cpad(float* dw_packed, int cout, int cin, int cin_src, int kh, int kw, int accumulate,
                                             float* grad_oihw, rtsds_stream_t s) {
     return unpack_impl(dw_packed, cout, cin, cin_src, kh, kw, accumulate, grad_oihw, s);
+}
+
+extern "C" int rtsds_pack_conv_weights_batch(const RtsdsPackJob* jobs, int n_jobs, int dtype, rtsds_stream_t s) {
+    RTSDS_REQUIRE(jobs && n_jobs > 0, "pack_conv_weights_batch: no jobs");
+    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "pack_conv_weights_batch: bad dtype");
+    for (int i = 0; i < n_jobs; ++i) {
+        const RtsdsPackJob& j = jobs[i];
+        RTSDS_REQUIRE(j.w && j.out && j.cout > 0 && j.cin > 0 && j.taps > 0 && j.cout_pad >= j.cout && j.cin_pad >= j.cin &&
+                          (j.kind == 0 || (j.kind == 1 && j.ck >= j.cout)), "pack_conv_weights_batch: bad job %d", i);
+    }
+    for (int base = 0; base < n_jobs; base += PACK_BATCH) {
+        PackBatch b;
+        memset(&b, 0, sizeof(b));
+        const int n = n_jobs - base < PACK_BATCH ? n_jobs - base : PACK_BATCH;
+        for (int i = 0; i < n; ++i) b.jobs[i] = jobs[base + i];
+        dim3 grid(48, n);
+        if (dtype == RTSDS_BF16) pack_batch_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(b);
+        else pack_batch_kernel<float><<<grid, 256, 0, as_stream(s)>>>(b);
+        count_launch();
+        int rc = check_launch("pack_batch_kernel");
+        if (rc != RTSDS_OK) return rc;
+    }
+    return RTSDS_OK;
+}
+
+extern "C" int rtsds_unpack_conv_wgrads_batch(const RtsdsUnpackJob* jobs, int n_jobs, rtsds_stream_t s) {
+    RTSDS_REQUIRE(jobs && n_jobs > 0, "unpack_conv_wgrads_batch: no jobs");
+    for (int base = 0; base < n_jobs; base += UNPACK_BATCH) {
+        UnpackBatch b;
+        memset(&b, 0, sizeof(b));
+        const int n = n_jobs - base < UNPACK_BATCH ? n_jobs - base : UNPACK_BATCH;
+        int blocks = 0, max_taps = 1;
+        for (int i = 0; i < n; ++i) {
+            const RtsdsUnpackJob& j = jobs[base + i];
+            RTSDS_REQUIRE(j.dw_packed && j.grad && j.cout > 0 && j.cin > 0 && j.cin_src >= j.cin && j.taps > 0 && j.taps <= 49,
+                          "unpack_conv_wgrads_batch: bad job %d", base + i);
+            b.jobs[i] = j;
+            b.first_block[i] = blocks;
+            blocks += j.cout * static_cast<int>(cdiv(j.cin_src, UNP_CI));
+            if (j.taps > max_taps) max_taps = j.taps;
+        }
+        b.first_block[n] = blocks;
+        b.n = n;
+        const size_t smem = sizeof(float) * max_taps * (UNP_CI + 1);
+        if (smem > 48 * 1024) {
+            static bool done = false;
+            if (!done) { cudaFuncSetAttribute(unpack_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); done = true; }
+        }
+        unpack_batch_kernel<<<blocks, 256, smem, as_stream(s)>>>(b);
+        count_launch();
+        int rc = check_launch("unpack_batch_kernel");
+        if (rc != RTSDS_OK) return rc;
+    }
+    return RTSDS_OK;
 }

@@ -44,6 +44,8 @@ class _PlanBase:
         if self.nc > 32:
             raise ops._lib.RtsdsError("num_classes > 32 is not supported by the head kernels")
         self._keep, self.pack_steps = [], []
+        if train:
+            self.pack_jobs, self.pending_unpack = [], []
         self._stats_total = 0
         self._scratch_act, self._scratch_w, self._ws_bytes = 0, 0, 0
         self._param_version = None
@@ -95,7 +97,14 @@ class _PlanBase:
         if ver != self._param_version:
             for s in self.pack_steps:
                 s()
+            if self.train:
+                ops.pack_conv_weights_batch([(c.weight, out, kind) for c, out, kind in self.pack_jobs], self.dt, self.use_tc)
             self._param_version = self._params_version()
+
+    def flush_unpack(self):
+        if self.pending_unpack:
+            ops.unpack_conv_wgrads_batch(self.pending_unpack)
+            self.pending_unpack = []
 
     def out_hw(self):
         h2, w2 = ops.conv_out_size(self.h, 7, 2, 3), ops.conv_out_size(self.w, 7, 2, 3)
@@ -312,6 +321,13 @@ class DeepLabTrainPlan(_PlanBase):
         """self.dz holds the gradient w.r.t. the low-resolution logits z (fp32 NHWC, pitch 32)."""
         n, dt, nc = self.n, self.dt, self.nc
         s = ops._s()
+        user_ready = ready
+
+        def ready(group):
+            self.flush_unpack()
+            user_ready(group)
+
+        self.pending_unpack = []
         npix = n * self.hf * self.wf
         # ---- ASPP: four dilated branches share dz ----
         biases = [u.conv.bias for u in self.aspp if u.conv.bias is not None and u.conv.bias in gw]
@@ -351,6 +367,7 @@ class DeepLabTrainPlan(_PlanBase):
         dstem = _Buf(self.gT1, ld=64, dtype=dt)
         check(lib().rtsds_maxpool3x3s2_bwd(self.stem.y.ptr, dy.ptr, n, self.stem.oh, self.stem.ow, 64, dt, 1, dstem.ptr, s), "maxpool_bwd")
         self.stem.backward(self.x, dstem, gw, wgrad=True)
+        self.flush_unpack()
 
 
 # ======================================================================================= autograd boundary

@@ -159,6 +159,34 @@ def unpack_conv_wgrad(dw_packed, grad_oihw: torch.Tensor, accumulate: bool) -> N
           "unpack_conv_wgrad")
 
 
+def pack_conv_weights_batch(jobs, dtype: int, tc: bool) -> None:
+    """jobs: list of (weight OIHW fp32 parameter, out tensor, kind) with kind 0 = forward layout
+    [cout_pad][taps][cin], 1 = dgrad operand [cout_pad(cin)][taps][ck]; one launch per 40 jobs."""
+    if not jobs:
+        return
+    arr = (_lib.PackJob * len(jobs))()
+    for a, (w, out, kind) in zip(arr, jobs):
+        w = w.detach()
+        co, ci, kh, kw = w.shape
+        a.w, a.out, a.cout, a.cin, a.taps, a.kind = _p(w), _p(out), co, ci, kh * kw, kind
+        if kind == 0:
+            a.cin_pad, a.cout_pad, a.ck = ci, cout_pad(co), 0
+        else:
+            a.cin_pad, a.cout_pad, a.ck = cout_pad(ci), co, dgrad_ck(co, tc)
+    check(lib().rtsds_pack_conv_weights_batch(C.cast(arr, C.c_void_p), len(jobs), dtype, _s()), "pack_conv_weights_batch")
+
+
+def unpack_conv_wgrads_batch(jobs) -> None:
+    """jobs: list of (dw_packed fp32 tensor, grad OIHW view, accumulate); one launch per 48 layers."""
+    if not jobs:
+        return
+    arr = (_lib.UnpackJob * len(jobs))()
+    for a, (dw, g, acc) in zip(arr, jobs):
+        co, ci, kh, kw = g.shape
+        a.dw_packed, a.grad, a.cout, a.cin, a.cin_src, a.taps, a.accumulate = _p(dw), _p(g), co, ci, ci, kh * kw, int(acc)
+    check(lib().rtsds_unpack_conv_wgrads_batch(C.cast(arr, C.c_void_p), len(jobs), _s()), "unpack_conv_wgrads_batch")
+
+
 def stem_conv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, k: int, stride: int, pad: int, scale=None,
               shift=None, act=ACT_NONE, slope=0.0, softmax_in=False, stats=None) -> None:
     _cuda(x, w, y)

