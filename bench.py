@@ -268,7 +268,30 @@ def run_infer(args, rank, world, local):
             e2e_step(i)
         e1.record()
         barrier(world)
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
+        e2e_serial_ms = max_over_ranks(e0.elapsed_time(e1), world)
+
+        # the same work as a steady-state loop: copies of neighbouring frames overlap the forward (rtsds_b200/serving.py);
+        # every frame is still copied in from pinned host memory and its prediction map copied back, inside the timed region
+        from rtsds_b200.serving import PipelinedSegmenter
+
+        pipe = PipelinedSegmenter(model, 1, H, W, depth=3)
+        checksum = 0
+        for i in range(6):
+            pipe.submit(host[i % n_inputs])
+        pipe.drain()
+        barrier(world)
+        t_wall = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            r = pipe.submit(host[i % n_inputs])
+            if r is not None:
+                checksum += int(r[0, 0, 0])
+        for r in pipe.drain():
+            checksum += int(r[0, 0, 0])
+        e1.record()
+        barrier(world)
+        e2e_wall_ms = 1e3 * (time.perf_counter() - t_wall)
+        e2e_ms = max(max_over_ranks(e0.elapsed_time(e1), world), max_over_ranks(e2e_wall_ms, world))
         e2e_fps = world * K / (e2e_ms / 1e3)
 
         rows = tc_conv_profile(model, dev_in[0]) if rank == 0 else []
@@ -304,7 +327,9 @@ def run_infer(args, rank, world, local):
                    "cuda_graph": cuda_graph},
         "clocks": clk.summary(),
         "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
-                "d2h_bytes_per_step": H * W * 8, "ms_per_step": round(e2e_ms / K, 4)},
+                "d2h_bytes_per_step": H * W * 8, "ms_per_step": round(e2e_ms / K, 4),
+                "how": "PipelinedSegmenter (3 frames in flight; H2D / forward+argmax / D2H on separate streams), wall clock incl. final drain",
+                "serial_fps": round(world * K / (e2e_serial_ms / 1e3), 2), "serial_ms_per_step": round(e2e_serial_ms / K, 4)},
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "readme_protocol": {"iterations": len(lat), "mean_latency_ms": round(1e3 * statistics.mean(lat), 4),

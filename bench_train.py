@@ -70,17 +70,27 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
     last_loss = loss.item()
 
     # end to end: pinned host batch -> device, step, loss read back every step (train.py:71-72,99)
-    sx, sy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
+    # the copies of batch i+1 overlap step i (rtsds_b200.serving.DevicePrefetcher: what a pin_memory DataLoader + prefetch
+    # does); every batch still crosses PCIe inside the timed region and the loss is read back every step
+    from rtsds_b200.serving import AsyncScalarReader, DevicePrefetcher
+
+    for sx, sy in DevicePrefetcher(((host_x[i % n_sets], host_y[i % n_sets]) for i in range(4)), dev):   # warm-up: staging buffers
+        step(warmup + steps, sx, sy)
+    batches = ((host_x[i % n_sets], host_y[i % n_sets]) for i in range(steps))
+    reader = AsyncScalarReader(dev)
+    n_read = 0
     bench.barrier(world)
+    t_wall = time.perf_counter()
     e0.record()
-    for i in range(steps):
-        sx.copy_(host_x[i % n_sets], non_blocking=True)
-        sy.copy_(host_y[i % n_sets], non_blocking=True)
+    for i, (sx, sy) in enumerate(DevicePrefetcher(batches, dev)):
         loss, stats = step(warmup + steps + i, sx, sy)
-        _ = loss.item()
+        n_read += reader.push(loss) is not None          # every step's loss crosses to the host, one step late
+    n_read += len(reader.drain())
+    assert n_read == steps
     e1.record()
     bench.barrier(world)
-    ms_e2e = bench.max_over_ranks(e0.elapsed_time(e1), world)
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    ms_e2e = max(bench.max_over_ranks(e0.elapsed_time(e1), world), bench.max_over_ranks(wall_ms, world))
 
     # validation pass: eval forward at 512x1024 + fused argmax/fast_hist on device, matrix all-reduced once
     model.eval()

@@ -160,7 +160,9 @@ class _ConvBN:
         if gwt is not None:
             if self.dw is not None:
                 ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, self.dw, self.tc)
-                p.pending_unpack.append((self.dw, gwt, True))                # converted in one launch per bucket
+                # converted in one launch per bucket; ASSIGNED: the flat gradient buffer of this backward pass is fresh and
+                # every conv weight receives exactly one contribution per pass (autograd accumulates across passes)
+                p.pending_unpack.append((self.dw, gwt, False))
             else:
                 dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
                 ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)

@@ -65,21 +65,31 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
         fa[j] = (rawmask && ch < c) ? fsc[ch] : 0.f; fb[j] = (rawmask && ch < c) ? fsh[ch] : 0.f;
     }
     if (prow < prows) {
-        for (long long p = static_cast<long long>(blockIdx.x) * prows + prow; p < n_pix; p += static_cast<long long>(gridDim.x) * prows) {
-            const F8 d = ld8(dy + p * dy_ld + g8 * 8);
-            const F8 r = ld8(raw + p * raw_ld + g8 * 8);
-            F8 yy;
-            if (rawmask) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) yy.v[j] = fmaf(r.v[j], fa[j], fb[j]);
-            } else if (relu) {
-                yy = ld8(y + p * y_ld + g8 * 8);
+        // two pixels per iteration: all loads are issued before the first use (memory-level parallelism)
+        const long long stride = static_cast<long long>(gridDim.x) * prows;
+        for (long long p = static_cast<long long>(blockIdx.x) * prows + prow; p < n_pix; p += 2 * stride) {
+            const long long q = p + stride;
+            const bool two = q < n_pix;
+            const F8 d0 = ld8(dy + p * dy_ld + g8 * 8);
+            const F8 r0 = ld8(raw + p * raw_ld + g8 * 8);
+            F8 d1, r1, y0, y1;
+            if (two) { d1 = ld8(dy + q * dy_ld + g8 * 8); r1 = ld8(raw + q * raw_ld + g8 * 8); }
+            if (relu && !rawmask) {
+                y0 = ld8(y + p * y_ld + g8 * 8);
+                if (two) y1 = ld8(y + q * y_ld + g8 * 8);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float g = (relu && !(yy.v[j] > 0.f)) ? 0.f : d.v[j];
-                s1[j] += g;
-                s2[j] += g * (r.v[j] - mu[j]) * is[j];
+                const float m0 = rawmask ? fmaf(r0.v[j], fa[j], fb[j]) : (relu ? y0.v[j] : 1.f);
+                const float g0 = (relu && !(m0 > 0.f)) ? 0.f : d0.v[j];
+                s1[j] += g0;
+                s2[j] += g0 * (r0.v[j] - mu[j]) * is[j];
+                if (two) {
+                    const float m1 = rawmask ? fmaf(r1.v[j], fa[j], fb[j]) : (relu ? y1.v[j] : 1.f);
+                    const float g1 = (relu && !(m1 > 0.f)) ? 0.f : d1.v[j];
+                    s1[j] += g1;
+                    s2[j] += g1 * (r1.v[j] - mu[j]) * is[j];
+                }
             }
         }
 #pragma unroll
@@ -690,7 +700,7 @@ static int bn_bwd_reduce_impl(const void* dy, int dy_ld, const void* y, int y_ld
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st);
     if (e != cudaSuccess) { set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
     const int prows = 256 / cg;
-    const int grid = grid_for(n_pix, prows, 4);
+    const int grid = grid_for(cdiv(n_pix, 2), prows, 8);
     const size_t sm = sizeof(float) * 2 * cg * 8;
     DISPATCH_T(dtype,
                (bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(

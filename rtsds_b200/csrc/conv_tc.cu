@@ -578,6 +578,9 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     // stages: keep two CTAs resident per SM (epilogue of one overlaps the main loop of the other)
     int stages = g_force_stages ? g_force_stages : (block_n == 128 ? 3 : (block_n == 64 ? 4 : 5));
     const int kb_per = kb_total / split;
+    // a grid that fits in one wave leaves one CTA per SM: use all of its shared memory as pipeline depth (the K loop of
+    // these small problems is TMA-latency bound), instead of keeping room for a second resident CTA
+    if (!g_force_stages && m_tiles * n_tiles * split <= num_sms()) stages = 12;
     if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
     while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
     p.stages = stages;

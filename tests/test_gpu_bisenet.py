@@ -293,3 +293,22 @@ def test_fused_ce_matches_stock_criterion_path(cuda):
     for k in res[0][2]:
         if not _ill_conditioned(k, "fp32"):
             assert _l2_rel(res[1][2][k], res[0][2][k]) < 5e-3, k
+
+
+def test_pipelined_segmenter_matches_direct_calls(cuda):
+    """rtsds_b200.serving.PipelinedSegmenter returns, in order, exactly what model(x).argmax(1) gives frame by frame."""
+    from rtsds_b200.serving import PipelinedSegmenter
+
+    m = _model(9, "bf16").eval()
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randn(1, 3, 128, 256, generator=g).pin_memory() for _ in range(7)]
+    with torch.no_grad():
+        want = [m(f.cuda()).argmax(1).cpu() for f in frames]
+    pipe = PipelinedSegmenter(m, 1, 128, 256, depth=3)
+    got = []
+    for f in frames:
+        r = pipe.submit(f)
+        if r is not None:
+            got.append(r.clone())
+    got += [r.clone() for r in pipe.drain()]
+    assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
