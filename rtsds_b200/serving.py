@@ -70,14 +70,16 @@ class DevicePrefetcher:
     """Training-side counterpart: wraps an iterable of pinned host (image, label) batches and yields device tensors,
     copying batch i+1 on a side stream while step i computes (what train.py:71-72's `.to(device)` does serially)."""
 
+    _staging = {}          # (device, slot, shapes) -> device buffers, shared by all instances: allocating 100+ MB per epoch is slow
+
     def __init__(self, batches, device, depth: int = 2):
         self.it, self.dev, self.depth = iter(batches), device, depth
         self.stream = torch.cuda.Stream(device)
         self.queue = []
-        self.bufs = {}
+        self.bufs = DevicePrefetcher._staging
 
     def _buffers(self, slot, tensors):
-        key = (slot, tuple((tuple(t.shape), t.dtype) for t in tensors))
+        key = (str(self.dev), slot, tuple((tuple(t.shape), t.dtype) for t in tensors))
         if key not in self.bufs:
             self.bufs[key] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in tensors]
         return self.bufs[key]
