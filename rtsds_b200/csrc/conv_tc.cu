@@ -138,16 +138,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
-        for (int i = threadIdx.x - 64; i < BLOCK_N; i += TC_THREADS - 64) {
-            const int co = n0 + i;
-            s_scale[i] = (p.scale && co < p.cout) ? p.scale[co] : 1.0f;
-            s_shift[i] = (p.shift && co < p.cout) ? p.shift[co] : 0.0f;
-        }
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+    // tail of the previous kernel in the stream; global memory is only touched after the dependency has resolved.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += TC_THREADS - 64) {
+            const int co = n0 + i;
+            s_scale[i] = (p.scale && co < p.cout) ? p.scale[co] : 1.0f;
+            s_shift[i] = (p.shift && co < p.cout) ? p.shift[co] : 0.0f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 
     if (warp == 0) {
         // =================== TMA producer ===================
@@ -477,7 +484,21 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
-    conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    static int use_pdl = -1;
+    if (use_pdl < 0) { const char* e = getenv("RTSDS_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, maps, p);
+    if (le != cudaSuccess) { set_error("conv_tc_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tc_kernel");
 }
