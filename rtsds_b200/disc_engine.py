@@ -248,6 +248,15 @@ class _DiscFn(torch.autograd.Function):
         g = dout.contiguous().view(-1).float()
         flat, gw = plan.new_grads()
         dx = plan.backward(g, gw, ctx.needs_input_grad[1])
+        if gw and getattr(plan.model, "rtsds_ddp", False):
+            # data parallel: average this pass's parameter gradients over the ranks (one small bucket: 20 K / 2.8 M floats);
+            # the input gradient stays local — it belongs to this rank's generator batch
+            from . import ddp
+
+            if ddp.is_distributed():
+                red = ddp.BucketedAllReduce(flat, {"all": (0, flat.numel())})
+                red.ready("all")
+                red.finish()
         return (None, dx, None) + tuple(gw.get(p) for p in ctx.params)
 
 

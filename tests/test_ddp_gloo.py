@@ -63,3 +63,19 @@ def test_param_buckets_rejects_holes():
         ddp.param_buckets([("a.w", torch.zeros(2)), ("b.w", torch.zeros(2)), ("a.b", torch.zeros(2))], (("a.", "A"), ("b.", "B")))
     with pytest.raises(ValueError):
         ddp.param_buckets([("c.w", torch.zeros(2))], (("a.", "A"),))
+
+
+def test_deeplab_and_discriminator_buckets_are_contiguous():
+    """Bucket layout of the other two trainable models: DeepLabV2 (5 buckets, reverse-topological) and the
+    discriminators (one bucket)."""
+    from models.deeplabv2.deeplabv2 import get_deeplab_v2
+    from rtsds_b200.deeplab_engine import DEEPLAB_GROUPS
+
+    m = get_deeplab_v2(19, pretrain=False)
+    named = list(m.named_parameters())
+    ranges = ddp.param_buckets(named, DEEPLAB_GROUPS)
+    assert set(ranges) == {"layer1", "layer2", "layer3", "layer4", "head"}
+    total = sum(p.numel() for _, p in named)
+    spans = sorted(ranges.values())
+    assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert ranges["head"][1] - ranges["head"][0] == sum(p.numel() for p in m.layer6.parameters())
