@@ -179,6 +179,24 @@ typedef struct RtsdsUnpackJob {
 int rtsds_pack_conv_weights_batch(const RtsdsPackJob* jobs, int n_jobs, int dtype, rtsds_stream_t s);
 int rtsds_unpack_conv_wgrads_batch(const RtsdsUnpackJob* jobs, int n_jobs, rtsds_stream_t s);
 
+/* ------------------------------------------------------------------------
+ * "Taps as N": k x k stride-1 conv with few output channels (c <= 32; the FFM ConvBlock 3x3 1024 -> 19,
+ * build_bisenet.py:64,74) evaluated so that the wide input is read once instead of once per tap:
+ *   forward : T = 1x1 conv of x with w_fwd (virtual OIHW [k*k*c, cin, 1, 1], N index t*c+co), then
+ *             y[p,co] = act(scale*sum_t T[p+off(t), t*c+co] + shift)  (tapn_gather; optional BN statistics of the raw sum)
+ *   backward: G[q,t*c+co] = dy[q-off(t),co] (tapn_scatter; g_ld >= k*k*c, pad columns zeroed), then
+ *             dx = 1x1 conv of G with w_bwd (virtual OIHW [cin, kpad, 1, 1]) and dW2 = 1x1 wgrad(G, x);
+ *             tapn_weight_grad ACCUMULATES dW2 ([k*k*c, cin]) into the [c, cin, k, k] gradient.
+ * ---------------------------------------------------------------------- */
+int rtsds_tapn_weights(const float* w_oihw, int c, int cin, int k, int kpad, float* w_fwd, float* w_bwd,
+                       rtsds_stream_t s);
+int rtsds_tapn_weight_grad(const float* dw2, int c, int cin, int k, float* grad_oihw, rtsds_stream_t s);
+int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int w, int c, int k, int pad, int dil,
+                      const float* scale, const float* shift, int act, float* stats, float* y, int y_ld,
+                      rtsds_stream_t s);
+int rtsds_tapn_scatter(const void* dy, int dy_ld, int dy_dtype, int n, int h, int w, int c, int k, int pad, int dil,
+                       void* g, int g_ld, int g_dtype, rtsds_stream_t s);
+
 /* Stem convolutions read the API-boundary image directly:
  * x fp32 NCHW [n,cin,h,w] (cin <= 32), w fp32 OIHW, y NHWC of out_dtype,
  * with scale/shift/act/stats as above.  softmax_in != 0 applies a softmax

@@ -63,6 +63,10 @@ SIGNATURES = {
     "rtsds_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_pack_conv_weights_batch": (_I, [_P, _I, _I, _P]),
     "rtsds_unpack_conv_wgrads_batch": (_I, [_P, _I, _P]),
+    "rtsds_tapn_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "rtsds_tapn_weight_grad": (_I, [_P, _I, _I, _I, _P, _P]),
+    "rtsds_tapn_gather": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "rtsds_tapn_scatter": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "rtsds_conv2d_tc_dgrad_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_tc_dgrad": (_I, [_CD, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "rtsds_conv2d_tc_wgrad": (_I, [_CD, _P, _P, _P, _P]),

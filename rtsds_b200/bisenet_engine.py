@@ -93,6 +93,19 @@ class BiSeNetPlan:
             need = int(ops.lib().rtsds_conv2d_tc_workspace_bytes(d))
             self._ws_bytes = max(self._ws_bytes, need)
 
+    def note_ws(self, b):
+        self._ws_bytes = max(self._ws_bytes, b)
+
+    def _conv_tapn(self, conv, bnmod, x, xshape, y, y_ld, act, in_ld):
+        """Skinny-output k x k conv + folded BatchNorm + activation in the taps-as-N form (rtsds_b200/tapn.py); y fp32."""
+        from .tapn import TapNConv
+
+        cout = conv.weight.shape[0]
+        tn = TapNConv(self, conv, x, xshape, in_ld, train=False)
+        bn = _BN(self, bnmod, cout)
+        self.pack_steps.append(lambda: ops.bn_fold(bnmod, bn.scale, bn.shift, conv.bias))
+        self.steps.append(lambda: tn.forward(bn.scale, bn.shift, act, None, y, y_ld))
+
     def _conv(self, conv, bnmod, x, xshape, y, out_ld, act, *, in_ld=None, residual=None, res_ld=0, out_dtype=None,
               x_off=0, y_off=0, bias=None, steps=None):
         """Append conv (+BN/bias, +residual, +act) reading NHWC x -> NHWC y.  Returns (oh, ow)."""
@@ -222,7 +235,12 @@ class BiSeNetPlan:
         self.pooled_f = self.buf(n, nc, dtype=f32)
         self.attn = self.buf(n, nc, dtype=f32)
         self.z = self.buf(n, h8, w8, 32, dtype=f32)
-        self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, out_dtype=F32)
+        from . import tapn
+
+        if not self.train and tapn.applicable(ffm.convblock.conv1):
+            self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, 1024)
+        else:
+            self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, out_dtype=F32)
         feat, pooled_f, z, attn = self.feat, self.pooled_f, self.z, self.attn
         final = m.conv if m.with_interpolation else None
         self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))

@@ -69,6 +69,12 @@ class _ConvBN:
             self.raw = y                       # bias-only conv writes straight to y
             self.d.out_ld = y.ld
             self.d.out_dtype = y.dtype
+        if getattr(self, "_no_std_weights", False):      # taps-as-N subclass: its own weight forms (rtsds_b200/tapn.py)
+            self.wpk = self.wdg = self.dw = None
+            self.ck = ops.dgrad_ck(self.cout, self.tc)
+            self.dyld = max(self.ck, cpad8)
+            plan.note_scratch(n * self.oh * self.ow * self.dyld, 0)
+            return
         self.wpk = plan.buf(ops.cout_pad(self.cout), k * k, cin)
         batched = hasattr(plan, "pack_jobs")        # plans that batch weight packing / gradient unpacking into few launches
         if batched:
@@ -154,23 +160,65 @@ class _ConvBN:
         else:
             d_raw = dy                                   # bias-only conv: dy already is the conv-output gradient
             assert dy.ld >= self.dyld and dy.dtype == dt
-        dd = self.bwd_desc()
-        dd.out_ld = d_raw.ld
         gwt = gw.get(self.conv.weight)
         if gwt is not None:
-            if self.dw is not None:
-                ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, self.dw, self.tc)
-                # converted in one launch per bucket; ASSIGNED: the flat gradient buffer of this backward pass is fresh and
-                # every conv weight receives exactly one contribution per pass (autograd accumulates across passes)
-                p.pending_unpack.append((self.dw, gwt, False))
-            else:
-                dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
-                ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)
-                ops.unpack_conv_wgrad(dwp, gwt, True)
+            self._weight_grad(d_raw, gwt)
         if dx is not None:
-            dd.in_ld = dx.ld
-            dd.res_ld = dx.ld
-            ops.conv2d_dgrad(dd, d_raw.ptr, self.wdg, dx.ptr, dx.dtype, self.tc, dx.ptr if dx_accumulate else None, p.ws)
+            self._input_grad(d_raw, dx, dx_accumulate)
+
+    def _weight_grad(self, d_raw: _Buf, gwt):
+        p = self.plan
+        dd = self.bwd_desc()
+        dd.out_ld = d_raw.ld
+        if self.dw is not None:
+            ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, self.dw, self.tc)
+            # converted in one launch per bucket; ASSIGNED: the flat gradient buffer of this backward pass is fresh and
+            # every conv weight receives exactly one contribution per pass (autograd accumulates across passes)
+            p.pending_unpack.append((self.dw, gwt, False))
+        else:
+            dwp = p.dw_view(self.cout * self.k * self.k * self.cin)     # kept zero: unpack clears what it reads
+            ops.conv2d_wgrad(dd, self.x.ptr, d_raw.ptr, dwp, self.tc)
+            ops.unpack_conv_wgrad(dwp, gwt, True)
+
+    def _input_grad(self, d_raw: _Buf, dx: _Buf, dx_accumulate):
+        dd = self.bwd_desc()
+        dd.out_ld = d_raw.ld
+        dd.in_ld = dx.ld
+        dd.res_ld = dx.ld
+        ops.conv2d_dgrad(dd, d_raw.ptr, self.wdg, dx.ptr, dx.dtype, self.tc, dx.ptr if dx_accumulate else None, self.plan.ws)
+
+
+class _TapNConvBN(_ConvBN):
+    """_ConvBN whose convolution runs in the taps-as-N form (rtsds_b200/tapn.py): skinny-output k x k convs."""
+
+    def __init__(self, plan, conv, bn, x: _Buf, xshape, y: _Buf, relu, residual=None, raw_dtype=None, need_dx=True):
+        from .tapn import TapNConv
+
+        assert bn is not None and raw_dtype == F32 and residual is None
+        self._no_std_weights = True
+        super().__init__(plan, conv, bn, x, xshape, y, relu, residual, raw_dtype, need_dx)
+        self.tapn = TapNConv(plan, conv, x.ptr, xshape, x.ld, train=True)
+
+    def _launch(self, d, scale, shift, res, stats, yptr):
+        assert scale is None and shift is None and res is None
+        self.tapn.forward(None, None, ACT_NONE, stats, yptr, self.raw.ld)
+
+    def backward(self, dy, gw, dx=None, dx_accumulate=False, g_out=None):
+        self._scattered = False
+        super().backward(dy, gw, dx, dx_accumulate, g_out)
+
+    def _scatter(self, d_raw):
+        if not self._scattered:
+            self.tapn.scatter(d_raw.ptr, d_raw.ld, d_raw.dtype)
+            self._scattered = True
+
+    def _weight_grad(self, d_raw, gwt):
+        self._scatter(d_raw)
+        self.tapn.weight_grad(gwt)
+
+    def _input_grad(self, d_raw, dx, dx_accumulate):
+        self._scatter(d_raw)
+        self.tapn.input_grad(dx.ptr, dx.ld, dx.dtype, dx_accumulate)
 
 
 class _Stem:
@@ -322,7 +370,10 @@ class BiSeNetTrainPlan:
         self.sup2 = _ConvBN(self, m.supervision2, None, _Buf(self.cat, ld=1024, off=256 + c3), (n, h8, w8, c4), z2b, False)
         ffm = m.feature_fusion_module
         self.feat = _Buf(self.zeros(n, h8, w8, 32, dtype=f32))
-        self.ffm = _ConvBN(self, ffm.convblock.conv1, ffm.convblock.bn, _Buf(self.cat, ld=1024), (n, h8, w8, 1024), self.feat, True,
+        from . import tapn
+
+        ffm_cls = _TapNConvBN if tapn.applicable(ffm.convblock.conv1) else _ConvBN
+        self.ffm = ffm_cls(self, ffm.convblock.conv1, ffm.convblock.bn, _Buf(self.cat, ld=1024), (n, h8, w8, 1024), self.feat, True,
                            raw_dtype=F32)
         self.pooled_f = self.buf(n, nc, dtype=f32)
         self.attn = self.buf(n, nc, dtype=f32)

@@ -6,6 +6,7 @@ tighter when the output is kept in fp32.  SIMT fp32 path: 1e-4.
 """
 import pytest
 import torch
+import torch.nn.functional as F
 
 from rtsds_b200 import ops
 from rtsds_b200.ops import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32
@@ -247,3 +248,72 @@ def test_conv_simt_backward_odd_channels(cuda):
     dx, dw = _run_bwd("simt", x, wt, dy, 1, 0, 1, F32)
     rdx, rdw = _bwd_ref(x, wt, dy, 1, 0, 1, False)
     assert rel_err(dx, rdx) < 1e-5 and rel_err(dw, rdw) < 1e-4
+
+
+# ----------------------------------------------------------------------------- taps-as-N form of skinny-output convs
+class _MiniPlan:
+    def __init__(self, dtype):
+        self.dt = dtype
+        self.use_tc = dtype == BF16
+        self.pack_steps, self._keep, self._ws = [], [], 0
+        self.ws = None
+
+    def buf(self, *shape, dtype=None):
+        t = torch.empty(shape, dtype=ops.torch_dtype(self.dt) if dtype is None else dtype, device="cuda")
+        self._keep.append(t)
+        return t
+
+    def zeros(self, *shape, dtype=None):
+        t = torch.zeros(shape, dtype=ops.torch_dtype(self.dt) if dtype is None else dtype, device="cuda")
+        self._keep.append(t)
+        return t
+
+    def note_ws(self, b):
+        self._ws = max(self._ws, b)
+
+
+@pytest.mark.parametrize("dtype,tol", [(F32, 1e-4), (BF16, 2e-2)])
+@pytest.mark.parametrize("n,h,w,cin,c,k,dil", [(2, 8, 12, 256, 19, 3, 1), (1, 23, 40, 1024, 19, 3, 1), (1, 17, 9, 512, 7, 3, 2)])
+def test_tapn_conv_forward_backward(cuda, dtype, tol, n, h, w, cin, c, k, dil):
+    """csrc/tapn.cu + rtsds_b200/tapn.py against F.conv2d autograd: output, BN statistics, input and weight gradients."""
+    from rtsds_b200.tapn import TapNConv
+
+    g = torch.Generator().manual_seed(cin + h)
+    pad = dil * (k // 2)
+    conv = torch.nn.Conv2d(cin, c, k, 1, pad, dil, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(c, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+    conv = conv.cuda()
+    x = torch.randn(n, cin, h, w, generator=g)
+    dy = torch.randn(n, c, h, w, generator=g)
+    rnd = bf16_round if dtype == BF16 else (lambda t: t)
+    xr = rnd(x).requires_grad_(True)
+    wr = rnd(conv.weight.detach().cpu()).requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, pad, dil)
+    yr.backward(rnd(dy))
+    plan = _MiniPlan(dtype)
+    tdt = ops.torch_dtype(dtype)
+    xg = nhwc(x, tdt)
+    tn = TapNConv(plan, conv, xg, (n, h, w, cin), cin, train=True)
+    plan.ws = torch.empty(max(plan._ws, 16), dtype=torch.uint8, device="cuda")
+    for s in plan.pack_steps:
+        s()
+    y = torch.zeros(n, h, w, 32, device="cuda")
+    stats = torch.zeros(2 * c, device="cuda")
+    tn.forward(None, None, ACT_NONE, stats, y, 32)
+    assert rel_err(nchw(y[..., :c]), yr.detach()) < tol
+    assert rel_err(stats[:c].cpu(), yr.detach().sum((0, 2, 3))) < max(tol, 1e-3)
+    assert rel_err(stats[c:].cpu(), (yr.detach() ** 2).sum((0, 2, 3))) < max(tol, 1e-3)
+    dyg = torch.zeros(n, h, w, 64, dtype=tdt, device="cuda")
+    dyg[..., :c] = nhwc(dy, tdt)
+    tn.scatter(dyg, 64, dtype)
+    gw = torch.zeros(c, cin, k, k, device="cuda")
+    tn.weight_grad(gw)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=tdt, device="cuda")
+    tn.input_grad(dx, cin, dtype, False)
+    assert rel_err(gw.cpu(), wr.grad) < tol, rel_err(gw.cpu(), wr.grad)
+    assert rel_err(nchw(dx), xr.grad) < tol, rel_err(nchw(dx), xr.grad)
+    tn.input_grad(dx, cin, dtype, True)                       # accumulate form: dx += dL/dx
+    assert rel_err(nchw(dx), 2 * xr.grad) < 2 * tol
+    tn.weight_grad(gw)                                        # the wgrad scratch was left clean
+    assert rel_err(gw.cpu(), 2 * wr.grad) < 2 * tol
