@@ -70,6 +70,10 @@ class BiSeNetPlan:
         self._param_version = None
         self.generation = 0
         self.graph = None
+        self.side = None
+        self.ws_side = None
+        self._side_branch = False
+        self.n_sp_steps = self.n_join = 0
         self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -125,10 +129,11 @@ class BiSeNetPlan:
         self._need_ws(d)
         use_tc = self.use_tc
         n_pix = n * d.oh * d.ow
+        side = self._side_branch          # convs of the side-stream branch get their own split-K workspace
 
         def launch(desc, scale, shift, res, stats):
             if use_tc:
-                ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats, self.ws)
+                ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats, self.ws_side if side else self.ws)
             else:
                 ops.conv2d_simt(desc, xp, wpk, yp, scale, shift, res, stats)
 
@@ -175,8 +180,13 @@ class BiSeNetPlan:
         fused_stems = self.use_tc and not self.train
         if not fused_stems:
             self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
+        self._side_branch = True
         self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
         self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, 1024, ACT_RELU)
+        self._side_branch = False
+        # the spatial path is independent of the context path until the concat buffer is consumed: its two convs run on a
+        # side stream (a parallel branch of the CUDA graph) and fill SMs the small layer-3/4 grids leave idle
+        self.n_sp_steps = len(self.steps)
 
         # ---- context path: ResNet-18 (build_contextpath.py:18-29) ----
         cp = m.context_path
@@ -221,6 +231,7 @@ class BiSeNetPlan:
         self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, 1024, 256, dt))
         self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, 1024, 256 + c3, dt))
         self.f3, self.s3, self.f4, self.s4 = f3, s3, f4, s4
+        self.n_join = len(self.steps)        # everything from here on reads the spatial-path slot of the concat buffer
 
         # ---- auxiliary heads, train only (reference :155-159) ----
         if self.train:
@@ -249,6 +260,7 @@ class BiSeNetPlan:
         self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
         if self._ws_bytes:
             self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+            self.ws_side = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
 
     def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp):
         """Both stems in one tensor-core kernel (csrc/stem_tc.cu); eval mode: BN folded + ReLU."""
@@ -319,7 +331,21 @@ class BiSeNetPlan:
             s(x)
 
     def run_mid(self):
-        for s in self.steps:
+        if ops._lib.dry_run() or self.n_sp_steps == 0:
+            for s in self.steps:
+                s()
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(self.device)
+        self.side.wait_stream(main)                           # fork
+        with torch.cuda.stream(self.side):
+            for s in self.steps[:self.n_sp_steps]:
+                s()
+        for s in self.steps[self.n_sp_steps:self.n_join]:
+            s()
+        main.wait_stream(self.side)                           # join
+        for s in self.steps[self.n_join:]:
             s()
 
     def forward_lowres(self, x, use_graph: bool):
