@@ -223,6 +223,23 @@ int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_
                              const void* d_raw_sp, float* dw_ws, float* g7_oihw, float* g3_oihw,
                              rtsds_stream_t s);
 
+/* Space-to-depth stems (tensor-core path): a k x k stride-2 conv on the 3-channel image (7x7 p3 or 3x3 p1) is a 4-tap
+ * implicit GEMM over P, the padded space-to-depth image:
+ *   P[n, i, j, (py*2+px)*3 + c] = x[n, c, 2(i-2)+py, 2(j-2)+px]   bf16 [n, oh+3, ow+3, 16], oh = (h-1)/2+1, zero outside
+ * (one window row = 4 pixels x 16 channels = 64 contiguous bf16; windows overlap with a pixel pitch of 16 elements,
+ * which the TMA tensor map expresses directly).  stem_s2d_weight turns OIHW [cout,3,k,k] into the virtual OIHW
+ * [cout,64,4,1] weight of that GEMM (pack it with rtsds_pack_conv_weight); stem_s2d_weight_grad ACCUMULATES the
+ * gradient of the virtual weight into the [cout,3,k,k] gradient.  conv_fwd has the epilogue of rtsds_conv2d_tc_fwd
+ * (scale/shift/act/stats); conv_wgrad accumulates dw_packed [cout][4][64] fp32 like rtsds_conv2d_tc_wgrad. */
+int rtsds_stem_s2d_pack(const float* x, int n, int h, int w, void* P, rtsds_stream_t s);
+int rtsds_stem_s2d_weight(const float* w_oihw, int cout, int k, int pad, float* w2_oihw, rtsds_stream_t s);
+int rtsds_stem_s2d_weight_grad(const float* g2_oihw, int cout, int k, int pad, float* grad_oihw, rtsds_stream_t s);
+int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, const void* w_packed, int cout, const float* scale,
+                            const float* shift, int act, float* stats, void* y, int out_ld, int out_dtype,
+                            rtsds_stream_t s);
+int rtsds_stem_s2d_conv_wgrad(const void* P, int n, int oh, int ow, const void* dy, int dy_ld, int cout,
+                              float* dw_packed, rtsds_stream_t s);
+
 /* nn.MaxPool2d(3, 2, 1[, ceil_mode]) on NHWC. */
 int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype,
                            int ceil_mode, void* y, rtsds_stream_t s);

@@ -857,6 +857,55 @@ static int launch_wgrad(const WgMaps& maps, const WgParams& p, dim3 grid, cudaSt
 
 // x: NHWC bf16 (pitch d->in_ld), dy: NHWC bf16 (pitch d->out_ld, a multiple of 8; channels >= cout read as zero
 // via TMA bounds), dw_packed: fp32 [cout][kh*kw][cin], ACCUMULATED into (caller zeroes it).
+// x views / taps come from a TapProblem (a regular conv or the sliding-window stem view); dy: NHWC bf16 [n,oh,ow,ldy].
+static int wgrad_run(const TapProblem& t, int cin, int cout, const void* dy, long long ldy, float* dw_packed, cudaStream_t st) {
+    WgMaps maps;
+    WgParams p;
+    memset(&maps, 0, sizeof(maps));
+    memset(&p, 0, sizeof(p));
+    pick_tile(t.oh, t.ow, &p.tile_w, &p.tile_h);
+    p.n_img = t.n_img; p.oh = t.oh; p.ow = t.ow;
+    p.tiles_w = static_cast<int>(cdiv(t.ow, p.tile_w));
+    p.tiles_h = static_cast<int>(cdiv(t.oh, p.tile_h));
+    p.cout = cout; p.cin = cin; p.n_taps = t.n_taps;
+    const int block_n = cin >= 256 ? 256 : (cin >= 128 ? 128 : 64);
+    p.ci_tiles = static_cast<int>(cdiv(cin, block_n));
+    const long long tiles_total = static_cast<long long>(t.n_img) * p.tiles_w * p.tiles_h;
+    RTSDS_REQUIRE(tiles_total < (1LL << 30), "conv2d_tc_wgrad: too many tiles");
+    p.tiles_total = static_cast<int>(tiles_total);
+    const int co_tiles = static_cast<int>(cdiv(cout, TC_BLOCK_M));
+    const long long base = static_cast<long long>(t.n_taps) * p.ci_tiles * co_tiles;
+    // one CTA per SM is resident (shared memory): aim at whole waves, never a ragged extra one
+    long long splits = (base >= num_sms() / 2 ? 1LL : 2LL) * num_sms() / base;
+    if (splits > tiles_total) splits = tiles_total;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = static_cast<int>(cdiv(tiles_total, splits));
+    splits = cdiv(tiles_total, p.tiles_per_split);
+    for (int i = 0; i < t.n_taps; ++i) { p.tap_dh[i] = t.dh[i]; p.tap_dw[i] = t.dw[i]; p.tap_map[i] = t.map[i]; }
+    p.dw = dw_packed;
+    // dy view: channel extent = cout (TMA zero-fills channels >= cout), pitch ldy
+    int rc = make_act_map(&maps.a, dy, cout, t.ow, t.oh, t.n_img, ldy, static_cast<long long>(t.ow) * ldy,
+                          static_cast<long long>(t.oh) * t.ow * ldy, p.tile_w, p.tile_h);
+    if (rc != RTSDS_OK) return rc;
+    int first = -1;
+    for (int i = 0; i < 4; ++i) {
+        if (!t.view[i].used) continue;
+        rc = make_act_map(&maps.b[i], t.view[i].base, cin, t.view[i].wd, t.view[i].hd, t.n_img, t.view[i].sw, t.view[i].sh,
+                          t.view[i].sn, p.tile_w, p.tile_h);
+        if (rc != RTSDS_OK) return rc;
+        if (first < 0) first = i;
+    }
+    for (int i = 0; i < 4; ++i)
+        if (!t.view[i].used) maps.b[i] = maps.b[first];
+    int stages = block_n == 256 ? 2 : (block_n == 128 ? 3 : 4);
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
+    p.stages = stages;
+    dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps * p.ci_tiles), static_cast<unsigned>(co_tiles));
+    if (block_n == 256) return launch_wgrad<256>(maps, p, grid, st);
+    if (block_n == 128) return launch_wgrad<128>(maps, p, grid, st);
+    return launch_wgrad<64>(maps, p, grid, st);
+}
+
 extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy, float* dw_packed,
                                      rtsds_stream_t s) {
     RTSDS_REQUIRE(d && x && dy && dw_packed, "conv2d_tc_wgrad: NULL argument");
@@ -868,50 +917,52 @@ extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, cons
     TapProblem t;
     rc = fwd_problem(d, x, nullptr, TC_BLOCK_K, 2, &t);
     if (rc != RTSDS_OK) return rc;
-    WgMaps maps;
-    WgParams p;
-    memset(&maps, 0, sizeof(maps));
-    memset(&p, 0, sizeof(p));
-    pick_tile(d->oh, d->ow, &p.tile_w, &p.tile_h);
-    p.n_img = d->n; p.oh = d->oh; p.ow = d->ow;
-    p.tiles_w = static_cast<int>(cdiv(d->ow, p.tile_w));
-    p.tiles_h = static_cast<int>(cdiv(d->oh, p.tile_h));
-    p.cout = d->cout; p.cin = d->cin; p.n_taps = t.n_taps;
-    const int block_n = d->cin >= 256 ? 256 : (d->cin >= 128 ? 128 : 64);
-    p.ci_tiles = static_cast<int>(cdiv(d->cin, block_n));
-    const long long tiles_total = static_cast<long long>(d->n) * p.tiles_w * p.tiles_h;
-    RTSDS_REQUIRE(tiles_total < (1LL << 30), "conv2d_tc_wgrad: too many tiles");
-    p.tiles_total = static_cast<int>(tiles_total);
-    const int co_tiles = static_cast<int>(cdiv(d->cout, TC_BLOCK_M));
-    const long long base = static_cast<long long>(t.n_taps) * p.ci_tiles * co_tiles;
-    // one CTA per SM is resident (shared memory): aim at whole waves, never a ragged extra one
-    long long splits = (base >= num_sms() / 2 ? 1LL : 2LL) * num_sms() / base;
-    if (splits > tiles_total) splits = tiles_total;
-    if (splits < 1) splits = 1;
-    p.tiles_per_split = static_cast<int>(cdiv(tiles_total, splits));
-    splits = cdiv(tiles_total, p.tiles_per_split);
-    for (int i = 0; i < t.n_taps; ++i) { p.tap_dh[i] = t.dh[i]; p.tap_dw[i] = t.dw[i]; p.tap_map[i] = t.map[i]; }
-    p.dw = dw_packed;
-    const long long ldy = d->out_ld;
-    // dy view: channel extent = cout (TMA zero-fills channels >= cout), pitch out_ld
-    rc = make_act_map(&maps.a, dy, d->cout, d->ow, d->oh, d->n, ldy, static_cast<long long>(d->ow) * ldy,
-                      static_cast<long long>(d->oh) * d->ow * ldy, p.tile_w, p.tile_h);
+    return wgrad_run(t, d->cin, d->cout, dy, d->out_ld, dw_packed, as_stream(s));
+}
+
+// =====================================================================================
+// Space-to-depth stems.  A k x k stride-2 conv on the 3-channel image (7x7 p3: torchvision resnet conv1 via
+// models/bisenet/build_contextpath.py:19 and deeplabv2.py:72; 3x3 p1: build_bisenet.py:24) is a 4x4 stride-1 conv over
+// the space-to-depth image (12 channels, stored padded to 16).  In the padded NHWC tensor
+//     P[n, i, j, (py*2+px)*3 + c] = x[n, c, 2(i-2)+py, 2(j-2)+px]        [n, OH+3, OW+3, 16] bf16, zero outside
+// the 4 pixels x 16 channels of one window ROW are 64 contiguous bf16 = one 128-byte UMMA K row, and windows of
+// neighbouring output pixels overlap with a pixel pitch of 16 elements.  A TMA tensor map with that (overlapping)
+// pixel stride makes the stem an ordinary 4-tap implicit GEMM (K = 4 x 64) for the kernels above — forward and
+// weight gradient — instead of a thread-gathered im2col.
+// =====================================================================================
+static void stem_s2d_problem(const void* P, int n, int oh, int ow, TapProblem* t) {
+    memset(t, 0, sizeof(*t));
+    const long long rowp = static_cast<long long>(ow + 3) * 16;
+    t->view[0] = TapView{P, ow, oh + 3, 16, rowp, rowp * (oh + 3), true};
+    t->ck = 64; t->c_extent = 64; t->n_img = n; t->oh = oh; t->ow = ow;
+    t->n_taps = 4;
+    for (int r = 0; r < 4; ++r) { t->dh[r] = static_cast<signed char>(r); t->dw[r] = 0; t->map[r] = 0; t->kb[r] = r; }
+    t->w_ktot = 256;
+}
+
+extern "C" int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, const void* w_packed, int cout,
+                                       const float* scale, const float* shift, int act, float* stats, void* y,
+                                       int out_ld, int out_dtype, rtsds_stream_t s) {
+    RTSDS_REQUIRE(P && w_packed && y && n > 0 && oh > 0 && ow > 0 && cout > 0, "stem_s2d_conv_fwd: bad argument");
+    RTSDS_REQUIRE(out_dtype == RTSDS_BF16 || out_dtype == RTSDS_F32, "stem_s2d_conv_fwd: bad out_dtype");
+    RTSDS_REQUIRE(out_ld >= cout && out_ld % (out_dtype == RTSDS_BF16 ? 8 : 4) == 0, "stem_s2d_conv_fwd: out_ld");
+    int rc = rtsds_check_device();
     if (rc != RTSDS_OK) return rc;
-    int first = -1;
-    for (int i = 0; i < 4; ++i) {
-        if (!t.view[i].used) continue;
-        rc = make_act_map(&maps.b[i], t.view[i].base, d->cin, t.view[i].wd, t.view[i].hd, d->n, t.view[i].sw, t.view[i].sh,
-                          t.view[i].sn, p.tile_w, p.tile_h);
-        if (rc != RTSDS_OK) return rc;
-        if (first < 0) first = i;
-    }
-    for (int i = 0; i < 4; ++i)
-        if (!t.view[i].used) maps.b[i] = maps.b[first];
-    int stages = block_n == 256 ? 2 : (block_n == 128 ? 3 : 4);
-    if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
-    p.stages = stages;
-    dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps * p.ci_tiles), static_cast<unsigned>(co_tiles));
-    if (block_n == 256) return launch_wgrad<256>(maps, p, grid, as_stream(s));
-    if (block_n == 128) return launch_wgrad<128>(maps, p, grid, as_stream(s));
-    return launch_wgrad<64>(maps, p, grid, as_stream(s));
+    TapProblem t;
+    stem_s2d_problem(P, n, oh, ow, &t);
+    t.w = w_packed; t.cout = cout;
+    t.out_sw = out_ld; t.out_sh = static_cast<long long>(ow) * out_ld; t.out_sn = t.out_sh * oh;
+    t.scale = scale; t.shift = shift; t.stats = stats; t.y = y;
+    t.out_dtype = out_dtype; t.act = act; t.split_req = 1;
+    return tp_run(t, nullptr, 0, as_stream(s));
+}
+
+extern "C" int rtsds_stem_s2d_conv_wgrad(const void* P, int n, int oh, int ow, const void* dy, int dy_ld, int cout,
+                                         float* dw_packed, rtsds_stream_t s) {
+    RTSDS_REQUIRE(P && dy && dw_packed && n > 0 && oh > 0 && ow > 0 && cout > 0 && dy_ld >= cout && dy_ld % 8 == 0, "stem_s2d_conv_wgrad: bad argument");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    TapProblem t;
+    stem_s2d_problem(P, n, oh, ow, &t);
+    return wgrad_run(t, 64, cout, dy, dy_ld, dw_packed, as_stream(s));
 }

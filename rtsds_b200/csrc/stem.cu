@@ -303,3 +303,91 @@ extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c,
     count_launch();
     return check_launch("maxpool_kernel");
 }
+
+
+// ---- space-to-depth stems (see conv_tc.cu: rtsds_stem_s2d_conv_*) -------------------------------------------------
+namespace rtsds {
+
+// P[n, i, j, (py*2+px)*3 + c] = x[n, c, 2(i-2)+py, 2(j-2)+px], channels 12..15 = 0; one thread per (n, i, j).
+__global__ void __launch_bounds__(256)
+stem_s2d_pack_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, __nv_bfloat16* __restrict__ P) {
+    const long long total = static_cast<long long>(n) * hp * wp;
+    const long long plane = static_cast<long long>(h) * w;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(idx % wp);
+        const long long r = idx / wp;
+        const int i = static_cast<int>(r % hp);
+        const int img = static_cast<int>(r / hp);
+        const int y0 = 2 * (i - 2), x0 = 2 * (j - 2);
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        const float* xi = x + static_cast<long long>(img) * 3 * plane;
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            const int yy = y0 + py;
+            if (yy < 0 || yy >= h) continue;
+            const bool a = x0 >= 0 && x0 < w, b = x0 + 1 >= 0 && x0 + 1 < w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* row = xi + c * plane + static_cast<long long>(yy) * w;
+                if (a) v[(py * 2 + 0) * 3 + c] = __ldg(row + x0);
+                if (b) v[(py * 2 + 1) * 3 + c] = __ldg(row + x0 + 1);
+            }
+        }
+        uint4 lo, hi;
+        lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+        hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = 0u; hi.w = 0u;
+        uint4* dst = reinterpret_cast<uint4*>(P + idx * 16);
+        dst[0] = lo; dst[1] = hi;
+    }
+}
+
+// w[co][c][k][k] (k = 7, pad 3 or k = 3, pad 1; stride 2) -> virtual OIHW w2[co][64][4][1]:
+//   w2[co, q*16 + (py*2+px)*3 + c, r] = w[co, c, ky, kx],  ky = 2r+py-1-(3-pad), kx = 2q+px-1-(3-pad)   (0 outside)
+__global__ void stem_s2d_weight_kernel(const float* __restrict__ w, int cout, int k, int pad, float* __restrict__ w2, int grad,
+                                       float* __restrict__ gw) {
+    const int total = cout * 64 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i & 3, ci = (i >> 2) & 63, co = i >> 8;
+        const int q = ci >> 4, e = ci & 15;
+        if (e >= 12) { if (!grad) w2[i] = 0.f; continue; }
+        const int par = e / 3, c = e - par * 3, py = par >> 1, px = par & 1;
+        const int ky = 2 * r + py - 1 - (3 - pad), kx = 2 * q + px - 1 - (3 - pad);
+        const bool ok = ky >= 0 && ky < k && kx >= 0 && kx < k;
+        if (grad) {
+            if (ok) gw[((co * 3 + c) * k + ky) * k + kx] += w2[i];        // the map is one-to-one: no atomics needed
+        } else {
+            w2[i] = ok ? w[((co * 3 + c) * k + ky) * k + kx] : 0.f;
+        }
+    }
+}
+
+}  // namespace rtsds
+
+extern "C" int rtsds_stem_s2d_pack(const float* x, int n, int h, int w, void* P, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && P && n > 0 && h >= 2 && w >= 2 && (reinterpret_cast<uintptr_t>(P) & 15) == 0, "stem_s2d_pack: bad argument");
+    const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+    const long long total = static_cast<long long>(n) * (oh + 3) * (ow + 3);
+    long long g = rtsds::cdiv(total, 256);
+    const long long cap = 16LL * rtsds::num_sms();
+    if (g > cap) g = cap;
+    rtsds::stem_s2d_pack_kernel<<<static_cast<int>(g), 256, 0, rtsds::as_stream(s)>>>(x, n, h, w, oh + 3, ow + 3, reinterpret_cast<__nv_bfloat16*>(P));
+    rtsds::count_launch();
+    return rtsds::check_launch("stem_s2d_pack_kernel");
+}
+
+extern "C" int rtsds_stem_s2d_weight(const float* w_oihw, int cout, int k, int pad, float* w2, rtsds_stream_t s) {
+    RTSDS_REQUIRE(w_oihw && w2 && cout > 0 && ((k == 7 && pad == 3) || (k == 3 && pad == 1)), "stem_s2d_weight: 7x7 p3 or 3x3 p1 only");
+    rtsds::stem_s2d_weight_kernel<<<static_cast<int>(rtsds::cdiv(cout * 256, 256)), 256, 0, rtsds::as_stream(s)>>>(w_oihw, cout, k, pad, w2, 0, nullptr);
+    rtsds::count_launch();
+    return rtsds::check_launch("stem_s2d_weight_kernel");
+}
+
+extern "C" int rtsds_stem_s2d_weight_grad(const float* g2, int cout, int k, int pad, float* grad_oihw, rtsds_stream_t s) {
+    RTSDS_REQUIRE(g2 && grad_oihw && cout > 0 && ((k == 7 && pad == 3) || (k == 3 && pad == 1)), "stem_s2d_weight_grad: 7x7 p3 or 3x3 p1 only");
+    rtsds::stem_s2d_weight_kernel<<<static_cast<int>(rtsds::cdiv(cout * 256, 256)), 256, 0, rtsds::as_stream(s)>>>(nullptr, cout, k, pad, const_cast<float*>(g2), 1, grad_oihw);
+    rtsds::count_launch();
+    return rtsds::check_launch("stem_s2d_weight_kernel");
+}

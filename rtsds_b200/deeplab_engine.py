@@ -21,7 +21,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .bisenet_train import _Buf, _ConvBN, _Stem
+from .bisenet_train import _Buf, _ConvBN, _s
 from .ops import ACT_NONE, ACT_RELU, BF16, F32, _p, check, lib
 
 DEEPLAB_GROUPS = (("conv1", "layer1"), ("bn1", "layer1"), ("layer1", "layer1"), ("layer2", "layer2"), ("layer3", "layer3"),
@@ -44,6 +44,7 @@ class _PlanBase:
         if self.nc > 32:
             raise ops._lib.RtsdsError("num_classes > 32 is not supported by the head kernels")
         self._keep, self.pack_steps = [], []
+        self.stem_P = None
         if train:
             self.pack_jobs, self.pending_unpack = [], []
         self._stats_total = 0
@@ -157,7 +158,16 @@ class DeepLabPlan(_PlanBase):
         stem = self.buf(n, h2, w2, 64)
         sscale, sshift = self.buf(64, dtype=torch.float32), self.buf(64, dtype=torch.float32)
         self.pack_steps.append(lambda: ops.bn_fold(m.bn1, sscale, sshift))
-        self.pre_steps.append(lambda x: ops.stem_conv(x, m.conv1.weight, stem, 7, 2, 3, sscale, sshift, ACT_RELU))
+        if self.use_tc:      # 7x7 s2 stem as a 4-tap implicit GEMM over the padded space-to-depth image
+            oh, ow, pshape = ops.stem_s2d_shape(n, self.h, self.w)
+            P = self.buf(*pshape, dtype=torch.bfloat16)
+            w2 = self.buf(64, 64, 4, 1, dtype=torch.float32)
+            wpk = self.buf(64, 4, 64, dtype=torch.bfloat16)
+            self.pack_steps.append(lambda: (ops.stem_s2d_weight(m.conv1.weight, w2), ops.pack_conv_weight(w2, BF16, wpk)))
+            self.pre_steps.append(lambda x: ops.stem_s2d_pack(x, P))
+            self.steps.append(lambda: ops.stem_s2d_conv_fwd(P, n, oh, ow, wpk, 64, stem, 64, BF16, sscale, sshift, ACT_RELU))
+        else:
+            self.pre_steps.append(lambda x: ops.stem_conv(x, m.conv1.weight, stem, 7, 2, 3, sscale, sshift, ACT_RELU))
         x = self.buf(n, ph, pw, 64)
         self.steps.append(lambda x=x: ops.maxpool3x3s2(stem, x, True))
         shape = (n, ph, pw, 64)
@@ -218,6 +228,74 @@ class DeepLabPlan(_PlanBase):
 
 
 # ======================================================================================= train
+class _StemS2D:
+    """k x k stride-2 conv on the NCHW fp32 image + BatchNorm + ReLU (no input gradient).  Tensor-core mode: a 4-tap
+    implicit GEMM over the plan's padded space-to-depth image `plan.stem_P` (csrc/conv_tc.cu: rtsds_stem_s2d_*), shared by
+    every stem of the plan; check mode (fp32): the direct CUDA-core kernels."""
+
+    def __init__(self, plan, conv, bn, k, pad, n, h, w):
+        self.plan, self.conv, self.bn, self.k, self.pad, self.n = plan, conv, bn, k, pad, n
+        self.oh, self.ow = ops.conv_out_size(h, k, 2, pad), ops.conv_out_size(w, k, 2, pad)
+        self.n_pix = n * self.oh * self.ow
+        self.raw = _Buf(plan.buf(n, self.oh, self.ow, 64))
+        self.y = _Buf(plan.buf(n, self.oh, self.ow, 64))
+        self.scale, self.shift = plan.buf(64, dtype=torch.float32), plan.buf(64, dtype=torch.float32)
+        self.save_mean, self.save_invstd = plan.buf(64, dtype=torch.float32), plan.buf(64, dtype=torch.float32)
+        self.stats = plan.alloc_stats(64)
+        self.sums = plan.buf(128, dtype=torch.float32)
+        plan.note_scratch(self.n_pix * 64, 0)
+        self.s2d = plan.use_tc
+        if self.s2d:
+            oh, ow, pshape = ops.stem_s2d_shape(n, h, w)
+            assert (oh, ow) == (self.oh, self.ow)
+            if getattr(plan, "stem_P", None) is None:
+                plan.stem_P = plan.buf(*pshape, dtype=torch.bfloat16)
+            f32 = torch.float32
+            self.w2 = plan.buf(64, 64, 4, 1, dtype=f32)
+            self.g2 = plan.buf(64, 64, 4, 1, dtype=f32)
+            self.wpk = plan.buf(64, 4, 64, dtype=torch.bfloat16)
+            self.dw = plan.zeros(64 * 4 * 64, dtype=f32)          # kept zero: unpack clears what it reads
+            plan.pack_steps.append(self._pack)
+
+    def _pack(self):
+        ops.stem_s2d_weight(self.conv.weight, self.w2)
+        ops.pack_conv_weight(self.w2, BF16, self.wpk)
+
+    def forward(self, x):
+        """plan.stem_P must hold the space-to-depth form of x in tensor-core mode (BiSeNetTrainPlan.forward packs it once)."""
+        p = self.plan
+        st = p.stats_view(self.stats, 64)
+        if self.s2d:
+            ops.stem_s2d_conv_fwd(p.stem_P, self.n, self.oh, self.ow, self.wpk, 64, self.raw.t, 64, BF16, stats=st)
+        else:
+            ops.stem_conv(x, self.conv.weight, self.raw.t, self.k, 2, self.pad, stats=st)
+        ops.bn_finalize(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd)
+        ops.scale_shift_act(self.raw.t, self.y.t, self.n_pix, 64, self.scale, self.shift, None, ACT_RELU)
+
+    def backward(self, x, dy: _Buf, gw):
+        p = self.plan
+        s = _s()
+        d_raw = p.d_raw_view(64)
+        check(lib().rtsds_bn_bwd_reduce_rawmask(dy.ptr, dy.ld, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
+                                                _p(self.scale), _p(self.shift), self.n_pix, 64, dy.dtype, _p(self.sums), s),
+              "bn_bwd_reduce_rawmask")
+        check(lib().rtsds_bn_bwd_apply_rawmask(dy.ptr, dy.ld, self.raw.ptr, 64, _p(self.save_mean), _p(self.save_invstd),
+                                               _p(self.bn.weight.detach()), _p(self.sums), _p(self.scale), _p(self.shift),
+                                               self.n_pix, 64, dy.dtype, d_raw.ptr, 64, p.dt, None, 0,
+                                               _p(gw.get(self.bn.weight)), _p(gw.get(self.bn.bias)), s), "bn_bwd_apply_rawmask")
+        gwt = gw.get(self.conv.weight)
+        if gwt is None:
+            return
+        if self.s2d:
+            ops.stem_s2d_conv_wgrad(p.stem_P, self.n, self.oh, self.ow, d_raw.ptr, 64, 64, self.dw)
+            ops.unpack_conv_wgrad(self.dw, self.g2, False)
+            ops.stem_s2d_weight_grad(self.g2, gwt)
+        else:
+            n, cin, h, w = x.shape
+            check(lib().rtsds_stem_conv_wgrad(_p(x), d_raw.ptr, p.dt, n, cin, h, w, 64, self.k, 2, self.pad, _p(gwt), s),
+                  "stem_conv_wgrad")
+
+
 class DeepLabTrainPlan(_PlanBase):
     def __init__(self, model, n, h, w, precision="bf16"):
         self._init_base(model, n, h, w, precision, True)
@@ -226,7 +304,7 @@ class DeepLabTrainPlan(_PlanBase):
     def _build(self):
         m, n, H, W = self.model, self.n, self.h, self.w
         f32 = torch.float32
-        self.stem = _Stem(self, m.conv1, m.bn1, 7, 3, n, H, W)
+        self.stem = _StemS2D(self, m.conv1, m.bn1, 7, 3, n, H, W)
         h2, w2, ph, pw = self.out_hw()
         self.pool = _Buf(self.buf(n, ph, pw, 64))
         self.pool_shape = (n, ph, pw, 64)
@@ -290,6 +368,8 @@ class DeepLabTrainPlan(_PlanBase):
         self.stats_all.zero_()
         self.generation += 1
         self.x = x
+        if self.use_tc:
+            ops.stem_s2d_pack(x, self.stem_P)
         self.stem.forward(x)
         ops.maxpool3x3s2(self.stem.y.t, self.pool.t, True)
         for b in self.blocks:
@@ -366,7 +446,7 @@ class DeepLabTrainPlan(_PlanBase):
         # ---- ceil-mode max-pool and the 7x7 stem ----
         dstem = _Buf(self.gT1, ld=64, dtype=dt)
         check(lib().rtsds_maxpool3x3s2_bwd(self.stem.y.ptr, dy.ptr, n, self.stem.oh, self.stem.ow, 64, dt, 1, dstem.ptr, s), "maxpool_bwd")
-        self.stem.backward(self.x, dstem, gw, wgrad=True)
+        self.stem.backward(self.x, dstem, gw)
         self.flush_unpack()
 
 

@@ -324,3 +324,33 @@ def ce_argmax_nchw_fwd(logits, target, ignore_index, acc, pred_out=None) -> None
     n, c, h, w = logits.shape
     check(lib().rtsds_ce_argmax_nchw_fwd(_p(logits), n, c, h * w, _p(target), int(ignore_index), _p(acc), _p(pred_out),
                                          _s()), "ce_argmax_nchw_fwd")
+
+
+# ----------------------------------------------------------------------------- space-to-depth stems
+def stem_s2d_shape(n, h, w):
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    return oh, ow, (n, oh + 3, ow + 3, 16)
+
+
+def stem_s2d_pack(x: torch.Tensor, P: torch.Tensor) -> None:
+    n, _, h, w = x.shape
+    check(lib().rtsds_stem_s2d_pack(_p(x), n, h, w, _p(P), _s()), "stem_s2d_pack")
+
+
+def stem_s2d_weight(w: torch.Tensor, w2: torch.Tensor) -> None:
+    co, _, k, _ = w.shape
+    check(lib().rtsds_stem_s2d_weight(_p(w.detach()), co, k, k // 2, _p(w2), _s()), "stem_s2d_weight")
+
+
+def stem_s2d_weight_grad(g2: torch.Tensor, grad: torch.Tensor) -> None:
+    co, _, k, _ = grad.shape
+    check(lib().rtsds_stem_s2d_weight_grad(_p(g2), co, k, k // 2, _p(grad), _s()), "stem_s2d_weight_grad")
+
+
+def stem_s2d_conv_fwd(P, n, oh, ow, wpk, cout, y, out_ld, out_dtype, scale=None, shift=None, act=ACT_NONE, stats=None) -> None:
+    check(lib().rtsds_stem_s2d_conv_fwd(_p(P), n, oh, ow, _p(wpk), cout, _p(scale), _p(shift), act, _p(stats), _p(y), out_ld,
+                                        out_dtype, _s()), "stem_s2d_conv_fwd")
+
+
+def stem_s2d_conv_wgrad(P, n, oh, ow, dy, dy_ld, cout, dw_packed) -> None:
+    check(lib().rtsds_stem_s2d_conv_wgrad(_p(P), n, oh, ow, _p(dy), dy_ld, cout, _p(dw_packed), _s()), "stem_s2d_conv_wgrad")

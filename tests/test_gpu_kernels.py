@@ -393,3 +393,38 @@ def test_stem_pair_tc_wgrad(cuda, n, h, w):
     ops.stem_pair_tc_wgrad(x.cuda(), nhwc(d7, torch.bfloat16), nhwc(d3, torch.bfloat16), ws, g7, g3)
     assert rel_err(g7.cpu() - 1, w7.grad) < 2e-3 and rel_err(g3.cpu() - 1, w3.grad) < 2e-3
     assert (ws == 0).all()
+
+
+# ----------------------------------------------------------------------------- space-to-depth stems
+@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (1, 512, 1024)])
+@pytest.mark.parametrize("k", [7, 3])
+def test_stem_s2d_forward_and_wgrad(cuda, n, h, w, k):
+    """The 4-tap implicit GEMM over the padded space-to-depth image == conv k x k stride 2 (7x7 p3 / 3x3 p1) on the image,
+    forward (+BN statistics) and weight gradient, incl. odd sizes."""
+    g = torch.Generator().manual_seed(h + k)
+    x = torch.randn(n, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, k, k, generator=g) * (2.0 / (3 * k * k)) ** 0.5
+    xr = x.to(torch.bfloat16).float()
+    wr = wt.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, 2, k // 2)
+    oh, ow, pshape = ops.stem_s2d_shape(n, h, w)
+    assert ref.shape[-2:] == (oh, ow)
+    P = torch.full(pshape, float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.stem_s2d_pack(x.cuda(), P)
+    w2 = torch.empty(64, 64, 4, 1, device="cuda")
+    ops.stem_s2d_weight(wt.cuda(), w2)
+    wpk = ops.pack_conv_weight(w2, BF16)
+    y = torch.full((n, oh, ow, 64), float("nan"), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(128, device="cuda")
+    ops.stem_s2d_conv_fwd(P, n, oh, ow, wpk, 64, y, 64, F32, stats=stats)
+    assert rel_err(nchw(y), ref.detach()) < 2e-5
+    assert rel_err(stats[:64].cpu(), ref.detach().sum((0, 2, 3))) < 1e-3
+    dy = torch.randn(n, 64, oh, ow, generator=g)
+    ref.backward(dy.to(torch.bfloat16).float())
+    dw = torch.zeros(64 * 4 * 64, device="cuda")
+    ops.stem_s2d_conv_wgrad(P, n, oh, ow, nhwc(dy, torch.bfloat16), 64, 64, dw)
+    g2 = torch.zeros(64, 64, 4, 1, device="cuda")
+    ops.unpack_conv_wgrad(dw, g2, False)
+    gw = torch.zeros(64, 3, k, k, device="cuda")
+    ops.stem_s2d_weight_grad(g2, gw)
+    assert rel_err(gw.cpu(), wr.grad) < 2e-3, rel_err(gw.cpu(), wr.grad)
