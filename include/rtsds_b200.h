@@ -429,6 +429,12 @@ int rtsds_disc_cls_bwd(const float* g, float g_scale, const float* tapsum, const
 int rtsds_bce_logits(const float* logit, int n, float target, float scale, float* loss, float* dlogit,
                      rtsds_stream_t s);
 
+/* Layout converters between the reference's NCHW fp32 tensors and the path's NHWC buffers (used where a sub-module is
+ * called on its own — models/bisenet/build_bisenet.py ConvBlock / Spatial_path / ARM / FFM, deeplabv2.py Bottleneck /
+ * ClassifierModule — the whole-model forwards never need them).  y/x NHWC [n,hw,ld], channels c_off .. c_off+c. */
+int rtsds_nchw_to_nhwc(const float* x, int n, int c, int64_t hw, int dtype, void* y, int ld, int c_off, rtsds_stream_t s);
+int rtsds_nhwc_to_nchw(const void* x, int dtype, int ld, int c_off, int n, int c, int64_t hw, float* y, rtsds_stream_t s);
+
 /* ------------------------------------------------------------------------
  * Loss: bilinear resize + nn.CrossEntropyLoss(ignore_index) (main.py:124-130,
  * train.py:86-92) + argmax / pixel accuracy (train.py:102-106) in one pass

@@ -83,6 +83,8 @@ SIGNATURES = {
     "rtsds_stem_s2d_weight_grad": (_I, [_P, _I, _I, _I, _P, _P]),
     "rtsds_stem_s2d_conv_fwd": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _P]),
     "rtsds_stem_s2d_conv_wgrad": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "rtsds_nchw_to_nhwc": (_I, [_P, _I, _I, _L, _I, _P, _I, _I, _P]),
+    "rtsds_nhwc_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _L, _P, _P]),
     "rtsds_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _I, _P, _P, _P]),
     "rtsds_bn_finalize": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -397,6 +397,53 @@ static int grid_for(long long total, int threads, int waves = 8) {
     return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+// ---------------------------------------------------------------- layout converters (standalone sub-module forwards)
+// NCHW fp32 [n,c,hw] <-> NHWC [n,hw,ld] (channel offset c_off) of type T, 32x32 tiles through shared memory so that both
+// sides are coalesced.  block (32, 8); grid (ceil(hw/32), ceil(c/32), n).
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ x, int c, long long hw, T* __restrict__ y, int ld, int c_off) {
+    __shared__ float s[32][33];
+    const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+    const int c0 = blockIdx.y * 32, img = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = c0 + ty + 8 * j;
+        const long long px = p0 + tx;
+        s[ty + 8 * j][tx] = (ch < c && px < hw) ? __ldg(x + (static_cast<long long>(img) * c + ch) * hw + px) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long px = p0 + ty + 8 * j;
+        const int ch = c0 + tx;
+        if (ch < c && px < hw) y[(static_cast<long long>(img) * hw + px) * ld + c_off + ch] = from_f32<T>(s[tx][ty + 8 * j]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, int c_off, int c, long long hw, float* __restrict__ y) {
+    __shared__ float s[32][33];
+    const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+    const int c0 = blockIdx.y * 32, img = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long px = p0 + ty + 8 * j;
+        const int ch = c0 + tx;
+        s[ty + 8 * j][tx] = (ch < c && px < hw) ? to_f32(x[(static_cast<long long>(img) * hw + px) * ld + c_off + ch]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = c0 + ty + 8 * j;
+        const long long px = p0 + tx;
+        if (ch < c && px < hw) y[(static_cast<long long>(img) * c + ch) * hw + px] = s[tx][ty + 8 * j];
+    }
+}
+
 }  // namespace rtsds
 
 using namespace rtsds;
@@ -545,4 +592,24 @@ extern "C" int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, 
     resize_nchw_kernel<<<grid, RS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw, out);
     count_launch();
     return check_launch("resize_nchw_kernel");
+}
+
+extern "C" int rtsds_nchw_to_nhwc(const float* x, int n, int c, int64_t hw, int dtype, void* y, int ld, int c_off, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && y && n > 0 && c > 0 && hw > 0 && ld >= c_off + c && c_off >= 0 && n <= 65535, "nchw_to_nhwc: bad argument");
+    dim3 grid(static_cast<unsigned>(cdiv(hw, 32)), static_cast<unsigned>(cdiv(c, 32)), n), block(32, 8);
+    if (dtype == RTSDS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<__nv_bfloat16*>(y), ld, c_off);
+    else if (dtype == RTSDS_F32) nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<float*>(y), ld, c_off);
+    else { set_error("nchw_to_nhwc: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int rtsds_nhwc_to_nchw(const void* x, int dtype, int ld, int c_off, int n, int c, int64_t hw, float* y, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && y && n > 0 && c > 0 && hw > 0 && ld >= c_off + c && c_off >= 0 && n <= 65535, "nhwc_to_nchw: bad argument");
+    dim3 grid(static_cast<unsigned>(cdiv(hw, 32)), static_cast<unsigned>(cdiv(c, 32)), n), block(32, 8);
+    if (dtype == RTSDS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, c_off, c, hw, y);
+    else if (dtype == RTSDS_F32) nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, c_off, c, hw, y);
+    else { set_error("nhwc_to_nchw: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("nhwc_to_nchw_kernel");
 }
