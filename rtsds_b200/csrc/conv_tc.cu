@@ -54,6 +54,7 @@ struct TcParams {
     int n_taps, kchunks;          // k-blocks = n_taps * kchunks
     int stages;
     int split_k;
+    int n_tiles_n, total_tiles, tiles_per_cta;      // persistent kernel: tile id = n_tile * m_tiles + m_tile
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
     short tap_kb[TAP_MAX];            // first weight k-block of each tap
     long long out_sn, out_sh, out_sw;     // element strides of y
@@ -83,6 +84,92 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
     }
     return v[0];
 }
+
+// Epilogue of one 32-column chunk of an accumulator row: optional train-mode BatchNorm statistics of the raw value,
+// scale/shift (folded BatchNorm or bias), residual add, activation, 16-byte stores.  Shared by both conv kernels.
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[32], int c0, int n0, bool valid, long long out_off,
+                                                  long long res_off, const float* s_scale, const float* s_shift, float* s_stats,
+                                                  int lane) {
+    const int co0 = n0 + c0;
+            if (p.stats) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
+            float s1 = warp_transpose_sum(t, lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] * v[j] : 0.0f;
+            float s2 = warp_transpose_sum(t, lane);
+            atomicAdd(&s_stats[c0 + lane], s1);
+            atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
+        }
+
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+            const bool full = (co0 + 32 <= p.cout);
+            if (p.out_dtype == RTSDS_BF16) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + out_off + co0;
+                const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+                if (full) {
+                    if (res) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res + res_off + co0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 rv = __ldg(rp + g);
+                            float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y);
+                            float2 c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+                            v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
+                            v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        o.x = pack_bf16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope));
+                        o.y = pack_bf16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope));
+                        o.z = pack_bf16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope));
+                        o.w = pack_bf16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope));
+                        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (co0 + j < p.cout) {
+                            float x = v[j];
+                            if (res) x += __bfloat162float(res[res_off + co0 + j]);
+                            dst[j] = __float2bfloat16_rn(apply_act(x, p.act, p.slope));
+                        }
+                    }
+                }
+            } else {
+                float* dst = reinterpret_cast<float*>(p.y) + out_off + co0;
+                const float* res = reinterpret_cast<const float*>(p.residual);
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (res) {
+                            float4 rv = __ldg(reinterpret_cast<const float4*>(res + res_off + co0 + j));
+                            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                        }
+                        o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
+                        o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (co0 + j < p.cout) {
+                            float x = v[j];
+                            if (res) x += res[res_off + co0 + j];
+                            dst[j] = apply_act(x, p.act, p.slope);
+                        }
+                    }
+                }
+            }
+        }
+    }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(TC_THREADS)
@@ -241,83 +328,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 continue;
             }
 
-            if (p.stats) {
-                float t[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
-                float s1 = warp_transpose_sum(t, lane);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] * v[j] : 0.0f;
-                float s2 = warp_transpose_sum(t, lane);
-                atomicAdd(&s_stats[c0 + lane], s1);
-                atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
-            }
-
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
-                const bool full = (co0 + 32 <= p.cout);
-                if (p.out_dtype == RTSDS_BF16) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + out_off + co0;
-                    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
-                    if (full) {
-                        if (res) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(res + res_off + co0);
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                uint4 rv = __ldg(rp + g);
-                                float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y);
-                                float2 c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
-                                v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
-                                v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
-                            }
-                        }
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 o;
-                            o.x = pack_bf16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope));
-                            o.y = pack_bf16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope));
-                            o.z = pack_bf16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope));
-                            o.w = pack_bf16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope));
-                            *reinterpret_cast<uint4*>(dst + g * 8) = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (co0 + j < p.cout) {
-                                float x = v[j];
-                                if (res) x += __bfloat162float(res[res_off + co0 + j]);
-                                dst[j] = __float2bfloat16_rn(apply_act(x, p.act, p.slope));
-                            }
-                        }
-                    }
-                } else {
-                    float* dst = reinterpret_cast<float*>(p.y) + out_off + co0;
-                    const float* res = reinterpret_cast<const float*>(p.residual);
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (res) {
-                                float4 rv = __ldg(reinterpret_cast<const float4*>(res + res_off + co0 + j));
-                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                            }
-                            o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
-                            o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
-                            *reinterpret_cast<float4*>(dst + j) = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (co0 + j < p.cout) {
-                                float x = v[j];
-                                if (res) x += res[res_off + co0 + j];
-                                dst[j] = apply_act(x, p.act, p.slope);
-                            }
-                        }
-                    }
-                }
-            }
+            tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
         }
         if (p.stats && p.split_k == 1) {
             // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
@@ -339,6 +350,212 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+// =====================================================================================
+// Persistent variant for grids of many tiles (training batches, stems): one CTA per SM walks a contiguous range of
+// output tiles.
+//   * the weights of the CTA's N tile stay RESIDENT in shared memory when all their K blocks fit (3x3 convs with
+//     <= 128 input channels, 1x1 convs, stems): only activation tiles stream through the TMA ring;
+//   * two TMEM accumulators: the epilogue of tile i (tcgen05.ld, BatchNorm statistics, stores) overlaps the TMA / MMA
+//     main loop of tile i+1;
+//   * barrier init, TMEM allocation and descriptor prefetch are paid once per CTA instead of once per tile.
+// =====================================================================================
+template <int BLOCK_N, bool B_RESIDENT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+    constexpr uint32_t TMEM_COLS = 2 * (BLOCK_N < 32 ? 32 : BLOCK_N);
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    const int kb_total = p.n_taps * p.kchunks;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * TC_A_BYTES;
+    const size_t b_slots = B_RESIDENT ? static_cast<size_t>(kb_total) : static_cast<size_t>(stages);
+    float* s_scale = reinterpret_cast<float*>(smem_b + b_slots * B_BYTES);
+    float* s_shift = s_scale + BLOCK_N;
+    float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 2 * BLOCK_N);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* acc_full = empty_bar + stages;                // [2]
+    uint64_t* acc_empty = acc_full + 2;                     // [2]
+    uint64_t* b_full = acc_empty + 2;
+    uint64_t* b_free = b_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.n_img;
+    const int t_begin = blockIdx.x * p.tiles_per_cta;
+    const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&maps.b);
+        ptx::prefetch_tmap(&maps.a[0]);
+        for (int i = 0; i < stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 128); }
+        ptx::mbar_init(b_full, 1);
+        ptx::mbar_init(b_free, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp >= 2)
+        for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        // =================== TMA producer ===================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, bfree_phase = 0;
+            int cur_n = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
+                const int img = m_tile / tiles_per_img;
+                const int trem = m_tile - img * tiles_per_img;
+                const int th = trem / p.tiles_w;
+                const int h0 = th * p.tile_h, w0 = (trem - th * p.tiles_w) * p.tile_w;
+                const int n0 = n_tile * BLOCK_N;
+                if (B_RESIDENT && n_tile != cur_n) {
+                    if (cur_n >= 0) { ptx::mbar_wait(b_free, bfree_phase); bfree_phase ^= 1; }   // MMAs of the old N tile retired
+                    ptx::mbar_expect_tx(b_full, static_cast<uint32_t>(kb_total) * B_BYTES);
+                    for (int kb = 0; kb < kb_total; ++kb) {
+                        const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
+                        ptx::tma_load_2d(smem_b + static_cast<size_t>(kb) * B_BYTES, &maps.b, b_full, (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
+                    }
+                    cur_n = n_tile;
+                }
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + (B_RESIDENT ? 0 : B_BYTES));
+                    ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES, &maps.a[p.tap_map[tap]], &full_bar[stage],
+                                     cc * TC_BLOCK_K, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
+                    if (!B_RESIDENT)
+                        ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
+                                         (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =================== MMA issuer ===================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, bfull_phase = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            int acc = 0, cur_n = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int n_tile = tile / m_tiles;
+                if (B_RESIDENT && n_tile != cur_n) {
+                    ptx::mbar_wait(b_full, bfull_phase);
+                    bfull_phase ^= 1;
+                    cur_n = n_tile;
+                }
+                ptx::mbar_wait(&acc_empty[acc], acc_phase[acc] ^ 1);        // the epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + static_cast<size_t>(stage) * TC_A_BYTES));
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(B_RESIDENT ? kb : stage) * B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                        ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&acc_full[acc]);
+                if (B_RESIDENT && tile + 1 < t_end && (tile + 1) / m_tiles != n_tile) ptx::umma_commit(b_free);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =================== epilogue (4 warps, 128 TMEM lanes) ===================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
+        uint32_t full_phase[2] = {0, 0};
+        int acc = 0, cur_n = -1;
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
+            const int img = m_tile / tiles_per_img;
+            const int trem = m_tile - img * tiles_per_img;
+            const int th = trem / p.tiles_w;
+            const int oh = th * p.tile_h + hl, ow = (trem - th * p.tiles_w) * p.tile_w + wl;
+            const int n0 = n_tile * BLOCK_N;
+            const bool valid = (oh < p.oh) && (ow < p.ow);
+            if (n_tile != cur_n) {
+                // new N tile: flush the statistics of the old one, load this one's scale / shift
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (p.stats && cur_n >= 0) {
+                    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                        const int co = cur_n * BLOCK_N + i;
+                        if (co < p.cout) {
+                            atomicAdd(&p.stats[co], s_stats[i]);
+                            atomicAdd(&p.stats[p.cout + co], s_stats[BLOCK_N + i]);
+                        }
+                        s_stats[i] = 0.0f; s_stats[BLOCK_N + i] = 0.0f;
+                    }
+                }
+                for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                    const int co = n0 + i;
+                    s_scale[i] = (p.scale && co < p.cout) ? p.scale[co] : 1.0f;
+                    s_shift[i] = (p.shift && co < p.cout) ? p.shift[co] : 0.0f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_n = n_tile;
+            }
+            ptx::mbar_wait(&acc_full[acc], full_phase[acc]);
+            full_phase[acc] ^= 1;
+            ptx::tc_fence_after();
+            const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
+            const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_addr + c0, r);
+                ptx::tmem_ld_wait();
+                if (c0 + 32 >= BLOCK_N) {                 // last read of this accumulator: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&acc_empty[acc]);
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
+            }
+            acc ^= 1;
+        }
+        if (p.stats && cur_n >= 0) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                const int co = cur_n * BLOCK_N + i;
+                if (co < p.cout) {
+                    atomicAdd(&p.stats[co], s_stats[i]);
+                    atomicAdd(&p.stats[p.cout + co], s_stats[BLOCK_N + i]);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // Sum split-K slices in slice order and apply the epilogue.
@@ -503,6 +720,36 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     return check_launch("conv_tc_kernel");
 }
 
+static size_t tcp_smem_bytes(int block_n, int stages, int b_slots) {
+    return 1024 + static_cast<size_t>(stages) * TC_A_BYTES + static_cast<size_t>(b_slots) * block_n * TC_BLOCK_K * 2 + 4 * block_n * 4 +
+           (2 * stages + 6) * 8 + 16;
+}
+
+template <int BLOCK_N, bool B_RESIDENT>
+static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("conv_tcp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT>, maps, p);
+    if (le != cudaSuccess) { set_error("conv_tcp_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
+    count_launch();
+    return check_launch("conv_tcp_kernel");
+}
+
 }  // namespace rtsds
 
 using namespace rtsds;
@@ -607,6 +854,28 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     p.stages = stages;
     RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv_tc: too many tiles");
 
+    // many tiles, no split-K: persistent CTAs (resident weights when they fit, double-buffered accumulators)
+    static int persist_mode = -1;
+    if (persist_mode < 0) { const char* e = getenv("RTSDS_NO_PERSISTENT"); persist_mode = (e && e[0] == '1') ? 0 : 1; }
+    const long long total_tiles = m_tiles * n_tiles;
+    // (only with resident weights: when they have to stream, two co-resident non-persistent CTAs per SM hide more latency)
+    const bool resident = kb_total >= 1 && tcp_smem_bytes(block_n, 3, kb_total) <= 227 * 1024;
+    if (persist_mode && split == 1 && resident && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30)) {
+        const size_t b_all = static_cast<size_t>(kb_total) * block_n * TC_BLOCK_K * 2;
+        int st = resident ? 8 : (block_n == 128 ? 6 : 8);
+        while (st > 2 && tcp_smem_bytes(block_n, st, resident ? kb_total : st) > 227 * 1024) --st;
+        (void)b_all;
+        p.stages = st;
+        p.n_tiles_n = n_tiles;
+        p.total_tiles = static_cast<int>(total_tiles);
+        int ctas = num_sms();
+        p.tiles_per_cta = static_cast<int>(cdiv(total_tiles, ctas));
+        ctas = static_cast<int>(cdiv(total_tiles, p.tiles_per_cta));
+        const size_t smem = tcp_smem_bytes(block_n, st, resident ? kb_total : st);
+        if (block_n == 128) return resident ? launch_tcp<128, true>(maps, p, ctas, smem, stream) : launch_tcp<128, false>(maps, p, ctas, smem, stream);
+        if (block_n == 64) return resident ? launch_tcp<64, true>(maps, p, ctas, smem, stream) : launch_tcp<64, false>(maps, p, ctas, smem, stream);
+        if (block_n == 32) return resident ? launch_tcp<32, true>(maps, p, ctas, smem, stream) : launch_tcp<32, false>(maps, p, ctas, smem, stream);
+    }
     dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
     int rc;
     if (block_n == 128) rc = launch_tc<128>(maps, p, grid, stream);
