@@ -1,6 +1,6 @@
 """Diagnostic: per-parameter gradient comparison between precision modes, in backward order."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from oracle import weights

@@ -1,5 +1,5 @@
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, bench, bench_train
 from rtsds_b200.bisenet_autograd import bisenet_fused_ce
 from rtsds_b200.serving import AsyncScalarReader, DevicePrefetcher

@@ -1,7 +1,7 @@
 """Diagnostic (not collected by pytest): compare the bf16 CUDA plan's intermediate buffers with the
 bf16-emulating oracle stage by stage."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from oracle import bisenet_bf16, bisenet_ref, weights

@@ -1,7 +1,7 @@
 """Diagnostic for the tcgen05 conv kernel (not collected by pytest): structured operands that
 reveal row / K-permutation problems in the TMA->smem->UMMA descriptor chain."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from rtsds_b200 import ops
