@@ -55,6 +55,7 @@ struct TcParams {
     int stages;
     int split_k;
     int n_tiles_n, total_tiles, tiles_per_cta;      // persistent kernel: tile id = n_tile * m_tiles + m_tile
+    int halo_d, halo_rows, a_stage_bytes, halo_baseoff;   // halo mode: dilation, rows of the halo tile, bytes per A stage
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
     short tap_kb[TAP_MAX];            // first weight k-block of each tap
     long long out_sn, out_sh, out_sw;     // element strides of y
@@ -361,7 +362,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 //     main loop of tile i+1;
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per CTA instead of once per tile.
 // =====================================================================================
-template <int BLOCK_N, bool B_RESIDENT>
+// HALO (3x3 stride-1 convs, tile = 8 x 16 output pixels): instead of one TMA box per filter tap, ONE box of the
+// (16+2d) x 16-pixel input neighbourhood per 64-channel chunk lands in shared memory (row pitch 16 pixels = 2048 B,
+// a multiple of the 1024-byte swizzle pattern) and each tap's A operand is a WINDOW into it: UMMA descriptor start =
+// tile + ((r*d)*16 + s*d) * 128 B, 8-row groups 2048 B apart.  4x fewer TMA rows than the tap-wise form — the TMA row
+// rate (~128 B per 8 clk per SM), not HBM or the tensor pipe, is what bounds the tap-wise kernels on 64/128-channel layers.
+template <int BLOCK_N, bool B_RESIDENT, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
@@ -372,8 +378,9 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     const int kb_total = p.n_taps * p.kchunks;
+    const int a_stage = HALO ? p.a_stage_bytes : TC_A_BYTES;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + static_cast<size_t>(stages) * TC_A_BYTES;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * a_stage;
     const size_t b_slots = B_RESIDENT ? static_cast<size_t>(kb_total) : static_cast<size_t>(stages);
     float* s_scale = reinterpret_cast<float*>(smem_b + b_slots * B_BYTES);
     float* s_shift = s_scale + BLOCK_N;
@@ -434,6 +441,15 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     }
                     cur_n = n_tile;
                 }
+                if (HALO) {
+                    for (int cc = 0; cc < p.kchunks; ++cc) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.halo_rows) * 16 * 128);
+                        ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * a_stage, &maps.a[1], &full_bar[stage], cc * TC_BLOCK_K,
+                                         w0 - p.halo_d, h0 - p.halo_d, img);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+                } else {
                 for (int kb = 0; kb < kb_total; ++kb) {
                     const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -444,6 +460,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
                                          (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
                 }
             }
         }
@@ -465,6 +482,25 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 ptx::mbar_wait(&acc_empty[acc], acc_phase[acc] ^ 1);        // the epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+                if (HALO) {
+                    for (int cc = 0; cc < p.kchunks; ++cc) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t a_base = ptx::smem_u32(smem_a + static_cast<size_t>(stage) * a_stage);
+                        for (int tap = 0; tap < p.n_taps; ++tap) {
+                            // window of this tap: rows (dh + d) .. +16, columns (dw + d) .. +8 of the 16-pixel-wide halo tile
+                            const uint32_t row_off = static_cast<uint32_t>((p.tap_dh[tap] + p.halo_d) * 16 + (p.tap_dw[tap] + p.halo_d));
+                            const uint32_t a_addr = a_base + row_off * 128u;
+                            const uint64_t da = ptx::umma_desc_k_sw128_ex(a_addr, 2048u, p.halo_baseoff ? (row_off & 7u) : 0u);
+                            const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(tap * p.kchunks + cc) * B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                                ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+                } else {
                 for (int kb = 0; kb < kb_total; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -475,6 +511,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
                 }
                 ptx::umma_commit(&acc_full[acc]);
                 if (B_RESIDENT && tile + 1 < t_end && (tile + 1) / m_tiles != n_tile) ptx::umma_commit(b_free);
@@ -720,16 +757,16 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     return check_launch("conv_tc_kernel");
 }
 
-static size_t tcp_smem_bytes(int block_n, int stages, int b_slots) {
-    return 1024 + static_cast<size_t>(stages) * TC_A_BYTES + static_cast<size_t>(b_slots) * block_n * TC_BLOCK_K * 2 + 4 * block_n * 4 +
+static size_t tcp_smem_bytes(int block_n, int stages, int b_slots, int a_stage = TC_A_BYTES) {
+    return 1024 + static_cast<size_t>(stages) * a_stage + static_cast<size_t>(b_slots) * block_n * TC_BLOCK_K * 2 + 4 * block_n * 4 +
            (2 * stages + 6) * 8 + 16;
 }
 
-template <int BLOCK_N, bool B_RESIDENT>
+template <int BLOCK_N, bool B_RESIDENT, bool HALO = false>
 static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tcp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
@@ -744,7 +781,7 @@ static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t sm
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT>, maps, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tcp_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tcp_kernel");
@@ -804,6 +841,40 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     memset(&p, 0, sizeof(p));
     int block_n, split;
     tp_plan(t, &block_n, &split, &p.tile_w, &p.tile_h);
+    // ---- halo mode: 3x3 stride-1 tap grids (forward or dgrad), weights resident, >= 2 waves of 8x16 tiles ----
+    static int halo_mode = -1, halo_baseoff = 0;     // measured: the UMMA unit swizzles on absolute smem address bits, base offset stays 0
+    if (halo_mode < 0) {
+        const char* e = getenv("RTSDS_NO_HALO");
+        halo_mode = (e && e[0] == '1') ? 0 : 1;
+        const char* b = getenv("RTSDS_HALO_BASEOFF");
+        if (b) halo_baseoff = atoi(b);
+    }
+    bool halo = false;
+    int halo_d = 0;
+    if (halo_mode && split == 1 && t.n_taps == 9 && t.view[0].used) {
+        for (int i = 0; i < 9; ++i) halo_d = max(halo_d, max(abs(t.dh[i]), abs(t.dw[i])));
+        halo = halo_d == 1 || halo_d == 2 || halo_d == 4;
+        bool seen[9] = {false};
+        for (int i = 0; i < 9 && halo; ++i) {
+            if (t.map[i] != 0 || t.dh[i] % halo_d || t.dw[i] % halo_d) { halo = false; break; }
+            const int r = t.dh[i] / halo_d + 1, q = t.dw[i] / halo_d + 1;
+            if (r < 0 || r > 2 || q < 0 || q > 2 || seen[r * 3 + q]) { halo = false; break; }
+            seen[r * 3 + q] = true;
+            if (t.kb[i] != i * (t.ck / TC_BLOCK_K)) halo = false;
+        }
+        if (halo) {
+            const int cp = conv_cout_pad(t.cout);
+            const int a_stage = (16 + 2 * halo_d) * 16 * 128;
+            const int kbt = 9 * (t.ck / TC_BLOCK_K);
+            // the whole Cout must be ONE resident N tile (otherwise every N tile re-loads the halo, and streaming the
+            // weights costs as many TMA rows as the taps did): in practice the 64-input-channel 3x3 layers
+            int bn = 0;
+            if ((cp == 64 || cp == 128) && tcp_smem_bytes(cp, 2, kbt, a_stage) <= 227 * 1024) bn = cp;
+            const long long mt = static_cast<long long>(t.n_img) * cdiv(t.ow, 8) * cdiv(t.oh, 16);
+            if (bn == 0 || mt * (cp / bn) < 2LL * num_sms()) halo = false;
+            else { block_n = bn; p.tile_w = 8; p.tile_h = 16; p.halo_d = halo_d; p.halo_rows = 16 + 2 * halo_d; p.a_stage_bytes = a_stage; p.halo_baseoff = halo_baseoff; }
+        }
+    }
     p.n_img = t.n_img; p.oh = t.oh; p.ow = t.ow;
     p.tiles_w = static_cast<int>(cdiv(t.ow, p.tile_w));
     p.tiles_h = static_cast<int>(cdiv(t.oh, p.tile_h));
@@ -825,6 +896,11 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     for (int i = 0; i < 4; ++i)
         if (!t.view[i].used && first_used >= 0) maps.a[i] = maps.a[first_used];
     for (int i = 0; i < t.n_taps; ++i) { p.tap_dh[i] = t.dh[i]; p.tap_dw[i] = t.dw[i]; p.tap_map[i] = t.map[i]; p.tap_kb[i] = static_cast<short>(t.kb[i]); }
+    if (halo) {      // one box of 16 x (16+2d) pixels per 64-channel chunk; out-of-image pixels are zero-filled = the padding
+        int rc = make_act_map(&maps.a[1], t.view[0].base, t.c_extent, t.view[0].wd, t.view[0].hd, t.n_img, t.view[0].sw, t.view[0].sh,
+                              t.view[0].sn, 16, p.halo_rows);
+        if (rc != RTSDS_OK) return rc;
+    }
     if (t.n_taps > 0) {
         int rc = make_weight_map(&maps.b, t.w, t.w_ktot, p.cout_pad, block_n);
         if (rc != RTSDS_OK) return rc;
@@ -859,6 +935,21 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     if (persist_mode < 0) { const char* e = getenv("RTSDS_NO_PERSISTENT"); persist_mode = (e && e[0] == '1') ? 0 : 1; }
     const long long total_tiles = m_tiles * n_tiles;
     // (only with resident weights: when they have to stream, two co-resident non-persistent CTAs per SM hide more latency)
+    if (halo) {
+        int st = 6;
+        while (st > 2 && tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes) > 227 * 1024) --st;
+        if (st > p.kchunks * 4) st = max(2, p.kchunks * 4);
+        p.stages = st;
+        p.n_tiles_n = n_tiles;
+        p.total_tiles = static_cast<int>(total_tiles);
+        int ctas = num_sms();
+        p.tiles_per_cta = static_cast<int>(cdiv(total_tiles, ctas));
+        ctas = static_cast<int>(cdiv(total_tiles, p.tiles_per_cta));
+        const size_t smem = tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes);
+        if (block_n == 128) return launch_tcp<128, true, true>(maps, p, ctas, smem, stream);
+        if (block_n == 64) return launch_tcp<64, true, true>(maps, p, ctas, smem, stream);
+        return launch_tcp<32, true, true>(maps, p, ctas, smem, stream);
+    }
     const bool resident = kb_total >= 1 && tcp_smem_bytes(block_n, 3, kb_total) <= 227 * 1024;
     if (persist_mode && split == 1 && resident && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30)) {
         const size_t b_all = static_cast<size_t>(kb_total) * block_n * TC_BLOCK_K * 2;

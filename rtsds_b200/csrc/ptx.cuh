@@ -152,6 +152,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// As above with an explicit stride between 8-row groups and the "matrix base offset" field (bits [49,52)) for operands
+// whose start address is not aligned to the 1024-byte swizzle pattern: a window into a larger swizzled tile.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // Same swizzle, MN-major operand: the MN extent is contiguous in memory
 // (64 bf16 = 128 B per K row); LBO = byte distance between 64-element MN
 // chunks, SBO = byte distance between groups of 8 K rows (1024 B).

@@ -317,3 +317,38 @@ def test_tapn_conv_forward_backward(cuda, dtype, tol, n, h, w, cin, c, k, dil):
     assert rel_err(nchw(dx), 2 * xr.grad) < 2 * tol
     tn.weight_grad(gw)                                        # the wgrad scratch was left clean
     assert rel_err(gw.cpu(), 2 * wr.grad) < 2 * tol
+
+
+# ----------------------------------------------------------------------------- persistent / halo variants (many tiles)
+# (name, n, cin, h, w, cout, k, stride, pad, dil): >= 2 waves of 128-pixel tiles so that the persistent kernel (resident
+# weights) and, for 3x3 stride-1, its halo form (one TMA box per 8x16 tile, taps as windows into it) are selected
+BIG_CASES = [
+    ("halo_64", 2, 64, 160, 192, 64, 3, 1, 1, 1),
+    ("halo_128_odd", 3, 128, 101, 131, 128, 3, 1, 1, 1),
+    ("halo_dil2", 2, 64, 130, 170, 64, 3, 1, 2, 2),
+    ("halo_dil4", 2, 64, 129, 161, 128, 3, 1, 4, 4),
+    ("persist_1x1", 2, 128, 160, 192, 64, 1, 1, 0, 1),
+    ("persist_s2", 2, 64, 256, 320, 128, 3, 2, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", BIG_CASES, ids=[c[0] for c in BIG_CASES])
+def test_conv_tc_many_tiles_forward_and_dgrad(cuda, case):
+    _, n, cin, h, w, cout, k, stride, pad, dil = case
+    x, wt, g = _mk(n, cin, h, w, cout, k, seed=5)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g)
+    y, stats, _ = run_conv("tc", x, wt, stride=stride, pad=pad, dil=dil, out_dtype=F32, out_ld=ops.cout_pad(cout), want_stats=True)
+    ref, raw = conv_ref(x, wt, stride=stride, pad=pad, dil=dil)
+    assert y.shape == ref.shape and rel_err(y, ref) < 2e-4, rel_err(y, ref)
+    assert rel_err(stats[:cout], raw.sum((0, 2, 3))) < 2e-3 and rel_err(stats[cout:], (raw * raw).sum((0, 2, 3))) < 2e-3
+    res = torch.randn_like(ref)
+    y2, _, _ = run_conv("tc", x, wt, stride=stride, pad=pad, dil=dil, scale=scale, shift=shift, residual=res, act=ACT_RELU)
+    ref2, _ = conv_ref(x, wt, stride=stride, pad=pad, dil=dil, scale=scale, shift=shift, residual=res, act=ACT_RELU)
+    assert rel_err(y2, ref2) < 1e-2
+    oh, ow = ref.shape[-2:]
+    dy = torch.randn(n, cout, oh, ow, generator=g)
+    dx, dw = _run_bwd("tc", x, wt, dy, stride, pad, dil, BF16)
+    rdx, rdw = _bwd_ref(x, wt, dy, stride, pad, dil, True)
+    assert rel_err(dx, rdx) < 2e-4, rel_err(dx, rdx)
+    assert rel_err(dw, rdw) < 2e-4, rel_err(dw, rdw)
