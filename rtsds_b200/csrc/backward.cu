@@ -5,6 +5,7 @@
 // All HBM-bound: vectorised 16-byte accesses, register/shuffle/shared-memory
 // reductions, one global atomic per channel per block.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace rtsds {
 
@@ -194,6 +195,209 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y
         st8(d_raw + p * d_raw_ld + g8 * 8, o);
         if (g_out) st8(g_out + p * g_ld + g8 * 8, gg);
     }
+}
+
+// ---- streamed forms (bf16, contiguous [n_pix, c], c = 8 * 2^k) -----------------------------------------------
+// The register form above keeps at most 4-6 16-byte loads per thread in flight at ~120 registers, i.e. ~32 KB per
+// SM, and stalls near 3 TB/s (latency bound).  Here one thread streams 8 KB tiles of every input into a 4-stage
+// shared-memory ring with cp.async.bulk (128+ KB in flight per SM, independent of registers); the 256 threads read
+// the tiles back conflict-free, one 16-byte chunk = one 8-channel group of one pixel each.
+constexpr int BNS_TILE = 8192;   // bytes per tensor per stage
+constexpr int bns_stages(int nt) { return 12 / nt; }   // 96 KB ring per block, two blocks per SM
+constexpr int BNS_CHUNKS = BNS_TILE / 16 / 256;   // 16-byte chunks per thread per tile (2)
+
+__device__ __forceinline__ F8 cvt8(const uint4& u) {
+    F8 r;
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+
+template <int NT>
+struct BnStream {
+    static constexpr int BNS_STAGES = bns_stages(NT);
+    uint8_t* ring;
+    uint64_t* full;
+    const __nv_bfloat16* src[NT];
+    long long n_pix, n_tiles;
+    int c, tile_px;
+    __device__ __forceinline__ void issue(int s, long long tile) const {
+        const long long px0 = tile * tile_px;
+        const long long left = n_pix - px0;
+        const uint32_t bytes = static_cast<uint32_t>((left < tile_px ? left : tile_px) * c * 2);
+        ptx::mbar_expect_tx(&full[s], NT * bytes);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            ptx::bulk_load_1d(ring + (s * NT + t) * BNS_TILE, src[t] + px0 * c, bytes, &full[s]);
+    }
+    __device__ __forceinline__ void start(uint8_t* smem) {
+        ring = smem;
+        full = reinterpret_cast<uint64_t*>(smem + BNS_STAGES * NT * BNS_TILE);
+        tile_px = BNS_TILE / (c * 2);
+        n_tiles = (n_pix + tile_px - 1) / tile_px;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < BNS_STAGES; ++s) ptx::mbar_init(&full[s], 1);
+            ptx::fence_barrier_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < BNS_STAGES; ++s) {
+                const long long tile = blockIdx.x + static_cast<long long>(s) * gridDim.x;
+                if (tile < n_tiles) issue(s, tile);
+            }
+        }
+    }
+    __device__ __forceinline__ const uint4* stage(int s, int t) const {
+        return reinterpret_cast<const uint4*>(ring + (s * NT + t) * BNS_TILE);
+    }
+};
+
+static size_t bns_smem(int nt, int floats = 0) { return static_cast<size_t>(bns_stages(nt)) * nt * BNS_TILE + 64 + sizeof(float) * floats; }
+
+template <bool WITH_Y>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_stream_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                            const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ fsc,
+                            const float* __restrict__ fsh, long long n_pix, int c, int relu, float* sums) {
+    extern __shared__ __align__(128) uint8_t bns_smem_buf[];
+    constexpr int NT = WITH_Y ? 3 : 2;
+    constexpr int BNS_STAGES = bns_stages(NT);
+    float* sh = reinterpret_cast<float*>(bns_smem_buf + BNS_STAGES * NT * BNS_TILE + 64);   // [2*c]
+    BnStream<NT> st;
+    st.src[0] = dy; st.src[1] = raw;
+    if (WITH_Y) st.src[NT - 1] = y;
+    st.n_pix = n_pix; st.c = c;
+    for (int i = threadIdx.x; i < 2 * c; i += 256) sh[i] = 0.f;
+    st.start(bns_smem_buf);
+    const int cg = c >> 3, g8 = threadIdx.x % cg, prow = threadIdx.x / cg, prows = 256 / cg;
+    const bool rawmask = relu && !WITH_Y;
+    float s1[8], s2[8], mu[8], fa[8], fb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = g8 * 8 + j;
+        s1[j] = 0.f; s2[j] = 0.f; mu[j] = mean[ch];
+        fa[j] = rawmask ? fsc[ch] : 0.f; fb[j] = rawmask ? fsh[ch] : 0.f;
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < st.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % BNS_STAGES;
+        ptx::mbar_wait(&st.full[s], (it / BNS_STAGES) & 1);
+        uint4 ud[BNS_CHUNKS], ur[BNS_CHUNKS], uy[BNS_CHUNKS];
+#pragma unroll
+        for (int k = 0; k < BNS_CHUNKS; ++k) {
+            ud[k] = st.stage(s, 0)[threadIdx.x + k * 256];
+            ur[k] = st.stage(s, 1)[threadIdx.x + k * 256];
+            if (WITH_Y) uy[k] = st.stage(s, NT - 1)[threadIdx.x + k * 256];
+        }
+        __syncthreads();   // every thread has read stage s: refill it
+        if (threadIdx.x == 0) {
+            const long long next = tile + static_cast<long long>(BNS_STAGES) * gridDim.x;
+            if (next < st.n_tiles) st.issue(s, next);
+        }
+        const long long px0 = tile * st.tile_px;
+#pragma unroll
+        for (int k = 0; k < BNS_CHUNKS; ++k) {
+            if (px0 + prow + k * prows >= n_pix) continue;
+            const F8 d = cvt8(ud[k]), r = cvt8(ur[k]);
+            F8 yy;
+            if (WITH_Y) yy = cvt8(uy[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float m = WITH_Y ? yy.v[j] : fmaf(r.v[j], fa[j], fb[j]);
+                const float g = (relu && !(m > 0.f)) ? 0.f : d.v[j];
+                s1[j] += g;
+                s2[j] = fmaf(g, r.v[j] - mu[j], s2[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[g8 * 8 + j], s1[j]);
+        atomicAdd(&sh[c + g8 * 8 + j], s2[j] * invstd[g8 * 8 + j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * c; i += 256) atomicAdd(&sums[i], sh[i]);
+}
+
+template <bool WITH_Y>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_stream_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                           const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                           const float* __restrict__ sums, const float* __restrict__ fsc, const float* __restrict__ fsh,
+                           long long n_pix, int c, int relu, __nv_bfloat16* __restrict__ d_raw,
+                           __nv_bfloat16* __restrict__ g_out, float* dgamma, float* dbeta) {
+    extern __shared__ __align__(128) uint8_t bns_smem_buf[];
+    constexpr int NT = WITH_Y ? 3 : 2;
+    constexpr int BNS_STAGES = bns_stages(NT);
+    BnStream<NT> st;
+    st.src[0] = dy; st.src[1] = raw;
+    if (WITH_Y) st.src[NT - 1] = y;
+    st.n_pix = n_pix; st.c = c;
+    st.start(bns_smem_buf);
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < c; i += 256) {
+            if (dgamma) dgamma[i] += sums[c + i];
+            if (dbeta) dbeta[i] += sums[i];
+        }
+    }
+    const int cg = c >> 3, g8 = threadIdx.x % cg, prow = threadIdx.x / cg, prows = 256 / cg;
+    const bool rawmask = relu && !WITH_Y;
+    const float inv_m = 1.0f / static_cast<float>(n_pix);
+    float ca[8], cb[8], cc[8], fa[8], fb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = g8 * 8 + j;
+        const float is = invstd[ch], gm = gamma ? gamma[ch] : 1.f;
+        ca[j] = gm * is;
+        cb[j] = -gm * is * is * sums[c + ch] * inv_m;
+        cc[j] = -ca[j] * sums[ch] * inv_m - cb[j] * mean[ch];
+        fa[j] = rawmask ? fsc[ch] : 0.f; fb[j] = rawmask ? fsh[ch] : 0.f;
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < st.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % BNS_STAGES;
+        ptx::mbar_wait(&st.full[s], (it / BNS_STAGES) & 1);
+        uint4 ud[BNS_CHUNKS], ur[BNS_CHUNKS], uy[BNS_CHUNKS];
+#pragma unroll
+        for (int k = 0; k < BNS_CHUNKS; ++k) {
+            ud[k] = st.stage(s, 0)[threadIdx.x + k * 256];
+            ur[k] = st.stage(s, 1)[threadIdx.x + k * 256];
+            if (WITH_Y) uy[k] = st.stage(s, NT - 1)[threadIdx.x + k * 256];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long next = tile + static_cast<long long>(BNS_STAGES) * gridDim.x;
+            if (next < st.n_tiles) st.issue(s, next);
+        }
+        const long long px0 = tile * st.tile_px;
+#pragma unroll
+        for (int k = 0; k < BNS_CHUNKS; ++k) {
+            const long long p = px0 + prow + k * prows;
+            if (p >= n_pix) continue;
+            const F8 d = cvt8(ud[k]), r = cvt8(ur[k]);
+            F8 yy, o, gg;
+            if (WITH_Y) yy = cvt8(uy[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float m = WITH_Y ? yy.v[j] : fmaf(r.v[j], fa[j], fb[j]);
+                const float g = (relu && !(m > 0.f)) ? 0.f : d.v[j];
+                gg.v[j] = g;
+                o.v[j] = fmaf(ca[j], g, fmaf(cb[j], r.v[j], cc[j]));
+            }
+            st8(d_raw + p * c + g8 * 8, o);
+            if (g_out) st8(g_out + p * c + g8 * 8, gg);
+        }
+    }
+}
+
+// streamed forms apply to contiguous bf16 tensors whose 8-channel groups divide the 256-thread block
+static bool bns_ok(int c, int dtype, int dy_ld, int raw_ld, const void* y, int y_ld, int64_t n_pix) {
+    static const bool off = getenv("RTSDS_NO_BN_STREAM") != nullptr;
+    if (off || dtype != RTSDS_BF16 || c < 8 || c > 2048 || (c & (c - 1)) != 0) return false;
+    if (dy_ld != c || raw_ld != c || (y && y_ld != c)) return false;
+    return n_pix * c >= (1 << 20);   // small maps: the register form has less fixed cost
 }
 
 // out[c] (+)= sum over pixels of x[p][c]   (bias gradients)
@@ -699,6 +903,27 @@ static int bn_bwd_reduce_impl(const void* dy, int dy_ld, const void* y, int y_ld
     cudaStream_t st = as_stream(s);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st);
     if (e != cudaSuccess) { set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+    if (bns_ok(c, dtype, dy_ld, raw_ld, relu ? y : nullptr, y_ld, n_pix)) {
+        const bool with_y = relu && y;
+        const int nt = with_y ? 3 : 2;
+        const long long n_tiles = cdiv(n_pix, static_cast<int64_t>(BNS_TILE / (c * 2)));
+        const long long cap = 2LL * num_sms();
+        const int grid = static_cast<int>(n_tiles < cap ? n_tiles : cap);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(bn_bwd_reduce_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bns_smem(3, 4096)));
+            cudaFuncSetAttribute(bn_bwd_reduce_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bns_smem(2, 4096)));
+            attr = true;
+        }
+        const __nv_bfloat16 *pdy = reinterpret_cast<const __nv_bfloat16*>(dy), *py = reinterpret_cast<const __nv_bfloat16*>(y),
+                            *praw = reinterpret_cast<const __nv_bfloat16*>(raw);
+        if (with_y)
+            bn_bwd_reduce_stream_kernel<true><<<grid, 256, bns_smem(nt, 2 * c), st>>>(pdy, py, praw, mean, invstd, fsc, fsh, n_pix, c, relu, sums);
+        else
+            bn_bwd_reduce_stream_kernel<false><<<grid, 256, bns_smem(nt, 2 * c), st>>>(pdy, nullptr, praw, mean, invstd, fsc, fsh, n_pix, c, relu, sums);
+        count_launch();
+        return check_launch("bn_bwd_reduce_stream_kernel");
+    }
     const int prows = 256 / cg;
     const int grid = grid_for(cdiv(n_pix, 2), prows, 8);
     const size_t sm = sizeof(float) * 2 * cg * 8;
@@ -737,6 +962,31 @@ static int bn_bwd_apply_impl(const void* dy, int dy_ld, const void* y, int y_ld,
     RTSDS_REQUIRE(dy_ld % 8 == 0 && raw_ld % 8 == 0 && d_raw_ld % 8 == 0 && d_raw_ld >= cg * 8, "bn_bwd_apply: pitches must be multiples of 8");
     RTSDS_REQUIRE(!g_out || (g_ld % 8 == 0 && g_ld >= cg * 8), "bn_bwd_apply: g_out pitch");
     cudaStream_t st = as_stream(s);
+    if (d_raw_dtype == RTSDS_BF16 && d_raw_ld == c && (!g_out || g_ld == c) &&
+        bns_ok(c, dtype, dy_ld, raw_ld, relu ? y : nullptr, y_ld, n_pix)) {
+        const bool with_y = relu && y;
+        const int nt = with_y ? 3 : 2;
+        const long long n_tiles = cdiv(n_pix, static_cast<int64_t>(BNS_TILE / (c * 2)));
+        const long long cap = 2LL * num_sms();
+        const int sgrid = static_cast<int>(n_tiles < cap ? n_tiles : cap);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(bn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bns_smem(3)));
+            cudaFuncSetAttribute(bn_bwd_apply_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bns_smem(2)));
+            attr = true;
+        }
+        const __nv_bfloat16 *pdy = reinterpret_cast<const __nv_bfloat16*>(dy), *py = reinterpret_cast<const __nv_bfloat16*>(y),
+                            *praw = reinterpret_cast<const __nv_bfloat16*>(raw);
+        __nv_bfloat16 *pdr = reinterpret_cast<__nv_bfloat16*>(d_raw), *pg = reinterpret_cast<__nv_bfloat16*>(g_out);
+        if (with_y)
+            bn_bwd_apply_stream_kernel<true><<<sgrid, 256, bns_smem(nt), st>>>(pdy, py, praw, mean, invstd, gamma, sums, fsc, fsh,
+                                                                               n_pix, c, relu, pdr, pg, dgamma, dbeta);
+        else
+            bn_bwd_apply_stream_kernel<false><<<sgrid, 256, bns_smem(nt), st>>>(pdy, nullptr, praw, mean, invstd, gamma, sums, fsc,
+                                                                                fsh, n_pix, c, relu, pdr, pg, dgamma, dbeta);
+        count_launch();
+        return check_launch("bn_bwd_apply_stream_kernel");
+    }
     const int grid = grid_for(n_pix * cg, 256);
 #define BN_APPLY(T, TO)                                                                                                  \
     bn_bwd_apply_kernel<T, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(dy), dy_ld, reinterpret_cast<const T*>(y), \

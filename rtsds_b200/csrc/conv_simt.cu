@@ -264,39 +264,63 @@ unpack_wgrad_kernel(float* __restrict__ dw, int cout, int cin, int cin_src, int 
 
 // ---- batched variants: one launch for many layers (the per-layer kernels above are launch-latency bound) ----
 constexpr int PACK_BATCH = 40;
-struct PackBatch { RtsdsPackJob jobs[PACK_BATCH]; };
+constexpr int PK_CO = 32, PK_ROW = 288;            // tile: 32 output channels x (ci_t * taps <= 288) contiguous OIHW floats
+struct PackBatch { RtsdsPackJob jobs[PACK_BATCH]; int first_block[PACK_BATCH + 1]; int n; };
+__host__ __device__ inline int pack_ci_tile(int taps) {
+    const int t = PK_ROW / taps;
+    return t < 1 ? 1 : (t > 256 ? 256 : t);
+}
+// One block = 32 output channels x ci_t input channels x all taps: the OIHW rows are read coalesced into shared
+// memory once and written out transposed, so neither side of either layout strides through memory.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__ PackBatch b) {
-    const RtsdsPackJob& j = b.jobs[blockIdx.y];
-    T* out = reinterpret_cast<T*>(j.out);
+    __shared__ float s_w[PK_CO][PK_ROW + 1];
+    int ji = 0;
+    while (ji + 1 < b.n && static_cast<int>(blockIdx.x) >= b.first_block[ji + 1]) ++ji;
+    const RtsdsPackJob& j = b.jobs[ji];
+    const int local = blockIdx.x - b.first_block[ji];
+    const int taps = j.taps, ci_t = pack_ci_tile(taps);
+    const int n_ci_tiles = (j.cin_pad + ci_t - 1) / ci_t;
+    const int co0 = (local / n_ci_tiles) * PK_CO, ci0 = (local % n_ci_tiles) * ci_t;
+    const int co_lim = j.kind == 0 ? j.cout_pad : j.ck;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nci = min(ci_t, j.cin - ci0);            // valid input channels of this tile (may be <= 0)
+    const int row = nci > 0 ? nci * taps : 0;
     const float* __restrict__ w = j.w;
+#pragma unroll
+    for (int r = warp; r < PK_CO; r += 8) {
+        const int co = co0 + r;
+        if (co < j.cout) {
+            const float* src = w + (static_cast<long long>(co) * j.cin + ci0) * taps;
+            for (int e = lane; e < row; e += 32) s_w[r][e] = __ldg(src + e);
+        }
+    }
+    __syncthreads();
+    T* out = reinterpret_cast<T*>(j.out);
+    const int ci_n = min(ci_t, j.cin_pad - ci0);       // input channels of this tile that exist in the padded layout
     if (j.kind == 0) {              // [cout_pad][taps][cin_pad]
-        const long long total = static_cast<long long>(j.cout_pad) * j.taps * j.cin_pad;
-        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-             i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const int c = static_cast<int>(i % j.cin_pad);
-            const long long r = i / j.cin_pad;
-            const int t = static_cast<int>(r % j.taps);
-            const int co = static_cast<int>(r / j.taps);
-            const float v = (co < j.cout && c < j.cin) ? w[(static_cast<long long>(co) * j.cin + c) * j.taps + t] : 0.f;
-            out[i] = from_f32<T>(v);
+        const int co_n = min(PK_CO, co_lim - co0);
+        for (int rt = warp; rt < co_n * taps; rt += 8) {
+            const int r = rt / taps, t = rt - r * taps;
+            const bool co_ok = co0 + r < j.cout;
+            T* dst = out + (static_cast<long long>(co0 + r) * taps + t) * j.cin_pad + ci0;
+            for (int c = lane; c < ci_n; c += 32) dst[c] = from_f32<T>((co_ok && c < nci) ? s_w[r][c * taps + t] : 0.f);
         }
     } else {                        // dgrad operand [cin_pad][taps][ck]
-        const long long total = static_cast<long long>(j.cin_pad) * j.taps * j.ck;
-        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-             i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const int co = static_cast<int>(i % j.ck);
-            const long long r = i / j.ck;
-            const int t = static_cast<int>(r % j.taps);
-            const int ci = static_cast<int>(r / j.taps);
-            const float v = (co < j.cout && ci < j.cin) ? w[(static_cast<long long>(co) * j.cin + ci) * j.taps + t] : 0.f;
-            out[i] = from_f32<T>(v);
+        for (int ct = warp; ct < ci_n * taps; ct += 8) {
+            const int c = ct / taps, t = ct - c * taps;
+            const int co = co0 + lane;
+            if (co < co_lim)
+                out[(static_cast<long long>(ci0 + c) * taps + t) * j.ck + co] =
+                    from_f32<T>((co < j.cout && c < nci) ? s_w[lane][c * taps + t] : 0.f);
         }
     }
 }
 
 constexpr int UNPACK_BATCH = 48;
 struct UnpackBatch { RtsdsUnpackJob jobs[UNPACK_BATCH]; int first_block[UNPACK_BATCH + 1]; int n; };
+// Loads, clears and stores are separate loops: no global store sits between two loads, so every load of a phase
+// is in flight at once (the one-loop form serialised a DRAM round trip per element).
 __global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant__ UnpackBatch b) {
     extern __shared__ float s_t[];                  // [taps][UNP_CI + 1]
     int ji = 0;
@@ -308,21 +332,43 @@ __global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant
     const int ci0 = (local - co * chunks) * UNP_CI;
     const int taps = j.taps;
     const int nci = min(UNP_CI, j.cin_src - ci0);
-    float* src = j.dw_packed + static_cast<long long>(co) * taps * j.cin_src;
-    for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
-        const int t = i / nci, c = i - t * nci;
-        float* p = src + static_cast<long long>(t) * j.cin_src + ci0 + c;
-        s_t[t * (UNP_CI + 1) + c] = *p;
-        *p = 0.f;
+    float* src = j.dw_packed + static_cast<long long>(co) * taps * j.cin_src + ci0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rows of nci floats: warp per (tap, 32-channel slice)
+    const int slices = (nci + 31) / 32;
+    for (int u = warp; u < taps * slices; u += 8) {
+        const int t = u / slices, c = (u - t * slices) * 32 + lane;
+        if (c < nci) s_t[t * (UNP_CI + 1) + c] = src[static_cast<long long>(t) * j.cin_src + c];
     }
     __syncthreads();
+    for (int u = warp; u < taps * slices; u += 8) {
+        const int t = u / slices, c = (u - t * slices) * 32 + lane;
+        if (c < nci) src[static_cast<long long>(t) * j.cin_src + c] = 0.f;
+    }
     const int nout = min(nci, j.cin - ci0);
     if (nout <= 0) return;
     float* dst = j.grad + (static_cast<long long>(co) * j.cin + ci0) * taps;
-    for (int i = threadIdx.x; i < taps * nout; i += blockDim.x) {
-        const int c = i / taps, t = i - c * taps;
-        const float v = s_t[t * (UNP_CI + 1) + c];
-        dst[i] = j.accumulate ? dst[i] + v : v;
+    const int total = taps * nout;
+    int c = threadIdx.x / taps, t = threadIdx.x - c * taps;
+    const int dc = 256 / taps, dt = 256 - dc * taps;
+    if (j.accumulate) {
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
+            float old[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) old[k] = i0 + k * 256 < total ? dst[i0 + k * 256] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k * 256 < total) dst[i0 + k * 256] = old[k] + s_t[t * (UNP_CI + 1) + c];
+                c += dc; t += dt;
+                if (t >= taps) { t -= taps; ++c; }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += 256) {
+            dst[i] = s_t[t * (UNP_CI + 1) + c];
+            c += dc; t += dt;
+            if (t >= taps) { t -= taps; ++c; }
+        }
     }
 }
 
@@ -482,17 +528,25 @@ extern "C" int rtsds_pack_conv_weights_batch(const RtsdsPackJob* jobs, int n_job
     RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "pack_conv_weights_batch: bad dtype");
     for (int i = 0; i < n_jobs; ++i) {
         const RtsdsPackJob& j = jobs[i];
-        RTSDS_REQUIRE(j.w && j.out && j.cout > 0 && j.cin > 0 && j.taps > 0 && j.cout_pad >= j.cout && j.cin_pad >= j.cin &&
+        RTSDS_REQUIRE(j.w && j.out && j.cout > 0 && j.cin > 0 && j.taps > 0 && j.taps <= PK_ROW && j.cout_pad >= j.cout && j.cin_pad >= j.cin &&
                           (j.kind == 0 || (j.kind == 1 && j.ck >= j.cout)), "pack_conv_weights_batch: bad job %d", i);
     }
     for (int base = 0; base < n_jobs; base += PACK_BATCH) {
         PackBatch b;
         memset(&b, 0, sizeof(b));
         const int n = n_jobs - base < PACK_BATCH ? n_jobs - base : PACK_BATCH;
-        for (int i = 0; i < n; ++i) b.jobs[i] = jobs[base + i];
-        dim3 grid(48, n);
-        if (dtype == RTSDS_BF16) pack_batch_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(b);
-        else pack_batch_kernel<float><<<grid, 256, 0, as_stream(s)>>>(b);
+        int blocks = 0;
+        for (int i = 0; i < n; ++i) {
+            const RtsdsPackJob& j = jobs[base + i];
+            b.jobs[i] = j;
+            b.first_block[i] = blocks;
+            const int co_lim = j.kind == 0 ? j.cout_pad : j.ck;
+            blocks += static_cast<int>(cdiv(co_lim, PK_CO) * cdiv(j.cin_pad, pack_ci_tile(j.taps)));
+        }
+        b.first_block[n] = blocks;
+        b.n = n;
+        if (dtype == RTSDS_BF16) pack_batch_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(s)>>>(b);
+        else pack_batch_kernel<float><<<blocks, 256, 0, as_stream(s)>>>(b);
         count_launch();
         int rc = check_launch("pack_batch_kernel");
         if (rc != RTSDS_OK) return rc;
