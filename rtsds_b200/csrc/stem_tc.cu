@@ -6,9 +6,14 @@
 // K = 3*7*7 = 147 (padded to 192), the 3x3 weights embedded (zero-padded) in the 7x7 K layout.
 //
 // There is no TMA path for an im2col of a 3-channel NCHW fp32 image, so the A tile is built by
-// 128 gather threads (one output pixel each): 147 L1-cached loads, converted to bf16 and written
-// with 16-byte stores straight into the 128-byte-swizzled K-major UMMA layout (conflict-free thanks
-// to the swizzle).  Persistent CTAs, warp-specialised:
+// 128 gather threads (one output pixel each).  The input patch of the tile ((2*TH+5) x (2*TW+5) x 3
+// floats) is first staged in shared memory with coalesced loads -- prefetched into registers one tile
+// ahead, so its L2/HBM latency hides behind the build of the current tile -- and split by column parity
+// so that the stride-2 window reads are bank-conflict free; the 147 window values of a pixel are then
+// shared-memory loads at compile-time offsets, converted to bf16 and written with 16-byte stores straight
+// into the 128-byte-swizzled K-major UMMA layout.  (Gathering straight from global memory cost one L2
+// round trip per 8 values: 5.4 us per tile, 5x the HBM time of the kernel.)
+// Persistent CTAs, warp-specialised:
 //   warps 0-3  gather (double-buffered A), warp 4 MMA issuer (tcgen05, 2 TMEM accumulators),
 //   warps 5-8  epilogue (tcgen05.ld -> folded BN + ReLU -> bf16 NHWC to both outputs; train mode:
 //              raw outputs + per-channel sum / sum of squares).
@@ -44,19 +49,52 @@ struct StemTcParams {
     float* dw;                 // [128][192] fp32, accumulated
 };
 
-// one thread gathers the 7x7x3 window of output pixel (img, oy, ox) into row `m` of the swizzled tile.
-// Fully unrolled: every k = (c*7 + r)*7 + s is a compile-time constant, so the 8-value staging
-// registers never touch local memory.
-__device__ __forceinline__ void gather_row(const StemTcParams& p, uint8_t* tile, int m, int img, int oy, int ox, bool valid) {
-    const int iy0 = oy * 2 - 3, ix0 = ox * 2 - 3;
-    const float* xi = p.x + static_cast<long long>(img) * 3 * p.h * p.w + static_cast<long long>(iy0) * p.w + ix0;
-    unsigned rmask = 0, cmask = 0;
+// ---- input patch staging ----------------------------------------------------------------------------------
+template <int TW>
+struct Patch {
+    static constexpr int TH = 128 / TW;
+    static constexpr int PH = 2 * TH + 5, PW = 2 * TW + 5;
+    // row pitch / parity-plane offset (floats): lanes of one warp span 32/TW tile rows (2 patch rows apart);
+    // the pitch places those rows in disjoint bank groups
+    static constexpr int RP = TW == 32 ? 72 : (TW == 16 ? 40 : 24);
+    static constexpr int PO = RP / 2;
+    static constexpr int N_EL = 3 * PH * PW;
+    static constexpr int PRE = (N_EL + 127) / 128;       // prefetch registers per gather thread (<= 22)
+    static_assert(3 * PH * RP <= 3072 && PO >= TW + 3, "patch buffer");
+};
+constexpr int S_PATCH_FLOATS = 3072;                 // 12 KiB per staged patch
+constexpr int S_PATCHES = 3;                         // ring: the patch of tile i+2 is in flight while tile i is built
+
+// asynchronous (cp.async) copy of tile t's patch into shared memory, zero-filled outside the image
+template <int TW>
+__device__ __forceinline__ void patch_issue(const StemTcParams& p, int t, int tid, float* patch) {
+    using P = Patch<TW>;
+    const int per = p.tiles_w * p.tiles_h;
+    const int img = t / per;
+    const int r = t - img * per;
+    const int th = r / p.tiles_w;
+    const int iy_base = th * P::TH * 2 - 3, ix_base = (r - th * p.tiles_w) * TW * 2 - 3;
+    const float* xi = p.x + static_cast<long long>(img) * 3 * p.h * p.w;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        if (valid && iy0 + i >= 0 && iy0 + i < p.h) rmask |= 1u << i;
-        if (ix0 + i >= 0 && ix0 + i < p.w) cmask |= 1u << i;
+    for (int k = 0; k < P::PRE; ++k) {
+        const int idx = tid + k * 128;
+        const int c = idx / (P::PH * P::PW), rem = idx - c * (P::PH * P::PW);
+        const int prow = rem / P::PW, pcol = rem - prow * P::PW;
+        const int iy = iy_base + prow, ix = ix_base + pcol;
+        const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        if (idx < P::N_EL)
+            ptx::cp_async_4(patch + (c * P::PH + prow) * P::RP + (pcol & 1) * P::PO + (pcol >> 1),
+                            ok ? xi + (static_cast<long long>(c) * p.h + iy) * p.w + ix : p.x, ok);
     }
-    const long long plane = static_cast<long long>(p.h) * p.w;
+}
+
+// one thread builds row `m` of the swizzled tile from the staged patch.  Fully unrolled: every
+// k = (c*7 + r)*7 + s is a compile-time constant, so are all shared-memory offsets.
+template <int TW>
+__device__ __forceinline__ void gather_row(const float* patch, uint8_t* tile, int m) {
+    using P = Patch<TW>;
+    const int my = m / TW, mx = m - my * TW;
+    const float* pb = patch + 2 * my * P::RP + mx;
 #pragma unroll
     for (int chunk = 0; chunk < SK / 8; ++chunk) {
         float v[8];
@@ -65,8 +103,7 @@ __device__ __forceinline__ void gather_row(const StemTcParams& p, uint8_t* tile,
             const int k = chunk * 8 + e;
             if (k < SK_REAL) {
                 const int c = k / 49, r = (k % 49) / 7, sx = k % 7;
-                const bool ok = ((rmask >> r) & 1u) && ((cmask >> sx) & 1u);
-                v[e] = ok ? __ldg(xi + c * plane + static_cast<long long>(r) * p.w + sx) : 0.f;
+                v[e] = pb[(c * P::PH + r) * P::RP + (sx & 1) * P::PO + (sx >> 1)];
             } else {
                 v[e] = 0.f;
             }
@@ -78,6 +115,34 @@ __device__ __forceinline__ void gather_row(const StemTcParams& p, uint8_t* tile,
         *reinterpret_cast<uint4*>(tile + atom * S_ATOM_BYTES + m * 128 + ((j ^ (m & 7)) << 4)) = u;
     }
 }
+
+// the gather warps' loop: keep two patches in flight, build the current tile, publish it
+#define STEM_GATHER_LOOP(FULL_BAR, EMPTY_BAR, TILE_BASE, EXTRA)                                              \
+    {                                                                                                        \
+        const int m = threadIdx.x;                                                                           \
+        const int gstep = static_cast<int>(gridDim.x);                                                       \
+        for (int k = 0; k < 2; ++k) {                                                                        \
+            if (static_cast<int>(blockIdx.x) + k * gstep < p.tiles_total)                                    \
+                patch_issue<TW>(p, blockIdx.x + k * gstep, m, s_patch + k * S_PATCH_FLOATS);                 \
+            ptx::cp_async_commit();                                                                          \
+        }                                                                                                    \
+        int it = 0;                                                                                          \
+        for (int t = blockIdx.x; t < p.tiles_total; t += gstep, ++it) {                                      \
+            const int buf = it & 1;                                                                          \
+            const uint32_t ph = (it >> 1) & 1;                                                               \
+            ptx::cp_async_wait<1>();            /* this thread's part of tile `it`'s patch has landed */     \
+            asm volatile("bar.sync 2, 128;" ::: "memory");   /* everyone's has; tile it-1 is fully built */  \
+            if (t + 2 * gstep < p.tiles_total)                                                               \
+                patch_issue<TW>(p, t + 2 * gstep, m, s_patch + ((it + 2) % S_PATCHES) * S_PATCH_FLOATS);     \
+            ptx::cp_async_commit();                                                                          \
+            ptx::mbar_wait(&EMPTY_BAR[buf], ph ^ 1);                                                         \
+            EXTRA                                                                                            \
+            gather_row<TW>(s_patch + (it % S_PATCHES) * S_PATCH_FLOATS, TILE_BASE + buf * S_A_BYTES, m);     \
+            ptx::fence_proxy_async();                                                                        \
+            ptx::mbar_arrive(&FULL_BAR[buf]);                                                                \
+        }                                                                                                    \
+        ptx::cp_async_wait<0>();                                                                             \
+    }
 
 __device__ __forceinline__ void tile_coords(const StemTcParams& p, int t, int m, int* img, int* oy, int* ox) {
     const int per = p.tiles_w * p.tiles_h;
@@ -103,14 +168,19 @@ __device__ __forceinline__ float warp_tsum(float (&v)[32], int lane) {
     return v[0];
 }
 
-__global__ void __launch_bounds__(S_THREADS, 1)
-stem_fwd_tc_kernel(const StemTcParams p) {
+struct StemWgMaps { CUtensorMap d_cp, d_sp; };      // [64, ow, oh, n] bf16 each: d_raw (wgrad loads) / y (forward stores)
+
+constexpr int SF_THREADS = 13 * 32;                 // 4 gather + 1 MMA + 8 epilogue warps
+template <int TW>
+__global__ void __launch_bounds__(SF_THREADS, 1)
+stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 128);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_a = smem;                                   // 2 x 48 KiB
     uint8_t* s_b = smem + 2 * S_A_BYTES;                   // 48 KiB: weights [128 rows][192 k], K-major swizzled
-    float* s_scale = reinterpret_cast<float*>(s_b + S_A_BYTES);
+    uint8_t* s_out = s_b + S_A_BYTES;                      // 2 x 16 KiB: bf16 output tiles [128 px][64 ch] (TMA store source)
+    float* s_scale = reinterpret_cast<float*>(s_out + 2 * S_ATOM_BYTES);
     float* s_shift = s_scale + 128;
     float* s_stats = s_shift + 128;                        // [2*128]
     uint64_t* a_full = reinterpret_cast<uint64_t*>(s_stats + 256);      // [2]
@@ -118,24 +188,26 @@ stem_fwd_tc_kernel(const StemTcParams p) {
     uint64_t* d_full = a_empty + 2;                                     // [2]
     uint64_t* d_empty = d_full + 2;                                     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* s_patch = reinterpret_cast<float*>(tmem_slot + 4);          // 3 x 12 KiB staged input patches
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // weights -> smem (swizzled), scale/shift, barriers
-    for (int i = threadIdx.x; i < 128 * (SK / 8); i += S_THREADS) {
+    for (int i = threadIdx.x; i < 128 * (SK / 8); i += SF_THREADS) {
         const int row = i / (SK / 8), chunk = i - row * (SK / 8);
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.wpk + row * SK + chunk * 8));
         const int atom = chunk >> 3, j = chunk & 7;
         *reinterpret_cast<uint4*>(s_b + atom * S_ATOM_BYTES + row * 128 + ((j ^ (row & 7)) << 4)) = u;
     }
-    for (int i = threadIdx.x; i < 128; i += S_THREADS) {
+    for (int i = threadIdx.x; i < 128; i += SF_THREADS) {
         s_scale[i] = p.scale ? p.scale[i] : 1.f;
         s_shift[i] = p.shift ? p.shift[i] : 0.f;
         s_stats[i] = 0.f; s_stats[128 + i] = 0.f;
     }
     if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&maps.d_cp); ptx::prefetch_tmap(&maps.d_sp);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
-            ptx::mbar_init(&d_full[i], 1); ptx::mbar_init(&d_empty[i], 128);
+            ptx::mbar_init(&d_full[i], 1); ptx::mbar_init(&d_empty[i], 256);
         }
         ptx::fence_barrier_init();
     }
@@ -148,18 +220,7 @@ stem_fwd_tc_kernel(const StemTcParams p) {
 
     if (warp < 4) {
         // ================= gather =================
-        const int m = threadIdx.x;                         // row of the tile
-        int it = 0;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            ptx::mbar_wait(&a_empty[buf], ph ^ 1);
-            int img, oy, ox;
-            tile_coords(p, t, m, &img, &oy, &ox);
-            gather_row(p, s_a + buf * S_A_BYTES, m, img, oy, ox, oy < p.oh && ox < p.ow);
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(&a_full[buf]);
-        }
+        STEM_GATHER_LOOP(a_full, a_empty, s_a, )
     } else if (warp == 4) {
         // ================= MMA =================
         if (lane == 0) {
@@ -184,8 +245,18 @@ stem_fwd_tc_kernel(const StemTcParams p) {
         __syncwarp();
     } else {
         // ================= epilogue =================
-        const int q = warp & 3;
+        // Two sets of four warps: set 0 drains the context-path half of the accumulator (columns 0..63), set 1 the
+        // spatial-path half.  Each thread owns one pixel; the bf16 tile is staged in shared memory (swizzled, so
+        // the 16-byte stores are conflict free) and leaves with ONE TMA store per set -- per-thread global
+        // stores of 128-byte-strided rows cost 32 LSU passes per instruction.
+        const int set = (warp - 5) >> 2;                   // 0: context path, 1: spatial path
+        const int q = warp & 3;                            // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;
+        const bool issuer = q == 0 && lane == 0;
+        const bool affine = p.scale != nullptr || p.shift != nullptr || p.relu;
+        uint8_t* stage = s_out + set * S_ATOM_BYTES;
+        const CUtensorMap* omap = set == 0 ? &maps.d_cp : &maps.d_sp;
+        const int bar_id = 3 + set;
         int it = 0;
         for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -193,11 +264,12 @@ stem_fwd_tc_kernel(const StemTcParams p) {
             int img, oy, ox;
             tile_coords(p, t, m, &img, &oy, &ox);
             const bool valid = oy < p.oh && ox < p.ow;
-            const long long pix = (static_cast<long long>(img) * p.oh + oy) * p.ow + ox;
             ptx::mbar_wait(&d_full[buf], ph);
             ptx::tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint4 packed[8];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int c0 = set * 64 + half * 32;
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + buf * 128 + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
                 ptx::tmem_ld_wait();
@@ -215,32 +287,46 @@ stem_fwd_tc_kernel(const StemTcParams p) {
                     atomicAdd(&s_stats[c0 + lane], s1);
                     atomicAdd(&s_stats[128 + c0 + lane], s2);
                 }
-                if (valid) {
-                    __nv_bfloat16* dst = (c0 < 64 ? p.y_cp : p.y_sp) + pix * 64 + (c0 & 63);
+                if (affine) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float xv = v[g * 8 + j] * s_scale[c0 + g * 8 + j] + s_shift[c0 + g * 8 + j];
-                            o[j] = p.relu ? fmaxf(xv, 0.f) : xv;
-                        }
-                        uint4 u;
-                        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-                        u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-                        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+                    for (int j = 0; j < 32; ++j) {
+                        const float xv = fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]);
+                        v[j] = p.relu ? fmaxf(xv, 0.f) : xv;
                     }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                    u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    packed[half * 4 + g] = u;
                 }
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&d_empty[buf]);
+            ptx::mbar_arrive(&d_empty[buf]);               // accumulator is in registers: the MMA warp may reuse it
+            if (issuer) ptx::bulk_wait_read0();            // previous tile's TMA store has read the staging tile
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stage + m * 128 + ((j ^ (m & 7)) << 4)) = packed[j];
+            ptx::fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (issuer) {
+                int i0, y0, x0;
+                tile_coords(p, t, 0, &i0, &y0, &x0);
+                ptx::tma_store_4d(omap, stage, 0, x0, y0, i0);     // clipped at the image border
+                ptx::bulk_commit();
+            }
         }
+        if (issuer) ptx::bulk_wait0();
         if (p.stats_cp) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int i = threadIdx.x - 160;              // 0..127
-            float* dst = i < 64 ? p.stats_cp : p.stats_sp;
-            atomicAdd(&dst[i & 63], s_stats[i]);
-            atomicAdd(&dst[64 + (i & 63)], s_stats[128 + i]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int i = threadIdx.x - 160;              // 0..255
+            if (i < 128) {
+                float* dst = i < 64 ? p.stats_cp : p.stats_sp;
+                atomicAdd(&dst[i & 63], s_stats[i]);
+                atomicAdd(&dst[64 + (i & 63)], s_stats[128 + i]);
+            }
         }
     }
     ptx::tc_fence_before();
@@ -249,8 +335,7 @@ stem_fwd_tc_kernel(const StemTcParams p) {
 }
 
 // ---- weight gradient: dW[128 co][192 k] += sum_pixels d_raw[pix][co] * im2col[pix][k] --------------------
-struct StemWgMaps { CUtensorMap d_cp, d_sp; };      // d_raw [64, ow, oh, n] bf16 each
-
+template <int TW>
 __global__ void __launch_bounds__(S_THREADS, 1)
 stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, SK, 1, 1);     // both operands MN-major, N = 192
@@ -263,6 +348,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams
     uint64_t* empty = a_full + 2;
     uint64_t* d_full = empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+    float* s_patch = reinterpret_cast<float*>(tmem_slot + 2);          // 3 x 12 KiB staged input patches
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&maps.d_cp); ptx::prefetch_tmap(&maps.d_sp);
@@ -278,23 +364,14 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams
     const bool have = static_cast<int>(blockIdx.x) < p.tiles_total;
 
     if (warp < 4) {
-        const int m = threadIdx.x;
-        int it = 0;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            ptx::mbar_wait(&empty[buf], ph ^ 1);
-            int img, oy, ox;
-            tile_coords(p, t, m, &img, &oy, &ox);
-            if (m == 0) {       // d_raw tiles by TMA (out-of-range pixels are zero-filled: they contribute nothing)
+        STEM_GATHER_LOOP(b_full, empty, s_b,
+            if (m == 0) {       /* d_raw tiles by TMA (out-of-range pixels are zero-filled: they contribute nothing) */
+                int img; int oy; int ox;
+                tile_coords(p, t, 0, &img, &oy, &ox);
                 ptx::mbar_expect_tx(&a_full[buf], 2 * S_ATOM_BYTES);
                 ptx::tma_load_4d(s_a + buf * 2 * S_ATOM_BYTES, &maps.d_cp, &a_full[buf], 0, ox, oy, img);
                 ptx::tma_load_4d(s_a + buf * 2 * S_ATOM_BYTES + S_ATOM_BYTES, &maps.d_sp, &a_full[buf], 0, ox, oy, img);
-            }
-            gather_row(p, s_b + buf * S_A_BYTES, m, img, oy, ox, oy < p.oh && ox < p.ow);
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(&b_full[buf]);
-        }
+            })
     } else if (warp == 4) {
         if (lane == 0) {
             int it = 0;
@@ -378,6 +455,34 @@ static int stem_geometry(int n, int h, int w, StemTcParams* p) {
     return RTSDS_OK;
 }
 
+// tensor maps over two NHWC bf16 [n, oh, ow, 64] tensors, one box = one 128-pixel tile (128-byte swizzle)
+static int stem_make_maps(const StemTcParams& p, const void* base_cp, const void* base_sp, StemWgMaps* maps, const char* who) {
+    static EncodeTiledFn2 enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("%s: cuTensorMapEncodeTiled unavailable", who);
+            return RTSDS_ECUDA;
+        }
+        enc = reinterpret_cast<EncodeTiledFn2>(fp);
+    }
+    memset(maps, 0, sizeof(*maps));
+    const void* bases[2] = {base_cp, base_sp};
+    CUtensorMap* ms[2] = {&maps->d_cp, &maps->d_sp};
+    for (int i = 0; i < 2; ++i) {
+        cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(p.ow), static_cast<cuuint64_t>(p.oh), static_cast<cuuint64_t>(p.n)};
+        cuuint64_t strides[3] = {64 * 2, static_cast<cuuint64_t>(p.ow) * 64 * 2, static_cast<cuuint64_t>(p.oh) * p.ow * 64 * 2};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.tile_w), static_cast<cuuint32_t>(p.tile_h), 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[i]), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed: %d", who, static_cast<int>(r)); return RTSDS_ECUDA; }
+    }
+    return RTSDS_OK;
+}
+
 }  // namespace rtsds
 
 using namespace rtsds;
@@ -406,15 +511,22 @@ extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const
     p.x = x; p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.scale = scale; p.shift = shift; p.relu = relu;
     p.stats_cp = stats_cp; p.stats_sp = stats_sp;
     p.y_cp = reinterpret_cast<__nv_bfloat16*>(y_cp); p.y_sp = reinterpret_cast<__nv_bfloat16*>(y_sp);
-    const size_t smem = 1024 + 3 * S_A_BYTES + 512 * 4 + 8 * 8 + 16;
+    StemWgMaps maps;
+    rc = stem_make_maps(p, y_cp, y_sp, &maps, "stem_pair_tc_fwd");
+    if (rc != RTSDS_OK) return rc;
+    const size_t smem = 1024 + 3 * S_A_BYTES + 2 * S_ATOM_BYTES + 512 * 4 + 8 * 8 + 16 + S_PATCHES * S_PATCH_FLOATS * 4;
     static bool done = false;
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("stem_pair_tc_fwd: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         done = true;
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
-    stem_fwd_tc_kernel<<<grid, S_THREADS, smem, as_stream(s)>>>(p);
+    if (p.tile_w == 32) stem_fwd_tc_kernel<32><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
+    else if (p.tile_w == 16) stem_fwd_tc_kernel<16><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
+    else stem_fwd_tc_kernel<8><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
     count_launch();
     return check_launch("stem_fwd_tc_kernel");
 }
@@ -431,40 +543,23 @@ extern "C" int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, con
     rc = stem_geometry(n, h, w, &p);
     if (rc != RTSDS_OK) return rc;
     p.x = x; p.dw = dw_ws;
-    static EncodeTiledFn2 enc = nullptr;
-    if (!enc) {
-        void* fp = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-            set_error("stem_pair_tc_wgrad: cuTensorMapEncodeTiled unavailable");
-            return RTSDS_ECUDA;
-        }
-        enc = reinterpret_cast<EncodeTiledFn2>(fp);
-    }
     StemWgMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    const void* bases[2] = {d_raw_cp, d_raw_sp};
-    CUtensorMap* ms[2] = {&maps.d_cp, &maps.d_sp};
-    for (int i = 0; i < 2; ++i) {
-        cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(p.ow), static_cast<cuuint64_t>(p.oh), static_cast<cuuint64_t>(n)};
-        cuuint64_t strides[3] = {64 * 2, static_cast<cuuint64_t>(p.ow) * 64 * 2, static_cast<cuuint64_t>(p.oh) * p.ow * 64 * 2};
-        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.tile_w), static_cast<cuuint32_t>(p.tile_h), 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
-        CUresult r = enc(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[i]), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("stem_pair_tc_wgrad: cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return RTSDS_ECUDA; }
-    }
-    const size_t smem = 1024 + 2 * S_A_BYTES + 4 * S_ATOM_BYTES + 7 * 8 + 16;
+    rc = stem_make_maps(p, d_raw_cp, d_raw_sp, &maps, "stem_pair_tc_wgrad");
+    if (rc != RTSDS_OK) return rc;
+    const size_t smem = 1024 + 2 * S_A_BYTES + 4 * S_ATOM_BYTES + 7 * 8 + 16 + S_PATCHES * S_PATCH_FLOATS * 4;
     static bool done = false;
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("stem_pair_tc_wgrad: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         done = true;
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
     cudaStream_t st = as_stream(s);
-    stem_wgrad_tc_kernel<<<grid, S_THREADS, smem, st>>>(maps, p);
+    if (p.tile_w == 32) stem_wgrad_tc_kernel<32><<<grid, S_THREADS, smem, st>>>(maps, p);
+    else if (p.tile_w == 16) stem_wgrad_tc_kernel<16><<<grid, S_THREADS, smem, st>>>(maps, p);
+    else stem_wgrad_tc_kernel<8><<<grid, S_THREADS, smem, st>>>(maps, p);
     stem_unpack_kernel<<<static_cast<int>(cdiv(128 * SK, 256)), 256, 0, st>>>(dw_ws, g7_oihw, g3_oihw);
     count_launch(2);
     return check_launch("stem_wgrad_tc kernels");

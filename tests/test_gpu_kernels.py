@@ -348,7 +348,7 @@ def test_ce_argmax_nchw(cuda):
 
 
 # ----------------------------------------------------------------------------- fused tensor-core stems
-@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (1, 512, 1024)])
+@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (1, 512, 1024), (2, 40, 50), (1, 70, 24), (3, 9, 11)])
 @pytest.mark.parametrize("train", [False, True])
 def test_stem_pair_tc(cuda, n, h, w, train):
     g = torch.Generator().manual_seed(h + w)
@@ -377,7 +377,7 @@ def test_stem_pair_tc(cuda, n, h, w, train):
         assert rel_err(nchw(ycp), r7) < 1e-2 and rel_err(nchw(ysp), r3) < 1e-2
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (2, 256, 512)])
+@pytest.mark.parametrize("n,h,w", [(1, 64, 96), (2, 72, 104), (1, 45, 81), (2, 256, 512), (2, 40, 50), (1, 70, 24), (3, 9, 11)])
 def test_stem_pair_tc_wgrad(cuda, n, h, w):
     g = torch.Generator().manual_seed(h * 3 + w)
     x = torch.randn(n, 3, h, w, generator=g)
