@@ -215,8 +215,16 @@ resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld,
 // and block.
 constexpr int FU_COLS = 128, FU_ROWS = 8, FU_CMAX = 20, FU_KR = 3, FU_FC = 20, FU_AP = FU_KR * FU_CMAX + 1;
 
-__global__ void __launch_bounds__(FU_COLS)
-resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
+// CT: compile-time class count (19 = Cityscapes/GTA5, every guard and the class loops resolve statically) or 0 = runtime c.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(FU_COLS, 4)
+resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c_rt, int z_ld, int oh, int ow, float rh, float rw,
                        const long long* __restrict__ target, long long ignore_index, double* acc,
                        long long* __restrict__ pred_out, float* __restrict__ dz) {
     __shared__ float s_z[FU_KR * FU_FC * FU_CMAX];
@@ -224,6 +232,7 @@ resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_l
     __shared__ float s_xl[2 * FU_COLS];
     __shared__ int s_run[4 * FU_FC];          // per source column: [first, last] thread whose i0 / i1 it is
     __shared__ double s_red[3][FU_COLS / 32];
+    const int c = CT ? CT : c_rt;
     const int tid = threadIdx.x;
     const int img = blockIdx.z, oy0 = blockIdx.y * FU_ROWS, ox0 = blockIdx.x * FU_COLS;
     const int oy1 = min(oy0 + FU_ROWS, oh) - 1, ox1 = min(ox0 + FU_COLS, ow) - 1;
@@ -289,31 +298,40 @@ resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c, int z_l
         if (!col_ok) continue;
         const float l0 = (k1 == k0) ? ly.l0 + ly.l1 : ly.l0;     // clamped border row: both weights hit the same source row
         const float l1 = (k1 == k0) ? 0.f : ly.l1;
+        const float l0s = l0 * 1.4426950408889634f, l1s = l1 * 1.4426950408889634f;
         const long long pix = (static_cast<long long>(img) * oh + oy) * ow + ox;
-        const long long t = target ? __ldg(target + pix) : ignore_index;
+        const long long t64 = target ? __ldg(target + pix) : ignore_index;
+        const int t = (t64 == ignore_index || t64 < 0 || t64 >= c) ? -1 : static_cast<int>(t64);   // -1: not counted
         float v[FU_CMAX];
-        float m = -INFINITY;
+        float m = -INFINITY, chk = 0.f;
         int arg = 0;
 #pragma unroll
         for (int ch = 0; ch < FU_CMAX; ++ch) {
             if (ch < c) {
-                v[ch] = l0 * zA[ch] + l1 * zB[ch];
-                if (v[ch] > m || (v[ch] != v[ch] && m == m)) { m = v[ch]; arg = ch; }
+                v[ch] = l0s * zA[ch] + l1s * zB[ch];          // logit * log2(e): same argmax, exp() becomes one ex2
+                chk += v[ch];
+                if (v[ch] > m) { m = v[ch]; arg = ch; }
             }
         }
+        if (chk != chk) {            // a NaN (or inf - inf) among the logits: torch.argmax takes the first NaN as the maximum
+            m = -INFINITY; arg = 0;
+#pragma unroll
+            for (int ch = 0; ch < FU_CMAX; ++ch)
+                if (ch < c && (v[ch] > m || (v[ch] != v[ch] && m == m))) { m = v[ch]; arg = ch; }
+        }
         if (pred_out) pred_out[pix] = arg;
-        if (arg == t) ncorrect += 1.f;
-        if (t == ignore_index || t < 0 || t >= c) continue;
+        if (arg == t64) ncorrect += 1.f;
+        if (t < 0) continue;
         float ssum = 0.f, vt = 0.f;
 #pragma unroll
         for (int ch = 0; ch < FU_CMAX; ++ch) {
             if (ch < c) {
                 if (ch == t) vt = v[ch];
-                v[ch] = __expf(v[ch] - m);
+                v[ch] = ex2_approx(v[ch] - m);
                 ssum += v[ch];
             }
         }
-        loss += m + __logf(ssum) - vt;
+        loss += (m + __log2f(ssum) - vt) * 0.6931471805599453f;
         nvalid += 1.f;
         const float inv = 1.0f / ssum;
 #pragma unroll
@@ -499,9 +517,14 @@ extern "C" int rtsds_resize_ce_fused(const float* z, int n, int h, int w, int c,
     }
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
     dim3 grid(static_cast<unsigned>(cdiv(ow, FU_COLS)), static_cast<unsigned>(cdiv(oh, FU_ROWS)), n);
-    resize_ce_fused_kernel<<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
-                                                              reinterpret_cast<const long long*>(target), ignore_index, acc,
-                                                              reinterpret_cast<long long*>(pred_out), dz_unnorm);
+    if (c == 19)
+        resize_ce_fused_kernel<19><<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
+                                                                      reinterpret_cast<const long long*>(target), ignore_index, acc,
+                                                                      reinterpret_cast<long long*>(pred_out), dz_unnorm);
+    else
+        resize_ce_fused_kernel<0><<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
+                                                                     reinterpret_cast<const long long*>(target), ignore_index, acc,
+                                                                     reinterpret_cast<long long*>(pred_out), dz_unnorm);
     count_launch();
     return check_launch("resize_ce_fused_kernel");
 }
