@@ -243,6 +243,10 @@ int rtsds_stem_s2d_conv_wgrad(const void* P, int n, int oh, int ow, const void* 
 /* nn.MaxPool2d(3, 2, 1[, ceil_mode]) on NHWC. */
 int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype,
                            int ceil_mode, void* y, rtsds_stream_t s);
+/* Training form: also writes idx [n,oh,ow,c/8] uint32 = per channel (one nibble each) the window position
+ * r*3+q of the first maximum, so that the backward pass (rtsds_maxpool3x3s2_bwd_idx) does not re-read x. */
+int rtsds_maxpool3x3s2_fwd_idx(const void* x, int n, int h, int w, int c, int dtype,
+                               int ceil_mode, void* y, uint32_t* idx, rtsds_stream_t s);
 
 /* ------------------------------------------------------------------------
  * BatchNorm helpers (nn.BatchNorm2d, eps/momentum per build_bisenet.py:135-137)
@@ -294,6 +298,8 @@ int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, int dtype, fl
 /* nn.MaxPool2d(3,2,1) backward: gradient goes to the first maximum of each window. */
 int rtsds_maxpool3x3s2_bwd(const void* x, const void* dy, int n, int h, int w, int c, int dtype,
                            int ceil_mode, void* dx, rtsds_stream_t s);
+int rtsds_maxpool3x3s2_bwd_idx(const uint32_t* idx, const void* dy, int n, int h, int w, int c, int dtype,
+                               int ceil_mode, void* dx, rtsds_stream_t s);
 /* weight gradient of a stem conv (x NCHW fp32, d_raw NHWC [n,oh,ow,64]); dw OIHW fp32 accumulated. */
 int rtsds_stem_conv_wgrad(const float* x, const void* d_raw, int d_dtype, int n, int cin, int h,
                           int w, int cout, int k, int stride, int pad, float* dw_oihw,

@@ -86,6 +86,7 @@ SIGNATURES = {
     "rtsds_nchw_to_nhwc": (_I, [_P, _I, _I, _L, _I, _P, _I, _I, _P]),
     "rtsds_nhwc_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _L, _P, _P]),
     "rtsds_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_maxpool3x3s2_fwd_idx": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rtsds_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _I, _P, _P, _P]),
     "rtsds_bn_finalize": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rtsds_scale_shift_act": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
@@ -95,6 +96,7 @@ SIGNATURES = {
     "rtsds_bn_bwd_apply_rawmask": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),
     "rtsds_channel_sum": (_I, [_P, _I, _L, _I, _I, _P, _P]),
     "rtsds_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rtsds_maxpool3x3s2_bwd_idx": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_resize_bwd_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "rtsds_gate_bwd_finish": (_I, [_P, _P, _P, _F, _I, _L, _I, _I, _P, _P]),

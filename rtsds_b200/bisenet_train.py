@@ -348,6 +348,7 @@ class BiSeNetTrainPlan:
         ph, pw = ops.maxpool_out_size(self.cp0.oh), ops.maxpool_out_size(self.cp0.ow)
         self.pool = _Buf(self.buf(n, ph, pw, 64))
         self.pool_shape = (n, ph, pw, 64)
+        self.pool_idx = self.buf(n, ph, pw, 8, dtype=torch.int32)
         self.blocks = []
         x, shape = self.pool, self.pool_shape
         for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
@@ -452,7 +453,7 @@ class BiSeNetTrainPlan:
         self.sp2.forward()
         self.sp3.forward()
         self.cp0.forward(x, conv_done=self.use_tc)
-        ops.maxpool3x3s2(self.cp0.y.t, self.pool.t)
+        ops.maxpool3x3s2(self.cp0.y.t, self.pool.t, False, self.pool_idx)
         for b in self.blocks:
             b["c1"].forward()
             if b["ds"] is not None:
@@ -578,7 +579,8 @@ class BiSeNetTrainPlan:
         # ---- max-pool and the 7x7 stem ----
         n_, ph, pw, _ = self.pool_shape
         dcp0 = _Buf(self.gT, ld=64, dtype=dt)
-        check(lib().rtsds_maxpool3x3s2_bwd(self.cp0.y.ptr, dy.ptr, n, self.cp0.oh, self.cp0.ow, 64, dt, 0, dcp0.ptr, s), "maxpool_bwd")
+        check(lib().rtsds_maxpool3x3s2_bwd_idx(self.pool_idx.data_ptr(), dy.ptr, n, self.cp0.oh, self.cp0.ow, 64, dt, 0, dcp0.ptr, s),
+              "maxpool_bwd_idx")
         self.cp0.backward(self.x, dcp0, gw, wgrad=not self.use_tc)
         # ---- spatial path ----
         d2 = _Buf(self.gA, ld=128, dtype=dt)

@@ -503,6 +503,40 @@ maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int h, int
     }
 }
 
+// Backward from the recorded first-maximum positions (maxpool_idx_kernel): one thread per (input pixel, 8-channel
+// group) gathers from the <= 4 windows that contain it; x is not read at all (4 B of index per 16 B of dy instead).
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_idx_kernel(const uint32_t* __restrict__ idx, const T* __restrict__ dy, int n, int h, int w, int c, int oh, int ow,
+                       T* __restrict__ dx) {
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * h * w * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % cg);
+        long long r = i / cg;
+        const int ix = static_cast<int>(r % w); r /= w;
+        const int iy = static_cast<int>(r % h);
+        const int img = static_cast<int>(r / h);
+        F8 acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+        const int a_lo = iy / 2, a_hi = min((iy + 1) / 2, oh - 1), b_lo = ix / 2, b_hi = min((ix + 1) / 2, ow - 1);
+        for (int oy = a_lo; oy <= a_hi; ++oy) {
+            for (int ox = b_lo; ox <= b_hi; ++ox) {
+                const long long wi = ((static_cast<long long>(img) * oh + oy) * ow + ox) * cg + g;
+                const uint32_t pk = __ldg(idx + wi);
+                const F8 gd = ld8(dy + wi * 8);
+                const uint32_t p = static_cast<uint32_t>((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (((pk >> (4 * j)) & 15u) == p) acc.v[j] += gd.v[j];
+            }
+        }
+        st8(dx + i * 8, acc);
+    }
+}
+
 // ---------------------------------------------------------------- adjoint bilinear resize helpers
 // candidate destination range [lo, hi] that can reference source index s (checked exactly by the caller)
 __device__ __forceinline__ void dst_range(int s, float rscale, int out_size, int* lo, int* hi) {
@@ -1051,6 +1085,25 @@ extern "C" int rtsds_maxpool3x3s2_bwd(const void* x, const void* dy, int n, int 
                "maxpool_bwd");
     count_launch();
     return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int rtsds_maxpool3x3s2_bwd_idx(const uint32_t* idx, const void* dy, int n, int h, int w, int c, int dtype,
+                                          int ceil_mode, void* dx, rtsds_stream_t s) {
+    RTSDS_REQUIRE(idx && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool_bwd_idx: bad argument");
+    auto osz = [&](int in) {
+        int o = ceil_mode ? (in + 2 - 3 + 1) / 2 + 1 : (in + 2 - 3) / 2 + 1;
+        if (ceil_mode && (o - 1) * 2 >= in + 1) --o;
+        return o;
+    };
+    const int oh = osz(h), ow = osz(w);
+    const long long total = static_cast<long long>(n) * h * w * (c / 8);
+    const int grid = grid_for(total, 256, 16);
+    DISPATCH_T(dtype,
+               (maxpool_bwd_idx_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const __nv_bfloat16*>(dy), n, h, w, c, oh, ow, reinterpret_cast<__nv_bfloat16*>(dx))),
+               (maxpool_bwd_idx_kernel<float><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const float*>(dy), n, h, w, c, oh, ow, reinterpret_cast<float*>(dx))),
+               "maxpool_bwd_idx");
+    count_launch();
+    return check_launch("maxpool_bwd_idx_kernel");
 }
 
 extern "C" int rtsds_resize_bwd_nhwc(const void* d_dst, int dst_ld, int dst_coff, int n, int h, int w, int c, int oh, int ow,

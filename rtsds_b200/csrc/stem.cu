@@ -251,6 +251,47 @@ maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int 
     }
 }
 
+// Training form: also records, per 8-channel group, the window position (r*3+q, one nibble per channel) of the FIRST
+// maximum in ATen's row-major scan (a later NaN overrides) -- the backward pass then never touches x.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_idx_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y,
+                   uint32_t* __restrict__ idx) {
+    const int cg = c / 8;
+    const long long total = static_cast<long long>(n) * oh * ow * cg;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % cg);
+        long long r = i / cg;
+        const int ox = static_cast<int>(r % ow); r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int img = static_cast<int>(r / oh);
+        Vec8 m;
+        int pos[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m.v[j] = -INFINITY; pos[j] = 15; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= w) continue;
+                const Vec8 t = load8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (t.v[j] > m.v[j] || pos[j] == 15 || t.v[j] != t.v[j]) { m.v[j] = t.v[j]; pos[j] = dy * 3 + dx; }
+            }
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) packed |= static_cast<uint32_t>(pos[j]) << (4 * j);
+        store8(y + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + g * 8, m);
+        idx[i] = packed;
+    }
+}
+
 }  // namespace rtsds
 
 using namespace rtsds;
@@ -281,8 +322,8 @@ extern "C" int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, i
     return RTSDS_EUNSUP;
 }
 
-extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
-                                      void* y, rtsds_stream_t s) {
+static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode, void* y, uint32_t* idx,
+                            rtsds_stream_t s) {
     RTSDS_REQUIRE(x && y, "maxpool: NULL argument");
     RTSDS_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape (c must be a multiple of 8)");
     RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "maxpool: bad dtype");
@@ -294,6 +335,16 @@ extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c,
     const int oh = osz(h), ow = osz(w);
     const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
     int grid = static_cast<int>(cdiv(total, 256) > 16LL * num_sms() ? 16LL * num_sms() : cdiv(total, 256));
+    if (idx) {
+        if (dtype == RTSDS_BF16)
+            maxpool_idx_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh,
+                                                                              ow, reinterpret_cast<__nv_bfloat16*>(y), idx);
+        else
+            maxpool_idx_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, oh, ow,
+                                                                      reinterpret_cast<float*>(y), idx);
+        count_launch();
+        return check_launch("maxpool_idx_kernel");
+    }
     if (dtype == RTSDS_BF16)
         maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh, ow,
                                                                       reinterpret_cast<__nv_bfloat16*>(y));
@@ -302,6 +353,17 @@ extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c,
                                                               reinterpret_cast<float*>(y));
     count_launch();
     return check_launch("maxpool_kernel");
+}
+
+extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
+                                      void* y, rtsds_stream_t s) {
+    return maxpool_fwd_impl(x, n, h, w, c, dtype, ceil_mode, y, nullptr, s);
+}
+
+extern "C" int rtsds_maxpool3x3s2_fwd_idx(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
+                                          void* y, uint32_t* idx, rtsds_stream_t s) {
+    RTSDS_REQUIRE(idx, "maxpool_fwd_idx: NULL idx");
+    return maxpool_fwd_impl(x, n, h, w, c, dtype, ceil_mode, y, idx, s);
 }
 
 

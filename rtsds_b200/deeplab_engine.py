@@ -308,6 +308,7 @@ class DeepLabTrainPlan(_PlanBase):
         h2, w2, ph, pw = self.out_hw()
         self.pool = _Buf(self.buf(n, ph, pw, 64))
         self.pool_shape = (n, ph, pw, 64)
+        self.pool_idx = self.buf(n, ph, pw, 8, dtype=torch.int32)
         self.blocks = []
         self.layer_first = {}
         x, shape = self.pool, self.pool_shape
@@ -371,7 +372,7 @@ class DeepLabTrainPlan(_PlanBase):
         if self.use_tc:
             ops.stem_s2d_pack(x, self.stem_P)
         self.stem.forward(x)
-        ops.maxpool3x3s2(self.stem.y.t, self.pool.t, True)
+        ops.maxpool3x3s2(self.stem.y.t, self.pool.t, True, self.pool_idx)
         for b in self.blocks:
             b["c1"].forward()
             b["c2"].forward()
@@ -445,7 +446,8 @@ class DeepLabTrainPlan(_PlanBase):
                 ready(self.layer_first[bi])
         # ---- ceil-mode max-pool and the 7x7 stem ----
         dstem = _Buf(self.gT1, ld=64, dtype=dt)
-        check(lib().rtsds_maxpool3x3s2_bwd(self.stem.y.ptr, dy.ptr, n, self.stem.oh, self.stem.ow, 64, dt, 1, dstem.ptr, s), "maxpool_bwd")
+        check(lib().rtsds_maxpool3x3s2_bwd_idx(self.pool_idx.data_ptr(), dy.ptr, n, self.stem.oh, self.stem.ow, 64, dt, 1, dstem.ptr, s),
+              "maxpool_bwd_idx")
         self.stem.backward(self.x, dstem, gw)
         self.flush_unpack()
 

@@ -15,7 +15,7 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc, check, lib
 __all__ = [
     "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ConvDesc", "dtype_code", "torch_dtype",
     "confusion_hist", "argmax_hist", "conv_out_size", "cout_pad", "pack_conv_weight", "conv2d_tc",
-    "conv2d_simt", "stem_conv", "maxpool3x3s2", "bn_fold", "bn_finalize", "scale_shift_act",
+    "conv2d_simt", "stem_conv", "maxpool3x3s2", "maxpool3x3s2_bwd_idx", "bn_fold", "bn_finalize", "scale_shift_act",
     "global_avgpool", "arm_gate", "gate_resize_nhwc", "ffm_head", "resize_to_nchw",
     "resize_ce_argmax_fwd", "resize_ce_bwd", "ce_argmax_nchw_fwd", "launch_count",
 ]
@@ -217,9 +217,22 @@ def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
           "stem_pair_tc_wgrad")
 
 
-def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, ceil_mode: bool = False) -> None:
+def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, ceil_mode: bool = False, idx: torch.Tensor | None = None) -> None:
+    """idx (int32 [n,oh,ow,c/8], training): receives the first-maximum window positions for maxpool3x3s2_bwd_idx."""
     n, h, w, c = x.shape
-    check(lib().rtsds_maxpool3x3s2_fwd(_p(x), n, h, w, c, dtype_code(x.dtype), int(ceil_mode), _p(y), _s()), "maxpool")
+    if idx is None:
+        check(lib().rtsds_maxpool3x3s2_fwd(_p(x), n, h, w, c, dtype_code(x.dtype), int(ceil_mode), _p(y), _s()), "maxpool")
+    else:
+        assert idx.dtype == torch.int32 and idx.numel() == y.numel() // 8
+        check(lib().rtsds_maxpool3x3s2_fwd_idx(_p(x), n, h, w, c, dtype_code(x.dtype), int(ceil_mode), _p(y), _p(idx), _s()),
+              "maxpool_idx")
+
+
+def maxpool3x3s2_bwd_idx(idx: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor, ceil_mode: bool = False) -> None:
+    """dx [n,h,w,c] <- gradient of the max-pool whose forward recorded idx; dy [n,oh,ow,c], same dtype as dx."""
+    n, h, w, c = dx.shape
+    check(lib().rtsds_maxpool3x3s2_bwd_idx(_p(idx), _p(dy), n, h, w, c, dtype_code(dx.dtype), int(ceil_mode), _p(dx), _s()),
+          "maxpool_bwd_idx")
 
 
 def maxpool_out_size(i: int, ceil_mode: bool = False) -> int:

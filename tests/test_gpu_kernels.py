@@ -146,6 +146,27 @@ def test_maxpool_backward(cuda, h, w, c, ceil, dtype):
     assert torch.equal(nchw(dx), x.grad)
 
 
+@pytest.mark.parametrize("h,w,c,ceil", [(32, 48, 64, False), (45, 81, 64, False), (45, 81, 64, True), (65, 129, 64, True), (33, 35, 24, False),
+                                        (18, 70, 128, True), (1, 1, 8, False), (2, 3, 8, True)])
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_maxpool_indexed_forward_backward(cuda, h, w, c, ceil, dtype):
+    """Training pair: the forward records the first-maximum positions, the backward routes dy with them alone."""
+    g = torch.Generator().manual_seed(h * 5 + w)
+    tdt = ops.torch_dtype(dtype)
+    x = torch.randint(0, 5, (2, c, h, w), generator=g).float().requires_grad_(True)
+    y = F.max_pool2d(x, 3, 2, 1, ceil_mode=ceil)
+    dy = torch.randint(-8, 9, y.shape, generator=g).float()
+    y.backward(dy)
+    oh, ow = y.shape[2], y.shape[3]
+    yg = torch.empty(2, oh, ow, c, dtype=tdt, device="cuda")
+    idx = torch.full((2, oh, ow, c // 8), -1, dtype=torch.int32, device="cuda")
+    ops.maxpool3x3s2(nhwc(x.detach(), tdt), yg, ceil, idx)
+    assert torch.equal(nchw(yg), y.detach())
+    dx = torch.full((2, h, w, c), float("nan"), dtype=tdt, device="cuda")
+    ops.maxpool3x3s2_bwd_idx(idx, nhwc(dy, tdt), dx, ceil)
+    assert torch.equal(nchw(dx), x.grad)
+
+
 # ----------------------------------------------------------------------------- batch norm helpers
 def test_bn_fold_and_finalize(cuda):
     g = torch.Generator().manual_seed(2)
