@@ -521,17 +521,26 @@ maxpool_bwd_idx_kernel(const uint32_t* __restrict__ idx, const T* __restrict__ d
         F8 acc;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-        const int a_lo = iy / 2, a_hi = min((iy + 1) / 2, oh - 1), b_lo = ix / 2, b_hi = min((ix + 1) / 2, ow - 1);
-        for (int oy = a_lo; oy <= a_hi; ++oy) {
-            for (int ox = b_lo; ox <= b_hi; ++ox) {
-                const long long wi = ((static_cast<long long>(img) * oh + oy) * ow + ox) * cg + g;
-                const uint32_t pk = __ldg(idx + wi);
-                const F8 gd = ld8(dy + wi * 8);
-                const uint32_t p = static_cast<uint32_t>((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+        // the (up to) 2 x 2 windows containing the pixel; all 8 loads are issued before the first use
+        const int oy0 = iy / 2, ox0 = ix / 2;
+        uint32_t pk[4];
+        F8 gd[4];
+        bool ok[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (((pk >> (4 * j)) & 15u) == p) acc.v[j] += gd.v[j];
-            }
+        for (int k = 0; k < 4; ++k) {
+            const int oy = oy0 + (k >> 1), ox = ox0 + (k & 1);
+            ok[k] = oy < oh && ox < ow && ((k >> 1) == 0 || (iy & 1)) && ((k & 1) == 0 || (ix & 1));
+            const long long wi = ((static_cast<long long>(img) * oh + (ok[k] ? oy : oy0)) * ow + (ok[k] ? ox : ox0)) * cg + g;
+            pk[k] = ok[k] ? __ldg(idx + wi) : 0xffffffffu;
+            gd[k] = ld8(dy + wi * 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int oy = oy0 + (k >> 1), ox = ox0 + (k & 1);
+            const uint32_t p = static_cast<uint32_t>((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ok[k] && ((pk[k] >> (4 * j)) & 15u) == p) acc.v[j] += gd[k].v[j];
         }
         st8(dx + i * 8, acc);
     }
