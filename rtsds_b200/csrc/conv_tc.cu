@@ -54,6 +54,7 @@ struct TcParams {
     int n_taps, kchunks;          // k-blocks = n_taps * kchunks
     int stages;
     int split_k;
+    int cluster_reduce;           // split-K slices of one tile form a thread-block cluster and reduce through DSMEM
     int n_tiles_n, total_tiles, tiles_per_cta;      // persistent kernel: tile id = n_tile * m_tiles + m_tile
     int halo_d, halo_rows, a_stage_bytes, halo_baseoff;   // halo mode: dilation, rows of the halo tile, bytes per A stage
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
@@ -319,6 +320,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int co0 = n0 + c0;
 
+            if (p.cluster_reduce) {      // this CTA's fp32 partial row goes to its own shared memory (the TMA ring is idle now)
+                float* dst = reinterpret_cast<float*>(smem) + row * (BLOCK_N + 4) + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                continue;
+            }
             if (p.split_k > 1) {
                 if (valid) {
                     float* dst = p.partial + (static_cast<long long>(blockIdx.z) * m_total + pix_lin) * p.cout_pad + co0;
@@ -342,6 +350,53 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
             }
         }
+    }
+
+    if (p.cluster_reduce) {
+        // ---- split-K reduction inside the cluster: the `split` CTAs of one output tile hold their partial tiles in
+        // shared memory; CTA r sums rows [r*128/split, (r+1)*128/split) over all ranks through DSMEM and runs the
+        // epilogue on them.  No workspace round trip through L2, no finish kernel.
+        ptx::cluster_sync_all();                    // every partial tile is written
+        if (warp >= 2) {
+            const int split = p.split_k;
+            const int rows_per = TC_BLOCK_M / split;                   // 64 or 32
+            const int rank = static_cast<int>(ptx::cluster_ctarank());
+            const int ntasks = rows_per * (BLOCK_N / 32);
+            for (int task = threadIdx.x - 64; task < ntasks; task += 128) {
+                const int chunk = task / rows_per;
+                const int row = rank * rows_per + (task - chunk * rows_per);
+                const int c0 = chunk * 32;
+                const int hl = row / p.tile_w;
+                const int oh = h0 + hl;
+                const int ow = w0 + (row - hl * p.tile_w);
+                const bool valid = (oh < p.oh) && (ow < p.ow);
+                const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
+                const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
+                const float* src = reinterpret_cast<const float*>(smem) + row * (BLOCK_N + 4) + c0;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                for (int q = 0; q < split; ++q) {                      // slice order: deterministic sum
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 t = ptx::ld_dsmem_f4(src + j, static_cast<uint32_t>(q));
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    }
+                }
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
+            }
+            if (p.stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                    const int co = n0 + i;
+                    if (co < p.cout) {
+                        atomicAdd(&p.stats[co], s_stats[i]);
+                        atomicAdd(&p.stats[p.cout + co], s_stats[BLOCK_N + i]);
+                    }
+                }
+            }
+        }
+        ptx::cluster_sync_all();                    // nobody leaves while a peer still reads its shared memory
     }
 
     // ---- teardown ----
@@ -746,11 +801,20 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.cluster_reduce) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = static_cast<unsigned>(p.split_k);
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tc_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
@@ -927,6 +991,14 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     if (!g_force_stages && m_tiles * n_tiles * split <= num_sms()) stages = 12;
     if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
     while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
+    // split-K of 2 or 4: the slices of a tile run as one thread-block cluster and reduce through distributed shared memory
+    static int cluster_mode = -1;
+    if (cluster_mode < 0) { const char* e = getenv("RTSDS_NO_CLUSTER_SPLITK"); cluster_mode = (e && e[0] == '1') ? 0 : 1; }
+    if (cluster_mode && (split == 2 || split == 4) && block_n >= 32) {
+        const size_t need = static_cast<size_t>(TC_BLOCK_M) * (block_n + 4) * sizeof(float);     // partial tile overlays the ring
+        while (static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) < need) ++stages;
+        if (tc_smem_bytes(block_n, stages) <= 227 * 1024) p.cluster_reduce = 1;
+    }
     p.stages = stages;
     RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv_tc: too many tiles");
 
@@ -974,7 +1046,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     else if (block_n == 32) rc = launch_tc<32>(maps, p, grid, stream);
     else { set_error("conv_tc: block_n %d", block_n); return RTSDS_EUNSUP; }
     if (rc != RTSDS_OK) return rc;
-    if (split > 1) {
+    if (split > 1 && !p.cluster_reduce) {
         const long long total = m_total * (p.cout_pad / 4);
         long long want = cdiv(total, 256);
         int g = static_cast<int>(want > 4LL * num_sms() ? 4LL * num_sms() : want);
