@@ -49,8 +49,8 @@ def run_adversarial(args, rank, world, local):
     gen.rtsds_ddp = dis.rtsds_ddp = world > 1
     ddp.broadcast_module(gen, 0)
     ddp.broadcast_module(dis, 0)
-    gopt = torch.optim.Adam(gen.parameters(), lr=1e-4)
-    dopt = torch.optim.Adam(dis.parameters(), lr=1e-4, weight_decay=1e-4)
+    gopt = torch.optim.Adam(gen.parameters(), lr=1e-4, fused=True)
+    dopt = torch.optim.Adam(dis.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     ce, bce = torch.nn.CrossEntropyLoss(ignore_index=19), torch.nn.BCEWithLogitsLoss()
     n_sets = 3
     g = torch.Generator().manual_seed(42 + rank)

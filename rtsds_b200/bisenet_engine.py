@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import ops, weights_epoch
 from .ops import ACT_NONE, ACT_RELU, BF16, F32
 
 
@@ -315,7 +315,7 @@ class BiSeNetPlan:
             v += p._version
         for b in self.model.buffers():
             v += b._version
-        return (v, self.model.conv.weight.data_ptr())
+        return (v, self.model.conv.weight.data_ptr(), weights_epoch.value())
 
     def refresh_weights(self, force=False):
         ver = self._params_version()

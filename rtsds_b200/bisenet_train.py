@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import ops, weights_epoch
 from .ops import ACT_NONE, ACT_RELU, BF16, F32, _p, check, lib
 
 
@@ -429,7 +429,7 @@ class BiSeNetTrainPlan:
         v = 0
         for p in self.model.parameters():
             v += p._version
-        return (v, self.model.conv.weight.data_ptr())
+        return (v, self.model.conv.weight.data_ptr(), weights_epoch.value())
 
     def refresh_weights(self):
         ver = self._params_version()
@@ -502,6 +502,7 @@ class BiSeNetTrainPlan:
     def backward_from_dz(self, gw, ready=lambda group: None):
         """self.dz[0..2] hold the gradients w.r.t. z, z1, z2 (fp32 NHWC pitch 32).  `ready(group)` is called
         as soon as every parameter gradient of a bucket (rtsds_b200/ddp.py) is final."""
+        weights_epoch.note_backward()          # an optimizer step may follow: every plan re-packs at its next forward
         m, n, dt = self.model, self.n, self.dt
         s = _s()
         a = self.arm

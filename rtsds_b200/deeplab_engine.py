@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import ops, weights_epoch
 from .bisenet_train import _Buf, _ConvBN, _s
 from .ops import ACT_NONE, ACT_RELU, BF16, F32, _p, check, lib
 
@@ -91,7 +91,7 @@ class _PlanBase:
         if not self.train:
             for b in self.model.buffers():
                 v += b._version
-        return (v, self.model.conv1.weight.data_ptr())
+        return (v, self.model.conv1.weight.data_ptr(), weights_epoch.value())
 
     def refresh_weights(self):
         ver = self._params_version()
@@ -400,6 +400,7 @@ class DeepLabTrainPlan(_PlanBase):
 
     def backward_from_dz(self, gw, ready=lambda group: None):
         """self.dz holds the gradient w.r.t. the low-resolution logits z (fp32 NHWC, pitch 32)."""
+        weights_epoch.note_backward()
         n, dt, nc = self.n, self.dt, self.nc
         s = ops._s()
         user_ready = ready

@@ -18,7 +18,7 @@ import ctypes as C
 
 import torch
 
-from . import ops
+from . import ops, weights_epoch
 from .ops import ACT_LRELU, BF16, F32, _p, check, lib
 
 
@@ -131,7 +131,7 @@ class DiscPlan:
 
     # ---------------- weights ----------------
     def _params_version(self):
-        return (sum(p._version for p in self.params), self.params[0].data_ptr())
+        return (sum(p._version for p in self.params), self.params[0].data_ptr(), weights_epoch.value())
 
     def refresh_weights(self):
         ver = self._params_version()
@@ -168,6 +168,7 @@ class DiscPlan:
 
     def backward(self, g, gw, need_dx, g_scale=1.0):
         """g: fp32 [n] = dL/dout.  gw: param -> fp32 grad view (missing = frozen).  Returns dL/dx (fp32 NCHW) or None."""
+        weights_epoch.note_backward()
         s = ops._s()
         dt = self.dt
         last = self.layers[-1]

@@ -312,3 +312,42 @@ def test_pipelined_segmenter_matches_direct_calls(cuda):
             got.append(r.clone())
     got += [r.clone() for r in pipe.drain()]
     assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+
+
+@pytest.mark.parametrize("fused_opt", [False, True])
+def test_weights_repacked_after_any_optimizer_step(cuda, fused_opt):
+    """torch's fused optimizers update parameters WITHOUT bumping the autograd version counters; the plans must still
+    see the new weights (train plan at the next step, eval plan after training) -- rtsds_b200/weights_epoch.py."""
+    from oracle import bisenet_ref, weights
+    x, y = _input(9, 2, 64, 96)
+    m = _model(9, "fp32").train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3, fused=fused_opt)
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        outs = m(x.cuda())
+        sum(torch.nn.functional.cross_entropy(t, y.cuda(), ignore_index=19) for t in outs).backward()
+        opt.step()
+    # train-mode forward with the UPDATED weights must equal the oracle evaluated on them
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        got = m(x.cuda())[0].cpu()
+        want = bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=True)[0]
+    assert _l2_rel(got, want) < 1e-4
+    # and so must the eval plan (it was never run before: also run it twice around one more step)
+    m.eval()
+    with torch.no_grad():
+        e0 = m(x.cuda()).cpu()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        assert _l2_rel(e0, bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=False)) < 1e-4
+    m.train()
+    opt.zero_grad(set_to_none=True)
+    outs = m(x.cuda())
+    sum(torch.nn.functional.cross_entropy(t, y.cuda(), ignore_index=19) for t in outs).backward()
+    opt.step()
+    m.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        e1 = m(x.cuda()).cpu()
+        assert _l2_rel(e1, bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=False)) < 1e-4
+    assert _l2_rel(e1, e0) > 1e-4          # the step did move the weights
