@@ -1158,12 +1158,17 @@ struct WgParams {
     float* dw;
 };
 
-template <int BLOCK_N>     // ci per CTA: 64 or 128
+// TAPS filter taps per CTA share one dy tile (the A operand): each tap has its own x tile (B operand) and its own
+// accumulator columns [tt*BLOCK_N, (tt+1)*BLOCK_N) in TMEM.  TAPS = 3 for the 64-input-channel 3x3 layers: the dy tile
+// crosses L2 -> SM three times instead of nine.
+template <int BLOCK_N, int TAPS>     // ci per CTA: 64, 128 or 256
 __global__ void __launch_bounds__(TC_THREADS)
 wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     constexpr int A_BYTES = 2 * WG_BOX_BYTES;                  // 128 co = two 64-channel boxes
-    constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+    constexpr int B1_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;    // one tap
+    constexpr int B_BYTES = TAPS * B1_BYTES;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N, 1, 1);
+    constexpr uint32_t TMEM_COLS = TAPS * BLOCK_N <= 64 ? 64 : (TAPS * BLOCK_N <= 128 ? 128 : (TAPS * BLOCK_N <= 256 ? 256 : 512));
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1176,8 +1181,8 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tap = blockIdx.y / p.ci_tiles;
-    const int ci0 = (blockIdx.y - tap * p.ci_tiles) * BLOCK_N;
+    const int tap0 = (blockIdx.y / p.ci_tiles) * TAPS;
+    const int ci0 = (blockIdx.y % p.ci_tiles) * BLOCK_N;
     const int co0 = blockIdx.z * TC_BLOCK_M;
     const int t_begin = blockIdx.x * p.tiles_per_split;
     const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
@@ -1185,12 +1190,12 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&maps.a);
-        ptx::prefetch_tmap(&maps.b[p.tap_map[tap]]);
+        ptx::prefetch_tmap(&maps.b[p.tap_map[tap0]]);
         for (int i = 0; i < stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
         ptx::mbar_init(tmem_full_bar, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_slot, BLOCK_N); ptx::tmem_relinquish(); }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -1199,22 +1204,29 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const CUtensorMap* bm = &maps.b[p.tap_map[tap]];
+            // rows 64..127 of the co tile do not exist when cout <= co0 + 64: their box is not loaded at all (the MMA
+            // then reads stale shared memory for those rows, which only reaches accumulator rows nobody stores)
+            const bool hi = co0 + 64 < p.cout;
             for (int t = t_begin; t < t_end; ++t) {
                 const int img = t / tiles_per_img;
                 const int r = t - img * tiles_per_img;
                 const int th = r / p.tiles_w;
                 const int h0 = th * p.tile_h, w0 = (r - th * p.tiles_w) * p.tile_w;
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                ptx::mbar_expect_tx(&full_bar[stage], (hi ? A_BYTES : WG_BOX_BYTES) + B_BYTES);
                 uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_BYTES;
                 uint8_t* sb = smem_b + static_cast<size_t>(stage) * B_BYTES;
                 ptx::tma_load_4d(sa, &maps.a, &full_bar[stage], co0, w0, h0, img);
-                ptx::tma_load_4d(sa + WG_BOX_BYTES, &maps.a, &full_bar[stage], co0 + 64, w0, h0, img);
+                if (hi) ptx::tma_load_4d(sa + WG_BOX_BYTES, &maps.a, &full_bar[stage], co0 + 64, w0, h0, img);
 #pragma unroll
-                for (int j = 0; j < BLOCK_N / 64; ++j)
-                    ptx::tma_load_4d(sb + j * WG_BOX_BYTES, bm, &full_bar[stage], ci0 + j * 64, w0 + p.tap_dw[tap],
-                                     h0 + p.tap_dh[tap], img);
+                for (int tt = 0; tt < TAPS; ++tt) {
+                    const int tap = tap0 + tt;
+                    const CUtensorMap* bm = &maps.b[p.tap_map[tap]];
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N / 64; ++j)
+                        ptx::tma_load_4d(sb + tt * B1_BYTES + j * WG_BOX_BYTES, bm, &full_bar[stage], ci0 + j * 64,
+                                         w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
+                }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -1228,10 +1240,13 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                 const uint32_t sa = ptx::smem_u32(smem_a + static_cast<size_t>(stage) * A_BYTES);
                 const uint32_t sb = ptx::smem_u32(smem_b + static_cast<size_t>(stage) * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BLOCK_M / 16; ++k) {      // 16 pixels (rows) per MMA = 2048 B
-                    const uint64_t da = ptx::umma_desc_mn_sw128(sa + k * 2048, WG_BOX_BYTES);
-                    const uint64_t db = ptx::umma_desc_mn_sw128(sb + k * 2048, WG_BOX_BYTES);
-                    ptx::umma_bf16(tmem_base, da, db, IDESC, (t > t_begin || k > 0) ? 1u : 0u);
+                for (int tt = 0; tt < TAPS; ++tt) {
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_M / 16; ++k) {      // 16 pixels (rows) per MMA = 2048 B
+                        const uint64_t da = ptx::umma_desc_mn_sw128(sa + k * 2048, WG_BOX_BYTES);
+                        const uint64_t db = ptx::umma_desc_mn_sw128(sb + tt * B1_BYTES + k * 2048, WG_BOX_BYTES);
+                        ptx::umma_bf16(tmem_base + tt * BLOCK_N, da, db, IDESC, (t > t_begin || k > 0) ? 1u : 0u);
+                    }
                 }
                 ptx::umma_commit(&empty_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -1245,12 +1260,13 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int cc = 0; cc < TAPS * BLOCK_N; cc += 32) {
+            const int tt = cc / BLOCK_N, c0 = cc - tt * BLOCK_N;
             uint32_t r[32];
-            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, r);
             ptx::tmem_ld_wait();
             if (co < p.cout) {
-                float* dst = p.dw + (static_cast<long long>(co) * p.n_taps + tap) * p.cin + ci0 + c0;
+                float* dst = p.dw + (static_cast<long long>(co) * p.n_taps + tap0 + tt) * p.cin + ci0 + c0;
                 if (ci0 + c0 + 32 <= p.cin) {
                     // 16-byte vector reductions: 8 per thread instead of 32 scalar atomics (cin % 64 == 0 keeps dst aligned)
 #pragma unroll
@@ -1268,19 +1284,19 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, BLOCK_N); }
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int TAPS>
 static int launch_wgrad(const WgMaps& maps, const WgParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (2 + BLOCK_N / 64) * WG_BOX_BYTES + (2 * p.stages + 1) * 8 + 16;
+    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (2 + TAPS * (BLOCK_N / 64)) * WG_BOX_BYTES + (2 * p.stages + 1) * 8 + 16;
     static bool done = false;
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         done = true;
     }
-    wgrad_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    wgrad_tc_kernel<BLOCK_N, TAPS><<<grid, TC_THREADS, smem, st>>>(maps, p);
     count_launch();
     return check_launch("wgrad_tc_kernel");
 }
@@ -1306,7 +1322,11 @@ static int wgrad_run(const TapProblem& t, int cin, int cout, const void* dy, lon
     RTSDS_REQUIRE(tiles_total < (1LL << 30), "conv2d_tc_wgrad: too many tiles");
     p.tiles_total = static_cast<int>(tiles_total);
     const int co_tiles = static_cast<int>(cdiv(cout, TC_BLOCK_M));
-    const long long base = static_cast<long long>(t.n_taps) * p.ci_tiles * co_tiles;
+    // 64-input-channel layers with a multiple of 3 taps: 3 taps per CTA share the dy tile
+    static int multi_tap = -1;
+    if (multi_tap < 0) { const char* e = getenv("RTSDS_NO_WGRAD_MULTITAP"); multi_tap = (e && e[0] == '1') ? 0 : 1; }
+    const int taps_per = (multi_tap && block_n == 64 && t.n_taps % 3 == 0) ? 3 : 1;
+    const long long base = static_cast<long long>(t.n_taps / taps_per) * p.ci_tiles * co_tiles;
     // one CTA per SM is resident (shared memory): aim at whole waves, never a ragged extra one
     long long splits = (base >= num_sms() / 2 ? 1LL : 2LL) * num_sms() / base;
     if (splits > tiles_total) splits = tiles_total;
@@ -1329,13 +1349,14 @@ static int wgrad_run(const TapProblem& t, int cin, int cout, const void* dy, lon
     }
     for (int i = 0; i < 4; ++i)
         if (!t.view[i].used) maps.b[i] = maps.b[first];
-    int stages = block_n == 256 ? 2 : (block_n == 128 ? 3 : 4);
+    int stages = taps_per == 3 ? 2 : (block_n == 256 ? 2 : (block_n == 128 ? 3 : 4));
     if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
     p.stages = stages;
-    dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps * p.ci_tiles), static_cast<unsigned>(co_tiles));
-    if (block_n == 256) return launch_wgrad<256>(maps, p, grid, st);
-    if (block_n == 128) return launch_wgrad<128>(maps, p, grid, st);
-    return launch_wgrad<64>(maps, p, grid, st);
+    dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps / taps_per * p.ci_tiles), static_cast<unsigned>(co_tiles));
+    if (taps_per == 3) return launch_wgrad<64, 3>(maps, p, grid, st);
+    if (block_n == 256) return launch_wgrad<256, 1>(maps, p, grid, st);
+    if (block_n == 128) return launch_wgrad<128, 1>(maps, p, grid, st);
+    return launch_wgrad<64, 1>(maps, p, grid, st);
 }
 
 extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy, float* dw_packed,

