@@ -68,6 +68,7 @@ class BiSeNetPlan:
         self.ws = None
         self._ws_bytes = 0
         self._param_version = None
+        self._n_state = -1
         self.generation = 0
         self.graph = None
         self.side = None
@@ -310,12 +311,11 @@ class BiSeNetPlan:
 
     # ------------------------------------------------------------------ execution
     def _params_version(self):
-        v = 0
-        for p in self.model.parameters():
-            v += p._version
-        for b in self.model.buffers():
-            v += b._version
-        return (v, self.model.conv.weight.data_ptr(), weights_epoch.value())
+        ts = self.__dict__.get("_version_tensors")
+        if ts is None or len(ts) != self._n_state:           # (re)collect on first use; module surgery changes the count
+            ts = list(self.model.parameters()) + list(self.model.buffers())
+            self._version_tensors, self._n_state = ts, len(ts)
+        return (sum([t._version for t in ts]), ts[0].data_ptr(), self.model.conv.weight.data_ptr(), weights_epoch.value())
 
     def refresh_weights(self, force=False):
         ver = self._params_version()
@@ -387,7 +387,9 @@ class BiSeNetPlan:
 def _get_plan(model, x, train):
     plans = model.__dict__.setdefault("_rtsds_plans", {})
     n, _, h, w = x.shape
-    key = (n, h, w, bool(train), model.rtsds_precision, x.device.index)
+    # lane: independent plan instances (own buffers / CUDA graph) so that several frames can be in flight on
+    # different streams (rtsds_b200/serving.py)
+    key = (n, h, w, bool(train), model.rtsds_precision, x.device.index, int(getattr(model, "rtsds_lane", 0)))
     plan = plans.get(key)
     if plan is None:
         plan = BiSeNetPlan(model, n, h, w, bool(train), model.rtsds_precision)

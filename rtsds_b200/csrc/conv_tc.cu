@@ -935,7 +935,9 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
             int bn = 0;
             if ((cp == 64 || cp == 128) && tcp_smem_bytes(cp, 2, kbt, a_stage) <= 227 * 1024) bn = cp;
             const long long mt = static_cast<long long>(t.n_img) * cdiv(t.ow, 8) * cdiv(t.oh, 16);
-            if (bn == 0 || mt * (cp / bn) < 2LL * num_sms()) halo = false;
+            static long long halo_min_tiles = -1;
+            if (halo_min_tiles < 0) { const char* e = getenv("RTSDS_HALO_MIN_TILES"); halo_min_tiles = e ? atoll(e) : 2LL * num_sms(); }
+            if (bn == 0 || mt * (cp / bn) < halo_min_tiles) halo = false;
             else { block_n = bn; p.tile_w = 8; p.tile_h = 16; p.halo_d = halo_d; p.halo_rows = 16 + 2 * halo_d; p.a_stage_bytes = a_stage; p.halo_baseoff = halo_baseoff; }
         }
     }

@@ -13,12 +13,16 @@ from . import ops
 
 
 class PipelinedSegmenter:
-    def __init__(self, model, batch: int, height: int, width: int, depth: int = 3):
+    def __init__(self, model, batch: int, height: int, width: int, depth: int = 3, lanes: int = 1):
+        """depth frames in flight; lanes > 1: consecutive frames run their forward on `lanes` compute streams with one
+        execution plan (buffers, CUDA graph) each, so the latency-bound batch-1 kernels of neighbouring frames overlap."""
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise ops._lib.RtsdsError("PipelinedSegmenter needs a CUDA model: rtsds_b200 has no CPU fallback")
         self.model, self.dev, self.depth = model.eval(), p0.device, depth
+        self.lanes = max(1, min(lanes, depth))
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.s_c = [torch.cuda.Stream(self.dev) for _ in range(self.lanes)] if self.lanes > 1 else [None]
         # one slot more than frames in flight: the buffer handed back by submit() is not reused before the NEXT submit()
         self.slots = slots = depth + 1
         self.x = [torch.empty(batch, 3, height, width, dtype=torch.float32, device=self.dev) for _ in range(slots)]
@@ -37,18 +41,26 @@ class PipelinedSegmenter:
         if len(self.pending) == self.depth:
             out = self._pop()
         k = self.i % self.slots
+        lane = self.i % self.lanes
         self.i += 1
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_done[k])              # the forward that read this input slot has finished
             self.x[k].copy_(host_image, non_blocking=True)
             self.ev_in[k].record(self.s_in)
-        cur.wait_event(self.ev_in[k])
-        cur.wait_event(self.ev_out[k])                          # the previous prediction in this slot has left the device
-        with torch.no_grad():
-            logits = self.model(self.x[k])
+        cs = self.s_c[lane] if self.lanes > 1 else cur
+        if cs is not cur:
+            cs.wait_stream(cur)                                 # whatever the caller queued before this frame (weight updates)
+        cs.wait_event(self.ev_in[k])
+        cs.wait_event(self.ev_out[k])                           # the previous prediction in this slot has left the device
+        with torch.no_grad(), torch.cuda.stream(cs):
+            self.model.rtsds_lane = lane
+            try:
+                logits = self.model(self.x[k])
+            finally:
+                self.model.rtsds_lane = 0
             ops.argmax_hist(logits, None, None, self.pred[k])
-        self.ev_done[k].record(cur)
+            self.ev_done[k].record(cs)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])
             self.host[k].copy_(self.pred[k], non_blocking=True)

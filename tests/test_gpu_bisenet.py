@@ -301,16 +301,18 @@ def test_fused_ce_matches_stock_criterion_path(cuda):
             assert _l2_rel(res[1][2][k], res[0][2][k]) < 5e-3, k
 
 
-def test_pipelined_segmenter_matches_direct_calls(cuda):
-    """rtsds_b200.serving.PipelinedSegmenter returns, in order, exactly what model(x).argmax(1) gives frame by frame."""
+@pytest.mark.parametrize("depth,lanes", [(3, 1), (4, 2), (3, 3)])
+def test_pipelined_segmenter_matches_direct_calls(cuda, depth, lanes):
+    """rtsds_b200.serving.PipelinedSegmenter returns, in order, exactly what model(x).argmax(1) gives frame by frame --
+    also with several frames computing concurrently on their own streams / execution plans (lanes > 1)."""
     from rtsds_b200.serving import PipelinedSegmenter
 
     m = _model(9, "bf16").eval()
     g = torch.Generator().manual_seed(3)
-    frames = [torch.randn(1, 3, 128, 256, generator=g).pin_memory() for _ in range(7)]
+    frames = [torch.randn(1, 3, 128, 256, generator=g).pin_memory() for _ in range(11)]
     with torch.no_grad():
         want = [m(f.cuda()).argmax(1).cpu() for f in frames]
-    pipe = PipelinedSegmenter(m, 1, 128, 256, depth=3)
+    pipe = PipelinedSegmenter(m, 1, 128, 256, depth=depth, lanes=lanes)
     got = []
     for f in frames:
         r = pipe.submit(f)
