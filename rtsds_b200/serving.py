@@ -43,28 +43,31 @@ class PipelinedSegmenter:
         k = self.i % self.slots
         lane = self.i % self.lanes
         self.i += 1
+        # torch.cuda.stream() contexts cost ~15 us of Python each: switch streams with set_stream and restore at the end
         cur = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(self.s_in):
+        try:
+            torch.cuda.set_stream(self.s_in)
             self.s_in.wait_event(self.ev_done[k])              # the forward that read this input slot has finished
             self.x[k].copy_(host_image, non_blocking=True)
             self.ev_in[k].record(self.s_in)
-        cs = self.s_c[lane] if self.lanes > 1 else cur
-        if cs is not cur:
-            cs.wait_stream(cur)                                 # whatever the caller queued before this frame (weight updates)
-        cs.wait_event(self.ev_in[k])
-        cs.wait_event(self.ev_out[k])                           # the previous prediction in this slot has left the device
-        with torch.no_grad(), torch.cuda.stream(cs):
+            cs = self.s_c[lane] if self.lanes > 1 else cur
+            if cs is not cur:
+                cs.wait_stream(cur)                             # whatever the caller queued before this frame (weight updates)
+            cs.wait_event(self.ev_in[k])
+            cs.wait_event(self.ev_out[k])                       # the previous prediction in this slot has left the device
+            torch.cuda.set_stream(cs)
             self.model.rtsds_lane = lane
-            try:
+            with torch.no_grad():
                 logits = self.model(self.x[k])
-            finally:
-                self.model.rtsds_lane = 0
-            ops.argmax_hist(logits, None, None, self.pred[k])
+                ops.argmax_hist(logits, None, None, self.pred[k])
             self.ev_done[k].record(cs)
-        with torch.cuda.stream(self.s_out):
+            torch.cuda.set_stream(self.s_out)
             self.s_out.wait_event(self.ev_done[k])
             self.host[k].copy_(self.pred[k], non_blocking=True)
             self.ev_out[k].record(self.s_out)
+        finally:
+            self.model.rtsds_lane = 0
+            torch.cuda.set_stream(cur)
         self.pending.append(k)
         return out
 
