@@ -285,15 +285,18 @@ gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int sr
 }
 
 // ---------------------------------------------------------------- FFM attention + final 1x1 conv
-constexpr int FFM_MAX_C = 32;
+constexpr int FFM_MAX_C = 32, FFM_THREADS = 128, FFM_PX = 32;
+// One block = tiles of 32 pixels: features are staged (coalesced) in shared memory with the attention applied, four
+// threads share a pixel and take every 4th output channel of the final 1x1 conv, results leave coalesced.
 template <typename T>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(FFM_THREADS)
 ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ pooled, long long hw, int c,
                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
                 float* attn_out, float* __restrict__ z, int z_ld) {
     __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C];
     __shared__ float s_w[FFM_MAX_C * FFM_MAX_C], s_b[FFM_MAX_C];
+    __shared__ float s_g[FFM_PX][FFM_MAX_C + 1], s_o[FFM_PX][FFM_MAX_C + 1];
     const int img = blockIdx.y;
     const int t = threadIdx.x;
     const float* pp = pooled + static_cast<long long>(img) * c;
@@ -310,32 +313,34 @@ ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ poo
         s_a[t] = a;
         if (attn_out && blockIdx.x == 0) attn_out[static_cast<long long>(img) * c + t] = a;
     }
-    __syncthreads();
-    // fold g = f*a + f into the 1x1 conv: W'[o][k] = Wc[o][k]; applied to g computed per pixel
-    for (int i = t; i < c * c; i += blockDim.x) s_w[i] = wc ? wc[i] : 0.f;
+    // g = f*a + f is folded into the operand of the 1x1 conv
+    for (int i = t; i < c * c; i += FFM_THREADS) s_w[i] = wc ? wc[i] : 0.f;
     if (t < c) s_b[t] = (wc && bc) ? bc[t] : 0.f;
     __syncthreads();
-    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + t; p < hw;
-         p += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const T* fp = f + (static_cast<long long>(img) * hw + p) * f_ld;
-        float g[FFM_MAX_C];
-#pragma unroll
-        for (int k = 0; k < FFM_MAX_C; ++k) {
-            if (k < c) { const float v = to_f32(fp[k]); g[k] = v * s_a[k] + v; } else g[k] = 0.f;
+    const long long n_tiles = (hw + FFM_PX - 1) / FFM_PX;
+    const int px = t >> 2, oq = t & 3;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p0 = tile * FFM_PX;
+        for (int i = t; i < FFM_PX * FFM_MAX_C; i += FFM_THREADS) {
+            const int q = i >> 5, k = i & 31;
+            float v = 0.f;
+            if (k < c && p0 + q < hw) v = to_f32(f[(static_cast<long long>(img) * hw + p0 + q) * f_ld + k]);
+            s_g[q][k] = k < c ? fmaf(v, s_a[k], v) : 0.f;
         }
-        float* zp = z + (static_cast<long long>(img) * hw + p) * z_ld;
+        __syncthreads();
         if (wc) {
-            for (int o = 0; o < c; ++o) {
+            for (int o = oq; o < c; o += 4) {
                 float acc = s_b[o];
-#pragma unroll
-                for (int k = 0; k < FFM_MAX_C; ++k)
-                    if (k < c) acc = fmaf(s_w[o * c + k], g[k], acc);
-                zp[o] = acc;
+                for (int k = 0; k < c; ++k) acc = fmaf(s_w[o * c + k], s_g[px][k], acc);
+                s_o[px][o] = acc;
             }
         } else {
-#pragma unroll
-            for (int k = 0; k < FFM_MAX_C; ++k)
-                if (k < c) zp[k] = g[k];
+            for (int o = oq; o < c; o += 4) s_o[px][o] = s_g[px][o];
+        }
+        __syncthreads();
+        for (int i = t; i < FFM_PX * FFM_MAX_C; i += FFM_THREADS) {
+            const int q = i >> 5, k = i & 31;
+            if (k < c && p0 + q < hw) z[(static_cast<long long>(img) * hw + p0 + q) * z_ld + k] = s_o[q][k];
         }
     }
 }
@@ -560,15 +565,15 @@ extern "C" int rtsds_ffm_head(const void* f, int f_dtype, int f_ld, const float*
                               const float* bc, float* attn_out, float* z, int z_ld, rtsds_stream_t s) {
     RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && z, "ffm_head: NULL argument");
     RTSDS_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= FFM_MAX_C && f_ld >= c && z_ld >= c, "ffm_head: bad shape");
-    long long bx = cdiv(hw, 64);
-    const long long cap = cdiv(16LL * num_sms(), n);
+    long long bx = cdiv(hw, FFM_PX);
+    const long long cap = cdiv(8LL * num_sms(), n);
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), n);
     if (f_dtype == RTSDS_BF16)
-        ffm_head_kernel<__nv_bfloat16><<<grid, 64, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(f), f_ld, pooled, hw,
+        ffm_head_kernel<__nv_bfloat16><<<grid, FFM_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(f), f_ld, pooled, hw,
                                                                        c, w1, b1, w2, b2, wc, bc, attn_out, z, z_ld);
     else if (f_dtype == RTSDS_F32)
-        ffm_head_kernel<float><<<grid, 64, 0, as_stream(s)>>>(reinterpret_cast<const float*>(f), f_ld, pooled, hw, c, w1, b1, w2,
+        ffm_head_kernel<float><<<grid, FFM_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const float*>(f), f_ld, pooled, hw, c, w1, b1, w2,
                                                                b2, wc, bc, attn_out, z, z_ld);
     else { set_error("ffm_head: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
