@@ -508,16 +508,16 @@ maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int h, int
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_idx_kernel(const uint32_t* __restrict__ idx, const T* __restrict__ dy, int n, int h, int w, int c, int oh, int ow,
-                       T* __restrict__ dx) {
+                       T* __restrict__ dx, Div3 dv) {
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * h * w * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % cg);
-        long long r = i / cg;
-        const int ix = static_cast<int>(r % w); r /= w;
-        const int iy = static_cast<int>(r % h);
-        const int img = static_cast<int>(r / h);
+        unsigned ug, ux, uy;
+        unsigned r = fdivmod(static_cast<unsigned>(i), dv.a, &ug);
+        r = fdivmod(r, dv.b, &ux);
+        const int img = static_cast<int>(fdivmod(r, dv.c, &uy));
+        const int g = static_cast<int>(ug), ix = static_cast<int>(ux), iy = static_cast<int>(uy);
         F8 acc;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
@@ -579,11 +579,40 @@ resize_bwd_nhwc_kernel(const T* __restrict__ d_dst, int dst_ld, int dst_coff, in
         F8 acc;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+        // column weights once per thread; per contributing destination row the loads go out four at a time
+        constexpr int RB_MAXC = 12;
+        float wxs[RB_MAXC];
+#pragma unroll
+        for (int k = 0; k < RB_MAXC; ++k) {
+            const int ox = xlo + k;
+            float wx = 0.f;
+            if (ox <= xhi) {
+                const Lerp lx = lerp_src(ox, rw, w);
+                wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
+            }
+            wxs[k] = wx;
+        }
         for (int oy = ylo; oy <= yhi; ++oy) {
             const Lerp ly = lerp_src(oy, rh, h);
             const float wy = (ly.i0 == y ? ly.l0 : 0.f) + (ly.i1 == y ? ly.l1 : 0.f);
             if (wy == 0.f) continue;
-            for (int ox = xlo; ox <= xhi; ++ox) {
+            const T* rowp = d_dst + ((static_cast<long long>(img) * oh + oy) * ow + xlo) * dst_ld + dst_coff + g8 * 8;
+#pragma unroll
+            for (int k0 = 0; k0 < RB_MAXC; k0 += 4) {
+                F8 g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (wxs[k0 + k] != 0.f) g[k] = ld8(rowp + static_cast<long long>(k0 + k) * dst_ld);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (wxs[k0 + k] != 0.f) {
+                        const float wgt = wy * wxs[k0 + k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(wgt, g[k].v[j], acc.v[j]);
+                    }
+                }
+            }
+            for (int ox = xlo + RB_MAXC; ox <= xhi; ++ox) {      // upsampling factors above ~4.5: the rest of the range
                 const Lerp lx = lerp_src(ox, rw, w);
                 const float wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
                 if (wx == 0.f) continue;
@@ -1106,10 +1135,12 @@ extern "C" int rtsds_maxpool3x3s2_bwd_idx(const uint32_t* idx, const void* dy, i
     };
     const int oh = osz(h), ow = osz(w);
     const long long total = static_cast<long long>(n) * h * w * (c / 8);
+    RTSDS_REQUIRE(total < (1LL << 31), "maxpool_bwd_idx: tensor too large");
     const int grid = grid_for(total, 256, 16);
+    const Div3 dv = {make_fastdiv(c / 8), make_fastdiv(w), make_fastdiv(h)};
     DISPATCH_T(dtype,
-               (maxpool_bwd_idx_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const __nv_bfloat16*>(dy), n, h, w, c, oh, ow, reinterpret_cast<__nv_bfloat16*>(dx))),
-               (maxpool_bwd_idx_kernel<float><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const float*>(dy), n, h, w, c, oh, ow, reinterpret_cast<float*>(dx))),
+               (maxpool_bwd_idx_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const __nv_bfloat16*>(dy), n, h, w, c, oh, ow, reinterpret_cast<__nv_bfloat16*>(dx), dv)),
+               (maxpool_bwd_idx_kernel<float><<<grid, 256, 0, as_stream(s)>>>(idx, reinterpret_cast<const float*>(dy), n, h, w, c, oh, ow, reinterpret_cast<float*>(dx), dv)),
                "maxpool_bwd_idx");
     count_launch();
     return check_launch("maxpool_bwd_idx_kernel");

@@ -59,6 +59,30 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 
 // Bilinear source index, align_corners=False, as ATen's
 // area_pixel_compute_source_index (negative source clamped to 0).
+// Division by a runtime constant as multiply + shift (exact for n < 2^31): the index decompositions of the grid-stride
+// kernels otherwise cost several 64-bit divisions per 16 bytes moved.
+struct FastDiv { unsigned d, mul, shr; };
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    f.shr = 31 + l;
+    f.mul = static_cast<unsigned>(((1ull << f.shr) + d - 1) / d);
+    if (d == 1) { f.mul = 0; f.shr = 0; }
+    return f;
+}
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) {
+    return f.d == 1 ? n : static_cast<unsigned>((static_cast<unsigned long long>(n) * f.mul) >> f.shr);
+}
+struct Div3 { FastDiv a, b, c; };
+// n -> (n / d, n % d)
+__device__ __forceinline__ unsigned fdivmod(unsigned n, const FastDiv& f, unsigned* rem) {
+    const unsigned q = fdiv(n, f);
+    *rem = n - q * f.d;
+    return q;
+}
+
 struct Lerp { int i0, i1; float l0, l1; };
 __device__ __forceinline__ Lerp lerp_src(int dst, float rscale, int in_size) {
     float r = rscale * (static_cast<float>(dst) + 0.5f) - 0.5f;

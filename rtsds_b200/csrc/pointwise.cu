@@ -255,16 +255,17 @@ __device__ __forceinline__ void st8(float* p, const V8& r) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int src_ld, const float* __restrict__ gate,
-                   int oh, int ow, float rh, float rw, T* __restrict__ dst, int dst_ld, int dst_coff) {
+                   int oh, int ow, float rh, float rw, T* __restrict__ dst, int dst_ld, int dst_coff, FastDiv dcg, FastDiv dow,
+                   FastDiv doh) {
     const int cg = c / 8;
-    const long long total = static_cast<long long>(n) * oh * ow * cg;
+    const long long total = static_cast<long long>(n) * oh * ow * cg;          // < 2^31 (host check)
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g8 = static_cast<int>(i % cg);
-        long long r = i / cg;
-        const int ox = static_cast<int>(r % ow); r /= ow;
-        const int oy = static_cast<int>(r % oh);
-        const int img = static_cast<int>(r / oh);
+        unsigned ug, ux, uy;
+        unsigned r = fdivmod(static_cast<unsigned>(i), dcg, &ug);
+        r = fdivmod(r, dow, &ux);
+        const int img = static_cast<int>(fdivmod(r, doh, &uy));
+        const int g8 = static_cast<int>(ug), ox = static_cast<int>(ux), oy = static_cast<int>(uy);
         const Lerp ly = lerp_src(oy, rh, h), lx = lerp_src(ox, rw, w);
         const T* b = src + static_cast<long long>(img) * h * w * src_ld + g8 * 8;
         const V8 p00 = ld8(b + (static_cast<long long>(ly.i0) * w + lx.i0) * src_ld);
@@ -547,14 +548,16 @@ extern "C" int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int 
     RTSDS_REQUIRE(c > 0 && c % 8 == 0 && src_ld >= c && dst_ld >= dst_coff + c, "gate_resize_nhwc: bad channel layout");
     RTSDS_REQUIRE(src_ld % 8 == 0 && dst_ld % 8 == 0 && dst_coff % 8 == 0, "gate_resize_nhwc: pitches/offset must be multiples of 8");
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    RTSDS_REQUIRE(static_cast<long long>(n) * oh * ow * (c / 8) < (1LL << 31), "gate_resize_nhwc: tensor too large");
     const int grid = grid_for(static_cast<long long>(n) * oh * ow * (c / 8), 256);
     if (dtype == RTSDS_BF16)
         gate_resize_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(src), n, h, w, c,
                                                                           src_ld, gate, oh, ow, rh, rw,
-                                                                          reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff);
+                                                                          reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff,
+                                                                          make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh));
     else if (dtype == RTSDS_F32)
         gate_resize_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(src), n, h, w, c, src_ld, gate,
-                                                                  oh, ow, rh, rw, reinterpret_cast<float*>(dst), dst_ld, dst_coff);
+                                                                  oh, ow, rh, rw, reinterpret_cast<float*>(dst), dst_ld, dst_coff, make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh));
     else { set_error("gate_resize_nhwc: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
     return check_launch("gate_resize_kernel");

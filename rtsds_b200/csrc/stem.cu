@@ -221,16 +221,16 @@ __device__ __forceinline__ void store8(float* p, const Vec8& r) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y) {
+maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y, Div3 dv) {
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % cg);
-        long long r = i / cg;
-        const int ox = static_cast<int>(r % ow); r /= ow;
-        const int oy = static_cast<int>(r % oh);
-        const int img = static_cast<int>(r / oh);
+        unsigned ug, ux, uy;
+        unsigned r = fdivmod(static_cast<unsigned>(i), dv.a, &ug);
+        r = fdivmod(r, dv.b, &ux);
+        const int img = static_cast<int>(fdivmod(r, dv.c, &uy));
+        const int g = static_cast<int>(ug), ox = static_cast<int>(ux), oy = static_cast<int>(uy);
         Vec8 m;
 #pragma unroll
         for (int j = 0; j < 8; ++j) m.v[j] = -INFINITY;
@@ -256,16 +256,16 @@ maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_idx_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y,
-                   uint32_t* __restrict__ idx) {
+                   uint32_t* __restrict__ idx, Div3 dv) {
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % cg);
-        long long r = i / cg;
-        const int ox = static_cast<int>(r % ow); r /= ow;
-        const int oy = static_cast<int>(r % oh);
-        const int img = static_cast<int>(r / oh);
+        unsigned ug, ux, uy;
+        unsigned r = fdivmod(static_cast<unsigned>(i), dv.a, &ug);
+        r = fdivmod(r, dv.b, &ux);
+        const int img = static_cast<int>(fdivmod(r, dv.c, &uy));
+        const int g = static_cast<int>(ug), ox = static_cast<int>(ux), oy = static_cast<int>(uy);
         Vec8 m;
         int pos[8];
 #pragma unroll
@@ -334,23 +334,25 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
     };
     const int oh = osz(h), ow = osz(w);
     const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
+    RTSDS_REQUIRE(total < (1LL << 31), "maxpool: tensor too large");
     int grid = static_cast<int>(cdiv(total, 256) > 16LL * num_sms() ? 16LL * num_sms() : cdiv(total, 256));
+    const Div3 dv = {make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh)};
     if (idx) {
         if (dtype == RTSDS_BF16)
             maxpool_idx_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh,
-                                                                              ow, reinterpret_cast<__nv_bfloat16*>(y), idx);
+                                                                              ow, reinterpret_cast<__nv_bfloat16*>(y), idx, dv);
         else
             maxpool_idx_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, oh, ow,
-                                                                      reinterpret_cast<float*>(y), idx);
+                                                                      reinterpret_cast<float*>(y), idx, dv);
         count_launch();
         return check_launch("maxpool_idx_kernel");
     }
     if (dtype == RTSDS_BF16)
         maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh, ow,
-                                                                      reinterpret_cast<__nv_bfloat16*>(y));
+                                                                      reinterpret_cast<__nv_bfloat16*>(y), dv);
     else
         maxpool_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, oh, ow,
-                                                              reinterpret_cast<float*>(y));
+                                                              reinterpret_cast<float*>(y), dv);
     count_launch();
     return check_launch("maxpool_kernel");
 }
