@@ -322,7 +322,7 @@ def run_infer(args, rank, world, local):
         # every frame is still copied in from pinned host memory and its prediction map copied back, inside the timed region
         from rtsds_b200.serving import PipelinedSegmenter
 
-        pipe = PipelinedSegmenter(model, 1, H, W, depth=3 if lanes == 1 else 4, lanes=lanes)
+        pipe = PipelinedSegmenter(model, 1, H, W, depth=3 if lanes == 1 else lanes + 2, lanes=lanes)
         checksum = 0
         for i in range(6):
             pipe.submit(host[i % n_inputs])
@@ -383,7 +383,7 @@ def run_infer(args, rank, world, local):
                           "note": "one frame at a time, back to back on one stream (= the per-frame latency)"},
         "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                 "d2h_bytes_per_step": H * W * 8, "ms_per_step": round(e2e_ms / K, 4),
-                "how": f"PipelinedSegmenter ({3 if lanes == 1 else 4} frames in flight; H2D / forward+argmax on {lanes} compute streams / D2H on separate streams), wall clock incl. final drain",
+                "how": f"PipelinedSegmenter ({3 if lanes == 1 else lanes + 2} frames in flight; H2D / forward+argmax on {lanes} compute streams / D2H on separate streams), wall clock incl. final drain",
                 "serial_fps": round(world * K / (e2e_serial_ms / 1e3), 2), "serial_ms_per_step": round(e2e_serial_ms / K, 4)},
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
@@ -462,7 +462,7 @@ def main():
     ap.add_argument("--disc", default="tiny", choices=["tiny", "full"], help="discriminator of the adversarial workload")
     ap.add_argument("--stock", action="store_true", help="adversarial workload: the reference's exact call sequence instead of the fused fast paths")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
-    ap.add_argument("--lanes", type=int, default=2, help="inference: concurrent batch-1 streams of the multi-stream / pipelined measurements")
+    ap.add_argument("--lanes", type=int, default=3, help="inference: concurrent batch-1 streams of the multi-stream / pipelined measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
