@@ -19,16 +19,35 @@ from . import ops
 from .ops import _p, check, lib
 
 
+_MAX_SLOTS = 2
+_stamp = 0
+
+
 def _get_train_plan(model, x):
+    """One train plan per input shape; a second one only when the first still holds the activations of a forward whose
+    backward has not run (train.py:199-213 with equal source / target sizes: two generator forwards, one backward)."""
     from .bisenet_train import BiSeNetTrainPlan
 
+    global _stamp
     plans = model.__dict__.setdefault("_rtsds_train_plans", {})
     n, _, h, w = x.shape
-    key = (n, h, w, model.rtsds_precision, x.device.index)
-    plan = plans.get(key)
-    if plan is None:
-        plan = BiSeNetTrainPlan(model, n, h, w, model.rtsds_precision)
-        plans[key] = plan
+    base = (n, h, w, model.rtsds_precision, x.device.index)
+    oldest = None
+    for slot in range(_MAX_SLOTS):
+        plan = plans.get(base + (slot,))
+        if plan is None:
+            plan = BiSeNetTrainPlan(model, n, h, w, model.rtsds_precision)
+            plan.awaiting_backward = False
+            plans[base + (slot,)] = plan
+            break
+        if not plan.awaiting_backward:
+            break
+        if oldest is None or plan.slot_stamp < oldest.slot_stamp:
+            oldest = plan
+    else:
+        plan = oldest
+    _stamp += 1
+    plan.slot_stamp = _stamp
     return plan
 
 
@@ -75,6 +94,7 @@ class _BiSeNetTrainFn(torch.autograd.Function):
         if plan.generation != ctx.gen:
             raise ops._lib.RtsdsError("BiSeNet backward called after another forward of the same shape reused the plan's "
                                       "saved activations; call backward() before the next forward()")
+        plan.awaiting_backward = False
         s = ops._s()
         main, aux = plan.out_sizes()
         for i, d in enumerate(douts):
@@ -99,6 +119,7 @@ def bisenet_train_forward(model, x):
             outs = tuple(plan.logits())
     else:
         outs = _BiSeNetTrainFn.apply(plan, x, *params)
+        plan.awaiting_backward = bool(outs[0].requires_grad)
     _bump_bn_counters(model)
     return outs
 
@@ -138,6 +159,7 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
         plan = ctx.plan
         if plan.generation != ctx.gen:
             raise ops._lib.RtsdsError("BiSeNet backward called after another forward reused the plan's saved activations")
+        plan.awaiting_backward = False
         main, aux = plan.out_sizes()
         plan.gscale.copy_((dloss.double() / ctx.stats[:, 1]).float())
         for i, z in enumerate((plan.z, plan.z1, plan.z2)):
@@ -168,6 +190,7 @@ def bisenet_fused_ce(model, x, target, ignore_index=255, return_logits=False):
     assert target.dtype == torch.int64
     plan = _get_train_plan(model, x)
     out = _BiSeNetFusedCEFn.apply(plan, x, target, int(ignore_index), *plan.params)
+    plan.awaiting_backward = bool(out[0].requires_grad)
     _bump_bn_counters(model)
     if return_logits:
         (oh, ow), _ = plan.out_sizes()

@@ -222,14 +222,34 @@ class DiscPlan:
         return dx
 
 
+_MAX_SLOTS = 4
+_stamp = 0
+
+
 def _get_plan(model, x):
+    """One plan per input shape -- and a further one (up to _MAX_SLOTS) whenever every existing plan of that shape
+    still holds the activations of a forward whose backward has not run yet: train.py:447-458 (adversarial_train_2)
+    calls the discriminator twice and then backpropagates through both calls at once."""
+    global _stamp
     plans = model.__dict__.setdefault("_rtsds_plans", {})
     n, c, h, w = x.shape
-    key = (n, c, h, w, model.rtsds_precision, x.device.index)
-    plan = plans.get(key)
-    if plan is None:
-        plan = DiscPlan(model, n, c, h, w, model.rtsds_precision)
-        plans[key] = plan
+    base = (n, c, h, w, model.rtsds_precision, x.device.index)
+    oldest = None
+    for slot in range(_MAX_SLOTS):
+        plan = plans.get(base + (slot,))
+        if plan is None:
+            plan = DiscPlan(model, n, c, h, w, model.rtsds_precision)
+            plan.awaiting_backward = False
+            plans[base + (slot,)] = plan
+            break
+        if not plan.awaiting_backward:
+            break
+        if oldest is None or plan.slot_stamp < oldest.slot_stamp:
+            oldest = plan
+    else:
+        plan = oldest          # every slot is pending (graphs dropped without backward): recycle the oldest one
+    _stamp += 1
+    plan.slot_stamp = _stamp
     return plan
 
 
@@ -238,6 +258,7 @@ class _DiscFn(torch.autograd.Function):
     def forward(ctx, plan, x, softmax_in, *params):
         out = plan.forward(x, softmax_in)
         ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
+        plan.awaiting_backward = True
         return out
 
     @staticmethod
@@ -246,6 +267,7 @@ class _DiscFn(torch.autograd.Function):
         if plan.generation != ctx.gen:
             raise ops._lib.RtsdsError("discriminator backward called after another forward of the same shape reused the "
                                       "plan's saved activations; call backward() before the next forward()")
+        plan.awaiting_backward = False
         g = dout.contiguous().view(-1).float()
         flat, gw = plan.new_grads()
         dx = plan.backward(g, gw, ctx.needs_input_grad[1])

@@ -173,3 +173,31 @@ def test_discriminator_rejects_cpu_tensor():
 
     with pytest.raises(RtsdsError):
         TinyDomainDiscriminator(19)(torch.zeros(1, 19, 32, 32))
+
+
+@pytest.mark.parametrize("tiny", [True, False])
+def test_two_forwards_then_one_backward(cuda, tiny):
+    """train.py:447-458 (adversarial_train_2): D(real) and D(fake) are both evaluated before ONE backward through their
+    summed losses -- each forward keeps its own saved activations (plan slots); the parameter gradients equal the sum of
+    the two passes done one after the other."""
+    g = torch.Generator().manual_seed(11)
+    xa = torch.softmax(torch.randn(2, 19, 64, 96, generator=g), 1).cuda()
+    xb = torch.softmax(torch.randn(2, 19, 64, 96, generator=g), 1).cuda()
+    bce = torch.nn.BCEWithLogitsLoss()
+    m = _model(tiny, "fp32")
+    oa, ob = m(xa), m(xb)
+    (bce(oa, torch.ones_like(oa)) + bce(ob, torch.zeros_like(ob))).backward()
+    both = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m2 = _model(tiny, "fp32")
+    oa2 = m2(xa)
+    bce(oa2, torch.ones_like(oa2)).backward()
+    ob2 = m2(xb)
+    bce(ob2, torch.zeros_like(ob2)).backward()
+    assert torch.allclose(oa, oa2, rtol=1e-5, atol=1e-6) and torch.allclose(ob, ob2, rtol=1e-5, atol=1e-6)   # GAP sums are atomics
+    for k, p in m2.named_parameters():
+        assert rel_l2(both[k], p.grad) < 1e-4, k
+    # a fifth pending forward recycles the oldest slot, whose backward then reports the stale activations
+    outs = [m(xa) for _ in range(5)]
+    with pytest.raises(Exception, match="backward"):
+        outs[0].sum().backward()
+    outs[4].sum().backward()

@@ -103,3 +103,29 @@ def test_reference_adversarial_loop_runs_on_the_drop_in_modules(ref_loops, monke
     assert calls.count("rtsds_disc_cls_fwd") == 2 * 3 and calls.count("rtsds_s2d_bwd") == 2 * 1
     assert calls.count("rtsds_s2d_weight_grad") == 2 * 2
     assert all(p.requires_grad for p in dis.parameters())
+
+
+def test_reference_adversarial_loop_2_runs_on_the_drop_in_modules(ref_loops, monkeypatch, tmp_path):
+    """train.py:322-500: the variant that trains D on target predictions and resizes every prediction to the
+    target size with F.adaptive_avg_pool2d -- stock torch ops on the drop-in modules' outputs, generator forwards under
+    torch.no_grad() in train mode, D output .requires_grad_(True)."""
+    train_mod, _ = ref_loops
+    if not hasattr(train_mod, "adversarial_train_2"):
+        pytest.skip("reference has no adversarial_train_2")
+    from models.bisenet.build_bisenet import BiSeNet
+    from models.domain_shift.adversarial.model import TinyDomainDiscriminator
+    from rtsds_b200 import _lib
+
+    monkeypatch.chdir(tmp_path)
+    gen, dis = BiSeNet(19, "resnet18"), TinyDomainDiscriminator(19)
+    gopt = torch.optim.Adam(gen.parameters(), lr=1e-4)
+    dopt = torch.optim.Adam(dis.parameters(), lr=1e-4, weight_decay=1e-4)
+    _lib.lib().calls.clear()
+    train_mod.adversarial_train_2(2, 1, gen, dis, gopt, dopt, _batches(1, 2, 96, 128), _batches(1, 2, 64, 96),
+                                  torch.nn.CrossEntropyLoss(ignore_index=19), torch.nn.BCEWithLogitsLoss(), 0.1,
+                                  1e-4, 0.9, 0.9, 1e-4, 1, 19, [f"c{i}" for i in range(19)], _batches(1, 1, 64, 96), 1, "cpu", 10,
+                                  [sys.modules["callbacks"].Callback()])
+    calls = _lib.lib().calls
+    assert calls.count("rtsds_disc_cls_fwd") >= 3          # one D forward for the generator loss, two for D's own step
+    assert calls.count("rtsds_conv2d_tc_wgrad") >= 20      # the generator's backward ran through the hand-written path
+    assert all(p.requires_grad for p in dis.parameters())
