@@ -34,7 +34,7 @@ H, W, NUM_CLASSES = 512, 1024, 19
 FWD_GFLOP_PER_IMG = 51.26          # conv FLOPs (2*MAC) of one eval forward at 512x1024
 FWD_CONV_MB_PER_IMG = 236.0        # ideal bf16 conv traffic
 LOGITS_MB_PER_IMG = 39.8           # fp32 [19,512,1024] API-boundary write
-CONV_DRAM_BYTES_PER_FORWARD = 117743360   # dram__bytes_read+write summed over the 22 conv launches (profiles/r01_conv_tc_infer_ncu_full.csv)
+CONV_DRAM_BYTES_PER_FORWARD = 120977408   # dram__bytes_read+write summed over the 22 conv launches (profiles/r01_conv_tc_infer_ncu_full.csv)
 
 
 def peaks():
