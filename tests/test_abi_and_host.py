@@ -120,6 +120,43 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     assert c["rtsds_conv2d_simt_fwd"] == 22 and c["rtsds_conv2d_tc_fwd"] == 0
 
 
+def test_weights_epoch_and_plan_slots_dry_run(monkeypatch):
+    """Host logic without a GPU: (1) a backward pass makes every plan re-pack its operands at the next forward even
+    when no tensor version counter moved (torch's fused optimizers); (2) a second train forward of the same shape that
+    is alive together with the first gets its own plan, and the slot is reused once its backward has run."""
+    monkeypatch.setenv("RTSDS_DRYRUN", "1")
+    from models.bisenet.build_bisenet import BiSeNet
+    from rtsds_b200 import _lib, weights_epoch
+
+    m = BiSeNet(19, "resnet18").train()
+    x = torch.zeros(2, 3, 64, 96)
+    y = torch.zeros(2, 64, 96, dtype=torch.int64)
+    ce = lambda outs: sum(torch.nn.functional.cross_entropy(t, y, ignore_index=19) for t in outs)
+    calls = _lib.lib().calls
+    calls.clear()
+    outs = m(x)
+    assert calls.count("rtsds_pack_conv_weights_batch") == 1
+    e0 = weights_epoch.value()
+    ce(outs).backward()
+    assert weights_epoch.value() == e0 + 1
+    calls.clear()
+    outs = m(x)                                       # nothing touched the parameters, but a backward ran: re-pack
+    assert calls.count("rtsds_pack_conv_weights_batch") == 1 and len(m._rtsds_train_plans) == 1
+    calls.clear()
+    with torch.no_grad():
+        m(x)                                          # first plan still awaits its backward: second slot, own operands
+    assert len(m._rtsds_train_plans) == 2 and calls.count("rtsds_pack_conv_weights_batch") == 1
+    outs2 = m(x)                                      # the no-grad forward left slot 2 free: reused, no third plan
+    assert len(m._rtsds_train_plans) == 2
+    (ce(outs) + ce(outs2)).backward()                 # both pending backward passes run on their own activations
+    assert weights_epoch.value() == e0 + 3
+    m.eval()
+    calls.clear()
+    m.rtsds_cuda_graph = False
+    m(x); m(x)
+    assert calls.count("rtsds_bn_fold") == 24          # eval plan folded its BatchNorms once, not on the second call
+
+
 def test_geometry_helpers():
     from rtsds_b200 import ops
 
