@@ -86,6 +86,9 @@ class _BiSeNetTrainFn(torch.autograd.Function):
         plan.forward(x)
         outs = plan.logits()
         ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
+        # heads nobody differentiates (the adversarial loss uses the main head only, train.py:218-229) arrive as None in
+        # backward instead of as materialised full-resolution zero tensors
+        ctx.set_materialize_grads(False)
         return tuple(outs)
 
     @staticmethod
