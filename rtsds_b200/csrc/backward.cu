@@ -887,20 +887,41 @@ resize_nchw_bwd_kernel(const float* __restrict__ dout, int n, int c, int oh, int
         dst_range(y, rh, oh, &ylo, &yhi);
         dst_range(x, rw, ow, &xlo, &xhi);
         const float* plane = dout + (static_cast<long long>(img) * c + ch) * oh * ow;
+        // column weights once per thread (the interpolation coordinates cost ~20 instructions each: recomputing them
+        // for every (row, column) candidate made this kernel instruction bound), then rows x columns of load + fma
+        constexpr int RN_MAXC = 20;                    // 2*scale + 4 candidates: upsampling factors up to 8
+        float wxs[RN_MAXC];
+#pragma unroll
+        for (int k = 0; k < RN_MAXC; ++k) {
+            const int ox = xlo + k;
+            float wx = 0.f;
+            if (ox <= xhi) {
+                const Lerp lx = lerp_src(ox, rw, w);
+                wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
+            }
+            wxs[k] = wx;
+        }
         float acc = 0.f;
         for (int oy = ylo; oy <= yhi; ++oy) {
             const Lerp ly = lerp_src(oy, rh, h);
             const float wy = (ly.i0 == y ? ly.l0 : 0.f) + (ly.i1 == y ? ly.l1 : 0.f);
             if (wy == 0.f) continue;
-            for (int ox = xlo; ox <= xhi; ++ox) {
+            const float* rowp = plane + static_cast<long long>(oy) * ow + xlo;
+            float rowacc = 0.f;
+#pragma unroll
+            for (int k = 0; k < RN_MAXC; ++k)
+                if (wxs[k] != 0.f) rowacc = fmaf(wxs[k], __ldg(rowp + k), rowacc);
+            for (int ox = xlo + RN_MAXC; ox <= xhi; ++ox) {
                 const Lerp lx = lerp_src(ox, rw, w);
                 const float wx = (lx.i0 == x ? lx.l0 : 0.f) + (lx.i1 == x ? lx.l1 : 0.f);
-                if (wx != 0.f) acc = fmaf(wy * wx, __ldg(plane + static_cast<long long>(oy) * ow + ox), acc);
+                if (wx != 0.f) rowacc = fmaf(wx, __ldg(plane + static_cast<long long>(oy) * ow + ox), rowacc);
             }
+            acc = fmaf(wy, rowacc, acc);
         }
         dz[((static_cast<long long>(img) * h + y) * w + x) * z_ld + ch] = acc;
     }
 }
+
 
 // ---------------------------------------------------------------- stem weight gradient
 // dw[co][ci][r][s] += sum_{n,oy,ox} d_raw[n,oy,ox,co] * x[n,ci,oy*2-pad+r,ox*2-pad+s]   (x NCHW fp32, d_raw NHWC)

@@ -449,3 +449,21 @@ def test_stem_s2d_forward_and_wgrad(cuda, n, h, w, k):
     gw = torch.zeros(64, 3, k, k, device="cuda")
     ops.stem_s2d_weight_grad(g2, gw)
     assert rel_err(gw.cpu(), wr.grad) < 2e-3, rel_err(gw.cpu(), wr.grad)
+
+
+@pytest.mark.parametrize("n,c,h,w,oh,ow", [(2, 19, 16, 24, 128, 192), (1, 19, 23, 40, 184, 320), (2, 7, 9, 70, 72, 560), (1, 19, 12, 20, 50, 77),
+                                            (1, 19, 5, 6, 160, 192), (2, 19, 33, 35, 33, 35), (1, 3, 64, 128, 512, 1024)])
+def test_resize_to_nchw_backward(cuda, n, c, h, w, oh, ow):
+    """Adjoint of the logits writer (bilinear, align_corners=False, NHWC pitch-32 source -> NCHW) against torch.autograd of
+    F.interpolate: integer and fractional factors, x32 (more candidates than the unrolled part), identity."""
+    from rtsds_b200._lib import check, lib
+    g = torch.Generator().manual_seed(h * w + oh)
+    z = torch.randn(n, c, h, w, generator=g, requires_grad=True)
+    dout = torch.randn(n, c, oh, ow, generator=g)
+    F.interpolate(z, size=(oh, ow), mode="bilinear", align_corners=False).backward(dout)
+    dz = torch.full((n, h, w, 32), float("nan"), device="cuda")
+    dg = dout.cuda()
+    check(lib().rtsds_resize_to_nchw_bwd(dg.data_ptr(), n, c, oh, ow, h, w, dz.data_ptr(), 32, None), "resize_to_nchw_bwd")
+    torch.cuda.synchronize()
+    got = dz[..., :c].permute(0, 3, 1, 2).cpu()
+    assert rel_err(got, z.grad) < 1e-5
