@@ -454,15 +454,38 @@ class DeepLabTrainPlan(_PlanBase):
 
 
 # ======================================================================================= autograd boundary
+_MAX_TRAIN_SLOTS = 2
+_stamp = 0
+
+
 def _get_plan(model, x, train):
+    """One plan per (shape, mode).  Train plans: a second slot only when the first still holds the activations of a
+    forward whose backward has not run (same rule as rtsds_b200/bisenet_autograd.py)."""
+    global _stamp
     plans = model.__dict__.setdefault("_rtsds_plans", {})
     n, _, h, w = x.shape
-    key = (n, h, w, bool(train), model.rtsds_precision, x.device.index)
-    plan = plans.get(key)
-    if plan is None:
-        cls = DeepLabTrainPlan if train else DeepLabPlan
-        plan = cls(model, n, h, w, model.rtsds_precision)
-        plans[key] = plan
+    base = (n, h, w, bool(train), model.rtsds_precision, x.device.index)
+    if not train:
+        plan = plans.get(base)
+        if plan is None:
+            plan = plans[base] = DeepLabPlan(model, n, h, w, model.rtsds_precision)
+        return plan
+    oldest = None
+    for slot in range(_MAX_TRAIN_SLOTS):
+        plan = plans.get(base + (slot,))
+        if plan is None:
+            plan = DeepLabTrainPlan(model, n, h, w, model.rtsds_precision)
+            plan.awaiting_backward = False
+            plans[base + (slot,)] = plan
+            break
+        if not plan.awaiting_backward:
+            break
+        if oldest is None or plan.slot_stamp < oldest.slot_stamp:
+            oldest = plan
+    else:
+        plan = oldest
+    _stamp += 1
+    plan.slot_stamp = _stamp
     return plan
 
 
@@ -502,6 +525,7 @@ class _DeepLabTrainFn(torch.autograd.Function):
         if plan.generation != ctx.gen:
             raise ops._lib.RtsdsError("DeepLabV2 backward called after another forward of the same shape reused the plan's "
                                       "saved activations; call backward() before the next forward()")
+        plan.awaiting_backward = False
         dout = dout.contiguous()
         check(lib().rtsds_resize_to_nchw_bwd(_p(dout), plan.n, plan.nc, plan.h, plan.w, plan.hf, plan.wf, _p(plan.dz), 32, ops._s()),
               "resize_to_nchw_bwd")
@@ -534,6 +558,7 @@ class _DeepLabFusedCEFn(torch.autograd.Function):
         plan = ctx.plan
         if plan.generation != ctx.gen:
             raise ops._lib.RtsdsError("DeepLabV2 backward called after another forward reused the plan's saved activations")
+        plan.awaiting_backward = False
         plan.gscale.copy_((dloss.double() / ctx.stats[1]).float().view(1))
         if ctx.one_pass:
             ops.scale_by_device_scalar(plan.dz, plan.gscale)
@@ -558,6 +583,7 @@ def deeplab_fused_ce(model, x, target, ignore_index=255):
     assert target.dtype == torch.int64
     plan = _get_plan(model, x, True)
     out = _DeepLabFusedCEFn.apply(plan, x, target, int(ignore_index), *plan.params)
+    plan.awaiting_backward = bool(out[0].requires_grad)
     _bump_bn_counters(model)
     return out
 
@@ -573,6 +599,7 @@ def deeplab_forward(model, x):
         plan = _get_plan(model, x, True)
         if torch.is_grad_enabled():
             out = _DeepLabTrainFn.apply(plan, x, *plan.params)
+            plan.awaiting_backward = bool(out.requires_grad)
         else:
             with torch.no_grad():
                 plan.forward(x)
