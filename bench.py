@@ -139,8 +139,8 @@ def max_over_ranks(v, world):
     return float(t.item())
 
 
-def make_model(device):
-    """Random-init weights of the BiSeNet-R18 architecture (no checkpoints offline)."""
+def make_model(device, context="resnet18"):
+    """Random-init weights of the BiSeNet architecture (no checkpoints offline)."""
     from models.bisenet.build_bisenet import BiSeNet
 
     torch.manual_seed(42)
@@ -148,7 +148,7 @@ def make_model(device):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        m = BiSeNet(NUM_CLASSES, "resnet18")
+        m = BiSeNet(NUM_CLASSES, context)
     # non-trivial BatchNorm running statistics so the folded epilogues do real work
     g = torch.Generator().manual_seed(7)
     for mod in m.modules():
@@ -214,7 +214,8 @@ def run_infer(args, rank, world, local):
     from rtsds_b200 import ops
 
     dev = torch.device("cuda", local)
-    model = make_model(dev)
+    r101 = args.context == "resnet101"          # eval only; the training half of the line is skipped
+    model = make_model(dev, args.context)
     n_inputs = 32                                   # 32 x 6.29 MB = 201 MB > 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
     host = torch.randn(n_inputs, 1, 3, H, W, generator=g).pin_memory()
@@ -346,7 +347,7 @@ def run_infer(args, rank, world, local):
 
     # ---- the other half of BASELINE.json's metric: data-parallel training images/s (configs[2]) ----
     train = None
-    if not args.no_train:
+    if not args.no_train and not r101:
         import bench_train
 
         del dev_in, host, model
@@ -368,10 +369,11 @@ def run_infer(args, rank, world, local):
     hbm_achieved = (FWD_CONV_MB_PER_IMG + LOGITS_MB_PER_IMG) * 1e6 / (step_ms * 1e-3) / 1e9
     cpu = cpu_baseline(args)
     line = {
-        "metric": "BiSeNet-R18 512x1024 inference FPS (batch 1)", "value": round(fps, 2), "unit": "frames/s",
+        "metric": f"BiSeNet-{'R101' if r101 else 'R18'} 512x1024 inference FPS (batch 1)", "value": round(fps, 2), "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "bisenet_r18_eval_b1_3x512x1024 (BASELINE.json configs[1])", "num_classes": NUM_CLASSES,
+        "config": {"workload": ("bisenet_r101_eval_b1_3x512x1024 (config.yaml backbone: resnet101, SURVEY N4)" if r101 else
+                                "bisenet_r18_eval_b1_3x512x1024 (BASELINE.json configs[1])"), "num_classes": NUM_CLASSES,
                    "weights": "random-init, seeded", "parallelism": "replicas only" if world > 1 else "single GPU",
                    "l2": "inputs rotate over 32 distinct images (201 MB > 126 MB L2); weights stay L2-resident as in "
                          "steady-state serving; latency_cold_l2_ms flushes L2 before every iteration",
@@ -392,11 +394,11 @@ def run_infer(args, rank, world, local):
                             "std_fps": round(statistics.pstdev(fps_i), 2)},
         "latency_cold_l2_ms": round(statistics.median(cold), 4),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": CONV_DRAM_BYTES_PER_FORWARD, "peak_source": pk["source"],
+                     "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None if r101 else CONV_DRAM_BYTES_PER_FORWARD, "peak_source": pk["source"],
                      "traffic_source": "ncu --set full of the 22 conv launches of one forward (cold L2), profiles/r01_conv_tc_infer_ncu_full.csv",
                      "kernel": "conv_tc_kernel (22 launches/forward, aggregated; each launch timed as the average of 20 back-to-back graph-replayed repeats, split-K finish kernels included)", "flops_per_step": tc_flops,
                      "kernel_ms_per_step": round(tc_ms, 4)},
-        "whole_step": {"tflops": round(FWD_GFLOP_PER_IMG / step_ms, 2), "frac_of_bf16_peak": round(FWD_GFLOP_PER_IMG / step_ms / pk["bf16_tflops"], 4),
+        "whole_step": None if r101 else {"tflops": round(FWD_GFLOP_PER_IMG / step_ms, 2), "frac_of_bf16_peak": round(FWD_GFLOP_PER_IMG / step_ms / pk["bf16_tflops"], 4),
                        "algorithmic_gbs": round(hbm_achieved, 1), "frac_of_hbm_peak": round(hbm_achieved / pk["hbm_gbs"], 4)},
         "conv_layers": [{"layer": r[2], "ms": round(r[3], 4), "tflops": round(r[0] / (r[3] * 1e-3) / 1e12, 1),
                          "gbs": round(r[1] / (r[3] * 1e-3) / 1e9, 1)} for r in rows],
@@ -406,13 +408,13 @@ def run_infer(args, rank, world, local):
     print(json.dumps(line))
 
 
-def cpu_reference_fps(seconds_budget=12.0, max_iters=60):
+def cpu_reference_fps(seconds_budget=12.0, max_iters=60, context="resnet18"):
     """Oracle port of the reference CPU path (BiSeNet eval, b=1, 512x1024) on all host threads."""
     from oracle import bisenet_ref, weights
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = weights.bisenet_r18_state(42)
+    sd = weights.bisenet_r101_state(42) if context == "resnet101" else weights.bisenet_r18_state(42)
     x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(1234))
     with torch.no_grad():
         bisenet_ref.bisenet_forward(x, sd, train=False)      # warm-up
@@ -426,7 +428,7 @@ def cpu_reference_fps(seconds_budget=12.0, max_iters=60):
 
 
 def cpu_baseline(args):
-    fps, threads, iters, _ = cpu_reference_fps()
+    fps, threads, iters, _ = cpu_reference_fps(context=args.context)
     return {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port",
             "sample": f"{iters} eval forwards of the oracle port (torch CPU fp32, README protocol) at b=1 3x512x1024"}
 
@@ -436,12 +438,14 @@ def run_reference(args, rank, world):
         return
     K, Wm = args.steps, args.warmup
     iters = max(3, min(K, 40))
-    fps, threads, n, ts = cpu_reference_fps(seconds_budget=60.0, max_iters=iters)
+    fps, threads, n, ts = cpu_reference_fps(seconds_budget=60.0, max_iters=iters, context=args.context)
+    r101 = args.context == "resnet101"
     line = {
-        "impl": "reference", "metric": "BiSeNet-R18 512x1024 inference FPS (batch 1)", "value": round(fps, 3),
+        "impl": "reference", "metric": f"BiSeNet-{'R101' if r101 else 'R18'} 512x1024 inference FPS (batch 1)", "value": round(fps, 3),
         "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / fps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bisenet_r18_eval_b1_3x512x1024 (BASELINE.json configs[1])", "num_classes": NUM_CLASSES,
+        "config": {"workload": ("bisenet_r101_eval_b1_3x512x1024 (config.yaml backbone: resnet101, SURVEY N4)" if r101 else
+                                "bisenet_r18_eval_b1_3x512x1024 (BASELINE.json configs[1])"), "num_classes": NUM_CLASSES,
                    "note": "reference CPU path (oracle port; the reference is not pip-installable and /root/reference is absent on the GPU box)"},
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{n} timed eval forwards at b=1 3x512x1024 on {threads} host threads"},
@@ -462,6 +466,7 @@ def main():
     ap.add_argument("--disc", default="tiny", choices=["tiny", "full"], help="discriminator of the adversarial workload")
     ap.add_argument("--stock", action="store_true", help="adversarial workload: the reference's exact call sequence instead of the fused fast paths")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
+    ap.add_argument("--context", default="resnet18", choices=["resnet18", "resnet101"], help="inference: BiSeNet context path (resnet101: eval only)")
     ap.add_argument("--lanes", type=int, default=3, help="inference: concurrent batch-1 streams of the multi-stream / pipelined measurements")
     args = ap.parse_args()
     if args.warmup < 3:

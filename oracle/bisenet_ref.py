@@ -73,6 +73,34 @@ def context_path_r18(x, sd, train, prefix="context_path.features"):
     return f3, f4, tail
 
 
+def bottleneck(x, sd, prefix, stride, train):
+    """torchvision Bottleneck.forward (resnet.py:143-163; v1.5: the stride sits on the 3x3 conv2)."""
+    out = F.relu(_bn(F.conv2d(x, sd[prefix + ".conv1.weight"]), sd, prefix + ".bn1", train))
+    out = F.relu(_bn(F.conv2d(out, sd[prefix + ".conv2.weight"], None, stride=stride, padding=1), sd, prefix + ".bn2", train))
+    out = _bn(F.conv2d(out, sd[prefix + ".conv3.weight"]), sd, prefix + ".bn3", train)
+    if prefix + ".downsample.0.weight" in sd:
+        idn = _bn(F.conv2d(x, sd[prefix + ".downsample.0.weight"], None, stride=stride), sd, prefix + ".downsample.1", train)
+    else:
+        idn = x
+    return F.relu(out + idn)
+
+
+def context_path_r101(x, sd, train, prefix="context_path.features"):
+    """resnet101.forward — models/bisenet/build_contextpath.py:45-56 (Bottleneck blocks [3, 4, 23, 3])."""
+    x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, stride=2, padding=3)
+    x = F.relu(_bn(x, sd, prefix + ".bn1", train))
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li, stride, blocks in ((1, 1, 3), (2, 2, 4), (3, 2, 23), (4, 2, 3)):
+        for b in range(blocks):
+            x = bottleneck(x, sd, f"{prefix}.layer{li}.{b}", stride if b == 0 else 1, train)
+        feats.append(x)
+    f3, f4 = feats[2], feats[3]
+    tail = torch.mean(f4, 3, keepdim=True)
+    tail = torch.mean(tail, 2, keepdim=True)
+    return f3, f4, tail
+
+
 def arm(x, sd, prefix, train):
     """AttentionRefinementModule.forward — build_bisenet.py:44-53."""
     g = F.adaptive_avg_pool2d(x, 1)
@@ -94,7 +122,9 @@ def ffm(sx, cx, sd, train, prefix="feature_fusion_module"):
 def bisenet_forward(x, sd, train, with_interpolation=True, return_intermediates=False):
     """BiSeNet.forward — build_bisenet.py:141-172.  train -> (result, cx1_sup, cx2_sup); eval -> result."""
     sx = spatial_path(x, sd, train)
-    cx1, cx2, tail = context_path_r18(x, sd, train)
+    # BiSeNet(num_classes, 'resnet101') (build_bisenet.py:95-102) is recognised by its Bottleneck conv3 weights
+    r101 = "context_path.features.layer1.0.conv3.weight" in sd
+    cx1, cx2, tail = (context_path_r101 if r101 else context_path_r18)(x, sd, train)
     f3, f4 = cx1, cx2
     cx1 = arm(cx1, sd, "attention_refinement_module1", train)
     cx2 = arm(cx2, sd, "attention_refinement_module2", train)

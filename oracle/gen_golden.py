@@ -92,6 +92,22 @@ def gen_bisenet(R, name, seed, n, h, w):
     print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.size > 8})
 
 
+def gen_bisenet_r101(R, name, seed, n, h, w):
+    """BiSeNet(19, 'resnet101'), eval forward only."""
+    x, _ = make_input(1000 + seed, n, h, w)
+    sd = weights.bisenet_r101_state(seed)
+    m = R["BiSeNet"](19, "resnet101")
+    missing = m.load_state_dict(weights.clone_state(sd))
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m.eval()
+    with torch.no_grad():
+        r = m(x)
+    out = {"shape": np.array([n, h, w]), "seed": np.array([seed]), "eval_result": sub(r), "eval_result_sum": summarize(r),
+           "eval_argmax": r.argmax(1)[..., ::SUB, ::SUB].numpy().astype(np.int16), "n_state_keys": np.array([len(m.state_dict())])}
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, r.shape, float(r.abs().max()))
+
+
 def gen_fast_hist(U):
     out = {}
     rng = np.random.default_rng(7)
@@ -196,6 +212,7 @@ def main():
     gen_bisenet(R, "bisenet_72x104", 1, 2, 72, 104)
     gen_discriminators(R)
     gen_deeplab(R, "deeplab_72x104", 2, 2, 72, 104)
+    gen_bisenet_r101(R, "bisenet_r101_64x96", 3, 1, 64, 96)
 
 
 if __name__ == "__main__":

@@ -94,6 +94,65 @@ def bisenet_r18_state(seed: int = 0, num_classes: int = 19) -> dict:
     return sd
 
 
+def resnet101_state(seed: int, prefix: str) -> dict:
+    """torchvision resnet101 parameter tree (conv1, bn1, layer1-4 Bottlenecks [3,4,23,3], fc); stride on conv2 (v1.5)."""
+    sd = {}
+    sd[prefix + ".conv1.weight"] = _conv_w(prefix + ".conv1.weight", seed, 64, 3, 7)
+    _bn(sd, prefix + ".bn1", seed, 64)
+    inpl = 64
+    for li, planes, blocks in ((1, 64, 3), (2, 128, 4), (3, 256, 23), (4, 512, 3)):
+        for b in range(blocks):
+            p = f"{prefix}.layer{li}.{b}"
+            cin = inpl if b == 0 else planes * 4
+            sd[p + ".conv1.weight"] = _conv_w(p + ".conv1.weight", seed, planes, cin, 1)
+            _bn(sd, p + ".bn1", seed, planes)
+            sd[p + ".conv2.weight"] = _conv_w(p + ".conv2.weight", seed, planes, planes, 3)
+            _bn(sd, p + ".bn2", seed, planes)
+            sd[p + ".conv3.weight"] = _conv_w(p + ".conv3.weight", seed, planes * 4, planes, 1, gain=1.0)
+            _bn(sd, p + ".bn3", seed, planes * 4)
+            sd[p + ".bn3.weight"] = sd[p + ".bn3.weight"] * 0.25      # keeps the 33 residual sums bounded
+            if b == 0:
+                sd[p + ".downsample.0.weight"] = _conv_w(p + ".downsample.0.weight", seed, planes * 4, cin, 1, gain=1.0)
+                _bn(sd, p + ".downsample.1", seed, planes * 4)
+        inpl = planes * 4
+    sd[prefix + ".fc.weight"] = torch.randn(1000, 2048, generator=_gen(prefix + ".fc.weight", seed)) * 0.02
+    sd[prefix + ".fc.bias"] = _vec(prefix + ".fc.bias", seed, 1000)
+    return sd
+
+
+def bisenet_r101_state(seed: int = 0, num_classes: int = 19) -> dict:
+    """state_dict of the reference's BiSeNet(num_classes, 'resnet101') (build_bisenet.py:95-102: ARMs 1024 / 2048,
+    FFM over 3328 channels), incl. the aliased context_path.{conv1,bn1,layer1..4}.* duplicates."""
+    sd = {}
+    nc = num_classes
+    for i, (ci, co) in enumerate(((3, 64), (64, 128), (128, 256)), start=1):
+        p = f"saptial_path.convblock{i}"
+        sd[p + ".conv1.weight"] = _conv_w(p + ".conv1.weight", seed, co, ci, 3)
+        _bn(sd, p + ".bn", seed, co)
+    feats = resnet101_state(seed, "context_path.features")
+    sd.update(feats)
+    for k, v in feats.items():
+        rest = k[len("context_path.features."):]
+        if rest.split(".")[0] in ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4"):
+            sd["context_path." + rest] = v
+    for i, c in ((1, 1024), (2, 2048)):
+        p = f"attention_refinement_module{i}"
+        sd[p + ".conv.weight"] = _conv_w(p + ".conv.weight", seed, c, c, 1)
+        sd[p + ".conv.bias"] = _vec(p + ".conv.bias", seed, c)
+        _bn(sd, p + ".bn", seed, c)
+        sd[f"supervision{i}.weight"] = _conv_w(f"supervision{i}.weight", seed, nc, c, 1)
+        sd[f"supervision{i}.bias"] = _vec(f"supervision{i}.bias", seed, nc)
+    p = "feature_fusion_module"
+    sd[p + ".convblock.conv1.weight"] = _conv_w(p + ".convblock.conv1.weight", seed, nc, 3328, 3)
+    _bn(sd, p + ".convblock.bn", seed, nc)
+    for j in (1, 2):
+        sd[f"{p}.conv{j}.weight"] = _conv_w(f"{p}.conv{j}.weight", seed, nc, nc, 1)
+        sd[f"{p}.conv{j}.bias"] = _vec(f"{p}.conv{j}.bias", seed, nc)
+    sd["conv.weight"] = _conv_w("conv.weight", seed, nc, nc, 1)
+    sd["conv.bias"] = _vec("conv.bias", seed, nc)
+    return sd
+
+
 def discriminator_state(seed: int = 0, tiny: bool = False, num_classes: int = 19) -> dict:
     """DomainDiscriminator (model.py:45-49) / TinyDomainDiscriminator (:72-73)."""
     sd = {}

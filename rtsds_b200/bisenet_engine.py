@@ -55,8 +55,9 @@ class BiSeNetPlan:
         self.use_tc = precision == "bf16"          # "bf16_simt": bf16 storage, CUDA-core convs (cross-check)
         self.tdt = ops.torch_dtype(self.dt)
         self.nc = model.conv.weight.shape[0]
-        if model._context_name != "resnet18":
-            raise ops._lib.RtsdsError("only the resnet18 context path is implemented (SURVEY C2: resnet101 out of scope)")
+        if model._context_name not in ("resnet18", "resnet101") or (train and model._context_name != "resnet18"):
+            raise ops._lib.RtsdsError("context paths: resnet18 (train + eval) and resnet101 (eval only, SURVEY N4); got "
+                                      f"{model._context_name!r} with train={train}")
         if self.nc > 32:
             raise ops._lib.RtsdsError("num_classes > 32 is not supported by the fused head kernels")
         self._stats_chunks = []
@@ -176,14 +177,16 @@ class BiSeNetPlan:
         self.h8, self.w8 = h8, w8
         sp1 = self.buf(n, h2, w2, 64)
         sp2 = self.buf(n, h4, w4, 128)
-        cat = self.buf(n, h8, w8, 1024)
-        self.cat = cat
+        # concat buffer of build_bisenet.py:153,72: 256 spatial-path channels | cx1 | cx2 (1024 wide for resnet18, 3328 for resnet101)
+        ccat = m.feature_fusion_module.convblock.conv1.weight.shape[1]
+        cat = self.buf(n, h8, w8, ccat)
+        self.cat, self.ccat = cat, ccat
         fused_stems = self.use_tc and not self.train
         if not fused_stems:
             self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
         self._side_branch = True
         self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
-        self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, 1024, ACT_RELU)
+        self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, ccat, ACT_RELU)
         self._side_branch = False
         # the spatial path is independent of the context path until the concat buffer is consumed: its two convs run on a
         # side stream (a parallel branch of the CUDA graph) and fill SMs the small layer-3/4 grids leave idle
@@ -204,7 +207,7 @@ class BiSeNetPlan:
         feats = []
         for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
             for blk in layer:
-                x, shape = self._basic_block(blk, x, shape)
+                x, shape = (self._bottleneck if hasattr(blk, "conv3") else self._basic_block)(blk, x, shape)
             feats.append((x, shape))
         (f3, s3), (f4, s4) = feats[2], feats[3]
         if min(h8, w8, s4[1], s4[2]) <= 0:
@@ -213,6 +216,8 @@ class BiSeNetPlan:
         # ---- ARMs, tail, gated resize into the concat buffer (reference :147-153) ----
         arm1, arm2 = m.attention_refinement_module1, m.attention_refinement_module2
         c3, c4 = s3[3], s4[3]
+        if 256 + c3 + c4 != ccat:
+            raise ops._lib.RtsdsError(f"feature fusion module expects {ccat} input channels, context path gives 256+{c3}+{c4}")
         pooled3 = self.buf(n, c3, dtype=f32)
         pooled4 = self.buf(n, c4, dtype=f32)
         gate3 = self.buf(n, c3, dtype=f32)
@@ -229,8 +234,8 @@ class BiSeNetPlan:
         self.steps.append(lambda: ops.arm_gate(pooled3, arm1.conv, arm1.bn, tr, n, c3, gate3, None, sv.get("lin3"), sv.get("xhat3")))
         # cx2 = ARM2(cx2) * tail, tail = GAP(feature4) = pooled4 (build_contextpath.py:27-28)
         self.steps.append(lambda: ops.arm_gate(pooled4, arm2.conv, arm2.bn, tr, n, c4, gate4, pooled4, sv.get("lin4"), sv.get("xhat4")))
-        self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, 1024, 256, dt))
-        self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, 1024, 256 + c3, dt))
+        self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, ccat, 256, dt))
+        self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, ccat, 256 + c3, dt))
         self.f3, self.s3, self.f4, self.s4 = f3, s3, f4, s4
         self.n_join = len(self.steps)        # everything from here on reads the spatial-path slot of the concat buffer
 
@@ -238,8 +243,8 @@ class BiSeNetPlan:
         if self.train:
             self.z1 = self.buf(n, h8, w8, 32, dtype=f32)
             self.z2 = self.buf(n, h8, w8, 32, dtype=f32)
-            self._conv(m.supervision1, None, cat, (n, h8, w8, c3), self.z1, 32, ACT_NONE, in_ld=1024, x_off=256, out_dtype=F32)
-            self._conv(m.supervision2, None, cat, (n, h8, w8, c4), self.z2, 32, ACT_NONE, in_ld=1024, x_off=256 + c3, out_dtype=F32)
+            self._conv(m.supervision1, None, cat, (n, h8, w8, c3), self.z1, 32, ACT_NONE, in_ld=ccat, x_off=256, out_dtype=F32)
+            self._conv(m.supervision2, None, cat, (n, h8, w8, c4), self.z2, 32, ACT_NONE, in_ld=ccat, x_off=256 + c3, out_dtype=F32)
 
         # ---- feature fusion module + final 1x1 conv at 1/8 resolution (reference :162-167) ----
         ffm = m.feature_fusion_module
@@ -250,9 +255,9 @@ class BiSeNetPlan:
         from . import tapn
 
         if not self.train and tapn.applicable(ffm.convblock.conv1):
-            self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, 1024)
+            self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, ccat)
         else:
-            self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, 1024), self.feat, 32, ACT_RELU, out_dtype=F32)
+            self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, out_dtype=F32)
         feat, pooled_f, z, attn = self.feat, self.pooled_f, self.z, self.attn
         final = m.conv if m.with_interpolation else None
         self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))
@@ -307,6 +312,28 @@ class BiSeNetPlan:
         else:
             res = x
         self._conv(blk.conv2, blk.bn2, t, (n, oh, ow, cout), y, cout, ACT_RELU, residual=res, res_ld=cout)
+        return y, (n, oh, ow, cout)
+
+    def _bottleneck(self, blk, x, shape):
+        """torchvision Bottleneck (resnet101 context path, build_contextpath.py:32-56): 1x1 -> 3x3 (carries the stride) -> 1x1,
+        each with folded BatchNorm; relu(out + shortcut(x))."""
+        n, h, w, cin = shape
+        planes = blk.conv1.weight.shape[0]
+        cout = blk.conv3.weight.shape[0]
+        st = blk.conv2.stride[0]
+        oh, ow = ops.conv_out_size(h, 3, st, 1), ops.conv_out_size(w, 3, st, 1)
+        t1 = self.buf(n, h, w, planes)
+        t2 = self.buf(n, oh, ow, planes)
+        y = self.buf(n, oh, ow, cout)
+        self._conv(blk.conv1, blk.bn1, x, shape, t1, planes, ACT_RELU)
+        self._conv(blk.conv2, blk.bn2, t1, (n, h, w, planes), t2, planes, ACT_RELU)
+        if blk.downsample is not None:
+            ds = self.buf(n, oh, ow, cout)
+            self._conv(blk.downsample[0], blk.downsample[1], x, shape, ds, cout, ACT_NONE)
+            res = ds
+        else:
+            res = x
+        self._conv(blk.conv3, blk.bn3, t2, (n, oh, ow, planes), y, cout, ACT_RELU, residual=res, res_ld=cout)
         return y, (n, oh, ow, cout)
 
     # ------------------------------------------------------------------ execution

@@ -379,3 +379,33 @@ def test_two_train_forwards_then_one_backward(cuda):
         if p.grad is not None and not _ill_conditioned(k, "fp32"):
             assert _l2_rel(both[k], p.grad) < 5e-3, k          # fp32 atomics order differs between the two schedules
     assert len(m._rtsds_train_plans) == 2 and len(m2._rtsds_train_plans) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_resnet101_context_path_eval_vs_reference_golden(cuda, golden_dir, precision):
+    """BiSeNet(19, 'resnet101') (build_bisenet.py:95-102), eval: Bottleneck context path, ARMs over 1024 / 2048
+    channels, 3328-channel concat buffer and FFM conv.  fp32 check mode must meet 1e-4 against the real reference's
+    output; bf16 through 33 stacked bottlenecks on random-init weights is held to a coarse bound."""
+    from models.bisenet.build_bisenet import BiSeNet
+    gold = np.load(os.path.join(golden_dir, "bisenet_r101_64x96.npz"))
+    n, h, w = (int(v) for v in gold["shape"])
+    seed = int(gold["seed"][0])
+    x, _ = _input(seed, n, h, w)
+    m = BiSeNet(19, "resnet101")
+    m.load_state_dict(weights.clone_state(weights.bisenet_r101_state(seed)))
+    m.rtsds_precision = precision
+    m = m.cuda().eval()
+    out = m(x.cuda())
+    assert out.shape == (n, 19, h, w) and torch.isfinite(out).all()
+    got, ref = out[..., ::SUB, ::SUB].cpu(), torch.from_numpy(gold["eval_result"])
+    agree = (out.argmax(1)[..., ::SUB, ::SUB].cpu().numpy() == gold["eval_argmax"]).mean()
+    if precision == "fp32":
+        assert rel_err(got, ref) < 1e-4, rel_err(got, ref)
+        assert agree >= 0.999, agree
+    else:
+        assert _l2_rel(got, ref) < 6e-2, _l2_rel(got, ref)
+        assert agree >= 0.85, agree
+    assert torch.equal(out, m(x.cuda()))          # CUDA-graph replay of the same plan
+    m.train()
+    with pytest.raises(Exception, match="resnet18"):
+        m(x.cuda().repeat(2, 1, 1, 1))            # training with the resnet101 context path is not built yet

@@ -135,3 +135,19 @@ def test_deeplab_oracle_matches_reference_outputs(golden_dir):
             np.testing.assert_allclose(g_.numpy(), gold[k], rtol=2e-3, atol=1e-7)
         if k.startswith("buf:"):
             np.testing.assert_allclose(sdt[k[4:]].detach().numpy(), gold[k], rtol=1e-4, atol=1e-6)
+
+
+def test_bisenet_resnet101_oracle_matches_reference_outputs(golden_dir):
+    """BiSeNet(19, 'resnet101') (build_bisenet.py:95-102, build_contextpath.py:32-56), eval forward."""
+    gold = np.load(os.path.join(golden_dir, "bisenet_r101_64x96.npz"))
+    n, h, w = (int(v) for v in gold["shape"])
+    seed = int(gold["seed"][0])
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    sd = weights.bisenet_r101_state(seed)
+    assert len(sd) == int(gold["n_state_keys"][0])            # 1298 state_dict keys incl. the aliased context_path.* duplicates
+    with torch.no_grad():
+        r = bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=False)
+    ref = torch.from_numpy(gold["eval_result"])
+    assert (r[..., ::3, ::3] - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    assert (r.argmax(1)[..., ::3, ::3].numpy() == gold["eval_argmax"]).all()
