@@ -405,7 +405,7 @@ def run_infer(args, rank, world, local):
         "train": train,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_reference_fps(seconds_budget=12.0, max_iters=60, context="resnet18"):
@@ -452,10 +452,23 @@ def run_reference(args, rank, world):
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """Write the result line to the process's original stdout (see main(); the descriptor travels in the environment
+    because bench_train / bench_extra import this file as a second module object next to __main__)."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(int(os.environ.get("RTSDS_BENCH_STDOUT_FD", "1")), data)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    # "NCCL version ..." banner straight to stdout when the box exports NCCL_DEBUG) and emit() writes the line to the real one
+    sys.stdout.flush()
+    os.environ["RTSDS_BENCH_STDOUT_FD"] = str(os.dup(1))
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

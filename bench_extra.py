@@ -99,7 +99,7 @@ def run_adversarial(args, rank, world, local):
     it_s = K / (ms / 1e3)
     img_s = world * b * it_s                          # source images (and as many target images) per second
     tfl = b * it_s * (G_TRAIN_GFLOP_720 + G_TRAIN_GFLOP_512) / 1e3
-    print(json.dumps(_line(
+    bench.emit((_line(
         "BiSeNet-R18 + discriminator adversarial training throughput (source images/s; each step also trains on as many target images)",
         img_s, "images/s", world, K, W, ms / K,
         {"workload": "adversarial_bisenet_r18 src 3x720x1280 + tgt 3x512x1024 (BASELINE.json configs[4])", "per_gpu_batch": b,
@@ -193,7 +193,7 @@ def run_deeplab(args, rank, world, local):
     pk = bench.peaks()
     img_s = world * b * K / (ms / 1e3)
     tfl = img_s / world * DEEPLAB_TRAIN_GFLOP_512 / 1e3
-    print(json.dumps(_line(
+    bench.emit((_line(
         "DeepLabV2-R101 512x1024 data-parallel training throughput", img_s, "images/s", world, K, W, ms / K,
         {"workload": "deeplabv2_r101_train_3x512x1024 (BASELINE.json configs[3])", "per_gpu_batch": b, "optimizer": "SGD momentum 0.9",
          "loss": "CE(ignore_index=19), fused resize+CE", "parallelism": f"dp{world}", "l2": "4 rotating input sets per rank"},

@@ -162,4 +162,4 @@ def run_train(args, rank, world, local):
         "final_loss": round(r["loss"], 4), "val_miou_random_weights": round(r["miou"], 5),
         "cpu_baseline": None,
     }
-    print(json.dumps(line))
+    bench.emit(line)
