@@ -16,12 +16,34 @@ import torch.nn as nn
 
 affine_par = True
 
+# (planes, stride, dilation) of layer1..layer4 -- output stride 8: the last two stages trade their stride for dilation (:78-81)
+_STAGES = ((64, 1, 1), (128, 2, 1), (256, 1, 2), (512, 1, 4))
+_ASPP_RATES = (6, 12, 18, 24)
+
+
+def _lazy(path):
+    def call(*args):
+        import importlib
+
+        mod, fn = path.rsplit(".", 1)
+        return getattr(importlib.import_module(mod), fn)(*args)
+    return call
+
+
+_bottleneck_fwd = _lazy("rtsds_b200.module_ops.bottleneck_forward")
+_classifier_fwd = _lazy("rtsds_b200.module_ops.classifier_forward")
+_deeplab_fwd = _lazy("rtsds_b200.deeplab_engine.deeplab_forward")
+
 
 def _frozen_bn(c):
+    """BatchNorm whose affine parameters never train (the reference switches requires_grad off one by one, :16-44)."""
     bn = nn.BatchNorm2d(c, affine=affine_par)
-    for p in bn.parameters():
-        p.requires_grad = False
+    bn.requires_grad_(False)
     return bn
+
+
+def _conv(cin, cout, k, **kw):
+    return nn.Conv2d(cin, cout, kernel_size=k, bias=False, **kw)
 
 
 class Bottleneck(nn.Module):
@@ -30,20 +52,16 @@ class Bottleneck(nn.Module):
 
     def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, stride=stride, bias=False)
-        self.bn1 = _frozen_bn(planes)
-        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=dilation, bias=False, dilation=dilation)
-        self.bn2 = _frozen_bn(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
-        self.bn3 = _frozen_bn(planes * 4)
-        self.relu = nn.ReLU(inplace=True)
-        self.downsample = downsample
-        self.stride = stride
+        wide = planes * self.expansion
+        pieces = (("conv1", _conv(inplanes, planes, 1, stride=stride)), ("bn1", _frozen_bn(planes)),
+                  ("conv2", _conv(planes, planes, 3, stride=1, padding=dilation, dilation=dilation)), ("bn2", _frozen_bn(planes)),
+                  ("conv3", _conv(planes, wide, 1)), ("bn3", _frozen_bn(wide)), ("relu", nn.ReLU(inplace=True)))
+        for name, mod in pieces:
+            self.add_module(name, mod)
+        self.downsample, self.stride = downsample, stride
 
     def forward(self, x):
-        from rtsds_b200.module_ops import bottleneck_forward
-
-        return bottleneck_forward(self, x)
+        return _bottleneck_fwd(self, x)
 
 
 class ClassifierModule(nn.Module):
@@ -51,84 +69,70 @@ class ClassifierModule(nn.Module):
 
     def __init__(self, inplanes, dilation_series, padding_series, num_classes):
         super().__init__()
-        self.conv2d_list = nn.ModuleList()
-        for dilation, padding in zip(dilation_series, padding_series):
-            self.conv2d_list.append(nn.Conv2d(inplanes, num_classes, kernel_size=3, stride=1, padding=padding,
-                                              dilation=dilation, bias=True))
-        for m in self.conv2d_list:
-            m.weight.data.normal_(0, 0.01)
+        self.conv2d_list = nn.ModuleList(
+            nn.Conv2d(inplanes, num_classes, kernel_size=3, stride=1, padding=pad, dilation=rate, bias=True)
+            for rate, pad in zip(dilation_series, padding_series))
+        for branch in self.conv2d_list:
+            nn.init.normal_(branch.weight, 0, 0.01)
 
     def forward(self, x):
-        from rtsds_b200.module_ops import classifier_forward
-
-        return classifier_forward(self, x)
+        return _classifier_fwd(self, x)
 
 
 class ResNetMulti(nn.Module):
     def __init__(self, block, layers, num_classes):
-        self.inplanes = 64
         super().__init__()
-        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
-        self.bn1 = _frozen_bn(64)
-        self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1, ceil_mode=True)
-        self.layer1 = self._make_layer(block, 64, layers[0])
-        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
-        self.layer3 = self._make_layer(block, 256, layers[2], stride=1, dilation=2)
-        self.layer4 = self._make_layer(block, 512, layers[3], stride=1, dilation=4)
-        self.layer6 = ClassifierModule(2048, [6, 12, 18, 24], [6, 12, 18, 24], num_classes)
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                m.weight.data.normal_(0, 0.01)
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
+        self.inplanes = 64
+        stem = (("conv1", _conv(3, 64, 7, stride=2, padding=3)), ("bn1", _frozen_bn(64)), ("relu", nn.ReLU(inplace=True)),
+                ("maxpool", nn.MaxPool2d(kernel_size=3, stride=2, padding=1, ceil_mode=True)))
+        for name, mod in stem:
+            self.add_module(name, mod)
+        for i, ((planes, stride, dilation), depth) in enumerate(zip(_STAGES, layers), start=1):
+            self.add_module(f"layer{i}", self._make_layer(block, planes, depth, stride=stride, dilation=dilation))
+        self.layer6 = ClassifierModule(512 * block.expansion, list(_ASPP_RATES), list(_ASPP_RATES), num_classes)
+        # reference :84-90: every conv N(0, 0.01) (the classifier's a second time), every BatchNorm gamma=1 beta=0
+        for mod in self.modules():
+            if isinstance(mod, nn.Conv2d):
+                nn.init.normal_(mod.weight, 0, 0.01)
+            elif isinstance(mod, nn.BatchNorm2d):
+                nn.init.ones_(mod.weight)
+                nn.init.zeros_(mod.bias)
         # rtsds_b200 execution options (not part of the reference API)
         self.rtsds_precision = "bf16"       # "fp32": CUDA-core check mode (BASELINE.json 1e-4 tolerance)
         self.rtsds_cuda_graph = True
 
     def _make_layer(self, block, planes, blocks, stride=1, dilation=1):
         # every stage of the reference ends up with a 1x1 projection shortcut on its first block (:88-97)
-        downsample = nn.Sequential(
-            nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
-            nn.BatchNorm2d(planes * block.expansion, affine=affine_par))
-        for p in downsample[1].parameters():
-            p.requires_grad = False
-        layers = [block(self.inplanes, planes, stride, dilation=dilation, downsample=downsample)]
-        self.inplanes = planes * block.expansion
-        for _ in range(1, blocks):
-            layers.append(block(self.inplanes, planes, dilation=dilation))
-        return nn.Sequential(*layers)
+        wide = planes * block.expansion
+        shortcut = nn.Sequential(_conv(self.inplanes, wide, 1, stride=stride), _frozen_bn(wide))
+        chain = [block(self.inplanes, planes, stride, dilation=dilation, downsample=shortcut)]
+        self.inplanes = wide
+        chain += [block(wide, planes, dilation=dilation) for _ in range(blocks - 1)]
+        return nn.Sequential(*chain)
 
     def forward(self, x):
-        from rtsds_b200.deeplab_engine import deeplab_forward
-
-        return deeplab_forward(self, x)
+        return _deeplab_fwd(self, x)
 
     def get_1x_lr_params_no_scale(self):
         """Trainable parameters of everything but the classifier (reference :133-156)."""
-        for mod in (self.conv1, self.bn1, self.layer1, self.layer2, self.layer3, self.layer4):
-            for p in mod.parameters():
-                if p.requires_grad:
-                    yield p
+        for name in ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4"):
+            yield from (p for p in getattr(self, name).parameters() if p.requires_grad)
 
     def get_10x_lr_params(self):
         """Parameters of the classifier (reference :158-170; its `self.multi_level` branch is dead code there)."""
         yield from self.layer6.parameters()
 
     def optim_parameters(self, lr):
-        return [{'params': self.get_1x_lr_params_no_scale(), 'lr': lr},
-                {'params': self.get_10x_lr_params(), 'lr': 10 * lr}]
+        return [dict(params=self.get_1x_lr_params_no_scale(), lr=lr), dict(params=self.get_10x_lr_params(), lr=10 * lr)]
 
 
 def get_deeplab_v2(num_classes=19, pretrain=True, pretrain_model_path='DeepLab_resnet_pretrained_imagenet.pth'):
     model = ResNetMulti(Bottleneck, [3, 4, 23, 3], num_classes)
     if pretrain:
         print('Deeplab pretraining loading...')
-        saved_state_dict = torch.load(pretrain_model_path)
-        new_params = model.state_dict().copy()
-        for key in saved_state_dict:
-            # checkpoint keys carry one leading scope component (reference :185-188)
-            new_params['.'.join(key.split('.')[1:])] = saved_state_dict[key]
-        model.load_state_dict(new_params, strict=False)
+        checkpoint = torch.load(pretrain_model_path)
+        merged = dict(model.state_dict())
+        # checkpoint keys carry one leading scope component (reference :185-188)
+        merged.update({key.split('.', 1)[1]: value for key, value in checkpoint.items()})
+        model.load_state_dict(merged, strict=False)
     return model
