@@ -20,6 +20,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")   # synthetic benchmark: seeded random-init backbone (no hub cache offline)
 import statistics
 import sys
 import threading

@@ -12,9 +12,9 @@
  *     available from rtsds_last_error_string() (thread-local),
  *   - has NO CPU fallback: a non-sm_100 device is RTSDS_EARCH.
  *
- * Activation layout inside the path is NHWC (channels innermost), bf16 in
- * the production mode and fp32 in the "fp32 check" mode (BASELINE.json
- * tolerance 1e-4).  API-boundary tensors (input image, returned logits,
+ * Activation layout inside the path is NHWC (channels innermost): 16-bit in
+ * the production modes (fp16 for eval-mode inference, bf16 for training) and
+ * fp32 in the "fp32 check" mode (BASELINE.json tolerance 1e-4).  API-boundary tensors (input image, returned logits,
  * labels) keep the reference's NCHW fp32 / int64 layout.
  *
  * Reference file:line citations are relative to /root/reference.
@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTSDS_ABI_VERSION 1
+#define RTSDS_ABI_VERSION 2
 
 /* error codes */
 #define RTSDS_OK        0
@@ -42,6 +42,8 @@ extern "C" {
 /* element types of activation buffers */
 #define RTSDS_F32   0
 #define RTSDS_BF16  1
+#define RTSDS_F16   2   /* IEEE half: the inference (eval-mode) storage/operand type — same tcgen05 kind::f16 rate as bf16,
+                           11-bit significand; on BASELINE config 1 it keeps argmax agreement >= 99.9 % where bf16 gives 99.78 % */
 
 /* activations fused into conv epilogues */
 #define RTSDS_ACT_NONE   0
@@ -100,8 +102,8 @@ typedef struct RtsdsConvDesc {
     int oh, ow;
     int act;
     float slope;
-    int in_dtype;      /* RTSDS_BF16 (tensor-core path) or RTSDS_F32 (check path) */
-    int out_dtype;     /* RTSDS_BF16 or RTSDS_F32 */
+    int in_dtype;      /* RTSDS_BF16 / RTSDS_F16 (tensor-core path; the packed weights have the same type) or RTSDS_F32 (check path) */
+    int out_dtype;     /* in_dtype or RTSDS_F32 */
     int split_k;       /* >1: split the reduction over this many CTAs (tensor-core path) */
 } RtsdsConvDesc;
 
@@ -211,13 +213,14 @@ int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, int cin, int
 /* Tensor-core stems of BiSeNet: the context-path conv7x7 s2 p3 3->64 (build_contextpath.py:19) and the
  * spatial-path conv3x3 s2 p1 3->64 (build_bisenet.py:24) read the same image on the same output grid and are
  * fused into one tcgen05 implicit GEMM (N = 64 + 64) whose im2col tile is gathered into swizzled shared
- * memory.  wpk: bf16 [128][192] from rtsds_stem_pack_weights; scale/shift: fp32 [128] (context-path BN in
+ * memory.  dtype: RTSDS_BF16 or RTSDS_F16 (operands and outputs; the weight gradient is bf16 only).
+ * wpk: [128][192] of dtype from rtsds_stem_pack_weights; scale/shift: fp32 [128] (context-path BN in
  * 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
  * wgrad: d_raw_*: NHWC bf16 [n,oh,ow,64]; dw_ws: fp32 [128*192] scratch, zero on entry and on return;
  * g7/g3: OIHW fp32 gradients, accumulated. */
-int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, void* wpk, rtsds_stream_t s);
+int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, int dtype, void* wpk, rtsds_stream_t s);
 int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
-                           const float* shift, int relu, float* stats_cp, float* stats_sp, void* y_cp,
+                           const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
                            void* y_sp, rtsds_stream_t s);
 int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_raw_cp,
                              const void* d_raw_sp, float* dw_ws, float* g7_oihw, float* g3_oihw,
@@ -326,12 +329,17 @@ int rtsds_arm_gate(const float* pooled, const float* w, const float* b, const fl
                    float* lin_out, float* xhat_out, rtsds_stream_t s);
 
 /* Bilinear resize (F.interpolate(mode='bilinear', align_corners=False), :151-152)
- * of src NHWC [n,h,w,c] scaled by gate[n,c] (NULL = 1) into dst NHWC
+ * of src NHWC [n,h,w,c] scaled by gate[n,c] (NULL = 1) and the constant gate_scale into dst NHWC
  * [n,oh,ow,dst_ld] at channel offset dst_coff: writes straight into the
  * torch.cat buffer of :153/:72. */
 int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int c, int src_ld,
-                           const float* gate, int oh, int ow, void* dst, int dst_ld,
+                           const float* gate, float gate_scale, int oh, int ow, void* dst, int dst_ld,
                            int dst_coff, int dtype, rtsds_stream_t s);
+/* Multiply input channels [c0, c1) of a packed conv weight ([rows][cin] of dtype, rows = cout_pad*taps) by `factor`:
+ * the block exponent of an activation slot stored scaled (fp16 inference keeps the `cx2 * tail` slot of the concat
+ * buffer, build_bisenet.py:149 — quadratic in the activations — at 2^-8 and its FFM weights at 2^8). */
+int rtsds_scale_packed_channels(void* w_packed, int dtype, int64_t rows, int cin, int c0, int c1, float factor,
+                                rtsds_stream_t s);
 
 /* FeatureFusionModule attention (:75-80) + final 1x1 conv (:167), evaluated at
  * feature resolution (the 1x1 conv commutes with the bilinear resize):

@@ -128,8 +128,10 @@ class BiSeNet(torch.nn.Module):
                                                   "supervision1", "supervision2", "feature_fusion_module", "conv")]
         self._context_name, self._num_classes = context_path, num_classes
         # rtsds_b200 execution options (not part of the reference API):
-        #   precision "bf16" (tcgen05 path) or "fp32" (check mode, BASELINE.json 1e-4 tolerance)
+        #   precision "bf16" (tcgen05 path: bf16 training, eval-mode inference in rtsds_eval_precision) or "fp32" (check
+        #   mode, BASELINE.json 1e-4 tolerance); eval precision "fp16" (default) or "bf16"
         self.rtsds_precision = "bf16"
+        self.rtsds_eval_precision = "fp16"
         self.rtsds_cuda_graph = True
 
     def init_weight(self):

@@ -112,7 +112,16 @@ def _load_pretrained(net: nn.Module, arch: str) -> None:
     files = {"resnet18": "resnet18-f37072fd.pth", "resnet101": "resnet101-63fe2227.pth"}
     path = os.path.join(torch.hub.get_dir(), "checkpoints", files[arch])
     if not os.path.exists(path):  # never touch the network from the hot path
-        warnings.warn(f"{arch}: ImageNet weights not in the local hub cache ({path}); using random init")
+        # The reference fails here without a network (URLError from torch.hub).  Silently training from a random backbone
+        # would change mIoU completely, so random init needs an explicit opt-in; build_bisenet.py disables `warnings`
+        # globally, hence a plain stderr line rather than warnings.warn.
+        if os.environ.get("RTSDS_ALLOW_RANDOM_INIT") != "1":
+            raise RuntimeError(f"{arch}: pretrained=True but the ImageNet weights are not in the local hub cache ({path}). "
+                               "Place the file there, or set RTSDS_ALLOW_RANDOM_INIT=1 to keep the seeded random init "
+                               "(synthetic benchmarks / parity tests).")
+        import sys
+        print(f"[rtsds_b200] {arch}: ImageNet weights not found ({path}); RTSDS_ALLOW_RANDOM_INIT=1 -> random init",
+              file=sys.stderr)
         return
     net.load_state_dict(torch.load(path, map_location="cpu"))
 
@@ -156,10 +165,11 @@ class resnet101(_ContextPath):
 
 
 def build_contextpath(name):
-    # The reference eagerly builds BOTH backbones (build_contextpath.py:59-64);
-    # only the requested one is built here.
-    if name == "resnet18":
-        return resnet18(pretrained=True)
-    if name == "resnet101":
-        return resnet101(pretrained=True)
-    raise KeyError(name)
+    # The reference eagerly builds BOTH backbones, resnet18 first (build_contextpath.py:59-64), and returns one.  The
+    # discarded one still consumes the global RNG stream, so it is built here too: under torch.manual_seed(s) the
+    # drop-in then draws exactly the reference's random-init weights (tests/test_config1_cpu.py pins this against
+    # tests/golden/config1.npz, produced by the real reference).
+    if name not in ("resnet18", "resnet101"):
+        raise KeyError(name)
+    model = {"resnet18": resnet18(pretrained=True), "resnet101": resnet101(pretrained=True)}
+    return model[name]

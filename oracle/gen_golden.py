@@ -201,11 +201,66 @@ def gen_deeplab(R, name, seed, n, h, w):
     print("wrote", name)
 
 
+def config1_inputs():
+    """BASELINE.json configs[0] / SURVEY 8(c) anchor, verbatim: data generator seed 1234, x ~ N(0,1) [2,3,512,1024],
+    labels uniform in [0,19] (19 = ignore)."""
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 3, 512, 1024, generator=g)
+    y = torch.randint(0, 20, (2, 512, 1024), generator=g)
+    return x, y
+
+
+def gen_config1(R, name="config1"):
+    """BASELINE config 1 on the REAL reference: torch.manual_seed(42) -> BiSeNet(19, 'resnet18') (the constructor's own
+    random init), eval and train forward, 3xCE with ignore_index 19 / 255, gradient norms.  Stored: per-tensor
+    checksums of the seeded state_dict (pins that the drop-in constructor draws the same weights), logits sub-sampled
+    every 16th pixel, argmax every 4th pixel, float64 checksums of the full tensors."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    x, y = config1_inputs()
+    torch.manual_seed(42)
+    m = R["BiSeNet"](19, "resnet18")
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    keys = [k for k, v in sd0.items() if v.dtype.is_floating_point]
+    out = {"state_keys": np.array(keys),
+           "state_sum": np.array([sd0[k].double().sum().item() for k in keys]),
+           "state_sumsq": np.array([(sd0[k].double() ** 2).sum().item() for k in keys]),
+           "x_sum": summarize(x), "y_sum": np.array([y.double().sum().item()])}
+    S, SA = 16, 4
+    m.eval()
+    with torch.no_grad():
+        r = m(x)
+    out["eval_result"] = r[..., ::S, ::S].contiguous().numpy().astype(np.float32)
+    out["eval_result_sum"] = summarize(r)
+    out["eval_argmax"] = r.argmax(1)[..., ::SA, ::SA].numpy().astype(np.int8)
+    m.train()
+    res, s1, s2 = m(x)
+    for k, t in (("train_result", res), ("train_sup1", s1), ("train_sup2", s2)):
+        out[k] = t.detach()[..., ::S, ::S].contiguous().numpy().astype(np.float32)
+        out[k + "_sum"] = summarize(t)
+        out[k + "_argmax"] = t.argmax(1)[..., ::SA, ::SA].numpy().astype(np.int8)
+    for ign in (19, 255):
+        yy = y.clone()
+        if ign == 255:
+            yy[yy == 19] = 255
+        loss = sum(F.cross_entropy(t, yy, ignore_index=ign) for t in (res, s1, s2))
+        out[f"train_loss_ign{ign}"] = np.array([loss.item()], dtype=np.float64)
+    loss = sum(F.cross_entropy(t, y, ignore_index=19) for t in (res, s1, s2))
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    out["grad_names"] = np.array(sorted(grads.keys()))
+    out["grad_norms"] = np.array([grads[k].double().norm().item() for k in sorted(grads.keys())])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, "loss ign19", out["train_loss_ign19"], "ign255", out["train_loss_ign255"])
+
+
 def main():
     assert refshim.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     R = refshim.load_models()
+    if "config1" in sys.argv[1:]:
+        gen_config1(R)
+        return
     U = refshim.load_utils_functions()
     gen_fast_hist(U)
     gen_bisenet(R, "bisenet_64x96", 0, 2, 64, 96)

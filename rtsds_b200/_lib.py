@@ -13,7 +13,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "librtsds_b200.so"
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
 
@@ -75,8 +76,8 @@ SIGNATURES = {
     "rtsds_pack_conv_weight_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_unpack_conv_wgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_stem_conv_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P, _I, _P, _P]),
-    "rtsds_stem_pack_weights": (_I, [_P, _P, _P, _P]),
-    "rtsds_stem_pair_tc_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "rtsds_stem_pack_weights": (_I, [_P, _P, _I, _P, _P]),
+    "rtsds_stem_pair_tc_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "rtsds_stem_pair_tc_wgrad": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "rtsds_stem_s2d_pack": (_I, [_P, _I, _I, _I, _P, _P]),
     "rtsds_stem_s2d_weight": (_I, [_P, _I, _I, _I, _P, _P]),
@@ -105,7 +106,8 @@ SIGNATURES = {
     "rtsds_resize_to_nchw_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rtsds_global_avgpool": (_I, [_P, _I, _L, _I, _I, _I, _P, _P]),
     "rtsds_arm_gate": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "rtsds_gate_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),
+    "rtsds_gate_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _F, _I, _I, _P, _I, _I, _I, _P]),
+    "rtsds_scale_packed_channels": (_I, [_P, _I, _L, _I, _I, _I, _F, _P]),
     "rtsds_ffm_head": (_I, [_P, _I, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "rtsds_resize_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_resize_ce_argmax_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P]),
@@ -163,7 +165,7 @@ class _DryLib:
                 return b"dry run"
             if name == "rtsds_launch_count":
                 return len(self.calls)
-            return 1 if name == "rtsds_abi_version" else 0
+            return ABI_VERSION if name == "rtsds_abi_version" else 0
 
         return fn
 
@@ -198,7 +200,7 @@ def lib():
             raise RtsdsError(f"{LIB_PATH} does not export {name}; rebuild with `python -m rtsds_b200.build --force`") from e
         fn.restype = res
         fn.argtypes = args
-    if handle.rtsds_abi_version() != 1:
+    if handle.rtsds_abi_version() != ABI_VERSION:
         raise RtsdsError("librtsds_b200.so ABI version mismatch")
     _lib = handle
     return handle

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -34,6 +35,14 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
     return __float2bfloat16_rn(v);
 }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+// fp16 conversions SATURATE to the largest finite half (cvt.rn.satfinite): an out-of-range activation degrades to a
+// clipped value instead of poisoning everything downstream with inf / NaN
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return __ushort_as_half(h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -43,6 +52,35 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+}
+// 16-bit storage selected at run time (warp-uniform flag): fp16 (RTSDS_F16) or bf16 (RTSDS_BF16)
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float2 unpack_16x2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
+__device__ __forceinline__ float ld_16(const void* p, long long i, bool f16) {
+    return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_16(void* p, long long i, float v, bool f16) {
+    if (f16) reinterpret_cast<__half*>(p)[i] = from_f32<__half>(v);
+    else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+// typed forms for kernels templated on the storage type
+template <typename T> __device__ __forceinline__ uint32_t pack_x2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack_x2<__nv_bfloat16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack_x2<__half>(float lo, float hi) { return pack_f16x2(lo, hi); }
+template <typename T> __device__ __forceinline__ float2 unpack_x2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack_x2<__nv_bfloat16>(uint32_t u) { return unpack_bf16x2(u); }
+template <> __device__ __forceinline__ float2 unpack_x2<__half>(uint32_t u) { return unpack_f16x2(u); }
+static inline bool is_16bit(int dtype) { return dtype == RTSDS_BF16 || dtype == RTSDS_F16; }
+static inline size_t dtype_size(int dtype) { return dtype == RTSDS_F32 ? 4 : 2; }
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == RTSDS_ACT_RELU) return fmaxf(v, 0.0f);

@@ -460,10 +460,13 @@ static int pack_weight_impl(const float* w_oihw, int cout, int cin, int cin_pad,
                             void* w_packed, rtsds_stream_t s) {
     RTSDS_REQUIRE(w_oihw && w_packed, "pack_conv_weight: NULL argument");
     RTSDS_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout && cin_pad >= cin, "pack_conv_weight: bad shape");
-    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "pack_conv_weight: bad dtype");
+    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32 || dtype == RTSDS_F16, "pack_conv_weight: bad dtype");
     const long long total = static_cast<long long>(cout_pad) * kh * kw * cin_pad;
     int grid = static_cast<int>(cdiv(total, 256) > 2048 ? 2048 : cdiv(total, 256));
-    if (dtype == RTSDS_BF16)
+    if (dtype == RTSDS_F16)
+        pack_weight_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, cin_pad, kh * kw, cout_pad,
+                                                                  reinterpret_cast<__half*>(w_packed));
+    else if (dtype == RTSDS_BF16)
         pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin, cin_pad, kh * kw, cout_pad,
                                                                          reinterpret_cast<__nv_bfloat16*>(w_packed));
     else
@@ -583,4 +586,33 @@ extern "C" int rtsds_unpack_conv_wgrads_batch(const RtsdsUnpackJob* jobs, int n_
         if (rc != RTSDS_OK) return rc;
     }
     return RTSDS_OK;
+}
+
+// ---- block exponent of an activation slot: scale input channels [c0, c1) of a packed weight -------------------------
+namespace rtsds {
+template <typename T>
+__global__ void scale_packed_channels_kernel(T* __restrict__ w, long long rows, int cin, int c0, int c1, float factor) {
+    const int span = c1 - c0;
+    const long long total = rows * span;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / span;
+        const int c = c0 + static_cast<int>(i - r * span);
+        T* p = w + r * cin + c;
+        *p = from_f32<T>(to_f32(*p) * factor);
+    }
+}
+}  // namespace rtsds
+
+extern "C" int rtsds_scale_packed_channels(void* w_packed, int dtype, int64_t rows, int cin, int c0, int c1, float factor,
+                                           rtsds_stream_t s) {
+    RTSDS_REQUIRE(w_packed && rows > 0 && cin > 0 && c0 >= 0 && c1 > c0 && c1 <= cin, "scale_packed_channels: bad argument");
+    const long long total = rows * (c1 - c0);
+    const int grid = static_cast<int>(cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256));
+    if (dtype == RTSDS_F16) scale_packed_channels_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<__half*>(w_packed), rows, cin, c0, c1, factor);
+    else if (dtype == RTSDS_BF16) scale_packed_channels_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<__nv_bfloat16*>(w_packed), rows, cin, c0, c1, factor);
+    else if (dtype == RTSDS_F32) scale_packed_channels_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<float*>(w_packed), rows, cin, c0, c1, factor);
+    else { set_error("scale_packed_channels: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("scale_packed_channels_kernel");
 }

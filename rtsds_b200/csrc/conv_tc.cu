@@ -69,6 +69,7 @@ struct TcParams {
     float* partial;                       // split-K slices [split][M_total][cout_pad]
     int out_dtype, act;
     float slope;
+    int f16;                              // operands (and 16-bit outputs / residuals) are IEEE half instead of bf16
 };
 
 // Reduce 32 per-thread values across the 32 lanes of a warp so that lane j
@@ -110,17 +111,18 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
             const bool full = (co0 + 32 <= p.cout);
-            if (p.out_dtype == RTSDS_BF16) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + out_off + co0;
-                const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+            if (p.out_dtype != RTSDS_F32) {
+                const bool f16 = p.out_dtype == RTSDS_F16;
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + out_off + co0;
+                const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual);
                 if (full) {
                     if (res) {
                         const uint4* rp = reinterpret_cast<const uint4*>(res + res_off + co0);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 rv = __ldg(rp + g);
-                            float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y);
-                            float2 c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+                            float2 a = unpack_16x2(rv.x, f16), b = unpack_16x2(rv.y, f16);
+                            float2 c = unpack_16x2(rv.z, f16), d = unpack_16x2(rv.w, f16);
                             v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
                             v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
                         }
@@ -128,10 +130,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 o;
-                        o.x = pack_bf16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope));
-                        o.y = pack_bf16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope));
-                        o.z = pack_bf16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope));
-                        o.w = pack_bf16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope));
+                        o.x = pack_16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope), f16);
+                        o.y = pack_16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope), f16);
+                        o.z = pack_16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope), f16);
+                        o.w = pack_16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope), f16);
                         *reinterpret_cast<uint4*>(dst + g * 8) = o;
                     }
                 } else {
@@ -139,8 +141,8 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
                     for (int j = 0; j < 32; ++j) {
                         if (co0 + j < p.cout) {
                             float x = v[j];
-                            if (res) x += __bfloat162float(res[res_off + co0 + j]);
-                            dst[j] = __float2bfloat16_rn(apply_act(x, p.act, p.slope));
+                            if (res) x += ld_16(res, res_off + co0 + j, f16);
+                            st_16(dst, j, apply_act(x, p.act, p.slope), f16);
                         }
                     }
                 }
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+    const uint32_t IDESC = ptx::umma_idesc_16(TC_BLOCK_M, BLOCK_N, p.f16 != 0);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr uint32_t TMEM_COLS = 2 * (BLOCK_N < 32 ? 32 : BLOCK_N);
-    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+    const uint32_t IDESC = ptx::umma_idesc_16(TC_BLOCK_M, BLOCK_N, p.f16 != 0);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -687,9 +689,10 @@ splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_t
                 atomicAdd(&s_acc[cout + c], raw * raw);
             }
             float o = raw * (p.scale ? p.scale[c] : 1.0f) + (p.shift ? p.shift[c] : 0.0f);
-            if (p.out_dtype == RTSDS_BF16) {
-                if (p.residual) o += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + c]);
-                reinterpret_cast<__nv_bfloat16*>(p.y)[out_off + c] = __float2bfloat16_rn(apply_act(o, p.act, p.slope));
+            if (p.out_dtype != RTSDS_F32) {
+                const bool f16 = p.out_dtype == RTSDS_F16;
+                if (p.residual) o += ld_16(p.residual, res_off + c, f16);
+                st_16(p.y, out_off + c, apply_act(o, p.act, p.slope), f16);
             } else {
                 if (p.residual) o += reinterpret_cast<const float*>(p.residual)[res_off + c];
                 reinterpret_cast<float*>(p.y)[out_off + c] = apply_act(o, p.act, p.slope);
@@ -949,7 +952,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     p.out_sn = t.out_sn; p.out_sh = t.out_sh; p.out_sw = t.out_sw;
     p.res_sn = t.res_sn; p.res_sh = t.res_sh; p.res_sw = t.res_sw;
     p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.y = t.y;
-    p.out_dtype = t.out_dtype; p.act = t.act; p.slope = t.slope;
+    p.out_dtype = t.out_dtype; p.act = t.act; p.slope = t.slope; p.f16 = t.in_f16;
     int first_used = -1;
     for (int i = 0; i < 4; ++i) {
         if (!t.view[i].used) continue;
@@ -1071,12 +1074,12 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
                                    const float* shift, const void* residual, float* stats, void* y,
                                    void* workspace, size_t ws_bytes, rtsds_stream_t s) {
     RTSDS_REQUIRE(d && x && w && y, "conv2d_tc_fwd: NULL argument");
-    RTSDS_REQUIRE(d->in_dtype == RTSDS_BF16, "conv2d_tc_fwd: input must be bf16");
-    RTSDS_REQUIRE(d->out_dtype == RTSDS_BF16 || d->out_dtype == RTSDS_F32, "conv2d_tc_fwd: bad out_dtype");
+    RTSDS_REQUIRE(is_16bit(d->in_dtype), "conv2d_tc_fwd: input must be bf16 or fp16");
+    RTSDS_REQUIRE(d->out_dtype == d->in_dtype || d->out_dtype == RTSDS_F32, "conv2d_tc_fwd: out_dtype must be the input type or fp32");
     RTSDS_REQUIRE(d->out_ld >= d->cout, "conv2d_tc_fwd: out_ld < cout");
     RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv2d_tc_fwd: pointers must be 16-byte aligned");
-    const int vec = d->out_dtype == RTSDS_BF16 ? 8 : 4;
+    const int vec = d->out_dtype != RTSDS_F32 ? 8 : 4;
     RTSDS_REQUIRE(d->out_ld % vec == 0, "conv2d_tc_fwd: out_ld=%d must be a multiple of %d", d->out_ld, vec);
     if (residual) {
         RTSDS_REQUIRE(d->res_ld >= d->cout && d->res_ld % vec == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,

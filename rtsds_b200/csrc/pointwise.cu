@@ -56,6 +56,18 @@ template <> struct V8io<__nv_bfloat16> {
         *reinterpret_cast<uint4*>(p) = u;
     }
 };
+template <> struct V8io<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float (&v)[8]) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    static __device__ __forceinline__ void st(__half* p, const float (&v)[8]) {
+        uint4 u;
+        u.x = pack_f16x2(v[0], v[1]); u.y = pack_f16x2(v[2], v[3]); u.z = pack_f16x2(v[4], v[5]); u.w = pack_f16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
 template <> struct V8io<float> {
     static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
         float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -234,6 +246,19 @@ __device__ __forceinline__ V8 ld8(const __nv_bfloat16* p) {
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
     return r;
 }
+__device__ __forceinline__ V8 ld8(const __half* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    V8 r;
+    float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ void st8(__half* p, const V8& r) {
+    uint4 u;
+    u.x = pack_f16x2(r.v[0], r.v[1]); u.y = pack_f16x2(r.v[2], r.v[3]);
+    u.z = pack_f16x2(r.v[4], r.v[5]); u.w = pack_f16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ V8 ld8(const float* p) {
     float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     V8 r;
@@ -255,8 +280,8 @@ __device__ __forceinline__ void st8(float* p, const V8& r) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int src_ld, const float* __restrict__ gate,
-                   int oh, int ow, float rh, float rw, T* __restrict__ dst, int dst_ld, int dst_coff, FastDiv dcg, FastDiv dow,
-                   FastDiv doh) {
+                   float gate_scale, int oh, int ow, float rh, float rw, T* __restrict__ dst, int dst_ld, int dst_coff,
+                   FastDiv dcg, FastDiv dow, FastDiv doh) {
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;          // < 2^31 (host check)
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -279,7 +304,7 @@ gate_resize_kernel(const T* __restrict__ src, int n, int h, int w, int c, int sr
         for (int j = 0; j < 8; ++j) {
             float v = ly.l0 * (lx.l0 * p00.v[j] + lx.l1 * p01.v[j]) + ly.l1 * (lx.l0 * p10.v[j] + lx.l1 * p11.v[j]);
             if (gate) v *= gv.v[j];
-            o.v[j] = v;
+            o.v[j] = v * gate_scale;
         }
         st8(dst + ((static_cast<long long>(img) * oh + oy) * ow + ox) * dst_ld + dst_coff + g8 * 8, o);
     }
@@ -517,6 +542,8 @@ extern "C" int rtsds_global_avgpool(const void* x, int n, int64_t hw, int c, int
     const float inv = 1.0f / static_cast<float>(hw);
     if (dtype == RTSDS_BF16)
         gap_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, ld, inv, out);
+    else if (dtype == RTSDS_F16)
+        gap_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), hw, c, ld, inv, out);
     else if (dtype == RTSDS_F32)
         gap_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), hw, c, ld, inv, out);
     else { set_error("global_avgpool: bad dtype"); return RTSDS_EINVAL; }
@@ -542,7 +569,7 @@ extern "C" int rtsds_arm_gate(const float* pooled, const float* w, const float* 
 }
 
 extern "C" int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int c, int src_ld, const float* gate,
-                                      int oh, int ow, void* dst, int dst_ld, int dst_coff, int dtype,
+                                      float gate_scale, int oh, int ow, void* dst, int dst_ld, int dst_coff, int dtype,
                                       rtsds_stream_t s) {
     RTSDS_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "gate_resize_nhwc: bad argument");
     RTSDS_REQUIRE(c > 0 && c % 8 == 0 && src_ld >= c && dst_ld >= dst_coff + c, "gate_resize_nhwc: bad channel layout");
@@ -552,11 +579,15 @@ extern "C" int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int 
     const int grid = grid_for(static_cast<long long>(n) * oh * ow * (c / 8), 256);
     if (dtype == RTSDS_BF16)
         gate_resize_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(src), n, h, w, c,
-                                                                          src_ld, gate, oh, ow, rh, rw,
+                                                                          src_ld, gate, gate_scale, oh, ow, rh, rw,
                                                                           reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff,
                                                                           make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh));
+    else if (dtype == RTSDS_F16)
+        gate_resize_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(src), n, h, w, c, src_ld, gate, gate_scale, oh, ow, rh, rw,
+                                                                   reinterpret_cast<__half*>(dst), dst_ld, dst_coff,
+                                                                   make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh));
     else if (dtype == RTSDS_F32)
-        gate_resize_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(src), n, h, w, c, src_ld, gate,
+        gate_resize_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(src), n, h, w, c, src_ld, gate, gate_scale,
                                                                   oh, ow, rh, rw, reinterpret_cast<float*>(dst), dst_ld, dst_coff, make_fastdiv(c / 8), make_fastdiv(ow), make_fastdiv(oh));
     else { set_error("gate_resize_nhwc: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
@@ -605,7 +636,8 @@ extern "C" int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, 
 extern "C" int rtsds_nchw_to_nhwc(const float* x, int n, int c, int64_t hw, int dtype, void* y, int ld, int c_off, rtsds_stream_t s) {
     RTSDS_REQUIRE(x && y && n > 0 && c > 0 && hw > 0 && ld >= c_off + c && c_off >= 0 && n <= 65535, "nchw_to_nhwc: bad argument");
     dim3 grid(static_cast<unsigned>(cdiv(hw, 32)), static_cast<unsigned>(cdiv(c, 32)), n), block(32, 8);
-    if (dtype == RTSDS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<__nv_bfloat16*>(y), ld, c_off);
+    if (dtype == RTSDS_F16) nchw_to_nhwc_kernel<__half><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<__half*>(y), ld, c_off);
+    else if (dtype == RTSDS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<__nv_bfloat16*>(y), ld, c_off);
     else if (dtype == RTSDS_F32) nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(s)>>>(x, c, hw, reinterpret_cast<float*>(y), ld, c_off);
     else { set_error("nchw_to_nhwc: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
@@ -615,7 +647,8 @@ extern "C" int rtsds_nchw_to_nhwc(const float* x, int n, int c, int64_t hw, int 
 extern "C" int rtsds_nhwc_to_nchw(const void* x, int dtype, int ld, int c_off, int n, int c, int64_t hw, float* y, rtsds_stream_t s) {
     RTSDS_REQUIRE(x && y && n > 0 && c > 0 && hw > 0 && ld >= c_off + c && c_off >= 0 && n <= 65535, "nhwc_to_nchw: bad argument");
     dim3 grid(static_cast<unsigned>(cdiv(hw, 32)), static_cast<unsigned>(cdiv(c, 32)), n), block(32, 8);
-    if (dtype == RTSDS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, c_off, c, hw, y);
+    if (dtype == RTSDS_F16) nhwc_to_nchw_kernel<__half><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(x), ld, c_off, c, hw, y);
+    else if (dtype == RTSDS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, c_off, c, hw, y);
     else if (dtype == RTSDS_F32) nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, c_off, c, hw, y);
     else { set_error("nhwc_to_nchw: bad dtype"); return RTSDS_EINVAL; }
     count_launch();

@@ -231,5 +231,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Same with the operand type chosen at run time: both A and B fp16 (format 0) or both bf16 (format 1).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, bool f16, int a_mn_major = 0, int b_mn_major = 0) {
+    return umma_idesc_bf16(m, n, a_mn_major, b_mn_major) & ~(f16 ? ((1u << 7) | (1u << 10)) : 0u);
+}
+
 }  // namespace ptx
 }  // namespace rtsds

@@ -202,6 +202,19 @@ __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
     return r;
 }
+__device__ __forceinline__ Vec8 load8(const __half* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    Vec8 r;
+    float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ void store8(__half* p, const Vec8& r) {
+    uint4 u;
+    u.x = pack_f16x2(r.v[0], r.v[1]); u.y = pack_f16x2(r.v[2], r.v[3]);
+    u.z = pack_f16x2(r.v[4], r.v[5]); u.w = pack_f16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ Vec8 load8(const float* p) {
     float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     Vec8 r;
@@ -326,7 +339,8 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
                             rtsds_stream_t s) {
     RTSDS_REQUIRE(x && y, "maxpool: NULL argument");
     RTSDS_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape (c must be a multiple of 8)");
-    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32, "maxpool: bad dtype");
+    RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32 || dtype == RTSDS_F16, "maxpool: bad dtype");
+    RTSDS_REQUIRE(!(idx && dtype == RTSDS_F16), "maxpool: the training form (idx) is bf16 / fp32 only");
     auto osz = [&](int in) {
         int o = ceil_mode ? (in + 2 - 3 + 1) / 2 + 1 : (in + 2 - 3) / 2 + 1;
         if (ceil_mode && (o - 1) * 2 >= in + 1) --o;   // last window must start inside input+left pad (torch rule)
@@ -347,7 +361,10 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
         count_launch();
         return check_launch("maxpool_idx_kernel");
     }
-    if (dtype == RTSDS_BF16)
+    if (dtype == RTSDS_F16)
+        maxpool_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(x), n, h, w, c, oh, ow,
+                                                               reinterpret_cast<__half*>(y), dv);
+    else if (dtype == RTSDS_BF16)
         maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh, ow,
                                                                       reinterpret_cast<__nv_bfloat16*>(y), dv);
     else

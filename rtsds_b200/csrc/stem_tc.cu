@@ -90,7 +90,7 @@ __device__ __forceinline__ void patch_issue(const StemTcParams& p, int t, int ti
 
 // one thread builds row `m` of the swizzled tile from the staged patch.  Fully unrolled: every
 // k = (c*7 + r)*7 + s is a compile-time constant, so are all shared-memory offsets.
-template <int TW>
+template <int TW, bool F16>
 __device__ __forceinline__ void gather_row(const float* patch, uint8_t* tile, int m) {
     using P = Patch<TW>;
     const int my = m / TW, mx = m - my * TW;
@@ -109,8 +109,13 @@ __device__ __forceinline__ void gather_row(const float* patch, uint8_t* tile, in
             }
         }
         uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        if (F16) {
+            u.x = pack_f16x2(v[0], v[1]); u.y = pack_f16x2(v[2], v[3]);
+            u.z = pack_f16x2(v[4], v[5]); u.w = pack_f16x2(v[6], v[7]);
+        } else {
+            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        }
         const int atom = chunk >> 3, j = chunk & 7;
         *reinterpret_cast<uint4*>(tile + atom * S_ATOM_BYTES + m * 128 + ((j ^ (m & 7)) << 4)) = u;
     }
@@ -137,7 +142,7 @@ __device__ __forceinline__ void gather_row(const float* patch, uint8_t* tile, in
             ptx::cp_async_commit();                                                                          \
             ptx::mbar_wait(&EMPTY_BAR[buf], ph ^ 1);                                                         \
             EXTRA                                                                                            \
-            gather_row<TW>(s_patch + (it % S_PATCHES) * S_PATCH_FLOATS, TILE_BASE + buf * S_A_BYTES, m);     \
+            gather_row<TW, STEM_F16>(s_patch + (it % S_PATCHES) * S_PATCH_FLOATS, TILE_BASE + buf * S_A_BYTES, m);     \
             ptx::fence_proxy_async();                                                                        \
             ptx::mbar_arrive(&FULL_BAR[buf]);                                                                \
         }                                                                                                    \
@@ -171,10 +176,11 @@ __device__ __forceinline__ float warp_tsum(float (&v)[32], int lane) {
 struct StemWgMaps { CUtensorMap d_cp, d_sp; };      // [64, ow, oh, n] bf16 each: d_raw (wgrad loads) / y (forward stores)
 
 constexpr int SF_THREADS = 13 * 32;                 // 4 gather + 1 MMA + 8 epilogue warps
-template <int TW>
+template <int TW, bool F16>
 __global__ void __launch_bounds__(SF_THREADS, 1)
 stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
-    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 128);
+    constexpr bool STEM_F16 = F16;                        // operand / output type: IEEE half (eval-mode inference) or bf16
+    constexpr uint32_t IDESC = ptx::umma_idesc_16(128, 128, F16);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_a = smem;                                   // 2 x 48 KiB
@@ -297,8 +303,13 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 u;
-                    u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                    u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    if (F16) {
+                        u.x = pack_f16x2(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_f16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        u.z = pack_f16x2(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_f16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    } else {
+                        u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    }
                     packed[half * 4 + g] = u;
                 }
             }
@@ -338,6 +349,7 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
 template <int TW>
 __global__ void __launch_bounds__(S_THREADS, 1)
 stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
+    constexpr bool STEM_F16 = false;                      // training operands are bf16
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, SK, 1, 1);     // both operands MN-major, N = 192
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -412,7 +424,8 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams
 }
 
 // pack both stems' OIHW fp32 weights into the fused [128][192] bf16 operand
-__global__ void stem_pack_kernel(const float* __restrict__ w7, const float* __restrict__ w3, __nv_bfloat16* __restrict__ out) {
+template <typename T>
+__global__ void stem_pack_kernel(const float* __restrict__ w7, const float* __restrict__ w3, T* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 128 * SK) return;
     const int row = i / SK, k = i - row * SK;
@@ -422,7 +435,7 @@ __global__ void stem_pack_kernel(const float* __restrict__ w7, const float* __re
         if (row < 64) v = w7[(row * 3 + c) * 49 + r * 7 + s];
         else if (r >= 2 && r <= 4 && s >= 2 && s <= 4) v = w3[((row - 64) * 3 + c) * 9 + (r - 2) * 3 + (s - 2)];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = from_f32<T>(v);
 }
 
 // scatter the fused fp32 gradient [128][192] back to the two OIHW gradients (accumulate), and clear it
@@ -487,10 +500,12 @@ static int stem_make_maps(const StemTcParams& p, const void* base_cp, const void
 
 using namespace rtsds;
 
-extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, void* wpk, rtsds_stream_t s) {
+extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, int dtype, void* wpk, rtsds_stream_t s) {
     RTSDS_REQUIRE(w7_oihw && w3_oihw && wpk, "stem_pack_weights: NULL argument");
-    stem_pack_kernel<<<static_cast<int>(cdiv(128 * SK, 256)), 256, 0, as_stream(s)>>>(w7_oihw, w3_oihw,
-                                                                                   reinterpret_cast<__nv_bfloat16*>(wpk));
+    RTSDS_REQUIRE(is_16bit(dtype), "stem_pack_weights: dtype must be bf16 or fp16");
+    const int g = static_cast<int>(cdiv(128 * SK, 256));
+    if (dtype == RTSDS_F16) stem_pack_kernel<__half><<<g, 256, 0, as_stream(s)>>>(w7_oihw, w3_oihw, reinterpret_cast<__half*>(wpk));
+    else stem_pack_kernel<__nv_bfloat16><<<g, 256, 0, as_stream(s)>>>(w7_oihw, w3_oihw, reinterpret_cast<__nv_bfloat16*>(wpk));
     count_launch();
     return check_launch("stem_pack_kernel");
 }
@@ -498,9 +513,10 @@ extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oih
 // Fused tensor-core stems.  x: NCHW fp32 [n,3,h,w]; wpk from rtsds_stem_pack_weights; scale/shift: fp32 [128]
 // (context-path BN in 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
 extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
-                                      const float* shift, int relu, float* stats_cp, float* stats_sp, void* y_cp,
+                                      const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
                                       void* y_sp, rtsds_stream_t s) {
     RTSDS_REQUIRE(x && wpk && y_cp && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
+    RTSDS_REQUIRE(is_16bit(dtype), "stem_pair_tc_fwd: dtype must be bf16 or fp16");
     RTSDS_REQUIRE((stats_cp == nullptr) == (stats_sp == nullptr), "stem_pair_tc_fwd: stats go together");
     int rc = rtsds_check_device();
     if (rc != RTSDS_OK) return rc;
@@ -517,16 +533,26 @@ extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const
     const size_t smem = 1024 + 3 * S_A_BYTES + 2 * S_ATOM_BYTES + 512 * 4 + 8 * 8 + 16 + S_PATCHES * S_PATCH_FLOATS * 4;
     static bool done = false;
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) { set_error("stem_pair_tc_fwd: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        const void* fns[6] = {(const void*)stem_fwd_tc_kernel<32, false>, (const void*)stem_fwd_tc_kernel<16, false>,
+                              (const void*)stem_fwd_tc_kernel<8, false>, (const void*)stem_fwd_tc_kernel<32, true>,
+                              (const void*)stem_fwd_tc_kernel<16, true>, (const void*)stem_fwd_tc_kernel<8, true>};
+        for (const void* f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("stem_pair_tc_fwd: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
+        }
         done = true;
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
-    if (p.tile_w == 32) stem_fwd_tc_kernel<32><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
-    else if (p.tile_w == 16) stem_fwd_tc_kernel<16><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
-    else stem_fwd_tc_kernel<8><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);
+    const bool f16 = dtype == RTSDS_F16;
+#define STEM_FWD(TWv)                                                                                         \
+    do {                                                                                                      \
+        if (f16) stem_fwd_tc_kernel<TWv, true><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);            \
+        else stem_fwd_tc_kernel<TWv, false><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);               \
+    } while (0)
+    if (p.tile_w == 32) STEM_FWD(32);
+    else if (p.tile_w == 16) STEM_FWD(16);
+    else STEM_FWD(8);
+#undef STEM_FWD
     count_launch();
     return check_launch("stem_fwd_tc_kernel");
 }

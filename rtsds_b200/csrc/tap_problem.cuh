@@ -25,6 +25,7 @@ struct TapProblem {
     const float* scale; const float* shift; const void* residual; float* stats; void* y;
     int out_dtype, act; float slope;
     int split_req;
+    int in_f16;                   // operands are IEEE half (RTSDS_F16) instead of bf16
 };
 
 
@@ -66,6 +67,7 @@ static inline int fwd_problem(const RtsdsConvDesc* d, const void* x, const void*
     t->out_sw = d->out_ld; t->out_sh = static_cast<long long>(d->ow) * d->out_ld; t->out_sn = t->out_sh * d->oh;
     t->res_sw = d->res_ld; t->res_sh = static_cast<long long>(d->ow) * d->res_ld; t->res_sn = t->res_sh * d->oh;
     t->out_dtype = d->out_dtype; t->act = d->act; t->slope = d->slope; t->split_req = d->split_k;
+    t->in_f16 = d->in_dtype == RTSDS_F16;
     return RTSDS_OK;
 }
 

@@ -10,10 +10,10 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc, check, lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F16, F32, ConvDesc, check, lib
 
 __all__ = [
-    "F32", "BF16", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ConvDesc", "dtype_code", "torch_dtype",
+    "F32", "BF16", "F16", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ConvDesc", "dtype_code", "torch_dtype",
     "confusion_hist", "argmax_hist", "conv_out_size", "cout_pad", "pack_conv_weight", "conv2d_tc",
     "conv2d_simt", "stem_conv", "maxpool3x3s2", "maxpool3x3s2_bwd_idx", "bn_fold", "bn_finalize", "scale_shift_act",
     "global_avgpool", "arm_gate", "gate_resize_nhwc", "ffm_head", "resize_to_nchw",
@@ -48,11 +48,13 @@ def dtype_code(dt: torch.dtype) -> int:
         return F32
     if dt == torch.bfloat16:
         return BF16
+    if dt == torch.float16:
+        return F16
     raise TypeError(f"unsupported activation dtype {dt}")
 
 
 def torch_dtype(code: int) -> torch.dtype:
-    return torch.bfloat16 if code == BF16 else torch.float32
+    return torch.bfloat16 if code == BF16 else torch.float16 if code == F16 else torch.float32
 
 
 def launch_count() -> int:
@@ -203,14 +205,15 @@ def stem_conv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, k: int, stride:
 def stem_pack_weights(w7: torch.Tensor, w3: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     if out is None:
         out = torch.empty((128, 192), dtype=torch.bfloat16, device=w7.device)
-    check(lib().rtsds_stem_pack_weights(_p(w7.detach()), _p(w3.detach()), _p(out), _s()), "stem_pack_weights")
+    check(lib().rtsds_stem_pack_weights(_p(w7.detach()), _p(w3.detach()), dtype_code(out.dtype), _p(out), _s()), "stem_pack_weights")
     return out
 
 
 def stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale=None, shift=None, relu=True, stats_cp=None, stats_sp=None) -> None:
     n, _, h, w = x.shape
+    assert wpk.dtype == y_cp.dtype == y_sp.dtype
     check(lib().rtsds_stem_pair_tc_fwd(_p(x), n, h, w, _p(wpk), _p(scale), _p(shift), int(relu), _p(stats_cp), _p(stats_sp),
-                                       _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
+                                       dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
 
 
 def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
@@ -293,9 +296,15 @@ def arm_gate(pooled, conv, bn, train, n, c, gate, mul=None, lin_out=None, xhat_o
                                _p(xhat_out), _s()), "arm_gate")
 
 
-def gate_resize_nhwc(src, n, h, w, c, src_ld, gate, oh, ow, dst, dst_ld, dst_coff, dtype) -> None:
-    check(lib().rtsds_gate_resize_nhwc(_p(src), n, h, w, c, src_ld, _p(gate), oh, ow, _p(dst), dst_ld, dst_coff, dtype,
-                                       _s()), "gate_resize_nhwc")
+def gate_resize_nhwc(src, n, h, w, c, src_ld, gate, oh, ow, dst, dst_ld, dst_coff, dtype, gate_scale=1.0) -> None:
+    check(lib().rtsds_gate_resize_nhwc(_p(src), n, h, w, c, src_ld, _p(gate), float(gate_scale), oh, ow, _p(dst), dst_ld,
+                                       dst_coff, dtype, _s()), "gate_resize_nhwc")
+
+
+def scale_packed_channels(wpk, rows, cin, c0, c1, factor) -> None:
+    """Input channels [c0, c1) of a packed weight [rows][cin] *= factor (block exponent of a scaled activation slot)."""
+    check(lib().rtsds_scale_packed_channels(_p(wpk), dtype_code(wpk.dtype), rows, cin, c0, c1, float(factor), _s()),
+          "scale_packed_channels")
 
 
 def ffm_head(f, f_dtype, f_ld, pooled, n, hw, c, conv1, conv2, final_conv, z, z_ld, attn_out=None) -> None:

@@ -17,8 +17,10 @@ def applicable(conv) -> bool:
 
 
 class TapNConv:
-    def __init__(self, plan, conv, x_ptr, xshape, in_ld, train: bool):
+    def __init__(self, plan, conv, x_ptr, xshape, in_ld, train: bool, in_scale=None):
         self.plan, self.conv, self.x_ptr = plan, conv, x_ptr
+        self.in_scale = in_scale        # (c0, c1, factor): input channels [c0, c1) are stored divided by factor
+        assert in_scale is None or not train
         n, h, w, cin = xshape
         self.n, self.h, self.w, self.cin, self.in_ld = n, h, w, cin, in_ld
         self.c = conv.weight.shape[0]
@@ -50,6 +52,9 @@ class TapNConv:
         check(lib().rtsds_tapn_weights(_p(self.conv.weight.detach()), self.c, self.cin, self.k, self.kpad, _p(self.w_fwd),
                                        _p(self.w_bwd), ops._s()), "tapn_weights")
         ops.pack_conv_weight(self.w_fwd, self.dt, self.wpk_fwd)
+        if self.in_scale is not None:
+            c0, c1, fac = self.in_scale
+            ops.scale_packed_channels(self.wpk_fwd, self.wpk_fwd.shape[0], self.cin, c0, c1, fac)
         if self.w_bwd is not None:
             ops.pack_conv_weight(self.w_bwd, self.dt, self.wpk_bwd)
 

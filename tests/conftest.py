@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# the context path is built with pretrained=True as in the reference; there is no network / hub cache here, so the
+# synthetic-weight tests opt in to the seeded random init explicitly (models/bisenet/build_contextpath.py)
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

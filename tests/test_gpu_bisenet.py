@@ -11,6 +11,7 @@ import torch
 from oracle import bisenet_bf16, bisenet_ref, weights
 
 from gpu_util import rel_err
+from parity_log import record
 
 pytestmark = pytest.mark.gpu
 SUB = 3
@@ -28,7 +29,9 @@ def _model(seed, precision):
 
     m = BiSeNet(19, "resnet18")
     m.load_state_dict(weights.clone_state(weights.bisenet_r18_state(seed)))
-    m.rtsds_precision = precision
+    # "fp16": the production mode (bf16 training, fp16 eval-mode inference); "bf16": bf16 in eval mode too
+    m.rtsds_precision = "bf16" if precision == "fp16" else precision
+    m.rtsds_eval_precision = "fp16" if precision == "fp16" else "bf16"
     return m.cuda()
 
 
@@ -41,8 +44,11 @@ def _bf16_floor(x, sd, ref):
 
 
 @pytest.mark.parametrize("name", ["bisenet_64x96", "bisenet_72x104"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
-def test_eval_forward_vs_reference_golden(cuda, golden_dir, name, precision, tol):
+# tiny maps (1408 sub-sampled pixels, one flip = 0.07 %) with synthetic BatchNorm statistics: ideal fp16 reaches
+# 99.6-99.9 % here and ideal bf16 97.3-98.2 % (oracle/bisenet_bf16.py); north_star's 99.9 % is asserted at full size on
+# BASELINE config 1 (tests/test_gpu_config1.py)
+@pytest.mark.parametrize("precision,tol,agree_min", [("fp32", 1e-4, 0.999), ("fp16", 2e-2, 0.99), ("bf16", 3e-2, 0.95)])
+def test_eval_forward_vs_reference_golden(cuda, golden_dir, name, precision, tol, agree_min):
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     n, h, w = (int(v) for v in gold["shape"])
     seed = int(gold["seed"][0])
@@ -54,7 +60,8 @@ def test_eval_forward_vs_reference_golden(cuda, golden_dir, name, precision, tol
     ref = torch.from_numpy(gold["eval_result"])
     assert rel_err(got, ref) < tol, rel_err(got, ref)
     agree = (out.argmax(1)[..., ::SUB, ::SUB].cpu().numpy() == gold["eval_argmax"]).mean()
-    assert agree >= (0.999 if precision == "fp32" else 0.95), agree   # tiny maps, random-init weights: bf16 flips near-ties
+    record(f"golden/{name}/eval/{precision}", rel=rel_err(got, ref), argmax_agree=float(agree), tol_rel=tol, tol_argmax=agree_min)
+    assert agree >= agree_min, agree
     # graph replay and eager execution give the same answer; second call reuses the plan
     out2 = m(x.cuda())
     assert torch.equal(out, out2)
@@ -103,11 +110,13 @@ def test_eval_forward_full_size_vs_oracle(cuda, n, h, w):
     with torch.no_grad():
         ref = bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=False)
     floor_err, floor_agree = _bf16_floor(x, sd, ref)
-    for precision, tol, agree_min in (("fp32", 1e-4, 0.9999), ("bf16", 2e-2, 0.999)):
+    for precision, tol, agree_min in (("fp32", 1e-4, 0.9999), ("fp16", 2e-2, 0.999), ("bf16", 2e-2, 0.999)):
         m = _model(42, precision).eval()
         out = m(x.cuda()).cpu()
         e = rel_err(out, ref)
         agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+        record(f"synthetic_weights_{n}x{h}x{w}/eval/{precision}", rel=e, argmax_agree=agree, ideal_bf16_rel=floor_err,
+               ideal_bf16_argmax=floor_agree)
         assert e < tol, (precision, e)
         if precision == "bf16":
             # no worse than an ideal bf16 pipeline: on random-init weights bf16 round-off itself flips
@@ -381,7 +390,63 @@ def test_two_train_forwards_then_one_backward(cuda):
     assert len(m._rtsds_train_plans) == 2 and len(m2._rtsds_train_plans) == 1
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_with_interpolation_false(cuda, precision):
+    """BiSeNet(..., with_interpolation=False) (build_bisenet.py:165-167): `result` is the FFM output at 1/8 resolution,
+    WITHOUT the x8 resize and without the final 1x1 conv (which then receives no gradient); the auxiliary heads are
+    still resized to the input size.  Eval and train (forward, loss through the stock criterion, backward) vs the oracle."""
+    from models.bisenet.build_bisenet import BiSeNet
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, h, w = 2, 128, 192
+    x, y = _input(11, n, h, w)
+    sd = weights.bisenet_r18_state(11)
+    m = BiSeNet(19, "resnet18", with_interpolation=False)
+    m.load_state_dict(weights.clone_state(sd))
+    m.rtsds_precision = "bf16" if precision == "fp16" else precision
+    m = m.cuda()
+    tol, amin = (1e-4, 0.999) if precision == "fp32" else (2e-2, 0.99)
+    # ---- eval: [N,19,H/8,W/8]
+    with torch.no_grad():
+        ref = bisenet_ref.bisenet_forward(x, weights.clone_state(sd), train=False, with_interpolation=False)
+    out = m.eval()(x.cuda())
+    assert out.shape == ref.shape == (n, 19, h // 8, w // 8)
+    e, a = rel_err(out.cpu(), ref), (out.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    record(f"with_interpolation_false/eval/{precision}", rel=e, argmax_agree=a, tol_rel=tol)
+    assert e <= tol and a >= amin, (e, a)
+    if precision != "fp32":
+        return                                    # training dtype parity (bf16) is covered by the floor tests above
+    # ---- train: tuple (1/8-res result, full-res aux heads); loss on the low-res result needs low-res labels
+    leaves = {}
+    sdt = weights.clone_state(sd)
+    for k, v in sdt.items():
+        if v.dtype.is_floating_point and "running" not in k and not k.startswith("context_path.features.fc"):
+            v.requires_grad_(True)
+            leaves[k] = v
+    y8 = y[:, ::8, ::8].contiguous()
+    r_ref = bisenet_ref.bisenet_forward(x, sdt, train=True, with_interpolation=False)
+    ref_loss = bisenet_ref.ce_loss(r_ref[0], y8, 19) + bisenet_ref.ce_loss(r_ref[1], y, 19) + bisenet_ref.ce_loss(r_ref[2], y, 19)
+    ref_loss.backward()
+    outs = m.train()(x.cuda())
+    assert outs[0].shape == (n, 19, h // 8, w // 8) and outs[1].shape == outs[2].shape == (n, 19, h, w)
+    ce = torch.nn.functional.cross_entropy
+    loss = ce(outs[0], y8.cuda(), ignore_index=19) + ce(outs[1], y.cuda(), ignore_index=19) + ce(outs[2], y.cuda(), ignore_index=19)
+    loss.backward()
+    for o, r in zip(outs, r_ref):
+        assert rel_err(o.detach().cpu(), r.detach()) <= 2e-4
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    assert grads["conv.weight"] is None or float(grads["conv.weight"].abs().max()) == 0.0     # the final conv is unused
+    worst = 0.0
+    for k, v in leaves.items():
+        if v.grad is None or _ill_conditioned(k, "fp32") or k.startswith("context_path.") and not k.startswith("context_path.features"):
+            continue
+        worst = max(worst, _l2_rel(grads[k].cpu(), v.grad))
+    record("with_interpolation_false/train/fp32", loss=loss.item(), ref_loss=ref_loss.item(), worst_grad_rel_l2=worst)
+    assert worst <= 5e-3, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 def test_resnet101_context_path_eval_vs_reference_golden(cuda, golden_dir, precision):
     """BiSeNet(19, 'resnet101') (build_bisenet.py:95-102), eval: Bottleneck context path, ARMs over 1024 / 2048
     channels, 3328-channel concat buffer and FFM conv.  fp32 check mode must meet 1e-4 against the real reference's
@@ -393,15 +458,20 @@ def test_resnet101_context_path_eval_vs_reference_golden(cuda, golden_dir, preci
     x, _ = _input(seed, n, h, w)
     m = BiSeNet(19, "resnet101")
     m.load_state_dict(weights.clone_state(weights.bisenet_r101_state(seed)))
-    m.rtsds_precision = precision
+    m.rtsds_precision = "bf16" if precision == "fp16" else precision
+    m.rtsds_eval_precision = "fp16" if precision == "fp16" else "bf16"
     m = m.cuda().eval()
     out = m(x.cuda())
     assert out.shape == (n, 19, h, w) and torch.isfinite(out).all()
     got, ref = out[..., ::SUB, ::SUB].cpu(), torch.from_numpy(gold["eval_result"])
     agree = (out.argmax(1)[..., ::SUB, ::SUB].cpu().numpy() == gold["eval_argmax"]).mean()
+    record(f"golden/bisenet_r101_64x96/eval/{precision}", rel=rel_err(got, ref), rel_l2=_l2_rel(got, ref), argmax_agree=float(agree))
     if precision == "fp32":
         assert rel_err(got, ref) < 1e-4, rel_err(got, ref)
         assert agree >= 0.999, agree
+    elif precision == "fp16":
+        assert rel_err(got, ref) < 2e-2, rel_err(got, ref)
+        assert agree >= 0.97, agree                # 704 sub-sampled pixels of a 64x96 map: one flip = 0.14 %
     else:
         assert _l2_rel(got, ref) < 6e-2, _l2_rel(got, ref)
         assert agree >= 0.85, agree

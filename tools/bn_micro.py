@@ -1,5 +1,6 @@
 """Times the BatchNorm backward kernels at the training step's map sizes (graph-replayed, L2 flushed by size)."""
 import os, sys
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")   # synthetic benchmark: seeded random-init backbone (no hub cache offline)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rtsds_b200._lib import check, lib

@@ -2,6 +2,7 @@
 batch-1 inference; prints CUDA-event timings, usable under ncu.  python tools_conv_micro.py [--set train|infer] [--ops fwd,dgrad,wgrad] [--reps 5]"""
 import argparse
 import os
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")   # synthetic benchmark: seeded random-init backbone (no hub cache offline)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

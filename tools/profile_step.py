@@ -3,6 +3,7 @@ step is GPU-bound so that the CPU runs ahead of the device).  python tools_profi
 import argparse
 import collections
 import os
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")   # synthetic benchmark: seeded random-init backbone (no hub cache offline)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

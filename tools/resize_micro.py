@@ -1,5 +1,6 @@
 """Times rtsds_resize_to_nchw_bwd (adjoint of the logits writer) at the training sizes."""
 import os, sys
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")   # synthetic benchmark: seeded random-init backbone (no hub cache offline)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rtsds_b200._lib import check, lib
