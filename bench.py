@@ -32,6 +32,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 H, W, NUM_CLASSES = 512, 1024, 19
+README_ITERS = 1000                # README.md:161-177
+EVAL_DTYPE = "fp16"                # eval-mode operand / activation type (fp32 accumulation); training: bf16
 FWD_GFLOP_PER_IMG = 51.26          # conv FLOPs (2*MAC) of one eval forward at 512x1024
 FWD_CONV_MB_PER_IMG = 236.0        # ideal bf16 conv traffic
 LOGITS_MB_PER_IMG = 39.8           # fp32 [19,512,1024] API-boundary write
@@ -280,13 +282,17 @@ def run_infer(args, rank, world, local):
             lane_fps = world * K / (lane_ms / 1e3)
 
         # ---- README protocol (README.md:157-177): per-iteration latency with a sync, mean/std of latency and 1/latency ----
+        # ALWAYS 1000 iterations, whatever --steps says: this loop is BASELINE.json's metric and the line's `value`
         lat = []
-        for i in range(min(K, 1000)):
-            t0 = time.perf_counter()
-            out = model(dev_in[i % n_inputs])
-            torch.cuda.synchronize()
-            lat.append(time.perf_counter() - t0)
+        barrier(world)
+        with ClockSampler(local) as clk_readme:
+            for i in range(README_ITERS):
+                t0 = time.perf_counter()
+                out = model(dev_in[i % n_inputs])
+                torch.cuda.synchronize()
+                lat.append(time.perf_counter() - t0)
         fps_i = [1.0 / t for t in lat]
+        readme_ms = max_over_ranks(1e3 * sum(lat) / len(lat), world)
 
         # ---- cold-L2 latency: flush between iterations, each iteration timed by its own event pair ----
         flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
@@ -347,15 +353,42 @@ def run_infer(args, rank, world, local):
         rows = tc_conv_profile(model, dev_in[0]) if rank == 0 else []
 
     # ---- the other half of BASELINE.json's metric: data-parallel training images/s (configs[2]) ----
-    train = None
+    model_state = {k: v.detach().cpu() for k, v in model.state_dict().items()} if rank == 0 else None
+    train, other = None, {}
     if not args.no_train and not r101:
         import bench_train
 
         del dev_in, host, model
         torch.cuda.empty_cache()
-        tk = max(5, min(K // 8, 30))
-        tr = bench_train.measure_train(args, rank, world, local, tk, 3, args.batch)
+        tk = max(100, K)                                   # >= 100 timed steps (1 s) whatever --steps says
+        tr = bench_train.measure_train(args, rank, world, local, tk, 10, args.batch)
         train = bench_train.train_summary(tr, world, args.batch, tk)
+        if not args.no_extra:
+            # BASELINE configs[3] / configs[4] on the same box in the same run, so that a driver record of them exists
+            import bench_extra
+            import copy
+
+            a2 = copy.copy(args)
+            a2.batch, a2.steps, a2.warmup = 0, 30, 5
+            torch.cuda.empty_cache()
+            dl = bench_extra.run_deeplab(a2, rank, world, local, emit=False)
+            torch.cuda.empty_cache()
+            adv = bench_extra.run_adversarial(a2, rank, world, local, emit=False)
+            torch.cuda.empty_cache()
+            if rank == 0:
+                keep = ("metric", "value", "unit", "steps", "ms_per_step", "config", "e2e", "launches_per_step", "roofline",
+                        "final_loss", "final_losses", "eval_b1")
+                other = {"config4_deeplabv2": {k: dl[k] for k in keep if k in dl},
+                         "config5_adversarial": {k: adv[k] for k in keep if k in adv}}
+    comparator = None
+    if rank == 0 and not args.no_comparator and not r101:
+        import bench_comparator
+
+        torch.cuda.empty_cache()
+        comparator = bench_comparator.run_all(torch.device("cuda", local), model_state, train_batch=args.batch,
+                                              full=not args.no_extra)
+        torch.cuda.empty_cache()
+    barrier(world)
 
     if rank != 0:
         return
@@ -364,26 +397,32 @@ def run_infer(args, rank, world, local):
     tc_ms = sum(r[3] for r in rows)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     single_fps, single_ms = fps, total_ms / K
-    if lane_fps is not None:          # headline = the serving configuration the e2e number uses too: `lanes` concurrent batch-1 streams
-        fps, total_ms = lane_fps, lane_ms
-    step_ms = total_ms / K
+    # headline: BASELINE.json's metric verbatim — one frame at a time, every iteration synchronised, 1000 iterations
+    fps, step_ms = world * 1e3 / readme_ms, readme_ms
     hbm_achieved = (FWD_CONV_MB_PER_IMG + LOGITS_MB_PER_IMG) * 1e6 / (step_ms * 1e-3) / 1e9
     cpu = cpu_baseline(args)
     line = {
         "metric": f"BiSeNet-{'R101' if r101 else 'R18'} 512x1024 inference FPS (batch 1)", "value": round(fps, 2), "unit": "frames/s",
-        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "n_gpus": world, "steps": K, "timed_iterations": README_ITERS, "warmup": Wm, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": EVAL_DTYPE, "data": "synthetic",
         "config": {"workload": ("bisenet_r101_eval_b1_3x512x1024 (config.yaml backbone: resnet101, SURVEY N4)" if r101 else
                                 "bisenet_r18_eval_b1_3x512x1024 (BASELINE.json configs[1])"), "num_classes": NUM_CLASSES,
                    "weights": "random-init, seeded", "parallelism": "replicas only" if world > 1 else "single GPU",
+                   "timed_region": f"value = README.md:161-177 protocol: {README_ITERS} iterations (regardless of --steps), one frame "
+                                   "at a time on one stream, torch.cuda.synchronize() and wall clock around every iteration; "
+                                   "device_timed = --steps frames back to back between CUDA events",
+                   "arithmetic": "tcgen05 kind::f16, fp16 operands / activations (IEEE half), fp32 TMEM accumulation; training runs bf16",
                    "l2": "inputs rotate over 32 distinct images (201 MB > 126 MB L2); weights stay L2-resident as in "
                          "steady-state serving; latency_cold_l2_ms flushes L2 before every iteration",
                    "cuda_graph": cuda_graph,
                    "streams": f"{lanes} concurrent batch-1 streams, one execution plan + CUDA graph each (single_stream = 1)"},
-        "clocks": clk.summary(),
-        "streams": lanes,
-        "single_stream": {"value": round(single_fps, 2), "unit": "frames/s", "ms_per_step": round(single_ms, 4),
-                          "note": "one frame at a time, back to back on one stream (= the per-frame latency)"},
+        "clocks": clk_readme.summary(),
+        "device_timed": {"value": round(single_fps, 2), "unit": "frames/s", "steps": K, "ms_per_step": round(single_ms, 4),
+                         "note": "single stream, one frame at a time back to back, CUDA events, no per-iteration sync",
+                         "clocks": clk.summary()},
+        "multi_stream": None if lane_fps is None else {
+            "value": round(lane_fps, 2), "unit": "frames/s", "streams": lanes, "ms_per_step": round(lane_ms / K, 4),
+            "note": f"{lanes} concurrent batch-1 streams (one execution plan + CUDA graph each): throughput serving, NOT the headline"},
         "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 3 * H * W * 4,
                 "d2h_bytes_per_step": H * W * 8, "ms_per_step": round(e2e_ms / K, 4),
                 "how": f"PipelinedSegmenter ({3 if lanes == 1 else lanes + 2} frames in flight; H2D / forward+argmax on {lanes} compute streams / D2H on separate streams), wall clock incl. final drain",
@@ -391,6 +430,7 @@ def run_infer(args, rank, world, local):
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "readme_protocol": {"iterations": len(lat), "mean_latency_ms": round(1e3 * statistics.mean(lat), 4),
+                            "median_latency_ms": round(1e3 * statistics.median(lat), 4),
                             "std_latency_ms": round(1e3 * statistics.pstdev(lat), 4), "mean_fps": round(statistics.mean(fps_i), 2),
                             "std_fps": round(statistics.pstdev(fps_i), 2)},
         "latency_cold_l2_ms": round(statistics.median(cold), 4),
@@ -404,7 +444,81 @@ def run_infer(args, rank, world, local):
         "conv_layers": [{"layer": r[2], "ms": round(r[3], 4), "tflops": round(r[0] / (r[3] * 1e-3) / 1e12, 1),
                          "gbs": round(r[1] / (r[3] * 1e-3) / 1e9, 1)} for r in rows],
         "train": train,
+        "other_configs": other,
+        "gpu_comparator": comparator,
         "cpu_baseline": cpu,
+    }
+    emit(line)
+
+
+def run_multi(args, rank, world, local):
+    """--gpus N > 1.  Batch-1 inference does not shard (replicas only); the path that shards — by batch, with ONE exchange
+    per step, the NCCL gradient all-reduce — is data-parallel TRAINING (BASELINE configs[2]), so that is the headline here:
+    images/s over all ranks, max(--steps, 100) timed steps between barriers, CUDA events, max over ranks.  The same step
+    is also timed on rank 0 ALONE in this run (no collective) so the scaling of this very box can be read off the line;
+    inference replicas are reported beside it."""
+    import bench_train
+
+    K = max(args.steps, 100)
+    Wm = max(args.warmup, 10)
+    solo = None
+    if rank == 0:
+        solo = bench_train.measure_train(args, 0, 1, local, K, Wm, args.batch, solo=True, e2e=False)
+    torch.cuda.empty_cache()
+    barrier(world)
+    r = bench_train.measure_train(args, rank, world, local, K, Wm, args.batch)
+    torch.cuda.empty_cache()
+
+    # ---- inference replicas (no collective): device-timed batch-1 FPS summed over ranks ----
+    dev = torch.device("cuda", local)
+    model = make_model(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    dev_in = torch.randn(32, 1, 3, H, W, generator=g).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(20):
+            model(dev_in[i % 32])
+        barrier(world)
+        e0.record()
+        for i in range(500):
+            model(dev_in[i % 32])
+        e1.record()
+        barrier(world)
+    rep_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    if rank != 0:
+        return
+    pk = peaks()
+    b = args.batch
+    img_s = world * b * K / (r["ms"] / 1e3)
+    img_s_e2e = world * b * K / (r["ms_e2e"] / 1e3)
+    solo_img_s = b * K / (solo["ms"] / 1e3)
+    per_gpu = img_s / world
+    G, MB = bench_train.TRAIN_GFLOP_PER_IMG_720, bench_train.TRAIN_CONV_MB_PER_IMG_720
+    line = {
+        "metric": "BiSeNet-R18 720x1280 data-parallel training throughput", "value": round(img_s, 2), "unit": "images/s",
+        "n_gpus": world, "steps": K, "steps_requested": args.steps, "warmup": Wm, "ms_per_step": round(r["ms"] / K, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "bisenet_r18_train_3x720x1280 (BASELINE.json configs[2]) — the headline under --gpus N > 1, "
+                               "because batch-1 inference (configs[1], the N = 1 headline) only replicates",
+                   "per_gpu_batch": b, "global_batch": b * world,
+                   "optimizer": "Adam lr 1e-4, poly LR on param_groups[0]", "loss": "3 x CE(ignore_index=19), fused resize+CE",
+                   "parallelism": f"dp{world}: one process per GPU, NCCL all-reduce (AVG) of the flat fp32 gradient in buckets, overlapped with backward; per-rank BatchNorm",
+                   "l2": "4 rotating input sets per rank, each larger than L2"},
+        "clocks": r["clocks"],
+        "single_gpu_same_run": {"value": round(solo_img_s, 2), "unit": "images/s", "ms_per_step": round(solo["ms"] / K, 3),
+                                "note": "the identical step on rank 0 alone, no collective, measured before the N-GPU run on this box"},
+        "e2e": {"value": round(img_s_e2e, 2), "unit": "images/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
+                "ms_per_step": round(r["ms_e2e"] / K, 3)},
+        "gpu_launches": int(r["launches"] * K), "launches_per_step": int(r["launches"]),
+        "roofline": {"bound": "tensor", "achieved": round(per_gpu * G / 1e3, 2), "peak": pk["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": round(per_gpu * G / 1e3 / pk["bf16_tflops_sustained"], 4), "traffic": None,
+                     "peak_source": pk["source"], "kernel": "whole training step (conv FLOPs only), per GPU"},
+        "whole_step_hbm": {"algorithmic_gbs": round(per_gpu * MB / 1e3, 1), "frac_of_hbm_peak": round(per_gpu * MB / 1e3 / pk["hbm_gbs"], 4)},
+        "final_loss": round(r["loss"], 4),
+        "validation": {"frames_per_s": round(r["val_fps"], 1), "miou_random_weights": round(r["miou"], 5)},
+        "inference_replicas": {"value": round(world * 500 / (rep_ms / 1e3), 1), "unit": "frames/s", "ms_per_frame": round(rep_ms / 500, 4),
+                               "note": "batch-1 eval forward on every GPU independently (replicas only, no collective), device-timed"},
+        "cpu_baseline": None,
     }
     emit(line)
 
@@ -480,6 +594,8 @@ def main():
     ap.add_argument("--disc", default="tiny", choices=["tiny", "full"], help="discriminator of the adversarial workload")
     ap.add_argument("--stock", action="store_true", help="adversarial workload: the reference's exact call sequence instead of the fused fast paths")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
+    ap.add_argument("--no-extra", action="store_true", help="skip the DeepLabV2 / adversarial extras and the long comparator legs")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the cuDNN comparator leg")
     ap.add_argument("--context", default="resnet18", choices=["resnet18", "resnet101"], help="inference: BiSeNet context path (resnet101: eval only)")
     ap.add_argument("--lanes", type=int, default=3, help="inference: concurrent batch-1 streams of the multi-stream / pipelined measurements")
     args = ap.parse_args()
@@ -494,7 +610,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: rtsds_b200 has no CPU fallback (use --impl reference for the CPU path)")
     rank, world, local = dist_setup(args.gpus)
     try:
-        if args.workload == "infer":
+        if args.workload == "infer" and world > 1:
+            run_multi(args, rank, world, local)
+        elif args.workload == "infer":
             run_infer(args, rank, world, local)
         elif args.workload == "adversarial":
             import bench_extra

@@ -30,7 +30,7 @@ def _line(metric, value, unit, world, K, W, ms, config, clocks, e2e, launches, r
     return d
 
 
-def run_adversarial(args, rank, world, local):
+def run_adversarial(args, rank, world, local, emit=True):
     import bench
     from models.bisenet.build_bisenet import BiSeNet
     from models.domain_shift.adversarial.model import DomainDiscriminator, TinyDomainDiscriminator
@@ -99,7 +99,7 @@ def run_adversarial(args, rank, world, local):
     it_s = K / (ms / 1e3)
     img_s = world * b * it_s                          # source images (and as many target images) per second
     tfl = b * it_s * (G_TRAIN_GFLOP_720 + G_TRAIN_GFLOP_512) / 1e3
-    bench.emit((_line(
+    line = (_line(
         "BiSeNet-R18 + discriminator adversarial training throughput (source images/s; each step also trains on as many target images)",
         img_s, "images/s", world, K, W, ms / K,
         {"workload": "adversarial_bisenet_r18 src 3x720x1280 + tgt 3x512x1024 (BASELINE.json configs[4])", "per_gpu_batch": b,
@@ -113,10 +113,13 @@ def run_adversarial(args, rank, world, local):
         {"bound": "tensor", "achieved": round(tfl, 2), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
          "frac": round(tfl / pk["bf16_tflops_sustained"], 4), "traffic": None, "peak_source": pk["source"],
          "kernel": "whole iteration, generator conv FLOPs only (2 fwd+bwd), per GPU"},
-        {"final_losses": {k: round(v, 6) for k, v in losses.items()}})))
+        {"final_losses": {k: round(v, 6) for k, v in losses.items()}}))
+    if emit:
+        bench.emit(line)
+    return line
 
 
-def run_deeplab(args, rank, world, local):
+def run_deeplab(args, rank, world, local, emit=True):
     import bench
     from models.deeplabv2.deeplabv2 import get_deeplab_v2
     from rtsds_b200 import ddp, ops
@@ -193,7 +196,7 @@ def run_deeplab(args, rank, world, local):
     pk = bench.peaks()
     img_s = world * b * K / (ms / 1e3)
     tfl = img_s / world * DEEPLAB_TRAIN_GFLOP_512 / 1e3
-    bench.emit((_line(
+    line = (_line(
         "DeepLabV2-R101 512x1024 data-parallel training throughput", img_s, "images/s", world, K, W, ms / K,
         {"workload": "deeplabv2_r101_train_3x512x1024 (BASELINE.json configs[3])", "per_gpu_batch": b, "optimizer": "SGD momentum 0.9",
          "loss": "CE(ignore_index=19), fused resize+CE", "parallelism": f"dp{world}", "l2": "4 rotating input sets per rank"},
@@ -206,4 +209,7 @@ def run_deeplab(args, rank, world, local):
          "kernel": "whole training step (conv FLOPs only), per GPU"},
         {"final_loss": round(final_loss, 4),
          "eval_b1": {"fps": round(world * 1e3 / ms_eval, 2), "ms": round(ms_eval, 3), "tflops": round(DEEPLAB_FWD_GFLOP_512 / ms_eval, 1),
-                     "frac_of_bf16_peak": round(DEEPLAB_FWD_GFLOP_512 / ms_eval / pk["bf16_tflops"], 4)}})))
+                     "frac_of_bf16_peak": round(DEEPLAB_FWD_GFLOP_512 / ms_eval / pk["bf16_tflops"], 4)}}))
+    if emit:
+        bench.emit(line)
+    return line

@@ -24,7 +24,8 @@ def poly_lr(optimizer, init_lr, it, max_iter, power=0.9):
     return lr
 
 
-def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280):
+def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280, solo=False, e2e=True):
+    """solo: this rank alone, no collective at all (the N = 1 figure measured inside a multi-GPU run; pass world=1)."""
     import bench
     from rtsds_b200 import ops
     from rtsds_b200.bisenet_autograd import bisenet_fused_ce
@@ -34,7 +35,8 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
     model.rtsds_ddp = world > 1
     from rtsds_b200 import ddp
 
-    ddp.broadcast_module(model, 0)
+    if not solo:
+        ddp.broadcast_module(model, 0)
     # stock torch.optim.Adam (main.py:116); fused=True is its single-kernel CUDA implementation of the same update
     if os.environ.get("RTSDS_BENCH_FOREACH_ADAM"):
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)          # torch's default on CUDA: the foreach implementation
@@ -79,6 +81,9 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
     # does); every batch still crosses PCIe inside the timed region and the loss is read back every step
     from rtsds_b200.serving import AsyncScalarReader, DevicePrefetcher
 
+    if not e2e:
+        return dict(ms=ms, ms_e2e=float("nan"), launches=launches, loss=last_loss, clocks=clk.summary(), miou=float("nan"),
+                    h2d=batch * (3 * h * w * 4 + h * w * 8), val_fps=None)
     for sx, sy in DevicePrefetcher(((host_x[i % n_sets], host_y[i % n_sets]) for i in range(4)), dev):   # warm-up: staging buffers
         step(warmup + steps, sx, sy)
     batches = ((host_x[i % n_sets], host_y[i % n_sets]) for i in range(steps))
@@ -102,17 +107,28 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280)
     hist = torch.zeros(19 * 19, dtype=torch.int64, device=dev)
     vx = torch.randn(1, 3, 512, 1024, generator=g).to(dev)
     vy = torch.randint(0, 20, (1, 512, 1024), generator=g).to(dev)
+    n_val = 64
     with torch.no_grad():
         for _ in range(4):
             out = model(vx)
             ops.argmax_hist(out, vy, hist, None)
-    ddp.allreduce_confusion(hist)
+        hist.zero_()
+        bench.barrier(world)
+        e0.record()
+        for _ in range(n_val):                       # validation.py:41-55 with the argmax + fast_hist fused on the device
+            out = model(vx)
+            ops.argmax_hist(out, vy, hist, None)
+        if not solo:
+            ddp.allreduce_confusion(hist)            # one 19x19 int64 all-reduce at the end of validation
+        e1.record()
+        bench.barrier(world)
+    val_ms = bench.max_over_ranks(e0.elapsed_time(e1), world)
     hh = hist.cpu().numpy().reshape(19, 19).astype("float64")
     import numpy as np
 
     iou = np.diag(hh) / (hh.sum(1) + hh.sum(0) - np.diag(hh) + 1e-5)        # utils.per_class_iou
     return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, loss=last_loss, clocks=clk.summary(), miou=float(np.nanmean(iou)),
-                h2d=batch * (3 * h * w * 4 + h * w * 8))
+                h2d=batch * (3 * h * w * 4 + h * w * 8), val_fps=world * n_val / (val_ms / 1e3))
 
 
 def train_summary(r, world, batch, K):
@@ -129,7 +145,11 @@ def train_summary(r, world, batch, K):
             "frac_of_bf16_sustained_peak": round(per_gpu * TRAIN_GFLOP_PER_IMG_720 / 1e3 / pk["bf16_tflops_sustained"], 4),
             "algorithmic_gbs_per_gpu": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3, 1),
             "frac_of_hbm_peak": round(per_gpu * TRAIN_CONV_MB_PER_IMG_720 / 1e3 / pk["hbm_gbs"], 4),
-            "final_loss": round(r["loss"], 4), "parallelism": f"dp{world}, NCCL bucketed all-reduce overlapped with backward"}
+            "final_loss": round(r["loss"], 4), "parallelism": f"dp{world}, NCCL bucketed all-reduce overlapped with backward",
+            "validation": None if r.get("val_fps") is None else {
+                "what": "BASELINE configs[2] second half: eval forward at 512x1024 + on-device argmax + fast_hist (validation.py:41-55), "
+                        "confusion matrix all-reduced once; frames/s over all ranks",
+                "frames_per_s": round(r["val_fps"], 1), "miou_random_weights": round(r["miou"], 5)}}
 
 
 def run_train(args, rank, world, local):

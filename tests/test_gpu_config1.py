@@ -148,9 +148,24 @@ def test_config1_backward_gradient_norms_vs_reference(cuda, c1, precision):
         errs[k] = abs(grads[k].double().norm().item() - rn) / max(rn, 1e-12)
     worst = max(errs, key=errs.get)
     med = sorted(errs.values())[len(errs) // 2]
-    record(f"config1/backward/{precision}", worst_param=worst, worst_grad_norm_rel=errs[worst], median_grad_norm_rel=med,
-           loss=loss.item())
+    fig = dict(worst_param=worst, worst_grad_norm_rel=errs[worst], median_grad_norm_rel=med, loss=loss.item())
     if precision == "fp32":
+        record("config1/backward/fp32", **fig)
         assert errs[worst] <= 2e-3, (worst, errs[worst])
-    else:
-        assert med <= 5e-2 and errs[worst] <= 0.5, (worst, errs[worst], med)
+        return
+    # bf16: gradients of this configuration inherit the train-mode ill-conditioning (module docstring); the yardstick is
+    # the ideal-bf16 emulation (fp32 oracle with straight-through bf16 rounding of the stored tensors, exact fp32 backward)
+    sde = {k: v.clone() for k, v in c1["sd"].items()}
+    leaves = {}
+    for k, v in sde.items():
+        if v.dtype.is_floating_point and "running" not in k and k in grads and grads[k] is not None:
+            v.requires_grad_(True)
+            leaves[k] = v
+    eo = bisenet_bf16.bisenet_train_bf16(c1["x"], sde)
+    sum(bisenet_ref.ce_loss(t, c1["y"], 19) for t in eo).backward()
+    emu = {k: abs(leaves[k].grad.double().norm().item() - rn) / max(rn, 1e-12)
+           for k, rn in zip((str(s) for s in gold["grad_names"]), gold["grad_norms"]) if k in errs and leaves[k].grad is not None}
+    emed = sorted(emu.values())[len(emu) // 2]
+    record("config1/backward/bf16", ideal_bf16_median_grad_norm_rel=emed, ideal_bf16_worst_grad_norm_rel=max(emu.values()), **fig)
+    assert med <= 1.6 * emed + 0.02, (med, emed)
+    assert errs[worst] <= 3.0 * max(emu.values()) + 0.05, (worst, errs[worst], max(emu.values()))
