@@ -49,8 +49,10 @@ def run_adversarial(args, rank, world, local, emit=True):
     gen.rtsds_ddp = dis.rtsds_ddp = world > 1
     ddp.broadcast_module(gen, 0)
     ddp.broadcast_module(dis, 0)
-    gopt = torch.optim.Adam(gen.parameters(), lr=1e-4, fused=True)
-    dopt = torch.optim.Adam(dis.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    from rtsds_b200.optim import FusedAdam, FusedSGD  # noqa: F401
+
+    gopt = FusedAdam(gen.parameters(), lr=1e-4)
+    dopt = FusedAdam(dis.parameters(), lr=1e-4, weight_decay=1e-4)
     ce, bce = torch.nn.CrossEntropyLoss(ignore_index=19), torch.nn.BCEWithLogitsLoss()
     n_sets = 3
     g = torch.Generator().manual_seed(42 + rank)
@@ -136,7 +138,9 @@ def run_deeplab(args, rank, world, local, emit=True):
     model = model.to(dev).train()
     model.rtsds_ddp = world > 1
     ddp.broadcast_module(model, 0)
-    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
+    from rtsds_b200.optim import FusedSGD
+
+    opt = FusedSGD([p for p in model.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
     n_sets = 4
     g = torch.Generator().manual_seed(42 + rank)
     hx = torch.randn(n_sets, b, 3, 512, 1024, generator=g).pin_memory()

@@ -182,6 +182,44 @@ int rtsds_pack_conv_weights_batch(const RtsdsPackJob* jobs, int n_jobs, int dtyp
 int rtsds_unpack_conv_wgrads_batch(const RtsdsUnpackJob* jobs, int n_jobs, rtsds_stream_t s);
 
 /* ------------------------------------------------------------------------
+ * Fused optimizer step: torch.optim.Adam / SGD as built at main.py:110-120 and stepped at train.py:96,
+ * 269-270, for ALL parameter tensors in ONE launch, together with the refresh of the packed conv operands the next
+ * forward / backward read (what rtsds_pack_conv_weights_batch did in separate launches).
+ *   job:   p / g / m / v fp32 device pointers of one parameter tensor (g NULL: the tensor is only re-packed; m NULL for
+ *          momentum-less SGD; v unused by SGD), `group` = index into the hyper-parameter arrays.
+ *          taps == 0: plain tensor of `numel` elements.  taps > 0: conv weight OIHW [cout][cin][taps] whose new value is
+ *          also written to out_fwd [cout_pad][taps][cin_pad_fwd] and / or out_dgrad [cin_pad_dgrad][taps][ck] (either may
+ *          be NULL) in `pack_dtype`.
+ *   hyper: per-group lr / weight_decay (L2, added to the gradient as torch does) read every step — poly_lr_scheduler
+ *          (utils.py:33-48) rewrites param_groups[0]['lr'] only; Adam: beta1, beta2, eps and the bias corrections of THIS
+ *          step (1/(1-beta1^t), 1/sqrt(1-beta2^t)); SGD: momentum, first_step != 0 on the step that initialises the
+ *          momentum buffer (torch: buf = grad).
+ * jobs / first_block (prefix sums of rtsds_optim_job_blocks over the jobs, n_jobs entries) live in DEVICE memory.
+ * ---------------------------------------------------------------------- */
+#define RTSDS_OPT_ADAM 0
+#define RTSDS_OPT_SGD  1
+#define RTSDS_OPT_MAX_GROUPS 8
+typedef struct RtsdsOptJob {
+    float* p; const float* g; float* m; float* v;
+    int64_t numel;
+    int group;
+    int taps, cout, cin;
+    int cout_pad, cin_pad_fwd, cin_pad_dgrad, ck;
+    void* out_fwd; void* out_dgrad;
+} RtsdsOptJob;
+typedef struct RtsdsOptHyper {
+    int kind;                                   /* RTSDS_OPT_ADAM / RTSDS_OPT_SGD */
+    int first_step;
+    float lr[RTSDS_OPT_MAX_GROUPS];
+    float weight_decay[RTSDS_OPT_MAX_GROUPS];
+    float beta1, beta2, eps, inv_bias_correction1, inv_bias_correction2_sqrt;
+    float momentum;
+} RtsdsOptHyper;
+int rtsds_optim_job_blocks(const RtsdsOptJob* job);
+int rtsds_optim_step(const RtsdsOptJob* jobs_dev, const int* first_block_dev, int n_jobs, int total_blocks,
+                     const RtsdsOptHyper* hyper, int pack_dtype, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
  * "Taps as N": k x k stride-1 conv with few output channels (c <= 32; the FFM ConvBlock 3x3 1024 -> 19,
  * build_bisenet.py:64,74) evaluated so that the wide input is read once instead of once per tap:
  *   forward : T = 1x1 conv of x with w_fwd (virtual OIHW [k*k*c, cin, 1, 1], N index t*c+co), then

@@ -14,6 +14,7 @@ from __future__ import annotations
 import warnings
 
 import torch
+from rtsds_b200.weights_epoch import PlanOwner
 from torch import nn
 
 from .build_contextpath import build_contextpath
@@ -104,7 +105,7 @@ class FeatureFusionModule(torch.nn.Module):
         return _ffm(self, input_1, input_2)
 
 
-class BiSeNet(torch.nn.Module):
+class BiSeNet(PlanOwner, torch.nn.Module):
     def __init__(self, num_classes, context_path, with_interpolation=True):
         super().__init__()
         self.with_interpolation = with_interpolation

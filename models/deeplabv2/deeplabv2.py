@@ -12,6 +12,7 @@ BatchNorm from conv-epilogue statistics.  No CPU fallback: a non-CUDA input rais
 from __future__ import annotations
 
 import torch
+from rtsds_b200.weights_epoch import PlanOwner
 import torch.nn as nn
 
 affine_par = True
@@ -79,7 +80,7 @@ class ClassifierModule(nn.Module):
         return _classifier_fwd(self, x)
 
 
-class ResNetMulti(nn.Module):
+class ResNetMulti(PlanOwner, nn.Module):
     def __init__(self, block, layers, num_classes):
         super().__init__()
         self.inplanes = 64

@@ -16,6 +16,7 @@ from __future__ import annotations
 import warnings
 
 import torch
+from rtsds_b200.weights_epoch import PlanOwner
 from torch import nn
 from torch.autograd import Function
 
@@ -49,7 +50,7 @@ class UpSampler(nn.Module):
         return upsampler_forward(self, x)
 
 
-class _DiscBase(nn.Module):
+class _DiscBase(PlanOwner, nn.Module):
     def _init_exec(self):
         # rtsds_b200 execution option (not part of the reference API): "bf16" (tcgen05 path) or
         # "fp32" (check mode, BASELINE.json 1e-4 tolerance)

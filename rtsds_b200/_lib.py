@@ -45,6 +45,23 @@ class UnpackJob(C.Structure):
                 ("taps", C.c_int), ("accumulate", C.c_int)]
 
 
+class OptJob(C.Structure):
+    """RtsdsOptJob (include/rtsds_b200.h)."""
+
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", C.c_int64),
+                ("group", C.c_int), ("taps", C.c_int), ("cout", C.c_int), ("cin", C.c_int), ("cout_pad", C.c_int),
+                ("cin_pad_fwd", C.c_int), ("cin_pad_dgrad", C.c_int), ("ck", C.c_int), ("out_fwd", C.c_void_p),
+                ("out_dgrad", C.c_void_p)]
+
+
+class OptHyper(C.Structure):
+    """RtsdsOptHyper (include/rtsds_b200.h)."""
+
+    _fields_ = [("kind", C.c_int), ("first_step", C.c_int), ("lr", C.c_float * 8), ("weight_decay", C.c_float * 8),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("inv_bias_correction1", C.c_float),
+                ("inv_bias_correction2_sqrt", C.c_float), ("momentum", C.c_float)]
+
+
 _P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _CD = C.POINTER(ConvDesc)
 
@@ -107,6 +124,8 @@ SIGNATURES = {
     "rtsds_global_avgpool": (_I, [_P, _I, _L, _I, _I, _I, _P, _P]),
     "rtsds_arm_gate": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
     "rtsds_gate_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _F, _I, _I, _P, _I, _I, _I, _P]),
+    "rtsds_optim_job_blocks": (_I, [C.POINTER(OptJob)]),
+    "rtsds_optim_step": (_I, [_P, _P, _I, _I, C.POINTER(OptHyper), _I, _P]),
     "rtsds_scale_packed_channels": (_I, [_P, _I, _L, _I, _I, _I, _F, _P]),
     "rtsds_ffm_head": (_I, [_P, _I, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "rtsds_resize_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
@@ -188,7 +207,17 @@ def lib():
     if not LIB_PATH.exists():
         if os.environ.get("RTSDS_NO_AUTOBUILD"):
             raise RtsdsError(f"{LIB_PATH} is missing; run `python -m rtsds_b200.build` (no CPU fallback exists)")
-        build()
+        build()                      # file-locked and linked atomically (rtsds_b200/build.py): safe under torchrun
+    elif not os.environ.get("RTSDS_NO_AUTOBUILD"):
+        # stale library: csrc/ or include/ changed since it was linked -> rebuild (needs nvcc; otherwise keep what is there)
+        try:
+            from .build import BUILD, source_digest
+
+            stamp = BUILD / "lib.digest"
+            if stamp.exists() and stamp.read_text() != source_digest():
+                build()
+        except Exception:  # noqa: BLE001 - no nvcc / read-only tree: the ABI version check below still guards the load
+            pass
     try:
         handle = C.CDLL(str(LIB_PATH))
     except OSError as e:  # pragma: no cover

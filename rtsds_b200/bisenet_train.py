@@ -288,6 +288,7 @@ class BiSeNetTrainPlan:
         self.generation = 0
         self.ws = None
         self._build()
+        weights_epoch.register_plan(self)        # the fused optimizers refresh this plan's packed operands (optim.py)
 
     def flush_unpack(self):
         if self.pending_unpack:
@@ -597,8 +598,11 @@ class BiSeNetTrainPlan:
 
     def _g(self, gw, p):
         g = gw.get(p)
-        if g is None:           # frozen parameter: kernels still need somewhere to write
-            g = self.buf(*p.shape, dtype=torch.float32)
+        if g is None:           # frozen parameter: kernels still need somewhere to write — ONE scratch target per parameter,
+            cache = self.__dict__.setdefault("_frozen_grad_scratch", {})     # not a new plan-owned buffer every backward
+            g = cache.get(p)
+            if g is None:
+                g = cache[p] = self.buf(*p.shape, dtype=torch.float32)
         return g
 
     def _copy(self, src: _Buf, dst: _Buf, shape):

@@ -45,7 +45,29 @@ def _digest(src: Path, headers: list[Path], extra: list[str]) -> str:
 
 
 def build(verbose: bool = False, force: bool = False, defines: list[str] | None = None) -> Path:
-    """Compile every csrc/*.cu and link librtsds_b200.so. Returns its path."""
+    """Compile every csrc/*.cu and link librtsds_b200.so. Returns its path.  Serialised across processes by a file lock
+    (under torchrun every rank may find the library missing at once)."""
+    import fcntl
+
+    BUILD.mkdir(exist_ok=True)
+    with open(BUILD / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose, force, defines)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def source_digest() -> str:
+    """Digest of every source / header / flag that goes into the library (stale-library check in _lib.lib())."""
+    h = hashlib.sha256()
+    for p in sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted((PKG.parent / "include").glob("*.h")):
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def _build_locked(verbose: bool, force: bool, defines: list[str] | None) -> Path:
     extra = [f"-D{d}" for d in (defines or [])]
     nvcc = _nvcc()
     BUILD.mkdir(exist_ok=True)
@@ -77,13 +99,18 @@ def build(verbose: bool = False, force: bool = False, defines: list[str] | None 
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or not LIB.exists():
+        # link to a private name and rename into place: a concurrent loader never sees a half-written library
+        tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")
         cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", str(LIB), *map(str, objs)]
+               "-o", str(tmp), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
         if verbose:
             print(f"[build] linked {LIB}", file=sys.stderr)
+    (BUILD / "lib.digest").write_text(source_digest())
     return LIB
 
 

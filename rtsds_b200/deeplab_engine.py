@@ -47,6 +47,7 @@ class _PlanBase:
         self.stem_P = None
         if train:
             self.pack_jobs, self.pending_unpack = [], []
+            weights_epoch.register_plan(self)    # the fused optimizers refresh this plan's packed operands (optim.py)
         self._stats_total = 0
         self._scratch_act, self._scratch_w, self._ws_bytes = 0, 0, 0
         self._param_version = None

@@ -85,19 +85,36 @@ class DevicePrefetcher:
     """Training-side counterpart: wraps an iterable of pinned host (image, label) batches and yields device tensors,
     copying batch i+1 on a side stream while step i computes (what train.py:71-72's `.to(device)` does serially)."""
 
-    _staging = {}          # (device, slot, shapes) -> device buffers, shared by all instances: allocating 100+ MB per epoch is slow
+    # Staging buffers are owned by ONE live prefetcher at a time.  A finished prefetcher returns its buffers to this
+    # free pool (allocating 100+ MB per epoch is slow); a second prefetcher alive at the same time with equal batch
+    # shapes (the source and target loaders of train.py:adversarial_train) checks out its OWN set, so it can never
+    # overwrite tensors the first one has yielded and the step is still reading.
+    _free = {}             # (device, shapes) -> [buffer sets]
 
     def __init__(self, batches, device, depth: int = 2):
         self.it, self.dev, self.depth = iter(batches), device, depth
         self.stream = torch.cuda.Stream(device)
         self.queue = []
-        self.bufs = DevicePrefetcher._staging
+        self.bufs = {}         # slot -> (pool key, device buffers) checked out by this instance
 
     def _buffers(self, slot, tensors):
-        key = (str(self.dev), slot, tuple((tuple(t.shape), t.dtype) for t in tensors))
-        if key not in self.bufs:
-            self.bufs[key] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in tensors]
-        return self.bufs[key]
+        key = (str(self.dev), tuple((tuple(t.shape), t.dtype) for t in tensors))
+        have = self.bufs.get(slot)
+        if have is not None and have[0] == key:
+            return have[1]
+        if have is not None:                                  # ragged last batch: this slot's shapes changed
+            DevicePrefetcher._free.setdefault(have[0], []).append(have[1])
+        pool = DevicePrefetcher._free.get(key)
+        bufs = pool.pop() if pool else [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in tensors]
+        self.bufs[slot] = (key, bufs)
+        return bufs
+
+    def release(self):
+        """Return the staging buffers to the free pool (called when the iterator is exhausted; later work on the
+        current stream is ordered after every step that read them)."""
+        for key, bufs in self.bufs.values():
+            DevicePrefetcher._free.setdefault(key, []).append(bufs)
+        self.bufs = {}
 
     def _enqueue(self, slot):
         try:
@@ -127,6 +144,7 @@ class DevicePrefetcher:
             self._enqueue(slot)
             slot = (slot + 1) % (self.depth + 1)
             yield tuple(dst)
+        self.release()
 
 
 class AsyncScalarReader:
