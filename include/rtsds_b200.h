@@ -78,6 +78,31 @@ int rtsds_confusion_hist(const int64_t* label, const int64_t* pred, int64_t n_pi
  * hist accumulated as above. */
 int rtsds_argmax_hist(const float* logits, const int64_t* label, int n, int n_cls,
                       int64_t hw, int64_t* pred_out, int64_t* hist, rtsds_stream_t s);
+/* Same with the class map written as uint8 [n, hw] (n_cls <= 256): the prediction a serving loop copies back to the host
+ * is 1 byte per pixel instead of the 8 of torch.argmax's int64 (validation.py:51 `.cpu()`). */
+int rtsds_argmax_hist_u8(const float* logits, const int64_t* label, int n, int n_cls,
+                         int64_t hw, uint8_t* pred_u8_out, int64_t* hist, rtsds_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * Device-side input pipeline: the per-sample CPU work of the reference's Dataset + transforms
+ * (main.py:60-108; datasets/cityscapes.py:66-72; datasets/gta5.py:68-82; utils.py:67-75) on the GPU, from the RAW
+ * uint8 planes.
+ *   image_u8_to_f32: read_image(...).float() -> transforms.Resize(size, antialias=True) -> transforms.Normalize:
+ *       src uint8 NCHW [n,c,h,w] (c <= 3) -> dst fp32 NCHW [n,c,oh,ow] = resize(float(src)) * scale3[ch] + bias3[ch]
+ *       (scale = 1/std, bias = -mean/std; HOST pointers).  Resize = ATen _upsample_bilinear2d_aa (triangle filter whose
+ *       support grows with the down-scaling factor; identity for equal sizes).
+ *   label_resize_clamp: read_image(...).long() -> Resize -> IntRangeTransformer(lo, hi): src uint8 or int64 [n,h,w] ->
+ *       int64 [n,oh,ow] = clamp(round_half_even(resize(float(src))), lo, hi)   (clamp == 0: no clamp, GTA5 labels).
+ *   stem_pair_tc_fwd_u8: rtsds_stem_pair_tc_fwd reading the uint8 image directly; the normalisation is applied while the
+ *       input patch is staged in shared memory, so a batch-1 frame costs no extra pass at all.
+ * ---------------------------------------------------------------------- */
+int rtsds_image_u8_to_f32(const uint8_t* src, int n, int c, int h, int w, int oh, int ow, const float* scale3,
+                          const float* bias3, float* dst, rtsds_stream_t s);
+int rtsds_label_resize_clamp(const void* src, int src_is_u8, int n, int h, int w, int oh, int ow, int clamp,
+                             int64_t lo, int64_t hi, int64_t* dst, rtsds_stream_t s);
+int rtsds_stem_pair_tc_fwd_u8(const uint8_t* x, const float* in_scale3, const float* in_bias3, int n, int h, int w,
+                              const void* wpk, const float* scale, const float* shift, int relu, int dtype,
+                              void* y_cp, void* y_sp, rtsds_stream_t s);
 
 /* ------------------------------------------------------------------------
  * Convolution (nn.Conv2d as used by models/bisenet/build_bisenet.py:11-12,

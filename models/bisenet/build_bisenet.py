@@ -133,6 +133,8 @@ class BiSeNet(PlanOwner, torch.nn.Module):
         #   mode, BASELINE.json 1e-4 tolerance); eval precision "fp16" (default) or "bf16"
         self.rtsds_precision = "bf16"
         self.rtsds_eval_precision = "fp16"
+        #   uint8 input frames: (mean, std) of the transforms.Normalize applied on the device (None: plain .float())
+        self.rtsds_input_norm = None
         self.rtsds_cuda_graph = True
 
     def init_weight(self):

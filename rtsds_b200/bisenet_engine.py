@@ -292,7 +292,16 @@ class BiSeNetPlan:
         self.pack_steps.append(lambda: ops.stem_pack_weights(conv7.weight, conv3.weight, wpk))
         self.pack_steps.append(lambda: ops.bn_fold(bn7, scale[:64], shift[:64]))
         self.pack_steps.append(lambda: ops.bn_fold(bn3, scale[64:], shift[64:]))
-        self.pre_steps.append(lambda x: ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True))
+        from .input_pipeline import stem_affine
+
+        def run(x):
+            if x.dtype == torch.uint8:          # raw frame: the normalisation happens while the patch is staged
+                sc, bi = stem_affine(self.model)
+                ops.stem_pair_tc_fwd_u8(x, sc, bi, wpk, y_cp, y_sp, scale, shift, True)
+            else:
+                ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True)
+
+        self.pre_steps.append(run)
 
     def _stem(self, conv, bnmod, y, k, stride, pad):
         cout = conv.weight.shape[0]
@@ -457,7 +466,15 @@ def bisenet_forward(model, x):
         raise ops._lib.RtsdsError("BiSeNet.forward needs a CUDA tensor: rtsds_b200 has no CPU fallback")
     if x.dim() != 4 or x.shape[1] != 3:
         raise ValueError(f"expected input [N,3,H,W], got {tuple(x.shape)}")
-    if x.dtype != torch.float32:
+    if x.dtype == torch.uint8:
+        # raw uint8 frames: the eval-mode tensor-core path reads them directly in its fused stem kernel; every
+        # other mode converts + normalises on the device first (one pass, csrc/input.cu)
+        if model.training or eval_precision(model) not in ("fp16", "bf16"):
+            from .input_pipeline import DeviceInputPipeline
+
+            norm = getattr(model, "rtsds_input_norm", None)
+            x = DeviceInputPipeline(None, *(norm if norm is not None else (None, None))).images(x)
+    elif x.dtype != torch.float32:
         x = x.float()
     x = x.contiguous()
     if model.training:

@@ -85,7 +85,7 @@ template <int VEC>
 __global__ void __launch_bounds__(HIST_THREADS)
 argmax_hist_kernel(const float* __restrict__ logits, const long long* __restrict__ label, int n,
                    int n_cls, long long hw, int copies, long long* __restrict__ pred_out,
-                   unsigned long long* hist) {
+                   uint8_t* __restrict__ pred_u8, unsigned long long* hist) {
     extern __shared__ unsigned sh_all[];
     const int nbins = n_cls * n_cls;
     for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh_all[i] = 0;
@@ -119,6 +119,17 @@ argmax_hist_kernel(const float* __restrict__ logits, const long long* __restrict
             for (int v = 0; v < VEC; ++v) {
                 // first maximum wins (torch.argmax); NaN is treated as maximal like torch
                 if (x[v] > best[v] || (x[v] != x[v] && best[v] == best[v])) { best[v] = x[v]; arg[v] = c; }
+            }
+        }
+        if (pred_u8) {                          // class map as one byte per pixel (n_cls <= 256): 8x fewer bytes back to the host
+            if (VEC == 4 && full) {
+                *reinterpret_cast<uint32_t*>(pred_u8 + img * hw + p0) =
+                    static_cast<uint32_t>(arg[0]) | (static_cast<uint32_t>(arg[1 % VEC]) << 8) |
+                    (static_cast<uint32_t>(arg[2 % VEC]) << 16) | (static_cast<uint32_t>(arg[3 % VEC]) << 24);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (p0 + v < hw) pred_u8[img * hw + p0 + v] = static_cast<uint8_t>(arg[v]);
             }
         }
 #pragma unroll
@@ -168,8 +179,8 @@ extern "C" int rtsds_confusion_hist(const int64_t* label, const int64_t* pred, i
     return check_launch("confusion_hist");
 }
 
-extern "C" int rtsds_argmax_hist(const float* logits, const int64_t* label, int n, int n_cls,
-                                 int64_t hw, int64_t* pred_out, int64_t* hist, rtsds_stream_t s) {
+static int argmax_hist_impl(const float* logits, const int64_t* label, int n, int n_cls, int64_t hw, int64_t* pred_out,
+                            uint8_t* pred_u8, int64_t* hist, rtsds_stream_t s) {
     RTSDS_REQUIRE(n_cls > 0 && n_cls <= 100, "argmax_hist: n_cls=%d out of range (1..100)", n_cls);
     RTSDS_REQUIRE(n >= 0 && hw >= 0, "argmax_hist: negative size");
     RTSDS_REQUIRE((label == nullptr) == (hist == nullptr), "argmax_hist: label and hist go together");
@@ -184,11 +195,22 @@ extern "C" int rtsds_argmax_hist(const float* logits, const int64_t* label, int 
     if (vec4)
         argmax_hist_kernel<4><<<grid, HIST_THREADS, smem, as_stream(s)>>>(
             logits, reinterpret_cast<const long long*>(label), n, n_cls, hw, copies,
-            reinterpret_cast<long long*>(pred_out), reinterpret_cast<unsigned long long*>(hist));
+            reinterpret_cast<long long*>(pred_out), pred_u8, reinterpret_cast<unsigned long long*>(hist));
     else
         argmax_hist_kernel<1><<<grid, HIST_THREADS, smem, as_stream(s)>>>(
             logits, reinterpret_cast<const long long*>(label), n, n_cls, hw, copies,
-            reinterpret_cast<long long*>(pred_out), reinterpret_cast<unsigned long long*>(hist));
+            reinterpret_cast<long long*>(pred_out), pred_u8, reinterpret_cast<unsigned long long*>(hist));
     count_launch();
     return check_launch("argmax_hist");
+}
+
+extern "C" int rtsds_argmax_hist(const float* logits, const int64_t* label, int n, int n_cls,
+                                 int64_t hw, int64_t* pred_out, int64_t* hist, rtsds_stream_t s) {
+    return argmax_hist_impl(logits, label, n, n_cls, hw, pred_out, nullptr, hist, s);
+}
+
+extern "C" int rtsds_argmax_hist_u8(const float* logits, const int64_t* label, int n, int n_cls,
+                                    int64_t hw, uint8_t* pred_u8_out, int64_t* hist, rtsds_stream_t s) {
+    RTSDS_REQUIRE(pred_u8_out && (hw % 4 != 0 || (reinterpret_cast<uintptr_t>(pred_u8_out) & 3) == 0), "argmax_hist_u8: pred_u8_out NULL or misaligned");
+    return argmax_hist_impl(logits, label, n, n_cls, hw, nullptr, pred_u8_out, hist, s);
 }

@@ -1,0 +1,144 @@
+// Device-side input pipeline: what the reference does on the CPU inside its Dataset / transforms
+// (main.py:60-108, datasets/cityscapes.py:66-72, datasets/gta5.py:68-82, utils.py:67-75) for every sample —
+//     read_image(...).float()  ->  transforms.Resize(size, antialias=True)  ->  transforms.Normalize(mean, std)
+//     read_image(...).long()   ->  transforms.Resize(size, antialias=True)  ->  IntRangeTransformer(0, num_classes)
+// — evaluated on the GPU from the raw uint8 image / label planes, so that a frame crosses PCIe as 3 bytes per pixel instead
+// of 12 (and a label as 1 byte instead of 8).  Memory-bound, one pass each.
+//
+// Resize semantics are torchvision's for tensors: F.interpolate(mode="bilinear", align_corners=False, antialias=True),
+// i.e. ATen's _upsample_bilinear2d_aa: a separable triangle filter whose support grows with the down-scaling factor,
+//     scale = in/out, support = max(scale, 1), center = scale*(i+0.5), xmin = max(int(center-support+0.5), 0),
+//     xsize = min(int(center+support+0.5), in) - xmin, w_j = tri((j + xmin - center + 0.5) / max(scale,1)) / sum_j
+// (for equal sizes this is the identity).  Integer tensors (labels) go through float, are ROUNDED (torch.round: half to
+// even) and cast back (torchvision _cast_squeeze_out), then clamped to [lo, hi] (IntRangeTransformer) and widened to int64.
+#include "common.cuh"
+
+namespace rtsds {
+
+struct AaAxis { float scale, support, invscale; };
+static inline AaAxis make_axis(int in, int out) {
+    AaAxis a;
+    a.scale = static_cast<float>(in) / static_cast<float>(out);      // area_pixel_compute_scale, align_corners=False
+    a.support = a.scale >= 1.f ? a.scale : 1.f;                       // interp_size/2 * scale, interp_size = 2
+    a.invscale = a.scale >= 1.f ? 1.f / a.scale : 1.f;
+    return a;
+}
+__device__ __forceinline__ void aa_window(int i, const AaAxis& a, int in, int* xmin, int* xsize, float* center) {
+    const float c = a.scale * (static_cast<float>(i) + 0.5f);
+    int lo = static_cast<int>(c - a.support + 0.5f);
+    if (lo < 0) lo = 0;
+    int hi = static_cast<int>(c + a.support + 0.5f);
+    if (hi > in) hi = in;
+    *xmin = lo; *xsize = hi - lo; *center = c;
+}
+__device__ __forceinline__ float aa_tri(float x) { x = fabsf(x); return x < 1.f ? 1.f - x : 0.f; }
+
+constexpr int AA_MAX_TAPS = 24;        // window per axis; covers down-scaling factors up to ~11
+
+// value at output (oy, ox) of plane `src` [h][w]; LOAD converts one source element to float
+template <typename S>
+__device__ __forceinline__ float aa_sample(const S* __restrict__ src, int h, int w, int oy, int ox, const AaAxis& ay, const AaAxis& ax) {
+    int y0, ny, x0, nx;
+    float cy, cx;
+    aa_window(oy, ay, h, &y0, &ny, &cy);
+    aa_window(ox, ax, w, &x0, &nx, &cx);
+    float wx[AA_MAX_TAPS];
+    float sx = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < nx; ++j) { wx[j] = aa_tri((static_cast<float>(j + x0) - cx + 0.5f) * ax.invscale); sx += wx[j]; }
+    const float inv_sx = sx != 0.f ? 1.f / sx : 0.f;
+    float acc = 0.f, sy = 0.f;
+    for (int i = 0; i < ny; ++i) {
+        const float wy = aa_tri((static_cast<float>(i + y0) - cy + 0.5f) * ay.invscale);
+        sy += wy;
+        const S* row = src + static_cast<long long>(y0 + i) * w + x0;
+        float r = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < nx; ++j) r = fmaf(wx[j], static_cast<float>(row[j]), r);
+        acc = fmaf(wy, r * inv_sx, acc);           // horizontal pass normalised first, as the separable ATen kernel does
+    }
+    return sy != 0.f ? acc / sy : 0.f;
+}
+
+// image: uint8 NCHW [n,3,h,w] -> fp32 NCHW [n,3,oh,ow], out = resize(float(src)) * scale[c] + bias[c]
+__global__ void __launch_bounds__(256)
+image_u8_kernel(const uint8_t* __restrict__ src, int n, int c, int h, int w, int oh, int ow, AaAxis ay, AaAxis ax, int identity,
+                float s0, float s1, float s2, float b0, float b1, float b2, float* __restrict__ dst) {
+    const long long total = static_cast<long long>(n) * c * oh * ow;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % ow);
+        const long long r = i / ow;
+        const int oy = static_cast<int>(r % oh);
+        const long long pl = r / oh;                  // plane index n*c + ch
+        const int ch = static_cast<int>(pl % c);
+        const uint8_t* p = src + pl * h * w;
+        const float v = identity ? static_cast<float>(p[static_cast<long long>(oy) * w + ox]) : aa_sample(p, h, w, oy, ox, ay, ax);
+        const float sc = ch == 0 ? s0 : (ch == 1 ? s1 : s2), bi = ch == 0 ? b0 : (ch == 1 ? b1 : b2);
+        dst[i] = fmaf(v, sc, bi);
+    }
+}
+
+// labels: S (uint8 or int64) [n,h,w] -> int64 [n,oh,ow] = clamp(round(resize(float(src))), lo, hi)
+template <typename S>
+__global__ void __launch_bounds__(256)
+label_kernel(const S* __restrict__ src, int n, int h, int w, int oh, int ow, AaAxis ay, AaAxis ax, int identity, int clamp,
+             long long lo, long long hi, long long* __restrict__ dst) {
+    const long long total = static_cast<long long>(n) * oh * ow;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % ow);
+        const long long r = i / ow;
+        const int oy = static_cast<int>(r % oh);
+        const S* p = src + (r / oh) * h * w;
+        long long v;
+        if (identity) v = static_cast<long long>(p[static_cast<long long>(oy) * w + ox]);
+        else v = static_cast<long long>(rintf(aa_sample(p, h, w, oy, ox, ay, ax)));      // torch.round: half to even
+        if (clamp) v = v < lo ? lo : (v > hi ? hi : v);
+        dst[i] = v;
+    }
+}
+
+}  // namespace rtsds
+
+using namespace rtsds;
+
+static int aa_check(int h, int w, int oh, int ow, const char* who) {
+    RTSDS_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0, "%s: empty tensor", who);
+    const float sy = static_cast<float>(h) / oh, sx = static_cast<float>(w) / ow;
+    RTSDS_REQUIRE(2.f * (sy > 1.f ? sy : 1.f) + 2.f <= AA_MAX_TAPS && 2.f * (sx > 1.f ? sx : 1.f) + 2.f <= AA_MAX_TAPS,
+                  "%s: down-scaling factor (%g, %g) beyond the supported filter window", who, sy, sx);
+    return RTSDS_OK;
+}
+
+extern "C" int rtsds_image_u8_to_f32(const uint8_t* src, int n, int c, int h, int w, int oh, int ow, const float* scale3,
+                                     const float* bias3, float* dst, rtsds_stream_t s) {
+    RTSDS_REQUIRE(src && dst && scale3 && bias3 && n > 0 && c >= 1 && c <= 3, "image_u8_to_f32: bad argument (c must be 1..3)");
+    int rc = aa_check(h, w, oh, ow, "image_u8_to_f32");
+    if (rc != RTSDS_OK) return rc;
+    const long long total = static_cast<long long>(n) * c * oh * ow;
+    const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
+    image_u8_kernel<<<grid, 256, 0, as_stream(s)>>>(src, n, c, h, w, oh, ow, make_axis(h, oh), make_axis(w, ow), h == oh && w == ow,
+                                                    scale3[0], scale3[c > 1 ? 1 : 0], scale3[c > 2 ? 2 : 0], bias3[0],
+                                                    bias3[c > 1 ? 1 : 0], bias3[c > 2 ? 2 : 0], dst);
+    count_launch();
+    return check_launch("image_u8_kernel");
+}
+
+extern "C" int rtsds_label_resize_clamp(const void* src, int src_is_u8, int n, int h, int w, int oh, int ow, int clamp,
+                                        int64_t lo, int64_t hi, int64_t* dst, rtsds_stream_t s) {
+    RTSDS_REQUIRE(src && dst && n > 0, "label_resize_clamp: bad argument");
+    int rc = aa_check(h, w, oh, ow, "label_resize_clamp");
+    if (rc != RTSDS_OK) return rc;
+    const long long total = static_cast<long long>(n) * oh * ow;
+    const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
+    const int ident = h == oh && w == ow;
+    if (src_is_u8)
+        label_kernel<uint8_t><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const uint8_t*>(src), n, h, w, oh, ow, make_axis(h, oh),
+                                                              make_axis(w, ow), ident, clamp, lo, hi, reinterpret_cast<long long*>(dst));
+    else
+        label_kernel<long long><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const long long*>(src), n, h, w, oh, ow, make_axis(h, oh),
+                                                                make_axis(w, ow), ident, clamp, lo, hi, reinterpret_cast<long long*>(dst));
+    count_launch();
+    return check_launch("label_kernel");
+}

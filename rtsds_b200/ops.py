@@ -74,9 +74,13 @@ def confusion_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: to
 
 def argmax_hist(logits: torch.Tensor, label: torch.Tensor | None, hist: torch.Tensor | None,
                 pred_out: torch.Tensor | None = None) -> None:
+    """pred_out: int64 [n,h,w] (torch.argmax's type) or uint8 [n,h,w] (one byte per pixel for the trip back to the host)."""
     _cuda(logits, label, hist, pred_out)
     assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 4
     n, c, h, w = logits.shape
+    if pred_out is not None and pred_out.dtype == torch.uint8:
+        check(lib().rtsds_argmax_hist_u8(_p(logits), _p(label), n, c, h * w, _p(pred_out), _p(hist), _s()), "argmax_hist_u8")
+        return
     check(lib().rtsds_argmax_hist(_p(logits), _p(label), n, c, h * w, _p(pred_out), _p(hist), _s()), "argmax_hist")
 
 
@@ -214,6 +218,14 @@ def stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale=None, shift=None, relu=True, stat
     assert wpk.dtype == y_cp.dtype == y_sp.dtype
     check(lib().rtsds_stem_pair_tc_fwd(_p(x), n, h, w, _p(wpk), _p(scale), _p(shift), int(relu), _p(stats_cp), _p(stats_sp),
                                        dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
+
+
+def stem_pair_tc_fwd_u8(x_u8, in_scale3, in_bias3, wpk, y_cp, y_sp, scale=None, shift=None, relu=True) -> None:
+    """Fused stems reading the RAW uint8 image; in_scale3 / in_bias3: ctypes float[3] (rtsds_b200/input_pipeline.py)."""
+    n, _, h, w = x_u8.shape
+    assert x_u8.dtype == torch.uint8 and wpk.dtype == y_cp.dtype == y_sp.dtype
+    check(lib().rtsds_stem_pair_tc_fwd_u8(_p(x_u8), in_scale3, in_bias3, n, h, w, _p(wpk), _p(scale), _p(shift), int(relu),
+                                          dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd_u8")
 
 
 def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
