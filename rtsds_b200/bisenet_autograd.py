@@ -65,19 +65,66 @@ def _grad_tuple(plan, params, gw):
     return tuple(None if (p in plan.unused or p not in gw) else gw[p] for p in params)
 
 
-def _run_backward(plan, gw, flat):
-    """Backward + (when model.rtsds_ddp and a process group is active) the bucketed gradient all-reduce
-    overlapped with it (rtsds_b200/ddp.py)."""
+def _aliases(plan, prev) -> bool:
+    """True when every live parameter's .grad still IS the view of `prev` this module handed to autograd."""
+    base, off = prev.data_ptr(), 0
+    for p in plan.params:
+        if p.requires_grad and p not in plan.unused:
+            g = p.grad
+            if g is None or g.data_ptr() != base + 4 * off or g.dtype != torch.float32:
+                return False
+        off += p.numel()
+    return True
+
+
+def _finish_backward(plan, params):
+    """Run the hand-written backward pass and hand the parameter gradients to autograd.
+
+    * Data parallel (model.rtsds_ddp, process group active): the flat fp32 gradient is all-reduced bucket by bucket while
+      backward still runs (rtsds_b200/ddp.py).
+    * Accumulation — a second backward before optimizer.step(), train.py:213 then :233 — when every p.grad still is the
+      view of the flat buffer of the previous backward, the new gradients are added there with ONE kernel and autograd
+      receives None (instead of one `add` kernel per tensor: 86 launches per adversarial iteration).
+    * model.rtsds_ddp_hold = True on the first of the two backward calls defers its all-reduce: the SUM is reduced once,
+      after the second ("allreduce G once after train.py:233"); rtsds_b200.train_steps.adversarial_step sets it.
+    """
     from . import ddp
 
-    if getattr(plan.model, "rtsds_ddp", False) and ddp.is_distributed():
-        if getattr(plan, "_buckets", None) is None:
-            plan._buckets = ddp.param_buckets(list(plan.model.named_parameters()), ddp.BISENET_GROUPS)
+    model = plan.model
+    use_ddp = getattr(model, "rtsds_ddp", False) and ddp.is_distributed()
+    hold = use_ddp and getattr(model, "rtsds_ddp_hold", False)
+    pending = use_ddp and model.__dict__.get("_rtsds_grad_pending_reduce", False)
+    prev = model.__dict__.get("_rtsds_grad_flat")
+    accumulate = prev is not None and prev.numel() == plan._grad_numel and prev.device == plan.device and _aliases(plan, prev)
+    if not accumulate:
+        prev = model.__dict__["_rtsds_grad_flat"] = None     # let the allocator hand the same block out again (stable pointers)
+    flat, gw = plan.new_grads()
+    if use_ddp and getattr(plan, "_buckets", None) is None:
+        plan._buckets = ddp.param_buckets(list(model.named_parameters()), ddp.BISENET_GROUPS)
+    if use_ddp and not hold and not pending:
         red = ddp.BucketedAllReduce(flat, plan._buckets)
         plan.backward_from_dz(gw, red.ready)
         red.finish()
     else:
         plan.backward_from_dz(gw)
+    if accumulate:
+        prev.add_(flat)
+        delivered = tuple(None for _ in params)
+        total = prev
+    else:
+        if pending:
+            raise ops._lib.RtsdsError("rtsds_ddp_hold: the gradients of the held backward were replaced before the next backward; "
+                                      "keep p.grad in place between the two backward calls of one iteration")
+        model.__dict__["_rtsds_grad_flat"] = flat
+        delivered = _grad_tuple(plan, params, gw)
+        total = flat
+    if hold:
+        model.__dict__["_rtsds_grad_pending_reduce"] = True
+    elif pending:
+        red = ddp.BucketedAllReduce(total, plan._buckets)        # the accumulated sum, once
+        red.finish()
+        model.__dict__["_rtsds_grad_pending_reduce"] = False
+    return delivered
 
 
 class _BiSeNetTrainFn(torch.autograd.Function):
@@ -108,9 +155,7 @@ class _BiSeNetTrainFn(torch.autograd.Function):
                 d = d.contiguous()
                 check(lib().rtsds_resize_to_nchw_bwd(_p(d), plan.n, plan.nc, oh, ow, plan.h8, plan.w8, _p(plan.dz[i]), 32, s),
                       "resize_to_nchw_bwd")
-        flat, gw = plan.new_grads()
-        _run_backward(plan, gw, flat)
-        return (None, None) + _grad_tuple(plan, ctx.params, gw)
+        return (None, None) + _finish_backward(plan, ctx.params)
 
 
 def bisenet_train_forward(model, x):
@@ -148,11 +193,26 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
             else:
                 ops.resize_ce_argmax_fwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, target, ignore_index, plan.acc[i],
                                          pred if i == 0 else None)
+        stats = plan.acc.clone()
+        ctx.den = stats[:, 1]
         per_head = (plan.acc[:, 0] / plan.acc[:, 1]).float()          # mean over valid pixels, per head
+        if getattr(plan.model, "rtsds_loss_norm", "local") == "global" and getattr(plan.model, "rtsds_ddp", False):
+            # nn.DataParallel semantics (utils.py:104-105): the criterion sees the GATHERED batch, i.e. every head's loss is
+            # sum(-log p) over all ranks / valid pixels of all ranks.  One tiny all-reduce (3 x 2 doubles) gives every rank
+            # that loss; its gradient is this rank's unnormalised gradient * world / global count, which the gradient
+            # all-reduce (AVG) turns into sum over ranks / global count (SURVEY 8e `global_valid_count`).
+            from . import ddp
+
+            if ddp.is_distributed():
+                import torch.distributed as dist
+
+                tot = plan.acc[:, :2].clone()
+                dist.all_reduce(tot)
+                per_head = (tot[:, 0] / tot[:, 1]).float()
+                ctx.den = tot[:, 1] / dist.get_world_size()
         loss = per_head.sum()
         ctx.plan, ctx.gen, ctx.params = plan, plan.generation, params
         ctx.target, ctx.ignore_index = target, ignore_index
-        stats = plan.acc.clone()
         ctx.stats = stats
         ctx.mark_non_differentiable(pred, stats)
         return loss, pred, stats
@@ -164,7 +224,7 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
             raise ops._lib.RtsdsError("BiSeNet backward called after another forward reused the plan's saved activations")
         plan.awaiting_backward = False
         main, aux = plan.out_sizes()
-        plan.gscale.copy_((dloss.double() / ctx.stats[:, 1]).float())
+        plan.gscale.copy_((dloss.double() / ctx.den).float())
         for i, z in enumerate((plan.z, plan.z1, plan.z2)):
             oh, ow = main if i == 0 else aux
             if ctx.one_pass[i]:
@@ -173,9 +233,7 @@ class _BiSeNetFusedCEFn(torch.autograd.Function):
                 plan.dz[i].zero_()
                 ops.resize_ce_bwd(z, plan.n, plan.h8, plan.w8, plan.nc, 32, oh, ow, ctx.target, ctx.ignore_index,
                                   plan.gscale[i:i + 1], plan.dz[i])
-        flat, gw = plan.new_grads()
-        _run_backward(plan, gw, flat)
-        return (None, None, None, None) + _grad_tuple(plan, ctx.params, gw)
+        return (None, None, None, None) + _finish_backward(plan, ctx.params)
 
 
 def bisenet_fused_ce(model, x, target, ignore_index=255, return_logits=False):

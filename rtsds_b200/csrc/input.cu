@@ -24,7 +24,10 @@ static inline AaAxis make_axis(int in, int out) {
     return a;
 }
 __device__ __forceinline__ void aa_window(int i, const AaAxis& a, int in, int* xmin, int* xsize, float* center) {
-    const float c = a.scale * (static_cast<float>(i) + 0.5f);
+    // ATen rounds the centre to float BEFORE it is used (center = scale * (i + 0.5)); __fmul_rn keeps nvcc from contracting
+    // the product into the subtractions below, which would use the unrounded centre: half an ulp of a coordinate near 2000
+    // is 6e-5 pixel — 1e-2 grey levels after the filter, harmless but not what the reference computes
+    const float c = __fmul_rn(a.scale, static_cast<float>(i) + 0.5f);
     int lo = static_cast<int>(c - a.support + 0.5f);
     if (lo < 0) lo = 0;
     int hi = static_cast<int>(c + a.support + 0.5f);

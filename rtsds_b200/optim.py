@@ -148,11 +148,11 @@ class _Fused(torch.optim.Optimizer):
         for t_prev, entries in by_step.items():
             key = (t_prev == 0 and self._kind == SGD, tuple((p.data_ptr(), g.data_ptr()) for p, g, _, _ in entries),
                    tuple(id(pl) for pl in self._plans))
-            tab = self._tables.get(len(entries))
-            if tab is None or tab["key"] != key:
-                tab = self._build_table(entries, self._pack_targets(), dev)
-                tab["key"] = key
-                self._tables[len(entries)] = tab
+            tab = self._tables.get(key)
+            if tab is None:
+                if len(self._tables) >= 4:                    # gradient buffers normally cycle through one or two addresses
+                    self._tables.pop(next(iter(self._tables)))
+                tab = self._tables[key] = self._build_table(entries, self._pack_targets(), dev)
             h = OptHyper()
             h.kind, h.first_step = self._kind, int(t_prev == 0)
             t = t_prev + 1

@@ -52,7 +52,13 @@ def adversarial_step(generator, discriminator, generator_optimizer, discriminato
             loss_gen_source = generator_loss(out, source_label)
             source_features = out
         loss_gen_source = loss_gen_source / iterations
-    loss_gen_source.backward()
+    # data parallel: the generator's gradient is the sum of this backward and the adversarial one below (train.py:213,233);
+    # it is all-reduced ONCE, after the second (rtsds_b200/bisenet_autograd.py:_finish_backward)
+    generator.rtsds_ddp_hold = bool(getattr(generator, "rtsds_ddp", False))
+    try:
+        loss_gen_source.backward()
+    finally:
+        generator.rtsds_ddp_hold = False
 
     # ---- generator, target batch: lambda * BCE(D(softmax(G(target))), 1) / iterations (train.py:218-233)
     out = generator(target_image)
