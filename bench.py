@@ -173,26 +173,30 @@ def tc_conv_profile(model, x, reps=20):
     from rtsds_b200 import ops
 
     plan = next(iter(model._rtsds_plans.values()))
-    real = ops.conv2d_tc
+    real, real_gap = ops.conv2d_tc, ops.conv2d_tc_gap
     calls = []
 
     def record(d, xx, w, y, *a, **k):
-        calls.append((d, xx, w, y, a, k))
+        calls.append((real, d, xx, w, y, a, k))
         real(d, xx, w, y, *a, **k)
 
-    ops.conv2d_tc = record
+    def record_gap(d, xx, w, y, *a, **k):       # the two convs whose epilogue also accumulates the ARM global pools
+        calls.append((real_gap, d, xx, w, y, a, k))
+        real_gap(d, xx, w, y, *a, **k)
+
+    ops.conv2d_tc, ops.conv2d_tc_gap = record, record_gap
     try:
         plan.run_pre(x)
         plan.run_mid()
         torch.cuda.synchronize()
     finally:
-        ops.conv2d_tc = real
+        ops.conv2d_tc, ops.conv2d_tc_gap = real, real_gap
     rows = []
-    for d, xx, w, y, a, k in calls:
+    for fn, d, xx, w, y, a, k in calls:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(reps):
-                real(d, xx, w, y, *a, **k)
+                fn(d, xx, w, y, *a, **k)
         g.replay()
         torch.cuda.synchronize()
         ts = []

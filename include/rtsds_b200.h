@@ -138,6 +138,12 @@ int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w,
                         const float* scale, const float* shift, const void* residual,
                         float* stats, void* y, void* workspace, size_t ws_bytes,
                         rtsds_stream_t s);
+/* Same with AdaptiveAvgPool2d(1) of the layer's OUTPUT fused into the epilogue (build_bisenet.py:46 ARM pooling,
+ * build_contextpath.py:27-28 tail): gap_out fp32 [n, cout], zeroed by the caller, receives the mean over oh*ow of the
+ * final (post-activation) values. */
+int rtsds_conv2d_tc_fwd_gap(const RtsdsConvDesc* d, const void* x, const void* w,
+                            const float* scale, const float* shift, const void* residual,
+                            void* y, float* gap_out, void* workspace, size_t ws_bytes, rtsds_stream_t s);
 size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d);
 /* output-channel padding of the packed weight layout (32, 64 or a multiple of 128). */
 int rtsds_conv_cout_pad(int cout);
@@ -258,7 +264,7 @@ int rtsds_tapn_weights(const float* w_oihw, int c, int cin, int k, int kpad, flo
 int rtsds_tapn_weight_grad(const float* dw2, int c, int cin, int k, float* grad_oihw, rtsds_stream_t s);
 int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int w, int c, int k, int pad, int dil,
                       const float* scale, const float* shift, int act, float* stats, float* y, int y_ld,
-                      rtsds_stream_t s);
+                      float* gap_out /* fp32 [n,c] += mean over h*w of y (NULL: skip; caller zeroes) */, rtsds_stream_t s);
 int rtsds_tapn_scatter(const void* dy, int dy_ld, int dy_dtype, int n, int h, int w, int c, int k, int pad, int dil,
                        void* g, int g_ld, int g_dtype, rtsds_stream_t s);
 
@@ -403,6 +409,27 @@ int rtsds_gate_resize_nhwc(const void* src, int n, int h, int w, int c, int src_
  * buffer, build_bisenet.py:149 — quadratic in the activations — at 2^-8 and its FFM weights at 2^8). */
 int rtsds_scale_packed_channels(void* w_packed, int dtype, int64_t rows, int cin, int c0, int c1, float factor,
                                 rtsds_stream_t s);
+
+/* Eval mode, both AttentionRefinementModules and the two gated resizes into the concat buffer (:147-153) in ONE launch:
+ * every block evaluates the gates of its own 32 channels from the pooled vector (folded BatchNorm) and streams its share
+ * of destination pixels.  pooled: fp32 [n,c] = mean of src over its pixels (e.g. from rtsds_conv2d_tc_fwd_gap);
+ * mul_pooled != 0 multiplies the gate by pooled[n,c] (`cx2 * tail`, :149); out_scale: constant factor (block exponent of
+ * the fp16 cx2 slot).  dst: NHWC [n,oh,ow,dst_ld] of dtype, channels dst_coff .. dst_coff+c of each side. */
+typedef struct RtsdsArmSide {
+    const void* src;            /* NHWC [n,h,w_in,c] of dtype (pitch c) */
+    const float* pooled;
+    const float* w; const float* b; const float* gamma; const float* beta;
+    const float* running_mean; const float* running_var;
+    float eps, out_scale;
+    int h, w_in, c, dst_coff, mul_pooled;
+} RtsdsArmSide;
+int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide* a4, int dtype, int n, int oh, int ow, void* dst,
+                          int dst_ld, rtsds_stream_t s);
+/* rtsds_ffm_head + rtsds_resize_to_nchw in one kernel: out fp32 NCHW [n,c,oh,ow] = bilinear resize of
+ * Wc (f*a + f) + bc, z evaluated in shared memory for the source rows each block needs (f fp32, pitch >= 32). */
+int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pooled, int n, int h, int w, int c, const float* w1,
+                          const float* b1, const float* w2, const float* b2, const float* wc, const float* bc,
+                          float* attn_out, int oh, int ow, float* out, rtsds_stream_t s);
 
 /* FeatureFusionModule attention (:75-80) + final 1x1 conv (:167), evaluated at
  * feature resolution (the 1x1 conv commutes with the bilinear resize):

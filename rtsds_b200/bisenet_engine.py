@@ -71,6 +71,8 @@ class BiSeNetPlan:
         self.steps = []          # everything between the stems and the low-res logits
         self.pack_steps = []     # weight repack / BN fold (run when parameters change)
         self.ws = None
+        self.ws_ds = None
+        self.side_ds = None
         self._ws_bytes = 0
         self._param_version = None
         self._n_state = -1
@@ -106,7 +108,7 @@ class BiSeNetPlan:
     def note_ws(self, b):
         self._ws_bytes = max(self._ws_bytes, b)
 
-    def _conv_tapn(self, conv, bnmod, x, xshape, y, y_ld, act, in_ld, in_scale=None):
+    def _conv_tapn(self, conv, bnmod, x, xshape, y, y_ld, act, in_ld, in_scale=None, gap_out=None):
         """Skinny-output k x k conv + folded BatchNorm + activation in the taps-as-N form (rtsds_b200/tapn.py); y fp32.
         in_scale = (c0, c1, factor): input channels [c0, c1) of x are stored divided by `factor` (block exponent)."""
         from .tapn import TapNConv
@@ -115,10 +117,10 @@ class BiSeNetPlan:
         tn = TapNConv(self, conv, x, xshape, in_ld, train=False, in_scale=in_scale)
         bn = _BN(self, bnmod, cout)
         self.pack_steps.append(lambda: ops.bn_fold(bnmod, bn.scale, bn.shift, conv.bias))
-        self.steps.append(lambda: tn.forward(bn.scale, bn.shift, act, None, y, y_ld))
+        self.steps.append(lambda: tn.forward(bn.scale, bn.shift, act, None, y, y_ld, gap_out))
 
     def _conv(self, conv, bnmod, x, xshape, y, out_ld, act, *, in_ld=None, residual=None, res_ld=0, out_dtype=None,
-              x_off=0, y_off=0, bias=None, steps=None, in_scale=None):
+              x_off=0, y_off=0, bias=None, steps=None, in_scale=None, gap_out=None):
         """Append conv (+BN/bias, +residual, +act) reading NHWC x -> NHWC y.  Returns (oh, ow)."""
         steps = self.steps if steps is None else steps
         n, h, w, cin = xshape
@@ -142,8 +144,11 @@ class BiSeNetPlan:
         side = self._side_branch          # convs of the side-stream branch get their own split-K workspace
 
         def launch(desc, scale, shift, res, stats):
-            if use_tc:
-                ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats, self.ws_side if side else self.ws)
+            if use_tc and gap_out is not None:       # eval: AdaptiveAvgPool2d(1) of this layer's output in its epilogue
+                ops.conv2d_tc_gap(desc, xp, wpk, yp, scale, shift, res, gap_out, self.ws)
+            elif use_tc:
+                ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats,
+                              self.ws_ds if side == 2 else (self.ws_side if side else self.ws))
             else:
                 ops.conv2d_simt(desc, xp, wpk, yp, scale, shift, res, stats)
 
@@ -213,6 +218,20 @@ class BiSeNetPlan:
         self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
         shape = (n, ph, pw, 64)
         feats = []
+        # eval-mode tensor-core path: the global average pools of feature3 / feature4 (ARM pooling, context-path tail) are
+        # accumulated by the epilogue of the conv that produces them; ARM gates + gated resizes are one launch
+        self.fused_arm = self.use_tc and not self.train
+        self._gap_for = {}
+        if self.fused_arm:
+            c3_, c4_ = cp.layer3[-1].bn2.num_features if not hasattr(cp.layer3[-1], "conv3") else cp.layer3[-1].bn3.num_features, \
+                cp.layer4[-1].bn2.num_features if not hasattr(cp.layer4[-1], "conv3") else cp.layer4[-1].bn3.num_features
+            # one buffer (and one memset per forward) for all three fused global pools: feature3, feature4, FFM feature
+            self.pooled_all = torch.zeros(n * (c3_ + c4_ + nc), dtype=f32, device=self.device)
+            self._keep.append(self.pooled_all)
+            self.pooled34 = self.pooled_all[:n * (c3_ + c4_)]
+            self._gap_for[id(cp.layer3[-1])] = self.pooled34[:n * c3_]
+            self._gap_for[id(cp.layer4[-1])] = self.pooled34[n * c3_:]
+            self.steps.append(lambda: self.pooled_all.zero_())
         for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
             for blk in layer:
                 x, shape = (self._bottleneck if hasattr(blk, "conv3") else self._basic_block)(blk, x, shape)
@@ -226,8 +245,8 @@ class BiSeNetPlan:
         c3, c4 = s3[3], s4[3]
         if 256 + c3 + c4 != ccat:
             raise ops._lib.RtsdsError(f"feature fusion module expects {ccat} input channels, context path gives 256+{c3}+{c4}")
-        pooled3 = self.buf(n, c3, dtype=f32)
-        pooled4 = self.buf(n, c4, dtype=f32)
+        pooled3 = self.pooled34[:n * c3].view(n, c3) if self.fused_arm else self.buf(n, c3, dtype=f32)
+        pooled4 = self.pooled34[n * c3:].view(n, c4) if self.fused_arm else self.buf(n, c4, dtype=f32)
         gate3 = self.buf(n, c3, dtype=f32)
         gate4 = self.buf(n, c4, dtype=f32)
         self.arm_saved = dict(pooled3=pooled3, pooled4=pooled4, gate3=gate3, gate4=gate4)
@@ -237,18 +256,29 @@ class BiSeNetPlan:
         sv = self.arm_saved
         tr = self.train
         dt = self.dt
-        self.steps.append(lambda: ops.global_avgpool(f3, n, s3[1] * s3[2], c3, c3, pooled3))
-        self.steps.append(lambda: ops.global_avgpool(f4, n, s4[1] * s4[2], c4, c4, pooled4))
-        self.steps.append(lambda: ops.arm_gate(pooled3, arm1.conv, arm1.bn, tr, n, c3, gate3, None, sv.get("lin3"), sv.get("xhat3")))
-        # cx2 = ARM2(cx2) * tail, tail = GAP(feature4) = pooled4 (build_contextpath.py:27-28)
-        self.steps.append(lambda: ops.arm_gate(pooled4, arm2.conv, arm2.bn, tr, n, c4, gate4, pooled4, sv.get("lin4"), sv.get("xhat4")))
-        self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, ccat, 256, dt))
+        fused_arm = self.fused_arm and c3 % 32 == 0 and c4 % 32 == 0
+        if not fused_arm:
+            if self.fused_arm:      # the pools came from the conv epilogues already
+                pass
+            else:
+                self.steps.append(lambda: ops.global_avgpool(f3, n, s3[1] * s3[2], c3, c3, pooled3))
+                self.steps.append(lambda: ops.global_avgpool(f4, n, s4[1] * s4[2], c4, c4, pooled4))
+            self.steps.append(lambda: ops.arm_gate(pooled3, arm1.conv, arm1.bn, tr, n, c3, gate3, None, sv.get("lin3"), sv.get("xhat3")))
+            # cx2 = ARM2(cx2) * tail, tail = GAP(feature4) = pooled4 (build_contextpath.py:27-28)
+            self.steps.append(lambda: ops.arm_gate(pooled4, arm2.conv, arm2.bn, tr, n, c4, gate4, pooled4, sv.get("lin4"), sv.get("xhat4")))
+            self.steps.append(lambda: ops.gate_resize_nhwc(f3, n, s3[1], s3[2], c3, c3, gate3, h8, w8, cat, ccat, 256, dt))
         # fp16 inference: `cx2 * tail` (reference :149) is QUADRATIC in the activations (feature4 times its own global
         # mean), the one tensor of the net whose range can leave fp16's 65504 while everything linear stays tame; its slot
         # of the concat buffer carries a block exponent of 2^-8, undone in the FFM conv's weights for those channels
         self.cx2_scale = 2.0 ** -8 if self.dt == F16 else 1.0
         cx2s = self.cx2_scale
-        self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, ccat, 256 + c3, dt, cx2s))
+        if fused_arm:
+            self.steps.append(lambda: ops.arm_gate_resize(
+                ops.arm_side(f3, pooled3, arm1, s3[1], s3[2], c3, 256),
+                ops.arm_side(f4, pooled4, arm2, s4[1], s4[2], c4, 256 + c3, mul_pooled=True, out_scale=cx2s),
+                dt, n, h8, w8, cat, ccat))
+        else:
+            self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, ccat, 256 + c3, dt, cx2s))
         self.f3, self.s3, self.f4, self.s4 = f3, s3, f4, s4
         self.n_join = len(self.steps)        # everything from here on reads the spatial-path slot of the concat buffer
 
@@ -262,27 +292,34 @@ class BiSeNetPlan:
         # ---- feature fusion module + final 1x1 conv at 1/8 resolution (reference :162-167) ----
         ffm = m.feature_fusion_module
         self.feat = self.buf(n, h8, w8, 32, dtype=f32)
-        self.pooled_f = self.buf(n, nc, dtype=f32)
+        self.pooled_f = self.pooled_all[n * (c3 + c4):].view(n, nc) if self.fused_arm else self.buf(n, nc, dtype=f32)
         self.attn = self.buf(n, nc, dtype=f32)
         self.z = self.buf(n, h8, w8, 32, dtype=f32)
         from . import tapn
 
         in_scale = (256 + c3, ccat, 1.0 / self.cx2_scale) if self.cx2_scale != 1.0 else None
+        feat, pooled_f, z, attn = self.feat, self.pooled_f, self.z, self.attn
+        final = m.conv if m.with_interpolation else None
+        # eval with the x8 head: the FFM attention, the final 1x1 conv and the resize to the NCHW logits are ONE kernel that
+        # runs when the caller asks for the logits (logits()); z at 1/8 resolution is never written
+        self.fused_tail = (not self.train) and final is not None
         if not self.train and tapn.applicable(ffm.convblock.conv1):
+            if not self.fused_arm:
+                self.steps.append(lambda: pooled_f.zero_())
             self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, ccat,
-                            in_scale=in_scale)
+                            in_scale=in_scale, gap_out=pooled_f)
         else:
             self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, out_dtype=F32,
                        in_scale=in_scale)
-        feat, pooled_f, z, attn = self.feat, self.pooled_f, self.z, self.attn
-        final = m.conv if m.with_interpolation else None
-        self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))
-        self.steps.append(lambda: ops.ffm_head(feat, F32, 32, pooled_f, n, h8 * w8, nc, ffm.conv1, ffm.conv2, final, z, 32, attn))
+            self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))
+        if not self.fused_tail:
+            self.steps.append(lambda: ops.ffm_head(feat, F32, 32, pooled_f, n, h8 * w8, nc, ffm.conv1, ffm.conv2, final, z, 32, attn))
 
         self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
         if self._ws_bytes:
             self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
             self.ws_side = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+            self.ws_ds = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
 
     def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp):
         """Both stems in one tensor-core kernel (csrc/stem_tc.cu); eval mode: BN folded + ReLU."""
@@ -329,14 +366,23 @@ class BiSeNetPlan:
         oh, ow = ops.conv_out_size(h, 3, st, 1), ops.conv_out_size(w, 3, st, 1)
         t = self.buf(n, oh, ow, cout)
         y = self.buf(n, oh, ow, cout)
-        self._conv(blk.conv1, blk.bn1, x, shape, t, cout, ACT_RELU)
         if blk.downsample is not None:
+            # the 1x1 stride-2 shortcut conv only depends on the block input: it runs on its own stream (a parallel branch of
+            # the CUDA graph) beside conv1 instead of between conv1 and conv2 — 4.5-5.4 us each off the critical path at b=1
             ds = self.buf(n, oh, ow, cout)
-            self._conv(blk.downsample[0], blk.downsample[1], x, shape, ds, cout, ACT_NONE)
+            branch = []
+            self._side_branch = 2
+            self._conv(blk.downsample[0], blk.downsample[1], x, shape, ds, cout, ACT_NONE, steps=branch)
+            self._side_branch = False
+            self.steps.append(("fork", branch))
+            self._conv(blk.conv1, blk.bn1, x, shape, t, cout, ACT_RELU)
+            self.steps.append(("join",))
             res = ds
         else:
+            self._conv(blk.conv1, blk.bn1, x, shape, t, cout, ACT_RELU)
             res = x
-        self._conv(blk.conv2, blk.bn2, t, (n, oh, ow, cout), y, cout, ACT_RELU, residual=res, res_ld=cout)
+        self._conv(blk.conv2, blk.bn2, t, (n, oh, ow, cout), y, cout, ACT_RELU, residual=res, res_ld=cout,
+                   gap_out=self._gap_for.get(id(blk)))
         return y, (n, oh, ow, cout)
 
     def _bottleneck(self, blk, x, shape):
@@ -358,7 +404,8 @@ class BiSeNetPlan:
             res = ds
         else:
             res = x
-        self._conv(blk.conv3, blk.bn3, t2, (n, oh, ow, planes), y, cout, ACT_RELU, residual=res, res_ld=cout)
+        self._conv(blk.conv3, blk.bn3, t2, (n, oh, ow, planes), y, cout, ACT_RELU, residual=res, res_ld=cout,
+                   gap_out=self._gap_for.get(id(blk)))
         return y, (n, oh, ow, cout)
 
     # ------------------------------------------------------------------ execution
@@ -382,27 +429,53 @@ class BiSeNetPlan:
         for s in self.pre_steps:
             s(x)
 
+    def _run(self, steps, main, parallel):
+        """Plain steps are callables; ("fork", [steps]) runs its steps on the shortcut stream from this point on,
+        ("join",) makes the main stream wait for them (graph capture turns both into dependency edges)."""
+        for s in steps:
+            if not isinstance(s, tuple):
+                s()
+            elif s[0] == "fork":
+                if parallel:
+                    self.side_ds.wait_stream(main)
+                    with torch.cuda.stream(self.side_ds):
+                        for b in s[1]:
+                            b()
+                else:
+                    for b in s[1]:
+                        b()
+            elif parallel:
+                main.wait_stream(self.side_ds)
+
     def run_mid(self):
         if ops._lib.dry_run() or self.n_sp_steps == 0:
-            for s in self.steps:
-                s()
+            self._run(self.steps, None, False)
             return
         main = torch.cuda.current_stream(self.device)
         if self.side is None:
             self.side = torch.cuda.Stream(self.device)
+            self.side_ds = torch.cuda.Stream(self.device)
         self.side.wait_stream(main)                           # fork
         with torch.cuda.stream(self.side):
-            for s in self.steps[:self.n_sp_steps]:
-                s()
-        for s in self.steps[self.n_sp_steps:self.n_join]:
-            s()
+            self._run(self.steps[:self.n_sp_steps], None, False)
+        self._run(self.steps[self.n_sp_steps:self.n_join], main, True)
         main.wait_stream(self.side)                           # join
-        for s in self.steps[self.n_join:]:
-            s()
+        self._run(self.steps[self.n_join:], main, True)
 
     def forward_lowres(self, x, use_graph: bool):
         """Run everything up to the 1/8-resolution logits (self.z [, z1, z2])."""
-        self.refresh_weights()
+        # Scanning the version counters of ~200 tensors costs ~20 us of Python: at batch 1 that is 5 % of a frame and sits
+        # BEFORE the first launch.  The O(1) part of the key (the process-wide weights epoch, bumped by every backward
+        # pass) is checked up front; the per-tensor scan runs after the frame has been enqueued, overlapping the GPU,
+        # and in the rare case it finds an in-place edit the operands are re-packed and the frame is issued again.
+        late_check = not self.train and self._param_version is not None and self._param_version[-1] == weights_epoch.value()
+        if not late_check:
+            self.refresh_weights()
+        self._enqueue(x, use_graph)
+        if late_check and self.refresh_weights():
+            self._enqueue(x, use_graph)
+
+    def _enqueue(self, x, use_graph: bool):
         if self.train and self._stats_total:
             self.stats_all.zero_()
         self.generation += 1
@@ -424,6 +497,11 @@ class BiSeNetPlan:
         if self.model.with_interpolation:
             # F.interpolate(scale_factor=8) (reference :166): output is 8x the 1/8-resolution map
             out = torch.empty((n, self.nc, self.h8 * 8, self.w8 * 8), dtype=torch.float32, device=self.device)
+            if self.fused_tail and z is self.z:
+                ffm = self.model.feature_fusion_module
+                ops.ffm_head_resize(self.feat, 32, self.pooled_f, n, self.h8, self.w8, self.nc, ffm.conv1, ffm.conv2, self.model.conv,
+                                    out, self.attn)
+                return out
         else:
             out = torch.empty((n, self.nc, self.h8, self.w8), dtype=torch.float32, device=self.device)
         ops.resize_to_nchw(z, n, self.h8, self.w8, self.nc, 32, out)

@@ -70,6 +70,8 @@ struct TcParams {
     int out_dtype, act;
     float slope;
     int f16;                              // operands (and 16-bit outputs / residuals) are IEEE half instead of bf16
+    float* gap_out;                       // [n_img][cout] fp32, += gap_scale * sum over pixels of the final output (or NULL)
+    float gap_scale;
 };
 
 // Reduce 32 per-thread values across the 32 lanes of a warp so that lane j
@@ -107,17 +109,18 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
         }
 
+        const bool full = (co0 + 32 <= p.cout);
+        const bool out16 = p.out_dtype != RTSDS_F32;
+        const bool f16 = p.out_dtype == RTSDS_F16;
         if (valid) {
+            // scale/shift (folded BatchNorm or bias) -> + residual -> activation, all in registers
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
-            const bool full = (co0 + 32 <= p.cout);
-            if (p.out_dtype != RTSDS_F32) {
-                const bool f16 = p.out_dtype == RTSDS_F16;
-                uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + out_off + co0;
-                const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual);
-                if (full) {
-                    if (res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res + res_off + co0);
+            if (p.residual) {
+                if (out16) {
+                    const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + res_off + co0;
+                    if (full) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 rv = __ldg(rp + g);
@@ -126,50 +129,66 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
                             v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
                             v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (co0 + j < p.cout) v[j] += ld_16(res, j, f16);
                     }
+                } else {
+                    const float* res = reinterpret_cast<const float*>(p.residual) + res_off + co0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 rv = __ldg(reinterpret_cast<const float4*>(res + j));
+                            v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (co0 + j < p.cout) v[j] += res[j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+        }
+        if (p.gap_out) {
+            // global average pool of THIS layer's output fused into its epilogue (ARM AdaptiveAvgPool2d(1) / context-path
+            // tail, build_bisenet.py:46, build_contextpath.py:27-28): per-channel sums of the final fp32 values
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
+            const float s1 = warp_transpose_sum(t, lane);
+            atomicAdd(&s_stats[c0 + lane], s1);
+        }
+        if (valid) {
+            if (out16) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + out_off + co0;
+                if (full) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 o;
-                        o.x = pack_16x2(apply_act(v[g * 8 + 0], p.act, p.slope), apply_act(v[g * 8 + 1], p.act, p.slope), f16);
-                        o.y = pack_16x2(apply_act(v[g * 8 + 2], p.act, p.slope), apply_act(v[g * 8 + 3], p.act, p.slope), f16);
-                        o.z = pack_16x2(apply_act(v[g * 8 + 4], p.act, p.slope), apply_act(v[g * 8 + 5], p.act, p.slope), f16);
-                        o.w = pack_16x2(apply_act(v[g * 8 + 6], p.act, p.slope), apply_act(v[g * 8 + 7], p.act, p.slope), f16);
+                        o.x = pack_16x2(v[g * 8 + 0], v[g * 8 + 1], f16);
+                        o.y = pack_16x2(v[g * 8 + 2], v[g * 8 + 3], f16);
+                        o.z = pack_16x2(v[g * 8 + 4], v[g * 8 + 5], f16);
+                        o.w = pack_16x2(v[g * 8 + 6], v[g * 8 + 7], f16);
                         *reinterpret_cast<uint4*>(dst + g * 8) = o;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (co0 + j < p.cout) {
-                            float x = v[j];
-                            if (res) x += ld_16(res, res_off + co0 + j, f16);
-                            st_16(dst, j, apply_act(x, p.act, p.slope), f16);
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.cout) st_16(dst, j, v[j], f16);
                 }
             } else {
                 float* dst = reinterpret_cast<float*>(p.y) + out_off + co0;
-                const float* res = reinterpret_cast<const float*>(p.residual);
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (res) {
-                            float4 rv = __ldg(reinterpret_cast<const float4*>(res + res_off + co0 + j));
-                            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                        }
-                        o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
-                        o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
-                        *reinterpret_cast<float4*>(dst + j) = o;
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (co0 + j < p.cout) {
-                            float x = v[j];
-                            if (res) x += res[res_off + co0 + j];
-                            dst[j] = apply_act(x, p.act, p.slope);
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.cout) dst[j] = v[j];
                 }
             }
         }
@@ -352,6 +371,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
             }
         }
+        if (p.gap_out && p.split_k == 1) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                const int co = n0 + i;
+                if (co < p.cout) atomicAdd(&p.gap_out[static_cast<long long>(img) * p.cout + co], s_stats[i] * p.gap_scale);
+            }
+        }
     }
 
     if (p.cluster_reduce) {
@@ -395,6 +421,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         atomicAdd(&p.stats[co], s_stats[i]);
                         atomicAdd(&p.stats[p.cout + co], s_stats[BLOCK_N + i]);
                     }
+                }
+            }
+            if (p.gap_out) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                    const int co = n0 + i;
+                    if (co < p.cout) atomicAdd(&p.gap_out[static_cast<long long>(img) * p.cout + co], s_stats[i] * p.gap_scale);
                 }
             }
         }
@@ -692,11 +725,14 @@ splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_t
             if (p.out_dtype != RTSDS_F32) {
                 const bool f16 = p.out_dtype == RTSDS_F16;
                 if (p.residual) o += ld_16(p.residual, res_off + c, f16);
-                st_16(p.y, out_off + c, apply_act(o, p.act, p.slope), f16);
+                o = apply_act(o, p.act, p.slope);
+                st_16(p.y, out_off + c, o, f16);
             } else {
                 if (p.residual) o += reinterpret_cast<const float*>(p.residual)[res_off + c];
-                reinterpret_cast<float*>(p.y)[out_off + c] = apply_act(o, p.act, p.slope);
+                o = apply_act(o, p.act, p.slope);
+                reinterpret_cast<float*>(p.y)[out_off + c] = o;
             }
+            if (p.gap_out) atomicAdd(&p.gap_out[static_cast<long long>(img) * cout + c], o * p.gap_scale);   // rare path
         }
     }
     if (p.stats) {
@@ -918,7 +954,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     }
     bool halo = false;
     int halo_d = 0;
-    if (halo_mode && split == 1 && t.n_taps == 9 && t.view[0].used) {
+    if (halo_mode && split == 1 && t.n_taps == 9 && t.view[0].used && !t.gap_out) {
         for (int i = 0; i < 9; ++i) halo_d = max(halo_d, max(abs(t.dh[i]), abs(t.dw[i])));
         halo = halo_d == 1 || halo_d == 2 || halo_d == 4;
         bool seen[9] = {false};
@@ -953,6 +989,8 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     p.res_sn = t.res_sn; p.res_sh = t.res_sh; p.res_sw = t.res_sw;
     p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.y = t.y;
     p.out_dtype = t.out_dtype; p.act = t.act; p.slope = t.slope; p.f16 = t.in_f16;
+    p.gap_out = t.gap_out; p.gap_scale = t.gap_out ? 1.0f / (static_cast<float>(t.oh) * static_cast<float>(t.ow)) : 0.f;
+    if (t.gap_out && t.stats) { set_error("conv_tc: gap_out and stats are mutually exclusive"); return RTSDS_EINVAL; }
     int first_used = -1;
     for (int i = 0; i < 4; ++i) {
         if (!t.view[i].used) continue;
@@ -1028,7 +1066,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
         return launch_tcp<32, true, true>(maps, p, ctas, smem, stream);
     }
     const bool resident = kb_total >= 1 && tcp_smem_bytes(block_n, 3, kb_total) <= 227 * 1024;
-    if (persist_mode && split == 1 && resident && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30)) {
+    if (persist_mode && split == 1 && resident && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30) && !t.gap_out) {
         const size_t b_all = static_cast<size_t>(kb_total) * block_n * TC_BLOCK_K * 2;
         int st = resident ? 8 : (block_n == 128 ? 6 : 8);
         while (st > 2 && tcp_smem_bytes(block_n, st, resident ? kb_total : st) > 227 * 1024) --st;
@@ -1091,6 +1129,29 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
     rc = fwd_problem(d, x, w, TC_BLOCK_K, 2, &t);
     if (rc != RTSDS_OK) return rc;
     t.scale = scale; t.shift = shift; t.residual = residual; t.stats = stats; t.y = y;
+    return tp_run(t, workspace, ws_bytes, as_stream(s));
+}
+
+// Same, with the global average pool of the layer's OUTPUT fused into the epilogue: gap_out fp32 [n, cout] (zeroed by the
+// caller) receives mean over oh*ow of the final (post-activation) values — AdaptiveAvgPool2d(1) of build_bisenet.py:46 and
+// the context-path tail of build_contextpath.py:27-28 without a separate pass over feature3 / feature4.
+extern "C" int rtsds_conv2d_tc_fwd_gap(const RtsdsConvDesc* d, const void* x, const void* w, const float* scale,
+                                       const float* shift, const void* residual, void* y, float* gap_out,
+                                       void* workspace, size_t ws_bytes, rtsds_stream_t s) {
+    RTSDS_REQUIRE(d && x && w && y && gap_out, "conv2d_tc_fwd_gap: NULL argument");
+    RTSDS_REQUIRE(is_16bit(d->in_dtype), "conv2d_tc_fwd_gap: input must be bf16 or fp16");
+    RTSDS_REQUIRE(d->out_dtype == d->in_dtype || d->out_dtype == RTSDS_F32, "conv2d_tc_fwd_gap: out_dtype must be the input type or fp32");
+    RTSDS_REQUIRE(d->out_ld >= d->cout && d->out_ld % (d->out_dtype != RTSDS_F32 ? 8 : 4) == 0, "conv2d_tc_fwd_gap: out_ld");
+    RTSDS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv2d_tc_fwd_gap: pointers must be 16-byte aligned");
+    if (residual)
+        RTSDS_REQUIRE(d->res_ld >= d->cout && (reinterpret_cast<uintptr_t>(residual) & 15) == 0, "conv2d_tc_fwd_gap: residual pitch/alignment");
+    int rc = rtsds_check_device();
+    if (rc != RTSDS_OK) return rc;
+    TapProblem t;
+    rc = fwd_problem(d, x, w, TC_BLOCK_K, 2, &t);
+    if (rc != RTSDS_OK) return rc;
+    t.scale = scale; t.shift = shift; t.residual = residual; t.stats = nullptr; t.y = y; t.gap_out = gap_out;
     return tp_run(t, workspace, ws_bytes, as_stream(s));
 }
 

@@ -371,6 +371,153 @@ ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ poo
     }
 }
 
+// ---------------------------------------------------------------- ARM gate + gated bilinear resize, both ARMs, one launch
+// Eval mode (folded BatchNorm).  A block owns 32 channels of one ARM and a chunk of destination pixels: it first evaluates
+// ITS 32 gates  g[n,c] = sigmoid(BN(W[c,:] . pooled[n,:] + b[c])) (* pooled[n,c] for the `cx2 * tail` of
+// build_bisenet.py:149) (* out_scale) — a warp per 4 channels, 32 dot products of length C, redundant across the pixel
+// chunks but 16 K MACs — and then streams its pixels: bilinear gather from the 1/16 or 1/32 feature map, times the gate,
+// 16-byte stores into the concat buffer slot.  Replaces arm_gate x2 + gate_resize x2 (4 launches, ~26 us at b=1).
+struct ArmSide {
+    const void* src; const float* pooled; const float* w; const float* b; const float* gamma; const float* beta;
+    const float* mean; const float* var; float eps, out_scale; int h, w_, c, coff, mul_pooled;
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, int oh, int ow, T* __restrict__ dst, int dst_ld) {
+    __shared__ float s_gate[32];
+    const bool second = static_cast<int>(blockIdx.x) >= blocks0;
+    const ArmSide& a = second ? a1 : a0;
+    const int local = second ? blockIdx.x - blocks0 : blockIdx.x;
+    const int cg = local / chunks, chunk = local - cg * chunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npix = oh * ow;
+    const int per = (npix + chunks - 1) / chunks;
+    const int p_begin = chunk * per, p_end = min(p_begin + per, npix);
+    const float rh = static_cast<float>(a.h) / static_cast<float>(oh), rw = static_cast<float>(a.w_) / static_cast<float>(ow);
+    const T* src = reinterpret_cast<const T*>(a.src);
+    for (int img = 0; img < n; ++img) {
+        const float* pp = a.pooled + static_cast<long long>(img) * a.c;
+        for (int k = 0; k < 4; ++k) {
+            const int co = cg * 32 + warp * 4 + k;
+            const float* wr = a.w + static_cast<long long>(co) * a.c;
+            float acc = 0.f;
+            for (int i = lane; i < a.c; i += 32) acc = fmaf(wr[i], pp[i], acc);
+            acc = warp_sum(acc) + (a.b ? a.b[co] : 0.f);
+            if (lane == 0) {
+                const float sc = a.gamma[co] / sqrtf(a.var[co] + a.eps);
+                const float sh = a.beta[co] - a.mean[co] * sc;
+                float v = 1.f / (1.f + expf(-(acc * sc + sh)));
+                if (a.mul_pooled) v *= pp[co];
+                s_gate[warp * 4 + k] = v * a.out_scale;
+            }
+        }
+        __syncthreads();
+        const int g8 = threadIdx.x & 3;                                   // 8-channel group inside the block's 32 channels
+        float gv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = s_gate[g8 * 8 + j];
+        const T* sb = src + static_cast<long long>(img) * a.h * a.w_ * a.c + cg * 32 + g8 * 8;
+        T* db = dst + static_cast<long long>(img) * npix * dst_ld + a.coff + cg * 32 + g8 * 8;
+        for (int p = p_begin + (threadIdx.x >> 2); p < p_end; p += 64) {
+            const int oy = p / ow, ox = p - oy * ow;
+            const Lerp ly = lerp_src(oy, rh, a.h), lx = lerp_src(ox, rw, a.w_);
+            const V8 p00 = ld8(sb + (static_cast<long long>(ly.i0) * a.w_ + lx.i0) * a.c);
+            const V8 p01 = ld8(sb + (static_cast<long long>(ly.i0) * a.w_ + lx.i1) * a.c);
+            const V8 p10 = ld8(sb + (static_cast<long long>(ly.i1) * a.w_ + lx.i0) * a.c);
+            const V8 p11 = ld8(sb + (static_cast<long long>(ly.i1) * a.w_ + lx.i1) * a.c);
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                o.v[j] = (ly.l0 * (lx.l0 * p00.v[j] + lx.l1 * p01.v[j]) + ly.l1 * (lx.l0 * p10.v[j] + lx.l1 * p11.v[j])) * gv[j];
+            st8(db + static_cast<long long>(p) * dst_ld, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- FFM attention + final 1x1 conv + x8 resize -> NCHW logits
+// out[n,o,oy,ox] = bc[o] + sum_k Wc[o,k] (1 + a[n,k]) * bilinear(f)[k]:  the 1x1 conv commutes with the bilinear resize, so z
+// is evaluated at feature resolution — here only for the source rows a block's output rows touch, in shared memory — and
+// the block then writes its rows of all classes.  Replaces ffm_head + resize_nchw (and the z round trip through L2).
+constexpr int FHR_ROWS = 4, FHR_THREADS = 256;
+__global__ void __launch_bounds__(FHR_THREADS)
+ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __restrict__ pooled, int h, int w, int c,
+                       const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                       const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
+                       float* attn_out, int oh, int ow, float rh, float rw, int max_rows, float* __restrict__ out) {
+    extern __shared__ float s_z[];                                        // [rows][w][c]
+    __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C], s_b[FFM_MAX_C];
+    __shared__ float s_w[FFM_MAX_C * FFM_MAX_C];
+    const int img = blockIdx.y, t = threadIdx.x;
+    const float* pp = pooled + static_cast<long long>(img) * c;
+    if (t < c) {
+        float acc = b1[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(w1[t * c + k], pp[k], acc);
+        s_h[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (t < c) {
+        float acc = b2[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(w2[t * c + k], s_h[k], acc);
+        const float a = 1.f / (1.f + expf(-acc));
+        s_a[t] = a;
+        s_b[t] = bc ? bc[t] : 0.f;
+        if (attn_out && blockIdx.x == 0) attn_out[static_cast<long long>(img) * c + t] = a;
+    }
+    __syncthreads();
+    for (int i = t; i < c * c; i += FHR_THREADS) s_w[i] = wc[i] * (1.f + s_a[i % c]);       // f*a + f folded into the weights
+    const int oy0 = blockIdx.x * FHR_ROWS, oy1 = min(oy0 + FHR_ROWS, oh);
+    const int ys = lerp_src(oy0, rh, h).i0, ye = lerp_src(oy1 - 1, rh, h).i1;
+    const int rows = ye - ys + 1;                                          // <= max_rows (host)
+    __syncthreads();
+    for (int i = t; i < rows * w; i += FHR_THREADS) {
+        const int r = i / w, x = i - r * w;
+        const float* fp = f + ((static_cast<long long>(img) * h + ys + r) * w + x) * f_ld;
+        float fv[FFM_MAX_C];
+#pragma unroll
+        for (int k = 0; k < FFM_MAX_C; k += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(fp + k));
+            fv[k] = q.x; fv[k + 1] = q.y; fv[k + 2] = q.z; fv[k + 3] = q.w;
+        }
+        float* zp = s_z + static_cast<long long>(i) * c;
+        for (int o = 0; o < c; ++o) {
+            float acc = s_b[o];
+#pragma unroll
+            for (int k = 0; k < FFM_MAX_C; ++k)
+                if (k < c) acc = fmaf(s_w[o * c + k], fv[k], acc);
+            zp[o] = acc;
+        }
+    }
+    __syncthreads();
+    const long long plane = static_cast<long long>(oh) * ow;
+    for (int ox = t * 4; ox < ow; ox += FHR_THREADS * 4) {
+        Lerp lx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lx[j] = lerp_src(min(ox + j, ow - 1), rw, w);
+        const bool vec = (ox + 4 <= ow) && ((ow & 3) == 0);
+        for (int oy = oy0; oy < oy1; ++oy) {
+            const Lerp ly = lerp_src(oy, rh, h);
+            const float* r0 = s_z + static_cast<long long>(ly.i0 - ys) * w * c;
+            const float* r1 = s_z + static_cast<long long>(ly.i1 - ys) * w * c;
+            float* op = out + static_cast<long long>(img) * c * plane + static_cast<long long>(oy) * ow + ox;
+            for (int ch = 0; ch < c; ++ch) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = ly.l0 * (lx[j].l0 * r0[lx[j].i0 * c + ch] + lx[j].l1 * r0[lx[j].i1 * c + ch]) +
+                           ly.l1 * (lx[j].l0 * r1[lx[j].i0 * c + ch] + lx[j].l1 * r1[lx[j].i1 * c + ch]);
+                if (vec) {
+                    __stcs(reinterpret_cast<float4*>(op + ch * plane), make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ox + j < ow) op[ch * plane + j] = v[j];
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- bilinear resize NHWC fp32 -> NCHW fp32
 constexpr int RS_THREADS = 256, RS_PX = 4, RS_TILE = RS_THREADS * RS_PX;
 __global__ void __launch_bounds__(RS_THREADS)
@@ -631,6 +778,56 @@ extern "C" int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, 
     resize_nchw_kernel<<<grid, RS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw, out);
     count_launch();
     return check_launch("resize_nchw_kernel");
+}
+
+extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide* a4, int dtype, int n, int oh, int ow, void* dst,
+                                     int dst_ld, rtsds_stream_t s) {
+    RTSDS_REQUIRE(a3 && a4 && dst && n > 0 && oh > 0 && ow > 0, "arm_gate_resize: bad argument");
+    const RtsdsArmSide* as[2] = {a3, a4};
+    ArmSide k[2];
+    for (int i = 0; i < 2; ++i) {
+        const RtsdsArmSide& a = *as[i];
+        RTSDS_REQUIRE(a.src && a.pooled && a.w && a.gamma && a.beta && a.running_mean && a.running_var, "arm_gate_resize: NULL pointer");
+        RTSDS_REQUIRE(a.c > 0 && a.c % 32 == 0 && a.h > 0 && a.w_in > 0 && a.dst_coff % 8 == 0 && a.dst_coff + a.c <= dst_ld,
+                      "arm_gate_resize: channels must be a multiple of 32 and fit the destination slot");
+        k[i] = ArmSide{a.src, a.pooled, a.w, a.b, a.gamma, a.beta, a.running_mean, a.running_var, a.eps, a.out_scale,
+                       a.h, a.w_in, a.c, a.dst_coff, a.mul_pooled};
+    }
+    RTSDS_REQUIRE(dst_ld % 8 == 0, "arm_gate_resize: dst_ld must be a multiple of 8");
+    const int groups = a3->c / 32 + a4->c / 32;
+    int chunks = static_cast<int>(cdiv(2LL * num_sms(), groups));
+    const int npix = oh * ow;
+    if (chunks > npix / 64) chunks = npix / 64 > 0 ? npix / 64 : 1;
+    const int blocks0 = (a3->c / 32) * chunks, blocks = groups * chunks;
+    cudaStream_t st = as_stream(s);
+    if (dtype == RTSDS_F16)
+        arm_gate_resize_kernel<__half><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld);
+    else if (dtype == RTSDS_BF16)
+        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld);
+    else if (dtype == RTSDS_F32)
+        arm_gate_resize_kernel<float><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld);
+    else { set_error("arm_gate_resize: bad dtype"); return RTSDS_EINVAL; }
+    count_launch();
+    return check_launch("arm_gate_resize_kernel");
+}
+
+extern "C" int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pooled, int n, int h, int w, int c, const float* w1,
+                                     const float* b1, const float* w2, const float* b2, const float* wc, const float* bc,
+                                     float* attn_out, int oh, int ow, float* out, rtsds_stream_t s) {
+    RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && wc && out && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "ffm_head_resize: bad argument");
+    RTSDS_REQUIRE(c > 0 && c <= FFM_MAX_C && f_ld >= FFM_MAX_C && f_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0,
+                  "ffm_head_resize: c <= %d, feature pitch >= %d floats and 16-byte aligned", FFM_MAX_C, FFM_MAX_C);
+    const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
+    const int max_rows = static_cast<int>(static_cast<double>(FHR_ROWS) * h / oh) + 3;
+    const size_t smem = sizeof(float) * static_cast<size_t>(max_rows) * w * c;
+    RTSDS_REQUIRE(smem <= 160 * 1024, "ffm_head_resize: %zu bytes of shared memory needed for %d source rows", smem, max_rows);
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(ffm_head_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; }
+    dim3 grid(static_cast<unsigned>(cdiv(oh, FHR_ROWS)), n);
+    ffm_head_resize_kernel<<<grid, FHR_THREADS, smem, as_stream(s)>>>(f, f_ld, pooled, h, w, c, w1, b1, w2, b2, wc, bc, attn_out, oh, ow,
+                                                                      rh, rw, max_rows, out);
+    count_launch();
+    return check_launch("ffm_head_resize_kernel");
 }
 
 extern "C" int rtsds_nchw_to_nhwc(const float* x, int n, int c, int64_t hw, int dtype, void* y, int ld, int c_off, rtsds_stream_t s) {

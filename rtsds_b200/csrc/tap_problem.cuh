@@ -26,6 +26,7 @@ struct TapProblem {
     int out_dtype, act; float slope;
     int split_req;
     int in_f16;                   // operands are IEEE half (RTSDS_F16) instead of bf16
+    float* gap_out;               // [n_img][cout] fp32: += mean over the output pixels of the final value (tensor-core path)
 };
 
 

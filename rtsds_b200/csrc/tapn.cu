@@ -52,14 +52,17 @@ template <int K>
 __global__ void __launch_bounds__(256)
 tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int w, int c, int k_rt, int pad, int dil,
                    const float* __restrict__ scale, const float* __restrict__ shift, int act, float* stats,
-                   float* __restrict__ y, int y_ld) {
+                   float* __restrict__ y, int y_ld, float* gap_out, float gap_scale) {
     __shared__ float s_stats[2][8][32];
     const int k = K > 0 ? K : k_rt;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const long long npix = static_cast<long long>(n) * h * w;
+    // blockIdx.y = image: the fused global average pool (gap_out) sums per image
+    const long long pix0 = static_cast<long long>(blockIdx.y) * h * w;
+    const long long npix = pix0 + static_cast<long long>(h) * w;
+    float gs = 0.f;
     const float sc = (scale && lane < c) ? scale[lane] : 1.f, sh = (shift && lane < c) ? shift[lane] : 0.f;
     float s1 = 0.f, s2 = 0.f;
-    for (long long p = static_cast<long long>(blockIdx.x) * 8 + wrp; p < npix; p += static_cast<long long>(gridDim.x) * 8) {
+    for (long long p = pix0 + static_cast<long long>(blockIdx.x) * 8 + wrp; p < npix; p += static_cast<long long>(gridDim.x) * 8) {
         const int x = static_cast<int>(p % w);
         const int yy = static_cast<int>((p / w) % h);
         float acc = 0.f;
@@ -93,7 +96,20 @@ tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int 
             float v = acc * sc + sh;
             if (act == RTSDS_ACT_RELU) v = fmaxf(v, 0.f);
             y[p * y_ld + lane] = v;
+            gs += v;
         }
+    }
+    if (gap_out) {                  // AdaptiveAvgPool2d(1) of the FFM feature (build_bisenet.py:75) fused into its producer
+        __syncthreads();
+        s_stats[0][wrp][lane] = gs;
+        __syncthreads();
+        if (wrp == 0 && lane < c) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a += s_stats[0][i][lane];
+            atomicAdd(&gap_out[static_cast<long long>(blockIdx.y) * c + lane], a * gap_scale);
+        }
+        __syncthreads();
     }
     if (stats) {
         s_stats[0][wrp][lane] = s1; s_stats[1][wrp][lane] = s2;
@@ -171,17 +187,20 @@ extern "C" int rtsds_tapn_weight_grad(const float* dw2, int c, int cin, int k, f
 
 extern "C" int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int w, int c, int k, int pad, int dil,
                                  const float* scale, const float* shift, int act, float* stats, float* y, int y_ld,
-                                 rtsds_stream_t s) {
+                                 float* gap_out, rtsds_stream_t s) {
     RTSDS_REQUIRE(t_buf && y && n > 0 && h > 0 && w > 0 && c > 0 && c <= 32 && k > 0 && t_ld >= k * k * c && y_ld >= c, "tapn_gather: bad argument");
-    const long long npix = static_cast<long long>(n) * h * w;
+    RTSDS_REQUIRE(n <= 65535, "tapn_gather: batch too large");
+    const long long npix = static_cast<long long>(h) * w;
     long long g = cdiv(npix, 8 * 4);
-    const long long cap = 8LL * num_sms();
+    const long long cap = cdiv(8LL * num_sms(), n);
     if (g > cap) g = cap;
     if (g < 1) g = 1;
+    const dim3 grid(static_cast<unsigned>(g), static_cast<unsigned>(n));
+    const float gsc = 1.0f / static_cast<float>(npix);
     if (k == 3)
-        tapn_gather_kernel<3><<<static_cast<int>(g), 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld);
+        tapn_gather_kernel<3><<<grid, 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
     else
-        tapn_gather_kernel<0><<<static_cast<int>(g), 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld);
+        tapn_gather_kernel<0><<<grid, 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
     count_launch();
     return check_launch("tapn_gather_kernel");
 }

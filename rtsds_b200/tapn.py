@@ -58,14 +58,15 @@ class TapNConv:
         if self.w_bwd is not None:
             ops.pack_conv_weight(self.w_bwd, self.dt, self.wpk_bwd)
 
-    def forward(self, scale, shift, act, stats, y_ptr, y_ld):
-        """y (fp32 NHWC, pitch y_ld) = act(scale * conv(x) + shift); stats: train-mode sum / sum of squares of conv(x)."""
+    def forward(self, scale, shift, act, stats, y_ptr, y_ld, gap_out=None):
+        """y (fp32 NHWC, pitch y_ld) = act(scale * conv(x) + shift); stats: train-mode sum / sum of squares of conv(x);
+        gap_out: fp32 [n,c] += mean over h*w of y (AdaptiveAvgPool2d(1) fused into the gather; caller zeroes it)."""
         if self.tc:
             ops.conv2d_tc(self.d_fwd, self.x_ptr, self.wpk_fwd, self.T, None, None, None, None, self.plan.ws)
         else:
             ops.conv2d_simt(self.d_fwd, self.x_ptr, self.wpk_fwd, self.T, None, None, None, None)
         check(lib().rtsds_tapn_gather(_p(self.T), self.t_ld, self.n, self.h, self.w, self.c, self.k, self.pad, self.dil, _p(scale),
-                                      _p(shift), act, _p(stats), _p(y_ptr), y_ld, ops._s()), "tapn_gather")
+                                      _p(shift), act, _p(stats), _p(y_ptr), y_ld, _p(gap_out), ops._s()), "tapn_gather")
 
     def scatter(self, dy_ptr, dy_ld, dy_dtype):
         check(lib().rtsds_tapn_scatter(_p(dy_ptr), dy_ld, dy_dtype, self.n, self.h, self.w, self.c, self.k, self.pad, self.dil,

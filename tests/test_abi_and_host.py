@@ -88,7 +88,9 @@ def test_bisenet_parameter_tree_matches_reference_contract():
 
 
 def test_plan_launch_sequence_dry_run(monkeypatch):
-    """RTSDS_DRYRUN records launches without a GPU: 22 tensor-core convs, 1 fused stem pair, ... per eval forward."""
+    """RTSDS_DRYRUN records launches without a GPU: 22 tensor-core convs (2 of them with the ARM global pool fused into the
+    epilogue), 1 fused stem pair, ONE kernel for both ARM gates + gated resizes, ONE for FFM attention + final conv + x8
+    resize ... per eval forward: 27 launches of this library (34 in round 1) + one memset."""
     monkeypatch.setenv("RTSDS_DRYRUN", "1")
     from models.bisenet.build_bisenet import BiSeNet
     from rtsds_b200 import _lib
@@ -98,14 +100,20 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     out = m(torch.zeros(1, 3, 512, 1024))
     assert out.shape == (1, 19, 512, 1024)
     c = collections.Counter(_lib.lib().calls)
-    assert c["rtsds_conv2d_tc_fwd"] == 22 and c["rtsds_stem_pair_tc_fwd"] == 1 and c["rtsds_maxpool3x3s2_fwd"] == 1
+    assert c["rtsds_conv2d_tc_fwd"] == 20 and c["rtsds_conv2d_tc_fwd_gap"] == 2
+    assert c["rtsds_stem_pair_tc_fwd"] == 1 and c["rtsds_maxpool3x3s2_fwd"] == 1
     assert c["rtsds_stem_conv_fwd"] == 0          # both stems run as one tensor-core kernel
-    assert c["rtsds_arm_gate"] == 2 and c["rtsds_gate_resize_nhwc"] == 2 and c["rtsds_ffm_head"] == 1
-    assert c["rtsds_resize_to_nchw"] == 1 and c["rtsds_bn_fold"] == 24
+    assert c["rtsds_arm_gate_resize"] == 1 and c["rtsds_arm_gate"] == 0 and c["rtsds_gate_resize_nhwc"] == 0 and c["rtsds_global_avgpool"] == 0
+    assert c["rtsds_tapn_gather"] == 1 and c["rtsds_ffm_head_resize"] == 1 and c["rtsds_ffm_head"] == 0 and c["rtsds_resize_to_nchw"] == 0
+    assert c["rtsds_bn_fold"] == 24
+    forward_calls = [k for k in _lib.lib().calls if not k.startswith(("rtsds_pack", "rtsds_bn_fold", "rtsds_stem_pack", "rtsds_tapn_weights",
+                                                                      "rtsds_conv_cout_pad", "rtsds_conv2d_tc_workspace", "rtsds_check",
+                                                                      "rtsds_scale_packed", "rtsds_launch_count"))]
+    assert len(forward_calls) == 27, (len(forward_calls), collections.Counter(forward_calls))
     _lib.lib().calls.clear()
     m(torch.zeros(1, 3, 512, 1024))                 # weights unchanged: no repack on the second call
     c = collections.Counter(_lib.lib().calls)
-    assert c["rtsds_pack_conv_weight"] == 0 and c["rtsds_conv2d_tc_fwd"] == 22
+    assert c["rtsds_pack_conv_weight"] == 0 and c["rtsds_conv2d_tc_fwd"] == 20
     # 720x1280 (GTA5) gives the odd 45x80 / 23x40 feature maps and a x8 head
     m.train()
     _lib.lib().calls.clear()
