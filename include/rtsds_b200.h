@@ -139,8 +139,10 @@ int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const void* w,
                         float* stats, void* y, void* workspace, size_t ws_bytes,
                         rtsds_stream_t s);
 /* Same with AdaptiveAvgPool2d(1) of the layer's OUTPUT fused into the epilogue (build_bisenet.py:46 ARM pooling,
- * build_contextpath.py:27-28 tail): gap_out fp32 [n, cout], zeroed by the caller, receives the mean over oh*ow of the
- * final (post-activation) values. */
+ * build_contextpath.py:27-28 tail), deterministically: gap_out fp32 [n][parts][cout], parts =
+ * rtsds_conv2d_tc_gap_parts(d); every CTA WRITES the partial mean (sum of the final post-activation values of its rows /
+ * (oh*ow)) of its part; the mean is the sum over parts, taken by the consumer in index order.  Nothing to zero. */
+int rtsds_conv2d_tc_gap_parts(const RtsdsConvDesc* d);
 int rtsds_conv2d_tc_fwd_gap(const RtsdsConvDesc* d, const void* x, const void* w,
                             const float* scale, const float* shift, const void* residual,
                             void* y, float* gap_out, void* workspace, size_t ws_bytes, rtsds_stream_t s);
@@ -264,7 +266,9 @@ int rtsds_tapn_weights(const float* w_oihw, int c, int cin, int k, int kpad, flo
 int rtsds_tapn_weight_grad(const float* dw2, int c, int cin, int k, float* grad_oihw, rtsds_stream_t s);
 int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int w, int c, int k, int pad, int dil,
                       const float* scale, const float* shift, int act, float* stats, float* y, int y_ld,
-                      float* gap_out /* fp32 [n,c] += mean over h*w of y (NULL: skip; caller zeroes) */, rtsds_stream_t s);
+                      float* gap_out /* NULL, or fp32 [n][rtsds_tapn_gather_parts(n,h,w)][c]: one partial mean of y per block,
+                                        written (deterministic: the consumer adds them in order) */, rtsds_stream_t s);
+int rtsds_tapn_gather_parts(int n, int h, int w);
 int rtsds_tapn_scatter(const void* dy, int dy_ld, int dy_dtype, int n, int h, int w, int c, int k, int pad, int dil,
                        void* g, int g_ld, int g_dtype, rtsds_stream_t s);
 
@@ -412,7 +416,8 @@ int rtsds_scale_packed_channels(void* w_packed, int dtype, int64_t rows, int cin
 
 /* Eval mode, both AttentionRefinementModules and the two gated resizes into the concat buffer (:147-153) in ONE launch:
  * every block evaluates the gates of its own 32 channels from the pooled vector (folded BatchNorm) and streams its share
- * of destination pixels.  pooled: fp32 [n,c] = mean of src over its pixels (e.g. from rtsds_conv2d_tc_fwd_gap);
+ * of destination pixels.  pooled: fp32 [n,pooled_parts,c], the mean of src over its pixels as pooled_parts partial means
+ * that are added in index order (rtsds_conv2d_tc_fwd_gap writes one per CTA; a plain mean is pooled_parts = 1);
  * mul_pooled != 0 multiplies the gate by pooled[n,c] (`cx2 * tail`, :149); out_scale: constant factor (block exponent of
  * the fp16 cx2 slot).  dst: NHWC [n,oh,ow,dst_ld] of dtype, channels dst_coff .. dst_coff+c of each side. */
 typedef struct RtsdsArmSide {
@@ -421,15 +426,16 @@ typedef struct RtsdsArmSide {
     const float* w; const float* b; const float* gamma; const float* beta;
     const float* running_mean; const float* running_var;
     float eps, out_scale;
-    int h, w_in, c, dst_coff, mul_pooled;
+    int h, w_in, c, dst_coff, mul_pooled, pooled_parts;
 } RtsdsArmSide;
 int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide* a4, int dtype, int n, int oh, int ow, void* dst,
                           int dst_ld, rtsds_stream_t s);
 /* rtsds_ffm_head + rtsds_resize_to_nchw in one kernel: out fp32 NCHW [n,c,oh,ow] = bilinear resize of
- * Wc (f*a + f) + bc, z evaluated in shared memory for the source rows each block needs (f fp32, pitch >= 32). */
+ * Wc (f*a + f) + bc, z evaluated in shared memory for the source rows each block needs (f fp32, pitch >= 32).
+ * pooled: fp32 [n][pooled_parts][c] partial means of f, added in index order (a plain mean: pooled_parts = 1). */
 int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pooled, int n, int h, int w, int c, const float* w1,
                           const float* b1, const float* w2, const float* b2, const float* wc, const float* bc,
-                          float* attn_out, int oh, int ow, float* out, rtsds_stream_t s);
+                          float* attn_out, int pooled_parts, int oh, int ow, float* out, rtsds_stream_t s);
 
 /* FeatureFusionModule attention (:75-80) + final 1x1 conv (:167), evaluated at
  * feature resolution (the 1x1 conv commutes with the bilinear resize):

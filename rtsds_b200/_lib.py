@@ -60,7 +60,7 @@ class ArmSide(C.Structure):
     _fields_ = [("src", C.c_void_p), ("pooled", C.c_void_p), ("w", C.c_void_p), ("b", C.c_void_p), ("gamma", C.c_void_p),
                 ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_float),
                 ("out_scale", C.c_float), ("h", C.c_int), ("w_in", C.c_int), ("c", C.c_int), ("dst_coff", C.c_int),
-                ("mul_pooled", C.c_int)]
+                ("mul_pooled", C.c_int), ("pooled_parts", C.c_int)]
 
 
 class OptHyper(C.Structure):
@@ -89,6 +89,7 @@ SIGNATURES = {
     "rtsds_conv_cout_pad": (_I, [_I]),
     "rtsds_conv2d_tc_tune": (None, [_I, _I]),
     "rtsds_conv2d_tc_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "rtsds_conv2d_tc_gap_parts": (_I, [_CD]),
     "rtsds_conv2d_tc_fwd_gap": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "rtsds_conv2d_tc_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_simt_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -99,7 +100,8 @@ SIGNATURES = {
     "rtsds_tapn_weight_grad": (_I, [_P, _I, _I, _I, _P, _P]),
     "rtsds_tapn_gather": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "rtsds_arm_gate_resize": (_I, [C.POINTER(ArmSide), C.POINTER(ArmSide), _I, _I, _I, _I, _P, _I, _P]),
-    "rtsds_ffm_head_resize": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "rtsds_ffm_head_resize": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "rtsds_tapn_gather_parts": (_I, [_I, _I, _I]),
     "rtsds_tapn_scatter": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "rtsds_conv2d_tc_dgrad_workspace_bytes": (_Z, [_CD]),
     "rtsds_conv2d_tc_dgrad": (_I, [_CD, _P, _P, _P, _P, _I, _P, _Z, _P]),

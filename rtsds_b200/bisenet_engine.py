@@ -143,9 +143,13 @@ class BiSeNetPlan:
         n_pix = n * d.oh * d.ow
         side = self._side_branch          # convs of the side-stream branch get their own split-K workspace
 
+        if gap_out is not None:      # eval: AdaptiveAvgPool2d(1) of this layer's output leaves its epilogue as per-CTA partial means
+            gap_out["parts"] = ops.conv2d_tc_gap_parts(d)
+            gap_out["buf"] = self.buf(n, gap_out["parts"], cout, dtype=torch.float32)
+
         def launch(desc, scale, shift, res, stats):
-            if use_tc and gap_out is not None:       # eval: AdaptiveAvgPool2d(1) of this layer's output in its epilogue
-                ops.conv2d_tc_gap(desc, xp, wpk, yp, scale, shift, res, gap_out, self.ws)
+            if use_tc and gap_out is not None:
+                ops.conv2d_tc_gap(desc, xp, wpk, yp, scale, shift, res, gap_out["buf"], self.ws)
             elif use_tc:
                 ops.conv2d_tc(desc, xp, wpk, yp, scale, shift, res, stats,
                               self.ws_ds if side == 2 else (self.ws_side if side else self.ws))
@@ -223,15 +227,9 @@ class BiSeNetPlan:
         self.fused_arm = self.use_tc and not self.train
         self._gap_for = {}
         if self.fused_arm:
-            c3_, c4_ = cp.layer3[-1].bn2.num_features if not hasattr(cp.layer3[-1], "conv3") else cp.layer3[-1].bn3.num_features, \
-                cp.layer4[-1].bn2.num_features if not hasattr(cp.layer4[-1], "conv3") else cp.layer4[-1].bn3.num_features
-            # one buffer (and one memset per forward) for all three fused global pools: feature3, feature4, FFM feature
-            self.pooled_all = torch.zeros(n * (c3_ + c4_ + nc), dtype=f32, device=self.device)
-            self._keep.append(self.pooled_all)
-            self.pooled34 = self.pooled_all[:n * (c3_ + c4_)]
-            self._gap_for[id(cp.layer3[-1])] = self.pooled34[:n * c3_]
-            self._gap_for[id(cp.layer4[-1])] = self.pooled34[n * c3_:]
-            self.steps.append(lambda: self.pooled_all.zero_())
+            self._gap3, self._gap4 = {}, {}          # filled by _conv: per-CTA partial means [n][parts][c] (deterministic)
+            self._gap_for[id(cp.layer3[-1])] = self._gap3
+            self._gap_for[id(cp.layer4[-1])] = self._gap4
         for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
             for blk in layer:
                 x, shape = (self._bottleneck if hasattr(blk, "conv3") else self._basic_block)(blk, x, shape)
@@ -245,8 +243,8 @@ class BiSeNetPlan:
         c3, c4 = s3[3], s4[3]
         if 256 + c3 + c4 != ccat:
             raise ops._lib.RtsdsError(f"feature fusion module expects {ccat} input channels, context path gives 256+{c3}+{c4}")
-        pooled3 = self.pooled34[:n * c3].view(n, c3) if self.fused_arm else self.buf(n, c3, dtype=f32)
-        pooled4 = self.pooled34[n * c3:].view(n, c4) if self.fused_arm else self.buf(n, c4, dtype=f32)
+        pooled3 = self._gap3["buf"] if self.fused_arm else self.buf(n, c3, dtype=f32)
+        pooled4 = self._gap4["buf"] if self.fused_arm else self.buf(n, c4, dtype=f32)
         gate3 = self.buf(n, c3, dtype=f32)
         gate4 = self.buf(n, c4, dtype=f32)
         self.arm_saved = dict(pooled3=pooled3, pooled4=pooled4, gate3=gate3, gate4=gate4)
@@ -256,13 +254,12 @@ class BiSeNetPlan:
         sv = self.arm_saved
         tr = self.train
         dt = self.dt
-        fused_arm = self.fused_arm and c3 % 32 == 0 and c4 % 32 == 0
+        fused_arm = self.fused_arm
+        if fused_arm and (c3 % 32 or c4 % 32):
+            raise ops._lib.RtsdsError("context-path channel counts must be multiples of 32")
         if not fused_arm:
-            if self.fused_arm:      # the pools came from the conv epilogues already
-                pass
-            else:
-                self.steps.append(lambda: ops.global_avgpool(f3, n, s3[1] * s3[2], c3, c3, pooled3))
-                self.steps.append(lambda: ops.global_avgpool(f4, n, s4[1] * s4[2], c4, c4, pooled4))
+            self.steps.append(lambda: ops.global_avgpool(f3, n, s3[1] * s3[2], c3, c3, pooled3))
+            self.steps.append(lambda: ops.global_avgpool(f4, n, s4[1] * s4[2], c4, c4, pooled4))
             self.steps.append(lambda: ops.arm_gate(pooled3, arm1.conv, arm1.bn, tr, n, c3, gate3, None, sv.get("lin3"), sv.get("xhat3")))
             # cx2 = ARM2(cx2) * tail, tail = GAP(feature4) = pooled4 (build_contextpath.py:27-28)
             self.steps.append(lambda: ops.arm_gate(pooled4, arm2.conv, arm2.bn, tr, n, c4, gate4, pooled4, sv.get("lin4"), sv.get("xhat4")))
@@ -274,8 +271,8 @@ class BiSeNetPlan:
         cx2s = self.cx2_scale
         if fused_arm:
             self.steps.append(lambda: ops.arm_gate_resize(
-                ops.arm_side(f3, pooled3, arm1, s3[1], s3[2], c3, 256),
-                ops.arm_side(f4, pooled4, arm2, s4[1], s4[2], c4, 256 + c3, mul_pooled=True, out_scale=cx2s),
+                ops.arm_side(f3, pooled3, arm1, s3[1], s3[2], c3, 256, parts=self._gap3["parts"]),
+                ops.arm_side(f4, pooled4, arm2, s4[1], s4[2], c4, 256 + c3, mul_pooled=True, out_scale=cx2s, parts=self._gap4["parts"]),
                 dt, n, h8, w8, cat, ccat))
         else:
             self.steps.append(lambda: ops.gate_resize_nhwc(f4, n, s4[1], s4[2], c4, c4, gate4, h8, w8, cat, ccat, 256 + c3, dt, cx2s))
@@ -292,7 +289,8 @@ class BiSeNetPlan:
         # ---- feature fusion module + final 1x1 conv at 1/8 resolution (reference :162-167) ----
         ffm = m.feature_fusion_module
         self.feat = self.buf(n, h8, w8, 32, dtype=f32)
-        self.pooled_f = self.pooled_all[n * (c3 + c4):].view(n, nc) if self.fused_arm else self.buf(n, nc, dtype=f32)
+        self.pooled_f = self.buf(n, nc, dtype=f32)
+        self.pooled_f_parts = 1
         self.attn = self.buf(n, nc, dtype=f32)
         self.z = self.buf(n, h8, w8, 32, dtype=f32)
         from . import tapn
@@ -303,11 +301,16 @@ class BiSeNetPlan:
         # eval with the x8 head: the FFM attention, the final 1x1 conv and the resize to the NCHW logits are ONE kernel that
         # runs when the caller asks for the logits (logits()); z at 1/8 resolution is never written
         self.fused_tail = (not self.train) and final is not None
-        if not self.train and tapn.applicable(ffm.convblock.conv1):
-            if not self.fused_arm:
-                self.steps.append(lambda: pooled_f.zero_())
+        if self.fused_tail and tapn.applicable(ffm.convblock.conv1):
+            # the FFM feature's AdaptiveAvgPool2d(1) (:75) leaves the gather as one partial mean per block
+            self.pooled_f_parts = int(ops.lib().rtsds_tapn_gather_parts(n, h8, w8))
+            pooled_f = self.pooled_f = self.buf(n, self.pooled_f_parts, nc, dtype=f32)
             self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, ccat,
                             in_scale=in_scale, gap_out=pooled_f)
+        elif not self.train and tapn.applicable(ffm.convblock.conv1):
+            self._conv_tapn(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, ccat,
+                            in_scale=in_scale)
+            self.steps.append(lambda: ops.global_avgpool(feat, n, h8 * w8, nc, 32, pooled_f))
         else:
             self._conv(ffm.convblock.conv1, ffm.convblock.bn, cat, (n, h8, w8, ccat), self.feat, 32, ACT_RELU, out_dtype=F32,
                        in_scale=in_scale)
@@ -500,7 +503,7 @@ class BiSeNetPlan:
             if self.fused_tail and z is self.z:
                 ffm = self.model.feature_fusion_module
                 ops.ffm_head_resize(self.feat, 32, self.pooled_f, n, self.h8, self.w8, self.nc, ffm.conv1, ffm.conv2, self.model.conv,
-                                    out, self.attn)
+                                    out, self.attn, self.pooled_f_parts)
                 return out
         else:
             out = torch.empty((n, self.nc, self.h8, self.w8), dtype=torch.float32, device=self.device)

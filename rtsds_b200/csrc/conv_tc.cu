@@ -159,7 +159,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
             const float s1 = warp_transpose_sum(t, lane);
-            atomicAdd(&s_stats[c0 + lane], s1);
+            s_stats[(threadIdx.x >> 5 & 3) * BLOCK_N + c0 + lane] += s1;      // this warp's own slot: fixed summation order
         }
         if (valid) {
             if (out16) {
@@ -208,8 +208,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint8_t* smem_b = smem + static_cast<size_t>(stages) * TC_A_BYTES;
     float* s_scale = reinterpret_cast<float*>(smem_b + static_cast<size_t>(stages) * B_BYTES);
     float* s_shift = s_scale + BLOCK_N;
-    float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 2 * BLOCK_N);
+    float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N] BatchNorm sums, or [4 warps][BLOCK_N] fused-pool slots
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 4 * BLOCK_N);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* tmem_full_bar = empty_bar + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -247,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         ptx::tmem_relinquish();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
+        for (int i = threadIdx.x - 64; i < 4 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -372,10 +372,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
         }
         if (p.gap_out && p.split_k == 1) {
+            // this CTA's partial of the fused pool: [image][tile of the image][cout], summed by the consumer in tile order
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                 const int co = n0 + i;
-                if (co < p.cout) atomicAdd(&p.gap_out[static_cast<long long>(img) * p.cout + co], s_stats[i] * p.gap_scale);
+                if (co < p.cout)
+                    p.gap_out[(static_cast<long long>(img) * tiles_per_img + trem) * p.cout + co] =
+                        ((s_stats[i] + s_stats[BLOCK_N + i]) + (s_stats[2 * BLOCK_N + i] + s_stats[3 * BLOCK_N + i])) * p.gap_scale;
             }
         }
     }
@@ -423,11 +426,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     }
                 }
             }
-            if (p.gap_out) {
+            if (p.gap_out) {        // partial index: (tile of the image, cluster rank) — every rank reduced its own rows
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int rank_ = static_cast<int>(ptx::cluster_ctarank());
                 for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
-                    if (co < p.cout) atomicAdd(&p.gap_out[static_cast<long long>(img) * p.cout + co], s_stats[i] * p.gap_scale);
+                    if (co < p.cout)
+                        p.gap_out[((static_cast<long long>(img) * tiles_per_img + trem) * p.split_k + rank_) * p.cout + co] =
+                            ((s_stats[i] + s_stats[BLOCK_N + i]) + (s_stats[2 * BLOCK_N + i] + s_stats[3 * BLOCK_N + i])) * p.gap_scale;
                 }
             }
         }
@@ -732,7 +738,7 @@ splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_t
                 o = apply_act(o, p.act, p.slope);
                 reinterpret_cast<float*>(p.y)[out_off + c] = o;
             }
-            if (p.gap_out) atomicAdd(&p.gap_out[static_cast<long long>(img) * cout + c], o * p.gap_scale);   // rare path
+            (void)img;
         }
     }
     if (p.stats) {
@@ -819,7 +825,7 @@ static void pick_tile(int oh, int ow, int* tw, int* th) {
 }
 
 static size_t tc_smem_bytes(int block_n, int stages) {
-    return 1024 + static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) + 4 * block_n * 4 +
+    return 1024 + static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) + 6 * block_n * 4 +
            (2 * stages + 1) * 8 + 16;
 }
 
@@ -927,6 +933,7 @@ static void tp_plan(const TapProblem& t, int* block_n, int* split, int* tile_w, 
     if (sp > kb_total) sp = kb_total;
     if (sp > 16) sp = 16;
     if (sp < 1) sp = 1;
+    if (t.gap_out) sp = sp >= 4 ? 4 : (sp >= 2 ? 2 : 1);      // the fused pool rides on the in-cluster split-K reduction
     *split = sp;
 }
 
@@ -1042,6 +1049,10 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
         while (static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) < need) ++stages;
         if (tc_smem_bytes(block_n, stages) <= 227 * 1024) p.cluster_reduce = 1;
     }
+    if (t.gap_out && split > 1 && !p.cluster_reduce) {
+        set_error("conv_tc: the fused global pool needs split_k 1, 2 or 4 (thread-block-cluster reduction); got %d", split);
+        return RTSDS_EUNSUP;
+    }
     p.stages = stages;
     RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv_tc: too many tiles");
 
@@ -1132,9 +1143,22 @@ extern "C" int rtsds_conv2d_tc_fwd(const RtsdsConvDesc* d, const void* x, const 
     return tp_run(t, workspace, ws_bytes, as_stream(s));
 }
 
-// Same, with the global average pool of the layer's OUTPUT fused into the epilogue: gap_out fp32 [n, cout] (zeroed by the
-// caller) receives mean over oh*ow of the final (post-activation) values — AdaptiveAvgPool2d(1) of build_bisenet.py:46 and
-// the context-path tail of build_contextpath.py:27-28 without a separate pass over feature3 / feature4.
+// Same, with the global average pool of the layer's OUTPUT fused into the epilogue — AdaptiveAvgPool2d(1) of
+// build_bisenet.py:46 and the context-path tail of build_contextpath.py:27-28 without a separate pass over feature3 /
+// feature4.  DETERMINISTIC: every CTA writes the (pre-scaled) partial sum of its own rows to
+// gap_out[image][part][cout], parts = rtsds_conv2d_tc_gap_parts(d); the consumer adds the parts in index order
+// (mean = sum over parts).  No atomics, nothing to zero.
+extern "C" int rtsds_conv2d_tc_gap_parts(const RtsdsConvDesc* d) {
+    if (!d) return 0;
+    TapProblem t;
+    if (fwd_problem(d, nullptr, nullptr, TC_BLOCK_K, 2, &t) != RTSDS_OK) return 0;
+    float dummy;
+    t.gap_out = &dummy;
+    int bn, sp, tw, th;
+    tp_plan(t, &bn, &sp, &tw, &th);
+    return static_cast<int>(cdiv(t.ow, tw) * cdiv(t.oh, th)) * sp;
+}
+
 extern "C" int rtsds_conv2d_tc_fwd_gap(const RtsdsConvDesc* d, const void* x, const void* w, const float* scale,
                                        const float* shift, const void* residual, void* y, float* gap_out,
                                        void* workspace, size_t ws_bytes, rtsds_stream_t s) {

@@ -379,12 +379,13 @@ ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ poo
 // 16-byte stores into the concat buffer slot.  Replaces arm_gate x2 + gate_resize x2 (4 launches, ~26 us at b=1).
 struct ArmSide {
     const void* src; const float* pooled; const float* w; const float* b; const float* gamma; const float* beta;
-    const float* mean; const float* var; float eps, out_scale; int h, w_, c, coff, mul_pooled;
+    const float* mean; const float* var; float eps, out_scale; int h, w_, c, coff, mul_pooled, parts;
 };
 template <typename T>
 __global__ void __launch_bounds__(256)
 arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, int oh, int ow, T* __restrict__ dst, int dst_ld) {
     __shared__ float s_gate[32];
+    extern __shared__ float s_pool[];                                     // [c]: pooled vector of the current image
     const bool second = static_cast<int>(blockIdx.x) >= blocks0;
     const ArmSide& a = second ? a1 : a0;
     const int local = second ? blockIdx.x - blocks0 : blockIdx.x;
@@ -396,7 +397,15 @@ arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, i
     const float rh = static_cast<float>(a.h) / static_cast<float>(oh), rw = static_cast<float>(a.w_) / static_cast<float>(ow);
     const T* src = reinterpret_cast<const T*>(a.src);
     for (int img = 0; img < n; ++img) {
-        const float* pp = a.pooled + static_cast<long long>(img) * a.c;
+        // pooled[n][parts][c]: per-CTA partial means of the producing conv's epilogue, added in part order (deterministic)
+        for (int ch = threadIdx.x; ch < a.c; ch += 256) {
+            const float* pq = a.pooled + static_cast<long long>(img) * a.parts * a.c + ch;
+            float acc = 0.f;
+            for (int q = 0; q < a.parts; ++q) acc += pq[static_cast<long long>(q) * a.c];
+            s_pool[ch] = acc;
+        }
+        __syncthreads();
+        const float* pp = s_pool;
         for (int k = 0; k < 4; ++k) {
             const int co = cg * 32 + warp * 4 + k;
             const float* wr = a.w + static_cast<long long>(co) * a.c;
@@ -444,12 +453,22 @@ __global__ void __launch_bounds__(FHR_THREADS)
 ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __restrict__ pooled, int h, int w, int c,
                        const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                        const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
-                       float* attn_out, int oh, int ow, float rh, float rw, int max_rows, float* __restrict__ out) {
+                       float* attn_out, int oh, int ow, float rh, float rw, int max_rows, int parts, float* __restrict__ out) {
     extern __shared__ float s_z[];                                        // [rows][w][c]
-    __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C], s_b[FFM_MAX_C];
+    __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C], s_b[FFM_MAX_C], s_p[8][FFM_MAX_C], s_pool[FFM_MAX_C];
     __shared__ float s_w[FFM_MAX_C * FFM_MAX_C];
     const int img = blockIdx.y, t = threadIdx.x;
-    const float* pp = pooled + static_cast<long long>(img) * c;
+    {   // pooled[n][parts][c]: partial means of the producer (one per block of the gather), added in a fixed order
+        const int ch = t & 31, stripe = t >> 5;
+        float acc = 0.f;
+        if (ch < c)
+            for (int q = stripe; q < parts; q += 8) acc += pooled[(static_cast<long long>(img) * parts + q) * c + ch];
+        s_p[stripe][ch] = acc;
+        __syncthreads();
+        if (t < c) s_pool[t] = ((s_p[0][t] + s_p[1][t]) + (s_p[2][t] + s_p[3][t])) + ((s_p[4][t] + s_p[5][t]) + (s_p[6][t] + s_p[7][t]));
+        __syncthreads();
+    }
+    const float* pp = s_pool;
     if (t < c) {
         float acc = b1[t];
         for (int k = 0; k < c; ++k) acc = fmaf(w1[t * c + k], pp[k], acc);
@@ -790,8 +809,9 @@ extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide*
         RTSDS_REQUIRE(a.src && a.pooled && a.w && a.gamma && a.beta && a.running_mean && a.running_var, "arm_gate_resize: NULL pointer");
         RTSDS_REQUIRE(a.c > 0 && a.c % 32 == 0 && a.h > 0 && a.w_in > 0 && a.dst_coff % 8 == 0 && a.dst_coff + a.c <= dst_ld,
                       "arm_gate_resize: channels must be a multiple of 32 and fit the destination slot");
+        RTSDS_REQUIRE(a.pooled_parts >= 1, "arm_gate_resize: pooled_parts must be >= 1");
         k[i] = ArmSide{a.src, a.pooled, a.w, a.b, a.gamma, a.beta, a.running_mean, a.running_var, a.eps, a.out_scale,
-                       a.h, a.w_in, a.c, a.dst_coff, a.mul_pooled};
+                       a.h, a.w_in, a.c, a.dst_coff, a.mul_pooled, a.pooled_parts};
     }
     RTSDS_REQUIRE(dst_ld % 8 == 0, "arm_gate_resize: dst_ld must be a multiple of 8");
     const int groups = a3->c / 32 + a4->c / 32;
@@ -800,12 +820,14 @@ extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide*
     if (chunks > npix / 64) chunks = npix / 64 > 0 ? npix / 64 : 1;
     const int blocks0 = (a3->c / 32) * chunks, blocks = groups * chunks;
     cudaStream_t st = as_stream(s);
+    const size_t sm = sizeof(float) * static_cast<size_t>(a3->c > a4->c ? a3->c : a4->c);
+    RTSDS_REQUIRE(sm <= 40 * 1024, "arm_gate_resize: too many channels");
     if (dtype == RTSDS_F16)
-        arm_gate_resize_kernel<__half><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld);
+        arm_gate_resize_kernel<__half><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld);
     else if (dtype == RTSDS_BF16)
-        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld);
+        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld);
     else if (dtype == RTSDS_F32)
-        arm_gate_resize_kernel<float><<<blocks, 256, 0, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld);
+        arm_gate_resize_kernel<float><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld);
     else { set_error("arm_gate_resize: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
     return check_launch("arm_gate_resize_kernel");
@@ -813,8 +835,9 @@ extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide*
 
 extern "C" int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pooled, int n, int h, int w, int c, const float* w1,
                                      const float* b1, const float* w2, const float* b2, const float* wc, const float* bc,
-                                     float* attn_out, int oh, int ow, float* out, rtsds_stream_t s) {
-    RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && wc && out && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "ffm_head_resize: bad argument");
+                                     float* attn_out, int pooled_parts, int oh, int ow, float* out, rtsds_stream_t s) {
+    RTSDS_REQUIRE(f && pooled && w1 && b1 && w2 && b2 && wc && out && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && pooled_parts >= 1,
+                  "ffm_head_resize: bad argument");
     RTSDS_REQUIRE(c > 0 && c <= FFM_MAX_C && f_ld >= FFM_MAX_C && f_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0,
                   "ffm_head_resize: c <= %d, feature pitch >= %d floats and 16-byte aligned", FFM_MAX_C, FFM_MAX_C);
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
@@ -825,7 +848,7 @@ extern "C" int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pool
     if (!done) { cudaFuncSetAttribute(ffm_head_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; }
     dim3 grid(static_cast<unsigned>(cdiv(oh, FHR_ROWS)), n);
     ffm_head_resize_kernel<<<grid, FHR_THREADS, smem, as_stream(s)>>>(f, f_ld, pooled, h, w, c, w1, b1, w2, b2, wc, bc, attn_out, oh, ow,
-                                                                      rh, rw, max_rows, out);
+                                                                      rh, rw, max_rows, pooled_parts, out);
     count_launch();
     return check_launch("ffm_head_resize_kernel");
 }

@@ -107,7 +107,8 @@ tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int 
             float a = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) a += s_stats[0][i][lane];
-            atomicAdd(&gap_out[static_cast<long long>(blockIdx.y) * c + lane], a * gap_scale);
+            // one partial mean per block, written (not accumulated): the consumer adds them in block order — deterministic
+            gap_out[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * c + lane] = a * gap_scale;
         }
         __syncthreads();
     }
@@ -185,16 +186,23 @@ extern "C" int rtsds_tapn_weight_grad(const float* dw2, int c, int cin, int k, f
     return check_launch("tapn_weight_grad_kernel");
 }
 
+// blocks per image; with the fused pool one block = one partial, so the grid is kept to about one wave
+static long long tapn_gather_blocks(int n, int h, int w, bool gap) {
+    const long long npix = static_cast<long long>(h) * w;
+    long long g = cdiv(npix, 8 * 4);
+    const long long cap = cdiv((gap ? 1LL : 8LL) * num_sms(), n);
+    if (g > cap) g = cap;
+    return g < 1 ? 1 : g;
+}
+extern "C" int rtsds_tapn_gather_parts(int n, int h, int w) { return static_cast<int>(tapn_gather_blocks(n, h, w, true)); }
+
 extern "C" int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int w, int c, int k, int pad, int dil,
                                  const float* scale, const float* shift, int act, float* stats, float* y, int y_ld,
                                  float* gap_out, rtsds_stream_t s) {
     RTSDS_REQUIRE(t_buf && y && n > 0 && h > 0 && w > 0 && c > 0 && c <= 32 && k > 0 && t_ld >= k * k * c && y_ld >= c, "tapn_gather: bad argument");
     RTSDS_REQUIRE(n <= 65535, "tapn_gather: batch too large");
     const long long npix = static_cast<long long>(h) * w;
-    long long g = cdiv(npix, 8 * 4);
-    const long long cap = cdiv(8LL * num_sms(), n);
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
+    const long long g = tapn_gather_blocks(n, h, w, gap_out != nullptr);
     const dim3 grid(static_cast<unsigned>(g), static_cast<unsigned>(n));
     const float gsc = 1.0f / static_cast<float>(npix);
     if (k == 3)

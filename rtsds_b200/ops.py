@@ -328,13 +328,18 @@ def ffm_head(f, f_dtype, f_ld, pooled, n, hw, c, conv1, conv2, final_conv, z, z_
 
 
 def conv2d_tc_gap(d: ConvDesc, x, w, y, scale, shift, residual, gap_out, workspace=None) -> None:
-    """conv2d_tc with AdaptiveAvgPool2d(1) of its output fused into the epilogue: gap_out fp32 [n,cout] += mean (caller zeroes)."""
+    """conv2d_tc with AdaptiveAvgPool2d(1) of its output fused into the epilogue: gap_out fp32 [n, gap_parts(d), cout] receives
+    one partial mean per CTA (deterministic; the consumer adds the parts in order)."""
     ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     check(lib().rtsds_conv2d_tc_fwd_gap(C.byref(d), _p(x), _p(w), _p(scale), _p(shift), _p(residual), _p(y), _p(gap_out),
                                         _p(workspace), ws_bytes, _s()), "conv2d_tc_fwd_gap")
 
 
-def arm_side(src, pooled, arm, h, w, c, dst_coff, mul_pooled=False, out_scale=1.0):
+def conv2d_tc_gap_parts(d: ConvDesc) -> int:
+    return int(lib().rtsds_conv2d_tc_gap_parts(C.byref(d)))
+
+
+def arm_side(src, pooled, arm, h, w, c, dst_coff, mul_pooled=False, out_scale=1.0, parts=1):
     """RtsdsArmSide of one AttentionRefinementModule in eval mode (folded BatchNorm from the running statistics)."""
     a = _lib.ArmSide()
     bn, conv = arm.bn, arm.conv
@@ -343,7 +348,7 @@ def arm_side(src, pooled, arm, h, w, c, dst_coff, mul_pooled=False, out_scale=1.
     a.gamma, a.beta = _p(bn.weight.detach()), _p(bn.bias.detach())
     a.running_mean, a.running_var = _p(bn.running_mean), _p(bn.running_var)
     a.eps, a.out_scale = float(bn.eps), float(out_scale)
-    a.h, a.w_in, a.c, a.dst_coff, a.mul_pooled = h, w, c, dst_coff, int(mul_pooled)
+    a.h, a.w_in, a.c, a.dst_coff, a.mul_pooled, a.pooled_parts = h, w, c, dst_coff, int(mul_pooled), int(parts)
     return a
 
 
@@ -351,13 +356,14 @@ def arm_gate_resize(side3, side4, dtype, n, oh, ow, dst, dst_ld) -> None:
     check(lib().rtsds_arm_gate_resize(C.byref(side3), C.byref(side4), dtype, n, oh, ow, _p(dst), dst_ld, _s()), "arm_gate_resize")
 
 
-def ffm_head_resize(f, f_ld, pooled, n, h, w, c, conv1, conv2, final_conv, out, attn_out=None) -> None:
-    """FFM attention + final 1x1 conv + bilinear resize to `out` (fp32 NCHW [n,c,oh,ow]) in one kernel."""
+def ffm_head_resize(f, f_ld, pooled, n, h, w, c, conv1, conv2, final_conv, out, attn_out=None, parts=1) -> None:
+    """FFM attention + final 1x1 conv + bilinear resize to `out` (fp32 NCHW [n,c,oh,ow]) in one kernel; pooled fp32
+    [n, parts, c] partial means of f."""
     oh, ow = out.shape[-2:]
     bc = final_conv.bias.detach() if final_conv.bias is not None else None
     check(lib().rtsds_ffm_head_resize(_p(f), f_ld, _p(pooled), n, h, w, c, _p(conv1.weight.detach()), _p(conv1.bias.detach()),
                                       _p(conv2.weight.detach()), _p(conv2.bias.detach()), _p(final_conv.weight.detach()), _p(bc),
-                                      _p(attn_out), oh, ow, _p(out), _s()), "ffm_head_resize")
+                                      _p(attn_out), int(parts), oh, ow, _p(out), _s()), "ffm_head_resize")
 
 
 def resize_to_nchw(z, n, h, w, c, z_ld, out) -> None:

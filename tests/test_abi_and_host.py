@@ -90,7 +90,7 @@ def test_bisenet_parameter_tree_matches_reference_contract():
 def test_plan_launch_sequence_dry_run(monkeypatch):
     """RTSDS_DRYRUN records launches without a GPU: 22 tensor-core convs (2 of them with the ARM global pool fused into the
     epilogue), 1 fused stem pair, ONE kernel for both ARM gates + gated resizes, ONE for FFM attention + final conv + x8
-    resize ... per eval forward: 27 launches of this library (34 in round 1) + one memset."""
+    resize ... per eval forward: 27 launches of this library (34 in round 1), no memset, no atomics."""
     monkeypatch.setenv("RTSDS_DRYRUN", "1")
     from models.bisenet.build_bisenet import BiSeNet
     from rtsds_b200 import _lib
@@ -108,7 +108,7 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     assert c["rtsds_bn_fold"] == 24
     forward_calls = [k for k in _lib.lib().calls if not k.startswith(("rtsds_pack", "rtsds_bn_fold", "rtsds_stem_pack", "rtsds_tapn_weights",
                                                                       "rtsds_conv_cout_pad", "rtsds_conv2d_tc_workspace", "rtsds_check",
-                                                                      "rtsds_scale_packed", "rtsds_launch_count"))]
+                                                                      "rtsds_scale_packed", "rtsds_launch_count", "rtsds_conv2d_tc_gap_parts", "rtsds_tapn_gather_parts"))]
     assert len(forward_calls) == 27, (len(forward_calls), collections.Counter(forward_calls))
     _lib.lib().calls.clear()
     m(torch.zeros(1, 3, 512, 1024))                 # weights unchanged: no repack on the second call
