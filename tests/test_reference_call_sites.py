@@ -129,3 +129,36 @@ def test_reference_adversarial_loop_2_runs_on_the_drop_in_modules(ref_loops, mon
     assert calls.count("rtsds_disc_cls_fwd") >= 3          # one D forward for the generator loss, two for D's own step
     assert calls.count("rtsds_conv2d_tc_wgrad") >= 20      # the generator's backward ran through the hand-written path
     assert all(p.requires_grad for p in dis.parameters())
+
+
+def test_loop_restatements_used_on_the_gpu_box_follow_the_real_loops(ref_loops):
+    """tests/ref_loop_stubs.py (what the -m gpu tests run, because /root/reference does not exist on the GPU box) against the
+    REAL train.py:train / validation.py:val: identical sequence of library calls and identical callback invocations."""
+    train_mod, val_mod = ref_loops
+    import ref_loop_stubs
+    from models.bisenet.build_bisenet import BiSeNet
+    from rtsds_b200 import _lib
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            if name.startswith("on_"):
+                return lambda *a, **k: self.calls.append((name, a[0] if a and isinstance(a[0], int) else None,
+                                                          sorted(a[1].keys()) if len(a) > 1 and isinstance(a[1], dict) else None))
+            raise AttributeError(name)
+
+    seqs = []
+    for train_fn, val_fn in ((train_mod.train, val_mod.val), (ref_loop_stubs.train, ref_loop_stubs.val)):
+        torch.manual_seed(0)
+        model = BiSeNet(19, "resnet18")
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        rec = Rec()
+        _lib.lib().calls.clear()
+        train_fn(0, model, _batches(2, 2, 64, 96), torch.nn.CrossEntropyLoss(ignore_index=19), opt, 1e-4, 100, 0.9, 1, "cpu", [rec])
+        val_fn(0, model, _batches(2, 1, 64, 96), 19, "cpu", [rec])
+        seqs.append((list(_lib.lib().calls), rec.calls, opt.param_groups[0]["lr"]))
+    assert seqs[0][0] == seqs[1][0]            # kernel-launch sequence
+    assert seqs[0][1] == seqs[1][1]            # callback names, batch indices, dict keys
+    assert seqs[0][2] == seqs[1][2]            # poly LR applied identically
