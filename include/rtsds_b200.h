@@ -100,6 +100,11 @@ int rtsds_image_u8_to_f32(const uint8_t* src, int n, int c, int h, int w, int oh
                           const float* bias3, float* dst, rtsds_stream_t s);
 int rtsds_label_resize_clamp(const void* src, int src_is_u8, int n, int h, int w, int oh, int ow, int clamp,
                              int64_t lo, int64_t hi, int64_t* dst, rtsds_stream_t s);
+/* F.adaptive_avg_pool2d on NCHW fp32 (train.py:410,438,445: adversarial_train_2 pools the generator's logits to the target
+ * label size before softmax -> discriminator); planes = n*c.  Windows as ATen: [floor(o*in/out), ceil((o+1)*in/out)).
+ * bwd: dx[i] = sum over the windows containing i of dy / area (gather form, deterministic). */
+int rtsds_adaptive_avgpool_nchw_fwd(const float* x, int64_t planes, int h, int w, int oh, int ow, float* y, rtsds_stream_t s);
+int rtsds_adaptive_avgpool_nchw_bwd(const float* dy, int64_t planes, int h, int w, int oh, int ow, float* dx, rtsds_stream_t s);
 int rtsds_stem_pair_tc_fwd_u8(const uint8_t* x, const float* in_scale3, const float* in_bias3, int n, int h, int w,
                               const void* wpk, const float* scale, const float* shift, int relu, int dtype,
                               void* y_cp, void* y_sp, rtsds_stream_t s);

@@ -83,6 +83,8 @@ SIGNATURES = {
     "rtsds_confusion_hist": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "rtsds_argmax_hist": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
     "rtsds_argmax_hist_u8": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
+    "rtsds_adaptive_avgpool_nchw_fwd": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
+    "rtsds_adaptive_avgpool_nchw_bwd": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "rtsds_image_u8_to_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rtsds_label_resize_clamp": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
     "rtsds_stem_pair_tc_fwd_u8": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -145,3 +145,74 @@ extern "C" int rtsds_label_resize_clamp(const void* src, int src_is_u8, int n, i
     count_launch();
     return check_launch("label_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// F.adaptive_avg_pool2d on NCHW fp32 logits (train.py:410,438,445, adversarial_train_2: the generator's prediction is
+// pooled to the target label size before softmax -> discriminator).  Window of output o along an axis:
+// [floor(o*in/out), ceil((o+1)*in/out)) — ATen's start_index / end_index.  Backward: every input pixel collects dy/area
+// from the (at most two per axis) windows that contain it — a gather, no atomics, deterministic.
+namespace rtsds {
+__device__ __forceinline__ int ap_start(int o, int in, int out) { return static_cast<int>((static_cast<long long>(o) * in) / out); }
+__device__ __forceinline__ int ap_end(int o, int in, int out) { return static_cast<int>((static_cast<long long>(o + 1) * in + out - 1) / out); }
+
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_fwd_kernel(const float* __restrict__ x, long long planes, int h, int w, int oh, int ow, float* __restrict__ y) {
+    const long long total = planes * oh * ow;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % ow);
+        const long long r = i / ow;
+        const int oy = static_cast<int>(r % oh);
+        const float* p = x + (r / oh) * h * w;
+        const int y0 = ap_start(oy, h, oh), y1 = ap_end(oy, h, oh), x0 = ap_start(ox, w, ow), x1 = ap_end(ox, w, ow);
+        float acc = 0.f;
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) acc += p[static_cast<long long>(yy) * w + xx];
+        y[i] = acc / static_cast<float>((y1 - y0) * (x1 - x0));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_bwd_kernel(const float* __restrict__ dy, long long planes, int h, int w, int oh, int ow, float* __restrict__ dx) {
+    const long long total = planes * h * w;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ix = static_cast<int>(i % w);
+        const long long r = i / w;
+        const int iy = static_cast<int>(r % h);
+        const float* g = dy + (r / h) * oh * ow;
+        // candidate outputs: around floor(i*out/in); a window never extends more than one output index away
+        const int cy = static_cast<int>((static_cast<long long>(iy) * oh) / h), cx = static_cast<int>((static_cast<long long>(ix) * ow) / w);
+        float acc = 0.f;
+        for (int oy = max(cy - 1, 0); oy <= min(cy + 1, oh - 1); ++oy) {
+            const int y0 = ap_start(oy, h, oh), y1 = ap_end(oy, h, oh);
+            if (iy < y0 || iy >= y1) continue;
+            for (int ox = max(cx - 1, 0); ox <= min(cx + 1, ow - 1); ++ox) {
+                const int x0 = ap_start(ox, w, ow), x1 = ap_end(ox, w, ow);
+                if (ix < x0 || ix >= x1) continue;
+                acc += g[static_cast<long long>(oy) * ow + ox] / static_cast<float>((y1 - y0) * (x1 - x0));
+            }
+        }
+        dx[i] = acc;
+    }
+}
+}  // namespace rtsds
+
+extern "C" int rtsds_adaptive_avgpool_nchw_fwd(const float* x, int64_t planes, int h, int w, int oh, int ow, float* y, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && y && planes > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "adaptive_avgpool_fwd: bad argument");
+    const long long total = planes * oh * ow;
+    const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
+    adaptive_avgpool_fwd_kernel<<<grid, 256, 0, as_stream(s)>>>(x, planes, h, w, oh, ow, y);
+    count_launch();
+    return check_launch("adaptive_avgpool_fwd_kernel");
+}
+
+extern "C" int rtsds_adaptive_avgpool_nchw_bwd(const float* dy, int64_t planes, int h, int w, int oh, int ow, float* dx, rtsds_stream_t s) {
+    RTSDS_REQUIRE(dy && dx && planes > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "adaptive_avgpool_bwd: bad argument");
+    RTSDS_REQUIRE(oh <= 2 * h && ow <= 2 * w, "adaptive_avgpool_bwd: up-sampling by more than 2x is not supported");
+    const long long total = planes * h * w;
+    const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
+    adaptive_avgpool_bwd_kernel<<<grid, 256, 0, as_stream(s)>>>(dy, planes, h, w, oh, ow, dx);
+    count_launch();
+    return check_launch("adaptive_avgpool_bwd_kernel");
+}

@@ -429,3 +429,31 @@ def stem_s2d_conv_fwd(P, n, oh, ow, wpk, cout, y, out_ld, out_dtype, scale=None,
 
 def stem_s2d_conv_wgrad(P, n, oh, ow, dy, dy_ld, cout, dw_packed) -> None:
     check(lib().rtsds_stem_s2d_conv_wgrad(_p(P), n, oh, ow, _p(dy), dy_ld, cout, _p(dw_packed), _s()), "stem_s2d_conv_wgrad")
+
+
+# ----------------------------------------------------------------------------- adaptive average pool
+class _AdaptiveAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+        check(lib().rtsds_adaptive_avgpool_nchw_fwd(_p(x), n * c, h, w, oh, ow, _p(y), _s()), "adaptive_avgpool_fwd")
+        ctx.shape = (n, c, h, w, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow = ctx.shape
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        check(lib().rtsds_adaptive_avgpool_nchw_bwd(_p(dy.contiguous()), n * c, h, w, oh, ow, _p(dx), _s()), "adaptive_avgpool_bwd")
+        return dx, None, None
+
+
+def adaptive_avg_pool2d(x: torch.Tensor, output_size) -> torch.Tensor:
+    """F.adaptive_avg_pool2d(x, output_size) for fp32 NCHW CUDA tensors (train.py:410,438,445), differentiable."""
+    _cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise TypeError("adaptive_avg_pool2d: fp32 [N,C,H,W] expected")
+    oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
+    return _AdaptiveAvgPool.apply(x, int(oh), int(ow))

@@ -467,3 +467,20 @@ def test_resize_to_nchw_backward(cuda, n, c, h, w, oh, ow):
     torch.cuda.synchronize()
     got = dz[..., :c].permute(0, 3, 1, 2).cpu()
     assert rel_err(got, z.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape,out", [((2, 19, 720, 1280), (512, 1024)), ((1, 19, 96, 130), (64, 96)), ((2, 5, 37, 53), (37, 53)),
+                                       ((1, 3, 40, 60), (64, 96))])
+def test_adaptive_avg_pool2d_matches_torch(cuda, shape, out):
+    """train.py:410,438,445 (adversarial_train_2): F.adaptive_avg_pool2d of the logits, forward and backward."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*shape, generator=g)
+    dy = torch.randn(shape[0], shape[1], *out, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.adaptive_avg_pool2d(xr, out)
+    yr.backward(dy)
+    xg = x.cuda().requires_grad_(True)
+    yg = ops.adaptive_avg_pool2d(xg, out)
+    yg.backward(dy.cuda())
+    assert (yg.cpu() - yr).abs().max().item() <= 1e-6 * max(1.0, yr.abs().max().item())
+    assert (xg.grad.cpu() - xr.grad).abs().max().item() <= 1e-6 * max(1.0, xr.grad.abs().max().item())

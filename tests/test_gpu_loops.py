@@ -90,13 +90,18 @@ def test_sync_free_train_loop_matches_the_reference_loop_body(cuda, precision, m
         res.append(rec.calls)
     slow, fast = res
     assert [c[0] for c in slow] == [c[0] for c in fast]                     # same callbacks, same order, same count
-    tol = 1e-5 if precision == "fp32" else 2e-2                               # bf16: fused CE vs materialised logits round differently
-    worst = 0.0
+    # the two loops take different kernels to the same numbers (fused resize+CE vs materialised logits + torch CE, fused vs
+    # torch Adam): the FIRST batch agrees to round-off; after that four optimizer steps of a train-mode net with 2-sample ARM
+    # statistics amplify the last-bit differences (1e-3 in fp32 after four steps, see tests/test_gpu_config1.py)
+    tol_first, tol = (1e-5, 5e-3) if precision == "fp32" else (2e-3, 2e-2)
+    worst, first = 0.0, None
     for (n1, a1, _), (n2, a2, _) in zip(slow, fast):
         if n1 in ("on_batch_end", "on_epoch_end"):
             assert a1[0] == a2[0] and a1[1].keys() == a2[1].keys()
-            for k in a1[1]:
-                worst = max(worst, abs(a1[1][k] - a2[1][k]) / max(abs(a1[1][k]), 1e-9))
+            e = max(abs(a1[1][k] - a2[1][k]) / max(abs(a1[1][k]), 1e-9) for k in a1[1])
+            first = e if first is None else first
+            worst = max(worst, e)
+    assert first <= tol_first, first
     record(f"loops/sync_free_train_vs_reference_body/{precision}", worst_rel_diff=worst, item_calls_reference=items[0], item_calls_sync_free=items[1])
     assert worst <= tol, worst
     assert items[0] >= 3 * len(data) and items[1] == 0                       # the reference body syncs 3x per batch, the fast loop never
