@@ -1044,7 +1044,9 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     // split-K of 2 or 4: the slices of a tile run as one thread-block cluster and reduce through distributed shared memory
     static int cluster_mode = -1;
     if (cluster_mode < 0) { const char* e = getenv("RTSDS_NO_CLUSTER_SPLITK"); cluster_mode = (e && e[0] == '1') ? 0 : 1; }
-    if (cluster_mode && (split == 2 || split == 4) && block_n >= 32) {
+    // (split 8: 16 rows per rank — a warp of the reduction then spans two 32-column chunks, which the per-warp BatchNorm /
+    // pool sums do not allow; plain epilogues only)
+    if (cluster_mode && (split == 2 || split == 4 || (split == 8 && !t.stats && !t.gap_out)) && block_n >= 32) {
         const size_t need = static_cast<size_t>(TC_BLOCK_M) * (block_n + 4) * sizeof(float);     // partial tile overlays the ring
         while (static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) < need) ++stages;
         if (tc_smem_bytes(block_n, stages) <= 227 * 1024) p.cluster_reduce = 1;

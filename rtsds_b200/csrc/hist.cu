@@ -106,19 +106,31 @@ argmax_hist_kernel(const float* __restrict__ logits, const long long* __restrict
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { best[v] = -INFINITY; arg[v] = 0; }
         const bool full = (p0 + VEC <= hw);
-        for (int c = 0; c < n_cls; ++c) {
-            float x[VEC];
-            if (VEC == 4 && full) {
-                float4 t = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
-                x[0] = t.x; x[1 % VEC] = t.y; x[2 % VEC] = t.z; x[3 % VEC] = t.w;
-            } else {
+        // The class planes are hw floats apart: the loads of one pixel group are independent, so they are issued eight
+        // planes at a time BEFORE the compare chain consumes them (one load per iteration of a runtime-bound loop left a
+        // single 16-byte request in flight per thread: 2.3 TB/s; eight in flight: the DRAM pipe is the limit).
+        for (int c0 = 0; c0 < n_cls; c0 += 8) {
+            float x[8][VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) x[v] = (p0 + v < hw) ? base[c * hw + v] : -INFINITY;
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k;
+                if (VEC == 4 && full) {
+                    float4 t = c < n_cls ? __ldcs(reinterpret_cast<const float4*>(base + c * hw)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    x[k][0] = t.x; x[k][1 % VEC] = t.y; x[k][2 % VEC] = t.z; x[k][3 % VEC] = t.w;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) x[k][v] = (c < n_cls && p0 + v < hw) ? base[c * hw + v] : -INFINITY;
+                }
             }
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                // first maximum wins (torch.argmax); NaN is treated as maximal like torch
-                if (x[v] > best[v] || (x[v] != x[v] && best[v] == best[v])) { best[v] = x[v]; arg[v] = c; }
+            for (int k = 0; k < 8; ++k) {
+                if (c0 + k < n_cls) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        // first maximum wins (torch.argmax); NaN is treated as maximal like torch
+                        if (x[k][v] > best[v] || (x[k][v] != x[k][v] && best[v] == best[v])) { best[v] = x[k][v]; arg[v] = c0 + k; }
+                    }
+                }
             }
         }
         if (pred_u8) {                          // class map as one byte per pixel (n_cls <= 256): 8x fewer bytes back to the host

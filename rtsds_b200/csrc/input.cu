@@ -181,13 +181,15 @@ adaptive_avgpool_bwd_kernel(const float* __restrict__ dy, long long planes, int 
         const long long r = i / w;
         const int iy = static_cast<int>(r % h);
         const float* g = dy + (r / h) * oh * ow;
-        // candidate outputs: around floor(i*out/in); a window never extends more than one output index away
-        const int cy = static_cast<int>((static_cast<long long>(iy) * oh) / h), cx = static_cast<int>((static_cast<long long>(ix) * ow) / w);
+        // candidate outputs: every o whose window [floor(o*in/out), ceil((o+1)*in/out)) can contain i lies in
+        // [floor(i*out/in) - 1, floor((i+1)*out/in) + 1]
+        const int cy0 = static_cast<int>((static_cast<long long>(iy) * oh) / h) - 1, cy1 = static_cast<int>((static_cast<long long>(iy + 1) * oh) / h) + 1;
+        const int cx0 = static_cast<int>((static_cast<long long>(ix) * ow) / w) - 1, cx1 = static_cast<int>((static_cast<long long>(ix + 1) * ow) / w) + 1;
         float acc = 0.f;
-        for (int oy = max(cy - 1, 0); oy <= min(cy + 1, oh - 1); ++oy) {
+        for (int oy = max(cy0, 0); oy <= min(cy1, oh - 1); ++oy) {
             const int y0 = ap_start(oy, h, oh), y1 = ap_end(oy, h, oh);
             if (iy < y0 || iy >= y1) continue;
-            for (int ox = max(cx - 1, 0); ox <= min(cx + 1, ow - 1); ++ox) {
+            for (int ox = max(cx0, 0); ox <= min(cx1, ow - 1); ++ox) {
                 const int x0 = ap_start(ox, w, ow), x1 = ap_end(ox, w, ow);
                 if (ix < x0 || ix >= x1) continue;
                 acc += g[static_cast<long long>(oy) * ow + ox] / static_cast<float>((y1 - y0) * (x1 - x0));
@@ -209,7 +211,6 @@ extern "C" int rtsds_adaptive_avgpool_nchw_fwd(const float* x, int64_t planes, i
 
 extern "C" int rtsds_adaptive_avgpool_nchw_bwd(const float* dy, int64_t planes, int h, int w, int oh, int ow, float* dx, rtsds_stream_t s) {
     RTSDS_REQUIRE(dy && dx && planes > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "adaptive_avgpool_bwd: bad argument");
-    RTSDS_REQUIRE(oh <= 2 * h && ow <= 2 * w, "adaptive_avgpool_bwd: up-sampling by more than 2x is not supported");
     const long long total = planes * h * w;
     const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
     adaptive_avgpool_bwd_kernel<<<grid, 256, 0, as_stream(s)>>>(dy, planes, h, w, oh, ow, dx);

@@ -509,22 +509,56 @@ ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __res
     }
     __syncthreads();
     const long long plane = static_cast<long long>(oh) * ow;
+    // Row geometry of the block (shared by every thread): for the x8 head the FHR_ROWS output rows of a block all lie
+    // between the same two source rows, and the 4 output pixels of a thread between the same two source columns; then one
+    // class costs 4 shared-memory reads for 16 outputs instead of 64 (the write phase was bound by those reads).
+    Lerp ly[FHR_ROWS];
+    bool rows_uniform = (oy1 - oy0) == FHR_ROWS;
+#pragma unroll
+    for (int r = 0; r < FHR_ROWS; ++r) {
+        ly[r] = lerp_src(min(oy0 + r, oh - 1), rh, h);
+        rows_uniform = rows_uniform && ly[r].i0 == ly[0].i0 && ly[r].i1 == ly[0].i1;
+    }
     for (int ox = t * 4; ox < ow; ox += FHR_THREADS * 4) {
         Lerp lx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) lx[j] = lerp_src(min(ox + j, ow - 1), rw, w);
         const bool vec = (ox + 4 <= ow) && ((ow & 3) == 0);
+        const bool uniform = rows_uniform && vec && lx[1].i0 == lx[0].i0 && lx[2].i0 == lx[0].i0 && lx[3].i0 == lx[0].i0 &&
+                             lx[1].i1 == lx[0].i1 && lx[2].i1 == lx[0].i1 && lx[3].i1 == lx[0].i1;
+        if (uniform) {
+            const float* z00 = s_z + (static_cast<long long>(ly[0].i0 - ys) * w + lx[0].i0) * c;
+            const float* z01 = s_z + (static_cast<long long>(ly[0].i0 - ys) * w + lx[0].i1) * c;
+            const float* z10 = s_z + (static_cast<long long>(ly[0].i1 - ys) * w + lx[0].i0) * c;
+            const float* z11 = s_z + (static_cast<long long>(ly[0].i1 - ys) * w + lx[0].i1) * c;
+            float* op = out + static_cast<long long>(img) * c * plane + static_cast<long long>(oy0) * ow + ox;
+            for (int ch = 0; ch < c; ++ch) {
+                const float a00 = z00[ch], a01 = z01[ch], a10 = z10[ch], a11 = z11[ch];
+                float top[4], bot[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    top[j] = lx[j].l0 * a00 + lx[j].l1 * a01;
+                    bot[j] = lx[j].l0 * a10 + lx[j].l1 * a11;
+                }
+#pragma unroll
+                for (int r = 0; r < FHR_ROWS; ++r)
+                    __stcs(reinterpret_cast<float4*>(op + ch * plane + static_cast<long long>(r) * ow),
+                           make_float4(ly[r].l0 * top[0] + ly[r].l1 * bot[0], ly[r].l0 * top[1] + ly[r].l1 * bot[1],
+                                       ly[r].l0 * top[2] + ly[r].l1 * bot[2], ly[r].l0 * top[3] + ly[r].l1 * bot[3]));
+            }
+            continue;
+        }
         for (int oy = oy0; oy < oy1; ++oy) {
-            const Lerp ly = lerp_src(oy, rh, h);
-            const float* r0 = s_z + static_cast<long long>(ly.i0 - ys) * w * c;
-            const float* r1 = s_z + static_cast<long long>(ly.i1 - ys) * w * c;
+            const Lerp lyy = lerp_src(oy, rh, h);
+            const float* r0 = s_z + static_cast<long long>(lyy.i0 - ys) * w * c;
+            const float* r1 = s_z + static_cast<long long>(lyy.i1 - ys) * w * c;
             float* op = out + static_cast<long long>(img) * c * plane + static_cast<long long>(oy) * ow + ox;
             for (int ch = 0; ch < c; ++ch) {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    v[j] = ly.l0 * (lx[j].l0 * r0[lx[j].i0 * c + ch] + lx[j].l1 * r0[lx[j].i1 * c + ch]) +
-                           ly.l1 * (lx[j].l0 * r1[lx[j].i0 * c + ch] + lx[j].l1 * r1[lx[j].i1 * c + ch]);
+                    v[j] = lyy.l0 * (lx[j].l0 * r0[lx[j].i0 * c + ch] + lx[j].l1 * r0[lx[j].i1 * c + ch]) +
+                           lyy.l1 * (lx[j].l0 * r1[lx[j].i0 * c + ch] + lx[j].l1 * r1[lx[j].i1 * c + ch]);
                 if (vec) {
                     __stcs(reinterpret_cast<float4*>(op + ch * plane), make_float4(v[0], v[1], v[2], v[3]));
                 } else {

@@ -93,7 +93,9 @@ def test_sync_free_train_loop_matches_the_reference_loop_body(cuda, precision, m
     # the two loops take different kernels to the same numbers (fused resize+CE vs materialised logits + torch CE, fused vs
     # torch Adam): the FIRST batch agrees to round-off; after that four optimizer steps of a train-mode net with 2-sample ARM
     # statistics amplify the last-bit differences (1e-3 in fp32 after four steps, see tests/test_gpu_config1.py)
-    tol_first, tol = (1e-5, 5e-3) if precision == "fp32" else (2e-3, 2e-2)
+    # bf16: two separate runs already differ through the order of the fp32 statistics atomics; the accuracy entry is a count of
+    # ~5 % of the pixels of a random-init net, so a few hundred flipped argmaxes move it by percents
+    tol_first, tol = (1e-5, 5e-3) if precision == "fp32" else (2e-2, 0.15)
     worst, first = 0.0, None
     for (n1, a1, _), (n2, a2, _) in zip(slow, fast):
         if n1 in ("on_batch_end", "on_epoch_end"):

@@ -1,0 +1,212 @@
+"""Achieved HBM bandwidth of every bandwidth-bound kernel north_star names, at the BASELINE sizes (round-2 evidence table).
+
+  python tools/hbm_kernels.py [--ncu] > gpurun_out/r02_hbm_kernels.json
+
+Each kernel is launched alone on inputs of its real size.  Timing: CUDA events on the launching stream around ONE launch,
+the 126 MB L2 flushed before every timed launch (a 256 MB buffer is rewritten), median of 15; `warm_us` is the same launch
+back to back without the flush.  achieved = ALGORITHMIC bytes (what the kernel must read + write once) / cold time; peak =
+MEASURED_PEAKS.json hbm_gbs.  With --ncu every kernel is launched exactly twice and nothing else is timed, for
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv ...
+whose per-launch DRAM traffic goes into the same table (tools/hbm_table.py merges the two)."""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import sys
+
+os.environ.setdefault("RTSDS_ALLOW_RANDOM_INIT", "1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from rtsds_b200 import ops  # noqa: E402
+from rtsds_b200.ops import ACT_RELU, BF16, F16, F32  # noqa: E402
+
+NCU = "--ncu" in sys.argv
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+g = torch.Generator().manual_seed(0)
+H, W = 512, 1024
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+K_SETS = 1 if NCU else 8          # rotating buffer sets: 8 x (>= 40 MB) exceeds the 126 MB L2 for every streaming case
+
+
+def measure(fn):
+    """fn(i) launches the kernel on buffer set i % K_SETS.  cold: 5 rounds over all sets back to back between ONE event pair
+    (each launch finds its inputs evicted by the 7 launches since it last ran); warm: the same set 20 times."""
+    if NCU:
+        fn(0); fn(0)
+        torch.cuda.synchronize()
+        return None, None
+    for i in range(K_SETS):
+        fn(i)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(K_SETS):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / K_SETS)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        fn(0)
+    b.record()
+    torch.cuda.synchronize()
+    return statistics.median(ts), a.elapsed_time(b) * 1e3 / 20
+
+
+rows = []
+
+
+def case(name, kernel, what, nbytes, fn):
+    cold, warm = measure(fn)
+    rows.append({"name": name, "kernel": kernel, "what": what, "algorithmic_bytes": int(nbytes), "cold_us": cold, "warm_us": warm})
+
+
+def sets(make):
+    return [make() for _ in range(K_SETS)]
+
+
+def rnd(*shape, dtype=torch.float32):
+    return torch.randn(*shape, generator=g).to(device=dev, dtype=dtype)
+
+
+from models.bisenet.build_bisenet import BiSeNet  # noqa: E402
+from rtsds_b200.input_pipeline import DeviceInputPipeline  # noqa: E402
+from rtsds_b200.optim import FusedAdam  # noqa: E402
+import ctypes as C  # noqa: E402
+
+torch.manual_seed(42)
+m = BiSeNet(19, "resnet18").to(dev).eval()
+a1, a2, ffm = m.attention_refinement_module1, m.attention_refinement_module2, m.feature_fusion_module
+sc, sh = rnd(128), rnd(128)
+one = (C.c_float * 3)(1.0, 1.0, 1.0)
+zero = (C.c_float * 3)(0.0, 0.0, 0.0)
+wpk = torch.empty(128, 192, dtype=torch.float16, device=dev)
+ops.stem_pack_weights(m.context_path.conv1.weight, m.saptial_path.convblock1.conv1.weight, wpk)
+
+for n in ((1,) if NCU else (1, 8)):        # n = 1: BASELINE configs[1] (latency regime); n = 8: validation / training batches (bandwidth regime)
+    tag = f"[n={n}]"
+    # ---- metric: fast_hist / argmax (validation.py:51-55)
+    logits = sets(lambda: rnd(n, 19, H, W))
+    label = sets(lambda: torch.randint(0, 20, (n, H, W), generator=g).to(dev))
+    pred = sets(lambda: torch.randint(0, 19, (n, H, W), generator=g).to(dev))
+    hist = torch.zeros(361, dtype=torch.int64, device=dev)
+    p64 = torch.empty(n, H, W, dtype=torch.int64, device=dev)
+    p8 = torch.empty(n, H, W, dtype=torch.uint8, device=dev)
+    case("confusion_hist " + tag, "confusion_hist_kernel", "utils.fast_hist: int64 label + int64 pred -> 19x19 int64", n * H * W * 16,
+         lambda i: ops.confusion_hist(label[i].view(-1), pred[i].view(-1), 19, hist))
+    case("argmax_hist " + tag, "argmax_hist_kernel<4>", f"torch.argmax + fast_hist fused: fp32 logits [{n},19,512,1024] + int64 label", n * H * W * (19 * 4 + 8),
+         lambda i: ops.argmax_hist(logits[i], label[i], hist, None))
+    case("argmax_u8 " + tag, "argmax_hist_kernel<4>", "argmax only, uint8 class map out (serving)", n * H * W * (19 * 4 + 1),
+         lambda i: ops.argmax_hist(logits[i], None, None, p8))
+    # ---- BiSeNet glue (eval, fp16 storage)
+    f3 = sets(lambda: rnd(n, 32, 64, 256, dtype=torch.float16))
+    f4 = sets(lambda: rnd(n, 16, 32, 512, dtype=torch.float16))
+    cat = sets(lambda: torch.empty(n, 64, 128, 1024, dtype=torch.float16, device=dev))
+    pooled3, pooled4 = rnd(n, 1, 256), rnd(n, 1, 512)
+    case("arm_gate_resize " + tag, "arm_gate_resize_kernel<__half>", "both ARM gates + gated x2 / x4 resize into the concat buffer (eval)",
+         n * (32 * 64 * 256 * 2 + 16 * 32 * 512 * 2 + 64 * 128 * 768 * 2),
+         lambda i: ops.arm_gate_resize(ops.arm_side(f3[i], pooled3, a1, 32, 64, 256, 256), ops.arm_side(f4[i], pooled4, a2, 16, 32, 512, 512, mul_pooled=True),
+                                       F16, n, 64, 128, cat[i], 1024))
+    feat = sets(lambda: rnd(n, 64, 128, 32))
+    pooled_f = rnd(n, 1, 19)
+    out = sets(lambda: torch.empty(n, 19, H, W, dtype=torch.float32, device=dev))
+    case("ffm_head_resize " + tag, "ffm_head_resize_kernel", f"FFM attention + final 1x1 conv + x8 bilinear -> fp32 NCHW logits [{n},19,512,1024]",
+         n * (64 * 128 * 32 * 4 + 19 * H * W * 4), lambda i: ops.ffm_head_resize(feat[i], 32, pooled_f, n, 64, 128, 19, ffm.conv1, ffm.conv2, m.conv, out[i]))
+    case("resize_to_nchw " + tag, "resize_nchw_kernel", "x8 bilinear of 1/8-res logits -> fp32 NCHW (auxiliary heads / stock call sites)",
+         n * (64 * 128 * 32 * 4 + 19 * H * W * 4), lambda i: ops.resize_to_nchw(feat[i], n, 64, 128, 19, 32, out[i]))
+    cp0 = sets(lambda: rnd(n, 256, 512, 64, dtype=torch.float16))
+    pool = torch.empty(n, 128, 256, 64, dtype=torch.float16, device=dev)
+    case("maxpool3x3s2 " + tag, "maxpool_kernel<__half>", f"MaxPool2d(3,2,1) on [{n},256,512,64] fp16", n * (256 * 512 * 64 * 2 + 128 * 256 * 64 * 2),
+         lambda i: ops.maxpool3x3s2(cp0[i], pool))
+    x32 = sets(lambda: rnd(n, 3, H, W))
+    xu8 = sets(lambda: torch.randint(0, 256, (n, 3, H, W), dtype=torch.uint8, generator=g).to(dev))
+    ycp = sets(lambda: torch.empty(n, 256, 512, 64, dtype=torch.float16, device=dev))
+    ysp = torch.empty(n, 256, 512, 64, dtype=torch.float16, device=dev)
+    case("stem_pair_tc_fwd " + tag, "stem_fwd_tc_kernel", "7x7 s2 + 3x3 s2 stems fused (tcgen05): fp32 image in, two fp16 maps out",
+         n * (3 * H * W * 4 + 2 * 256 * 512 * 64 * 2), lambda i: ops.stem_pair_tc_fwd(x32[i], wpk, ycp[i], ysp, sc, sh, True))
+    case("stem_pair_tc_fwd_u8 " + tag, "stem_fwd_tc_kernel", "same, RAW uint8 image in (normalised while staging)", n * (3 * H * W + 2 * 256 * 512 * 64 * 2),
+         lambda i: ops.stem_pair_tc_fwd_u8(xu8[i], one, zero, wpk, ycp[i], ysp, sc, sh, True))
+    T = sets(lambda: rnd(n, 64, 128, 176))
+    fo = torch.empty(n, 64, 128, 32, dtype=torch.float32, device=dev)
+    case("tapn_gather " + tag, "tapn_gather_kernel<3>", "sum of the 9 shifted planes of the FFM taps-as-N GEMM + folded BN + ReLU", n * (64 * 128 * (176 + 32) * 4),
+         lambda i: ops.check(ops.lib().rtsds_tapn_gather(T[i].data_ptr(), 176, n, 64, 128, 19, 3, 1, 1, sc.data_ptr(), sh.data_ptr(), ACT_RELU, None,
+                                                        fo.data_ptr(), 32, None, ops._s()), "gather"))
+    # ---- input pipeline: Cityscapes 1024x2048 -> 512x1024
+    pipe = DeviceInputPipeline((H, W))
+    big = sets(lambda: torch.randint(0, 256, (n, 3, 1024, 2048), dtype=torch.uint8, generator=g).to(dev))
+    bigl = sets(lambda: torch.randint(0, 34, (n, 1024, 2048), dtype=torch.uint8, generator=g).to(dev))
+    xo = torch.empty(n, 3, H, W, dtype=torch.float32, device=dev)
+    lo = torch.empty(n, H, W, dtype=torch.int64, device=dev)
+    case("image_u8_to_f32 " + tag, "image_u8_kernel", "uint8 [n,3,1024,2048] -> antialiased x0.5 + Normalize -> fp32 [n,3,512,1024]", n * (3 * 1024 * 2048 + 3 * H * W * 4),
+         lambda i: pipe.images(big[i], xo))
+    case("label_resize_clamp " + tag, "label_kernel<uint8_t>", "uint8 labels [n,1024,2048] -> antialiased x0.5, round, clamp -> int64", n * (1024 * 2048 + H * W * 8),
+         lambda i: pipe.labels(bigl[i], (0, 19), lo))
+    # ---- discriminator side (adversarial step)
+    nd = min(n, 4)
+    oh2, ow2 = H // 2 + 1, W // 2 + 1
+    lg = sets(lambda: rnd(nd, 19, H, W))
+    xs = torch.empty(nd, oh2, ow2, 128, dtype=torch.bfloat16, device=dev)
+    case(f"s2d_fwd_softmax [n={nd}]", "s2d_fwd_kernel", "F.softmax(dim=1) of fp32 logits fused into the discriminator conv1 operand (bf16 space-to-depth)",
+         nd * 19 * H * W * 4 + xs.numel() * 2, lambda i: ops.check(ops.lib().rtsds_s2d_fwd(lg[i].data_ptr(), nd, 19, H, W, 1, BF16, xs.data_ptr(), ops._s()), "s2d"))
+    y1 = sets(lambda: rnd(nd, 256, 512, 64, dtype=torch.bfloat16))
+    wcls, bcls = rnd(1, 64, 4, 4), rnd(1)
+    tapsum = torch.empty(nd, 16, 64, dtype=torch.float32, device=dev)
+    dout = torch.empty(nd, dtype=torch.float32, device=dev)
+    case(f"disc_cls_fwd [n={nd}]", "disc_cls_tapsum_kernel", "Tiny discriminator classifier conv 4x4 s2 (Cout = 1) + AdaptiveAvgPool2d(1) on [n,256,512,64] bf16",
+         nd * 256 * 512 * 64 * 2, lambda i: ops.check(ops.lib().rtsds_disc_cls_fwd(y1[i].data_ptr(), 64, BF16, nd, 256, 512, 64, wcls.data_ptr(), bcls.data_ptr(),
+                                                                                  tapsum.data_ptr(), dout.data_ptr(), ops._s()), "cls"))
+    del logits, label, pred, f3, f4, cat, feat, out, cp0, x32, xu8, ycp, T, big, bigl, lg, y1
+    torch.cuda.empty_cache()
+
+lossb = torch.empty(1, dtype=torch.float32, device=dev)
+dl = torch.empty(2, dtype=torch.float32, device=dev)
+d2 = rnd(2)
+case("bce_logits", "bce_logits_kernel", "BCEWithLogitsLoss of 2 logits vs a constant target (launch latency only)", 24,
+     lambda i: ops.check(ops.lib().rtsds_bce_logits(d2.data_ptr(), 2, 1.0, 0.01, lossb.data_ptr(), dl.data_ptr(), ops._s()), "bce"))
+
+# ---- training-side bandwidth kernels (b = 8, 720 x 1280 shapes)
+act = sets(lambda: rnd(8, 180, 320, 64, dtype=torch.bfloat16))
+yact = torch.empty(8, 180, 320, 64, dtype=torch.bfloat16, device=dev)
+s64, h64 = rnd(64), rnd(64)
+case("scale_shift_act", "scale_shift_act_kernel", "train-mode BatchNorm apply + ReLU on [8,180,320,64] bf16", 8 * 180 * 320 * 64 * 4,
+     lambda i: ops.scale_shift_act(act[i], yact, 8 * 180 * 320, 64, s64, h64, None, ACT_RELU))
+ps = [torch.nn.Parameter(rnd(512, 512, 3, 3)) for _ in range(5)] + [torch.nn.Parameter(rnd(1000, 512))]
+for p in ps:
+    p.grad = rnd(*p.shape)
+opt = FusedAdam(ps, lr=1e-4)
+opt.step()
+nel = sum(p.numel() for p in ps)
+case("optim_step", "optim_step_kernel", "fused Adam over 12.3 M parameters: p, g, m, v read, p, m, v written", nel * 28, lambda i: opt.step())
+lab8 = sets(lambda: torch.randint(0, 20, (8, 720, 1280), generator=g).to(dev))
+z8 = rnd(8, 90, 160, 32)
+dz8 = torch.zeros(8, 90, 160, 32, dtype=torch.float32, device=dev)
+acc = torch.zeros(4, dtype=torch.float64, device=dev)
+pr8 = torch.empty(8, 720, 1280, dtype=torch.int64, device=dev)
+case("resize_ce_fused", "resize_ce_fused_kernel<19>", "x8 bilinear + CrossEntropy(ignore) + argmax + gradient at 1/8 res, [8,720,1280] int64 labels (instruction bound)",
+     8 * 720 * 1280 * 16 + z8.numel() * 4 * 2, lambda i: ops.resize_ce_fused(z8, 8, 90, 160, 19, 32, 720, 1280, lab8[i], 19, acc, pr8, dz8))
+
+pk, src = peak()
+for r in rows:
+    if r["cold_us"]:
+        r["achieved_gbs"] = round(r["algorithmic_bytes"] / r["cold_us"] / 1e3, 1)
+        r["frac_of_hbm_peak"] = round(r["achieved_gbs"] / pk, 3)
+        r["warm_gbs"] = round(r["algorithmic_bytes"] / r["warm_us"] / 1e3, 1)
+        r["cold_us"], r["warm_us"] = round(r["cold_us"], 2), round(r["warm_us"], 2)
+print(json.dumps({"peak_hbm_gbs": pk, "peak_source": src, "timing": "CUDA events around 8 back-to-back launches over 8 rotating buffer sets (inputs evicted from L2 between uses), median of 5 rounds" if not NCU else "ncu pass",
+                  "rows": rows}, indent=1))
