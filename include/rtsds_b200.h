@@ -93,8 +93,10 @@ int rtsds_argmax_hist_u8(const float* logits, const int64_t* label, int n, int n
  *       support grows with the down-scaling factor; identity for equal sizes).
  *   label_resize_clamp: read_image(...).long() -> Resize -> IntRangeTransformer(lo, hi): src uint8 or int64 [n,h,w] ->
  *       int64 [n,oh,ow] = clamp(round_half_even(resize(float(src))), lo, hi)   (clamp == 0: no clamp, GTA5 labels).
- *   stem_pair_tc_fwd_u8: rtsds_stem_pair_tc_fwd reading the uint8 image directly; the normalisation is applied while the
- *       input patch is staged in shared memory, so a batch-1 frame costs no extra pass at all.
+ * For frames that already have the network's size the image kernel is a pure convert + normalise pass (16 pixels per
+ * thread): ~3 us for a 512x1024 frame, after which the fused stems run unchanged.  (A variant of the stem kernel that read
+ * the uint8 frame itself was measured 20 us SLOWER per frame: the conversion lands on the gather warps, which are that
+ * kernel's critical path — profiles/r02_summary.md.)
  * ---------------------------------------------------------------------- */
 int rtsds_image_u8_to_f32(const uint8_t* src, int n, int c, int h, int w, int oh, int ow, const float* scale3,
                           const float* bias3, float* dst, rtsds_stream_t s);
@@ -105,9 +107,7 @@ int rtsds_label_resize_clamp(const void* src, int src_is_u8, int n, int h, int w
  * bwd: dx[i] = sum over the windows containing i of dy / area (gather form, deterministic). */
 int rtsds_adaptive_avgpool_nchw_fwd(const float* x, int64_t planes, int h, int w, int oh, int ow, float* y, rtsds_stream_t s);
 int rtsds_adaptive_avgpool_nchw_bwd(const float* dy, int64_t planes, int h, int w, int oh, int ow, float* dx, rtsds_stream_t s);
-int rtsds_stem_pair_tc_fwd_u8(const uint8_t* x, const float* in_scale3, const float* in_bias3, int n, int h, int w,
-                              const void* wpk, const float* scale, const float* shift, int relu, int dtype,
-                              void* y_cp, void* y_sp, rtsds_stream_t s);
+
 
 /* ------------------------------------------------------------------------
  * Convolution (nn.Conv2d as used by models/bisenet/build_bisenet.py:11-12,

@@ -87,7 +87,6 @@ SIGNATURES = {
     "rtsds_adaptive_avgpool_nchw_bwd": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "rtsds_image_u8_to_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rtsds_label_resize_clamp": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
-    "rtsds_stem_pair_tc_fwd_u8": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
     "rtsds_conv_cout_pad": (_I, [_I]),
     "rtsds_conv2d_tc_tune": (None, [_I, _I]),
     "rtsds_conv2d_tc_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -71,6 +71,7 @@ class BiSeNetPlan:
         self.steps = []          # everything between the stems and the low-res logits
         self.pack_steps = []     # weight repack / BN fold (run when parameters change)
         self.ws = None
+        self.x_f32 = None
         self.ws_ds = None
         self.side_ds = None
         self._ws_bytes = 0
@@ -335,11 +336,15 @@ class BiSeNetPlan:
         from .input_pipeline import stem_affine
 
         def run(x):
-            if x.dtype == torch.uint8:          # raw frame: the normalisation happens while the patch is staged
+            if x.dtype == torch.uint8:
+                # raw uint8 frame: convert + normalise into a plan-owned fp32 image (one 3 us pass, csrc/input.cu)
+                if self.x_f32 is None:
+                    self.x_f32 = self.buf(self.n, 3, self.h, self.w, dtype=torch.float32)
                 sc, bi = stem_affine(self.model)
-                ops.stem_pair_tc_fwd_u8(x, sc, bi, wpk, y_cp, y_sp, scale, shift, True)
-            else:
-                ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True)
+                ops.check(ops.lib().rtsds_image_u8_to_f32(ops._p(x), self.n, 3, self.h, self.w, self.h, self.w, sc, bi, ops._p(self.x_f32),
+                                                          ops._s()), "image_u8_to_f32")
+                x = self.x_f32
+            ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True)
 
         self.pre_steps.append(run)
 

@@ -82,6 +82,25 @@ image_u8_kernel(const uint8_t* __restrict__ src, int n, int c, int h, int w, int
     }
 }
 
+// same-size case (a camera frame already at network resolution): pure convert + normalise, 16 pixels per thread
+// (one 16-byte load, four 16-byte stores).  plane = h*w must be a multiple of 16 and src 16-byte aligned (host check).
+__global__ void __launch_bounds__(256)
+image_u8_identity_kernel(const uint8_t* __restrict__ src, long long total16, int plane16, int c, float s0, float s1, float s2,
+                         float b0, float b1, float b2, float* __restrict__ dst) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>((i / plane16) % c);
+        const float sc = ch == 0 ? s0 : (ch == 1 ? s1 : s2), bi = ch == 0 ? b0 : (ch == 1 ? b1 : b2);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+        float4* o = reinterpret_cast<float4*>(dst) + i * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = make_float4(fmaf(static_cast<float>(wds[k] & 0xffu), sc, bi), fmaf(static_cast<float>((wds[k] >> 8) & 0xffu), sc, bi),
+                               fmaf(static_cast<float>((wds[k] >> 16) & 0xffu), sc, bi), fmaf(static_cast<float>(wds[k] >> 24), sc, bi));
+    }
+}
+
 // labels: S (uint8 or int64) [n,h,w] -> int64 [n,oh,ow] = clamp(round(resize(float(src))), lo, hi)
 template <typename S>
 __global__ void __launch_bounds__(256)
@@ -120,6 +139,15 @@ extern "C" int rtsds_image_u8_to_f32(const uint8_t* src, int n, int c, int h, in
     int rc = aa_check(h, w, oh, ow, "image_u8_to_f32");
     if (rc != RTSDS_OK) return rc;
     const long long total = static_cast<long long>(n) * c * oh * ow;
+    const long long plane = static_cast<long long>(h) * w;
+    if (h == oh && w == ow && plane % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const long long t16 = total / 16;
+        const int g16 = static_cast<int>(cdiv(t16, 256) > 16LL * num_sms() ? 16LL * num_sms() : cdiv(t16, 256));
+        image_u8_identity_kernel<<<g16, 256, 0, as_stream(s)>>>(src, t16, static_cast<int>(plane / 16), c, scale3[0], scale3[c > 1 ? 1 : 0],
+                                                                scale3[c > 2 ? 2 : 0], bias3[0], bias3[c > 1 ? 1 : 0], bias3[c > 2 ? 2 : 0], dst);
+        count_launch();
+        return check_launch("image_u8_identity_kernel");
+    }
     const int grid = static_cast<int>(cdiv(total, 256) > 32LL * num_sms() ? 32LL * num_sms() : cdiv(total, 256));
     image_u8_kernel<<<grid, 256, 0, as_stream(s)>>>(src, n, c, h, w, oh, ow, make_axis(h, oh), make_axis(w, ow), h == oh && w == ow,
                                                     scale3[0], scale3[c > 1 ? 1 : 0], scale3[c > 2 ? 2 : 0], bias3[0],

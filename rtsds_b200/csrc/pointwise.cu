@@ -406,18 +406,27 @@ arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, i
         }
         __syncthreads();
         const float* pp = s_pool;
-        for (int k = 0; k < 4; ++k) {
-            const int co = cg * 32 + warp * 4 + k;
+        {   // 32 gates, 8 threads each: every thread sums a stride-8 slice of its dot product, shuffles combine the slices
+            const int gi = threadIdx.x >> 3, sub = threadIdx.x & 7;
+            const int co = cg * 32 + gi;
             const float* wr = a.w + static_cast<long long>(co) * a.c;
-            float acc = 0.f;
-            for (int i = lane; i < a.c; i += 32) acc = fmaf(wr[i], pp[i], acc);
-            acc = warp_sum(acc) + (a.b ? a.b[co] : 0.f);
-            if (lane == 0) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+            for (int i = sub; i < a.c; i += 16) {
+                acc0 = fmaf(__ldg(wr + i), pp[i], acc0);
+                acc1 = fmaf(__ldg(wr + i + 8), pp[i + 8], acc1);          // c is a multiple of 32
+            }
+            float acc = acc0 + acc1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (sub == 0) {
+                acc += a.b ? a.b[co] : 0.f;
                 const float sc = a.gamma[co] / sqrtf(a.var[co] + a.eps);
                 const float sh = a.beta[co] - a.mean[co] * sc;
                 float v = 1.f / (1.f + expf(-(acc * sc + sh)));
                 if (a.mul_pooled) v *= pp[co];
-                s_gate[warp * 4 + k] = v * a.out_scale;
+                s_gate[gi] = v * a.out_scale;
             }
         }
         __syncthreads();

@@ -47,10 +47,6 @@ struct StemTcParams {
     __nv_bfloat16* y_sp;
     // wgrad
     float* dw;                 // [128][192] fp32, accumulated
-    // uint8 input (device-side input pipeline): x_u8 NCHW [n,3,h,w]; the loader applies
-    // float(x) * in_scale[c] + in_bias[c] (= transforms.Normalize on the .float() image) while staging the patch
-    const uint8_t* x_u8;
-    float in_scale[3], in_bias[3];
 };
 
 // ---- input patch staging ----------------------------------------------------------------------------------
@@ -89,53 +85,6 @@ __device__ __forceinline__ void patch_issue(const StemTcParams& p, int t, int ti
         if (idx < P::N_EL)
             ptx::cp_async_4(patch + (c * P::PH + prow) * P::RP + (pcol & 1) * P::PO + (pcol >> 1),
                             ok ? xi + (static_cast<long long>(c) * p.h + iy) * p.w + ix : p.x, ok);
-    }
-}
-
-// uint8 input: the bytes of tile t's patch are loaded into registers (packed four per register, with a validity mask for
-// the zero padding) while the previous tile is being built, and converted + normalised into the staged patch afterwards.
-template <int TW>
-__device__ __forceinline__ void patch_load_u8(const StemTcParams& p, int t, int tid, uint32_t (&regs)[6], uint32_t* mask) {
-    using P = Patch<TW>;
-    static_assert(P::PRE <= 24, "patch registers");
-    const int per = p.tiles_w * p.tiles_h;
-    const int img = t / per;
-    const int r = t - img * per;
-    const int th = r / p.tiles_w;
-    const int iy_base = th * P::TH * 2 - 3, ix_base = (r - th * p.tiles_w) * TW * 2 - 3;
-    const uint8_t* xi = p.x_u8 + static_cast<long long>(img) * 3 * p.h * p.w;
-    uint32_t mk = 0;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) regs[q] = 0;
-#pragma unroll
-    for (int k = 0; k < P::PRE; ++k) {
-        const int idx = tid + k * 128;
-        const int c = idx / (P::PH * P::PW), rem = idx - c * (P::PH * P::PW);
-        const int prow = rem / P::PW, pcol = rem - prow * P::PW;
-        const int iy = iy_base + prow, ix = ix_base + pcol;
-        const bool ok = idx < P::N_EL && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-        if (ok) {
-            const uint32_t b = __ldg(xi + (static_cast<long long>(c) * p.h + iy) * p.w + ix);
-            regs[k >> 2] |= b << ((k & 3) * 8);
-            mk |= 1u << k;
-        }
-    }
-    *mask = mk;
-}
-template <int TW>
-__device__ __forceinline__ void patch_store_u8(const StemTcParams& p, int tid, const uint32_t (&regs)[6], uint32_t mask, float* patch) {
-    using P = Patch<TW>;
-#pragma unroll
-    for (int k = 0; k < P::PRE; ++k) {
-        const int idx = tid + k * 128;
-        const int c = idx / (P::PH * P::PW), rem = idx - c * (P::PH * P::PW);
-        const int prow = rem / P::PW, pcol = rem - prow * P::PW;
-        if (idx < P::N_EL) {
-            const float b = static_cast<float>((regs[k >> 2] >> ((k & 3) * 8)) & 0xffu);
-            const float sc = c == 0 ? p.in_scale[0] : (c == 1 ? p.in_scale[1] : p.in_scale[2]);
-            const float bi = c == 0 ? p.in_bias[0] : (c == 1 ? p.in_bias[1] : p.in_bias[2]);
-            patch[(c * P::PH + prow) * P::RP + (pcol & 1) * P::PO + (pcol >> 1)] = ((mask >> k) & 1u) ? fmaf(b, sc, bi) : 0.f;
-        }
     }
 }
 
@@ -227,7 +176,7 @@ __device__ __forceinline__ float warp_tsum(float (&v)[32], int lane) {
 struct StemWgMaps { CUtensorMap d_cp, d_sp; };      // [64, ow, oh, n] bf16 each: d_raw (wgrad loads) / y (forward stores)
 
 constexpr int SF_THREADS = 13 * 32;                 // 4 gather + 1 MMA + 8 epilogue warps
-template <int TW, bool F16, bool U8>
+template <int TW, bool F16>
 __global__ void __launch_bounds__(SF_THREADS, 1)
 stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p) {
     constexpr bool STEM_F16 = F16;                        // operand / output type: IEEE half (eval-mode inference) or bf16
@@ -277,31 +226,7 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
 
     if (warp < 4) {
         // ================= gather =================
-        if constexpr (U8) {
-            const int m = threadIdx.x;
-            const int gstep = static_cast<int>(gridDim.x);
-            uint32_t regs[6], mask;
-            for (int k = 0; k < 2; ++k)
-                if (static_cast<int>(blockIdx.x) + k * gstep < p.tiles_total) {
-                    patch_load_u8<TW>(p, blockIdx.x + k * gstep, m, regs, &mask);
-                    patch_store_u8<TW>(p, m, regs, mask, s_patch + k * S_PATCH_FLOATS);
-                }
-            int it = 0;
-            for (int t = blockIdx.x; t < p.tiles_total; t += gstep, ++it) {
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                asm volatile("bar.sync 2, 128;" ::: "memory");      // patch of tile `it` is complete; tile it-1 is fully built
-                const bool nxt = t + 2 * gstep < p.tiles_total;
-                if (nxt) patch_load_u8<TW>(p, t + 2 * gstep, m, regs, &mask);    // in flight while this tile is built
-                ptx::mbar_wait(&a_empty[buf], ph ^ 1);
-                gather_row<TW, STEM_F16>(s_patch + (it % S_PATCHES) * S_PATCH_FLOATS, s_a + buf * S_A_BYTES, m);
-                ptx::fence_proxy_async();
-                ptx::mbar_arrive(&a_full[buf]);
-                if (nxt) patch_store_u8<TW>(p, m, regs, mask, s_patch + ((it + 2) % S_PATCHES) * S_PATCH_FLOATS);
-            }
-        } else {
-            STEM_GATHER_LOOP(a_full, a_empty, s_a, )
-        }
+        STEM_GATHER_LOOP(a_full, a_empty, s_a, )
     } else if (warp == 4) {
         // ================= MMA =================
         if (lane == 0) {
@@ -587,10 +512,10 @@ extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oih
 
 // Fused tensor-core stems.  x: NCHW fp32 [n,3,h,w]; wpk from rtsds_stem_pack_weights; scale/shift: fp32 [128]
 // (context-path BN in 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
-static int stem_pair_fwd_impl(const float* x, const uint8_t* x_u8, const float* in_scale3, const float* in_bias3, int n, int h, int w,
-                              const void* wpk, const float* scale, const float* shift, int relu, float* stats_cp, float* stats_sp,
-                              int dtype, void* y_cp, void* y_sp, rtsds_stream_t s) {
-    RTSDS_REQUIRE((x || x_u8) && wpk && y_cp && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
+extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                                      const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
+                                      void* y_sp, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && wpk && y_cp && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
     RTSDS_REQUIRE(is_16bit(dtype), "stem_pair_tc_fwd: dtype must be bf16 or fp16");
     RTSDS_REQUIRE((stats_cp == nullptr) == (stats_sp == nullptr), "stem_pair_tc_fwd: stats go together");
     int rc = rtsds_check_device();
@@ -601,8 +526,6 @@ static int stem_pair_fwd_impl(const float* x, const uint8_t* x_u8, const float* 
     if (rc != RTSDS_OK) return rc;
     p.x = x; p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.scale = scale; p.shift = shift; p.relu = relu;
     p.stats_cp = stats_cp; p.stats_sp = stats_sp;
-    p.x_u8 = x_u8;
-    for (int i = 0; i < 3; ++i) { p.in_scale[i] = in_scale3 ? in_scale3[i] : 1.f; p.in_bias[i] = in_bias3 ? in_bias3[i] : 0.f; }
     p.y_cp = reinterpret_cast<__nv_bfloat16*>(y_cp); p.y_sp = reinterpret_cast<__nv_bfloat16*>(y_sp);
     StemWgMaps maps;
     rc = stem_make_maps(p, y_cp, y_sp, &maps, "stem_pair_tc_fwd");
@@ -610,12 +533,9 @@ static int stem_pair_fwd_impl(const float* x, const uint8_t* x_u8, const float* 
     const size_t smem = 1024 + 3 * S_A_BYTES + 2 * S_ATOM_BYTES + 512 * 4 + 8 * 8 + 16 + S_PATCHES * S_PATCH_FLOATS * 4;
     static bool done = false;
     if (!done) {
-        const void* fns[12] = {(const void*)stem_fwd_tc_kernel<32, false, false>, (const void*)stem_fwd_tc_kernel<16, false, false>,
-                               (const void*)stem_fwd_tc_kernel<8, false, false>, (const void*)stem_fwd_tc_kernel<32, true, false>,
-                               (const void*)stem_fwd_tc_kernel<16, true, false>, (const void*)stem_fwd_tc_kernel<8, true, false>,
-                               (const void*)stem_fwd_tc_kernel<32, false, true>, (const void*)stem_fwd_tc_kernel<16, false, true>,
-                               (const void*)stem_fwd_tc_kernel<8, false, true>, (const void*)stem_fwd_tc_kernel<32, true, true>,
-                               (const void*)stem_fwd_tc_kernel<16, true, true>, (const void*)stem_fwd_tc_kernel<8, true, true>};
+        const void* fns[6] = {(const void*)stem_fwd_tc_kernel<32, false>, (const void*)stem_fwd_tc_kernel<16, false>,
+                              (const void*)stem_fwd_tc_kernel<8, false>, (const void*)stem_fwd_tc_kernel<32, true>,
+                              (const void*)stem_fwd_tc_kernel<16, true>, (const void*)stem_fwd_tc_kernel<8, true>};
         for (const void* f : fns) {
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) { set_error("stem_pair_tc_fwd: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
@@ -623,13 +543,11 @@ static int stem_pair_fwd_impl(const float* x, const uint8_t* x_u8, const float* 
         done = true;
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
-    const bool f16 = dtype == RTSDS_F16, u8 = x_u8 != nullptr;
+    const bool f16 = dtype == RTSDS_F16;
 #define STEM_FWD(TWv)                                                                                         \
     do {                                                                                                      \
-        if (f16 && u8) stem_fwd_tc_kernel<TWv, true, true><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);         \
-        else if (f16) stem_fwd_tc_kernel<TWv, true, false><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);         \
-        else if (u8) stem_fwd_tc_kernel<TWv, false, true><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);          \
-        else stem_fwd_tc_kernel<TWv, false, false><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);                 \
+        if (f16) stem_fwd_tc_kernel<TWv, true><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);            \
+        else stem_fwd_tc_kernel<TWv, false><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);               \
     } while (0)
     if (p.tile_w == 32) STEM_FWD(32);
     else if (p.tile_w == 16) STEM_FWD(16);
@@ -637,21 +555,6 @@ static int stem_pair_fwd_impl(const float* x, const uint8_t* x_u8, const float* 
 #undef STEM_FWD
     count_launch();
     return check_launch("stem_fwd_tc_kernel");
-}
-
-extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
-                                      const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
-                                      void* y_sp, rtsds_stream_t s) {
-    return stem_pair_fwd_impl(x, nullptr, nullptr, nullptr, n, h, w, wpk, scale, shift, relu, stats_cp, stats_sp, dtype, y_cp, y_sp, s);
-}
-
-// Same with the RAW uint8 image as input: in_scale3 / in_bias3 (HOST pointers, 3 floats each, NULL = 1 / 0)
-// are the per-channel affine applied to float(x) while the patch is staged — 1/std and -mean/std for
-// transforms.Normalize(mean, std) (main.py:70,82).  The zero padding of the conv applies to the normalised image.
-extern "C" int rtsds_stem_pair_tc_fwd_u8(const uint8_t* x, const float* in_scale3, const float* in_bias3, int n, int h, int w,
-                                         const void* wpk, const float* scale, const float* shift, int relu, int dtype,
-                                         void* y_cp, void* y_sp, rtsds_stream_t s) {
-    return stem_pair_fwd_impl(nullptr, x, in_scale3, in_bias3, n, h, w, wpk, scale, shift, relu, nullptr, nullptr, dtype, y_cp, y_sp, s);
 }
 
 // Fused weight gradient of both stems.  d_raw_*: NHWC bf16 [n,oh,ow,64]; dw_ws: fp32 [128*192] scratch that is

@@ -6,8 +6,9 @@ raw uint8 planes (csrc/input.cu), so a frame crosses PCIe as 3 bytes per pixel i
     x = pipe.images(u8_batch)                                  # uint8 [N,3,h,w] cuda -> fp32 [N,3,512,1024]
     y = pipe.labels(u8_labels, clamp=(0, 19))                  # uint8/int64 [N,1,h,w] or [N,h,w] -> int64 [N,512,1024]
 
-and, for batch-1 inference, no extra pass at all: `model(u8_frame)` — the eval-mode BiSeNet forward accepts a uint8 NCHW
-tensor and applies `model.rtsds_input_norm = (mean, std)` while its fused stem kernel stages the input patch.
+and, for inference, `model(u8_frame)`: the eval-mode BiSeNet forward accepts a uint8 NCHW tensor and applies
+`model.rtsds_input_norm = (mean, std)` in a 3 us convert + normalise pass in front of its fused stem kernel (reading the
+bytes inside the stem kernel was measured slower: the conversion lands on that kernel's critical gather warps).
 
 The reference normalises the 0..255 float image with the ImageNet mean / std of 0..1 images (main.py:70: `.float()` is
 never divided by 255); that quirk is kept: the defaults below are the reference's numbers on the reference's scale."""

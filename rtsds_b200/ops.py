@@ -220,14 +220,6 @@ def stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale=None, shift=None, relu=True, stat
                                        dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
 
 
-def stem_pair_tc_fwd_u8(x_u8, in_scale3, in_bias3, wpk, y_cp, y_sp, scale=None, shift=None, relu=True) -> None:
-    """Fused stems reading the RAW uint8 image; in_scale3 / in_bias3: ctypes float[3] (rtsds_b200/input_pipeline.py)."""
-    n, _, h, w = x_u8.shape
-    assert x_u8.dtype == torch.uint8 and wpk.dtype == y_cp.dtype == y_sp.dtype
-    check(lib().rtsds_stem_pair_tc_fwd_u8(_p(x_u8), in_scale3, in_bias3, n, h, w, _p(wpk), _p(scale), _p(shift), int(relu),
-                                          dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd_u8")
-
-
 def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
     n, _, h, w = x.shape
     check(lib().rtsds_stem_pair_tc_wgrad(_p(x), n, h, w, _p(d_raw_cp), _p(d_raw_sp), _p(dw_ws), _p(g7), _p(g3), _s()),

@@ -56,7 +56,7 @@ def test_label_pipeline_matches_torchvision(cuda, src, size, clamp, dtype):
 
 
 def test_model_accepts_raw_uint8_frames(cuda):
-    """model(uint8 frame) == model(Normalize(frame.float())): the fused stem kernel normalises while staging its patch."""
+    """model(uint8 frame) == model(Normalize(frame.float())): the forward converts + normalises raw frames on the device."""
     from models.bisenet.build_bisenet import BiSeNet
     from oracle import weights
 

@@ -2,9 +2,10 @@
 
   python tools/hbm_kernels.py [--ncu] > gpurun_out/r02_hbm_kernels.json
 
-Each kernel is launched alone on inputs of its real size.  Timing: CUDA events on the launching stream around ONE launch,
-the 126 MB L2 flushed before every timed launch (a 256 MB buffer is rewritten), median of 15; `warm_us` is the same launch
-back to back without the flush.  achieved = ALGORITHMIC bytes (what the kernel must read + write once) / cold time; peak =
+Each kernel is launched alone on inputs of its real size.  Timing: CUDA events on the launching stream around 8 back-to-back
+launches over 8 ROTATING buffer sets (together larger than the 126 MB L2, so every launch finds its inputs evicted), median
+of 5 rounds; `warm_us` is the same buffer set 20 times.  n = 1 rows are BASELINE configs[1] sizes (launch-latency regime: 1-40 MB
+per launch), n = 8 rows the validation / training batch (bandwidth regime).  achieved = ALGORITHMIC bytes / cold time; peak =
 MEASURED_PEAKS.json hbm_gbs.  With --ncu every kernel is launched exactly twice and nothing else is timed, for
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv ...
 whose per-launch DRAM traffic goes into the same table (tools/hbm_table.py merges the two)."""
@@ -140,8 +141,10 @@ for n in ((1,) if NCU else (1, 8)):        # n = 1: BASELINE configs[1] (latency
     ysp = torch.empty(n, 256, 512, 64, dtype=torch.float16, device=dev)
     case("stem_pair_tc_fwd " + tag, "stem_fwd_tc_kernel", "7x7 s2 + 3x3 s2 stems fused (tcgen05): fp32 image in, two fp16 maps out",
          n * (3 * H * W * 4 + 2 * 256 * 512 * 64 * 2), lambda i: ops.stem_pair_tc_fwd(x32[i], wpk, ycp[i], ysp, sc, sh, True))
-    case("stem_pair_tc_fwd_u8 " + tag, "stem_fwd_tc_kernel", "same, RAW uint8 image in (normalised while staging)", n * (3 * H * W + 2 * 256 * 512 * 64 * 2),
-         lambda i: ops.stem_pair_tc_fwd_u8(xu8[i], one, zero, wpk, ycp[i], ysp, sc, sh, True))
+    xf = torch.empty(n, 3, H, W, dtype=torch.float32, device=dev)
+    same = DeviceInputPipeline(None)
+    case("image_u8_to_f32 same size " + tag, "image_u8_identity_kernel", "uint8 frame -> float + Normalize at the network size (serving path)", n * 3 * H * W * 5,
+         lambda i: same.images(xu8[i], xf))
     T = sets(lambda: rnd(n, 64, 128, 176))
     fo = torch.empty(n, 64, 128, 32, dtype=torch.float32, device=dev)
     case("tapn_gather " + tag, "tapn_gather_kernel<3>", "sum of the 9 shifted planes of the FFM taps-as-N GEMM + folded BN + ReLU", n * (64 * 128 * (176 + 32) * 4),
