@@ -127,7 +127,8 @@ def test_frozen_discriminator_and_detached_input(cuda):
         prm.requires_grad = True
     x2 = logits.clone().requires_grad_(True)
     F.binary_cross_entropy_with_logits(m(F.softmax(x2, 1)), torch.ones(2, 1, 1, 1, device="cuda")).backward()
-    assert torch.equal(dx_frozen, x2.grad)
+    # same kernels either way; bit-equal except for the order of fp32 atomics in the CUDA-core dgrad (seen once in ~10 runs)
+    assert (dx_frozen - x2.grad).abs().max().item() <= 1e-6 * dx_frozen.abs().max().item()
     g1 = [prm.grad.clone() for prm in m.parameters()]
     # detached input: parameter grads only; a second backward ACCUMULATES into .grad like autograd does
     p = m(F.softmax(logits, 1).detach())
