@@ -313,6 +313,14 @@ int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_
  * gradient of the virtual weight into the [cout,3,k,k] gradient.  conv_fwd has the epilogue of rtsds_conv2d_tc_fwd
  * (scale/shift/act/stats); conv_wgrad accumulates dw_packed [cout][4][64] fp32 like rtsds_conv2d_tc_wgrad. */
 int rtsds_stem_s2d_pack(const float* x, int n, int h, int w, void* P, rtsds_stream_t s);
+/* General form: x fp32 NCHW or (x_is_u8) the RAW uint8 frame; P = scale3[c]*x + bias3[c] inside the image (HOST float[3]
+ * each, NULL = 1 / 0: transforms.Normalize of main.py:70 folded into the pack), 0 outside; P of p_dtype
+ * (RTSDS_BF16 / RTSDS_F16).  rtsds_stem_s2d_conv_fwd_dt: the conv on such a P (weights packed in the same type). */
+int rtsds_stem_s2d_pack_ex(const void* x, int x_is_u8, const float* scale3, const float* bias3, int n, int h, int w,
+                           int p_dtype, void* P, rtsds_stream_t s);
+int rtsds_stem_s2d_conv_fwd_dt(const void* P, int p_dtype, int n, int oh, int ow, const void* w_packed, int cout,
+                               const float* scale, const float* shift, int act, void* y, int out_ld, int out_dtype,
+                               rtsds_stream_t s);
 int rtsds_stem_s2d_weight(const float* w_oihw, int cout, int k, int pad, float* w2_oihw, rtsds_stream_t s);
 int rtsds_stem_s2d_weight_grad(const float* g2_oihw, int cout, int k, int pad, float* grad_oihw, rtsds_stream_t s);
 int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, const void* w_packed, int cout, const float* scale,
@@ -324,6 +332,9 @@ int rtsds_stem_s2d_conv_wgrad(const void* P, int n, int oh, int ow, const void* 
 /* nn.MaxPool2d(3, 2, 1[, ceil_mode]) on NHWC. */
 int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype,
                            int ceil_mode, void* y, rtsds_stream_t s);
+/* Same for an input whose pixels are x_ld >= c elements apart (a channel slice of a wider NHWC buffer). */
+int rtsds_maxpool3x3s2_fwd_ld(const void* x, int n, int h, int w, int c, int x_ld, int dtype,
+                              int ceil_mode, void* y, rtsds_stream_t s);
 /* Training form: also writes idx [n,oh,ow,c/8] uint32 = per channel (one nibble each) the window position
  * r*3+q of the first maximum, so that the backward pass (rtsds_maxpool3x3s2_bwd_idx) does not re-read x. */
 int rtsds_maxpool3x3s2_fwd_idx(const void* x, int n, int h, int w, int c, int dtype,

@@ -85,6 +85,9 @@ SIGNATURES = {
     "rtsds_argmax_hist_u8": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
     "rtsds_adaptive_avgpool_nchw_fwd": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "rtsds_adaptive_avgpool_nchw_bwd": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
+    "rtsds_stem_s2d_pack_ex": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rtsds_stem_s2d_conv_fwd_dt": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _P]),
+    "rtsds_maxpool3x3s2_fwd_ld": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rtsds_image_u8_to_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rtsds_label_resize_clamp": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
     "rtsds_conv_cout_pad": (_I, [_I]),

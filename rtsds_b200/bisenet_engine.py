@@ -69,6 +69,7 @@ class BiSeNetPlan:
         self._stats_total = 0
         self.pre_steps = []      # read the caller's input tensor (outside the CUDA graph)
         self.steps = []          # everything between the stems and the low-res logits
+        self.head_steps = []     # first nodes of the graph, before the spatial-path branch forks (the s2d stem GEMM)
         self.pack_steps = []     # weight repack / BN fold (run when parameters change)
         self.ws = None
         self.x_f32 = None
@@ -193,17 +194,28 @@ class BiSeNetPlan:
         h4, w4 = cs(h2, 3, 2, 1), cs(w2, 3, 2, 1)
         h8, w8 = cs(h4, 3, 2, 1), cs(w4, 3, 2, 1)
         self.h8, self.w8 = h8, w8
-        sp1 = self.buf(n, h2, w2, 64)
+        import os
+
+        fused_stems = self.use_tc and not self.train
+        # eval stems: "gather" = the thread-gathered im2col kernel of csrc/stem_tc.cu (default: 34 us at b=1 512x1024);
+        # "s2d" = space-to-depth pack + ONE TMA-fed tcgen05 GEMM for both stems (N = 64 + 64, K = 4 taps x 64 = 256 instead of
+        # 147): measured 9 us SLOWER per frame (pack + a GEMM with 74 % more K), kept as an A/B switch (RTSDS_STEM=s2d)
+        self.stem_mode = os.environ.get("RTSDS_STEM", "gather") if fused_stems else "direct"
+        s2d = self.stem_mode == "s2d"
+        stems = self.buf(n, h2, w2, 128) if s2d else None       # context-path map in channels 0..63, spatial-path map in 64..127
+        sp1 = stems if s2d else self.buf(n, h2, w2, 64)
         sp2 = self.buf(n, h4, w4, 128)
         # concat buffer of build_bisenet.py:153,72: 256 spatial-path channels | cx1 | cx2 (1024 wide for resnet18, 3328 for resnet101)
         ccat = m.feature_fusion_module.convblock.conv1.weight.shape[1]
         cat = self.buf(n, h8, w8, ccat)
         self.cat, self.ccat = cat, ccat
-        fused_stems = self.use_tc and not self.train
         if not fused_stems:
             self._stem(sp.convblock1.conv1, sp.convblock1.bn, sp1, 3, 2, 1)
         self._side_branch = True
-        self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
+        if s2d:
+            self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU, in_ld=128, x_off=64)
+        else:
+            self._conv(sp.convblock2.conv1, sp.convblock2.bn, sp1, (n, h2, w2, 64), sp2, 128, ACT_RELU)
         self._conv(sp.convblock3.conv1, sp.convblock3.bn, sp2, (n, h4, w4, 128), cat, ccat, ACT_RELU)
         self._side_branch = False
         # the spatial path is independent of the context path until the concat buffer is consumed: its two convs run on a
@@ -213,14 +225,19 @@ class BiSeNetPlan:
         # ---- context path: ResNet-18 (build_contextpath.py:18-29) ----
         cp = m.context_path
         ch2, cw2 = cs(H, 7, 2, 3), cs(W, 7, 2, 3)
-        cp0 = self.buf(n, ch2, cw2, 64)
-        if fused_stems:
+        cp0 = stems if s2d else self.buf(n, ch2, cw2, 64)
+        if s2d:
+            self._stem_pair_s2d(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, stems)
+        elif fused_stems:
             self._stem_pair(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, cp0, sp1)
         else:
             self._stem(cp.conv1, cp.bn1, cp0, 7, 2, 3)
         ph, pw = ops.maxpool_out_size(ch2), ops.maxpool_out_size(cw2)
         x = self.buf(n, ph, pw, 64)
-        self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
+        if s2d:
+            self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2_ld(cp0, n, ch2, cw2, 64, 128, self.dt, x))
+        else:
+            self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
         shape = (n, ph, pw, 64)
         feats = []
         # eval-mode tensor-core path: the global average pools of feature3 / feature4 (ARM pooling, context-path tail) are
@@ -324,6 +341,36 @@ class BiSeNetPlan:
             self.ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
             self.ws_side = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
             self.ws_ds = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def _stem_pair_s2d(self, conv7, bn7, conv3, bn3, y128):
+        """Both stems as ONE 4-tap implicit GEMM over the padded space-to-depth image P (csrc/conv_tc.cu rtsds_stem_s2d_*):
+        the 3x3 s2 p1 window is the centre of the 7x7 s2 p3 window, so both filters live in the same virtual
+        [cout, 64, 4, 1] weight layout and share every A tile.  The pack kernel reads the caller's image — fp32, or the RAW
+        uint8 frame with transforms.Normalize folded in — and runs eagerly; the GEMM reads only plan-owned
+        memory and is the first node of the CUDA graph."""
+        from .input_pipeline import stem_affine
+
+        n = self.n
+        oh, ow, pshape = ops.stem_s2d_shape(n, self.h, self.w)
+        P = self.buf(*pshape)
+        w2 = self.buf(128, 64, 4, 1, dtype=torch.float32)
+        wpk = self.buf(128, 4, 64)
+        scale = self.buf(128, dtype=torch.float32)
+        shift = self.buf(128, dtype=torch.float32)
+        self.pack_steps.append(lambda: (ops.stem_s2d_weight(conv7.weight, w2[:64]), ops.stem_s2d_weight(conv3.weight, w2[64:]),
+                                        ops.pack_conv_weight(w2, self.dt, wpk)))
+        self.pack_steps.append(lambda: ops.bn_fold(bn7, scale[:64], shift[:64]))
+        self.pack_steps.append(lambda: ops.bn_fold(bn3, scale[64:], shift[64:]))
+
+        def pack(x):
+            if x.dtype == torch.uint8:
+                sc, bi = stem_affine(self.model)
+                ops.stem_s2d_pack_ex(x, P, sc, bi)
+            else:
+                ops.stem_s2d_pack_ex(x, P)
+
+        self.pre_steps.append(pack)
+        self.head_steps.append(lambda: ops.stem_s2d_conv_fwd_dt(P, n, oh, ow, wpk, 128, y128, 128, self.dt, scale, shift, ACT_RELU))
 
     def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp):
         """Both stems in one tensor-core kernel (csrc/stem_tc.cu); eval mode: BN folded + ReLU."""
@@ -456,6 +503,8 @@ class BiSeNetPlan:
                 main.wait_stream(self.side_ds)
 
     def run_mid(self):
+        for s in self.head_steps:
+            s()
         if ops._lib.dry_run() or self.n_sp_steps == 0:
             self._run(self.steps, None, False)
             return

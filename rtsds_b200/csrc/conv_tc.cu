@@ -1485,12 +1485,12 @@ static void stem_s2d_problem(const void* P, int n, int oh, int ow, TapProblem* t
     t->w_ktot = 256;
 }
 
-extern "C" int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, const void* w_packed, int cout,
-                                       const float* scale, const float* shift, int act, float* stats, void* y,
-                                       int out_ld, int out_dtype, rtsds_stream_t s) {
+static int stem_s2d_conv_fwd_impl(const void* P, int p_dtype, int n, int oh, int ow, const void* w_packed, int cout,
+                                  const float* scale, const float* shift, int act, float* stats, void* y,
+                                  int out_ld, int out_dtype, rtsds_stream_t s) {
     RTSDS_REQUIRE(P && w_packed && y && n > 0 && oh > 0 && ow > 0 && cout > 0, "stem_s2d_conv_fwd: bad argument");
-    RTSDS_REQUIRE(out_dtype == RTSDS_BF16 || out_dtype == RTSDS_F32, "stem_s2d_conv_fwd: bad out_dtype");
-    RTSDS_REQUIRE(out_ld >= cout && out_ld % (out_dtype == RTSDS_BF16 ? 8 : 4) == 0, "stem_s2d_conv_fwd: out_ld");
+    RTSDS_REQUIRE(is_16bit(p_dtype) && (out_dtype == p_dtype || out_dtype == RTSDS_F32), "stem_s2d_conv_fwd: bad dtypes");
+    RTSDS_REQUIRE(out_ld >= cout && out_ld % (out_dtype != RTSDS_F32 ? 8 : 4) == 0, "stem_s2d_conv_fwd: out_ld");
     int rc = rtsds_check_device();
     if (rc != RTSDS_OK) return rc;
     TapProblem t;
@@ -1498,8 +1498,21 @@ extern "C" int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, con
     t.w = w_packed; t.cout = cout;
     t.out_sw = out_ld; t.out_sh = static_cast<long long>(ow) * out_ld; t.out_sn = t.out_sh * oh;
     t.scale = scale; t.shift = shift; t.stats = stats; t.y = y;
-    t.out_dtype = out_dtype; t.act = act; t.split_req = 1;
+    t.out_dtype = out_dtype; t.act = act; t.split_req = 1; t.in_f16 = p_dtype == RTSDS_F16;
     return tp_run(t, nullptr, 0, as_stream(s));
+}
+
+extern "C" int rtsds_stem_s2d_conv_fwd(const void* P, int n, int oh, int ow, const void* w_packed, int cout,
+                                       const float* scale, const float* shift, int act, float* stats, void* y,
+                                       int out_ld, int out_dtype, rtsds_stream_t s) {
+    return stem_s2d_conv_fwd_impl(P, RTSDS_BF16, n, oh, ow, w_packed, cout, scale, shift, act, stats, y, out_ld, out_dtype, s);
+}
+
+// P (and the packed weights) of p_dtype = RTSDS_BF16 or RTSDS_F16 (eval-mode inference).
+extern "C" int rtsds_stem_s2d_conv_fwd_dt(const void* P, int p_dtype, int n, int oh, int ow, const void* w_packed, int cout,
+                                          const float* scale, const float* shift, int act, void* y, int out_ld, int out_dtype,
+                                          rtsds_stream_t s) {
+    return stem_s2d_conv_fwd_impl(P, p_dtype, n, oh, ow, w_packed, cout, scale, shift, act, nullptr, y, out_ld, out_dtype, s);
 }
 
 extern "C" int rtsds_stem_s2d_conv_wgrad(const void* P, int n, int oh, int ow, const void* dy, int dy_ld, int cout,

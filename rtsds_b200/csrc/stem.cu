@@ -234,7 +234,7 @@ __device__ __forceinline__ void store8(float* p, const Vec8& r) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow, T* __restrict__ y, Div3 dv) {
+maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int x_ld, int oh, int ow, T* __restrict__ y, Div3 dv) {
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -255,7 +255,7 @@ maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int 
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = ox * 2 - 1 + dx;
                 if (ix < 0 || ix >= w) continue;
-                const Vec8 t = load8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + g * 8);
+                const Vec8 t = load8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * x_ld + g * 8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) m.v[j] = fmaxf(m.v[j], t.v[j]);
             }
@@ -336,7 +336,9 @@ extern "C" int rtsds_stem_conv_fwd(const float* x, const float* w_oihw, int n, i
 }
 
 static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode, void* y, uint32_t* idx,
-                            rtsds_stream_t s) {
+                            rtsds_stream_t s, int x_ld = 0) {
+    if (x_ld == 0) x_ld = c;
+    RTSDS_REQUIRE(x_ld >= c && x_ld % 8 == 0 && (idx == nullptr || x_ld == c), "maxpool: input pitch must be >= c and a multiple of 8");
     RTSDS_REQUIRE(x && y, "maxpool: NULL argument");
     RTSDS_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape (c must be a multiple of 8)");
     RTSDS_REQUIRE(dtype == RTSDS_BF16 || dtype == RTSDS_F32 || dtype == RTSDS_F16, "maxpool: bad dtype");
@@ -362,13 +364,13 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
         return check_launch("maxpool_idx_kernel");
     }
     if (dtype == RTSDS_F16)
-        maxpool_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(x), n, h, w, c, oh, ow,
+        maxpool_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(x), n, h, w, c, x_ld, oh, ow,
                                                                reinterpret_cast<__half*>(y), dv);
     else if (dtype == RTSDS_BF16)
-        maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, oh, ow,
+        maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, x_ld, oh, ow,
                                                                       reinterpret_cast<__nv_bfloat16*>(y), dv);
     else
-        maxpool_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, oh, ow,
+        maxpool_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, x_ld, oh, ow,
                                                               reinterpret_cast<float*>(y), dv);
     count_launch();
     return check_launch("maxpool_kernel");
@@ -377,6 +379,13 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
 extern "C" int rtsds_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
                                       void* y, rtsds_stream_t s) {
     return maxpool_fwd_impl(x, n, h, w, c, dtype, ceil_mode, y, nullptr, s);
+}
+
+// same, reading an input whose pixels are x_ld elements apart (a channel slice of a wider buffer: the fused stems write
+// the context-path and spatial-path maps side by side)
+extern "C" int rtsds_maxpool3x3s2_fwd_ld(const void* x, int n, int h, int w, int c, int x_ld, int dtype, int ceil_mode,
+                                         void* y, rtsds_stream_t s) {
+    return maxpool_fwd_impl(x, n, h, w, c, dtype, ceil_mode, y, nullptr, s, x_ld);
 }
 
 extern "C" int rtsds_maxpool3x3s2_fwd_idx(const void* x, int n, int h, int w, int c, int dtype, int ceil_mode,
@@ -389,11 +398,16 @@ extern "C" int rtsds_maxpool3x3s2_fwd_idx(const void* x, int n, int h, int w, in
 // ---- space-to-depth stems (see conv_tc.cu: rtsds_stem_s2d_conv_*) -------------------------------------------------
 namespace rtsds {
 
-// P[n, i, j, (py*2+px)*3 + c] = x[n, c, 2(i-2)+py, 2(j-2)+px], channels 12..15 = 0; one thread per (n, i, j).
+// P[n, i, j, (py*2+px)*3 + c] = a_c * x[n, c, 2(i-2)+py, 2(j-2)+px] + b_c inside the image, 0 outside (the conv's zero
+// padding applies to the NORMALISED image); channels 12..15 = 0; one thread per (n, i, j).  TI: float image or RAW uint8
+// frame (the uint8 -> float conversion and transforms.Normalize cost nothing extra here); TO: bf16 or fp16.
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-stem_s2d_pack_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, __nv_bfloat16* __restrict__ P) {
+stem_s2d_pack_kernel(const TI* __restrict__ x, int n, int h, int w, int hp, int wp, float a0, float a1, float a2, float b0, float b1,
+                     float b2, TO* __restrict__ P) {
     const long long total = static_cast<long long>(n) * hp * wp;
     const long long plane = static_cast<long long>(h) * w;
+    const float av[3] = {a0, a1, a2}, bv[3] = {b0, b1, b2};
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int j = static_cast<int>(idx % wp);
@@ -404,7 +418,7 @@ stem_s2d_pack_kernel(const float* __restrict__ x, int n, int h, int w, int hp, i
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        const float* xi = x + static_cast<long long>(img) * 3 * plane;
+        const TI* xi = x + static_cast<long long>(img) * 3 * plane;
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
             const int yy = y0 + py;
@@ -412,14 +426,14 @@ stem_s2d_pack_kernel(const float* __restrict__ x, int n, int h, int w, int hp, i
             const bool a = x0 >= 0 && x0 < w, b = x0 + 1 >= 0 && x0 + 1 < w;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float* row = xi + c * plane + static_cast<long long>(yy) * w;
-                if (a) v[(py * 2 + 0) * 3 + c] = __ldg(row + x0);
-                if (b) v[(py * 2 + 1) * 3 + c] = __ldg(row + x0 + 1);
+                const TI* row = xi + c * plane + static_cast<long long>(yy) * w;
+                if (a) v[(py * 2 + 0) * 3 + c] = fmaf(static_cast<float>(__ldg(row + x0)), av[c], bv[c]);
+                if (b) v[(py * 2 + 1) * 3 + c] = fmaf(static_cast<float>(__ldg(row + x0 + 1)), av[c], bv[c]);
             }
         }
         uint4 lo, hi;
-        lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-        hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = 0u; hi.w = 0u;
+        lo.x = pack_x2<TO>(v[0], v[1]); lo.y = pack_x2<TO>(v[2], v[3]); lo.z = pack_x2<TO>(v[4], v[5]); lo.w = pack_x2<TO>(v[6], v[7]);
+        hi.x = pack_x2<TO>(v[8], v[9]); hi.y = pack_x2<TO>(v[10], v[11]); hi.z = 0u; hi.w = 0u;
         uint4* dst = reinterpret_cast<uint4*>(P + idx * 16);
         dst[0] = lo; dst[1] = hi;
     }
@@ -447,16 +461,31 @@ __global__ void stem_s2d_weight_kernel(const float* __restrict__ w, int cout, in
 
 }  // namespace rtsds
 
-extern "C" int rtsds_stem_s2d_pack(const float* x, int n, int h, int w, void* P, rtsds_stream_t s) {
-    RTSDS_REQUIRE(x && P && n > 0 && h >= 2 && w >= 2 && (reinterpret_cast<uintptr_t>(P) & 15) == 0, "stem_s2d_pack: bad argument");
+extern "C" int rtsds_stem_s2d_pack_ex(const void* x, int x_is_u8, const float* scale3, const float* bias3, int n, int h, int w,
+                                      int p_dtype, void* P, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && P && n > 0 && h > 0 && w > 0, "stem_s2d_pack: bad argument");
+    RTSDS_REQUIRE(p_dtype == RTSDS_BF16 || p_dtype == RTSDS_F16, "stem_s2d_pack: P must be bf16 or fp16");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
     const long long total = static_cast<long long>(n) * (oh + 3) * (ow + 3);
     long long g = rtsds::cdiv(total, 256);
     const long long cap = 16LL * rtsds::num_sms();
     if (g > cap) g = cap;
-    rtsds::stem_s2d_pack_kernel<<<static_cast<int>(g), 256, 0, rtsds::as_stream(s)>>>(x, n, h, w, oh + 3, ow + 3, reinterpret_cast<__nv_bfloat16*>(P));
+    const float a0 = scale3 ? scale3[0] : 1.f, a1 = scale3 ? scale3[1] : 1.f, a2 = scale3 ? scale3[2] : 1.f;
+    const float b0 = bias3 ? bias3[0] : 0.f, b1 = bias3 ? bias3[1] : 0.f, b2 = bias3 ? bias3[2] : 0.f;
+    cudaStream_t st = rtsds::as_stream(s);
+    const int gi = static_cast<int>(g);
+#define S2D_PACK(TI, TO) rtsds::stem_s2d_pack_kernel<TI, TO><<<gi, 256, 0, st>>>(reinterpret_cast<const TI*>(x), n, h, w, oh + 3, ow + 3, a0, a1, a2, b0, b1, b2, reinterpret_cast<TO*>(P))
+    if (x_is_u8 && p_dtype == RTSDS_F16) S2D_PACK(uint8_t, __half);
+    else if (x_is_u8) S2D_PACK(uint8_t, __nv_bfloat16);
+    else if (p_dtype == RTSDS_F16) S2D_PACK(float, __half);
+    else S2D_PACK(float, __nv_bfloat16);
+#undef S2D_PACK
     rtsds::count_launch();
     return rtsds::check_launch("stem_s2d_pack_kernel");
+}
+
+extern "C" int rtsds_stem_s2d_pack(const float* x, int n, int h, int w, void* P, rtsds_stream_t s) {
+    return rtsds_stem_s2d_pack_ex(x, 0, nullptr, nullptr, n, h, w, RTSDS_BF16, P, s);
 }
 
 extern "C" int rtsds_stem_s2d_weight(const float* w_oihw, int cout, int k, int pad, float* w2, rtsds_stream_t s) {

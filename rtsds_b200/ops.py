@@ -404,6 +404,23 @@ def stem_s2d_pack(x: torch.Tensor, P: torch.Tensor) -> None:
     check(lib().rtsds_stem_s2d_pack(_p(x), n, h, w, _p(P), _s()), "stem_s2d_pack")
 
 
+def stem_s2d_pack_ex(x: torch.Tensor, P: torch.Tensor, scale3=None, bias3=None) -> None:
+    """x fp32 or RAW uint8 NCHW -> P (bf16 / fp16) = scale3*x + bias3 inside the image (ctypes float[3], None = 1 / 0)."""
+    n, _, h, w = x.shape
+    check(lib().rtsds_stem_s2d_pack_ex(_p(x), int(x.dtype == torch.uint8), scale3, bias3, n, h, w, dtype_code(P.dtype), _p(P), _s()),
+          "stem_s2d_pack")
+
+
+def stem_s2d_conv_fwd_dt(P, n, oh, ow, wpk, cout, y, out_ld, out_dtype, scale=None, shift=None, act=ACT_NONE) -> None:
+    check(lib().rtsds_stem_s2d_conv_fwd_dt(_p(P), dtype_code(P.dtype), n, oh, ow, _p(wpk), cout, _p(scale), _p(shift), act, _p(y),
+                                           out_ld, out_dtype, _s()), "stem_s2d_conv_fwd")
+
+
+def maxpool3x3s2_ld(x_ptr, n, h, w, c, x_ld, dtype, y: torch.Tensor, ceil_mode: bool = False) -> None:
+    """MaxPool2d(3,2,1) of a channel slice (pixel pitch x_ld) of a wider NHWC buffer."""
+    check(lib().rtsds_maxpool3x3s2_fwd_ld(_p(x_ptr), n, h, w, c, x_ld, dtype, int(ceil_mode), _p(y), _s()), "maxpool_ld")
+
+
 def stem_s2d_weight(w: torch.Tensor, w2: torch.Tensor) -> None:
     co, _, k, _ = w.shape
     check(lib().rtsds_stem_s2d_weight(_p(w.detach()), co, k, k // 2, _p(w2), _s()), "stem_s2d_weight")
