@@ -55,6 +55,8 @@ struct TcParams {
     int stages;
     int split_k;
     int cluster_reduce;           // split-K slices of one tile form a thread-block cluster and reduce through DSMEM
+    int mc;                       // 2: pairs of N tiles (cluster y) share every A tile — each CTA loads half of it and TMA multicasts
+    int mc_dw, mc_dh;             // box-coordinate step (w, h) of the second half of the A tile
     int n_tiles_n, total_tiles, tiles_per_cta;      // persistent kernel: tile id = n_tile * m_tiles + m_tile
     int halo_d, halo_rows, a_stage_bytes, halo_baseoff;   // halo mode: dilation, rows of the halo tile, bytes per A stage
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
@@ -229,6 +231,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * blockIdx.z) / p.split_k);
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (blockIdx.z + 1)) / p.split_k);
 
+    // cluster = (1, mc, split_k): rank = y + mc * z.  y pairs share A tiles (multicast), z slices share the output tile
+    const bool clustered = p.cluster_reduce || p.mc > 1;
+    const uint32_t crank = clustered ? ptx::cluster_ctarank() : 0u;
+    const uint32_t yrank = p.mc > 1 ? crank % static_cast<uint32_t>(p.mc) : 0u;
+    const uint32_t zrank = p.mc > 1 ? crank / static_cast<uint32_t>(p.mc) : crank;
+    const uint16_t pair_mask = static_cast<uint16_t>(((1u << p.mc) - 1u) << (zrank * p.mc));
+
     // ---- one-time setup ----
     if (warp == 0 && lane == 0) {
         if (p.n_taps > 0) {
@@ -237,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
         for (int i = 0; i < stages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], p.mc > 1 ? p.mc : 1);     // multicast: every CTA of the pair must release the stage
         }
         ptx::mbar_init(tmem_full_bar, 1);
         ptx::fence_barrier_init();
@@ -251,6 +260,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (p.mc > 1) ptx::cluster_sync_all();        // peers multicast into this CTA's ring and arrive on its barriers: init first
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
@@ -276,6 +286,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const int cc = kb - tap * p.kchunks;
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + B_BYTES);
+                if (p.mc > 1) {
+                    // this CTA fetches half yrank of the A tile (the maps' box is half a tile) and multicasts it to the pair;
+                    // the other half arrives from the peer, on this same barrier
+                    ptx::tma_load_4d_mc(smem_a + static_cast<size_t>(stage) * TC_A_BYTES + yrank * (TC_A_BYTES / 2),
+                                        &maps.a[p.tap_map[tap]], &full_bar[stage], cc * TC_BLOCK_K,
+                                        w0 + p.tap_dw[tap] + static_cast<int>(yrank) * p.mc_dw,
+                                        h0 + p.tap_dh[tap] + static_cast<int>(yrank) * p.mc_dh, img, pair_mask);
+                } else
                 ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES,
                                  &maps.a[p.tap_map[tap]], &full_bar[stage], cc * TC_BLOCK_K,
                                  w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
@@ -301,7 +319,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC,
                                    (kb > kb_begin || k > 0) ? 1u : 0u);
                 }
-                ptx::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
+                if (p.mc > 1) ptx::umma_commit_mc(&empty_bar[stage], pair_mask);   // releases the stage in BOTH CTAs of the pair
+                else ptx::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             if (kb_end > kb_begin) ptx::umma_commit(tmem_full_bar);   // accumulator complete
@@ -391,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (warp >= 2) {
             const int split = p.split_k;
             const int rows_per = TC_BLOCK_M / split;                   // 64 or 32
-            const int rank = static_cast<int>(ptx::cluster_ctarank());
+            const int rank = static_cast<int>(zrank);
             const int ntasks = rows_per * (BLOCK_N / 32);
             for (int task = threadIdx.x - 64; task < ntasks; task += 128) {
                 const int chunk = task / rows_per;
@@ -410,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 for (int q = 0; q < split; ++q) {                      // slice order: deterministic sum
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 t = ptx::ld_dsmem_f4(src + j, static_cast<uint32_t>(q));
+                        const float4 t = ptx::ld_dsmem_f4(src + j, yrank + static_cast<uint32_t>(q * (p.mc > 1 ? p.mc : 1)));
                         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
@@ -428,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
             if (p.gap_out) {        // partial index: (tile of the image, cluster rank) — every rank reduced its own rows
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int rank_ = static_cast<int>(ptx::cluster_ctarank());
+                const int rank_ = static_cast<int>(zrank);
                 for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
                     if (co < p.cout)
@@ -438,6 +457,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
         }
         ptx::cluster_sync_all();                    // nobody leaves while a peer still reads its shared memory
+    } else if (p.mc > 1) {
+        ptx::cluster_sync_all();                    // nobody leaves while the peer's MMA commits still arrive on its barriers
     }
 
     // ---- teardown ----
@@ -853,9 +874,10 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
-    if (p.cluster_reduce) {
+    if (p.cluster_reduce || p.mc > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = static_cast<unsigned>(p.split_k);
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = static_cast<unsigned>(p.mc > 1 ? p.mc : 1);
+        attr[na].val.clusterDim.z = static_cast<unsigned>(p.cluster_reduce ? p.split_k : 1);
         ++na;
     }
     cfg.attrs = attr;
@@ -992,6 +1014,24 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     p.tiles_h = static_cast<int>(cdiv(t.oh, p.tile_h));
     p.cout = t.cout; p.cout_pad = conv_cout_pad(t.cout);
     p.n_taps = t.n_taps; p.kchunks = t.ck / TC_BLOCK_K;
+    // ---- A-tile multicast: the N tiles of one M tile read the same activations.  With an even number of N tiles and a
+    // grid small enough that the non-persistent kernel runs it, pairs of N tiles form a cluster along y; each CTA fetches
+    // half of every A tile and TMA multicasts it to both (L2 -> SM activation traffic halves).
+    static int mc_mode = -1;
+    if (mc_mode < 0) { const char* e = getenv("RTSDS_MC"); mc_mode = e ? atoi(e) : 0; }
+    p.mc = 1;
+    {
+        const int n_tiles_ = p.cout_pad / block_n;
+        const long long tot = static_cast<long long>(t.n_img) * p.tiles_w * p.tiles_h * n_tiles_;
+        const int zdim = (split == 2 || split == 4 || split == 8) ? split : 1;       // upper bound of the split-K cluster depth
+        if (mc_mode && !halo && t.n_taps > 0 && n_tiles_ % 2 == 0 && 2 * zdim <= 8 && tot * split < 2LL * num_sms()) {
+            p.mc = 2;
+            if (p.tile_h >= 2) { p.mc_dh = p.tile_h / 2; p.mc_dw = 0; }
+            else { p.mc_dh = 0; p.mc_dw = p.tile_w / 2; }
+        }
+    }
+    const int box_w = p.mc > 1 && p.tile_h < 2 ? p.tile_w / 2 : p.tile_w;
+    const int box_h = p.mc > 1 && p.tile_h >= 2 ? p.tile_h / 2 : p.tile_h;
     p.out_sn = t.out_sn; p.out_sh = t.out_sh; p.out_sw = t.out_sw;
     p.res_sn = t.res_sn; p.res_sh = t.res_sh; p.res_sw = t.res_sw;
     p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.y = t.y;
@@ -1002,7 +1042,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     for (int i = 0; i < 4; ++i) {
         if (!t.view[i].used) continue;
         int rc = make_act_map(&maps.a[i], t.view[i].base, t.c_extent, t.view[i].wd, t.view[i].hd, t.n_img, t.view[i].sw,
-                              t.view[i].sh, t.view[i].sn, p.tile_w, p.tile_h);
+                              t.view[i].sh, t.view[i].sn, box_w, box_h);
         if (rc != RTSDS_OK) return rc;
         if (first_used < 0) first_used = i;
     }

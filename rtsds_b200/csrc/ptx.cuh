@@ -85,6 +85,17 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// Multicast form: the box lands at the SAME shared-memory offset in every CTA of `cta_mask` (cluster ranks) and completes
+// tx bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+
 // TMA store shared -> global (bulk async-group completion) and its group bookkeeping
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -158,6 +169,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
+                 : "memory");
+}
+// Same, arriving on the mbarrier at this offset in EVERY CTA of cta_mask (a stage that a multicast TMA load filled in
+// several CTAs may only be overwritten once all of them have consumed it).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread

@@ -4,6 +4,8 @@ tcgen05 path: operands are bf16, accumulation fp32 -> compare with the oracle on
 bf16-rounded operands; tolerance 2e-2 rel for bf16 outputs (BASELINE.json), much
 tighter when the output is kept in fp32.  SIMT fp32 path: 1e-4.
 """
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -352,3 +354,17 @@ def test_conv_tc_many_tiles_forward_and_dgrad(cuda, case):
     rdx, rdw = _bwd_ref(x, wt, dy, stride, pad, dil, True)
     assert rel_err(dx, rdx) < 2e-4, rel_err(dx, rdx)
     assert rel_err(dw, rdw) < 2e-4, rel_err(dw, rdw)
+
+
+def test_conv_tc_a_tile_multicast_switch(cuda):
+    """RTSDS_MC=1 (read once per process): pairs of N tiles of one M tile form a cluster and TMA-multicast each other's
+    half of every A tile.  Measured slower than independent CTAs on B200 (DESIGN.md §Kernels), so it is off by default;
+    the path stays correct: the tensor-core forward / split-K / backward cases re-run in a child process with it on."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, RTSDS_MC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "raw_fp32_out or split_k or block_n_variants or epilogue_bn or test_conv_tc_backward"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
