@@ -156,6 +156,12 @@ size_t rtsds_conv2d_tc_workspace_bytes(const RtsdsConvDesc* d);
 int rtsds_conv_cout_pad(int cout);
 /* process-wide tuning override for experiments: block_n in {0=auto,32,64,128}, stages (0=auto). */
 void rtsds_conv2d_tc_tune(int block_n, int stages);
+/* debug: while `buf` (device memory, 256 bytes per CTA of the largest grid) is non-NULL, every non-persistent conv_tc launch
+ * writes per-CTA time stamps into it (globaltimer at entry/exit, clock64 at: entry, setup done, dependency resolved, last TMA
+ * issued, first operands landed, last MMA issued, accumulator complete, own epilogue done, exit).  tools/conv_timeline.py. */
+void rtsds_debug_conv_trace(void* buf);
+/* debug: 4 clock64 stamps per block of arm_gate_resize (64 bytes per block): start, pooled vector ready, gates ready, done. */
+void rtsds_debug_arm_trace(void* buf);
 
 /* CUDA-core implicit GEMM with fp32 accumulation; any cin; x/w dtype per
  * d->in_dtype.  This is the fp32 check mode (and a bf16 cross-check). */

@@ -92,6 +92,8 @@ SIGNATURES = {
     "rtsds_label_resize_clamp": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
     "rtsds_conv_cout_pad": (_I, [_I]),
     "rtsds_conv2d_tc_tune": (None, [_I, _I]),
+    "rtsds_debug_conv_trace": (None, [_P]),
+    "rtsds_debug_arm_trace": (None, [_P]),
     "rtsds_conv2d_tc_fwd": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "rtsds_conv2d_tc_gap_parts": (_I, [_CD]),
     "rtsds_conv2d_tc_fwd_gap": (_I, [_CD, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

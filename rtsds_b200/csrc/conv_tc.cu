@@ -57,6 +57,10 @@ struct TcParams {
     int cluster_reduce;           // split-K slices of one tile form a thread-block cluster and reduce through DSMEM
     int mc;                       // 2: pairs of N tiles (cluster y) share every A tile — each CTA loads half of it and TMA multicasts
     int mc_dw, mc_dh;             // box-coordinate step (w, h) of the second half of the A tile
+    int res_pre;                  // the 16-bit residual row may be prefetched whole (Cout is a multiple of the N tile)
+    int rbuf_bytes;               // cluster split-K: receive buffer [split][128/split rows][BLOCK_N+4] fp32 after the TMA ring
+    int b_early;                  // weight tiles of the first ring pass are fetched BEFORE the programmatic-dependency wait
+    unsigned long long* trace;    // debug: 16 time stamps per CTA (rtsds_debug_conv_trace), NULL in production
     int n_tiles_n, total_tiles, tiles_per_cta;      // persistent kernel: tile id = n_tile * m_tiles + m_tile
     int halo_d, halo_rows, a_stage_bytes, halo_baseoff;   // halo mode: dilation, rows of the halo tile, bytes per A stage
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
@@ -94,10 +98,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 // Epilogue of one 32-column chunk of an accumulator row: optional train-mode BatchNorm statistics of the raw value,
 // scale/shift (folded BatchNorm or bias), residual add, activation, 16-byte stores.  Shared by both conv kernels.
+// rpre != NULL: the 16-bit residual of this row (all BLOCK_N channels, 16-byte pieces) was fetched into registers while the
+// main loop ran, instead of paying its latency here.
 template <int BLOCK_N>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[32], int c0, int n0, bool valid, long long out_off,
                                                   long long res_off, const float* s_scale, const float* s_shift, float* s_stats,
-                                                  int lane) {
+                                                  int lane, const uint4* rpre = nullptr) {
     const int co0 = n0 + c0;
             if (p.stats) {
             float t[32];
@@ -116,22 +122,49 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
         const bool f16 = p.out_dtype == RTSDS_F16;
         if (valid) {
             // scale/shift (folded BatchNorm or bias) -> + residual -> activation, all in registers
+            // (the four epilogue warps sit on four different schedulers, one warp each: nothing hides latency, so every
+            // per-element branch or scalar shared load costs its full latency — uniform switches are hoisted out of the
+            // element loops and the per-channel constants come in as 16-byte broadcast loads)
+            {
+                const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                for (int g = 0; g < 8; ++g) {
+                    const float4 a = sc4[g], b = sh4[g];
+                    v[4 * g + 0] = fmaf(v[4 * g + 0], a.x, b.x); v[4 * g + 1] = fmaf(v[4 * g + 1], a.y, b.y);
+                    v[4 * g + 2] = fmaf(v[4 * g + 2], a.z, b.z); v[4 * g + 3] = fmaf(v[4 * g + 3], a.w, b.w);
+                }
+            }
+            if (p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 16] = clock64();
             if (p.residual) {
-                if (out16) {
-                    const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + res_off + co0;
-                    if (full) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res);
+                if (out16 && full) {
+                    uint4 rv[4];
+                    if (rpre) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) rv[g] = rpre[c0 / 8 + g];
+                    } else {
+                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + res_off + co0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);            // four independent loads in flight
+                    }
+                    if (f16) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            uint4 rv = __ldg(rp + g);
-                            float2 a = unpack_16x2(rv.x, f16), b = unpack_16x2(rv.y, f16);
-                            float2 c = unpack_16x2(rv.z, f16), d = unpack_16x2(rv.w, f16);
+                            const float2 a = unpack_f16x2(rv[g].x), b = unpack_f16x2(rv[g].y), c = unpack_f16x2(rv[g].z), d = unpack_f16x2(rv[g].w);
                             v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
                             v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
                         }
                     } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float2 a = unpack_bf16x2(rv[g].x), b = unpack_bf16x2(rv[g].y), c = unpack_bf16x2(rv[g].z), d = unpack_bf16x2(rv[g].w);
+                            v[g * 8 + 0] += a.x; v[g * 8 + 1] += a.y; v[g * 8 + 2] += b.x; v[g * 8 + 3] += b.y;
+                            v[g * 8 + 4] += c.x; v[g * 8 + 5] += c.y; v[g * 8 + 6] += d.x; v[g * 8 + 7] += d.y;
+                        }
+                    }
+                } else if (out16) {
+                    const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + res_off + co0;
+                    {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (co0 + j < p.cout) v[j] += ld_16(res, j, f16);
@@ -151,8 +184,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
                     }
                 }
             }
+            if (p.act == RTSDS_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            } else if (p.act == RTSDS_ACT_LRELU) {
+                const float slope = p.slope;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * slope;
+            }
+            if (p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 17] = clock64();
         }
         if (p.gap_out) {
             // global average pool of THIS layer's output fused into its epilogue (ARM AdaptiveAvgPool2d(1) / context-path
@@ -164,19 +204,27 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             s_stats[(threadIdx.x >> 5 & 3) * BLOCK_N + c0 + lane] += s1;      // this warp's own slot: fixed summation order
         }
         if (valid) {
-            if (out16) {
-                uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + out_off + co0;
-                if (full) {
+            if (out16 && full) {
+                uint4 o[4];
+                if (f16) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 o;
-                        o.x = pack_16x2(v[g * 8 + 0], v[g * 8 + 1], f16);
-                        o.y = pack_16x2(v[g * 8 + 2], v[g * 8 + 3], f16);
-                        o.z = pack_16x2(v[g * 8 + 4], v[g * 8 + 5], f16);
-                        o.w = pack_16x2(v[g * 8 + 6], v[g * 8 + 7], f16);
-                        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                        o[g].x = pack_f16x2(v[g * 8 + 0], v[g * 8 + 1]); o[g].y = pack_f16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        o[g].z = pack_f16x2(v[g * 8 + 4], v[g * 8 + 5]); o[g].w = pack_f16x2(v[g * 8 + 6], v[g * 8 + 7]);
                     }
                 } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        o[g].x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o[g].y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        o[g].z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o[g].w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y) + out_off + co0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dst[g] = o[g];
+            } else if (out16) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + out_off + co0;
+                {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (co0 + j < p.cout) st_16(dst, j, v[j], f16);
@@ -208,7 +256,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int stages = p.stages;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + static_cast<size_t>(stages) * TC_A_BYTES;
-    float* s_scale = reinterpret_cast<float*>(smem_b + static_cast<size_t>(stages) * B_BYTES);
+    float* rbuf = reinterpret_cast<float*>(smem_b + static_cast<size_t>(stages) * B_BYTES);
+    float* s_scale = reinterpret_cast<float*>(smem_b + static_cast<size_t>(stages) * B_BYTES + p.rbuf_bytes);
     float* s_shift = s_scale + BLOCK_N;
     float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N] BatchNorm sums, or [4 warps][BLOCK_N] fused-pool slots
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 4 * BLOCK_N);
@@ -230,6 +279,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int kb_total = p.n_taps * p.kchunks;
     const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * blockIdx.z) / p.split_k);
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (blockIdx.z + 1)) / p.split_k);
+    unsigned long long* trace = p.trace ? p.trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    if (trace && threadIdx.x == 0) { trace[0] = ptx::globaltimer(); trace[1] = clock64(); }
 
     // cluster = (1, mc, split_k): rank = y + mc * z.  y pairs share A tiles (multicast), z slices share the output tile
     const bool clustered = p.cluster_reduce || p.mc > 1;
@@ -260,13 +311,32 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (p.mc > 1) ptx::cluster_sync_all();        // peers multicast into this CTA's ring and arrive on its barriers: init first
+    // peers write into this CTA's shared memory (multicast TMA / pushed split-K partials): it must exist, i.e. the CTA must
+    // have started.  Multicast needs that before the first load (full sync); the pushes only before the epilogue, so there
+    // the arrive is here and every thread waits at the end of its main-loop role (long since complete by then).
+    const bool started_barrier = p.cluster_reduce && p.mc <= 1;
+    if (p.mc > 1) ptx::cluster_sync_all();
+    else if (started_barrier) ptx::cluster_arrive();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
     // tail of the previous kernel in the stream; global memory is only touched after the dependency has resolved.
+    // The weights do not depend on the previous kernel: the producer thread requests the B tiles of the first ring pass
+    // BEFORE waiting, so their L2/HBM latency overlaps the predecessor's tail as well.
+    const int kb_pre = (p.b_early && p.mc <= 1) ? min(stages, kb_end - kb_begin) : 0;
+    if (trace && threadIdx.x == 0) trace[2] = clock64();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kb_pre; ++i) {
+            const int kb = kb_begin + i;
+            const int tap = kb / p.kchunks;
+            const int cc = kb - tap * p.kchunks;
+            ptx::mbar_expect_tx(&full_bar[i], TC_A_BYTES + B_BYTES);
+            ptx::tma_load_2d(smem_b + static_cast<size_t>(i) * B_BYTES, &maps.b, &full_bar[i], (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (trace && threadIdx.x == 0) trace[3] = clock64();
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < BLOCK_N; i += TC_THREADS - 64) {
             const int co = n0 + i;
@@ -284,8 +354,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 const int tap = kb / p.kchunks;
                 const int cc = kb - tap * p.kchunks;
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + B_BYTES);
+                const bool pre = kb - kb_begin < kb_pre;          // first ring pass: stage empty by construction, B already in flight
+                if (!pre) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + B_BYTES);
+                }
                 if (p.mc > 1) {
                     // this CTA fetches half yrank of the A tile (the maps' box is half a tile) and multicasts it to the pair;
                     // the other half arrives from the peer, on this same barrier
@@ -297,12 +370,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES,
                                  &maps.a[p.tap_map[tap]], &full_bar[stage], cc * TC_BLOCK_K,
                                  w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
-                ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
-                                 (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
+                if (!pre)
+                    ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
+                                     (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
+            if (trace) trace[4] = clock64();
         }
         __syncwarp();
+        if (started_barrier) ptx::cluster_wait();
     } else if (warp == 1) {
         // =================== MMA issuer ===================
         if (lane == 0) {
@@ -311,6 +387,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
+                if (trace && kb == kb_begin) trace[5] = clock64();
                 const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + static_cast<size_t>(stage) * TC_A_BYTES));
                 const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(stage) * B_BYTES));
 #pragma unroll
@@ -324,8 +401,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             if (kb_end > kb_begin) ptx::umma_commit(tmem_full_bar);   // accumulator complete
+            if (trace) trace[6] = clock64();
         }
         __syncwarp();
+        if (started_barrier) ptx::cluster_wait();
     } else {
         // =================== epilogue (4 warps, 128 TMEM lanes) ===================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -335,10 +414,22 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int ow = w0 + (row - hl * p.tile_w);
         const bool valid = (oh < p.oh) && (ow < p.ow);
         const bool have_acc = kb_end > kb_begin;     // a tap-less problem (e.g. odd pixels of a 1x1 s2 dgrad) is all zeros
+        // residual row -> registers while the main loop runs (narrow tiles only: 16 bytes x BLOCK_N/8 per thread)
+        constexpr bool RES_PRE = BLOCK_N <= 64;
+        uint4 rres[RES_PRE ? BLOCK_N / 8 : 1];
+        const bool res_pre = RES_PRE && p.residual && p.res_pre && valid && p.split_k == 1;
+        if (res_pre) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + img * p.res_sn + oh * p.res_sh +
+                                                            ow * p.res_sw + n0);
+#pragma unroll
+            for (int g = 0; g < (RES_PRE ? BLOCK_N / 8 : 1); ++g) rres[g] = __ldg(rp + g);
+        }
         if (have_acc) {
             ptx::mbar_wait(tmem_full_bar, 0);
             ptx::tc_fence_after();
         }
+        if (started_barrier) ptx::cluster_wait();
+        if (trace && threadIdx.x == 64) trace[7] = clock64();
 
         const long long m_total = static_cast<long long>(p.n_img) * p.oh * p.ow;
         const long long pix_lin = (static_cast<long long>(img) * p.oh + oh) * p.ow + ow;
@@ -355,16 +446,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
+            if (trace && threadIdx.x == 64) trace[c0 == 0 ? 13 : 15] = clock64();
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int co0 = n0 + c0;
 
-            if (p.cluster_reduce) {      // this CTA's fp32 partial row goes to its own shared memory (the TMA ring is idle now)
-                float* dst = reinterpret_cast<float*>(smem) + row * (BLOCK_N + 4) + c0;
+            if (p.cluster_reduce) {
+                // PUSH: this fp32 partial row goes straight into the receive buffer of the CTA that owns the row
+                // (slot = this CTA's split rank).  Remote stores are fire-and-forget: no DSMEM load latency anywhere.
+                const int rows_per = TC_BLOCK_M / p.split_k;
+                const int owner = row / rows_per;
+                const float* dst = rbuf + (static_cast<int>(zrank) * rows_per + (row - owner * rows_per)) * (BLOCK_N + 4) + c0;
+                const uint32_t ra = ptx::mapa_u32(dst, yrank + static_cast<uint32_t>(owner * (p.mc > 1 ? p.mc : 1)));
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) ptx::st_dsmem_f4(ra + j * 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 continue;
             }
             if (p.split_k > 1) {
@@ -377,7 +473,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 continue;
             }
 
-            tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
+            tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr);
+            if (trace && threadIdx.x == 64 && c0 == 0) trace[14] = clock64();
         }
         if (p.stats && p.split_k == 1) {
             // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
@@ -402,19 +499,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
     }
 
+    if (trace && threadIdx.x == 64) trace[8] = clock64();
     if (p.cluster_reduce) {
-        // ---- split-K reduction inside the cluster: the `split` CTAs of one output tile hold their partial tiles in
-        // shared memory; CTA r sums rows [r*128/split, (r+1)*128/split) over all ranks through DSMEM and runs the
-        // epilogue on them.  No workspace round trip through L2, no finish kernel.
-        ptx::cluster_sync_all();                    // every partial tile is written
+        // ---- split-K reduction inside the cluster: every CTA has pushed its partial rows into the receive buffer of the
+        // rank that owns them; CTA r now sums rows [r*128/split, (r+1)*128/split) over the `split` slots of its OWN shared
+        // memory (slot order = deterministic) and runs the epilogue on them.  No workspace round trip through L2, no
+        // finish kernel, no remote loads; nobody touches a peer's memory after this barrier, so CTAs exit independently.
+        ptx::cluster_sync_all();
+        if (trace && threadIdx.x == 64) trace[11] = clock64();
         if (warp >= 2) {
             const int split = p.split_k;
-            const int rows_per = TC_BLOCK_M / split;                   // 64 or 32
+            const int rows_per = TC_BLOCK_M / split;                   // 64, 32 or 16
             const int rank = static_cast<int>(zrank);
             const int ntasks = rows_per * (BLOCK_N / 32);
             for (int task = threadIdx.x - 64; task < ntasks; task += 128) {
                 const int chunk = task / rows_per;
-                const int row = rank * rows_per + (task - chunk * rows_per);
+                const int lrow = task - chunk * rows_per;
+                const int row = rank * rows_per + lrow;
                 const int c0 = chunk * 32;
                 const int hl = row / p.tile_w;
                 const int oh = h0 + hl;
@@ -422,15 +523,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const bool valid = (oh < p.oh) && (ow < p.ow);
                 const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
                 const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
-                const float* src = reinterpret_cast<const float*>(smem) + row * (BLOCK_N + 4) + c0;
+                const float* src = rbuf + lrow * (BLOCK_N + 4) + c0;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 for (int q = 0; q < split; ++q) {                      // slice order: deterministic sum
+                    const float4* sq = reinterpret_cast<const float4*>(src + q * rows_per * (BLOCK_N + 4));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 t = ptx::ld_dsmem_f4(src + j, yrank + static_cast<uint32_t>(q * (p.mc > 1 ? p.mc : 1)));
-                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = sq[j];
+                        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                     }
                 }
                 tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
@@ -456,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
             }
         }
-        ptx::cluster_sync_all();                    // nobody leaves while a peer still reads its shared memory
+        if (trace && threadIdx.x == 64) trace[12] = clock64();
     } else if (p.mc > 1) {
         ptx::cluster_sync_all();                    // nobody leaves while the peer's MMA commits still arrive on its barriers
     }
@@ -464,6 +566,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ---- teardown ----
     ptx::tc_fence_before();
     __syncthreads();
+    if (trace && threadIdx.x == 64) { trace[9] = clock64(); trace[10] = ptx::globaltimer(); }
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -845,14 +948,14 @@ static void pick_tile(int oh, int ow, int* tw, int* th) {
     }
 }
 
-static size_t tc_smem_bytes(int block_n, int stages) {
-    return 1024 + static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) + 6 * block_n * 4 +
+static size_t tc_smem_bytes(int block_n, int stages, size_t rbuf = 0) {
+    return 1024 + static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) + rbuf + 6 * block_n * 4 +
            (2 * stages + 1) * 8 + 16;
 }
 
 template <int BLOCK_N>
 static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st) {
-    size_t smem = tc_smem_bytes(BLOCK_N, p.stages);
+    size_t smem = tc_smem_bytes(BLOCK_N, p.stages, p.rbuf_bytes);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -927,6 +1030,10 @@ extern "C" int rtsds_conv_cout_pad(int cout) { return conv_cout_pad(cout); }
 // Tuning knobs (process-wide, set from Python for experiments): block_n in {0=auto,32,64,128},
 // stages 0=auto.
 static int g_force_block_n = 0, g_force_stages = 0;
+static unsigned long long* g_tc_trace = nullptr;
+// Debug: subsequent non-persistent conv_tc launches write 16 stamps per CTA into `buf` (device memory, >= 16*8*CTAs bytes);
+// NULL switches it off.  tools/conv_timeline.py reads them.
+extern "C" void rtsds_debug_conv_trace(void* buf) { g_tc_trace = reinterpret_cast<unsigned long long*>(buf); }
 extern "C" void rtsds_conv2d_tc_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
 
 static int tc_pick_block_n(int cout_pad, long long m_tiles) {
@@ -1078,7 +1185,12 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     const int kb_per = kb_total / split;
     // a grid that fits in one wave leaves one CTA per SM: use all of its shared memory as pipeline depth (the K loop of
     // these small problems is TMA-latency bound), instead of keeping room for a second resident CTA
-    if (!g_force_stages && m_tiles * n_tiles * split <= num_sms()) stages = 12;
+    static int wave_stages = -1, b_early = -1;
+    if (wave_stages < 0) { const char* e = getenv("RTSDS_TC_WAVE_STAGES"); wave_stages = e ? atoi(e) : 12; }
+    if (b_early < 0) { const char* e = getenv("RTSDS_TC_B_EARLY"); b_early = e ? atoi(e) : 1; }
+    p.b_early = b_early;
+    p.trace = g_tc_trace;
+    if (!g_force_stages && m_tiles * n_tiles * split <= num_sms()) stages = wave_stages;
     if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
     while (tc_smem_bytes(block_n, stages) > 227 * 1024) --stages;
     // split-K of 2 or 4: the slices of a tile run as one thread-block cluster and reduce through distributed shared memory
@@ -1087,15 +1199,17 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     // (split 8: 16 rows per rank — a warp of the reduction then spans two 32-column chunks, which the per-warp BatchNorm /
     // pool sums do not allow; plain epilogues only)
     if (cluster_mode && (split == 2 || split == 4 || (split == 8 && !t.stats && !t.gap_out)) && block_n >= 32) {
-        const size_t need = static_cast<size_t>(TC_BLOCK_M) * (block_n + 4) * sizeof(float);     // partial tile overlays the ring
-        while (static_cast<size_t>(stages) * (TC_A_BYTES + block_n * TC_BLOCK_K * 2) < need) ++stages;
-        if (tc_smem_bytes(block_n, stages) <= 227 * 1024) p.cluster_reduce = 1;
+        // receive buffer for the pushed partial rows (NOT an overlay of the ring: peers write it while this CTA still streams)
+        const size_t need = static_cast<size_t>(TC_BLOCK_M) * (block_n + 4) * sizeof(float);
+        while (stages > 2 && tc_smem_bytes(block_n, stages, need) > 227 * 1024) --stages;
+        if (tc_smem_bytes(block_n, stages, need) <= 227 * 1024) { p.cluster_reduce = 1; p.rbuf_bytes = static_cast<int>(need); }
     }
     if (t.gap_out && split > 1 && !p.cluster_reduce) {
         set_error("conv_tc: the fused global pool needs split_k 1, 2 or 4 (thread-block-cluster reduction); got %d", split);
         return RTSDS_EUNSUP;
     }
     p.stages = stages;
+    p.res_pre = t.residual && t.out_dtype != RTSDS_F32 && t.cout % block_n == 0;
     RTSDS_REQUIRE(m_tiles <= 0x7fffffffLL, "conv_tc: too many tiles");
 
     // many tiles, no split-K: persistent CTAs (resident weights when they fit, double-buffered accumulators)

@@ -371,6 +371,8 @@ ffm_head_kernel(const T* __restrict__ f, int f_ld, const float* __restrict__ poo
     }
 }
 
+static unsigned long long* g_arm_trace = nullptr;
+
 // ---------------------------------------------------------------- ARM gate + gated bilinear resize, both ARMs, one launch
 // Eval mode (folded BatchNorm).  A block owns 32 channels of one ARM and a chunk of destination pixels: it first evaluates
 // ITS 32 gates  g[n,c] = sigmoid(BN(W[c,:] . pooled[n,:] + b[c])) (* pooled[n,c] for the `cx2 * tail` of
@@ -383,8 +385,15 @@ struct ArmSide {
 };
 template <typename T>
 __global__ void __launch_bounds__(256)
-arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, int oh, int ow, T* __restrict__ dst, int dst_ld) {
+arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, int oh, int ow, T* __restrict__ dst, int dst_ld,
+                       unsigned long long* trace) {
     __shared__ float s_gate[32];
+    if (trace && threadIdx.x == 0) {
+        trace[blockIdx.x * 8 + 0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        trace[blockIdx.x * 8 + 4] = gt;
+    }
     extern __shared__ float s_pool[];                                     // [c]: pooled vector of the current image
     const bool second = static_cast<int>(blockIdx.x) >= blocks0;
     const ArmSide& a = second ? a1 : a0;
@@ -398,23 +407,40 @@ arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, i
     const T* src = reinterpret_cast<const T*>(a.src);
     for (int img = 0; img < n; ++img) {
         // pooled[n][parts][c]: per-CTA partial means of the producing conv's epilogue, added in part order (deterministic)
+        // (loads batched eight at a time: a plain loop is one L2 round trip per part, 16-32 of them back to back)
         for (int ch = threadIdx.x; ch < a.c; ch += 256) {
             const float* pq = a.pooled + static_cast<long long>(img) * a.parts * a.c + ch;
             float acc = 0.f;
-            for (int q = 0; q < a.parts; ++q) acc += pq[static_cast<long long>(q) * a.c];
+            int q = 0;
+            for (; q + 8 <= a.parts; q += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(pq + static_cast<long long>(q + j) * a.c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc += v[j];
+            }
+            for (; q < a.parts; ++q) acc += __ldg(pq + static_cast<long long>(q) * a.c);
             s_pool[ch] = acc;
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[blockIdx.x * 8 + 1] = clock64();
         const float* pp = s_pool;
         {   // 32 gates, 8 threads each: every thread sums a stride-8 slice of its dot product, shuffles combine the slices
             const int gi = threadIdx.x >> 3, sub = threadIdx.x & 7;
             const int co = cg * 32 + gi;
             const float* wr = a.w + static_cast<long long>(co) * a.c;
             float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-            for (int i = sub; i < a.c; i += 16) {
-                acc0 = fmaf(__ldg(wr + i), pp[i], acc0);
-                acc1 = fmaf(__ldg(wr + i + 8), pp[i + 8], acc1);          // c is a multiple of 32
+            for (int i0 = sub; i0 < a.c; i0 += 128) {                        // 16 weights in flight per thread (c % 32 == 0)
+                float wv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) wv[j] = (i0 + 8 * j < a.c) ? __ldg(wr + i0 + 8 * j) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    if (i0 + 8 * j < a.c) {                               // pairs stay together: c is a multiple of 16
+                        acc0 = fmaf(wv[j], pp[i0 + 8 * j], acc0);
+                        acc1 = fmaf(wv[j + 1], pp[i0 + 8 * j + 8], acc1);
+                    }
+                }
             }
             float acc = acc0 + acc1;
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -430,26 +456,48 @@ arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, i
             }
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[blockIdx.x * 8 + 2] = clock64();
         const int g8 = threadIdx.x & 3;                                   // 8-channel group inside the block's 32 channels
         float gv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = s_gate[g8 * 8 + j];
         const T* sb = src + static_cast<long long>(img) * a.h * a.w_ * a.c + cg * 32 + g8 * 8;
         T* db = dst + static_cast<long long>(img) * npix * dst_ld + a.coff + cg * 32 + g8 * 8;
-        for (int p = p_begin + (threadIdx.x >> 2); p < p_end; p += 64) {
+        // two pixels per thread and trip: 8 independent 16-byte gathers in flight instead of 4
+        for (int p = p_begin + (threadIdx.x >> 2); p < p_end; p += 128) {
+            const int pb = p + 64;
+            const bool two = pb < p_end;
             const int oy = p / ow, ox = p - oy * ow;
+            const int oyb = two ? pb / ow : oy, oxb = two ? pb - oyb * ow : ox;
             const Lerp ly = lerp_src(oy, rh, a.h), lx = lerp_src(ox, rw, a.w_);
+            const Lerp lyb = lerp_src(oyb, rh, a.h), lxb = lerp_src(oxb, rw, a.w_);
             const V8 p00 = ld8(sb + (static_cast<long long>(ly.i0) * a.w_ + lx.i0) * a.c);
             const V8 p01 = ld8(sb + (static_cast<long long>(ly.i0) * a.w_ + lx.i1) * a.c);
             const V8 p10 = ld8(sb + (static_cast<long long>(ly.i1) * a.w_ + lx.i0) * a.c);
             const V8 p11 = ld8(sb + (static_cast<long long>(ly.i1) * a.w_ + lx.i1) * a.c);
+            const V8 q00 = ld8(sb + (static_cast<long long>(lyb.i0) * a.w_ + lxb.i0) * a.c);
+            const V8 q01 = ld8(sb + (static_cast<long long>(lyb.i0) * a.w_ + lxb.i1) * a.c);
+            const V8 q10 = ld8(sb + (static_cast<long long>(lyb.i1) * a.w_ + lxb.i0) * a.c);
+            const V8 q11 = ld8(sb + (static_cast<long long>(lyb.i1) * a.w_ + lxb.i1) * a.c);
             V8 o;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 o.v[j] = (ly.l0 * (lx.l0 * p00.v[j] + lx.l1 * p01.v[j]) + ly.l1 * (lx.l0 * p10.v[j] + lx.l1 * p11.v[j])) * gv[j];
             st8(db + static_cast<long long>(p) * dst_ld, o);
+            if (two) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o.v[j] = (lyb.l0 * (lxb.l0 * q00.v[j] + lxb.l1 * q01.v[j]) + lyb.l1 * (lxb.l0 * q10.v[j] + lxb.l1 * q11.v[j])) * gv[j];
+                st8(db + static_cast<long long>(pb) * dst_ld, o);
+            }
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) {
+            trace[blockIdx.x * 8 + 3] = clock64();
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            trace[blockIdx.x * 8 + 5] = gt;
+        }
     }
 }
 
@@ -462,16 +510,31 @@ __global__ void __launch_bounds__(FHR_THREADS)
 ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __restrict__ pooled, int h, int w, int c,
                        const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                        const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
-                       float* attn_out, int oh, int ow, float rh, float rw, int max_rows, int parts, float* __restrict__ out) {
+                       float* attn_out, int oh, int ow, float rh, float rw, int max_rows, int parts, float* __restrict__ out,
+                       unsigned long long* trace) {
     extern __shared__ float s_z[];                                        // [rows][w][c]
+    if (trace && threadIdx.x == 0) trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 0] = clock64();
     __shared__ float s_h[FFM_MAX_C], s_a[FFM_MAX_C], s_b[FFM_MAX_C], s_p[8][FFM_MAX_C], s_pool[FFM_MAX_C];
-    __shared__ float s_w[FFM_MAX_C * FFM_MAX_C];
+    __shared__ float s_w[FFM_MAX_C * FFM_MAX_C], s_w1[FFM_MAX_C * FFM_MAX_C], s_w2[FFM_MAX_C * FFM_MAX_C];
+    __shared__ float s_b1[FFM_MAX_C], s_b2[FFM_MAX_C];
     const int img = blockIdx.y, t = threadIdx.x;
-    {   // pooled[n][parts][c]: partial means of the producer (one per block of the gather), added in a fixed order
+    {   // every block repeats this prologue, and it is a chain of dependent global-memory round trips if done naively
+        // (2 x c serial weight loads per thread): all operands come in with ONE round trip, spread over the block
+        for (int i = t; i < c * c; i += FHR_THREADS) { s_w1[i] = __ldg(w1 + i); s_w2[i] = __ldg(w2 + i); s_w[i] = __ldg(wc + i); }
+        if (t < c) { s_b1[t] = __ldg(b1 + t); s_b2[t] = __ldg(b2 + t); s_b[t] = bc ? __ldg(bc + t) : 0.f; }
+        // pooled[n][parts][c]: partial means of the producer (one per block of the gather), added in a fixed order
         const int ch = t & 31, stripe = t >> 5;
         float acc = 0.f;
-        if (ch < c)
-            for (int q = stripe; q < parts; q += 8) acc += pooled[(static_cast<long long>(img) * parts + q) * c + ch];
+        if (ch < c) {
+            const float* pq = pooled + static_cast<long long>(img) * parts * c + ch;
+            int q = stripe;
+            for (; q + 24 < parts; q += 32) {                                  // four independent loads in flight
+                const float v0 = __ldg(pq + static_cast<long long>(q) * c), v1 = __ldg(pq + static_cast<long long>(q + 8) * c);
+                const float v2 = __ldg(pq + static_cast<long long>(q + 16) * c), v3 = __ldg(pq + static_cast<long long>(q + 24) * c);
+                acc += v0; acc += v1; acc += v2; acc += v3;
+            }
+            for (; q < parts; q += 8) acc += __ldg(pq + static_cast<long long>(q) * c);
+        }
         s_p[stripe][ch] = acc;
         __syncthreads();
         if (t < c) s_pool[t] = ((s_p[0][t] + s_p[1][t]) + (s_p[2][t] + s_p[3][t])) + ((s_p[4][t] + s_p[5][t]) + (s_p[6][t] + s_p[7][t]));
@@ -479,21 +542,21 @@ ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __res
     }
     const float* pp = s_pool;
     if (t < c) {
-        float acc = b1[t];
-        for (int k = 0; k < c; ++k) acc = fmaf(w1[t * c + k], pp[k], acc);
+        float acc = s_b1[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(s_w1[t * c + k], pp[k], acc);
         s_h[t] = fmaxf(acc, 0.f);
     }
     __syncthreads();
     if (t < c) {
-        float acc = b2[t];
-        for (int k = 0; k < c; ++k) acc = fmaf(w2[t * c + k], s_h[k], acc);
+        float acc = s_b2[t];
+        for (int k = 0; k < c; ++k) acc = fmaf(s_w2[t * c + k], s_h[k], acc);
         const float a = 1.f / (1.f + expf(-acc));
         s_a[t] = a;
-        s_b[t] = bc ? bc[t] : 0.f;
         if (attn_out && blockIdx.x == 0) attn_out[static_cast<long long>(img) * c + t] = a;
     }
     __syncthreads();
-    for (int i = t; i < c * c; i += FHR_THREADS) s_w[i] = wc[i] * (1.f + s_a[i % c]);       // f*a + f folded into the weights
+    for (int i = t; i < c * c; i += FHR_THREADS) s_w[i] *= 1.f + s_a[i % c];                 // f*a + f folded into the weights
+    if (trace && threadIdx.x == 0) trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 1] = clock64();
     const int oy0 = blockIdx.x * FHR_ROWS, oy1 = min(oy0 + FHR_ROWS, oh);
     const int ys = lerp_src(oy0, rh, h).i0, ye = lerp_src(oy1 - 1, rh, h).i1;
     const int rows = ye - ys + 1;                                          // <= max_rows (host)
@@ -517,6 +580,7 @@ ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __res
         }
     }
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
     const long long plane = static_cast<long long>(oh) * ow;
     // Row geometry of the block (shared by every thread): for the x8 head the FHR_ROWS output rows of a block all lie
     // between the same two source rows, and the 4 output pixels of a thread between the same two source columns; then one
@@ -578,6 +642,7 @@ ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __res
             }
         }
     }
+    if (trace && threadIdx.x == 0) trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 3] = clock64();
 }
 
 // ---------------------------------------------------------------- bilinear resize NHWC fp32 -> NCHW fp32
@@ -842,6 +907,10 @@ extern "C" int rtsds_resize_to_nchw(const float* z, int n, int h, int w, int c, 
     return check_launch("resize_nchw_kernel");
 }
 
+// debug: per-block clock64 stamps of arm_gate_resize_kernel (start, pooled vector ready, gates ready, pixels streamed) and of
+// ffm_head_resize_kernel (start, attention + weights ready, z rows ready, rows written)
+extern "C" void rtsds_debug_arm_trace(void* buf) { g_arm_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide* a4, int dtype, int n, int oh, int ow, void* dst,
                                      int dst_ld, rtsds_stream_t s) {
     RTSDS_REQUIRE(a3 && a4 && dst && n > 0 && oh > 0 && ow > 0, "arm_gate_resize: bad argument");
@@ -858,19 +927,31 @@ extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide*
     }
     RTSDS_REQUIRE(dst_ld % 8 == 0, "arm_gate_resize: dst_ld must be a multiple of 8");
     const int groups = a3->c / 32 + a4->c / 32;
-    int chunks = static_cast<int>(cdiv(2LL * num_sms(), groups));
+    const size_t sm = sizeof(float) * static_cast<size_t>(a3->c > a4->c ? a3->c : a4->c);
+    RTSDS_REQUIRE(sm <= 40 * 1024, "arm_gate_resize: too many channels");
+    // exactly ONE wave: every block costs ~10 us of mostly latency (pooled vector, gates, gathers), so a handful of blocks
+    // left over for a second wave doubles the kernel (measured: 312 blocks on 296 slots = 23 us, per-block time 10 us)
+    static int occ[3] = {0, 0, 0};
+    const int oi = dtype == RTSDS_F16 ? 0 : (dtype == RTSDS_BF16 ? 1 : 2);
+    if (!occ[oi]) {
+        int o = 0;
+        if (oi == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, arm_gate_resize_kernel<__half>, 256, 40 * 1024);
+        else if (oi == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, arm_gate_resize_kernel<__nv_bfloat16>, 256, 40 * 1024);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, arm_gate_resize_kernel<float>, 256, 40 * 1024);
+        occ[oi] = o > 0 ? o : 1;
+    }
+    int chunks = static_cast<int>(static_cast<long long>(occ[oi]) * num_sms() / groups);
+    if (chunks < 1) chunks = 1;
     const int npix = oh * ow;
     if (chunks > npix / 64) chunks = npix / 64 > 0 ? npix / 64 : 1;
     const int blocks0 = (a3->c / 32) * chunks, blocks = groups * chunks;
     cudaStream_t st = as_stream(s);
-    const size_t sm = sizeof(float) * static_cast<size_t>(a3->c > a4->c ? a3->c : a4->c);
-    RTSDS_REQUIRE(sm <= 40 * 1024, "arm_gate_resize: too many channels");
     if (dtype == RTSDS_F16)
-        arm_gate_resize_kernel<__half><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld);
+        arm_gate_resize_kernel<__half><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld, g_arm_trace);
     else if (dtype == RTSDS_BF16)
-        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld);
+        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, g_arm_trace);
     else if (dtype == RTSDS_F32)
-        arm_gate_resize_kernel<float><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld);
+        arm_gate_resize_kernel<float><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld, g_arm_trace);
     else { set_error("arm_gate_resize: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
     return check_launch("arm_gate_resize_kernel");
@@ -891,7 +972,7 @@ extern "C" int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pool
     if (!done) { cudaFuncSetAttribute(ffm_head_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; }
     dim3 grid(static_cast<unsigned>(cdiv(oh, FHR_ROWS)), n);
     ffm_head_resize_kernel<<<grid, FHR_THREADS, smem, as_stream(s)>>>(f, f_ld, pooled, h, w, c, w1, b1, w2, b2, wc, bc, attn_out, oh, ow,
-                                                                      rh, rw, max_rows, pooled_parts, out);
+                                                                      rh, rw, max_rows, pooled_parts, out, g_arm_trace);
     count_launch();
     return check_launch("ffm_head_resize_kernel");
 }

@@ -3,7 +3,7 @@
   python tools/hbm_kernels.py [--ncu] > gpurun_out/r02_hbm_kernels.json
 
 Each kernel is launched alone on inputs of its real size.  Timing: CUDA events on the launching stream around 8 back-to-back
-launches over 8 ROTATING buffer sets (together larger than the 126 MB L2, so every launch finds its inputs evicted), median
+launches (replayed from a CUDA graph, so host-side wrapper time is not measured) over 8 ROTATING buffer sets (together larger than the 126 MB L2, so every launch finds its inputs evicted), median
 of 5 rounds; `warm_us` is the same buffer set 20 times.  n = 1 rows are BASELINE configs[1] sizes (launch-latency regime: 1-40 MB
 per launch), n = 8 rows the validation / training batch (bandwidth regime).  achieved = ALGORITHMIC bytes / cold time; peak =
 MEASURED_PEAKS.json hbm_gbs.  With --ncu every kernel is launched exactly twice and nothing else is timed, for
@@ -52,19 +52,41 @@ def measure(fn):
     for i in range(K_SETS):
         fn(i)
     torch.cuda.synchronize()
+
+    def replayable(body):
+        """The launches are replayed from a CUDA graph, as inside the engine's frame graph: several of the Python wrappers
+        (ctypes structs, descriptor set-up) cost more host time than their kernel runs, which an eager loop would measure."""
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                body()
+            gr.replay()
+            torch.cuda.synchronize()
+            return gr.replay
+        except Exception:                                  # not capturable (allocates / syncs): eager loop
+            torch.cuda.synchronize()
+            return body
+
+    def cold_body():
+        for i in range(K_SETS):
+            fn(i)
+
+    def warm_body():
+        for _ in range(20):
+            fn(0)
+
+    run_cold, run_warm = replayable(cold_body), replayable(warm_body)
     ts = []
     for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(K_SETS):
-            fn(i)
+        run_cold()
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3 / K_SETS)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(20):
-        fn(0)
+    run_warm()
     b.record()
     torch.cuda.synchronize()
     return statistics.median(ts), a.elapsed_time(b) * 1e3 / 20

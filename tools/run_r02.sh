@@ -18,3 +18,6 @@ $CMD3 > gpurun_out/r02_train_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02_train_launches.csv $CMD3 > gpurun_out/r02_train_ncu.log 2>&1
 echo "train launch list rc=$?"
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python tools/hbm_kernels.py > gpurun_out/r02_hbm_kernels.json 2> gpurun_out/r02_hbm_kernels.err &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:_kernel --csv --log-file gpurun_out/r02_hbm_ncu.csv python tools/hbm_kernels.py --ncu > gpurun_out/r02_hbm_ncu.log 2>&1
+echo "hbm table rc=$?"
