@@ -436,22 +436,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
         const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
 
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t r[32];
-            if (have_acc) {
-                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-                ptx::tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (trace && threadIdx.x == 64) trace[c0 == 0 ? 13 : 15] = clock64();
+        // One 32-column chunk of this thread's accumulator row.
+        auto do_chunk = [&](uint32_t (&r)[32], int c0) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int co0 = n0 + c0;
-
             if (p.cluster_reduce) {
                 // PUSH: this fp32 partial row goes straight into the receive buffer of the CTA that owns the row
                 // (slot = this CTA's split rank).  Remote stores are fire-and-forget: no DSMEM load latency anywhere.
@@ -461,19 +451,34 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const uint32_t ra = ptx::mapa_u32(dst, yrank + static_cast<uint32_t>(owner * (p.mc > 1 ? p.mc : 1)));
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) ptx::st_dsmem_f4(ra + j * 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                continue;
-            }
-            if (p.split_k > 1) {
+            } else if (p.split_k > 1) {
                 if (valid) {
                     float* dst = p.partial + (static_cast<long long>(blockIdx.z) * m_total + pix_lin) * p.cout_pad + co0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                continue;
+            } else {
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr);
             }
-
-            tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr);
+        };
+        // (two chunks per trip — both TMEM loads in flight, two interleaved instruction streams — was measured: 168
+        // registers, small spills, no gain; the chunk time is dominated by the row-per-lane 16-byte global stores)
+        constexpr int CW = 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
+            uint32_t ra[32], rb[32];
+            if (have_acc) {
+                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, ra);
+                if (CW == 64) ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0 + 32, rb);
+                ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ra[j] = rb[j] = 0u;
+            }
+            if (trace && threadIdx.x == 64) trace[c0 == 0 ? 13 : 15] = clock64();
+            do_chunk(ra, c0);
+            if (CW == 64) do_chunk(rb, c0 + 32);
             if (trace && threadIdx.x == 64 && c0 == 0) trace[14] = clock64();
         }
         if (p.stats && p.split_k == 1) {
@@ -1036,14 +1041,6 @@ static unsigned long long* g_tc_trace = nullptr;
 extern "C" void rtsds_debug_conv_trace(void* buf) { g_tc_trace = reinterpret_cast<unsigned long long*>(buf); }
 extern "C" void rtsds_conv2d_tc_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
 
-static int tc_pick_block_n(int cout_pad, long long m_tiles) {
-    if (g_force_block_n && cout_pad % g_force_block_n == 0) return g_force_block_n;
-    if (cout_pad <= 64) return cout_pad;
-    // few M tiles: narrower N tiles give more CTAs
-    if (m_tiles * (cout_pad / 128) < num_sms()) return 64;
-    return 128;
-}
-
 static int tc_auto_split(long long ctas, int kb_total) {
     int split = 1;
     const int sms = num_sms();
@@ -1051,12 +1048,27 @@ static int tc_auto_split(long long ctas, int kb_total) {
     return split;
 }
 
+static int tc_pick_block_n(int cout_pad, long long m_tiles, int kb_total) {
+    if (g_force_block_n && cout_pad % g_force_block_n == 0) return g_force_block_n;
+    if (cout_pad <= 64) return cout_pad;
+    const long long wide = m_tiles * (cout_pad / 128);
+    if (wide >= num_sms()) return 128;
+    // Few M tiles.  The K loop of these launches runs at the L2->SM fabric rate, and a 128-wide tile moves a third fewer
+    // operand bytes per flop than a 64-wide one; the missing CTAs come back as split-K slices, which reduce inside a
+    // cluster (<= 4 deep) — worth it while every slice keeps >= 8 k-blocks and the grid still covers most of the SMs
+    // (tools/deep_conv_sweep.py: 256->256 32x64 13.3 -> 12.0 us, 128->128 64x128 12.3 -> 11.6 us; 128->256 s2 and the
+    // 512-channel layers stay on 64-wide tiles).
+    const int sp = tc_auto_split(wide, kb_total);
+    if (sp >= 2 && sp <= 4 && kb_total / sp >= 8 && wide * sp * 5 >= 4LL * num_sms()) return 128;
+    return 64;      // narrower N tiles give more CTAs
+}
+
 static void tp_plan(const TapProblem& t, int* block_n, int* split, int* tile_w, int* tile_h) {
     pick_tile(t.oh, t.ow, tile_w, tile_h);
     const long long m_tiles = static_cast<long long>(t.n_img) * cdiv(t.ow, *tile_w) * cdiv(t.oh, *tile_h);
     const int cp = conv_cout_pad(t.cout);
-    *block_n = tc_pick_block_n(cp, m_tiles);
     const int kb_total = t.n_taps * (t.ck / TC_BLOCK_K);
+    *block_n = tc_pick_block_n(cp, m_tiles, kb_total);
     int sp = t.split_req;
     if (sp <= 0) sp = tc_auto_split(m_tiles * (cp / *block_n), kb_total);
     if (sp > kb_total) sp = kb_total;

@@ -12,7 +12,8 @@ from rtsds_b200 import ops  # noqa: E402
 from rtsds_b200.ops import F16  # noqa: E402
 
 SHAPES = [(1, 32, 64, 256, 256, 3, 1), (1, 16, 32, 512, 512, 3, 1), (1, 64, 128, 128, 256, 3, 2), (1, 32, 64, 256, 512, 3, 2),
-          (1, 64, 128, 128, 128, 3, 1), (1, 128, 256, 64, 64, 3, 1)]
+          (1, 64, 128, 128, 128, 3, 1), (1, 128, 256, 64, 64, 3, 1), (1, 128, 256, 128, 256, 3, 2), (1, 64, 128, 1024, 171, 1, 1),
+          (1, 256, 512, 64, 128, 3, 2)]
 
 
 def timed(fn, reps=20):
@@ -38,8 +39,9 @@ for n, h, w, cin, cout, k, st in SHAPES:
     res = []
     for bn in (0, 64, 128):
         for sp in (0, 1, 2, 4, 8):
-            d = ops.make_conv_desc(n, h, w, cin, cin, cout, cout, k, st, 1, 1, in_dtype=F16, out_dtype=F16, split_k=sp)
-            y = torch.zeros(n, d.oh, d.ow, cout, dtype=torch.float16, device="cuda")
+            ld = (cout + 7) // 8 * 8
+            d = ops.make_conv_desc(n, h, w, cin, cin, cout, ld, k, st, k // 2, 1, in_dtype=F16, out_dtype=F16, split_k=sp)
+            y = torch.zeros(n, d.oh, d.ow, ld, dtype=torch.float16, device="cuda")
             ops.lib().rtsds_conv2d_tc_tune(bn, 0)
             ws = torch.empty(max(int(ops.lib().rtsds_conv2d_tc_workspace_bytes(d)), 16), dtype=torch.uint8, device="cuda")
             try:
