@@ -626,7 +626,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput part of the default run")
     ap.add_argument("--no-extra", action="store_true", help="skip the DeepLabV2 / adversarial extras and the long comparator legs")
     ap.add_argument("--no-comparator", action="store_true", help="skip the cuDNN comparator leg")
-    ap.add_argument("--context", default="resnet18", choices=["resnet18", "resnet101"], help="inference: BiSeNet context path (resnet101: eval only)")
+    ap.add_argument("--context", default="resnet18", choices=["resnet18", "resnet101"], help="BiSeNet context path (inference and --workload train)")
     ap.add_argument("--lanes", type=int, default=3, help="inference: concurrent batch-1 streams of the multi-stream / pipelined measurements")
     args = ap.parse_args()
     if args.warmup < 3:

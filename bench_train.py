@@ -31,7 +31,7 @@ def measure_train(args, rank, world, local, steps, warmup, batch, h=720, w=1280,
     from rtsds_b200.bisenet_autograd import bisenet_fused_ce
 
     dev = torch.device("cuda", local)
-    model = bench.make_model(dev).train()
+    model = bench.make_model(dev, getattr(args, "context", "resnet18")).train()
     model.rtsds_ddp = world > 1
     from rtsds_b200 import ddp
 
@@ -206,4 +206,9 @@ def run_train(args, rank, world, local):
         "final_loss": round(r["loss"], 4), "val_miou_random_weights": round(r["miou"], 5),
         "cpu_baseline": None,
     }
+    if getattr(args, "context", "resnet18") == "resnet101":      # the Bottleneck context path (build_bisenet.py:95-102)
+        line["metric"] = "BiSeNet-R101 720x1280 data-parallel training throughput"
+        line["config"]["workload"] = "bisenet_r101_train_3x720x1280 (SURVEY N4: context_path='resnet101')"
+        line["roofline"] = None                                  # the FLOP constants above are the ResNet-18 model's
+        line["whole_step_hbm"] = None
     bench.emit(line)

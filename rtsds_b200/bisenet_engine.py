@@ -59,9 +59,8 @@ class BiSeNetPlan:
         self.use_tc = precision in ("bf16", "fp16")  # "bf16_simt": bf16 storage, CUDA-core convs (cross-check)
         self.tdt = ops.torch_dtype(self.dt)
         self.nc = model.conv.weight.shape[0]
-        if model._context_name not in ("resnet18", "resnet101") or (train and model._context_name != "resnet18"):
-            raise ops._lib.RtsdsError("context paths: resnet18 (train + eval) and resnet101 (eval only, SURVEY N4); got "
-                                      f"{model._context_name!r} with train={train}")
+        if model._context_name not in ("resnet18", "resnet101"):
+            raise ops._lib.RtsdsError(f"context paths: resnet18 and resnet101 (build_bisenet.py:95-113); got {model._context_name!r}")
         if self.nc > 32:
             raise ops._lib.RtsdsError("num_classes > 32 is not supported by the fused head kernels")
         self._stats_chunks = []

@@ -270,8 +270,8 @@ class BiSeNetTrainPlan:
         if not p0.is_cuda and not ops._lib.dry_run():
             raise ops._lib.RtsdsError("BiSeNet parameters must live on a CUDA device (no CPU fallback)")
         check(lib().rtsds_check_device(), "device check")
-        if model._context_name != "resnet18":
-            raise ops._lib.RtsdsError("only the resnet18 context path is implemented")
+        if model._context_name not in ("resnet18", "resnet101"):
+            raise ops._lib.RtsdsError(f"context paths: resnet18 and resnet101 (build_bisenet.py:95-113); got {model._context_name!r}")
         self.model, self.device = model, p0.device
         self.n, self.h, self.w = n, h, w
         # "bf16": tensor-core kernels; "fp32": CUDA-core check mode; "bf16_simt": bf16 storage with the CUDA-core
@@ -340,10 +340,14 @@ class BiSeNetTrainPlan:
         h4, w4 = cs(h2, 3, 2, 1), cs(w2, 3, 2, 1)
         h8, w8 = cs(h4, 3, 2, 1), cs(w4, 3, 2, 1)
         self.h8, self.w8 = h8, w8
-        self.cat = self.buf(n, h8, w8, 1024)
+        # concat buffer of build_bisenet.py:153,72: 256 spatial-path channels | cx1 | cx2 (1024 wide for resnet18, 3328 for
+        # resnet101 — Bottleneck context path)
+        self.r101 = hasattr(cp.layer1[0], "conv3")
+        self.catw = catw = 256 + (1024 + 2048 if self.r101 else 256 + 512)
+        self.cat = self.buf(n, h8, w8, catw)
         sp2y = _Buf(self.buf(n, h4, w4, 128))
         self.sp2 = _ConvBN(self, sp.convblock2.conv1, sp.convblock2.bn, self.sp1.y, (n, h2, w2, 64), sp2y, True)
-        self.sp3 = _ConvBN(self, sp.convblock3.conv1, sp.convblock3.bn, sp2y, (n, h4, w4, 128), _Buf(self.cat, ld=1024), True)
+        self.sp3 = _ConvBN(self, sp.convblock3.conv1, sp.convblock3.bn, sp2y, (n, h4, w4, 128), _Buf(self.cat, ld=catw), True)
         # context path
         self.cp0 = _Stem(self, cp.conv1, cp.bn1, 7, 3, n, H, W)
         ph, pw = ops.maxpool_out_size(self.cp0.oh), ops.maxpool_out_size(self.cp0.ow)
@@ -351,12 +355,16 @@ class BiSeNetTrainPlan:
         self.pool_shape = (n, ph, pw, 64)
         self.pool_idx = self.buf(n, ph, pw, 8, dtype=torch.int32)
         self.blocks = []
+        self.layer_first = {}                    # index of the first block of layer2..4 -> its gradient bucket
         x, shape = self.pool, self.pool_shape
-        for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
+        for li, layer in enumerate((cp.layer1, cp.layer2, cp.layer3, cp.layer4), 1):
+            if li > 1:
+                self.layer_first[len(self.blocks)] = f"layer{li}"
             for blk in layer:
-                x, shape = self._block(blk, x, shape)
-        self.f3, self.s3 = self.blocks[5]["y"], self.blocks[5]["shape"]
-        self.f4, self.s4 = self.blocks[7]["y"], self.blocks[7]["shape"]
+                x, shape = (self._bottleneck if self.r101 else self._block)(blk, x, shape)
+        self.i_l4 = len(self.blocks) - len(cp.layer4)       # first block of layer4: its input is feature3 (also read by ARM1)
+        self.f3, self.s3 = self.blocks[self.i_l4 - 1]["y"], self.blocks[self.i_l4 - 1]["shape"]
+        self.f4, self.s4 = self.blocks[-1]["y"], self.blocks[-1]["shape"]
         c3, c4 = self.s3[3], self.s4[3]
         self.c3, self.c4 = c3, c4
         self.arm = {}
@@ -368,14 +376,14 @@ class BiSeNetTrainPlan:
         zdt = self.dt
         z1b = _Buf(self.z1, dtype=F32)
         z2b = _Buf(self.z2, dtype=F32)
-        self.sup1 = _ConvBN(self, m.supervision1, None, _Buf(self.cat, ld=1024, off=256), (n, h8, w8, c3), z1b, False)
-        self.sup2 = _ConvBN(self, m.supervision2, None, _Buf(self.cat, ld=1024, off=256 + c3), (n, h8, w8, c4), z2b, False)
+        self.sup1 = _ConvBN(self, m.supervision1, None, _Buf(self.cat, ld=catw, off=256), (n, h8, w8, c3), z1b, False)
+        self.sup2 = _ConvBN(self, m.supervision2, None, _Buf(self.cat, ld=catw, off=256 + c3), (n, h8, w8, c4), z2b, False)
         ffm = m.feature_fusion_module
         self.feat = _Buf(self.zeros(n, h8, w8, 32, dtype=f32))
         from . import tapn
 
         ffm_cls = _TapNConvBN if tapn.applicable(ffm.convblock.conv1) else _ConvBN
-        self.ffm = ffm_cls(self, ffm.convblock.conv1, ffm.convblock.bn, _Buf(self.cat, ld=1024), (n, h8, w8, 1024), self.feat, True,
+        self.ffm = ffm_cls(self, ffm.convblock.conv1, ffm.convblock.bn, _Buf(self.cat, ld=catw), (n, h8, w8, catw), self.feat, True,
                            raw_dtype=F32)
         self.pooled_f = self.buf(n, nc, dtype=f32)
         self.attn = self.buf(n, nc, dtype=f32)
@@ -384,11 +392,14 @@ class BiSeNetTrainPlan:
         self.dz = [self.zeros(n, h8, w8, 32, dtype=f32) for _ in range(3)]
         self.dzb = [self.zeros(n, h8, w8, 64 if self.dt == BF16 else 32, dtype=self.tdt) for _ in range(2)]   # aux dy operands
         self.dfeat = self.zeros(n, h8, w8, 32, dtype=f32)
-        self.dcat = self.zeros(n, h8, w8, 1024)
+        self.dcat = self.zeros(n, h8, w8, catw)
         self.dg3 = self.buf(n, self.s3[1], self.s3[2], c3, dtype=f32)
         self.dg4 = self.buf(n, self.s4[1], self.s4[2], c4, dtype=f32)
-        max_act = max(self.sp1.n_pix * 64, self.cp0.n_pix * 64)
+        max_act = max([self.sp1.n_pix * 64, self.cp0.n_pix * 64] + [b["shape"][0] * b["shape"][1] * b["shape"][2] * b["shape"][3] for b in self.blocks]
+                      + [b["xshape"][0] * b["xshape"][1] * b["xshape"][2] * b["xshape"][3] for b in self.blocks])
         self.gA, self.gB, self.gT, self.gG = (self.buf(max_act) for _ in range(4))
+        if self.r101:
+            self.gT1 = self.buf(max_act)
         self.stats_all = torch.zeros(max(self._stats_total, 1), dtype=f32, device=self.device)
         self.d_raw_scratch = self.zeros(max(self._scratch_act, 1))
         self.dw_scratch = self.zeros(max(self._scratch_w, 1), dtype=f32)
@@ -425,6 +436,28 @@ class BiSeNetTrainPlan:
         self.blocks.append(dict(c1=c1, c2=c2, ds=ds, x=x, xshape=shape, y=y, shape=(n, oh, ow, cout)))
         return y, (n, oh, ow, cout)
 
+    def _bottleneck(self, blk, x: _Buf, shape):
+        """torchvision Bottleneck (build_contextpath.py:32-56): 1x1 -> 3x3 (carries the stride) -> 1x1 (+ shortcut) -> ReLU."""
+        n, h, w, cin = shape
+        planes = blk.conv1.weight.shape[0]
+        st = blk.conv2.stride[0]
+        oh, ow = ops.conv_out_size(h, 3, st, 1), ops.conv_out_size(w, 3, st, 1)
+        t1 = _Buf(self.buf(n, h, w, planes))
+        t2 = _Buf(self.buf(n, oh, ow, planes))
+        y = _Buf(self.buf(n, oh, ow, planes * 4))
+        c1 = _ConvBN(self, blk.conv1, blk.bn1, x, shape, t1, True)
+        c2 = _ConvBN(self, blk.conv2, blk.bn2, t1, (n, h, w, planes), t2, True)
+        ds = None
+        if blk.downsample is not None:
+            dsy = _Buf(self.buf(n, oh, ow, planes * 4))
+            ds = _ConvBN(self, blk.downsample[0], blk.downsample[1], x, shape, dsy, False)
+            res = dsy
+        else:
+            res = x
+        c3 = _ConvBN(self, blk.conv3, blk.bn3, t2, (n, oh, ow, planes), y, True, residual=res)
+        self.blocks.append(dict(c1=c1, c2=c2, c3=c3, ds=ds, x=x, xshape=shape, y=y, shape=(n, oh, ow, planes * 4), tshape=(n, h, w, planes)))
+        return y, (n, oh, ow, planes * 4)
+
     # ---------------- weights ----------------
     def _params_version(self):
         v = 0
@@ -460,6 +493,8 @@ class BiSeNetTrainPlan:
             if b["ds"] is not None:
                 b["ds"].forward()
             b["c2"].forward()
+            if "c3" in b:
+                b["c3"].forward()
         a, dt = self.arm, self.dt
         s3, s4, c3, c4, h8, w8 = self.s3, self.s4, self.c3, self.c4, self.h8, self.w8
         arm1, arm2 = m.attention_refinement_module1, m.attention_refinement_module2
@@ -467,8 +502,8 @@ class BiSeNetTrainPlan:
         ops.global_avgpool(self.f4.t, n, s4[1] * s4[2], c4, c4, a["pooled4"])
         ops.arm_gate(a["pooled3"], arm1.conv, arm1.bn, True, n, c3, a["gate3"], None, a["lin3"], a["xhat3"])
         ops.arm_gate(a["pooled4"], arm2.conv, arm2.bn, True, n, c4, a["gate4"], a["pooled4"], a["lin4"], a["xhat4"])
-        ops.gate_resize_nhwc(self.f3.t, n, s3[1], s3[2], c3, c3, a["gate3"], h8, w8, self.cat, 1024, 256, dt)
-        ops.gate_resize_nhwc(self.f4.t, n, s4[1], s4[2], c4, c4, a["gate4"], h8, w8, self.cat, 1024, 256 + c3, dt)
+        ops.gate_resize_nhwc(self.f3.t, n, s3[1], s3[2], c3, c3, a["gate3"], h8, w8, self.cat, self.catw, 256, dt)
+        ops.gate_resize_nhwc(self.f4.t, n, s4[1], s4[2], c4, c4, a["gate4"], h8, w8, self.cat, self.catw, 256 + c3, dt)
         self.sup1.forward()
         self.sup2.forward()
         self.ffm.forward()
@@ -527,7 +562,8 @@ class BiSeNetTrainPlan:
                                        _p(gw.get(final.weight)) if final is not None else None,
                                        _p(gw.get(final.bias)) if final is not None else None, s), "ffm_head_bwd")
         # ---- FFM ConvBlock: -> dcat (assign over all 1024 channels) ----
-        dcat = _Buf(self.dcat, ld=1024)
+        catw = self.catw
+        dcat = _Buf(self.dcat, ld=catw)
         self.ffm.backward(_Buf(self.dfeat, dtype=F32), gw, dx=dcat, dx_accumulate=False)
         # ---- auxiliary heads: 1x1 convs on the cx1 / cx2 slots of the concat buffer ----
         for i, (layer, off) in enumerate(((self.sup1, 256), (self.sup2, 256 + c3))):
@@ -537,14 +573,14 @@ class BiSeNetTrainPlan:
                 check(lib().rtsds_channel_sum(_p(dzi), 32, npix8, nc, F32, _p(gb), s), "channel_sum")
             dyb = self.dzb[i]
             ops.scale_shift_act_ptr(dzi, dyb, npix8, nc, None, None, None, ACT_NONE, 0.0, 32, dyb.shape[-1], nc, F32, dt)
-            layer.backward(_Buf(dyb), gw, dx=_Buf(self.dcat, ld=1024, off=off), dx_accumulate=True)
+            layer.backward(_Buf(dyb), gw, dx=_Buf(self.dcat, ld=catw, off=off), dx_accumulate=True)
         # ---- gated resize + ARM backward -> gradients of f3 / f4 ----
         dF = {}
         for tag, f, shp, c, off, arm in (("3", self.f3, s3, c3, 256, m.attention_refinement_module1),
                                          ("4", self.f4, s4, c4, 256 + c3, m.attention_refinement_module2)):
             hw = shp[1] * shp[2]
             dgt = self.dg3 if tag == "3" else self.dg4
-            check(lib().rtsds_resize_bwd_nhwc(_p(self.dcat), 1024, off, n, shp[1], shp[2], c, h8, w8, f.ptr, dt, _p(dgt),
+            check(lib().rtsds_resize_bwd_nhwc(_p(self.dcat), catw, off, n, shp[1], shp[2], c, h8, w8, f.ptr, dt, _p(dgt),
                                               _p(a["dgate" + tag]), s), "resize_bwd_nhwc")
             mul = a["pooled4"] if tag == "4" else None
             check(lib().rtsds_arm_gate_bwd(_p(a["dgate" + tag]), _p(a["pooled" + tag]), _p(a["lin" + tag]), _p(a["xhat" + tag]),
@@ -566,18 +602,30 @@ class BiSeNetTrainPlan:
             b = self.blocks[bi]
             cout, cin = b["shape"][3], b["xshape"][3]
             g = _Buf(self.gG, ld=cout, dtype=dt)
-            dT = _Buf(self.gT, ld=cout, dtype=dt)
-            acc_in = bi == 6
+            acc_in = bi == self.i_l4
             dx = _Buf(self.gB if acc_in else dy.t, ld=cin, dtype=dt)
-            b["c2"].backward(dy, gw, dx=dT, dx_accumulate=False, g_out=g)
-            if b["ds"] is not None:
-                b["ds"].backward(g, gw, dx=dx, dx_accumulate=acc_in)
+            if "c3" in b:                                   # Bottleneck: conv3 (+shortcut) -> conv2 -> conv1
+                planes = cout // 4
+                dT2 = _Buf(self.gT, ld=planes, dtype=dt)
+                dT1 = _Buf(self.gT1, ld=planes, dtype=dt)
+                b["c3"].backward(dy, gw, dx=dT2, dx_accumulate=False, g_out=g)
+                if b["ds"] is not None:
+                    b["ds"].backward(g, gw, dx=dx, dx_accumulate=acc_in)
+                else:
+                    self._copy(g, dx, b["xshape"])
+                b["c2"].backward(dT2, gw, dx=dT1, dx_accumulate=False)
+                b["c1"].backward(dT1, gw, dx=dx, dx_accumulate=True)
             else:
-                self._copy(g, dx, b["xshape"])            # identity shortcut (never the accumulating block)
-            b["c1"].backward(dT, gw, dx=dx, dx_accumulate=True)
+                dT = _Buf(self.gT, ld=cout, dtype=dt)
+                b["c2"].backward(dy, gw, dx=dT, dx_accumulate=False, g_out=g)
+                if b["ds"] is not None:
+                    b["ds"].backward(g, gw, dx=dx, dx_accumulate=acc_in)
+                else:
+                    self._copy(g, dx, b["xshape"])            # identity shortcut (never the accumulating block)
+                b["c1"].backward(dT, gw, dx=dx, dx_accumulate=True)
             dy = dx
-            if bi in (6, 4, 2):
-                ready({6: "layer4", 4: "layer3", 2: "layer2"}[bi])
+            if bi in self.layer_first:
+                ready(self.layer_first[bi])
         # ---- max-pool and the 7x7 stem ----
         n_, ph, pw, _ = self.pool_shape
         dcp0 = _Buf(self.gT, ld=64, dtype=dt)
@@ -586,7 +634,7 @@ class BiSeNetTrainPlan:
         self.cp0.backward(self.x, dcp0, gw, wgrad=not self.use_tc)
         # ---- spatial path ----
         d2 = _Buf(self.gA, ld=128, dtype=dt)
-        self.sp3.backward(_Buf(self.dcat, ld=1024), gw, dx=d2, dx_accumulate=False)
+        self.sp3.backward(_Buf(self.dcat, ld=catw), gw, dx=d2, dx_accumulate=False)
         d1 = _Buf(self.gB, ld=64, dtype=dt)
         self.sp2.backward(d2, gw, dx=d1, dx_accumulate=False)
         self.sp1.backward(self.x, d1, gw, wgrad=not self.use_tc)

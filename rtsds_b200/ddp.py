@@ -6,8 +6,26 @@ images are independent, BatchNorm statistics stay per rank exactly as under Data
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+# RTSDS_DDP_TIMELINE=1: CUDA events at backward start, at every bucket's "gradients final" point, at backward end and — on the
+# compute stream, after the wait on each bucket's collective — at "bucket averaged"; last_timeline() turns the most recent
+# step's events into milliseconds (tools/ddp_timeline.py prints them).  Off by default: no events are recorded.
+TIMELINE = os.environ.get("RTSDS_DDP_TIMELINE", "0") == "1"
+_last = None
+
+
+def last_timeline():
+    """[(bucket, MB, ready_ms, averaged_ms)], backward_end_ms of the most recent step (times since the reducer was created =
+    backward start), or None."""
+    if _last is None:
+        return None
+    torch.cuda.synchronize()
+    t0, rows, end = _last
+    return [(g, mb, t0.elapsed_time(r), t0.elapsed_time(d)) for g, mb, r, d in rows], t0.elapsed_time(end)
 
 
 def is_distributed() -> bool:
@@ -48,6 +66,10 @@ class BucketedAllReduce:
         self.done = set()
         self.world = dist.get_world_size() if is_distributed() else 1
         self.avg = self.world > 1 and dist.get_backend() == "nccl"
+        self.tl = None
+        if TIMELINE and self.world > 1 and flat.is_cuda:
+            self.tl = (torch.cuda.Event(enable_timing=True), [])
+            self.tl[0].record()
 
     def ready(self, group: str):
         """Call when backward has finished writing the gradients of `group`."""
@@ -56,6 +78,10 @@ class BucketedAllReduce:
         self.done.add(group)
         s, e = self.ranges[group]
         op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        if self.tl is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.tl[1].append([group, (e - s) * 4 / 1e6, ev, None])
         self.handles.append(dist.all_reduce(self.flat[s:e], op=op, async_op=True))
 
     def finish(self):
@@ -64,8 +90,18 @@ class BucketedAllReduce:
             return self.flat
         for g in self.ranges:
             self.ready(g)
-        for h in self.handles:
+        if self.tl is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()                                  # backward end (every bucket has been signalled)
+        for i, h in enumerate(self.handles):
             h.wait()
+            if self.tl is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self.tl[1][i][3] = ev
+        if self.tl is not None:
+            global _last
+            _last = (self.tl[0], [tuple(r) for r in self.tl[1]], end)
         if not self.avg:
             self.flat.mul_(1.0 / self.world)
         return self.flat

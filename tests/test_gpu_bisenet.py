@@ -478,6 +478,51 @@ def test_resnet101_context_path_eval_vs_reference_golden(cuda, golden_dir, preci
         assert _l2_rel(got, ref) < 6e-2, _l2_rel(got, ref)
         assert agree >= 0.85, agree
     assert torch.equal(out, m(x.cuda()))          # CUDA-graph replay of the same plan
-    m.train()
-    with pytest.raises(Exception, match="resnet18"):
-        m(x.cuda().repeat(2, 1, 1, 1))            # training with the resnet101 context path is not built yet
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_resnet101_context_path_training_vs_oracle(cuda, precision):
+    """BiSeNet(19, 'resnet101') in TRAIN mode: train-mode forward (batch-statistics BatchNorm through 33
+    Bottlenecks), 3 x CE, backward -- outputs, loss and every parameter gradient against the CPU oracle's autograd."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    from models.bisenet.build_bisenet import BiSeNet
+
+    seed = 5
+    sd = weights.bisenet_r101_state(seed)
+    x, y = _input(seed, 2, 128, 192)
+    m = BiSeNet(19, "resnet101")
+    m.load_state_dict(weights.clone_state(sd))
+    m.rtsds_precision = precision
+    m = m.cuda().train()
+    outs = m(x.cuda())
+    loss = sum(torch.nn.functional.cross_entropy(t, y.cuda(), ignore_index=19) for t in outs)
+    loss.backward()
+    ref_sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in weights.clone_state(sd).items()}
+    ref = bisenet_ref.bisenet_forward(x, ref_sd, train=True)
+    ref_loss = sum(bisenet_ref.ce_loss(t, y, 19) for t in ref)
+    ref_loss.backward()
+    err = max(rel_err(t.detach().cpu(), r.detach()) for t, r in zip(outs, ref))
+    record(f"bisenet_r101_train_2x128x192/{precision}", rel=err, loss=loss.item(), ref_loss=ref_loss.item())
+    if precision == "fp32":
+        assert err < 5e-4, err
+        assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    else:
+        # 101 stacked bf16 layers with batch statistics over 48-768 samples: only the loss is a meaningful bf16 bound here
+        assert abs(loss.item() - ref_loss.item()) < 5e-2 * max(1.0, abs(ref_loss.item()))
+    named = dict(m.named_parameters())
+    worst, n_checked = 0.0, 0
+    for k, p in named.items():
+        rg = ref_sd[k].grad
+        if rg is None or p.grad is None:
+            assert rg is None or float(rg.abs().max()) == 0.0 or "fc." in k, k
+            continue
+        if _ill_conditioned(k, precision):
+            continue
+        assert torch.isfinite(p.grad).all(), k
+        e = _l2_rel(p.grad.cpu(), rg)
+        worst = max(worst, e)
+        n_checked += 1
+        if precision == "fp32":
+            assert e < 5e-2, (k, e)
+    record(f"bisenet_r101_train_2x128x192/{precision}/grads", worst_l2_rel=worst, tensors=n_checked)
+    assert n_checked > 250
