@@ -306,6 +306,11 @@ int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oihw, int dtyp
 int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
                            const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
                            void* y_sp, rtsds_stream_t s);
+/* Eval-mode form with the context path's nn.MaxPool2d(3, 2, 1) (build_contextpath.py:21) fused into the epilogue: the
+ * 1/2-resolution context-path map is never written; `pool` (NHWC [n, (oh-1)/2+1, (ow-1)/2+1, 64] of dtype) must be ZERO on
+ * entry and receives the pooled map (16-byte max-reductions of post-ReLU values: bit-identical to pooling the stored map). */
+int rtsds_stem_pair_tc_fwd_pool(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                                const float* shift, int dtype, void* pool, void* y_sp, rtsds_stream_t s);
 int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, const void* d_raw_cp,
                              const void* d_raw_sp, float* dw_ws, float* g7_oihw, float* g3_oihw,
                              rtsds_stream_t s);

@@ -119,6 +119,7 @@ SIGNATURES = {
     "rtsds_stem_conv_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P, _I, _P, _P]),
     "rtsds_stem_pack_weights": (_I, [_P, _P, _I, _P, _P]),
     "rtsds_stem_pair_tc_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "rtsds_stem_pair_tc_fwd_pool": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "rtsds_stem_pair_tc_wgrad": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "rtsds_stem_s2d_pack": (_I, [_P, _I, _I, _I, _P, _P]),
     "rtsds_stem_s2d_weight": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -19,6 +19,8 @@ Data layout in HBM (bf16 production mode; fp32 in check mode):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops, weights_epoch
@@ -89,6 +91,11 @@ class BiSeNetPlan:
     def buf(self, *shape, dtype=None):
         # kernels are handed raw pointers, so the plan must keep every buffer alive itself
         t = torch.empty(shape, dtype=self.tdt if dtype is None else dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def zeros(self, *shape, dtype=None):
+        t = torch.zeros(shape, dtype=self.tdt if dtype is None else dtype, device=self.device)
         self._keep.append(t)
         return t
 
@@ -224,19 +231,27 @@ class BiSeNetPlan:
         # ---- context path: ResNet-18 (build_contextpath.py:18-29) ----
         cp = m.context_path
         ch2, cw2 = cs(H, 7, 2, 3), cs(W, 7, 2, 3)
-        cp0 = stems if s2d else self.buf(n, ch2, cw2, 64)
+        ph, pw = ops.maxpool_out_size(ch2), ops.maxpool_out_size(cw2)
+        # RTSDS_STEM_POOL=1 (eval): the max-pool rides on the stem kernel's epilogue (16-byte max-reductions into a zeroed pooled
+        # map; the 1/2-resolution context-path map is never written): 27 -> 26 launches and 34 MB less traffic per frame, but
+        # measured time-neutral at b=1 (0.3433 vs 0.3417 ms: the reductions cost the stem what the pool launch saved) — off
+        # by default, the separate max-pool launch stays.
+        self.pool_in_stem = fused_stems and not s2d and not self.train and os.environ.get("RTSDS_STEM_POOL", "0") == "1"
+        cp0 = stems if s2d else (None if self.pool_in_stem else self.buf(n, ch2, cw2, 64))
+        x = self.zeros(n, ph, pw, 64) if self.pool_in_stem else self.buf(n, ph, pw, 64)
         if s2d:
             self._stem_pair_s2d(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, stems)
         elif fused_stems:
-            self._stem_pair(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, cp0, sp1)
+            self._stem_pair(cp.conv1, cp.bn1, sp.convblock1.conv1, sp.convblock1.bn, cp0, sp1, pool=x if self.pool_in_stem else None)
         else:
             self._stem(cp.conv1, cp.bn1, cp0, 7, 2, 3)
-        ph, pw = ops.maxpool_out_size(ch2), ops.maxpool_out_size(cw2)
-        x = self.buf(n, ph, pw, 64)
-        if s2d:
+        if self.pool_in_stem:
+            pass
+        elif s2d:
             self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2_ld(cp0, n, ch2, cw2, 64, 128, self.dt, x))
         else:
             self.steps.append(lambda cp0=cp0, x=x: ops.maxpool3x3s2(cp0, x))
+        pool_buf = x
         shape = (n, ph, pw, 64)
         feats = []
         # eval-mode tensor-core path: the global average pools of feature3 / feature4 (ARM pooling, context-path tail) are
@@ -248,9 +263,15 @@ class BiSeNetPlan:
             self._gap_for[id(cp.layer3[-1])] = self._gap3
             self._gap_for[id(cp.layer4[-1])] = self._gap4
         for layer in (cp.layer1, cp.layer2, cp.layer3, cp.layer4):
-            for blk in layer:
+            for bi, blk in enumerate(layer):
                 x, shape = (self._bottleneck if hasattr(blk, "conv3") else self._basic_block)(blk, x, shape)
+                if self.pool_in_stem and layer is cp.layer1 and bi == 0:
+                    # the pooled map has been consumed (conv input + shortcut of the first block): clear it for the next frame's
+                    # max-reductions on the side branch; the next ("join",) — the first downsample block — orders it
+                    self.steps.append(("fork", [lambda pool_buf=pool_buf: pool_buf.zero_()]))
             feats.append((x, shape))
+        if self.pool_in_stem:
+            self.steps.append(("join",))
         (f3, s3), (f4, s4) = feats[2], feats[3]
         if min(h8, w8, s4[1], s4[2]) <= 0:
             raise ops._lib.RtsdsError("input too small for BiSeNet")
@@ -371,7 +392,7 @@ class BiSeNetPlan:
         self.pre_steps.append(pack)
         self.head_steps.append(lambda: ops.stem_s2d_conv_fwd_dt(P, n, oh, ow, wpk, 128, y128, 128, self.dt, scale, shift, ACT_RELU))
 
-    def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp):
+    def _stem_pair(self, conv7, bn7, conv3, bn3, y_cp, y_sp, pool=None):
         """Both stems in one tensor-core kernel (csrc/stem_tc.cu); eval mode: BN folded + ReLU."""
         wpk = self.buf(128, 192)
         scale = self.buf(128, dtype=torch.float32)
@@ -390,7 +411,10 @@ class BiSeNetPlan:
                 ops.check(ops.lib().rtsds_image_u8_to_f32(ops._p(x), self.n, 3, self.h, self.w, self.h, self.w, sc, bi, ops._p(self.x_f32),
                                                           ops._s()), "image_u8_to_f32")
                 x = self.x_f32
-            ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True)
+            if pool is not None:
+                ops.stem_pair_tc_fwd_pool(x, wpk, pool, y_sp, scale, shift)
+            else:
+                ops.stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale, shift, True)
 
         self.pre_steps.append(run)
 
@@ -544,6 +568,8 @@ class BiSeNetPlan:
                 with torch.cuda.graph(g):
                     self.run_mid()
                 self.graph = g
+                if getattr(self, "pool_in_stem", False):
+                    self.run_pre(x)                  # the warm-up pass consumed (and cleared) the stem's pooled map: refill it
             self.graph.replay()
         else:
             self.run_mid()

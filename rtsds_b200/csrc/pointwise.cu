@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(256)
 arm_gate_resize_kernel(ArmSide a0, ArmSide a1, int blocks0, int chunks, int n, int oh, int ow, T* __restrict__ dst, int dst_ld,
                        unsigned long long* trace) {
     __shared__ float s_gate[32];
+    pdl_wait();
     if (trace && threadIdx.x == 0) {
         trace[blockIdx.x * 8 + 0] = clock64();
         unsigned long long gt;
@@ -522,6 +523,7 @@ ffm_head_resize_kernel(const float* __restrict__ f, int f_ld, const float* __res
         // (2 x c serial weight loads per thread): all operands come in with ONE round trip, spread over the block
         for (int i = t; i < c * c; i += FHR_THREADS) { s_w1[i] = __ldg(w1 + i); s_w2[i] = __ldg(w2 + i); s_w[i] = __ldg(wc + i); }
         if (t < c) { s_b1[t] = __ldg(b1 + t); s_b2[t] = __ldg(b2 + t); s_b[t] = bc ? __ldg(bc + t) : 0.f; }
+        pdl_wait();                          // the weights above are parameters; everything below reads the predecessor's output
         // pooled[n][parts][c]: partial means of the producer (one per block of the gather), added in a fixed order
         const int ch = t & 31, stripe = t >> 5;
         float acc = 0.f;
@@ -947,11 +949,11 @@ extern "C" int rtsds_arm_gate_resize(const RtsdsArmSide* a3, const RtsdsArmSide*
     const int blocks0 = (a3->c / 32) * chunks, blocks = groups * chunks;
     cudaStream_t st = as_stream(s);
     if (dtype == RTSDS_F16)
-        arm_gate_resize_kernel<__half><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld, g_arm_trace);
+        launch_pdl(arm_gate_resize_kernel<__half>, dim3(blocks), dim3(256), sm, st, k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__half*>(dst), dst_ld, g_arm_trace);
     else if (dtype == RTSDS_BF16)
-        arm_gate_resize_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, g_arm_trace);
+        launch_pdl(arm_gate_resize_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), sm, st, k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, g_arm_trace);
     else if (dtype == RTSDS_F32)
-        arm_gate_resize_kernel<float><<<blocks, 256, sm, st>>>(k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld, g_arm_trace);
+        launch_pdl(arm_gate_resize_kernel<float>, dim3(blocks), dim3(256), sm, st, k[0], k[1], blocks0, chunks, n, oh, ow, reinterpret_cast<float*>(dst), dst_ld, g_arm_trace);
     else { set_error("arm_gate_resize: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
     return check_launch("arm_gate_resize_kernel");
@@ -971,8 +973,8 @@ extern "C" int rtsds_ffm_head_resize(const float* f, int f_ld, const float* pool
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(ffm_head_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; }
     dim3 grid(static_cast<unsigned>(cdiv(oh, FHR_ROWS)), n);
-    ffm_head_resize_kernel<<<grid, FHR_THREADS, smem, as_stream(s)>>>(f, f_ld, pooled, h, w, c, w1, b1, w2, b2, wc, bc, attn_out, oh, ow,
-                                                                      rh, rw, max_rows, pooled_parts, out, g_arm_trace);
+    launch_pdl(ffm_head_resize_kernel, grid, dim3(FHR_THREADS), smem, as_stream(s), f, f_ld, pooled, h, w, c, w1, b1, w2, b2, wc, bc, attn_out,
+               oh, ow, rh, rw, max_rows, pooled_parts, out, g_arm_trace);
     count_launch();
     return check_launch("ffm_head_resize_kernel");
 }

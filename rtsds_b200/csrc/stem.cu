@@ -235,6 +235,7 @@ __device__ __forceinline__ void store8(float* p, const Vec8& r) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const T* __restrict__ x, int n, int h, int w, int c, int x_ld, int oh, int ow, T* __restrict__ y, Div3 dv) {
+    pdl_wait();
     const int cg = c / 8;
     const long long total = static_cast<long long>(n) * oh * ow * cg;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -364,14 +365,14 @@ static int maxpool_fwd_impl(const void* x, int n, int h, int w, int c, int dtype
         return check_launch("maxpool_idx_kernel");
     }
     if (dtype == RTSDS_F16)
-        maxpool_kernel<__half><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __half*>(x), n, h, w, c, x_ld, oh, ow,
-                                                               reinterpret_cast<__half*>(y), dv);
+        launch_pdl(maxpool_kernel<__half>, dim3(grid), dim3(256), 0, as_stream(s), reinterpret_cast<const __half*>(x), n, h, w, c, x_ld, oh, ow,
+                   reinterpret_cast<__half*>(y), dv);
     else if (dtype == RTSDS_BF16)
-        maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, x_ld, oh, ow,
-                                                                      reinterpret_cast<__nv_bfloat16*>(y), dv);
+        launch_pdl(maxpool_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(s), reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c,
+                   x_ld, oh, ow, reinterpret_cast<__nv_bfloat16*>(y), dv);
     else
-        maxpool_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), n, h, w, c, x_ld, oh, ow,
-                                                              reinterpret_cast<float*>(y), dv);
+        launch_pdl(maxpool_kernel<float>, dim3(grid), dim3(256), 0, as_stream(s), reinterpret_cast<const float*>(x), n, h, w, c, x_ld, oh, ow,
+                   reinterpret_cast<float*>(y), dv);
     count_launch();
     return check_launch("maxpool_kernel");
 }

@@ -45,6 +45,10 @@ struct StemTcParams {
     float* stats_sp;
     __nv_bfloat16* y_cp;       // NHWC [n,oh,ow,64]
     __nv_bfloat16* y_sp;
+    // eval: MaxPool2d(3, 2, 1) of the context-path map fused into the epilogue.  pool: NHWC [n,ph,pw,64], ZERO on entry; every
+    // tile max-reduces its (post-ReLU, >= 0) partial windows into it; y_cp itself is then never written.
+    void* pool;
+    int ph, pw;
     // wgrad
     float* dw;                 // [128][192] fp32, accumulated
 };
@@ -86,6 +90,20 @@ __device__ __forceinline__ void patch_issue(const StemTcParams& p, int t, int ti
             ptx::cp_async_4(patch + (c * P::PH + prow) * P::RP + (pcol & 1) * P::PO + (pcol >> 1),
                             ok ? xi + (static_cast<long long>(c) * p.h + iy) * p.w + ix : p.x, ok);
     }
+}
+
+// packed 16-bit pair maximum / 16-byte max-reduction to global memory (REDG.MAX.F16x8 / BF16x8)
+template <bool F16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if (F16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ void red_max_16x8(void* dst, uint4 v) {
+    if (F16) asm volatile("red.global.v4.f16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // one thread builds row `m` of the swizzled tile from the staged patch.  Fully unrolled: every
@@ -322,7 +340,45 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
                 *reinterpret_cast<uint4*>(stage + m * 128 + ((j ^ (m & 7)) << 4)) = packed[j];
             ptx::fence_proxy_async();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (issuer) {
+            if (set == 0 && p.pool) {
+                // ---- fused 3x3 stride-2 max-pool (build_contextpath.py:21, nn.MaxPool2d(3, 2, 1)): the staged tile covers rows
+                // [y0, y0+th) x columns [x0, x0+tw) of the stem output; it holds part of the windows of pooled rows
+                // y0/2 .. (y0+th)/2 and columns x0/2 .. (x0+tw)/2.  Each (pooled pixel, 8-channel group) takes the maximum
+                // over the window pixels inside this tile and max-reduces it into the (zeroed) pooled map: values are
+                // post-ReLU (>= 0) and max is exact, so the result is bit-identical to pooling the stored map.
+                int i0, y0, x0;
+                tile_coords(p, t, 0, &i0, &y0, &x0);
+                const int th = p.tile_h, tw = p.tile_w;
+                const int npy = th / 2 + 1, npx = tw / 2 + 1;
+                const int items = npy * npx * 8;
+                for (int it2 = m; it2 < items; it2 += 128) {
+                    const int g = it2 & 7;
+                    const int pp = it2 >> 3;
+                    const int ly = pp / npx, lx = pp - ly * npx;
+                    const int py = y0 / 2 + ly, px = x0 / 2 + lx;
+                    if (py >= p.ph || px >= p.pw) continue;
+                    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+                    bool any = false;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int ry = 2 * py + dy - y0;
+                        if (ry < 0 || ry >= th || 2 * py + dy >= p.oh) continue;
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int rx = 2 * px + dx - x0;
+                            if (rx < 0 || rx >= tw || 2 * px + dx >= p.ow) continue;
+                            const int mm = ry * tw + rx;
+                            const uint4 u = *reinterpret_cast<const uint4*>(stage + mm * 128 + ((g ^ (mm & 7)) << 4));
+                            acc.x = max16x2<F16>(acc.x, u.x); acc.y = max16x2<F16>(acc.y, u.y);
+                            acc.z = max16x2<F16>(acc.z, u.z); acc.w = max16x2<F16>(acc.w, u.w);
+                            any = true;
+                        }
+                    }
+                    if (any)
+                        red_max_16x8<F16>(reinterpret_cast<uint8_t*>(p.pool) +
+                                          (((static_cast<long long>(i0) * p.ph + py) * p.pw + px) * 64 + g * 8) * 2, acc);
+                }
+            } else if (issuer) {
                 int i0, y0, x0;
                 tile_coords(p, t, 0, &i0, &y0, &x0);
                 ptx::tma_store_4d(omap, stage, 0, x0, y0, i0);     // clipped at the image border
@@ -512,10 +568,11 @@ extern "C" int rtsds_stem_pack_weights(const float* w7_oihw, const float* w3_oih
 
 // Fused tensor-core stems.  x: NCHW fp32 [n,3,h,w]; wpk from rtsds_stem_pack_weights; scale/shift: fp32 [128]
 // (context-path BN in 0..63, spatial-path BN in 64..127) or NULL; stats_*: fp32 [2*64] train-mode sums or NULL.
-extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
-                                      const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
-                                      void* y_sp, rtsds_stream_t s) {
-    RTSDS_REQUIRE(x && wpk && y_cp && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
+static int stem_pair_fwd_impl(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                              const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
+                              void* y_sp, void* pool, rtsds_stream_t s) {
+    RTSDS_REQUIRE(x && wpk && (y_cp || pool) && y_sp && n > 0 && h > 0 && w > 0, "stem_pair_tc_fwd: bad argument");
+    RTSDS_REQUIRE(!pool || (relu && !stats_cp), "stem_pair_tc_fwd_pool: the fused max-pool needs the ReLU epilogue (eval mode)");
     RTSDS_REQUIRE(is_16bit(dtype), "stem_pair_tc_fwd: dtype must be bf16 or fp16");
     RTSDS_REQUIRE((stats_cp == nullptr) == (stats_sp == nullptr), "stem_pair_tc_fwd: stats go together");
     int rc = rtsds_check_device();
@@ -527,8 +584,11 @@ extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const
     p.x = x; p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.scale = scale; p.shift = shift; p.relu = relu;
     p.stats_cp = stats_cp; p.stats_sp = stats_sp;
     p.y_cp = reinterpret_cast<__nv_bfloat16*>(y_cp); p.y_sp = reinterpret_cast<__nv_bfloat16*>(y_sp);
+    p.pool = pool; p.ph = (p.oh + 2 - 3) / 2 + 1; p.pw = (p.ow + 2 - 3) / 2 + 1;
+    RTSDS_REQUIRE(!pool || (p.tile_h % 2 == 0 && p.tile_w % 2 == 0 && (reinterpret_cast<uintptr_t>(pool) & 15) == 0),
+                  "stem_pair_tc_fwd_pool: tile geometry / alignment");
     StemWgMaps maps;
-    rc = stem_make_maps(p, y_cp, y_sp, &maps, "stem_pair_tc_fwd");
+    rc = stem_make_maps(p, y_cp ? y_cp : y_sp, y_sp, &maps, "stem_pair_tc_fwd");
     if (rc != RTSDS_OK) return rc;
     const size_t smem = 1024 + 3 * S_A_BYTES + 2 * S_ATOM_BYTES + 512 * 4 + 8 * 8 + 16 + S_PATCHES * S_PATCH_FLOATS * 4;
     static bool done = false;
@@ -555,6 +615,21 @@ extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const
 #undef STEM_FWD
     count_launch();
     return check_launch("stem_fwd_tc_kernel");
+}
+
+extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                                      const float* shift, int relu, float* stats_cp, float* stats_sp, int dtype, void* y_cp,
+                                      void* y_sp, rtsds_stream_t s) {
+    RTSDS_REQUIRE(y_cp, "stem_pair_tc_fwd: NULL y_cp");
+    return stem_pair_fwd_impl(x, n, h, w, wpk, scale, shift, relu, stats_cp, stats_sp, dtype, y_cp, y_sp, nullptr, s);
+}
+
+// Eval-mode form with nn.MaxPool2d(3, 2, 1) of the context-path stem fused in: the 1/2-resolution map is never written,
+// `pool` (NHWC [n, (oh-1)/2+1, (ow-1)/2+1, 64], 16-bit) must be ZERO on entry and receives the pooled map.
+extern "C" int rtsds_stem_pair_tc_fwd_pool(const float* x, int n, int h, int w, const void* wpk, const float* scale,
+                                           const float* shift, int dtype, void* pool, void* y_sp, rtsds_stream_t s) {
+    RTSDS_REQUIRE(pool, "stem_pair_tc_fwd_pool: NULL pool");
+    return stem_pair_fwd_impl(x, n, h, w, wpk, scale, shift, 1, nullptr, nullptr, dtype, nullptr, y_sp, pool, s);
 }
 
 // Fused weight gradient of both stems.  d_raw_*: NHWC bf16 [n,oh,ow,64]; dw_ws: fp32 [128*192] scratch that is

@@ -54,6 +54,7 @@ tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int 
                    const float* __restrict__ scale, const float* __restrict__ shift, int act, float* stats,
                    float* __restrict__ y, int y_ld, float* gap_out, float gap_scale) {
     __shared__ float s_stats[2][8][32];
+    pdl_wait();
     const int k = K > 0 ? K : k_rt;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     // blockIdx.y = image: the fused global average pool (gap_out) sums per image
@@ -206,9 +207,9 @@ extern "C" int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int
     const dim3 grid(static_cast<unsigned>(g), static_cast<unsigned>(n));
     const float gsc = 1.0f / static_cast<float>(npix);
     if (k == 3)
-        tapn_gather_kernel<3><<<grid, 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
+        launch_pdl(tapn_gather_kernel<3>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
     else
-        tapn_gather_kernel<0><<<grid, 256, 0, as_stream(s)>>>(t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
+        launch_pdl(tapn_gather_kernel<0>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
     count_launch();
     return check_launch("tapn_gather_kernel");
 }

@@ -220,6 +220,14 @@ def stem_pair_tc_fwd(x, wpk, y_cp, y_sp, scale=None, shift=None, relu=True, stat
                                        dtype_code(wpk.dtype), _p(y_cp), _p(y_sp), _s()), "stem_pair_tc_fwd")
 
 
+def stem_pair_tc_fwd_pool(x, wpk, pool, y_sp, scale, shift) -> None:
+    """Both stems + folded BN + ReLU, with MaxPool2d(3,2,1) of the context-path map fused in; `pool` must be zero on entry."""
+    n, _, h, w = x.shape
+    assert wpk.dtype == pool.dtype == y_sp.dtype
+    check(lib().rtsds_stem_pair_tc_fwd_pool(_p(x), n, h, w, _p(wpk), _p(scale), _p(shift), dtype_code(wpk.dtype), _p(pool), _p(y_sp),
+                                            _s()), "stem_pair_tc_fwd_pool")
+
+
 def stem_pair_tc_wgrad(x, d_raw_cp, d_raw_sp, dw_ws, g7, g3) -> None:
     n, _, h, w = x.shape
     check(lib().rtsds_stem_pair_tc_wgrad(_p(x), n, h, w, _p(d_raw_cp), _p(d_raw_sp), _p(dw_ws), _p(g7), _p(g3), _s()),

@@ -526,3 +526,24 @@ def test_resnet101_context_path_training_vs_oracle(cuda, precision):
             assert e < 5e-2, (k, e)
     record(f"bisenet_r101_train_2x128x192/{precision}/grads", worst_l2_rel=worst, tensors=n_checked)
     assert n_checked > 250
+
+
+def test_stem_with_fused_maxpool_switch_is_bit_identical(cuda):
+    """RTSDS_STEM_POOL=1: MaxPool2d(3,2,1) fused into the stem epilogue (max-reductions of post-ReLU values into a zeroed
+    map, re-zeroed inside the frame graph once consumed) gives bit-identical logits, frame after frame."""
+    import subprocess
+    import sys
+
+    code = ("import torch, os, sys; sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'tests'));"
+            "from test_gpu_bisenet import _model, _input;"
+            "m = _model(3, 'fp16').eval(); x, _ = _input(3, 1, 256, 512);"
+            "outs = [m((x + i).cuda()).cpu() for i in range(3)]; torch.save(outs, sys.argv[1])")
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/rtsds_stem_pool_{flag}.pt"
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, RTSDS_STEM_POOL=flag), capture_output=True, text=True,
+                           timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(path))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
