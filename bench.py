@@ -37,7 +37,7 @@ EVAL_DTYPE = "fp16"                # eval-mode operand / activation type (fp32 a
 FWD_GFLOP_PER_IMG = 51.26          # conv FLOPs (2*MAC) of one eval forward at 512x1024
 FWD_CONV_MB_PER_IMG = 236.0        # ideal bf16 conv traffic
 LOGITS_MB_PER_IMG = 39.8           # fp32 [19,512,1024] API-boundary write
-CONV_DRAM_BYTES_PER_FORWARD = 120977408   # dram__bytes_read+write summed over the 22 conv launches (profiles/r01_conv_tc_infer_ncu_full.csv)
+CONV_DRAM_BYTES_PER_FORWARD = 147054336   # dram__bytes_read+write summed over the conv launches of one forward (profiles/r02_conv_tc_infer_ncu_full.csv)
 
 
 def peaks():
@@ -466,7 +466,7 @@ def run_infer(args, rank, world, local):
         "latency_cold_l2_ms": round(statistics.median(cold), 4),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None if r101 else CONV_DRAM_BYTES_PER_FORWARD, "peak_source": pk["source"],
-                     "traffic_source": "ncu --set full of the 22 conv launches of one forward (cold L2), profiles/r01_conv_tc_infer_ncu_full.csv",
+                     "traffic_source": "ncu --set full of the conv launches of one forward (cold L2), profiles/r02_conv_tc_infer_ncu_full.csv",
                      "kernel": "conv_tc_kernel (22 launches/forward, aggregated; each launch timed as the average of 20 back-to-back graph-replayed repeats, split-K finish kernels included)", "flops_per_step": tc_flops,
                      "kernel_ms_per_step": round(tc_ms, 4)},
         "whole_step": None if r101 else {"tflops": round(FWD_GFLOP_PER_IMG / step_ms, 2), "frac_of_bf16_peak": round(FWD_GFLOP_PER_IMG / step_ms / pk["bf16_tflops"], 4),
