@@ -58,6 +58,15 @@ const char* rtsds_last_error_string(void);
 int         rtsds_check_device(void);
 /* number of kernel launches issued by this library since load (all threads). */
 int64_t     rtsds_launch_count(void);
+/* Deterministic mode (default off; RTSDS_DETERMINISTIC=1 in the environment turns it on at load).  SURVEY.md §5/§7.2 ask
+ * for run-to-run reproducible parity runs: ATen's CPU path, which the reference's results come from, sums in a fixed
+ * order.  When on, the cross-CTA floating-point reductions of the training path — train-mode BatchNorm sum / sum of
+ * squares in every conv and stem epilogue, the weight-gradient partials of every wgrad kernel, the BatchNorm-backward
+ * sums — are accumulated exactly (64.64 fixed point, integer atomics, one rounding to fp32 at the end) in library-owned
+ * scratch instead of through fp32 atomics, so results do not depend on CTA arrival order.  Buffers and signatures are
+ * unchanged; each affected call costs one memset and one small finishing launch more. */
+void        rtsds_set_deterministic(int on);
+int         rtsds_get_deterministic(void);
 
 /* ------------------------------------------------------------------------
  * Metric: utils.fast_hist (utils.py:52-58)

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rtsds_last_error_string": (C.c_char_p, []),
     "rtsds_check_device": (_I, []),
     "rtsds_launch_count": (_L, []),
+    "rtsds_set_deterministic": (None, [_I]),
+    "rtsds_get_deterministic": (_I, []),
     "rtsds_confusion_hist": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "rtsds_argmax_hist": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),
     "rtsds_argmax_hist_u8": (_I, [_P, _P, _I, _I, _L, _P, _P, _P]),

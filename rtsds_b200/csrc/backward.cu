@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ raw,
                      int raw_ld, const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ fsc, const float* __restrict__ fsh, long long n_pix, int c,
-                     int relu, float* sums) {
+                     int relu, float* sums, unsigned long long* det) {
     extern __shared__ float sh[];             // [2*cp]
     const int cg = (c + 7) / 8, cp = cg * 8;
     for (int i = threadIdx.x; i < 2 * cp; i += blockDim.x) sh[i] = 0.f;
@@ -93,13 +93,24 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
                 }
             }
         }
+        if (det) {            // deterministic mode: this thread's partial sums go straight into the exact accumulators
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sh[g8 * 8 + j], s1[j]);
-            atomicAdd(&sh[cp + g8 * 8 + j], s2[j]);
+            for (int j = 0; j < 8; ++j) {
+                if (g8 * 8 + j < c) {
+                    det_add(det + 2 * (g8 * 8 + j), s1[j]);
+                    det_add(det + 2 * (c + g8 * 8 + j), s2[j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sh[g8 * 8 + j], s1[j]);
+                atomicAdd(&sh[cp + g8 * 8 + j], s2[j]);
+            }
         }
     }
     __syncthreads();
+    if (det) return;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         atomicAdd(&sums[i], sh[i]);
         atomicAdd(&sums[c + i], sh[cp + i]);
@@ -996,7 +1007,12 @@ static int bn_bwd_reduce_impl(const void* dy, int dy_ld, const void* y, int y_ld
     cudaStream_t st = as_stream(s);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st);
     if (e != cudaSuccess) { set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
-    if (bns_ok(c, dtype, dy_ld, raw_ld, relu ? y : nullptr, y_ld, n_pix)) {
+    unsigned long long* det = nullptr;
+    if (det_mode()) {             // deterministic mode: register-form kernel + exact accumulators, rounded into sums afterwards
+        det = det_scratch(st, 2 * static_cast<size_t>(c));
+        if (!det) return RTSDS_ECUDA;
+    }
+    if (!det && bns_ok(c, dtype, dy_ld, raw_ld, relu ? y : nullptr, y_ld, n_pix)) {
         const bool with_y = relu && y;
         const int nt = with_y ? 3 : 2;
         const long long n_tiles = cdiv(n_pix, static_cast<int64_t>(BNS_TILE / (c * 2)));
@@ -1023,13 +1039,15 @@ static int bn_bwd_reduce_impl(const void* dy, int dy_ld, const void* y, int y_ld
     DISPATCH_T(dtype,
                (bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(
                    reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
-                   reinterpret_cast<const __nv_bfloat16*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums)),
+                   reinterpret_cast<const __nv_bfloat16*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums, det)),
                (bn_bwd_reduce_kernel<float><<<grid, 256, sm, st>>>(
                    reinterpret_cast<const float*>(dy), dy_ld, reinterpret_cast<const float*>(y), y_ld,
-                   reinterpret_cast<const float*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums)),
+                   reinterpret_cast<const float*>(raw), raw_ld, mean, invstd, fsc, fsh, n_pix, c, relu, sums, det)),
                "bn_bwd_reduce");
     count_launch();
-    return check_launch("bn_bwd_reduce_kernel");
+    int rc = check_launch("bn_bwd_reduce_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, sums, 2 * static_cast<size_t>(c), false, st);
+    return rc;
 }
 
 extern "C" int rtsds_bn_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* raw, int raw_ld,

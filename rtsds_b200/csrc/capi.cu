@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <atomic>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace rtsds {
 
@@ -39,9 +41,66 @@ int num_sms() {
     return cached[dev];
 }
 
+// ---- deterministic mode (common.cuh: det_add) ------------------------------------------------------------------------
+static std::atomic<int> g_det{-1};
+bool det_mode() {
+    int v = g_det.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("RTSDS_DETERMINISTIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+        g_det.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+
+struct DetRegion { unsigned long long* p = nullptr; size_t n = 0; };
+static std::mutex g_det_mu;
+static std::map<std::pair<int, cudaStream_t>, DetRegion> g_det_regions;
+
+unsigned long long* det_scratch(cudaStream_t st, size_t n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_det_mu);
+    DetRegion& r = g_det_regions[std::make_pair(dev, st)];
+    if (r.n < n) {
+        // grow: cudaFree waits for the work that still reads the old region
+        if (r.p) cudaFree(r.p);
+        size_t want = n < (size_t(1) << 20) ? (size_t(1) << 20) : n + n / 4;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&r.p), want * 16);
+        if (e != cudaSuccess) {
+            r.p = nullptr; r.n = 0;
+            set_error("deterministic mode: cudaMalloc of %zu bytes failed: %s", want * 16, cudaGetErrorString(e));
+            return nullptr;
+        }
+        r.n = want;
+    }
+    if (cudaMemsetAsync(r.p, 0, n * 16, st) != cudaSuccess) {
+        set_error("deterministic mode: cudaMemsetAsync failed");
+        return nullptr;
+    }
+    return r.p;
+}
+
+__global__ void det_finish_kernel(const unsigned long long* acc, float* dst, size_t n, int accumulate) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = static_cast<float>(det_value(acc + 2 * i));
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+
+int det_finish(const unsigned long long* acc, float* dst, size_t n, bool accumulate, cudaStream_t st) {
+    if (n == 0) return RTSDS_OK;
+    det_finish_kernel<<<static_cast<unsigned>(cdiv(static_cast<int64_t>(n), 256)), 256, 0, st>>>(acc, dst, n, accumulate ? 1 : 0);
+    count_launch();
+    return check_launch("det_finish_kernel");
+}
+
 }  // namespace rtsds
 
 extern "C" {
+
+void rtsds_set_deterministic(int on) { rtsds::g_det.store(on ? 1 : 0, std::memory_order_relaxed); }
+int rtsds_get_deterministic(void) { return rtsds::det_mode() ? 1 : 0; }
 
 int rtsds_abi_version(void) { return RTSDS_ABI_VERSION; }
 

@@ -57,6 +57,39 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int num_sms();
 
+// ---- deterministic (order-independent) accumulation ------------------------------------------------------------------
+// rtsds_set_deterministic(1): every cross-CTA floating-point reduction of the training path that normally goes through
+// fp32 atomics (train-mode BatchNorm sums, weight-gradient partials, BatchNorm-backward sums) is accumulated EXACTLY
+// instead, in 64.64 two's-complement fixed point with integer atomics, and rounded to fp32 once at the end.  Integer
+// addition is associative, so the result does not depend on the order in which CTAs arrive: two runs are bit-identical.
+// Range +-9.2e18, resolution 5.4e-20 per contribution (an fp32 contribution below that is dropped: it could not have
+// changed an fp32 sum of ordinary magnitude either).  An accumulator is two 64-bit words {low, high}; the scratch that
+// holds them belongs to the library (one region per stream), the caller-visible buffers stay fp32.
+__device__ __forceinline__ void det_add(unsigned long long* acc, float v) {
+    if (v == 0.0f || !(fabsf(v) < 9.0e18f)) return;            // zeros, NaN/inf and out-of-range values are skipped
+    const double d = static_cast<double>(v);
+    const double fl = floor(d);
+    const long long hi = static_cast<long long>(fl);
+    const unsigned long long lo = __double2ull_rz((d - fl) * 18446744073709551616.0);     // (d - fl) in [0,1): < 2^64
+    const unsigned long long old = atomicAdd(acc, lo);
+    const unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
+    const unsigned long long h = static_cast<unsigned long long>(hi) + carry;
+    if (h) atomicAdd(acc + 1, h);
+}
+// out-of-line pair (sum, sum of squares) for the hot epilogues: keeps the fp64 conversion code out of their register budget
+static __device__ __noinline__ void det_add2(unsigned long long* a, float va, unsigned long long* b, float vb) {
+    det_add(a, va);
+    det_add(b, vb);
+}
+__device__ __forceinline__ double det_value(const unsigned long long* acc) {
+    return static_cast<double>(static_cast<long long>(acc[1])) + static_cast<double>(acc[0]) * 5.421010862427522e-20;   // 2^-64
+}
+bool det_mode();
+// zeroed scratch of n accumulators (16 bytes each) for this stream; NULL + error set when the allocation fails
+unsigned long long* det_scratch(cudaStream_t st, size_t n);
+// dst[i] = (accumulate ? dst[i] : 0) + fp32(acc[i]) for i < n, on the stream
+int det_finish(const unsigned long long* acc, float* dst, size_t n, bool accumulate, cudaStream_t st);
+
 // ---- dtype helpers ---------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }

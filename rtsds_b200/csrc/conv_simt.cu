@@ -109,7 +109,16 @@ tap_simt_kernel(const TapProblem p, long long m_total) {
             }
         }
     }
-    if (p.stats) {
+    if (p.det) {                  // deterministic mode: every thread's 4-row sums go into the exact accumulators
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = n0 + tx * 4 + j;
+            if (co < p.cout) {
+                det_add(p.det + 2 * co, cs[j]);
+                det_add(p.det + 2 * (p.cout + co), cq[j]);
+            }
+        }
+    } else if (p.stats) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             atomicAdd(&s_sum[tx * 4 + j], cs[j]);
@@ -131,6 +140,7 @@ struct WgradSimt {
     int n_img, oh, ow, cin, cout, n_taps;
     signed char dh[TAP_MAX], dw[TAP_MAX], map[TAP_MAX];
     float* out;
+    unsigned long long* det;      // deterministic mode: exact accumulators with out's layout, else NULL
     long long pix_per_split;
 };
 
@@ -197,7 +207,11 @@ wgrad_simt_kernel(const WgradSimt p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = ci0 + tx * 4 + j;
-            if (ci < p.cin) atomicAdd(&p.out[(static_cast<long long>(co) * p.n_taps + t) * p.cin + ci], acc[i][j]);
+            if (ci < p.cin) {
+                const long long o = (static_cast<long long>(co) * p.n_taps + t) * p.cin + ci;
+                if (p.det) det_add(p.det + 2 * o, acc[i][j]);
+                else atomicAdd(&p.out[o], acc[i][j]);
+            }
         }
     }
 }
@@ -374,14 +388,22 @@ __global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant
 
 int conv_cout_pad(int cout);
 
-static int simt_run(const TapProblem& t, int in_dtype, cudaStream_t st) {
+static int simt_run(const TapProblem& t_in, int in_dtype, cudaStream_t st) {
+    TapProblem t = t_in;
     const long long m_total = static_cast<long long>(t.n_img) * t.oh * t.ow;
     if (m_total == 0) return RTSDS_OK;
+    t.det = nullptr;
+    if (t.stats && det_mode()) {
+        t.det = det_scratch(st, 2 * static_cast<size_t>(t.cout));
+        if (!t.det) return RTSDS_ECUDA;
+    }
     dim3 grid(static_cast<unsigned>(cdiv(m_total, SC_TM)), static_cast<unsigned>(cdiv(t.cout, SC_TN)));
     if (in_dtype == RTSDS_BF16) tap_simt_kernel<__nv_bfloat16><<<grid, SC_THREADS, 0, st>>>(t, m_total);
     else tap_simt_kernel<float><<<grid, SC_THREADS, 0, st>>>(t, m_total);
     count_launch();
-    return check_launch("tap_simt_kernel");
+    int rc = check_launch("tap_simt_kernel");
+    if (rc == RTSDS_OK && t.det) rc = det_finish(t.det, t.stats, 2 * static_cast<size_t>(t.cout), true, st);
+    return rc;
 }
 
 }  // namespace rtsds
@@ -450,10 +472,17 @@ extern "C" int rtsds_conv2d_simt_wgrad(const RtsdsConvDesc* d, const void* x, co
     splits = cdiv(m_total, p.pix_per_split);
     dim3 grid(static_cast<unsigned>(cdiv(d->cout, SC_TM)), static_cast<unsigned>(cdiv(d->cin, SC_TN) * t.n_taps),
               static_cast<unsigned>(splits));
+    const size_t n_dw = static_cast<size_t>(d->cout) * t.n_taps * d->cin;
+    if (det_mode()) {
+        p.det = det_scratch(as_stream(s), n_dw);
+        if (!p.det) return RTSDS_ECUDA;
+    }
     if (d->in_dtype == RTSDS_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, SC_THREADS, 0, as_stream(s)>>>(p);
     else wgrad_simt_kernel<float><<<grid, SC_THREADS, 0, as_stream(s)>>>(p);
     count_launch();
-    return check_launch("wgrad_simt_kernel");
+    rc = check_launch("wgrad_simt_kernel");
+    if (rc == RTSDS_OK && p.det) rc = det_finish(p.det, dw_packed, n_dw, true, as_stream(s));
+    return rc;
 }
 
 static int pack_weight_impl(const float* w_oihw, int cout, int cin, int cin_pad, int kh, int kw, int cout_pad, int dtype,

@@ -71,6 +71,9 @@ struct TcParams {
     const float* shift;
     const void* residual;                 // same dtype as y
     float* stats;
+    int dbg;                              // RTSDS_TC_DBG bit mask, persistent kernel only (bound-finding experiments; results are
+                                          // WRONG when set): 1 no global stores, 2 no tcgen05.ld, 4 no MMA, 8 no A-tile TMA
+    unsigned long long* det;              // deterministic mode: [2*cout] exact accumulators (common.cuh: det_add) instead of stats
     void* y;
     float* partial;                       // split-K slices [split][M_total][cout_pad]
     int out_dtype, act;
@@ -96,6 +99,9 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
     return v[0];
 }
 
+constexpr int TR_PITCH = 36;                                  // floats per row of the per-warp transpose scratch (16-byte aligned rows)
+constexpr int TR_BYTES = 4 * 32 * TR_PITCH * 4;               // four epilogue warps
+
 // Epilogue of one 32-column chunk of an accumulator row: optional train-mode BatchNorm statistics of the raw value,
 // scale/shift (folded BatchNorm or bias), residual add, activation, 16-byte stores.  Shared by both conv kernels.
 // rpre != NULL: the 16-bit residual of this row (all BLOCK_N channels, 16-byte pieces) was fetched into registers while the
@@ -103,18 +109,43 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 template <int BLOCK_N>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[32], int c0, int n0, bool valid, long long out_off,
                                                   long long res_off, const float* s_scale, const float* s_shift, float* s_stats,
-                                                  int lane, const uint4* rpre = nullptr) {
+                                                  int lane, const uint4* rpre = nullptr, float* s_tr = nullptr) {
     const int co0 = n0 + c0;
             if (p.stats) {
+            float s1, s2;
+            if (s_tr) {
+                // column sums of this warp's 32 x 32 block through a shared-memory transpose (s_tr: this warp's own
+                // [32][TR_PITCH] floats): 8 row stores + 32 conflict-free column loads per thread instead of two
+                // 31-shuffle butterflies with their selects (measured 0.65 us of a 1.45 us chunk, epi_timeline.py)
+                float4* rowp = reinterpret_cast<float4*>(s_tr + lane * TR_PITCH);
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    rowp[g] = valid ? make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float x0 = s_tr[i * TR_PITCH + lane], x1 = s_tr[(i + 1) * TR_PITCH + lane];
+                    a0 += x0; a1 += x1;
+                    b0 = fmaf(x0, x0, b0); b1 = fmaf(x1, x1, b1);
+                }
+                __syncwarp();
+                s1 = a0 + a1; s2 = b0 + b1;
+            } else {
             float t[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] : 0.0f;
-            float s1 = warp_transpose_sum(t, lane);
+            s1 = warp_transpose_sum(t, lane);
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] * v[j] : 0.0f;
-            float s2 = warp_transpose_sum(t, lane);
-            atomicAdd(&s_stats[c0 + lane], s1);
-            atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
+            s2 = warp_transpose_sum(t, lane);
+            }
+            if (p.det) {                  // order-independent: this warp's 32-row sums go straight into the exact accumulators
+                if (co0 + lane < p.cout) det_add2(p.det + 2 * (co0 + lane), s1, p.det + 2 * (p.cout + co0 + lane), s2);
+            } else {
+                atomicAdd(&s_stats[c0 + lane], s1);
+                atomicAdd(&s_stats[BLOCK_N + c0 + lane], s2);
+            }
         }
 
         const bool full = (co0 + 32 <= p.cout);
@@ -125,7 +156,9 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             // (the four epilogue warps sit on four different schedulers, one warp each: nothing hides latency, so every
             // per-element branch or scalar shared load costs its full latency — uniform switches are hoisted out of the
             // element loops and the per-channel constants come in as 16-byte broadcast loads)
-            {
+            // (train-mode forward writes the RAW conv output and dgrad has no affine at all: both skip this — measured
+            // 0.34 us of a 0.8 us chunk on the training shapes, tools/debug/epi_timeline.py)
+            if (p.scale != nullptr || p.shift != nullptr) {
                 const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
                 const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
@@ -203,7 +236,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             const float s1 = warp_transpose_sum(t, lane);
             s_stats[(threadIdx.x >> 5 & 3) * BLOCK_N + c0 + lane] += s1;      // this warp's own slot: fixed summation order
         }
-        if (valid) {
+        if (valid && !(p.dbg & 1)) {
             if (out16 && full) {
                 uint4 o[4];
                 if (f16) {
@@ -459,7 +492,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             } else {
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr);
+                // (transpose scratch of the BatchNorm sums: the operand ring, idle once the accumulator is complete — not with
+                // A-tile multicast, where a peer's TMA may still write into this CTA's ring)
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
+                                           p.mc <= 1 ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
         };
         // (two chunks per trip — both TMEM loads in flight, two interleaved instruction streams — was measured: 168
@@ -481,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (CW == 64) do_chunk(rb, c0 + 32);
             if (trace && threadIdx.x == 64 && c0 == 0) trace[14] = clock64();
         }
-        if (p.stats && p.split_k == 1) {
+        if (p.stats && !p.det && p.split_k == 1) {
             // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
@@ -540,9 +576,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                     }
                 }
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
+                                           p.mc <= 1 ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
-            if (p.stats) {
+            if (p.stats && !p.det) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
@@ -592,11 +629,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // a multiple of the 1024-byte swizzle pattern) and each tap's A operand is a WINDOW into it: UMMA descriptor start =
 // tile + ((r*d)*16 + s*d) * 128 B, 8-row groups 2048 B apart.  4x fewer TMA rows than the tap-wise form — the TMA row
 // rate (~128 B per 8 clk per SM), not HBM or the tensor pipe, is what bounds the tap-wise kernels on 64/128-channel layers.
-template <int BLOCK_N, bool B_RESIDENT, bool HALO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+//
+// EPI = number of epilogue warp groups (4 warps each).  The epilogue of these kernels is LATENCY bound, not instruction
+// bound: one warp per scheduler spends ~1200 cycles on the ~100 instructions of a 32-column chunk (tcgen05.ld + wait,
+// convert, strided 16-byte stores; tools/debug/epi_timeline.py), which caps a CTA at ~1 output tile per 3-6 us while the MMA
+// loop of the 64..256-channel training layers needs 1-2 us.  With EPI = 2 a second group drains the NEXT tile at the same
+// time (accumulator ring of 2*EPI TMEM buffers; tile j of the CTA -> buffer j % (2*EPI), group j % EPI), two warps per
+// scheduler hide each other's latency, and every group keeps its own scale/shift/statistics staging and named barrier.
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-    constexpr uint32_t TMEM_COLS = 2 * (BLOCK_N < 32 ? 32 : BLOCK_N);
+    constexpr int NACC = 2 * EPI;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
     const uint32_t IDESC = ptx::umma_idesc_16(TC_BLOCK_M, BLOCK_N, p.f16 != 0);
 
     extern __shared__ uint8_t smem_raw[];
@@ -607,16 +653,16 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + static_cast<size_t>(stages) * a_stage;
     const size_t b_slots = B_RESIDENT ? static_cast<size_t>(kb_total) : static_cast<size_t>(stages);
-    float* s_scale = reinterpret_cast<float*>(smem_b + b_slots * B_BYTES);
-    float* s_shift = s_scale + BLOCK_N;
-    float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 2 * BLOCK_N);
+    float* s_epi = reinterpret_cast<float*>(smem_b + b_slots * B_BYTES);      // per group: scale | shift | stats [2] (BLOCK_N each)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_epi + EPI * 4 * BLOCK_N);
     uint64_t* empty_bar = full_bar + stages;
-    uint64_t* acc_full = empty_bar + stages;                // [2]
-    uint64_t* acc_empty = acc_full + 2;                     // [2]
-    uint64_t* b_full = acc_empty + 2;
+    uint64_t* acc_full = empty_bar + stages;                // [NACC]
+    uint64_t* acc_empty = acc_full + NACC;                  // [NACC]
+    uint64_t* b_full = acc_empty + NACC;
     uint64_t* b_free = b_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
+    // transpose scratch of the BatchNorm sums (only allocated when p.stats: tcp_smem_bytes' `extra`)
+    float* s_tr_all = p.stats ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15)) : nullptr;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -629,14 +675,14 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         ptx::prefetch_tmap(&maps.b);
         ptx::prefetch_tmap(&maps.a[0]);
         for (int i = 0; i < stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 128); }
         ptx::mbar_init(b_full, 1);
         ptx::mbar_init(b_free, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
     if (warp >= 2)
-        for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += TC_THREADS - 64) s_stats[i] = 0.0f;
+        for (int i = threadIdx.x - 64; i < EPI * 4 * BLOCK_N; i += 128 * EPI) s_epi[i] = 0.0f;
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -669,6 +715,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 if (HALO) {
                     for (int cc = 0; cc < p.kchunks; ++cc) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (p.dbg & 8) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
                         ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.halo_rows) * 16 * 128);
                         ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * a_stage, &maps.a[1], &full_bar[stage], cc * TC_BLOCK_K,
                                          w0 - p.halo_d, h0 - p.halo_d, img);
@@ -678,6 +725,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 for (int kb = 0; kb < kb_total; ++kb) {
                     const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if ((p.dbg & 8) && B_RESIDENT) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
                     ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + (B_RESIDENT ? 0 : B_BYTES));
                     ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES, &maps.a[p.tap_map[tap]], &full_bar[stage],
                                      cc * TC_BLOCK_K, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
@@ -695,8 +743,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, bfull_phase = 0;
-            uint32_t acc_phase[2] = {0, 0};
-            int acc = 0, cur_n = -1;
+            int cur_n = -1;
             for (int tile = t_begin; tile < t_end; ++tile) {
                 const int n_tile = tile / m_tiles;
                 if (B_RESIDENT && n_tile != cur_n) {
@@ -704,9 +751,11 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     bfull_phase ^= 1;
                     cur_n = n_tile;
                 }
-                ptx::mbar_wait(&acc_empty[acc], acc_phase[acc] ^ 1);        // the epilogue has drained this accumulator
+                const int j = tile - t_begin, acc = j % NACC;
+                const uint32_t use_parity = static_cast<uint32_t>(j / NACC) & 1u;      // k-th use of this accumulator: parity k & 1
+                ptx::mbar_wait(&acc_empty[acc], use_parity ^ 1);            // the epilogue has drained this accumulator
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * ACC_COLS;
                 if (HALO) {
                     for (int cc = 0; cc < p.kchunks; ++cc) {
                         ptx::mbar_wait(&full_bar[stage], phase);
@@ -718,6 +767,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             const uint32_t a_addr = a_base + row_off * 128u;
                             const uint64_t da = ptx::umma_desc_k_sw128_ex(a_addr, 2048u, p.halo_baseoff ? (row_off & 7u) : 0u);
                             const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(tap * p.kchunks + cc) * B_BYTES));
+                            if (p.dbg & 4) continue;
 #pragma unroll
                             for (int k = 0; k < TC_BLOCK_K / 16; ++k)
                                 ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
@@ -731,28 +781,34 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ptx::tc_fence_after();
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + static_cast<size_t>(stage) * TC_A_BYTES));
                     const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(B_RESIDENT ? kb : stage) * B_BYTES));
+                    if (!(p.dbg & 4)) {
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k)
                         ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 }
                 ptx::umma_commit(&acc_full[acc]);
                 if (B_RESIDENT && tile + 1 < t_end && (tile + 1) / m_tiles != n_tile) ptx::umma_commit(b_free);
-                acc_phase[acc] ^= 1;
-                acc ^= 1;
             }
         }
         __syncwarp();
     } else {
-        // =================== epilogue (4 warps, 128 TMEM lanes) ===================
-        const int q = warp & 3;
+        // =================== epilogue (EPI groups of 4 warps, 128 TMEM lanes each) ===================
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+        const int grp = (warp - 2) >> 2;                        // epilogue group: tiles j = grp, grp + EPI, ...
+        const int tig = static_cast<int>(threadIdx.x) - 64 - 128 * grp;      // thread in group, 0..127
+        const int bar_id = 1 + grp;
+        float* s_scale = s_epi + grp * 4 * BLOCK_N;
+        float* s_shift = s_scale + BLOCK_N;
+        float* s_stats = s_shift + BLOCK_N;                     // [2*BLOCK_N]
+        float* s_tr = s_tr_all ? s_tr_all + (grp * 4 + q) * 32 * TR_PITCH : nullptr;
         const int row = q * 32 + lane;
         const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
-        uint32_t full_phase[2] = {0, 0};
-        int acc = 0, cur_n = -1;
-        for (int tile = t_begin; tile < t_end; ++tile) {
+        int cur_n = -1;
+        for (int tile = t_begin + grp; tile < t_end; tile += EPI) {
             const int n_tile = tile / m_tiles, m_tile = tile - n_tile * m_tiles;
             const int img = m_tile / tiles_per_img;
             const int trem = m_tile - img * tiles_per_img;
@@ -762,9 +818,9 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const bool valid = (oh < p.oh) && (ow < p.ow);
             if (n_tile != cur_n) {
                 // new N tile: flush the statistics of the old one, load this one's scale / shift
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (p.stats && cur_n >= 0) {
-                    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (p.stats && !p.det && cur_n >= 0) {
+                    for (int i = tig; i < BLOCK_N; i += 128) {
                         const int co = cur_n * BLOCK_N + i;
                         if (co < p.cout) {
                             atomicAdd(&p.stats[co], s_stats[i]);
@@ -773,25 +829,30 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         s_stats[i] = 0.0f; s_stats[BLOCK_N + i] = 0.0f;
                     }
                 }
-                for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+                for (int i = tig; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
                     s_scale[i] = (p.scale && co < p.cout) ? p.scale[co] : 1.0f;
                     s_shift[i] = (p.shift && co < p.cout) ? p.shift[co] : 0.0f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 cur_n = n_tile;
             }
-            ptx::mbar_wait(&acc_full[acc], full_phase[acc]);
-            full_phase[acc] ^= 1;
+            const int j = tile - t_begin, acc = j % NACC;
+            ptx::mbar_wait(&acc_full[acc], static_cast<uint32_t>(j / NACC) & 1u);
             ptx::tc_fence_after();
             const long long out_off = img * p.out_sn + oh * p.out_sh + ow * p.out_sw;
             const long long res_off = img * p.res_sn + oh * p.res_sh + ow * p.res_sw;
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * ACC_COLS;
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32(t_addr + c0, r);
-                ptx::tmem_ld_wait();
+                if (p.dbg & 2) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) r[jj] = static_cast<uint32_t>(jj + c0);
+                } else {
+                    ptx::tmem_ld_32x32(t_addr + c0, r);
+                    ptx::tmem_ld_wait();
+                }
                 if (c0 + 32 >= BLOCK_N) {                 // last read of this accumulator: hand it back to the MMA warp
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(&acc_empty[acc]);
@@ -799,13 +860,12 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane);
+                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr, s_tr);
             }
-            acc ^= 1;
         }
-        if (p.stats && cur_n >= 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+        if (p.stats && !p.det && cur_n >= 0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            for (int i = tig; i < BLOCK_N; i += 128) {
                 const int co = cur_n * BLOCK_N + i;
                 if (co < p.cout) {
                     atomicAdd(&p.stats[co], s_stats[i]);
@@ -852,7 +912,10 @@ splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_t
             const int c = co + j;
             if (c >= cout) break;
             float raw = v[j];
-            if (p.stats) {
+            if (p.det) {
+                det_add(p.det + 2 * c, raw);
+                det_add(p.det + 2 * (cout + c), raw * raw);
+            } else if (p.stats) {
                 atomicAdd(&s_acc[c], raw);
                 atomicAdd(&s_acc[cout + c], raw * raw);
             }
@@ -870,7 +933,7 @@ splitk_finish_kernel(const float* __restrict__ partial, int split, long long m_t
             (void)img;
         }
     }
-    if (p.stats) {
+    if (p.stats && !p.det) {
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * cout; i += blockDim.x)
             if (s_acc[i] != 0.0f) atomicAdd(&p.stats[i], s_acc[i]);
@@ -996,23 +1059,24 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     return check_launch("conv_tc_kernel");
 }
 
-static size_t tcp_smem_bytes(int block_n, int stages, int b_slots, int a_stage = TC_A_BYTES) {
-    return 1024 + static_cast<size_t>(stages) * a_stage + static_cast<size_t>(b_slots) * block_n * TC_BLOCK_K * 2 + 4 * block_n * 4 +
-           (2 * stages + 6) * 8 + 16;
+constexpr int TCP_EPI_MAX = 2;                                // epilogue groups of the persistent kernel (sizes its shared memory)
+static size_t tcp_smem_bytes(int block_n, int stages, int b_slots, int a_stage = TC_A_BYTES, size_t extra = 0) {
+    return 1024 + static_cast<size_t>(stages) * a_stage + static_cast<size_t>(b_slots) * block_n * TC_BLOCK_K * 2 +
+           TCP_EPI_MAX * 4 * block_n * 4 + (2 * stages + 4 * TCP_EPI_MAX + 2) * 8 + 16 + extra;
 }
 
-template <int BLOCK_N, bool B_RESIDENT, bool HALO = false>
-static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI>
+static int launch_tcp_epi(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tcp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(64 + 128 * EPI);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1020,10 +1084,19 @@ static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t sm
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO>, maps, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tcp_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tcp_kernel");
+}
+
+// RTSDS_TCP_EPI=1: one epilogue group (the round-1 form) instead of two — A/B switch
+template <int BLOCK_N, bool B_RESIDENT, bool HALO = false>
+static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+    static int epi = -1;
+    if (epi < 0) { const char* e = getenv("RTSDS_TCP_EPI"); epi = (e && e[0] == '1') ? 1 : 2; }
+    if (epi == 1) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 1>(maps, p, grid, smem, st);
+    return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2>(maps, p, grid, smem, st);
 }
 
 }  // namespace rtsds
@@ -1085,7 +1158,19 @@ static size_t tp_workspace(const TapProblem& t) {
     return static_cast<size_t>(sp) * t.n_img * t.oh * t.ow * conv_cout_pad(t.cout) * sizeof(float);
 }
 
+static int tp_run_inner(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStream_t stream, unsigned long long* det);
+
+// Deterministic mode: the BatchNorm sums of this launch go into exact accumulators, rounded into t.stats afterwards.
 static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    if (!t.stats || !det_mode()) return tp_run_inner(t, workspace, ws_bytes, stream, nullptr);
+    unsigned long long* det = det_scratch(stream, 2 * static_cast<size_t>(t.cout));
+    if (!det) return RTSDS_ECUDA;
+    int rc = tp_run_inner(t, workspace, ws_bytes, stream, det);
+    if (rc != RTSDS_OK) return rc;
+    return det_finish(det, t.stats, 2 * static_cast<size_t>(t.cout), true, stream);
+}
+
+static int tp_run_inner(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStream_t stream, unsigned long long* det) {
     TcMaps maps;
     TcParams p;
     memset(&maps, 0, sizeof(maps));
@@ -1153,7 +1238,8 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     const int box_h = p.mc > 1 && p.tile_h >= 2 ? p.tile_h / 2 : p.tile_h;
     p.out_sn = t.out_sn; p.out_sh = t.out_sh; p.out_sw = t.out_sw;
     p.res_sn = t.res_sn; p.res_sh = t.res_sh; p.res_sw = t.res_sw;
-    p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.y = t.y;
+    p.scale = t.scale; p.shift = t.shift; p.residual = t.residual; p.stats = t.stats; p.det = det; p.y = t.y;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RTSDS_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     p.out_dtype = t.out_dtype; p.act = t.act; p.slope = t.slope; p.f16 = t.in_f16;
     p.gap_out = t.gap_out; p.gap_scale = t.gap_out ? 1.0f / (static_cast<float>(t.oh) * static_cast<float>(t.ow)) : 0.f;
     if (t.gap_out && t.stats) { set_error("conv_tc: gap_out and stats are mutually exclusive"); return RTSDS_EINVAL; }
@@ -1228,10 +1314,11 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
     static int persist_mode = -1;
     if (persist_mode < 0) { const char* e = getenv("RTSDS_NO_PERSISTENT"); persist_mode = (e && e[0] == '1') ? 0 : 1; }
     const long long total_tiles = m_tiles * n_tiles;
+    const size_t tr_extra = t.stats ? TCP_EPI_MAX * TR_BYTES + 16 : 0;      // per-warp transpose scratch of the BatchNorm sums
     // (only with resident weights: when they have to stream, two co-resident non-persistent CTAs per SM hide more latency)
     if (halo) {
         int st = 6;
-        while (st > 2 && tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes) > 227 * 1024) --st;
+        while (st > 2 && tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes, tr_extra) > 227 * 1024) --st;
         if (st > p.kchunks * 4) st = max(2, p.kchunks * 4);
         p.stages = st;
         p.n_tiles_n = n_tiles;
@@ -1239,16 +1326,22 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
         int ctas = num_sms();
         p.tiles_per_cta = static_cast<int>(cdiv(total_tiles, ctas));
         ctas = static_cast<int>(cdiv(total_tiles, p.tiles_per_cta));
-        const size_t smem = tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes);
+        const size_t smem = tcp_smem_bytes(block_n, st, kb_total, p.a_stage_bytes, tr_extra);
         if (block_n == 128) return launch_tcp<128, true, true>(maps, p, ctas, smem, stream);
         if (block_n == 64) return launch_tcp<64, true, true>(maps, p, ctas, smem, stream);
         return launch_tcp<32, true, true>(maps, p, ctas, smem, stream);
     }
-    const bool resident = kb_total >= 1 && tcp_smem_bytes(block_n, 3, kb_total) <= 227 * 1024;
-    if (persist_mode && split == 1 && resident && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30) && !t.gap_out) {
+    const bool resident = kb_total >= 1 && tcp_smem_bytes(block_n, 3, kb_total, TC_A_BYTES, tr_extra) <= 227 * 1024;
+    // Weights that do not fit stream through the ring with the A tiles.  Measured (tools/conv_micro.py, two epilogue groups):
+    // faster than two co-resident one-tile CTAs up to K = 1152 (64->128 s2 with statistics 187 -> 124 us, 128->256 s2
+    // 120 -> 105 us, 128->128 65 -> 62 us), slower beyond (256->256 54 -> 66 us, 512->512 d4 124 -> 146 us): the longer
+    // the K loop, the more the second resident CTA's main loop is worth.  RTSDS_PERSIST_STREAM=<max k-blocks> overrides.
+    static int persist_stream = -1;
+    if (persist_stream < 0) { const char* e = getenv("RTSDS_PERSIST_STREAM"); persist_stream = e ? atoi(e) : 18; }
+    if (persist_mode && split == 1 && (resident || kb_total <= persist_stream) && total_tiles >= 2LL * num_sms() && total_tiles < (1LL << 30) && !t.gap_out) {
         const size_t b_all = static_cast<size_t>(kb_total) * block_n * TC_BLOCK_K * 2;
         int st = resident ? 8 : (block_n == 128 ? 6 : 8);
-        while (st > 2 && tcp_smem_bytes(block_n, st, resident ? kb_total : st) > 227 * 1024) --st;
+        while (st > 2 && tcp_smem_bytes(block_n, st, resident ? kb_total : st, TC_A_BYTES, tr_extra) > 227 * 1024) --st;
         (void)b_all;
         p.stages = st;
         p.n_tiles_n = n_tiles;
@@ -1256,7 +1349,7 @@ static int tp_run(const TapProblem& t, void* workspace, size_t ws_bytes, cudaStr
         int ctas = num_sms();
         p.tiles_per_cta = static_cast<int>(cdiv(total_tiles, ctas));
         ctas = static_cast<int>(cdiv(total_tiles, p.tiles_per_cta));
-        const size_t smem = tcp_smem_bytes(block_n, st, resident ? kb_total : st);
+        const size_t smem = tcp_smem_bytes(block_n, st, resident ? kb_total : st, TC_A_BYTES, tr_extra);
         if (block_n == 128) return resident ? launch_tcp<128, true>(maps, p, ctas, smem, stream) : launch_tcp<128, false>(maps, p, ctas, smem, stream);
         if (block_n == 64) return resident ? launch_tcp<64, true>(maps, p, ctas, smem, stream) : launch_tcp<64, false>(maps, p, ctas, smem, stream);
         if (block_n == 32) return resident ? launch_tcp<32, true>(maps, p, ctas, smem, stream) : launch_tcp<32, false>(maps, p, ctas, smem, stream);
@@ -1414,7 +1507,20 @@ struct WgParams {
     int stages;
     signed char tap_dh[TAP_MAX], tap_dw[TAP_MAX], tap_map[TAP_MAX];
     float* dw;
+    unsigned long long* det;      // deterministic mode: exact accumulators with dw's layout (common.cuh: det_add), else NULL
 };
+
+// Deterministic mode: this thread's accumulator row, one column at a time, into the exact accumulators (common.cuh: det_add)
+// that mirror dw.  Out of line and column-wise so that the production epilogue's registers are untouched.
+__device__ __noinline__ void wgrad_det_epilogue(const WgParams& p, uint32_t trow, int n_cols, int block_n, int co, int ci0, int tap0) {
+    for (int cc = 0; cc < n_cols; ++cc) {
+        const float v = __uint_as_float(ptx::tmem_ld_32x32_x1(trow + cc));       // warp-uniform: every lane loads its row
+        ptx::tmem_ld_wait();
+        const int tt = cc / block_n, ci = ci0 + cc - tt * block_n;
+        if (co < p.cout && ci < p.cin)
+            det_add(p.det + 2 * ((static_cast<long long>(co) * p.n_taps + tap0 + tt) * p.cin + ci), v);
+    }
+}
 
 // TAPS filter taps per CTA share one dy tile (the A operand): each tap has its own x tile (B operand) and its own
 // accumulator columns [tt*BLOCK_N, (tt+1)*BLOCK_N) in TMEM.  TAPS = 3 for the 64-input-channel 3x3 layers: the dy tile
@@ -1517,8 +1623,9 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         const int co = co0 + q * 32 + lane;
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
+        if (p.det) wgrad_det_epilogue(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16), TAPS * BLOCK_N, BLOCK_N, co, ci0, tap0);
 #pragma unroll 1
-        for (int cc = 0; cc < TAPS * BLOCK_N; cc += 32) {
+        for (int cc = p.det ? TAPS * BLOCK_N : 0; cc < TAPS * BLOCK_N; cc += 32) {
             const int tt = cc / BLOCK_N, c0 = cc - tt * BLOCK_N;
             uint32_t r[32];
             ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, r);
@@ -1611,10 +1718,17 @@ static int wgrad_run(const TapProblem& t, int cin, int cout, const void* dy, lon
     if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
     p.stages = stages;
     dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(t.n_taps / taps_per * p.ci_tiles), static_cast<unsigned>(co_tiles));
-    if (taps_per == 3) return launch_wgrad<64, 3>(maps, p, grid, st);
-    if (block_n == 256) return launch_wgrad<256, 1>(maps, p, grid, st);
-    if (block_n == 128) return launch_wgrad<128, 1>(maps, p, grid, st);
-    return launch_wgrad<64, 1>(maps, p, grid, st);
+    const size_t n_dw = static_cast<size_t>(cout) * t.n_taps * cin;
+    if (det_mode()) {
+        p.det = det_scratch(st, n_dw);
+        if (!p.det) return RTSDS_ECUDA;
+    }
+    if (taps_per == 3) rc = launch_wgrad<64, 3>(maps, p, grid, st);
+    else if (block_n == 256) rc = launch_wgrad<256, 1>(maps, p, grid, st);
+    else if (block_n == 128) rc = launch_wgrad<128, 1>(maps, p, grid, st);
+    else rc = launch_wgrad<64, 1>(maps, p, grid, st);
+    if (rc == RTSDS_OK && p.det) rc = det_finish(p.det, dw_packed, n_dw, true, st);
+    return rc;
 }
 
 extern "C" int rtsds_conv2d_tc_wgrad(const RtsdsConvDesc* d, const void* x, const void* dy, float* dw_packed,

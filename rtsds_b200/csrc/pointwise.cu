@@ -148,7 +148,7 @@ scale_shift_act_kernel(const TX* __restrict__ x, const float* __restrict__ scale
 // grid (c/32, psplit, n), block 256 = 32 channels x 8 pixel lanes; out pre-zeroed.
 template <typename T>
 __global__ void __launch_bounds__(256)
-gap_kernel(const T* __restrict__ x, long long hw, int c, int ld, float inv_hw, float* __restrict__ out) {
+gap_kernel(const T* __restrict__ x, long long hw, int c, int ld, float inv_hw, float* __restrict__ out, unsigned long long* det) {
     __shared__ float s[8][33];
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
     const int pl = threadIdx.x >> 5;
@@ -173,7 +173,8 @@ gap_kernel(const T* __restrict__ x, long long hw, int c, int ld, float inv_hw, f
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x];
-        atomicAdd(&out[static_cast<long long>(img) * c + ch], t * inv_hw);
+        if (det) det_add(det + 2 * (static_cast<long long>(img) * c + ch), t * inv_hw);      // deterministic mode (common.cuh)
+        else atomicAdd(&out[static_cast<long long>(img) * c + ch], t * inv_hw);
     }
 }
 
@@ -816,15 +817,22 @@ extern "C" int rtsds_global_avgpool(const void* x, int n, int64_t hw, int c, int
     if (psplit < 1) psplit = 1;
     dim3 grid(cb, static_cast<unsigned>(psplit), n);
     const float inv = 1.0f / static_cast<float>(hw);
+    unsigned long long* det = nullptr;
+    if (psplit > 1 && det_mode()) {
+        det = det_scratch(st, static_cast<size_t>(n) * c);
+        if (!det) return RTSDS_ECUDA;
+    }
     if (dtype == RTSDS_BF16)
-        gap_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, ld, inv, out);
+        gap_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, ld, inv, out, det);
     else if (dtype == RTSDS_F16)
-        gap_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), hw, c, ld, inv, out);
+        gap_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), hw, c, ld, inv, out, det);
     else if (dtype == RTSDS_F32)
-        gap_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), hw, c, ld, inv, out);
+        gap_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), hw, c, ld, inv, out, det);
     else { set_error("global_avgpool: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
-    return check_launch("gap_kernel");
+    int rc = check_launch("gap_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, out, static_cast<size_t>(n) * c, false, st);
+    return rc;
 }
 
 extern "C" int rtsds_arm_gate(const float* pooled, const float* w, const float* b, const float* gamma,

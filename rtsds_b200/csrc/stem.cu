@@ -43,7 +43,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 template <int K, int S>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ scale,
-                 const float* __restrict__ shift, float* stats, void* y, StemParams p) {
+                 const float* __restrict__ shift, float* stats, unsigned long long* det, void* y, StemParams p) {
     constexpr int PH = (ST_TH - 1) * S + K, PW = (ST_TW - 1) * S + K;
     constexpr int PWP = PW | 1;     // odd pitch: stride-S column reads spread over banks
     extern __shared__ float smem[];
@@ -140,8 +140,13 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, con
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = valid ? acc[half * 32 + j] * acc[half * 32 + j] : 0.f;
             float s2 = warp_transpose_sum32(t, lane);
-            atomicAdd(&s_stat[half * 32 + lane], s1);
-            atomicAdd(&s_stat[ST_COUT + half * 32 + lane], s2);
+            if (det) {            // deterministic mode: exact accumulators (common.cuh) in the layout of stats
+                det_add(det + 2 * (half * 32 + lane), s1);
+                det_add(det + 2 * (ST_COUT + half * 32 + lane), s2);
+            } else {
+                atomicAdd(&s_stat[half * 32 + lane], s1);
+                atomicAdd(&s_stat[ST_COUT + half * 32 + lane], s2);
+            }
         }
     }
     if (valid) {
@@ -169,7 +174,7 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, con
                 dst[g] = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
         }
     }
-    if (stats) {
+    if (stats && !det) {
         __syncthreads();
         if (tid < 2 * ST_COUT) atomicAdd(&stats[tid], s_stat[tid]);
     }
@@ -187,9 +192,16 @@ static int launch_stem(const float* x, const float* w, const float* scale, const
         done = true;
     }
     dim3 grid(static_cast<unsigned>(cdiv(p.ow, ST_TW)), static_cast<unsigned>(cdiv(p.oh, ST_TH)), static_cast<unsigned>(p.n));
-    stem_conv_kernel<K, S><<<grid, ST_THREADS, smem, st>>>(x, w, scale, shift, stats, y, p);
+    unsigned long long* det = nullptr;
+    if (stats && det_mode()) {
+        det = det_scratch(st, 2 * ST_COUT);
+        if (!det) return RTSDS_ECUDA;
+    }
+    stem_conv_kernel<K, S><<<grid, ST_THREADS, smem, st>>>(x, w, scale, shift, stats, det, y, p);
     count_launch();
-    return check_launch("stem_conv_kernel");
+    int rc = check_launch("stem_conv_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, stats, 2 * ST_COUT, true, st);
+    return rc;
 }
 
 // ---- MaxPool2d(kernel 3, stride 2, pad 1[, ceil_mode]) on NHWC --------------------

@@ -51,6 +51,9 @@ struct StemTcParams {
     int ph, pw;
     // wgrad
     float* dw;                 // [128][192] fp32, accumulated
+    // deterministic mode (common.cuh: det_add): exact accumulators instead of the fp32 atomics — forward: [2][2*64] in the
+    // layout of stats_cp then stats_sp; wgrad: [128][192] in the layout of dw.  NULL otherwise.
+    unsigned long long* det;
 };
 
 // ---- input patch staging ----------------------------------------------------------------------------------
@@ -308,8 +311,15 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
 #pragma unroll
                     for (int j = 0; j < 32; ++j) tt[j] = valid ? v[j] * v[j] : 0.f;
                     const float s2 = warp_tsum(tt, lane);
-                    atomicAdd(&s_stats[c0 + lane], s1);
-                    atomicAdd(&s_stats[128 + c0 + lane], s2);
+                    if (p.det) {
+                        const int ch = c0 + lane;                      // 0..63 context path, 64..127 spatial path
+                        unsigned long long* d = p.det + 2 * ((ch >> 6) * 128 + (ch & 63));
+                        det_add(d, s1);
+                        det_add(d + 2 * 64, s2);
+                    } else {
+                        atomicAdd(&s_stats[c0 + lane], s1);
+                        atomicAdd(&s_stats[128 + c0 + lane], s2);
+                    }
                 }
                 if (affine) {
 #pragma unroll
@@ -386,7 +396,7 @@ stem_fwd_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams p
             }
         }
         if (issuer) ptx::bulk_wait0();
-        if (p.stats_cp) {
+        if (p.stats_cp && !p.det) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int i = threadIdx.x - 160;              // 0..255
             if (i < 128) {
@@ -471,7 +481,10 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemWgMaps maps, const StemTcParams
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (c0 + j < SK_REAL) atomicAdd(&p.dw[co * SK + c0 + j], __uint_as_float(r[j]));
+                if (c0 + j < SK_REAL) {
+                    if (p.det) det_add(p.det + 2 * (co * SK + c0 + j), __uint_as_float(r[j]));
+                    else atomicAdd(&p.dw[co * SK + c0 + j], __uint_as_float(r[j]));
+                }
         }
     }
     ptx::tc_fence_before();
@@ -604,6 +617,10 @@ static int stem_pair_fwd_impl(const float* x, int n, int h, int w, const void* w
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
     const bool f16 = dtype == RTSDS_F16;
+    if (stats_cp && det_mode()) {
+        p.det = det_scratch(as_stream(s), 256);
+        if (!p.det) return RTSDS_ECUDA;
+    }
 #define STEM_FWD(TWv)                                                                                         \
     do {                                                                                                      \
         if (f16) stem_fwd_tc_kernel<TWv, true><<<grid, SF_THREADS, smem, as_stream(s)>>>(maps, p);            \
@@ -614,7 +631,10 @@ static int stem_pair_fwd_impl(const float* x, int n, int h, int w, const void* w
     else STEM_FWD(8);
 #undef STEM_FWD
     count_launch();
-    return check_launch("stem_fwd_tc_kernel");
+    rc = check_launch("stem_fwd_tc_kernel");
+    if (rc == RTSDS_OK && p.det) rc = det_finish(p.det, stats_cp, 128, true, as_stream(s));
+    if (rc == RTSDS_OK && p.det) rc = det_finish(p.det + 2 * 128, stats_sp, 128, true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_stem_pair_tc_fwd(const float* x, int n, int h, int w, const void* wpk, const float* scale,
@@ -658,9 +678,17 @@ extern "C" int rtsds_stem_pair_tc_wgrad(const float* x, int n, int h, int w, con
     }
     const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
     cudaStream_t st = as_stream(s);
+    if (det_mode()) {
+        p.det = det_scratch(st, 128 * SK);
+        if (!p.det) return RTSDS_ECUDA;
+    }
     if (p.tile_w == 32) stem_wgrad_tc_kernel<32><<<grid, S_THREADS, smem, st>>>(maps, p);
     else if (p.tile_w == 16) stem_wgrad_tc_kernel<16><<<grid, S_THREADS, smem, st>>>(maps, p);
     else stem_wgrad_tc_kernel<8><<<grid, S_THREADS, smem, st>>>(maps, p);
+    if (p.det) {                                   // dw_ws (zero on entry) receives the rounded exact sums, then unpacks as usual
+        rc = det_finish(p.det, dw_ws, 128 * SK, true, st);
+        if (rc != RTSDS_OK) return rc;
+    }
     stem_unpack_kernel<<<static_cast<int>(cdiv(128 * SK, 256)), 256, 0, st>>>(dw_ws, g7_oihw, g3_oihw);
     count_launch(2);
     return check_launch("stem_wgrad_tc kernels");

@@ -23,6 +23,7 @@ struct TapProblem {
     int cout;                     // GEMM N (real), padded via conv_cout_pad
     long long out_sn, out_sh, out_sw, res_sn, res_sh, res_sw;
     const float* scale; const float* shift; const void* residual; float* stats; void* y;
+    unsigned long long* det;      // deterministic mode: exact accumulators [2*cout] replacing the atomics on stats (set by the launcher only)
     int out_dtype, act; float slope;
     int split_req;
     int in_f16;                   // operands are IEEE half (RTSDS_F16) instead of bf16

@@ -52,7 +52,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int w, int c, int k_rt, int pad, int dil,
                    const float* __restrict__ scale, const float* __restrict__ shift, int act, float* stats,
-                   float* __restrict__ y, int y_ld, float* gap_out, float gap_scale) {
+                   unsigned long long* det, float* __restrict__ y, int y_ld, float* gap_out, float gap_scale) {
     __shared__ float s_stats[2][8][32];
     pdl_wait();
     const int k = K > 0 ? K : k_rt;
@@ -120,8 +120,13 @@ tapn_gather_kernel(const float* __restrict__ t_buf, int t_ld, int n, int h, int 
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a += s_stats[0][i][lane]; b += s_stats[1][i][lane]; }
-            atomicAdd(&stats[lane], a);
-            atomicAdd(&stats[c + lane], b);
+            if (det) {            // deterministic mode: the block's sums (fixed warp order) go into exact accumulators
+                det_add(det + 2 * lane, a);
+                det_add(det + 2 * (c + lane), b);
+            } else {
+                atomicAdd(&stats[lane], a);
+                atomicAdd(&stats[c + lane], b);
+            }
         }
     }
 }
@@ -206,12 +211,19 @@ extern "C" int rtsds_tapn_gather(const float* t_buf, int t_ld, int n, int h, int
     const long long g = tapn_gather_blocks(n, h, w, gap_out != nullptr);
     const dim3 grid(static_cast<unsigned>(g), static_cast<unsigned>(n));
     const float gsc = 1.0f / static_cast<float>(npix);
+    unsigned long long* det = nullptr;
+    if (stats && det_mode()) {
+        det = det_scratch(as_stream(s), 2 * static_cast<size_t>(c));
+        if (!det) return RTSDS_ECUDA;
+    }
     if (k == 3)
-        launch_pdl(tapn_gather_kernel<3>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
+        launch_pdl(tapn_gather_kernel<3>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, det, y, y_ld, gap_out, gsc);
     else
-        launch_pdl(tapn_gather_kernel<0>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, y, y_ld, gap_out, gsc);
+        launch_pdl(tapn_gather_kernel<0>, grid, dim3(256), 0, as_stream(s), t_buf, t_ld, n, h, w, c, k, pad, dil, scale, shift, act, stats, det, y, y_ld, gap_out, gsc);
     count_launch();
-    return check_launch("tapn_gather_kernel");
+    int rc = check_launch("tapn_gather_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, stats, 2 * static_cast<size_t>(c), true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_tapn_scatter(const void* dy, int dy_ld, int dy_dtype, int n, int h, int w, int c, int k, int pad, int dil,

@@ -61,6 +61,17 @@ def launch_count() -> int:
     return int(lib().rtsds_launch_count())
 
 
+def set_deterministic(on: bool = True) -> None:
+    """Order-independent (exact fixed-point) accumulation for the train-mode BatchNorm sums, weight-gradient partials and
+    BatchNorm-backward sums instead of fp32 atomics (include/rtsds_b200.h: rtsds_set_deterministic).  For parity runs:
+    the reference's CPU path sums in a fixed order, so its results are reproducible run to run."""
+    lib().rtsds_set_deterministic(1 if on else 0)
+
+
+def is_deterministic() -> bool:
+    return bool(lib().rtsds_get_deterministic())
+
+
 # ----------------------------------------------------------------------------- metric
 def confusion_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.Tensor,
                    n_bad: torch.Tensor | None = None) -> None:

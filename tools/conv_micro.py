@@ -54,7 +54,9 @@ def main():
         wsb = max(int(ops.lib().rtsds_conv2d_tc_workspace_bytes(d)), int(ops.lib().rtsds_conv2d_tc_dgrad_workspace_bytes(d)), 16)
         ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
         dd = ops.make_conv_desc(n, h, w, cin, cin, cout, ck, k, st, pad, dil, in_dtype=BF16, out_dtype=BF16)
+        stats = torch.zeros(2 * cout, dtype=torch.float32, device="cuda")
         fns = {"fwd": lambda: ops.conv2d_tc(d, x, wpk, y, None, None, None, None, ws),
+               "fwds": lambda: ops.conv2d_tc(d, x, wpk, y, None, None, None, stats, ws),      # + train-mode BatchNorm sums
                "dgrad": lambda: ops.conv2d_dgrad(dd, dy, wdg, dx, BF16, True, None, ws),
                "wgrad": lambda: ops.conv2d_wgrad(dd, x, dy, dw, True)}
         gf = 2.0 * n * d.oh * d.ow * cout * cin * k * k / 1e9
