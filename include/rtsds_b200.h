@@ -374,6 +374,16 @@ int rtsds_bn_finalize(const float* stats, double count, const float* gamma, cons
                       float eps, float momentum, int c, float* running_mean, float* running_var,
                       float* scale, float* shift, float* save_mean, float* save_invstd,
                       rtsds_stream_t s);
+/* rtsds_bn_finalize followed by rtsds_scale_shift_act(x, scale, shift, residual, ...) in ONE launch (train-mode
+ * nn.BatchNorm2d [+ residual] [+ ReLU] of ConvBlock / BasicBlock / Bottleneck, build_bisenet.py:14-17): every thread
+ * derives its channels' scale/shift from the sums with bn_finalize's arithmetic; scale/shift/save_* and the running
+ * statistics are written as bn_finalize writes them.  Falls back to the two launches for channel counts or pitches the
+ * vector path does not cover. */
+int rtsds_bn_finalize_apply(const float* stats, double count, const float* gamma, const float* beta, float eps,
+                            float momentum, int c, float* running_mean, float* running_var, float* scale,
+                            float* shift, float* save_mean, float* save_invstd, const void* x,
+                            const void* residual, int64_t n_pix, int x_ld, int res_ld, int y_ld, int act,
+                            float slope, int x_dtype, int y_dtype, void* y, rtsds_stream_t s);
 /* y = act(scale[c]*x + shift[c] + residual) elementwise over NHWC. */
 int rtsds_scale_shift_act(const void* x, const float* scale, const float* shift,
                           const void* residual, int64_t n_pix, int c, int x_ld, int res_ld,

@@ -135,6 +135,7 @@ SIGNATURES = {
     "rtsds_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _I, _P, _P, _P]),
     "rtsds_bn_finalize": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rtsds_scale_shift_act": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
+    "rtsds_bn_finalize_apply": (_I, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P, _P]),
     "rtsds_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _L, _I, _I, _I, _P, _P]),
     "rtsds_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),
     "rtsds_bn_bwd_reduce_rawmask": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P]),

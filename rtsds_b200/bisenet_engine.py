@@ -179,9 +179,8 @@ class BiSeNetPlan:
             def run_train():
                 st = self._stats_view(bn.stats, cout)
                 launch(d, None, None, None, st)              # raw conv output + per-channel sums
-                ops.bn_finalize(st, n_pix, bnmod, bn.scale, bn.shift, bn.save_mean, bn.save_invstd)
-                ops.scale_shift_act_ptr(yp, yp, n_pix, cout, bn.scale, bn.shift, rp, act, 0.0, out_ld, out_ld,
-                                        res_ld if res_ld else cout, out_dtype, out_dtype)
+                ops.bn_finalize_apply_ptr(st, n_pix, bnmod, bn.scale, bn.shift, bn.save_mean, bn.save_invstd, yp, yp, n_pix, cout,
+                                          rp, act, 0.0, out_ld, out_ld, res_ld if res_ld else cout, out_dtype, out_dtype)
 
             steps.append(run_train)
         return d.oh, d.ow

@@ -113,11 +113,12 @@ class _ConvBN:
             return
         st = p.stats_view(self.stats, self.cout)
         self._launch(self.d, None, None, None, st, self.raw.ptr)
-        ops.bn_finalize(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd)
-        ops.scale_shift_act_ptr(self.raw.ptr, self.y.ptr, self.n_pix, self.cout, self.scale, self.shift,
-                                self.res.ptr if self.res is not None else None, ACT_RELU if self.relu else ACT_NONE, 0.0,
-                                self.raw.ld, self.y.ld, self.res.ld if self.res is not None else self.cout, self.raw.dtype,
-                                self.y.dtype)
+        # batch statistics -> scale/shift (+ running buffers) and the normalise [+ residual] [+ ReLU] pass in ONE launch
+        ops.bn_finalize_apply_ptr(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd,
+                                  self.raw.ptr, self.y.ptr, self.n_pix, self.cout,
+                                  self.res.ptr if self.res is not None else None, ACT_RELU if self.relu else ACT_NONE, 0.0,
+                                  self.raw.ld, self.y.ld, self.res.ld if self.res is not None else self.cout, self.raw.dtype,
+                                  self.y.dtype)
 
     def _launch(self, d, scale, shift, res, stats, yptr):
         if self.tc:
@@ -243,8 +244,9 @@ class _Stem:
         st = p.stats_view(self.stats, 64)
         if not conv_done:
             ops.stem_conv(x, self.conv.weight, self.raw.t, self.k, 2, self.pad, stats=st)
-        ops.bn_finalize(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd)
-        ops.scale_shift_act(self.raw.t, self.y.t, self.n_pix, 64, self.scale, self.shift, None, ACT_RELU)
+        ops.bn_finalize_apply_ptr(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd, self.raw.t,
+                                  self.y.t, self.n_pix, 64, None, ACT_RELU, 0.0, 64, 64, 64, ops.dtype_code(self.raw.t.dtype),
+                                  ops.dtype_code(self.y.t.dtype))
 
     def backward(self, x, dy: _Buf, gw, wgrad=True):
         p = self.plan

@@ -270,8 +270,9 @@ class _StemS2D:
             ops.stem_s2d_conv_fwd(p.stem_P, self.n, self.oh, self.ow, self.wpk, 64, self.raw.t, 64, BF16, stats=st)
         else:
             ops.stem_conv(x, self.conv.weight, self.raw.t, self.k, 2, self.pad, stats=st)
-        ops.bn_finalize(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd)
-        ops.scale_shift_act(self.raw.t, self.y.t, self.n_pix, 64, self.scale, self.shift, None, ACT_RELU)
+        ops.bn_finalize_apply_ptr(st, self.n_pix, self.bn, self.scale, self.shift, self.save_mean, self.save_invstd, self.raw.t,
+                                  self.y.t, self.n_pix, 64, None, ACT_RELU, 0.0, 64, 64, 64, ops.dtype_code(self.raw.t.dtype),
+                                  ops.dtype_code(self.y.t.dtype))
 
     def backward(self, x, dy: _Buf, gw):
         p = self.plan

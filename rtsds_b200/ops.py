@@ -15,7 +15,7 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F16, F32, ConvDesc, check
 __all__ = [
     "F32", "BF16", "F16", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ConvDesc", "dtype_code", "torch_dtype",
     "confusion_hist", "argmax_hist", "conv_out_size", "cout_pad", "pack_conv_weight", "conv2d_tc",
-    "conv2d_simt", "stem_conv", "maxpool3x3s2", "maxpool3x3s2_bwd_idx", "bn_fold", "bn_finalize", "scale_shift_act",
+    "conv2d_simt", "stem_conv", "maxpool3x3s2", "maxpool3x3s2_bwd_idx", "bn_fold", "bn_finalize", "bn_finalize_apply_ptr", "scale_shift_act",
     "global_avgpool", "arm_gate", "gate_resize_nhwc", "ffm_head", "resize_to_nchw",
     "resize_ce_argmax_fwd", "resize_ce_bwd", "ce_argmax_nchw_fwd", "launch_count",
 ]
@@ -288,6 +288,17 @@ def bn_finalize(stats, count, bn, scale, shift, save_mean=None, save_invstd=None
                                   float(mom), c, _p(bn.running_mean if update_running else None),
                                   _p(bn.running_var if update_running else None), _p(scale), _p(shift), _p(save_mean),
                                   _p(save_invstd), _s()), "bn_finalize")
+
+
+def bn_finalize_apply_ptr(stats, count, bn, scale, shift, save_mean, save_invstd, xp, yp, n_pix, c, resp, act, slope, x_ld,
+                          y_ld, res_ld, x_dtype, y_dtype, update_running=True) -> None:
+    """bn_finalize + scale_shift_act_ptr as ONE launch (train-mode BatchNorm [+ residual] [+ activation])."""
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    check(lib().rtsds_bn_finalize_apply(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
+                                        float(mom), c, _p(bn.running_mean if update_running else None),
+                                        _p(bn.running_var if update_running else None), _p(scale), _p(shift), _p(save_mean),
+                                        _p(save_invstd), _p(xp), _p(resp), n_pix, x_ld, res_ld, y_ld, act, slope, x_dtype,
+                                        y_dtype, _p(yp), _s()), "bn_finalize_apply")
 
 
 def scale_shift_act(x, y, n_pix, c, scale=None, shift=None, residual=None, act=ACT_NONE, slope=0.0, x_ld=None,

@@ -120,7 +120,7 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     outs = m(torch.zeros(2, 3, 720, 1280))
     assert [tuple(o.shape) for o in outs] == [(2, 19, 720, 1280)] * 3
     c = collections.Counter(_lib.lib().calls)
-    assert c["rtsds_conv2d_tc_fwd"] == 24 and c["rtsds_bn_finalize"] == 24 and c["rtsds_resize_to_nchw"] == 3
+    assert c["rtsds_conv2d_tc_fwd"] == 24 and c["rtsds_bn_finalize"] + c["rtsds_bn_finalize_apply"] == 24 and c["rtsds_resize_to_nchw"] == 3
     m.rtsds_precision = "fp32"
     _lib.lib().calls.clear()
     m.eval()(torch.zeros(1, 3, 64, 96))

@@ -125,3 +125,44 @@ def test_unpack_batch(cuda, accumulate):
     for (dw, grad, _), ref in zip(jobs, want):
         assert torch.equal(grad, ref), tuple(grad.shape)
         assert not dw.any(), "scratch must be left zeroed"
+
+
+# ----------------------------------------------------------------------------- train-mode BatchNorm forward in one launch
+@pytest.mark.parametrize("n_pix,c", [(40003, 64), (9001, 256), (1031, 2048), (300, 128), (777, 24)])
+@pytest.mark.parametrize("dtype", [BF16, F32])
+@pytest.mark.parametrize("residual", [False, True])
+def test_bn_finalize_apply_equals_the_two_launch_form(cuda, n_pix, c, dtype, residual):
+    """rtsds_bn_finalize_apply == rtsds_bn_finalize + rtsds_scale_shift_act, bit for bit (c = 24: the fallback itself)."""
+    from rtsds_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n_pix + c)
+    tdt = torch.bfloat16 if dtype == BF16 else torch.float32
+    raw = (torch.randn(n_pix, c, device="cuda", generator=g) * 1.5 + 0.3).to(tdt)
+    res = torch.randn(n_pix, c, device="cuda", generator=g).to(tdt) if residual else None
+    stats = torch.cat([raw.float().sum(0), (raw.float() ** 2).sum(0)]).contiguous()
+    outs = []
+    for fused in (False, True):
+        bn = torch.nn.BatchNorm2d(c).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(c, device="cuda", generator=g) * 0 + torch.linspace(0.5, 1.5, c, device="cuda"))
+            bn.bias.copy_(torch.linspace(-0.2, 0.2, c, device="cuda"))
+        scale, shift = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        sm, si = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        y = torch.full((n_pix, c), 7.0, device="cuda", dtype=tdt)
+        if fused:
+            ops.bn_finalize_apply_ptr(stats, n_pix, bn, scale, shift, sm, si, raw, y, n_pix, c, res, ops.ACT_RELU, 0.0, c, c, c, dtype, dtype)
+        else:
+            ops.bn_finalize(stats, n_pix, bn, scale, shift, sm, si)
+            ops.scale_shift_act_ptr(raw, y, n_pix, c, scale, shift, res, ops.ACT_RELU, 0.0, c, c, c, dtype, dtype)
+        torch.cuda.synchronize()
+        outs.append((y, scale, shift, sm, si, bn.running_mean.clone(), bn.running_var.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # and it is BatchNorm: torch on the same (rounded) input
+    ref = torch.nn.functional.batch_norm(raw.float(), None, None, torch.linspace(0.5, 1.5, c, device="cuda"),
+                                         torch.linspace(-0.2, 0.2, c, device="cuda"), True, 0.1, 1e-5)
+    if residual:
+        ref = ref + res.float()
+    ref = torch.relu(ref)
+    tol = 2e-2 if dtype == BF16 else 1e-4
+    assert (outs[1][0].float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
