@@ -106,12 +106,15 @@ constexpr int TR_BYTES = 4 * 32 * TR_PITCH * 4;               // four epilogue w
 // scale/shift (folded BatchNorm or bias), residual add, activation, 16-byte stores.  Shared by both conv kernels.
 // rpre != NULL: the 16-bit residual of this row (all BLOCK_N channels, 16-byte pieces) was fetched into registers while the
 // main loop ran, instead of paying its latency here.
-template <int BLOCK_N>
+// STATS = false compiles the train-mode BatchNorm sums (and the deterministic-mode call) out: the eval-mode instantiation of
+// the one-tile kernel keeps the register allocation and schedule it had before those paths existed (measured: their mere
+// presence cost the batch-1 frame 1.3 %).
+template <int BLOCK_N, bool STATS = true>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[32], int c0, int n0, bool valid, long long out_off,
                                                   long long res_off, const float* s_scale, const float* s_shift, float* s_stats,
                                                   int lane, const uint4* rpre = nullptr, float* s_tr = nullptr) {
     const int co0 = n0 + c0;
-            if (p.stats) {
+            if (STATS && p.stats) {
             float s1, s2;
             if (s_tr) {
                 // column sums of this warp's 32 x 32 block through a shared-memory transpose (s_tr: this warp's own
@@ -277,9 +280,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
         }
     }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    // (STATS: see tc_epilogue_chunk)
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     const uint32_t IDESC = ptx::umma_idesc_16(TC_BLOCK_M, BLOCK_N, p.f16 != 0);
@@ -494,8 +498,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             } else {
                 // (transpose scratch of the BatchNorm sums: the operand ring, idle once the accumulator is complete — not with
                 // A-tile multicast, where a peer's TMA may still write into this CTA's ring)
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
-                                           p.mc <= 1 ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
+                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
+                                                  (STATS && p.mc <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
         };
         // (two chunks per trip — both TMEM loads in flight, two interleaved instruction streams — was measured: 168
@@ -517,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (CW == 64) do_chunk(rb, c0 + 32);
             if (trace && threadIdx.x == 64 && c0 == 0) trace[14] = clock64();
         }
-        if (p.stats && !p.det && p.split_k == 1) {
+        if (STATS && p.stats && !p.det && p.split_k == 1) {
             // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
@@ -576,10 +580,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                     }
                 }
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
-                                           p.mc <= 1 ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
+                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
+                                                  (STATS && p.mc <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
-            if (p.stats && !p.det) {
+            if (STATS && p.stats && !p.det) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
@@ -1026,7 +1030,8 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     size_t smem = tc_smem_bytes(BLOCK_N, p.stages, p.rbuf_bytes);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
@@ -1053,7 +1058,8 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, maps, p);
+    cudaError_t le = p.stats ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps, p)
+                             : cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tc_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tc_kernel");
