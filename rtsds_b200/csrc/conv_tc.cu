@@ -171,7 +171,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
                     v[4 * g + 2] = fmaf(v[4 * g + 2], a.z, b.z); v[4 * g + 3] = fmaf(v[4 * g + 3], a.w, b.w);
                 }
             }
-            if (p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 16] = clock64();
+            if (STATS && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 16] = clock64();
             if (p.residual) {
                 if (out16 && full) {
                     uint4 rv[4];
@@ -228,7 +228,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * slope;
             }
-            if (p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 17] = clock64();
+            if (STATS && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 17] = clock64();
         }
         if (p.gap_out) {
             // global average pool of THIS layer's output fused into its epilogue (ARM AdaptiveAvgPool2d(1) / context-path
@@ -239,7 +239,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             const float s1 = warp_transpose_sum(t, lane);
             s_stats[(threadIdx.x >> 5 & 3) * BLOCK_N + c0 + lane] += s1;      // this warp's own slot: fixed summation order
         }
-        if (valid && !(p.dbg & 1)) {
+        if (valid && !(STATS && (p.dbg & 1))) {
             if (out16 && full) {
                 uint4 o[4];
                 if (f16) {
@@ -316,15 +316,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int kb_total = p.n_taps * p.kchunks;
     const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * blockIdx.z) / p.split_k);
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (blockIdx.z + 1)) / p.split_k);
-    unsigned long long* trace = p.trace ? p.trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    // the lean (STATS = false) instantiation is the production eval kernel: no time stamps, no A-tile multicast either
+    const int mc_ = STATS ? p.mc : 1;
+    unsigned long long* trace = (STATS && p.trace) ? p.trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
     if (trace && threadIdx.x == 0) { trace[0] = ptx::globaltimer(); trace[1] = clock64(); }
 
     // cluster = (1, mc, split_k): rank = y + mc * z.  y pairs share A tiles (multicast), z slices share the output tile
-    const bool clustered = p.cluster_reduce || p.mc > 1;
+    const bool clustered = p.cluster_reduce || mc_ > 1;
     const uint32_t crank = clustered ? ptx::cluster_ctarank() : 0u;
-    const uint32_t yrank = p.mc > 1 ? crank % static_cast<uint32_t>(p.mc) : 0u;
-    const uint32_t zrank = p.mc > 1 ? crank / static_cast<uint32_t>(p.mc) : crank;
-    const uint16_t pair_mask = static_cast<uint16_t>(((1u << p.mc) - 1u) << (zrank * p.mc));
+    const uint32_t yrank = mc_ > 1 ? crank % static_cast<uint32_t>(mc_) : 0u;
+    const uint32_t zrank = mc_ > 1 ? crank / static_cast<uint32_t>(mc_) : crank;
+    const uint16_t pair_mask = static_cast<uint16_t>(((1u << mc_) - 1u) << (zrank * mc_));
 
     // ---- one-time setup ----
     if (warp == 0 && lane == 0) {
@@ -334,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
         for (int i = 0; i < stages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], p.mc > 1 ? p.mc : 1);     // multicast: every CTA of the pair must release the stage
+            ptx::mbar_init(&empty_bar[i], mc_ > 1 ? mc_ : 1);     // multicast: every CTA of the pair must release the stage
         }
         ptx::mbar_init(tmem_full_bar, 1);
         ptx::fence_barrier_init();
@@ -351,8 +353,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // peers write into this CTA's shared memory (multicast TMA / pushed split-K partials): it must exist, i.e. the CTA must
     // have started.  Multicast needs that before the first load (full sync); the pushes only before the epilogue, so there
     // the arrive is here and every thread waits at the end of its main-loop role (long since complete by then).
-    const bool started_barrier = p.cluster_reduce && p.mc <= 1;
-    if (p.mc > 1) ptx::cluster_sync_all();
+    const bool started_barrier = p.cluster_reduce && mc_ <= 1;
+    if (mc_ > 1) ptx::cluster_sync_all();
     else if (started_barrier) ptx::cluster_arrive();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -360,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // tail of the previous kernel in the stream; global memory is only touched after the dependency has resolved.
     // The weights do not depend on the previous kernel: the producer thread requests the B tiles of the first ring pass
     // BEFORE waiting, so their L2/HBM latency overlaps the predecessor's tail as well.
-    const int kb_pre = (p.b_early && p.mc <= 1) ? min(stages, kb_end - kb_begin) : 0;
+    const int kb_pre = (p.b_early && mc_ <= 1) ? min(stages, kb_end - kb_begin) : 0;
     if (trace && threadIdx.x == 0) trace[2] = clock64();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kb_pre; ++i) {
@@ -388,15 +390,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // (tap, channel chunk) of the k-block advance incrementally: a division by the runtime chunk count per TMA
+            // issue sat on the critical path of this one-thread loop
+            int tap = kb_begin / p.kchunks;
+            int cc = kb_begin - tap * p.kchunks;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
-                const int tap = kb / p.kchunks;
-                const int cc = kb - tap * p.kchunks;
                 const bool pre = kb - kb_begin < kb_pre;          // first ring pass: stage empty by construction, B already in flight
                 if (!pre) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + B_BYTES);
                 }
-                if (p.mc > 1) {
+                if (mc_ > 1) {
                     // this CTA fetches half yrank of the A tile (the maps' box is half a tile) and multicasts it to the pair;
                     // the other half arrives from the peer, on this same barrier
                     ptx::tma_load_4d_mc(smem_a + static_cast<size_t>(stage) * TC_A_BYTES + yrank * (TC_A_BYTES / 2),
@@ -411,6 +415,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ptx::tma_load_2d(smem_b + static_cast<size_t>(stage) * B_BYTES, &maps.b, &full_bar[stage],
                                      (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
+                if (++cc == p.kchunks) { cc = 0; ++tap; }
             }
             if (trace) trace[4] = clock64();
         }
@@ -433,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC,
                                    (kb > kb_begin || k > 0) ? 1u : 0u);
                 }
-                if (p.mc > 1) ptx::umma_commit_mc(&empty_bar[stage], pair_mask);   // releases the stage in BOTH CTAs of the pair
+                if (mc_ > 1) ptx::umma_commit_mc(&empty_bar[stage], pair_mask);   // releases the stage in BOTH CTAs of the pair
                 else ptx::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
@@ -485,7 +490,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const int rows_per = TC_BLOCK_M / p.split_k;
                 const int owner = row / rows_per;
                 const float* dst = rbuf + (static_cast<int>(zrank) * rows_per + (row - owner * rows_per)) * (BLOCK_N + 4) + c0;
-                const uint32_t ra = ptx::mapa_u32(dst, yrank + static_cast<uint32_t>(owner * (p.mc > 1 ? p.mc : 1)));
+                const uint32_t ra = ptx::mapa_u32(dst, yrank + static_cast<uint32_t>(owner * (mc_ > 1 ? mc_ : 1)));
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) ptx::st_dsmem_f4(ra + j * 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             } else if (p.split_k > 1) {
@@ -499,7 +504,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 // (transpose scratch of the BatchNorm sums: the operand ring, idle once the accumulator is complete — not with
                 // A-tile multicast, where a peer's TMA may still write into this CTA's ring)
                 tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
-                                                  (STATS && p.mc <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
+                                                  (STATS && mc_ <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
         };
         // (two chunks per trip — both TMEM loads in flight, two interleaved instruction streams — was measured: 168
@@ -550,6 +555,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         // rank that owns them; CTA r now sums rows [r*128/split, (r+1)*128/split) over the `split` slots of its OWN shared
         // memory (slot order = deterministic) and runs the epilogue on them.  No workspace round trip through L2, no
         // finish kernel, no remote loads; nobody touches a peer's memory after this barrier, so CTAs exit independently.
+        // (requesting the residual of the first reduction task BEFORE this barrier was measured: the four live 16-byte
+        // registers across the barrier cost the lean kernel 24 registers and 1 % of the frame — not kept)
         ptx::cluster_sync_all();
         if (trace && threadIdx.x == 64) trace[11] = clock64();
         if (warp >= 2) {
@@ -581,7 +588,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     }
                 }
                 tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
-                                                  (STATS && p.mc <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
+                                                  (STATS && mc_ <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
             if (STATS && p.stats && !p.det) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -605,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
         }
         if (trace && threadIdx.x == 64) trace[12] = clock64();
-    } else if (p.mc > 1) {
+    } else if (mc_ > 1) {
         ptx::cluster_sync_all();                    // nobody leaves while the peer's MMA commits still arrive on its barriers
     }
 
@@ -710,9 +717,9 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 if (B_RESIDENT && n_tile != cur_n) {
                     if (cur_n >= 0) { ptx::mbar_wait(b_free, bfree_phase); bfree_phase ^= 1; }   // MMAs of the old N tile retired
                     ptx::mbar_expect_tx(b_full, static_cast<uint32_t>(kb_total) * B_BYTES);
-                    for (int kb = 0; kb < kb_total; ++kb) {
-                        const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
+                    for (int kb = 0, tap = 0, cc = 0; kb < kb_total; ++kb) {
                         ptx::tma_load_2d(smem_b + static_cast<size_t>(kb) * B_BYTES, &maps.b, b_full, (p.tap_kb[tap] + cc) * TC_BLOCK_K, n0);
+                        if (++cc == p.kchunks) { cc = 0; ++tap; }
                     }
                     cur_n = n_tile;
                 }
@@ -726,8 +733,8 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
                 } else {
-                for (int kb = 0; kb < kb_total; ++kb) {
-                    const int tap = kb / p.kchunks, cc = kb - tap * p.kchunks;
+                for (int kb = 0, tap = 0, cc = -1; kb < kb_total; ++kb) {
+                    if (++cc == p.kchunks) { cc = 0; ++tap; }              // (tap, chunk) advance without a division per TMA issue
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if ((p.dbg & 8) && B_RESIDENT) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
                     ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + (B_RESIDENT ? 0 : B_BYTES));
@@ -1058,8 +1065,9 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = p.stats ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps, p)
-                             : cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps, p);
+    const bool full = p.stats || p.trace || p.mc > 1 || p.dbg;
+    cudaError_t le = full ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps, p)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tc_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tc_kernel");
