@@ -37,7 +37,7 @@ EVAL_DTYPE = "fp16"                # eval-mode operand / activation type (fp32 a
 FWD_GFLOP_PER_IMG = 51.26          # conv FLOPs (2*MAC) of one eval forward at 512x1024
 FWD_CONV_MB_PER_IMG = 236.0        # ideal bf16 conv traffic
 LOGITS_MB_PER_IMG = 39.8           # fp32 [19,512,1024] API-boundary write
-CONV_DRAM_BYTES_PER_FORWARD = 147054336   # dram__bytes_read+write summed over the conv launches of one forward (profiles/r02_conv_tc_infer_ncu_full.csv)
+CONV_DRAM_BYTES_PER_FORWARD = 120935168   # dram__bytes_read+write summed over the 22 conv launches of one forward (profiles/r02_conv_tc_infer_ncu_full.csv)
 
 
 def peaks():
