@@ -647,9 +647,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // loop of the 64..256-channel training layers needs 1-2 us.  With EPI = 2 a second group drains the NEXT tile at the same
 // time (accumulator ring of 2*EPI TMEM buffers; tile j of the CTA -> buffer j % (2*EPI), group j % EPI), two warps per
 // scheduler hide each other's latency, and every group keeps its own scale/shift/statistics staging and named barrier.
-template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI>
+// STATS = false: the instantiation for launches without BatchNorm sums and without the debug switches (dgrad, eval) — those
+// paths are compiled out, as in conv_tc_kernel.
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, bool STATS>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    const int dbg_ = STATS ? p.dbg : 0;
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr int NACC = 2 * EPI;
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -673,7 +676,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint64_t* b_free = b_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
     // transpose scratch of the BatchNorm sums (only allocated when p.stats: tcp_smem_bytes' `extra`)
-    float* s_tr_all = p.stats ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15)) : nullptr;
+    float* s_tr_all = (STATS && p.stats) ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15)) : nullptr;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -726,7 +729,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 if (HALO) {
                     for (int cc = 0; cc < p.kchunks; ++cc) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (p.dbg & 8) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
+                        if (dbg_ & 8) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
                         ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.halo_rows) * 16 * 128);
                         ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * a_stage, &maps.a[1], &full_bar[stage], cc * TC_BLOCK_K,
                                          w0 - p.halo_d, h0 - p.halo_d, img);
@@ -736,7 +739,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 for (int kb = 0, tap = 0, cc = -1; kb < kb_total; ++kb) {
                     if (++cc == p.kchunks) { cc = 0; ++tap; }              // (tap, chunk) advance without a division per TMA issue
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if ((p.dbg & 8) && B_RESIDENT) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
+                    if ((dbg_ & 8) && B_RESIDENT) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
                     ptx::mbar_expect_tx(&full_bar[stage], TC_A_BYTES + (B_RESIDENT ? 0 : B_BYTES));
                     ptx::tma_load_4d(smem_a + static_cast<size_t>(stage) * TC_A_BYTES, &maps.a[p.tap_map[tap]], &full_bar[stage],
                                      cc * TC_BLOCK_K, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
@@ -778,7 +781,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             const uint32_t a_addr = a_base + row_off * 128u;
                             const uint64_t da = ptx::umma_desc_k_sw128_ex(a_addr, 2048u, p.halo_baseoff ? (row_off & 7u) : 0u);
                             const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(tap * p.kchunks + cc) * B_BYTES));
-                            if (p.dbg & 4) continue;
+                            if (dbg_ & 4) continue;
 #pragma unroll
                             for (int k = 0; k < TC_BLOCK_K / 16; ++k)
                                 ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
@@ -792,7 +795,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ptx::tc_fence_after();
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + static_cast<size_t>(stage) * TC_A_BYTES));
                     const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + static_cast<size_t>(B_RESIDENT ? kb : stage) * B_BYTES));
-                    if (!(p.dbg & 4)) {
+                    if (!(dbg_ & 4)) {
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k)
                         ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
@@ -830,7 +833,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (n_tile != cur_n) {
                 // new N tile: flush the statistics of the old one, load this one's scale / shift
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                if (p.stats && !p.det && cur_n >= 0) {
+                if (STATS && p.stats && !p.det && cur_n >= 0) {
                     for (int i = tig; i < BLOCK_N; i += 128) {
                         const int co = cur_n * BLOCK_N + i;
                         if (co < p.cout) {
@@ -857,7 +860,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t r[32];
-                if (p.dbg & 2) {
+                if (dbg_ & 2) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) r[jj] = static_cast<uint32_t>(jj + c0);
                 } else {
@@ -871,10 +874,10 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                tc_epilogue_chunk<BLOCK_N>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr, s_tr);
+                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr, s_tr);
             }
         }
-        if (p.stats && !p.det && cur_n >= 0) {
+        if (STATS && p.stats && !p.det && cur_n >= 0) {
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             for (int i = tig; i < BLOCK_N; i += 128) {
                 const int co = cur_n * BLOCK_N + i;
@@ -1079,11 +1082,11 @@ static size_t tcp_smem_bytes(int block_n, int stages, int b_slots, int a_stage =
            TCP_EPI_MAX * 4 * block_n * 4 + (2 * stages + 4 * TCP_EPI_MAX + 2) * 8 + 16 + extra;
 }
 
-template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI>
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, bool STATS>
 static int launch_tcp_epi(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tcp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
@@ -1098,7 +1101,7 @@ static int launch_tcp_epi(const TcMaps& maps, const TcParams& p, int grid, size_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI>, maps, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, STATS>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tcp_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tcp_kernel");
@@ -1109,8 +1112,9 @@ template <int BLOCK_N, bool B_RESIDENT, bool HALO = false>
 static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static int epi = -1;
     if (epi < 0) { const char* e = getenv("RTSDS_TCP_EPI"); epi = (e && e[0] == '1') ? 1 : 2; }
-    if (epi == 1) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 1>(maps, p, grid, smem, st);
-    return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2>(maps, p, grid, smem, st);
+    if (epi == 1) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 1, true>(maps, p, grid, smem, st);
+    if (p.stats || p.dbg) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, true>(maps, p, grid, smem, st);
+    return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, false>(maps, p, grid, smem, st);
 }
 
 }  // namespace rtsds
