@@ -106,13 +106,16 @@ constexpr int TR_BYTES = 4 * 32 * TR_PITCH * 4;               // four epilogue w
 // scale/shift (folded BatchNorm or bias), residual add, activation, 16-byte stores.  Shared by both conv kernels.
 // rpre != NULL: the 16-bit residual of this row (all BLOCK_N channels, 16-byte pieces) was fetched into registers while the
 // main loop ran, instead of paying its latency here.
-// STATS = false compiles the train-mode BatchNorm sums (and the deterministic-mode call) out: the eval-mode instantiation of
+// MODE 0 compiles the train-mode BatchNorm sums (and the deterministic-mode call) out: the eval-mode instantiation of
 // the one-tile kernel keeps the register allocation and schedule it had before those paths existed (measured: their mere
 // presence cost the batch-1 frame 1.3 %).
-template <int BLOCK_N, bool STATS = true>
+// MODE: 0 = lean (no BatchNorm sums, no debug paths), 1 = train (BatchNorm sums through fp32 atomics, no debug paths),
+// 2 = full (sums incl. the deterministic mode, time stamps, A-tile multicast, stage-removal switches).
+template <int BLOCK_N, int MODE = 2>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[32], int c0, int n0, bool valid, long long out_off,
                                                   long long res_off, const float* s_scale, const float* s_shift, float* s_stats,
                                                   int lane, const uint4* rpre = nullptr, float* s_tr = nullptr) {
+    constexpr bool STATS = MODE >= 1, FULL = MODE == 2;
     const int co0 = n0 + c0;
             if (STATS && p.stats) {
             float s1, s2;
@@ -143,7 +146,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             for (int j = 0; j < 32; ++j) t[j] = valid ? v[j] * v[j] : 0.0f;
             s2 = warp_transpose_sum(t, lane);
             }
-            if (p.det) {                  // order-independent: this warp's 32-row sums go straight into the exact accumulators
+            if (FULL && p.det) {          // order-independent: this warp's 32-row sums go straight into the exact accumulators
                 if (co0 + lane < p.cout) det_add2(p.det + 2 * (co0 + lane), s1, p.det + 2 * (p.cout + co0 + lane), s2);
             } else {
                 atomicAdd(&s_stats[c0 + lane], s1);
@@ -171,7 +174,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
                     v[4 * g + 2] = fmaf(v[4 * g + 2], a.z, b.z); v[4 * g + 3] = fmaf(v[4 * g + 3], a.w, b.w);
                 }
             }
-            if (STATS && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 16] = clock64();
+            if (FULL && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 16] = clock64();
             if (p.residual) {
                 if (out16 && full) {
                     uint4 rv[4];
@@ -228,7 +231,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * slope;
             }
-            if (STATS && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 17] = clock64();
+            if (FULL && p.trace && threadIdx.x == 64 && c0 == 0) p.trace[32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 17] = clock64();
         }
         if (p.gap_out) {
             // global average pool of THIS layer's output fused into its epilogue (ARM AdaptiveAvgPool2d(1) / context-path
@@ -239,7 +242,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
             const float s1 = warp_transpose_sum(t, lane);
             s_stats[(threadIdx.x >> 5 & 3) * BLOCK_N + c0 + lane] += s1;      // this warp's own slot: fixed summation order
         }
-        if (valid && !(STATS && (p.dbg & 1))) {
+        if (valid && !(FULL && (p.dbg & 1))) {
             if (out16 && full) {
                 uint4 o[4];
                 if (f16) {
@@ -280,10 +283,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, float (&v)[
         }
     }
 
-template <int BLOCK_N, bool STATS>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-    // (STATS: see tc_epilogue_chunk)
+    constexpr bool STATS = MODE >= 1, FULL = MODE == 2;       // (MODE: see tc_epilogue_chunk)
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     const uint32_t IDESC = ptx::umma_idesc_16(TC_BLOCK_M, BLOCK_N, p.f16 != 0);
@@ -317,8 +320,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * blockIdx.z) / p.split_k);
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (blockIdx.z + 1)) / p.split_k);
     // the lean (STATS = false) instantiation is the production eval kernel: no time stamps, no A-tile multicast either
-    const int mc_ = STATS ? p.mc : 1;
-    unsigned long long* trace = (STATS && p.trace) ? p.trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    const int mc_ = FULL ? p.mc : 1;
+    unsigned long long* trace = (FULL && p.trace) ? p.trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
     if (trace && threadIdx.x == 0) { trace[0] = ptx::globaltimer(); trace[1] = clock64(); }
 
     // cluster = (1, mc, split_k): rank = y + mc * z.  y pairs share A tiles (multicast), z slices share the output tile
@@ -503,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             } else {
                 // (transpose scratch of the BatchNorm sums: the operand ring, idle once the accumulator is complete — not with
                 // A-tile multicast, where a peer's TMA may still write into this CTA's ring)
-                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
+                tc_epilogue_chunk<BLOCK_N, MODE>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, res_pre ? rres : nullptr,
                                                   (STATS && mc_ <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
         };
@@ -526,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (CW == 64) do_chunk(rb, c0 + 32);
             if (trace && threadIdx.x == 64 && c0 == 0) trace[14] = clock64();
         }
-        if (STATS && p.stats && !p.det && p.split_k == 1) {
+        if (STATS && p.stats && !(FULL && p.det) && p.split_k == 1) {
             // all 4 epilogue warps have added their rows: named barrier 1, 128 threads
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
@@ -587,10 +590,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                     }
                 }
-                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
+                tc_epilogue_chunk<BLOCK_N, MODE>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr,
                                                   (STATS && mc_ <= 1) ? reinterpret_cast<float*>(smem) + (warp & 3) * 32 * TR_PITCH : nullptr);
             }
-            if (STATS && p.stats && !p.det) {
+            if (STATS && p.stats && !(FULL && p.det)) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
                     const int co = n0 + i;
@@ -649,10 +652,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // scheduler hide each other's latency, and every group keeps its own scale/shift/statistics staging and named barrier.
 // STATS = false: the instantiation for launches without BatchNorm sums and without the debug switches (dgrad, eval) — those
 // paths are compiled out, as in conv_tc_kernel.
-template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, bool STATS>
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, int MODE>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-    const int dbg_ = STATS ? p.dbg : 0;
+    constexpr bool STATS = MODE >= 1, FULL = MODE == 2;       // (MODE: see tc_epilogue_chunk)
+    const int dbg_ = FULL ? p.dbg : 0;
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr int NACC = 2 * EPI;
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -833,7 +837,7 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (n_tile != cur_n) {
                 // new N tile: flush the statistics of the old one, load this one's scale / shift
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                if (STATS && p.stats && !p.det && cur_n >= 0) {
+                if (STATS && p.stats && !(FULL && p.det) && cur_n >= 0) {
                     for (int i = tig; i < BLOCK_N; i += 128) {
                         const int co = cur_n * BLOCK_N + i;
                         if (co < p.cout) {
@@ -874,10 +878,10 @@ conv_tcp_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                tc_epilogue_chunk<BLOCK_N, STATS>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr, s_tr);
+                tc_epilogue_chunk<BLOCK_N, MODE>(p, v, c0, n0, valid, out_off, res_off, s_scale, s_shift, s_stats, lane, nullptr, s_tr);
             }
         }
-        if (STATS && p.stats && !p.det && cur_n >= 0) {
+        if (STATS && p.stats && !(FULL && p.det) && cur_n >= 0) {
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             for (int i = tig; i < BLOCK_N; i += 128) {
                 const int co = cur_n * BLOCK_N + i;
@@ -1040,8 +1044,9 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     size_t smem = tc_smem_bytes(BLOCK_N, p.stages, p.rbuf_bytes);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
@@ -1068,9 +1073,10 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStrea
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const bool full = p.stats || p.trace || p.mc > 1 || p.dbg;
-    cudaError_t le = full ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps, p)
-                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps, p);
+    const bool full = p.trace || p.mc > 1 || p.dbg || p.det;
+    cudaError_t le = full ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, 2>, maps, p)
+                     : p.stats ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, 1>, maps, p)
+                               : cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, 0>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tc_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tc_kernel");
@@ -1082,11 +1088,11 @@ static size_t tcp_smem_bytes(int block_n, int stages, int b_slots, int a_stage =
            TCP_EPI_MAX * 4 * block_n * 4 + (2 * stages + 4 * TCP_EPI_MAX + 2) * 8 + 16 + extra;
 }
 
-template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, bool STATS>
+template <int BLOCK_N, bool B_RESIDENT, bool HALO, int EPI, int MODE>
 static int launch_tcp_epi(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tcp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RTSDS_ECUDA; }
         attr_done = true;
     }
@@ -1101,7 +1107,7 @@ static int launch_tcp_epi(const TcMaps& maps, const TcParams& p, int grid, size_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, STATS>, maps, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tcp_kernel<BLOCK_N, B_RESIDENT, HALO, EPI, MODE>, maps, p);
     if (le != cudaSuccess) { set_error("conv_tcp_kernel: launch: %s", cudaGetErrorString(le)); return RTSDS_ECUDA; }
     count_launch();
     return check_launch("conv_tcp_kernel");
@@ -1112,9 +1118,10 @@ template <int BLOCK_N, bool B_RESIDENT, bool HALO = false>
 static int launch_tcp(const TcMaps& maps, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     static int epi = -1;
     if (epi < 0) { const char* e = getenv("RTSDS_TCP_EPI"); epi = (e && e[0] == '1') ? 1 : 2; }
-    if (epi == 1) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 1, true>(maps, p, grid, smem, st);
-    if (p.stats || p.dbg) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, true>(maps, p, grid, smem, st);
-    return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, false>(maps, p, grid, smem, st);
+    if (epi == 1) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 1, 2>(maps, p, grid, smem, st);
+    if (p.dbg || p.det) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, 2>(maps, p, grid, smem, st);
+    if (p.stats) return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, 1>(maps, p, grid, smem, st);
+    return launch_tcp_epi<BLOCK_N, B_RESIDENT, HALO, 2, 0>(maps, p, grid, smem, st);
 }
 
 }  // namespace rtsds
