@@ -640,7 +640,13 @@ def bisenet_forward(model, x):
         from .bisenet_autograd import bisenet_train_forward
 
         return bisenet_train_forward(model, x)
+    if torch.is_grad_enabled() and x.requires_grad:
+        # The reference's eval-mode forward is an ordinary autograd graph.  The eval plan here (folded BatchNorm, fp16, CUDA
+        # graph) has no backward; a caller who explicitly asks for input gradients must not get a silently detached tensor.
+        raise ops._lib.RtsdsError("BiSeNet eval-mode forward is inference only (no backward through the folded-BatchNorm plan): "
+                                  "call it under torch.no_grad(), or use model.train() / rtsds_precision='fp32' training mode "
+                                  "for gradients")
     plan = _get_plan(model, x, False)
-    with torch.no_grad():
+    with torch.no_grad():          # parameters that require grad do not make the eval output differentiable (documented)
         plan.forward_lowres(x, use_graph=model.rtsds_cuda_graph)
         return plan.logits(plan.z)

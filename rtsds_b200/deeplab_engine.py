@@ -608,6 +608,10 @@ def deeplab_forward(model, x):
                 out = plan.logits()
         _bump_bn_counters(model)
         return out, None, None
+    if torch.is_grad_enabled() and x.requires_grad:
+        # as BiSeNet's eval forward: inference only — never a silently detached tensor for a caller who wants input gradients
+        raise ops._lib.RtsdsError("DeepLabV2 eval-mode forward is inference only (no backward through the folded-BatchNorm plan): "
+                                  "call it under torch.no_grad(), or use model.train() for gradients")
     plan = _get_plan(model, x, False)
     with torch.no_grad():
         plan.forward_lowres(x, model.rtsds_cuda_graph)

@@ -128,6 +128,25 @@ def test_plan_launch_sequence_dry_run(monkeypatch):
     assert c["rtsds_conv2d_simt_fwd"] == 22 and c["rtsds_conv2d_tc_fwd"] == 0
 
 
+def test_eval_forward_refuses_input_gradients_dry_run(monkeypatch):
+    """the reference's eval forward is an autograd graph; the eval plan here is inference only, so a
+    caller who asks for gradients w.r.t. the input gets an error, not a silently detached tensor.  Under no_grad (what
+    validation.py does) and for parameters that merely require grad it runs."""
+    monkeypatch.setenv("RTSDS_DRYRUN", "1")
+    from models.bisenet.build_bisenet import BiSeNet
+    from rtsds_b200 import RtsdsError
+
+    m = BiSeNet(19, "resnet18").eval()
+    m.rtsds_cuda_graph = False
+    x = torch.zeros(1, 3, 64, 64, requires_grad=True)
+    with pytest.raises(RtsdsError):
+        m(x)
+    with torch.no_grad():
+        assert m(x).shape == (1, 19, 64, 64)
+    out = m(torch.zeros(1, 3, 64, 64))
+    assert out.shape == (1, 19, 64, 64) and not out.requires_grad
+
+
 def test_weights_epoch_and_plan_slots_dry_run(monkeypatch):
     """Host logic without a GPU: (1) a backward pass makes every plan re-pack its operands at the next forward even
     when no tensor version counter moved (torch's fused optimizers); (2) a second train forward of the same shape that
