@@ -62,7 +62,8 @@ int64_t     rtsds_launch_count(void);
  * for run-to-run reproducible parity runs: ATen's CPU path, which the reference's results come from, sums in a fixed
  * order.  When on, the cross-CTA floating-point reductions of the training path — train-mode BatchNorm sum / sum of
  * squares in every conv and stem epilogue, the weight-gradient partials of every wgrad kernel, the BatchNorm-backward
- * sums — are accumulated exactly (64.64 fixed point, integer atomics, one rounding to fp32 at the end) in library-owned
+ * sums, the split global pool, bias gradients, the ARM gate / FFM head gradients and the loss-gradient scatter of the CE
+ * kernels — are accumulated exactly (64.64 fixed point, integer atomics, one rounding to fp32 at the end) in library-owned
  * scratch instead of through fp32 atomics, so results do not depend on CTA arrival order.  Buffers and signatures are
  * unchanged; each affected call costs one memset and one small finishing launch more. */
 void        rtsds_set_deterministic(int on);

@@ -414,7 +414,7 @@ static bool bns_ok(int c, int dtype, int dy_ld, int raw_ld, const void* y, int y
 // out[c] (+)= sum over pixels of x[p][c]   (bias gradients)
 template <typename T>
 __global__ void __launch_bounds__(256)
-channel_sum_kernel(const T* __restrict__ x, int ld, long long n_pix, int c, float* out) {
+channel_sum_kernel(const T* __restrict__ x, int ld, long long n_pix, int c, float* out, unsigned long long* det) {
     __shared__ float sh[8][33];
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
     const int pl = threadIdx.x >> 5;
@@ -428,7 +428,8 @@ channel_sum_kernel(const T* __restrict__ x, int ld, long long n_pix, int c, floa
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
-        atomicAdd(&out[ch], t);
+        if (det) det_add(det + 2 * ch, t);               // deterministic mode (common.cuh)
+        else atomicAdd(&out[ch], t);
     }
 }
 
@@ -572,7 +573,8 @@ __device__ __forceinline__ void dst_range(int s, float rscale, int out_size, int
 template <typename T>
 __global__ void __launch_bounds__(256)
 resize_bwd_nhwc_kernel(const T* __restrict__ d_dst, int dst_ld, int dst_coff, int n, int h, int w, int c, int oh, int ow,
-                       float rh, float rw, const T* __restrict__ src, float* __restrict__ d_src, float* dgate) {
+                       float rh, float rw, const T* __restrict__ src, float* __restrict__ d_src, float* dgate,
+                       unsigned long long* det) {
     extern __shared__ float sh[];     // [c] per-image partial dgate (block works on one image)
     const int cg = c / 8;
     const int img = blockIdx.y;
@@ -638,10 +640,16 @@ resize_bwd_nhwc_kernel(const T* __restrict__ d_dst, int dst_ld, int dst_coff, in
         if (dgate) {
             const F8 s = ld8(src + sp);
 #pragma unroll
+            if (det) {            // deterministic mode: per-thread products straight into the exact accumulators of dgate
+#pragma unroll
+                for (int j = 0; j < 8; ++j) det_add(det + 2 * (static_cast<long long>(img) * c + g8 * 8 + j), acc.v[j] * s.v[j]);
+            } else {
+#pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(&sh[g8 * 8 + j], acc.v[j] * s.v[j]);
+            }
         }
     }
-    if (dgate) {
+    if (dgate && !det) {
         __syncthreads();
         for (int i = threadIdx.x; i < c; i += blockDim.x)
             if (sh[i] != 0.f) atomicAdd(&dgate[static_cast<long long>(img) * c + i], sh[i]);
@@ -755,7 +763,7 @@ constexpr int FB_CHUNK = 128;
 __global__ void __launch_bounds__(FB_CHUNK)
 ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ f, int f_ld,
                           const float* __restrict__ attn, const float* __restrict__ wc, long long hw, int c,
-                          float* da_raw, float* dwc, float* dbc) {
+                          float* da_raw, float* dwc, float* dbc, unsigned long long* det) {
     __shared__ float s_w[FB_MAXC * FB_MAXC];
     __shared__ float s_dz[FB_CHUNK][FB_MAXC + 1], s_g[FB_CHUNK][FB_MAXC + 1];
     __shared__ float s_da[FB_MAXC], s_a1[FB_MAXC];
@@ -801,6 +809,23 @@ ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* 
         }
         __syncwarp();
     }
+    if (det) {
+        // deterministic mode: exact accumulators laid out as [da_raw: n*c | dwc: c*c | dbc: c]; every thread adds its own
+        // (fixed-order) partial sums, nothing goes through the block's shared-memory atomics
+        const long long n_img = gridDim.y;
+#pragma unroll
+        for (int k = 0; k < FB_MAXC; ++k)          // (compile-time indices: a runtime one would push da[] into local memory)
+            if (k < c) det_add(det + 2 * (static_cast<long long>(img) * c + k), da[k]);
+        if (wc && lane < c) {
+            if (dbc) det_add(det + 2 * (n_img * c + static_cast<long long>(c) * c + lane), db);
+            if (dwc) {
+#pragma unroll
+                for (int k = 0; k < FB_MAXC; ++k)
+                    if (k < c) det_add(det + 2 * (n_img * c + lane * c + k), dw_row[k]);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < FB_MAXC; ++k)
         if (k < c) atomicAdd(&s_da[k], da[k]);
@@ -820,7 +845,7 @@ ffm_head_bwd_pass1_kernel(const float* __restrict__ dz, int dz_ld, const float* 
 __global__ void __launch_bounds__(64)
 ffm_head_bwd_pass2_kernel(const float* __restrict__ da_raw, const float* __restrict__ pooled, const float* __restrict__ attn,
                           const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2, int c,
-                          float* dpooled, float* dw1, float* db1, float* dw2, float* db2) {
+                          float* dpooled, float* dw1, float* db1, float* dw2, float* db2, unsigned long long* det) {
     __shared__ float s_h[FB_MAXC], s_dv[FB_MAXC], s_dh[FB_MAXC];
     const int img = blockIdx.x, t = threadIdx.x;
     const float* pp = pooled + static_cast<long long>(img) * c;
@@ -836,16 +861,26 @@ ffm_head_bwd_pass2_kernel(const float* __restrict__ da_raw, const float* __restr
         float acc = 0.f;
         for (int o = 0; o < c; ++o) acc = fmaf(w2[o * c + t], s_dv[o], acc);
         s_dh[t] = s_h[t] > 0.f ? acc : 0.f;                  // grad at conv1 output (through ReLU)
+        if (det) {            // deterministic mode: [db2: c | dw2: c*c | db1: c | dw1: c*c]
+            det_add(det + 2 * t, s_dv[t]);
+            for (int k = 0; k < c; ++k) det_add(det + 2 * (c + t * c + k), s_dv[t] * fmaxf(s_h[k], 0.f));
+        } else {
         atomicAdd(&db2[t], s_dv[t]);
         for (int k = 0; k < c; ++k) atomicAdd(&dw2[t * c + k], s_dv[t] * fmaxf(s_h[k], 0.f));
+        }
     }
     __syncthreads();
     if (t < c) {
         float acc = 0.f;
         for (int o = 0; o < c; ++o) acc = fmaf(w1[o * c + t], s_dh[o], acc);
         dpooled[static_cast<long long>(img) * c + t] = acc;
+        if (det) {
+            det_add(det + 2 * (c + c * c + t), s_dh[t]);
+            for (int k = 0; k < c; ++k) det_add(det + 2 * (2 * c + c * c + t * c + k), s_dh[t] * pp[k]);
+        } else {
         atomicAdd(&db1[t], s_dh[t]);
         for (int k = 0; k < c; ++k) atomicAdd(&dw1[t * c + k], s_dh[t] * pp[k]);
+        }
     }
 }
 
@@ -1137,10 +1172,17 @@ extern "C" int rtsds_channel_sum(const void* x, int ld, int64_t n_pix, int c, in
     if (py > cap) py = cap;
     if (py < 1) py = 1;
     dim3 grid(static_cast<unsigned>(cdiv(c, 32)), static_cast<unsigned>(py));
-    DISPATCH_T(dtype, (channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, n_pix, c, out)),
-               (channel_sum_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, n_pix, c, out)), "channel_sum");
+    unsigned long long* det = nullptr;
+    if (py > 1 && det_mode()) {
+        det = det_scratch(as_stream(s), static_cast<size_t>(c));
+        if (!det) return RTSDS_ECUDA;
+    }
+    DISPATCH_T(dtype, (channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, n_pix, c, out, det)),
+               (channel_sum_kernel<float><<<grid, 256, 0, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, n_pix, c, out, det)), "channel_sum");
     count_launch();
-    return check_launch("channel_sum_kernel");
+    int rc = check_launch("channel_sum_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, out, static_cast<size_t>(c), true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_maxpool3x3s2_bwd(const void* x, const void* dy, int n, int h, int w, int c, int dtype, int ceil_mode,
@@ -1200,12 +1242,19 @@ extern "C" int rtsds_resize_bwd_nhwc(const void* d_dst, int dst_ld, int dst_coff
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), n);
     const size_t sm = sizeof(float) * c;
+    unsigned long long* det = nullptr;
+    if (dgate && det_mode()) {
+        det = det_scratch(st, static_cast<size_t>(n) * c);
+        if (!det) return RTSDS_ECUDA;
+    }
     DISPATCH_T(dtype,
-               (resize_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const __nv_bfloat16*>(src), d_src, dgate)),
-               (resize_bwd_nhwc_kernel<float><<<grid, 256, sm, st>>>(reinterpret_cast<const float*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const float*>(src), d_src, dgate)),
+               (resize_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const __nv_bfloat16*>(src), d_src, dgate, det)),
+               (resize_bwd_nhwc_kernel<float><<<grid, 256, sm, st>>>(reinterpret_cast<const float*>(d_dst), dst_ld, dst_coff, n, h, w, c, oh, ow, rh, rw, reinterpret_cast<const float*>(src), d_src, dgate, det)),
                "resize_bwd_nhwc");
     count_launch();
-    return check_launch("resize_bwd_nhwc_kernel");
+    int rc = check_launch("resize_bwd_nhwc_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, dgate, static_cast<size_t>(n) * c, true, st);
+    return rc;
 }
 
 extern "C" int rtsds_gate_bwd_finish(const float* d_gated, const float* gate, const float* add, float add_scale, int n,
@@ -1251,8 +1300,30 @@ extern "C" int rtsds_ffm_head_bwd(const float* dz, int dz_ld, const float* f, in
     const long long cap = cdiv(2LL * num_sms(), n);
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), n);
-    ffm_head_bwd_pass1_kernel<<<grid, FB_CHUNK, 0, st>>>(dz, dz_ld, f, f_ld, attn, wc, hw, c, da_ws, dwc, dbc);
-    ffm_head_bwd_pass2_kernel<<<n, 64, 0, st>>>(da_ws, pooled, attn, w1, b1, w2, c, dpooled_ws, dw1, db1, dw2, db2);
+    const bool det_on = det_mode();
+    const size_t nc = static_cast<size_t>(n) * c, cc = static_cast<size_t>(c) * c;
+    unsigned long long* det = nullptr;
+    if (det_on) {
+        det = det_scratch(st, nc + cc + c);
+        if (!det) return RTSDS_ECUDA;
+    }
+    ffm_head_bwd_pass1_kernel<<<grid, FB_CHUNK, 0, st>>>(dz, dz_ld, f, f_ld, attn, wc, hw, c, da_ws, dwc, dbc, det);
+    if (det) {
+        int rc = det_finish(det, da_ws, nc, true, st);
+        if (rc == RTSDS_OK && wc && dwc) rc = det_finish(det + 2 * nc, dwc, cc, true, st);
+        if (rc == RTSDS_OK && wc && dbc) rc = det_finish(det + 2 * (nc + cc), dbc, static_cast<size_t>(c), true, st);
+        if (rc != RTSDS_OK) return rc;
+        det = det_scratch(st, 2 * c + 2 * cc);          // pass 2: [db2 | dw2 | db1 | dw1]
+        if (!det) return RTSDS_ECUDA;
+    }
+    ffm_head_bwd_pass2_kernel<<<n, 64, 0, st>>>(da_ws, pooled, attn, w1, b1, w2, c, dpooled_ws, dw1, db1, dw2, db2, det);
+    if (det) {
+        int rc = det_finish(det, db2, static_cast<size_t>(c), true, st);
+        if (rc == RTSDS_OK) rc = det_finish(det + 2 * c, dw2, cc, true, st);
+        if (rc == RTSDS_OK) rc = det_finish(det + 2 * (c + cc), db1, static_cast<size_t>(c), true, st);
+        if (rc == RTSDS_OK) rc = det_finish(det + 2 * (2 * c + cc), dw1, cc, true, st);
+        if (rc != RTSDS_OK) return rc;
+    }
     long long bx3 = cdiv(hw, 128);
     const long long cap3 = cdiv(8LL * num_sms(), n);
     if (bx3 > cap3) bx3 = cap3;

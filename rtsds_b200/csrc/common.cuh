@@ -81,6 +81,7 @@ static __device__ __noinline__ void det_add2(unsigned long long* a, float va, un
     det_add(a, va);
     det_add(b, vb);
 }
+static __device__ __noinline__ void det_add1(unsigned long long* a, float va) { det_add(a, va); }
 __device__ __forceinline__ double det_value(const unsigned long long* acc) {
     return static_cast<double>(static_cast<long long>(acc[1])) + static_cast<double>(acc[0]) * 5.421010862427522e-20;   // 2^-64
 }

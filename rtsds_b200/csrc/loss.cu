@@ -102,7 +102,8 @@ constexpr int BW_ROWS = 8, BW_COLS = 128, BW_GP = 21;      // G pitch: odd, so p
 __global__ void __launch_bounds__(LS_THREADS)
 resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld, int oh, int ow, float rh, float rw,
                      const long long* __restrict__ target, long long ignore_index,
-                     const float* __restrict__ grad_scale, float* __restrict__ dz, int max_rows, int max_cols) {
+                     const float* __restrict__ grad_scale, float* __restrict__ dz, int max_rows, int max_cols,
+                     unsigned long long* det) {
     extern __shared__ float sm[];
     const int img = blockIdx.z;
     const int oy0 = blockIdx.y * BW_ROWS, ox0 = blockIdx.x * BW_COLS;
@@ -198,8 +199,11 @@ resize_ce_bwd_kernel(const float* __restrict__ z, int h, int w, int c, int z_ld,
             }
             acc = fmaf(wy, rowacc, acc);
         }
-        if (acc != 0.f)
-            atomicAdd(dz + ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch, acc);
+        if (acc != 0.f) {
+            const long long o = ((static_cast<long long>(img) * h + ys + row) * w + xs + col) * z_ld + ch;
+            if (det) det_add1(det + 2 * o, acc);          // deterministic mode: exact accumulators with dz's layout
+            else atomicAdd(dz + o, acc);
+        }
     }
 }
 
@@ -226,7 +230,7 @@ template <int CT>
 __global__ void __launch_bounds__(FU_COLS, 4)
 resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c_rt, int z_ld, int oh, int ow, float rh, float rw,
                        const long long* __restrict__ target, long long ignore_index, double* acc,
-                       long long* __restrict__ pred_out, float* __restrict__ dz) {
+                       long long* __restrict__ pred_out, float* __restrict__ dz, unsigned long long* det) {
     __shared__ float s_z[FU_KR * FU_FC * FU_CMAX];
     __shared__ float s_a[FU_COLS * FU_AP];
     __shared__ float s_xl[2 * FU_COLS];
@@ -359,8 +363,11 @@ resize_ce_fused_kernel(const float* __restrict__ z, int h, int w, int c_rt, int 
             float sum = 0.f;
             for (int tx = s_run[4 * col + 0]; tx <= s_run[4 * col + 1]; ++tx) sum = fmaf(s_xl[2 * tx], s_a[tx * FU_AP + off], sum);
             for (int tx = s_run[4 * col + 2]; tx <= s_run[4 * col + 3]; ++tx) sum = fmaf(s_xl[2 * tx + 1], s_a[tx * FU_AP + off], sum);
-            if (sum != 0.f)
-                atomicAdd(dz + ((static_cast<long long>(img) * h + ys + k) * w + xs + col) * z_ld + ch, sum);
+            if (sum != 0.f) {
+                const long long o = ((static_cast<long long>(img) * h + ys + k) * w + xs + col) * z_ld + ch;
+                if (det) det_add1(det + 2 * o, sum);      // deterministic mode: exact accumulators with dz's layout
+                else atomicAdd(dz + o, sum);
+            }
         }
     }
     if (acc) {
@@ -480,11 +487,19 @@ extern "C" int rtsds_resize_ce_bwd(const float* z, int n, int h, int w, int c, i
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(resize_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); done = true; }
     dim3 grid(static_cast<unsigned>(cdiv(ow, BW_COLS)), static_cast<unsigned>(cdiv(oh, BW_ROWS)), n);
+    const size_t n_dz = static_cast<size_t>(n) * h * w * z_ld;
+    unsigned long long* det = nullptr;
+    if (det_mode()) {
+        det = det_scratch(as_stream(s), n_dz);
+        if (!det) return RTSDS_ECUDA;
+    }
     resize_ce_bwd_kernel<<<grid, LS_THREADS, smem, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
                                                                    reinterpret_cast<const long long*>(target), ignore_index,
-                                                                   grad_scale, dz, max_rows, max_cols);
+                                                                   grad_scale, dz, max_rows, max_cols, det);
     count_launch();
-    return check_launch("resize_ce_bwd_kernel");
+    int rc = check_launch("resize_ce_bwd_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, dz, n_dz, true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_ce_argmax_nchw_fwd(const float* logits, int n, int c, int64_t hw, const int64_t* target,
@@ -517,16 +532,24 @@ extern "C" int rtsds_resize_ce_fused(const float* z, int n, int h, int w, int c,
     }
     const float rh = resize_scale(h, oh), rw = resize_scale(w, ow);
     dim3 grid(static_cast<unsigned>(cdiv(ow, FU_COLS)), static_cast<unsigned>(cdiv(oh, FU_ROWS)), n);
+    const size_t n_dz = static_cast<size_t>(n) * h * w * z_ld;
+    unsigned long long* det = nullptr;
+    if (dz_unnorm && det_mode()) {          // (the loss / count sums in `acc` are doubles of per-block partials: reported values only)
+        det = det_scratch(as_stream(s), n_dz);
+        if (!det) return RTSDS_ECUDA;
+    }
     if (c == 19)
         resize_ce_fused_kernel<19><<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
                                                                       reinterpret_cast<const long long*>(target), ignore_index, acc,
-                                                                      reinterpret_cast<long long*>(pred_out), dz_unnorm);
+                                                                      reinterpret_cast<long long*>(pred_out), dz_unnorm, det);
     else
         resize_ce_fused_kernel<0><<<grid, FU_COLS, 0, as_stream(s)>>>(z, h, w, c, z_ld, oh, ow, rh, rw,
                                                                      reinterpret_cast<const long long*>(target), ignore_index, acc,
-                                                                     reinterpret_cast<long long*>(pred_out), dz_unnorm);
+                                                                     reinterpret_cast<long long*>(pred_out), dz_unnorm, det);
     count_launch();
-    return check_launch("resize_ce_fused_kernel");
+    int rc = check_launch("resize_ce_fused_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, dz_unnorm, n_dz, true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_scale_by_device_scalar(float* x, int64_t n, const float* scale, rtsds_stream_t s) {
