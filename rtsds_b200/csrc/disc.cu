@@ -166,7 +166,7 @@ __device__ __forceinline__ void stg8(float* p, const G8& r) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const T* dy, int dy_ld, const T* __restrict__ y, int y_ld, long long n_pix, int c,
-               float slope, T* d_raw, int d_raw_ld, float* dbias) {
+               float slope, T* d_raw, int d_raw_ld, float* dbias, unsigned long long* det) {
     extern __shared__ float sh[];             // [c]
     for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
@@ -188,12 +188,15 @@ act_bwd_kernel(const T* dy, int dy_ld, const T* __restrict__ y, int y_ld, long l
             }
             stg8(d_raw + p * d_raw_ld + g8 * 8, o);
         }
-        if (dbias) {
+        if (dbias && det) {          // deterministic mode (common.cuh): this thread's sums into the exact accumulators
+#pragma unroll
+            for (int j = 0; j < 8; ++j) det_add(det + 2 * (g8 * 8 + j), s1[j]);
+        } else if (dbias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(&sh[g8 * 8 + j], s1[j]);
         }
     }
-    if (dbias) {
+    if (dbias && !det) {
         __syncthreads();
         for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
     }
@@ -203,7 +206,8 @@ act_bwd_kernel(const T* dy, int dy_ld, const T* __restrict__ y, int y_ld, long l
 // tapsum[n][r*4+s][c] += sum of x[n,hh,ww,c] over the pixels tap (r,s) visits; one block per image row.
 template <typename T>
 __global__ void __launch_bounds__(256)
-disc_cls_tapsum_kernel(const T* __restrict__ x, int ld, int h, int w, int c, int oh, int ow, float* __restrict__ tapsum) {
+disc_cls_tapsum_kernel(const T* __restrict__ x, int ld, int h, int w, int c, int oh, int ow, float* __restrict__ tapsum,
+                       unsigned long long* det) {
     extern __shared__ float sh[];             // [4][c]
     const int hh = blockIdx.x, img = blockIdx.y;
     for (int i = threadIdx.x; i < 4 * c; i += blockDim.x) sh[i] = 0.f;
@@ -229,6 +233,24 @@ disc_cls_tapsum_kernel(const T* __restrict__ x, int ld, int h, int w, int c, int
                 for (int j = 0; j < 8; ++j) { if (va) a1[j] += v.v[j]; if (vb) a3[j] += v.v[j]; }
             }
         }
+        if (det) {
+            // deterministic mode: this thread's four column-tap sums straight into the exact accumulators of the (up to two)
+            // row taps this input row feeds; nothing goes through the block's shared-memory atomics
+            const int r0d = (hh + 1) & 1;
+            const int oad = (hh + 1 - r0d) >> 1;
+            const bool vad = oad < oh, vbd = oad >= 1 && oad - 1 < oh;
+            unsigned long long* dd = det + 2 * (static_cast<long long>(img) * 16 * c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = g8 * 8 + j;
+                const float av[4] = {a0[j], a1[j], a2[j], a3[j]};
+#pragma unroll
+                for (int sx = 0; sx < 4; ++sx) {
+                    if (vad) det_add(dd + 2 * ((r0d * 4 + sx) * c + ch), av[sx]);
+                    if (vbd) det_add(dd + 2 * (((r0d + 2) * 4 + sx) * c + ch), av[sx]);
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             atomicAdd(&sh[0 * c + g8 * 8 + j], a0[j]);
@@ -236,7 +258,9 @@ disc_cls_tapsum_kernel(const T* __restrict__ x, int ld, int h, int w, int c, int
             atomicAdd(&sh[2 * c + g8 * 8 + j], a2[j]);
             atomicAdd(&sh[3 * c + g8 * 8 + j], a3[j]);
         }
+        }
     }
+    if (det) return;
     __syncthreads();
     const int r0 = (hh + 1) & 1;
     const int oa = (hh + 1 - r0) >> 1;
@@ -295,7 +319,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 disc_cls_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ wgt, const T* __restrict__ x, int ld, int h,
                       int w, int c, int oh, int ow, float inv_p, float g_scale, int masked, float slope,
-                      T* __restrict__ d_raw, int d_ld, float* dbias_prev) {
+                      T* __restrict__ d_raw, int d_ld, float* dbias_prev, unsigned long long* det) {
     extern __shared__ float sh[];             // [4][c] row-combined weights, [c] bias sums
     float* s_w = sh;
     float* s_b = sh + 4 * c;
@@ -342,12 +366,15 @@ disc_cls_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ wgt
             for (int j = 0; j < 8; ++j) bs[j] += o.v[j];
             stg8(d_raw + (rowoff + ww) * d_ld + g8 * 8, o);
         }
-        if (dbias_prev) {
+        if (dbias_prev && det) {     // deterministic mode (common.cuh)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) det_add(det + 2 * (g8 * 8 + j), bs[j]);
+        } else if (dbias_prev) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(&s_b[g8 * 8 + j], bs[j]);
         }
     }
-    if (dbias_prev) {
+    if (dbias_prev && !det) {
         __syncthreads();
         for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dbias_prev[i], s_b[i]);
     }
@@ -444,17 +471,24 @@ extern "C" int rtsds_act_bwd(const void* dy, int dy_ld, const void* y, int y_ld,
     const long long cap = 8LL * num_sms();
     const int grid = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
     const size_t sm = sizeof(float) * c;
+    unsigned long long* det = nullptr;
+    if (dbias && det_mode()) {
+        det = det_scratch(as_stream(s), static_cast<size_t>(c));
+        if (!det) return RTSDS_ECUDA;
+    }
     if (dtype == RTSDS_BF16)
         act_bwd_kernel<__nv_bfloat16><<<grid, threads, sm, as_stream(s)>>>(
             reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld, n_pix, c, slope,
-            reinterpret_cast<__nv_bfloat16*>(d_raw), d_raw_ld, dbias);
+            reinterpret_cast<__nv_bfloat16*>(d_raw), d_raw_ld, dbias, det);
     else if (dtype == RTSDS_F32)
         act_bwd_kernel<float><<<grid, threads, sm, as_stream(s)>>>(reinterpret_cast<const float*>(dy), dy_ld,
                                                                   reinterpret_cast<const float*>(y), y_ld, n_pix, c, slope,
-                                                                  reinterpret_cast<float*>(d_raw), d_raw_ld, dbias);
+                                                                  reinterpret_cast<float*>(d_raw), d_raw_ld, dbias, det);
     else { set_error("act_bwd: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
-    return check_launch("act_bwd_kernel");
+    int rc = check_launch("act_bwd_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, dbias, static_cast<size_t>(c), true, as_stream(s));
+    return rc;
 }
 
 extern "C" int rtsds_disc_cls_fwd(const void* x, int ld, int dtype, int n, int h, int w, int c, const float* w_oihw,
@@ -467,13 +501,20 @@ extern "C" int rtsds_disc_cls_fwd(const void* x, int ld, int dtype, int n, int h
     const int threads = cls_threads(c);
     dim3 grid(h, n);
     const size_t sm = sizeof(float) * 4 * c;
+    unsigned long long* det = nullptr;
+    const size_t n_ts = static_cast<size_t>(n) * 16 * c;
+    if (det_mode()) {
+        det = det_scratch(as_stream(s), n_ts);
+        if (!det) return RTSDS_ECUDA;
+    }
     if (dtype == RTSDS_BF16)
-        disc_cls_tapsum_kernel<__nv_bfloat16><<<grid, threads, sm, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, h, w, c, oh, ow, tapsum);
+        disc_cls_tapsum_kernel<__nv_bfloat16><<<grid, threads, sm, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, h, w, c, oh, ow, tapsum, det);
     else if (dtype == RTSDS_F32)
-        disc_cls_tapsum_kernel<float><<<grid, threads, sm, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, h, w, c, oh, ow, tapsum);
+        disc_cls_tapsum_kernel<float><<<grid, threads, sm, as_stream(s)>>>(reinterpret_cast<const float*>(x), ld, h, w, c, oh, ow, tapsum, det);
     else { set_error("disc_cls_fwd: bad dtype"); return RTSDS_EINVAL; }
     count_launch();
     int rc = check_launch("disc_cls_tapsum_kernel");
+    if (rc == RTSDS_OK && det) rc = det_finish(det, tapsum, n_ts, true, as_stream(s));
     if (rc != RTSDS_OK) return rc;
     disc_cls_finish_kernel<<<n, 256, 0, as_stream(s)>>>(tapsum, w_oihw, bias, c, 1.0f / (static_cast<float>(oh) * ow), out);
     count_launch();
@@ -498,17 +539,24 @@ extern "C" int rtsds_disc_cls_bwd(const float* g, float g_scale, const float* ta
         const int threads = cls_threads(c);
         dim3 grid(h, n);
         const size_t sm = sizeof(float) * 5 * c;
+        unsigned long long* det = nullptr;
+        if (dbias_prev && det_mode()) {
+            det = det_scratch(as_stream(s), static_cast<size_t>(c));
+            if (!det) return RTSDS_ECUDA;
+        }
         if (dtype == RTSDS_BF16)
             disc_cls_dgrad_kernel<__nv_bfloat16><<<grid, threads, sm, as_stream(s)>>>(
                 g, w_oihw, reinterpret_cast<const __nv_bfloat16*>(x), ld, h, w, c, oh, ow, inv_p, g_scale, masked, slope,
-                reinterpret_cast<__nv_bfloat16*>(d_raw), d_ld, dbias_prev);
+                reinterpret_cast<__nv_bfloat16*>(d_raw), d_ld, dbias_prev, det);
         else if (dtype == RTSDS_F32)
             disc_cls_dgrad_kernel<float><<<grid, threads, sm, as_stream(s)>>>(g, w_oihw, reinterpret_cast<const float*>(x), ld, h, w, c,
                                                                             oh, ow, inv_p, g_scale, masked, slope,
-                                                                            reinterpret_cast<float*>(d_raw), d_ld, dbias_prev);
+                                                                            reinterpret_cast<float*>(d_raw), d_ld, dbias_prev, det);
         else { set_error("disc_cls_bwd: bad dtype"); return RTSDS_EINVAL; }
         count_launch();
-        return check_launch("disc_cls_dgrad_kernel");
+        int rc = check_launch("disc_cls_dgrad_kernel");
+        if (rc == RTSDS_OK && det) rc = det_finish(det, dbias_prev, static_cast<size_t>(c), true, as_stream(s));
+        return rc;
     }
     return RTSDS_OK;
 }

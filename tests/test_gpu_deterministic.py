@@ -234,3 +234,40 @@ def test_bisenet_train_step_is_bit_reproducible(cuda, det, fused):
            differing=", ".join(f"{k}={diffs[k]:.2e}" for k in differing[:8]))
     # every reduction of the step (stock criterion path) is covered by the mode: ALL 90 gradient tensors are bit-identical
     assert not differing, differing[:8]
+
+
+@pytest.mark.parametrize("tiny", [True, False], ids=["tiny_d", "full_d"])
+def test_adversarial_iteration_is_bit_reproducible(cuda, det, tiny):
+    """One iteration of the reference's adversarial loop (train.py:177-270; bf16, fused fast paths): generator + discriminator,
+    two generator backward passes, two discriminator passes.  With SGD(lr, no momentum) the updated parameters are a direct
+    read-out of the gradients: two runs from the same state give bit-identical generator AND discriminator parameters."""
+    from models.bisenet.build_bisenet import BiSeNet
+    from models.domain_shift.adversarial.model import DomainDiscriminator, TinyDomainDiscriminator
+    from oracle import weights
+    from rtsds_b200.train_steps import adversarial_step
+
+    g = torch.Generator().manual_seed(99)
+    src = torch.randn(2, 3, 192, 320, generator=g).cuda()
+    lbl = torch.randint(0, 20, (2, 192, 320), generator=g).cuda()
+    tgt = torch.randn(2, 3, 128, 256, generator=g).cuda()
+
+    def run():
+        gen = BiSeNet(19, "resnet18")
+        gen.load_state_dict(weights.clone_state(weights.bisenet_r18_state(7)))
+        dis = (TinyDomainDiscriminator if tiny else DomainDiscriminator)(19)
+        dis.load_state_dict(weights.discriminator_state(7, tiny=tiny))
+        gen, dis = gen.cuda().train(), dis.cuda().train()
+        gopt = torch.optim.SGD(gen.parameters(), lr=0.5)
+        dopt = torch.optim.SGD(dis.parameters(), lr=0.5)
+        out = adversarial_step(gen, dis, gopt, dopt, src, lbl, tgt, torch.nn.CrossEntropyLoss(ignore_index=19),
+                               torch.nn.BCEWithLogitsLoss(), 0.1, 4, fused=True)
+        torch.cuda.synchronize()
+        return ({k: p.detach().clone() for k, p in gen.named_parameters()}, {k: p.detach().clone() for k, p in dis.named_parameters()},
+                {k: float(v) for k, v in out.items()})
+
+    g1, d1, o1 = run()
+    g2, d2, o2 = run()
+    bad = [k for k in g1 if not torch.equal(g1[k], g2[k])] + ["D." + k for k in d1 if not torch.equal(d1[k], d2[k])]
+    record(f"deterministic:adversarial_iteration:{'tiny' if tiny else 'full'}_d", parameters=len(g1) + len(d1),
+           parameters_differing=len(bad), losses=", ".join(f"{k}={v:.6g}" for k, v in o1.items()))
+    assert not bad, bad[:8]
