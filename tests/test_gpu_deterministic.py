@@ -271,3 +271,34 @@ def test_adversarial_iteration_is_bit_reproducible(cuda, det, tiny):
     record(f"deterministic:adversarial_iteration:{'tiny' if tiny else 'full'}_d", parameters=len(g1) + len(d1),
            parameters_differing=len(bad), losses=", ".join(f"{k}={v:.6g}" for k, v in o1.items()))
     assert not bad, bad[:8]
+
+
+def test_deeplab_train_step_is_bit_reproducible(cuda, det):
+    """DeepLabV2-ResNet101 (bf16, fused resize + CE), 2x3x136x200: two runs from the same state give bit-identical loss-side
+    argmax maps, BatchNorm running statistics and gradients for every trainable parameter."""
+    from models.deeplabv2.deeplabv2 import get_deeplab_v2
+    from oracle import weights
+    from rtsds_b200.deeplab_engine import deeplab_fused_ce
+
+    g = torch.Generator().manual_seed(2004)
+    x = torch.randn(2, 3, 136, 200, generator=g).cuda()
+    y = torch.randint(0, 20, (2, 136, 200), generator=g).cuda()
+
+    def run():
+        m = get_deeplab_v2(19, pretrain=False)
+        m.load_state_dict(weights.clone_state(weights.deeplab_state(4)))
+        m.rtsds_precision = "bf16"
+        m = m.cuda().train()
+        loss, pred, _ = deeplab_fused_ce(m, x, y, 19)
+        loss.backward()
+        torch.cuda.synchronize()
+        bufs = {k: v.clone() for k, v in m.state_dict().items() if "running" in k}
+        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        return pred.clone(), bufs, grads
+
+    p1, b1, g1 = run()
+    p2, b2, g2 = run()
+    assert torch.equal(p1, p2)
+    bad = [k for k in b1 if not torch.equal(b1[k], b2[k])] + [k for k in g1 if not torch.equal(g1[k], g2[k])]
+    record("deterministic:deeplab_train_2x3x136x200", grad_tensors=len(g1), tensors_differing=len(bad))
+    assert len(g1) > 100 and not bad, bad[:8]
