@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTSDS_ABI_VERSION 2
+#define RTSDS_ABI_VERSION 3
 
 /* error codes */
 #define RTSDS_OK        0

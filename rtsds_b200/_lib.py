@@ -14,7 +14,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "librtsds_b200.so"
 
 F32, BF16, F16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
 

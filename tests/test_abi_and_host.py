@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(handle, s), f"{s} declared in include/rtsds_b200.h but not exported"
     assert syms == set(_lib.SIGNATURES), syms ^ set(_lib.SIGNATURES)
     handle.rtsds_abi_version.restype = ctypes.c_int
-    assert handle.rtsds_abi_version() == 2
+    assert handle.rtsds_abi_version() == _lib.ABI_VERSION == 3
     handle.rtsds_conv_cout_pad.restype = ctypes.c_int
     assert [handle.rtsds_conv_cout_pad(c) for c in (1, 19, 32, 33, 64, 65, 128, 129, 512)] == [32, 32, 32, 64, 64, 128, 128, 256, 512]
 
